@@ -1,0 +1,588 @@
+"""numpy restatement of the reference's path simulation + LSM backward induction.
+
+TEST INFRASTRUCTURE ONLY (checker, CPU baseline).  Never imported by the product.
+
+Parity status
+-------------
+The reference (Levicoz/Options-model) ships NO golden vectors or known-answer tests
+for this path.  This restatement is therefore pinned against
+outputs of the reference's own functions, generated in the build container by
+``oracle/gen_golden.py`` (which imports the real reference from /root/reference with
+its I/O-only dependencies stubbed) and committed under ``tests/golden/``:
+
+* path schemes, features, Welford, RNG seed tree, European streaming, calibrator
+  scheme: pinned bit-for-bit / to 1e-15 against the real reference functions;
+* the LSM loop skeleton (discount order, sticky mask, strict ``>``, N-1 discounts,
+  global normalisation): pinned against the real ``price_american_enhanced_lsm`` run
+  with its network class swapped for a deterministic stand-in;
+* the polynomial regressor itself does not exist in the reference (``lsm_poly_degree``
+  is a dead parameter, options_model_2.py:176-180): its definition is SURVEY.md
+  section 8(c) and it is pinned only by this file's own goldens ("restatement").
+
+All ``file:line`` citations are relative to /root/reference.
+om3 = options_model_3/options_model_3.py, om3gpu = options_model_3/option_model_3_gpu.py,
+om2 = options_model_2.py, hc = options_model_3/heston_calibration.py.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional
+
+import numpy as np
+from numpy.random import default_rng
+
+# --------------------------------------------------------------------------------------
+# RNG seed tree  (om3:69-79, identical in om3gpu:101-111)
+# --------------------------------------------------------------------------------------
+
+
+class RNGManager:
+    """om3:69-79.  master = default_rng(seed); child seed = master.integers(0, 2**31-1)."""
+
+    def __init__(self, master_seed: int = 42):
+        self.master_rng = default_rng(master_seed)
+        self.master_seed = master_seed
+
+    def get_child_rng(self) -> np.random.Generator:
+        return default_rng(self.master_rng.integers(0, 2**31 - 1))
+
+    def get_child_seed(self) -> int:
+        return self.master_rng.integers(0, 2**31 - 1)
+
+
+# --------------------------------------------------------------------------------------
+# Welford streaming estimator  (om3:33-63)
+# --------------------------------------------------------------------------------------
+
+
+def welford_batch_update(mean, m2, n, batch):
+    """Chan merge of (mean, M2, n) with one batch.  om3:33-49."""
+    batch = np.asarray(batch, dtype=np.float64)
+    b_n = batch.size
+    if b_n == 0:
+        return mean, m2, n
+    batch_mean = batch.mean()
+    batch_m2 = ((batch - batch_mean) ** 2).sum()
+    delta = batch_mean - mean
+    new_n = n + b_n
+    if new_n == 0:
+        return mean, m2, n
+    mean_new = mean + delta * (b_n / new_n)
+    m2_new = m2 + batch_m2 + delta**2 * n * b_n / new_n
+    return mean_new, m2_new, new_n
+
+
+def monte_carlo_price_streaming(simulator_func, total_paths, chunk_size, *a, **kw):
+    """om3:51-63."""
+    n_done, mean, m2 = 0, 0.0, 0.0
+    while n_done < total_paths:
+        batch = min(chunk_size, total_paths - n_done)
+        payoffs = simulator_func(batch, *a, **kw)
+        mean, m2, n_done = welford_batch_update(mean, m2, n_done, payoffs)
+    variance = m2 / (n_done - 1) if n_done > 1 else 0.0
+    stderr = np.sqrt(variance / n_done) if n_done > 0 else 0.0
+    return mean, stderr, n_done
+
+
+# --------------------------------------------------------------------------------------
+# Payoff and features
+# --------------------------------------------------------------------------------------
+
+
+def payoff(S, K, option_type):
+    """om3:376-380."""
+    if option_type == "call":
+        return np.maximum(S - K, 0)
+    return np.maximum(K - S, 0)
+
+
+def features_ref7(S, K, r, T, t_current):
+    """[1, x, x^2, x^3, max(x-1,0), sqrt(tau), x*sqrt(tau)].  om3:105-121."""
+    x = S / K
+    tau = T - t_current
+    tau_sqrt = float(np.sqrt(max(tau, 1e-6)))
+    tau_col = np.full_like(x, tau_sqrt, dtype=np.float64)
+    return np.column_stack(
+        [
+            np.ones_like(x, dtype=np.float64),
+            x.astype(np.float64),
+            (x**2).astype(np.float64),
+            (x**3).astype(np.float64),
+            np.maximum(x - 1, 0).astype(np.float64),
+            tau_col,
+            (x * tau_col).astype(np.float64),
+        ]
+    )
+
+
+# --------------------------------------------------------------------------------------
+# Path simulation (CPU fp64 schemes)
+# --------------------------------------------------------------------------------------
+
+
+def draw_gbm_normals(rng, N, M):
+    """One call standard_normal((N, M//2)).  om3:475."""
+    return rng.standard_normal((N, M // 2))
+
+
+def gbm_paths_antithetic(S0, r, sigma, T, M, N, Z_half):
+    """Antithetic multiplicative log-Euler GBM, step-major S[(N+1), M].  om3:473-480.
+
+    Columns [0, M/2) use +Z, columns [M/2, M) use -Z (om3:476).
+    """
+    dt = T / N
+    drift = (r - 0.5 * sigma**2) * dt
+    diffusion = sigma * np.sqrt(dt)
+    Z = np.concatenate([Z_half, -Z_half], axis=1)
+    S = np.zeros((N + 1, M), dtype=np.float64)
+    S[0] = S0
+    for t in range(1, N + 1):
+        S[t] = S[t - 1] * np.exp(drift + diffusion * Z[t - 1])
+    return S
+
+
+def draw_heston_normals(rng, N, M):
+    """Per step: z1_half then z2_half, each standard_normal(M//2).  om3:222-224."""
+    Z1 = np.empty((N, M // 2))
+    Z2 = np.empty((N, M // 2))
+    for t in range(N):
+        Z1[t] = rng.standard_normal(M // 2)
+        Z2[t] = rng.standard_normal(M // 2)
+    return Z1, Z2
+
+
+def heston_paths_antithetic(S0, r, T, v0, kappa, theta, xi, rho, M, N, Z1_half, Z2_half, return_v=False):
+    """Absorption-Euler Heston, antithetic, step-major.  om3:211-233 (even M only).
+
+    v_prev = max(v,0); v' = max(v_prev + kappa(theta-v_prev)dt + xi sqrt(v_prev dt) w2, 0);
+    S' = S exp((r - v_prev/2)dt + sqrt(v_prev dt) w1);  w1=z1, w2=rho z1 + sqrt(1-rho^2) z2.
+    """
+    dt = T / N
+    S = np.zeros((N + 1, M), dtype=np.float64)
+    v = np.zeros((N + 1, M), dtype=np.float64)
+    S[0] = S0
+    v[0] = v0
+    for t in range(1, N + 1):
+        z1 = np.concatenate([Z1_half[t - 1], -Z1_half[t - 1]])
+        z2 = np.concatenate([Z2_half[t - 1], -Z2_half[t - 1]])
+        w1 = z1
+        w2 = rho * z1 + np.sqrt(1 - rho**2) * z2
+        v_prev = np.maximum(v[t - 1], 0)
+        v[t] = v_prev + kappa * (theta - v_prev) * dt + xi * np.sqrt(v_prev * dt) * w2
+        v[t] = np.maximum(v[t], 0)
+        S[t] = S[t - 1] * np.exp((r - 0.5 * v_prev) * dt + np.sqrt(v_prev * dt) * w1)
+    return (S, v) if return_v else S
+
+
+def heston_paths_full_truncation(S0, r, T, v0, kappa, theta, xi, rho, M, N, Z1_half, Z2_half):
+    """Lord-Koekkoek-van Dijk full truncation (NOT in the reference; north-star scheme).
+
+    The state v may go negative; only v+ = max(v,0) enters drift and diffusion.
+    """
+    dt = T / N
+    S = np.zeros((N + 1, M), dtype=np.float64)
+    S[0] = S0
+    v = np.full(M, v0, dtype=np.float64)
+    for t in range(1, N + 1):
+        z1 = np.concatenate([Z1_half[t - 1], -Z1_half[t - 1]])
+        z2 = np.concatenate([Z2_half[t - 1], -Z2_half[t - 1]])
+        w2 = rho * z1 + np.sqrt(1 - rho**2) * z2
+        vp = np.maximum(v, 0)
+        sq = np.sqrt(vp * dt)
+        S[t] = S[t - 1] * np.exp((r - 0.5 * vp) * dt + sq * z1)
+        v = v + kappa * (theta - vp) * dt + xi * sq * w2
+    return S
+
+
+# --------------------------------------------------------------------------------------
+# Path simulation (torch fp32 variants, restated in numpy float32)
+# --------------------------------------------------------------------------------------
+
+
+def bs_paths_fp32(S0, r, T, sigma, M, N, Z_half32):
+    """om3gpu:117-138 in float32 arithmetic (even M)."""
+    f = np.float32
+    dt = T / N
+    drift = f((r - 0.5 * sigma**2) * dt)
+    diffusion = f(sigma) * np.sqrt(f(dt))  # sigma * torch.sqrt(torch.tensor(dt))
+    Z = np.concatenate([Z_half32, -Z_half32], axis=1).astype(f)
+    S = np.full((N + 1, M), f(S0), dtype=f)
+    for t in range(1, N + 1):
+        S[t] = S[t - 1] * np.exp(drift + diffusion * Z[t - 1])
+    return S
+
+
+def bs_paths_logspace_fp32(S0, r, T, sigma, M, N, Z32):
+    """om3gpu:150-185 ("bandwidth optimized"): no antithetic, cumulative sum in log space."""
+    f = np.float32
+    dt = T / max(1, N)
+    drift = f((r - 0.5 * sigma * sigma) * dt)
+    diffusion = f(sigma * math.sqrt(dt))
+    logS = np.empty((N + 1, M), dtype=f)
+    logS[0] = f(math.log(max(S0, 1e-12)))
+    inc = drift + diffusion * Z32.astype(f)
+    for t in range(1, N + 1):
+        logS[t] = logS[t - 1] + inc[t - 1]
+    return np.exp(logS)
+
+
+def heston_paths_fp32(S0, r, T, v0, kappa, theta, xi, rho, M, N, Z1_half32, Z2_half32):
+    """om3gpu:187-225 in float32 arithmetic (even M)."""
+    f = np.float32
+    dt = f(T / N)
+    kappa, theta, xi, rho = f(kappa), f(theta), f(xi), f(rho)
+    sqrt_1_rho2 = np.sqrt(f(1) - rho * rho)
+    S = np.full((N + 1, M), f(S0), dtype=f)
+    v = np.full((N + 1, M), f(v0), dtype=f)
+    rr = f(r)
+    for t in range(1, N + 1):
+        z1 = np.concatenate([Z1_half32[t - 1], -Z1_half32[t - 1]]).astype(f)
+        z2 = np.concatenate([Z2_half32[t - 1], -Z2_half32[t - 1]]).astype(f)
+        w2 = rho * z1 + sqrt_1_rho2 * z2
+        v_prev = np.maximum(v[t - 1], f(0))
+        sq = np.sqrt(v_prev * dt)
+        v[t] = np.maximum(v_prev + kappa * (theta - v_prev) * dt + xi * sq * w2, f(0))
+        S[t] = S[t - 1] * np.exp((rr - f(0.5) * v_prev) * dt + sq * z1)
+    return S
+
+
+# --------------------------------------------------------------------------------------
+# Calibrator scheme (hc.HestonPricer)
+# --------------------------------------------------------------------------------------
+
+
+def hc_draw_normals(rng, n_paths, n_steps, antithetic=True):
+    """Z1 then Z2_indep, each one standard_normal((n_sim, n_steps)) call.  hc:224-238."""
+    n_sim = n_paths // 2 if antithetic else n_paths
+    Z1 = rng.standard_normal((n_sim, n_steps))
+    Z2i = rng.standard_normal((n_sim, n_steps))
+    return Z1, Z2i
+
+
+def hc_simulate_paths(kappa, theta, sigma, rho, v0, S0, T, r, n_paths, n_steps, Z1, Z2i, antithetic=True):
+    """Arithmetic-Euler S, floored-variance Heston; path-major (n_paths, n_steps+1).  hc:204-257."""
+    dt = T / n_steps
+    S = np.zeros((n_paths, n_steps + 1))
+    V = np.zeros((n_paths, n_steps + 1))
+    S[:, 0] = S0
+    V[:, 0] = v0
+    Z2 = rho * Z1 + np.sqrt(1 - rho**2) * Z2i
+    if antithetic:
+        Z1 = np.vstack([Z1, -Z1])
+        Z2 = np.vstack([Z2, -Z2])
+    sqrt_dt = np.sqrt(dt)
+    for t in range(n_steps):
+        V_pos = np.maximum(V[:, t], 1e-8)
+        sqrt_V = np.sqrt(V_pos)
+        dV = kappa * (theta - V_pos) * dt + sigma * sqrt_V * sqrt_dt * Z2[:, t]
+        V[:, t + 1] = np.maximum(V_pos + dV, 1e-8)
+        dS = r * S[:, t] * dt + sqrt_V * S[:, t] * sqrt_dt * Z1[:, t]
+        S[:, t + 1] = S[:, t] + dS
+    return S, V
+
+
+def hc_price_european(S_T, K, T, r, option_type="call"):
+    """exp(-rT) * mean(payoff(S_T)).  hc:265-277."""
+    if option_type.lower() == "call":
+        pay = np.maximum(S_T - K, 0)
+    else:
+        pay = np.maximum(K - S_T, 0)
+    return float(np.exp(-r * T) * np.mean(pay))
+
+
+# --------------------------------------------------------------------------------------
+# Regressors for the per-date LSM loop
+# --------------------------------------------------------------------------------------
+
+PIVOT_RTOL = 1e-14  # pivot < 1e-14 * trace(G) -> "no exercise at this date"
+
+
+def basis_matrix(S_itm, K, basis, T=None, t_current=None, r=None):
+    x = np.asarray(S_itm, dtype=np.float64) / K
+    if basis == "poly2":
+        return np.column_stack([np.ones_like(x), x, x * x])
+    if basis == "poly3":
+        return np.column_stack([np.ones_like(x), x, x * x, x * x * x])
+    if basis == "ref7":
+        return features_ref7(np.asarray(S_itm, dtype=np.float64), K, r, T, t_current)
+    raise ValueError(basis)
+
+
+def cholesky_solve_guarded(G, g, rtol=PIVOT_RTOL):
+    """LDL^T (no pivoting) with the pivot guard of SURVEY.md 8(c).
+
+    Returns beta, or None when a pivot d_k <= rtol * trace(G) (degenerate system).
+    The CUDA kernel runs exactly this recurrence in fp64.
+    """
+    p = G.shape[0]
+    tr = float(np.trace(G))
+    L = np.eye(p)
+    d = np.zeros(p)
+    for k in range(p):
+        s = G[k, k]
+        for j in range(k):
+            s -= L[k, j] * L[k, j] * d[j]
+        if not (s > rtol * tr):
+            return None
+        d[k] = s
+        for i in range(k + 1, p):
+            u = G[i, k]
+            for j in range(k):
+                u -= L[i, j] * L[k, j] * d[j]
+            L[i, k] = u / s
+    # forward: L z = g ; diag: w = z/d ; back: L^T beta = w
+    z = np.array(g, dtype=np.float64).copy()
+    for i in range(p):
+        for j in range(i):
+            z[i] -= L[i, j] * z[j]
+    w = z / d
+    beta = w.copy()
+    for i in range(p - 1, -1, -1):
+        for j in range(i + 1, p):
+            beta[i] -= L[j, i] * beta[j]
+    return beta
+
+
+class PolyRegressor:
+    """Per-date least squares on basis columns; in-sample continuation."""
+
+    def __init__(self, K, basis="poly2", T=None, r=None):
+        self.K, self.basis, self.T, self.r = K, basis, T, r
+        self.p = {"poly2": 3, "poly3": 4, "ref7": 7}[basis]
+
+    def __call__(self, t, t_current, S_itm, Y):
+        Phi = basis_matrix(S_itm, self.K, self.basis, self.T, t_current, self.r)
+        n = Phi.shape[0]
+        if n < self.p:
+            return None, None
+        G = Phi.T @ Phi
+        g = Phi.T @ np.asarray(Y, dtype=np.float64)
+        beta = cholesky_solve_guarded(G, g)
+        if beta is None:
+            return None, None
+        return Phi @ beta, beta
+
+
+@dataclass
+class SweepResult:
+    price: float
+    stderr: float
+    betas: np.ndarray  # [N+1, p], NaN rows where no regression happened
+    boundary: np.ndarray  # [N+1], put: max exercised S; call: min exercised S; NaN if none
+    ex_count: np.ndarray  # [N+1] int64, paths newly exercised at date t
+    n_itm: np.ndarray  # [N+1] int64, regression rows at date t
+    cashflows: Optional[np.ndarray] = field(default=None, repr=False)
+    exercised: Optional[np.ndarray] = field(default=None, repr=False)
+
+
+def lsm_sweep(S, K, r, T, option_type="put", regressor: Optional[Callable] = None, basis="poly2",
+              semantics="reference", keep_state=False) -> SweepResult:
+    """The reference's backward loop with a pluggable per-date regressor.
+
+    semantics="reference" follows om3:616-651 (= om3:485-500, om2:278-310):
+      cf = payoff(S[N]); for t = N-1..1: cf *= exp(-r dt) (ALL paths, before the mask, om3:620);
+      itm = (payoff(S[t]) > 0) & ~exercised (om3:621); skip if none (om3:623);
+      exercise where payoff > continuation, strict (om3:643-644); cf[ex] = payoff, exercised[ex] = True
+      (sticky, om3:646-649); price = mean(cf) after N-1 discounts (om3:651).
+    semantics="textbook": no sticky mask (a later-date exercise is overwritten by an earlier one),
+      and one more discount so the value is at time 0.
+    """
+    S = np.asarray(S)
+    N = S.shape[0] - 1
+    M = S.shape[1]
+    dt = T / N
+    discount = np.exp(-r * dt)
+    if regressor is None:
+        regressor = PolyRegressor(K, basis, T=T, r=r)
+    p = getattr(regressor, "p", 1)
+    sticky = semantics == "reference"
+
+    cf = payoff(S[-1], K, option_type).astype(np.float64)
+    exercised = np.zeros(M, dtype=bool)
+    betas = np.full((N + 1, p), np.nan)
+    boundary = np.full(N + 1, np.nan)
+    ex_count = np.zeros(N + 1, dtype=np.int64)
+    n_itm = np.zeros(N + 1, dtype=np.int64)
+
+    for t in range(N - 1, 0, -1):
+        cf *= discount
+        pay_t = payoff(S[t], K, option_type)
+        itm = pay_t > 0
+        if sticky:
+            itm &= ~exercised
+        n_itm[t] = int(itm.sum())
+        if not np.any(itm):
+            continue
+        X = S[t, itm]
+        cont, beta = regressor(t, t * dt, X, cf[itm])
+        if cont is None:
+            continue
+        if beta is not None:
+            betas[t, : len(beta)] = beta
+        immediate = pay_t[itm]
+        to_ex = immediate > cont
+        idx = np.where(itm)[0][to_ex]
+        cf[idx] = immediate[to_ex]
+        exercised[idx] = True
+        ex_count[t] = idx.size
+        if idx.size:
+            boundary[t] = X[to_ex].max() if option_type == "put" else X[to_ex].min()
+
+    scale = 1.0 if sticky else discount
+    price = float(cf.mean() * scale)
+    stderr = float(cf.std(ddof=1) / math.sqrt(M) * scale) if M > 1 else 0.0
+    return SweepResult(price, stderr, betas, boundary, ex_count, n_itm,
+                       cf * scale if keep_state else None, exercised if keep_state else None)
+
+
+# --------------------------------------------------------------------------------------
+# v3 "global regressor" structure (om3:482-651) with a pluggable fit
+# --------------------------------------------------------------------------------------
+
+
+def lsm_global(S, K, r, T, option_type, fit: Callable, target_ddof=0):
+    """om3:482-651 with the network replaced by ``fit``.
+
+    Pass 1 (om3:485-516): exercised is never set, so the targets are discounted TERMINAL payoffs of
+    every ITM path at every date.  Normalisation om3:550-563 (population std; om3gpu:731 uses the
+    sample std -> target_ddof=1).  ``fit(Xn, Ys) -> predict(Xn) -> Ys_hat``.  Pass 2 (om3:615-651)
+    applies the sticky-mask loop with continuation = predict(norm(features)) * Y_std + Y_mean.
+    """
+    S = np.asarray(S, dtype=np.float64)
+    N = S.shape[0] - 1
+    M = S.shape[1]
+    dt = T / N
+    discount = np.exp(-r * dt)
+    cf = payoff(S[-1], K, option_type).astype(np.float64)
+    feats, targs = [], []
+    for t in range(N - 1, 0, -1):
+        cf *= discount
+        itm = payoff(S[t], K, option_type) > 0
+        if not np.any(itm):
+            continue
+        feats.append(features_ref7(S[t, itm], K, r, T, t * dt))
+        targs.append(cf[itm].reshape(-1, 1))
+    if not feats:
+        return float(cf.mean()), None
+    X_all = np.vstack(feats)
+    Y_all = np.vstack(targs)
+    Y_mean = Y_all.mean()
+    Y_std = Y_all.std(ddof=target_ddof)
+    if Y_std > 0:
+        Ys = (Y_all - Y_mean) / Y_std
+    else:
+        Ys = Y_all - Y_mean
+        Y_std = 1.0
+    f_mean = X_all.mean(axis=0)
+    f_std = X_all.std(axis=0)
+    f_std[f_std == 0] = 1
+    Xn = (X_all - f_mean) / f_std
+    predict = fit(Xn, Ys)
+
+    cf = payoff(S[-1], K, option_type).astype(np.float64)
+    exercised = np.zeros(M, dtype=bool)
+    for t in range(N - 1, 0, -1):
+        cf *= discount
+        itm = (payoff(S[t], K, option_type) > 0) & (~exercised)
+        if not np.any(itm):
+            continue
+        X = S[t, itm]
+        fn = (features_ref7(X, K, r, T, t * dt) - f_mean) / f_std
+        cont = np.asarray(predict(fn)).reshape(-1) * Y_std + Y_mean
+        immediate = payoff(X, K, option_type)
+        to_ex = immediate > cont
+        idx = np.where(itm)[0][to_ex]
+        cf[idx] = immediate[to_ex]
+        exercised[idx] = True
+    stats = dict(Y_mean=float(Y_mean), Y_std=float(Y_std), f_mean=f_mean, f_std=f_std, n_rows=int(X_all.shape[0]))
+    return float(cf.mean()), stats
+
+
+# --------------------------------------------------------------------------------------
+# European estimators
+# --------------------------------------------------------------------------------------
+
+
+def price_european_streaming(K, r, sigma, option_type, rng_manager, S0, T, num_simulations=10000,
+                             num_time_steps=50, chunk_size=500, heston_params=None):
+    """om3:382-437: per chunk a fresh child rng, a full path array, payoff of S[-1], Welford merge."""
+    discount_factor = np.exp(-r * T)
+
+    def simulator(batch_size):
+        rng = rng_manager.get_child_rng()
+        N = num_time_steps
+        if heston_params is not None:
+            M = batch_size // 2 * 2
+            Z1, Z2 = draw_heston_normals(rng, N, M)
+            hp = heston_params
+            S = heston_paths_antithetic(S0, r, T, hp["v0"], hp["kappa"], hp["theta"], hp["xi"], hp["rho"], M, N, Z1, Z2)
+            if batch_size % 2 != 0:  # om3:235-249
+                dt = T / N
+                S_odd = np.zeros((N + 1, 1)); v_odd = np.zeros((N + 1, 1))
+                S_odd[0] = S0; v_odd[0] = hp["v0"]
+                for t in range(1, N + 1):
+                    z1 = rng.standard_normal(1); z2 = rng.standard_normal(1)
+                    w2 = hp["rho"] * z1 + np.sqrt(1 - hp["rho"] ** 2) * z2
+                    vp = np.maximum(v_odd[t - 1], 0)
+                    v_odd[t] = np.maximum(vp + hp["kappa"] * (hp["theta"] - vp) * dt + hp["xi"] * np.sqrt(vp * dt) * w2, 0)
+                    S_odd[t] = S_odd[t - 1] * np.exp((r - 0.5 * vp) * dt + np.sqrt(vp * dt) * z1)
+                S = np.concatenate([S, S_odd], axis=1)
+        else:
+            M = batch_size // 2 * 2
+            Zh = draw_gbm_normals(rng, N, M)
+            S = gbm_paths_antithetic(S0, r, sigma, T, M, N, Zh)
+            if batch_size % 2 != 0:  # om3:417-423
+                dt = T / N
+                drift = (r - 0.5 * sigma**2) * dt
+                diffusion = sigma * np.sqrt(dt)
+                S_odd = np.zeros((N + 1, 1)); S_odd[0] = S0
+                Z_odd = rng.standard_normal((N, 1))
+                for t in range(1, N + 1):
+                    S_odd[t] = S_odd[t - 1] * np.exp(drift + diffusion * Z_odd[t - 1])
+                S = np.concatenate([S, S_odd], axis=1)
+        return (payoff(S[-1], K, option_type) * discount_factor).astype(np.float64)
+
+    return monte_carlo_price_streaming(simulator, num_simulations, chunk_size)
+
+
+def european_from_paths(S_T, K, r, T, option_type):
+    """Discounted terminal payoff mean / stderr (a12) on a given terminal slab."""
+    pay = payoff(np.asarray(S_T, dtype=np.float64), K, option_type) * np.exp(-r * T)
+    n = pay.size
+    return float(pay.mean()), float(pay.std(ddof=1) / math.sqrt(n)) if n > 1 else 0.0
+
+
+# --------------------------------------------------------------------------------------
+# End-to-end restatement of price_american_enhanced_lsm with the polynomial regressor
+# --------------------------------------------------------------------------------------
+
+
+def price_american_lsm(S0, K, r, T, option_type, num_simulations, num_time_steps, rng_manager, sigma=None,
+                       heston_params=None, basis="poly2", semantics="reference", return_paths=False):
+    """om3:439-480 (validation, RNG order, path model routing) + lsm_sweep."""
+    if S0 <= 0 or K <= 0 or T <= 0:
+        raise ValueError("S0, K, T must be positive.")
+    if r < 0:
+        raise ValueError("r must be non-negative.")
+    if num_simulations <= 0 or num_time_steps <= 0:
+        raise ValueError("num_simulations and num_time_steps must be positive integers.")
+    rng = rng_manager.get_child_rng()
+    rng_manager.get_child_seed()  # om3:455 consumes a second master draw (torch.manual_seed)
+    M = num_simulations // 2 * 2
+    N = num_time_steps
+    if heston_params is not None:
+        hp = heston_params
+        Z1, Z2 = draw_heston_normals(rng, N, M)
+        S = heston_paths_antithetic(S0, r, T, hp["v0"], hp["kappa"], hp["theta"], hp["xi"], hp["rho"], M, N, Z1, Z2)
+        normals = (Z1, Z2)
+    else:
+        if sigma is None:
+            raise ValueError("sigma is None: provide sigma, iv_model, or heston configuration")
+        Zh = draw_gbm_normals(rng, N, M)
+        S = gbm_paths_antithetic(S0, r, sigma, T, M, N, Zh)
+        normals = (Zh,)
+    res = lsm_sweep(S, K, r, T, option_type, basis=basis, semantics=semantics)
+    if return_paths:
+        return res, S, normals
+    return res
