@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- path-steps/sec of the Heston American-put LSM hot path on N B200s (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--paths M] [--dates T]
+
+Own arm (default): one process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A "step" is
+one pass of the hot path over one option: K1 path generation (Philox in-register, step-major fp32 slab) +
+the persistent LSM sweep + the final payoff reduction, for BASELINE config 2 (Heston kappa=2 theta=0.04
+xi=0.5 rho=-0.7, 252 steps, 1M paths, quadratic-polynomial LSM).  With N GPUs every rank prices its own
+independent option (option-sharding, no data-path collective: weak scaling).  Timing: CUDA events on the
+launching stream, barrier + synchronize on both sides, max over ranks.  The 1 GB slab is 8x the L2, so no
+explicit L2 flush is needed between iterations.
+
+Reference arm (--impl reference): the reference is pure Python and cannot travel to the GPU box, so this
+times its restatement (oracle/lsm_oracle.py, numpy) on the host cores, reference-style: a process pool
+with one independent option per worker (options_model_3.py:1053-1056), each step a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HP = dict(v0=0.04, kappa=2.0, theta=0.04, xi=0.5, rho=-0.7)
+S0, K, R, T = 100.0, 100.0, 0.05, 1.0
+METRIC = "path-steps/sec, Heston American put LSM"
+UNIT = "path-steps/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU side: the oracle port (checker / baseline only)
+# ------------------------------------------------------------------------------------------------------
+def _cpu_price_one(args):
+    seed, M, N = args
+    import numpy as np
+
+    from oracle import lsm_oracle as orc
+
+    rng = np.random.default_rng(seed)
+    Z1, Z2 = orc.draw_heston_normals(rng, N, M)
+    S = orc.heston_paths_antithetic(S0, R, T, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2)
+    return orc.lsm_sweep(S, K, R, T, "put").price
+
+
+def cpu_baseline_single(M, N):
+    _cpu_price_one((0, 2000, 8))  # imports + warm-up outside the timed sample
+    t0 = time.perf_counter()
+    price = _cpu_price_one((1, M, N))
+    dt = time.perf_counter() - t0
+    return {"value": M * N / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"numpy oracle (draws + Heston paths + poly2 LSM sweep), {M} paths x {N} steps, "
+                      f"{dt:.1f} s, price {price:.4f}; host has {os.cpu_count()} cpus"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ProcessPoolExecutor
+
+    cores = os.cpu_count() or 1
+    M, N = args.ref_paths, args.dates
+    with ProcessPoolExecutor(max_workers=cores) as ex:
+        def step(i):
+            return list(ex.map(_cpu_price_one, [(1000 * i + w, M, N) for w in range(cores)]))
+        for i in range(args.warmup):
+            step(i)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        dt = time.perf_counter() - t0
+    val = cores * M * N * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE config 2 (Heston American put, poly2 LSM, {N} steps), bounded sample: "
+                               f"{cores} independent options x {M} paths per step, one per worker process"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"oracle/lsm_oracle.py (numpy restatement of options_model_3.py:211-233,615-651 with the "
+                                   f"8(c) polynomial regressor); {cores} worker processes x {M} paths x {N} steps per step"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.stop = index, [], set(), threading.Event()
+        self.max_mhz = None
+        self.th = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake": 0x80}
+        while not self.stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        if self.th:
+            self.th.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------
+def run_own_arm(args):
+    import torch
+
+    from options_model_b200 import _lib as L
+    from options_model_b200 import compat
+    from options_model_b200 import engine as E
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    M, N = args.paths, args.dates
+    eng = E.Engine(local)
+    stream = torch.cuda.Stream(device=local)
+    model = E.heston(S0, R, T, **HP)
+    b = 4  # fp32 storage
+    with torch.cuda.stream(stream):
+        slab = eng.alloc_slab(M, N, "f32")
+        view = slab[:, :M]
+
+        def step(i, ev=None):
+            rng = E.RngSpec(seed=42, stream=rank * 1_000_003 + i)  # a fresh option (stream) per step and rank
+            if ev:
+                ev[0].record()
+            eng.paths(model, M, N, "f32", rng, out=slab)
+            if ev:
+                ev[1].record()
+            eng.lsm(view, K, R, T, "put", "poly2", "reference", "auto", asynchronous=True)
+            if ev:
+                ev[2].record()
+
+        for i in range(args.warmup):
+            step(i)
+        barrier()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        l0 = eng.launch_count()
+        with ClockSampler(local) as clocks:
+            t_start = torch.cuda.Event(enable_timing=True)
+            t_end = torch.cuda.Event(enable_timing=True)
+            t_start.record()
+            for i in range(args.steps):
+                step(args.warmup + i, evs[i])
+            t_end.record()
+            barrier()
+        launches = eng.launch_count() - l0
+        ms_total = t_start.elapsed_time(t_end)
+        res = eng.lsm_fetch(N, "poly2", arrays=False)
+        ms_paths = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+        ms_sweep = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+
+        # end-to-end through the reference-facing call: host scalars in, host float out, every step
+        pricer = compat.AdvancedOptionPricer(K=K, r=R, sigma=None, option_type="put", rng_manager=compat.RNGManager(42),
+                                             use_heston=True, heston_params=HP, use_control_variate=False,
+                                             device=local)
+        for _ in range(max(1, args.warmup // 2)):
+            pricer.price_american_enhanced_lsm(S0, T, M, N)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            price_e2e = pricer.price_american_enhanced_lsm(S0, T, M, N)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        barrier()
+
+    if dist is not None:
+        t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(t[0]), float(t[1])
+    else:
+        e2e_ms = e2e_s * 1e3
+
+    if rank == 0:
+        import ctypes
+
+        peak, peak_src = load_peaks()
+        path_steps = world * M * N * args.steps
+        value = path_steps / (ms_total * 1e-3)
+        # algorithmic bytes: generation b per path-step (rows 0..N stored); sweep 3b per path
+        # per exercise date (+ b for the terminal row); pipeline 4b per path-step.
+        bytes_paths = b * M * (N + 1)
+        bytes_sweep = 3 * b * M * (N - 1) + b * M
+        kern = {
+            "paths_kernel<f32,heston_ref_absorb,vec4,philox>": {
+                "ms": ms_paths, "alg_bytes": bytes_paths, "GBps": bytes_paths / (ms_paths * 1e-3) / 1e9},
+            "lsm_resident_kernel<f32,poly2>": {
+                "ms": ms_sweep, "alg_bytes": bytes_sweep, "GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9},
+        }
+        dom = max(kern, key=lambda k: kern[k]["ms"])
+        ach = kern[dom]["GBps"]
+        cpu = cpu_baseline_single(args.cpu_paths, N) if world == 1 and not args.no_cpu else None
+        h2d = ctypes.sizeof(L.ModelParams) + ctypes.sizeof(L.RngParams) + ctypes.sizeof(L.LsmParams)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE config 2: American put, Heston (kappa=2, theta=0.04, xi=0.5, rho=-0.7), "
+                                   f"{N} steps, {M} paths per option, poly2 LSM (reference semantics), one option per "
+                                   f"GPU per step",
+                       "storage": "fp32 step-major slab, fp64 Gram/solve/decision", "rng": "Philox4x32-10 in-register",
+                       "sharding": "options across ranks (no data-path collective)",
+                       "l2": f"slab {b * M * (N + 1) / 1e6:.0f} MB per step > L2 ({eng.l2_bytes / 1e6:.0f} MB): no flush needed",
+                       "price": res.price, "stderr": res.stderr},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": None, "kernel": dom, "peak_source": peak_src,
+                         "pipeline_frac": (4 * b * M * N * world * args.steps) / (ms_total * 1e-3) / 1e9 / (peak * world),
+                         "kernels": kern},
+            "e2e": {"value": world * M * N * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms / args.steps, "price": price_e2e,
+                    "call": "compat.AdvancedOptionPricer.price_american_enhanced_lsm (host scalars in, host float out; "
+                            "the path's inputs are option/model scalars, normals are generated in-kernel)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--paths", type=int, default=1_000_000)
+    ap.add_argument("--dates", type=int, default=252)
+    ap.add_argument("--cpu-paths", type=int, default=400_000, help="CPU-baseline sample size (paths)")
+    ap.add_argument("--ref-paths", type=int, default=50_000, help="reference arm: paths per worker per step")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "own":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_own_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,196 @@
+/*
+ * optmc.h -- C ABI of the B200-native American-option Monte Carlo engine (liboptmc.so).
+ *
+ * Drop-in boundary for the data-parallel hot path of Levicoz/Options-model:
+ * path simulation + Longstaff-Schwartz backward induction (+ the European payoff reduction).
+ * The reference has NO FFI of its own (it is pure Python); each entry point below names the
+ * reference function it replaces (file:line relative to the reference tree;
+ * om3 = options_model_3/options_model_3.py, om3gpu = options_model_3/option_model_3_gpu.py,
+ * om2 = options_model_2.py, hc = options_model_3/heston_calibration.py).
+ *
+ * Conventions
+ *  - Every function returns OPTMC_OK (0) or a negative error class; the message is available from
+ *    optmc_last_error() (thread-local).  OPTMC_EINVAL maps to the reference's ValueError
+ *    (om3:447-452), everything else to RuntimeError.
+ *  - "dev" pointers are CUDA device pointers owned by the CALLER (e.g. torch tensor.data_ptr()).
+ *    "host" pointers are ordinary host memory owned by the caller.  The library owns only the
+ *    opaque context (stream, workspace, exchange slots).
+ *  - Path slabs are STEP-MAJOR: S[(N+1)][ld], row t = exercise date t, S[0][*] = S0 -- the layout of
+ *    the reference's S array (om3:477, om3:217).  Columns [0, M/2) are the +Z paths, [M/2, M) the
+ *    antithetic -Z paths (om3:476, om3:225-226).
+ *  - A context is bound to one device and is not thread-safe.  All work is issued on the context's
+ *    stream; only the *_fetch / host-result calls synchronise.
+ *  - There is no CPU fallback: without a CUDA device optmc_ctx_create fails with OPTMC_ECUDA.
+ */
+#ifndef OPTMC_H
+#define OPTMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPTMC_ABI_VERSION 1
+
+enum optmc_status {
+  OPTMC_OK = 0,
+  OPTMC_EINVAL = -1,       /* bad argument: ValueError in the compat layer */
+  OPTMC_ECUDA = -2,        /* CUDA runtime / launch failure */
+  OPTMC_ENOMEM = -3,       /* workspace allocation failed */
+  OPTMC_EUNSUPPORTED = -4  /* valid request this build cannot serve */
+};
+
+enum optmc_dtype { OPTMC_F32 = 0, OPTMC_F64 = 1 };
+
+enum optmc_model { OPTMC_MODEL_GBM = 0, OPTMC_MODEL_HESTON = 1 };
+
+enum optmc_scheme {
+  OPTMC_SCHEME_GBM_LOG_EULER = 0,        /* om3:473-480  S *= exp(drift + diffusion Z), per step */
+  OPTMC_SCHEME_GBM_LOGSPACE = 1,         /* om3gpu:150-185 cumulative log-space sum, exp at the end */
+  OPTMC_SCHEME_HESTON_REF_ABSORB = 2,    /* om3:228-233 / om3gpu:218-225 absorption Euler (the reference's scheme) */
+  OPTMC_SCHEME_HESTON_FULL_TRUNC = 3,    /* Lord et al. full truncation (north-star scheme; not in the reference) */
+  OPTMC_SCHEME_HESTON_REF_CALIB = 4      /* hc:240-255 arithmetic Euler on S, variance floored at 1e-8 */
+};
+
+enum optmc_basis {
+  OPTMC_BASIS_POLY2 = 2, /* [1, x, x^2], x = S/K : first three reference features (om3:112-115) */
+  OPTMC_BASIS_POLY3 = 3  /* [1, x, x^2, x^3]     : first four reference features */
+};
+
+/* LSM loop semantics.  REFERENCE = STICKY | REF_DISCOUNT reproduces om3:616-651. */
+#define OPTMC_SEM_STICKY_MASK 1u  /* itm = payoff>0 && !exercised (om3:621); exercised is sticky (om3:649) */
+#define OPTMC_SEM_REF_DISCOUNT 2u /* N-1 discounts, value at time dt (om3:619-620,651) instead of N */
+#define OPTMC_SEM_REFERENCE (OPTMC_SEM_STICKY_MASK | OPTMC_SEM_REF_DISCOUNT)
+#define OPTMC_SEM_TEXTBOOK 0u
+
+/* Which sweep implementation to run (results are identical; this exists for tests and profiling). */
+enum optmc_sweep_impl {
+  OPTMC_SWEEP_AUTO = 0,     /* resident persistent kernel when the slab slice fits on chip, else split */
+  OPTMC_SWEEP_RESIDENT = 1, /* one cooperative launch for all dates; cash-flows live in registers */
+  OPTMC_SWEEP_SPLIT = 2     /* three small launches per date; cash-flows in HBM */
+};
+
+typedef struct optmc_ctx optmc_ctx;
+
+typedef struct optmc_model_params {
+  int32_t model;  /* optmc_model */
+  int32_t scheme; /* optmc_scheme */
+  double S0, r, T;
+  double sigma;                     /* GBM volatility */
+  double v0, kappa, theta, xi, rho; /* Heston (xi = vol-of-vol; hc.HestonParams calls it sigma) */
+} optmc_model_params;
+
+typedef struct optmc_rng_params {
+  uint64_t seed;   /* Philox4x32-10 key */
+  uint64_t stream; /* Philox counter word 3 (low 32 bits) -- one independent stream per option */
+  /* Optional external normals (device pointers), step-major [N][M/2] (or [N][M] when antithetic = 0),
+   * row t-1 drives step t (om3:475-480; om3:223-224).  NULL => Philox in-register generation.
+   * GBM uses z1 only.  z_dtype is the element type of the z buffers. */
+  const void* z1_dev;
+  const void* z2_dev;
+  int32_t z_dtype;     /* optmc_dtype */
+  int32_t antithetic;  /* 1: [Z, -Z] column layout (om3:476); 0: independent columns (om3gpu:173) */
+  int64_t pair_offset; /* global index of local pair 0: path-sharding across GPUs keeps Philox counters global */
+} optmc_rng_params;
+
+typedef struct optmc_lsm_params {
+  double K, r, T;
+  int32_t is_put;      /* 1 put, 0 call (om3:376-380) */
+  int32_t basis;       /* optmc_basis */
+  uint32_t semantics;  /* OPTMC_SEM_* */
+  int32_t impl;        /* optmc_sweep_impl */
+} optmc_lsm_params;
+
+/* Host-side result block.  Array members may be NULL (not copied back). */
+typedef struct optmc_lsm_result {
+  double price;      /* mean cash-flow (om3:651), times one more discount under TEXTBOOK */
+  double stderr_;    /* sample std / sqrt(M) */
+  int64_t n_paths;
+  int32_t impl_used; /* optmc_sweep_impl actually run */
+  int32_t n_launches;/* kernels launched by this call */
+  double* betas;     /* host [N+1][p], NaN rows where no regression was solved */
+  double* boundary;  /* host [N+1]: put -> max exercised S, call -> min exercised S, NaN if none */
+  int64_t* ex_count; /* host [N+1]: paths newly exercised at date t */
+  int64_t* n_itm;    /* host [N+1]: regression rows at date t */
+} optmc_lsm_result;
+
+typedef struct optmc_european_result {
+  double mean;    /* discounted payoff mean: exp(-rT) * mean(payoff(S_T))  (om3:425, hc:274-275) */
+  double stderr_; /* sample std / sqrt(n) (om3:61-62) */
+  int64_t n_paths;
+} optmc_european_result;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int optmc_abi_version(void);
+const char* optmc_last_error(void);
+int optmc_ctx_create(int device, optmc_ctx** out);
+int optmc_ctx_destroy(optmc_ctx* ctx);
+/* Use a caller-provided cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0/NULL => the
+ * context's own stream. */
+int optmc_ctx_set_stream(optmc_ctx* ctx, void* cuda_stream);
+int optmc_ctx_synchronize(optmc_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t optmc_ctx_launch_count(optmc_ctx* ctx);
+/* Device properties the host layer needs for grid sizing / reporting: out[0]=SM count,
+ * out[1]=L2 bytes, out[2]=max opt-in shared memory per block, out[3]=compute capability major*10+minor. */
+int optmc_ctx_device_info(optmc_ctx* ctx, int64_t out[4]);
+
+/* ---- path simulation (replaces om3:473-480, om3:211-251, om3gpu:117-248, hc:204-257) ---------- */
+/* S_dev: [(N+1)][ld] of `dtype`; ld >= M.  V_dev (Heston only, may be NULL): same shape, the variance
+ * slab the reference also builds (om3:218, hc:217).  M must be even when rng->antithetic. */
+int optmc_paths_gbm(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M, int32_t N,
+                    int32_t dtype, void* S_dev, int64_t ld);
+int optmc_paths_heston(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                       int32_t N, int32_t dtype, void* S_dev, void* V_dev, int64_t ld);
+/* The standard normals the Philox path kernels consume, written step-major [N][M/2] (test aid: feed
+ * them to the oracle).  which = 0 -> z1 (asset), 1 -> z2 (variance, Heston only). */
+int optmc_philox_normals(optmc_ctx* ctx, const optmc_rng_params* rng, int32_t model, int64_t M, int32_t N,
+                         int32_t which, int32_t dtype, void* Z_dev);
+/* Philox4x32-10 known-answer hook: runs n blocks on the device.  ctr[n][4], key[n][2] -> out[n][4] (host). */
+int optmc_philox_kat(optmc_ctx* ctx, int32_t n, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
+
+/* ---- LSM backward induction (replaces the loop of om3:615-651 / om3:485-500 / om2:278-310 with the
+ *      polynomial regressor of SURVEY.md 8(c)) ------------------------------------------------------- */
+int optmc_lsm_poly(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                   const optmc_lsm_params* lp, optmc_lsm_result* out /* NULL: asynchronous, fetch later */);
+/* Synchronise and copy the last sweep's results to the host. */
+int optmc_lsm_fetch(optmc_ctx* ctx, optmc_lsm_result* out);
+
+/* Per-date building blocks for path-sharded multi-GPU sweeps: the host all-reduces `gram_dev`
+ * (optmc_lsm_gram_len doubles) between the two calls. */
+int optmc_lsm_gram_len(int32_t basis);
+int optmc_lsm_begin(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                    const optmc_lsm_params* lp);
+int optmc_lsm_gram_date(optmc_ctx* ctx, int32_t t, double* gram_dev);
+int optmc_lsm_update_date(optmc_ctx* ctx, int32_t t, const double* gram_dev);
+/* sums_dev[0..2] = sum(cf), sum(cf^2), n over the local paths (all-reduce, then price = s0/n). */
+int optmc_lsm_finish(optmc_ctx* ctx, double* sums_dev);
+
+/* ---- fused host-facing calls (what the compat layer's pricer methods call) ------------------- */
+/* price_american_enhanced_lsm (om3:439-651): paths into a context-owned slab + sweep.  Host scalars in,
+ * host results out. */
+int optmc_price_american(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                         int32_t N, int32_t dtype, const optmc_lsm_params* lp, optmc_lsm_result* out);
+/* price_european_streaming / price_european_gpu / HestonPricer.price_european_option
+ * (om3:382-437, om3gpu:605-653, hc:259-281): paths are generated and reduced in registers, nothing is
+ * stored.  n_options options share mp/rng except K[i], T[i], is_put[i]; option i uses Philox stream
+ * rng->stream + stream_id[i] (options with equal ids see the same paths: "simulate once per unique T",
+ * hc:289-306).  results: host [n_options]. */
+int optmc_price_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                               int32_t N, int32_t dtype, int32_t n_options, const double* K, const double* T,
+                               const int32_t* is_put, const int32_t* stream_id /* NULL: option i -> i */,
+                               optmc_european_result* results);
+/* European reduction over an existing terminal slab row (a12 on stored paths). */
+int optmc_european_from_slab(optmc_ctx* ctx, const void* ST_dev, int64_t M, int32_t dtype, double K, double r,
+                             double T, int32_t is_put, optmc_european_result* out);
+
+/* ---- parity aid: create_regression_features (om3:105-121, om3gpu:342-377) ---------------------- */
+/* F_dev: [n][7] row-major of `dtype`. */
+int optmc_features_ref7(optmc_ctx* ctx, const void* S_dev, int64_t n, int32_t dtype, double K, double r, double T,
+                        double t_current, void* F_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTMC_H */

@@ -1,0 +1,124 @@
+"""ctypes binding of liboptmc.so -- one Python declaration per prototype in include/optmc.h."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# enums (include/optmc.h)
+OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
+F32, F64 = 0, 1
+MODEL_GBM, MODEL_HESTON = 0, 1
+SCHEME_GBM_LOG_EULER, SCHEME_GBM_LOGSPACE, SCHEME_HESTON_REF_ABSORB, SCHEME_HESTON_FULL_TRUNC, SCHEME_HESTON_REF_CALIB = range(5)
+BASIS_POLY2, BASIS_POLY3 = 2, 3
+SEM_STICKY_MASK, SEM_REF_DISCOUNT = 1, 2
+SEM_REFERENCE, SEM_TEXTBOOK = 3, 0
+SWEEP_AUTO, SWEEP_RESIDENT, SWEEP_SPLIT = 0, 1, 2
+
+
+class OptmcError(RuntimeError):
+    pass
+
+
+class ModelParams(C.Structure):
+    _fields_ = [("model", C.c_int32), ("scheme", C.c_int32), ("S0", C.c_double), ("r", C.c_double), ("T", C.c_double),
+                ("sigma", C.c_double), ("v0", C.c_double), ("kappa", C.c_double), ("theta", C.c_double),
+                ("xi", C.c_double), ("rho", C.c_double)]
+
+
+class RngParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("stream", C.c_uint64), ("z1_dev", C.c_void_p), ("z2_dev", C.c_void_p),
+                ("z_dtype", C.c_int32), ("antithetic", C.c_int32), ("pair_offset", C.c_int64)]
+
+
+class LsmParams(C.Structure):
+    _fields_ = [("K", C.c_double), ("r", C.c_double), ("T", C.c_double), ("is_put", C.c_int32), ("basis", C.c_int32),
+                ("semantics", C.c_uint32), ("impl", C.c_int32)]
+
+
+class LsmResult(C.Structure):
+    _fields_ = [("price", C.c_double), ("stderr_", C.c_double), ("n_paths", C.c_int64), ("impl_used", C.c_int32),
+                ("n_launches", C.c_int32), ("betas", C.POINTER(C.c_double)), ("boundary", C.POINTER(C.c_double)),
+                ("ex_count", C.POINTER(C.c_int64)), ("n_itm", C.POINTER(C.c_int64))]
+
+
+class EuropeanResult(C.Structure):
+    _fields_ = [("mean", C.c_double), ("stderr_", C.c_double), ("n_paths", C.c_int64)]
+
+
+# name -> (restype, argtypes); must list every symbol include/optmc.h declares (tests check this)
+_P = C.POINTER
+PROTOTYPES = {
+    "optmc_abi_version": (C.c_int, []),
+    "optmc_last_error": (C.c_char_p, []),
+    "optmc_ctx_create": (C.c_int, [C.c_int, _P(C.c_void_p)]),
+    "optmc_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "optmc_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "optmc_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "optmc_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "optmc_ctx_device_info": (C.c_int, [C.c_void_p, _P(C.c_int64)]),
+    "optmc_paths_gbm": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_int64]),
+    "optmc_paths_heston": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_int64]),
+    "optmc_philox_normals": (C.c_int, [C.c_void_p, _P(RngParams), C.c_int32, C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_void_p]),
+    "optmc_philox_kat": (C.c_int, [C.c_void_p, C.c_int32, _P(C.c_uint32), _P(C.c_uint32), _P(C.c_uint32)]),
+    "optmc_lsm_poly": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
+                                 _P(LsmResult)]),
+    "optmc_lsm_fetch": (C.c_int, [C.c_void_p, _P(LsmResult)]),
+    "optmc_lsm_gram_len": (C.c_int, [C.c_int32]),
+    "optmc_lsm_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams)]),
+    "optmc_lsm_gram_date": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "optmc_lsm_update_date": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
+    "optmc_lsm_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "optmc_price_american": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
+                                       _P(LsmParams), _P(LsmResult)]),
+    "optmc_price_european_batch": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32,
+                                             C.c_int32, C.c_int32, _P(C.c_double), _P(C.c_double), _P(C.c_int32),
+                                             _P(C.c_int32), _P(EuropeanResult)]),
+    "optmc_european_from_slab": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double,
+                                           C.c_double, C.c_int32, _P(EuropeanResult)]),
+    "optmc_features_ref7": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double,
+                                      C.c_double, C.c_double, C.c_void_p]),
+}
+
+
+def library_path() -> str:
+    return os.environ.get("OPTMC_LIB", os.path.join(HERE, "liboptmc.so"))
+
+
+def load_library():
+    """Load liboptmc.so (built in-tree by __graft_entry__.build() / make).  No fallback of any kind."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise OptmcError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         f"(or `make -C options-model_b200`). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.optmc_abi_version() != 1:
+        raise OptmcError("liboptmc.so ABI version mismatch; rebuild")
+    _LIB = lib
+    return lib
+
+
+def check(rc: int):
+    """Map a C status to the reference's exception types (om3:447-452 raise ValueError)."""
+    if rc == OK:
+        return
+    msg = load_library().optmc_last_error().decode("utf-8", "replace")
+    if rc == EINVAL:
+        raise ValueError(msg)
+    if rc == ENOMEM:
+        raise MemoryError(msg)
+    if rc == EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise OptmcError(msg)

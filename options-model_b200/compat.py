@@ -1,0 +1,557 @@
+"""Drop-in mirror of the reference's Python call signatures for the hot path.
+
+Same names, argument meaning and error behaviour as the reference; the bodies route to liboptmc.so.
+om3 = options_model_3/options_model_3.py, om3gpu = options_model_3/option_model_3_gpu.py,
+om2 = options_model_2.py, om1 = Options_model.py, hc = options_model_3/heston_calibration.py.
+
+What differs from the reference, by design:
+  * The continuation regressor is the polynomial least-squares fit of SURVEY.md 8(c) (``lsm_regressor``
+    keyword, default "poly2") instead of a torch network; ``nn_*`` arguments are accepted and ignored.
+  * Random numbers: functions that receive an explicit numpy ``Generator`` / rely on torch's global
+    generator (simulate_heston_paths_antithetic, simulate_*_torch, HestonPricer.simulate_paths) draw
+    from it exactly as the reference does and feed the draws to the kernels, so results match the
+    reference draw-for-draw.  The pricer methods use in-kernel Philox keyed by the RNGManager child
+    seed; they consume the same number of master draws as the reference (om3:454-455, om3:392).
+  * iv_model (local volatility) is out of scope for this round: NotImplementedError.
+"""
+from __future__ import annotations
+
+import logging
+import math
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+from numpy.random import default_rng
+
+from . import _lib as L
+from . import engine as E
+
+
+# ---------------------------------------------------------------------------------------------------
+# RNG seed tree (om3:69-79) -- host integers only
+# ---------------------------------------------------------------------------------------------------
+class RNGManager:
+    def __init__(self, master_seed: int = 42):
+        self.master_rng = default_rng(master_seed)
+        self.master_seed = master_seed
+
+    def get_child_rng(self) -> np.random.Generator:
+        child_seed = self.master_rng.integers(0, 2**31 - 1)
+        return default_rng(child_seed)
+
+    def get_child_seed(self) -> int:
+        return self.master_rng.integers(0, 2**31 - 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# closed forms used by the control variate (om3:150-159) -- scalar host math, not on the hot path
+# ---------------------------------------------------------------------------------------------------
+def _ncdf(x: float) -> float:
+    return 0.5 * (1.0 + math.erf(x / math.sqrt(2.0)))
+
+
+class BlackScholesGreeks:
+    @staticmethod
+    def black_scholes_price(S, K, T, r, sigma, option_type="call"):
+        d1 = (math.log(S / K) + (r + 0.5 * sigma**2) * T) / (sigma * math.sqrt(T))
+        d2 = d1 - sigma * math.sqrt(T)
+        if option_type == "call":
+            return S * _ncdf(d1) - K * math.exp(-r * T) * _ncdf(d2)
+        return K * math.exp(-r * T) * _ncdf(-d2) - S * _ncdf(-d1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# free path-simulation functions
+# ---------------------------------------------------------------------------------------------------
+def _engine(device=0) -> E.Engine:
+    return E.default_engine(device)
+
+
+def _dev_index(device) -> int:
+    import torch
+
+    d = torch.device(device) if not isinstance(device, torch.device) else device
+    if d.type != "cuda":
+        raise L.OptmcError(f"device {d} requested; options_model_b200 runs on CUDA devices only (no CPU fallback)")
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+def simulate_heston_paths_antithetic(S0: float, r: float, T: float, v0: float, kappa: float, theta: float,
+                                     xi: float, rho: float, num_simulations: int, num_time_steps: int,
+                                     rng: np.random.Generator) -> np.ndarray:
+    """om3:211-251.  Draws z1_half, z2_half per step from ``rng`` exactly like the reference (om3:223-224),
+    runs the absorption-Euler kernel in fp64 on those draws, returns S[(N+1), num_simulations] (host)."""
+    import torch
+
+    eng = _engine()
+    N = int(num_time_steps)
+    M = num_simulations // 2 * 2
+    out = np.zeros((N + 1, num_simulations), dtype=np.float64)
+    model = E.heston(S0, r, T, v0, kappa, theta, xi, rho)
+    if M > 0:
+        Z1 = np.empty((N, M // 2)); Z2 = np.empty((N, M // 2))
+        for t in range(N):
+            Z1[t] = rng.standard_normal(M // 2)
+            Z2[t] = rng.standard_normal(M // 2)
+        z1 = torch.from_numpy(Z1).to(eng.tdev); z2 = torch.from_numpy(Z2).to(eng.tdev)
+        S = eng.paths(model, M, N, "f64", E.RngSpec(z1=z1, z2=z2))
+        out[:, :M] = S.cpu().numpy()
+    if num_simulations % 2 != 0:  # om3:235-249: one extra, non-antithetic path
+        Zo = np.empty((2, N, 1))
+        for t in range(N):
+            Zo[0, t] = rng.standard_normal(1)
+            Zo[1, t] = rng.standard_normal(1)
+        z = torch.from_numpy(Zo).to(eng.tdev)
+        S = eng.paths(model, 1, N, "f64", E.RngSpec(z1=z[0].contiguous(), z2=z[1].contiguous(), antithetic=False))
+        out[:, M:] = S.cpu().numpy()
+    return out
+
+
+def simulate_bs_paths_torch(S0: float, r: float, T: float, sigma: float, num_simulations: int, num_time_steps: int,
+                            device, philox_seed: Optional[int] = None):
+    """om3gpu:117-148.  fp32, antithetic.  Default: Z_half = torch.randn(N, M//2, device=device) as the
+    reference draws it (so torch.manual_seed reproduces the reference's paths); philox_seed=int switches
+    to in-register Philox (nothing but S touches HBM)."""
+    import torch
+
+    eng = _engine(_dev_index(device))
+    M = num_simulations // 2 * 2
+    N = int(num_time_steps)
+    model = E.gbm(S0, r, T, sigma)
+    if philox_seed is not None:
+        S = eng.paths(model, M, N, "f32", E.RngSpec(seed=philox_seed))
+    else:
+        Zh = torch.randn(N, M // 2, device=eng.tdev)
+        S = eng.paths(model, M, N, "f32", E.RngSpec(z1=Zh))
+    if num_simulations % 2 != 0:  # om3gpu:141-146
+        Zo = torch.randn(N, 1, device=eng.tdev)
+        So = eng.paths(model, 1, N, "f32", E.RngSpec(z1=Zo, antithetic=False))
+        S = torch.cat([S, So], dim=1)
+    return S
+
+
+def simulate_bs_paths_torch_bandwidth_optimized(S0: float, r: float, T: float, sigma: float, num_simulations: int,
+                                                num_time_steps: int, device, philox_seed: Optional[int] = None):
+    """om3gpu:150-185: no antithetic, cumulative sum in log space, exp at the end (one launch here)."""
+    import torch
+
+    eng = _engine(_dev_index(device))
+    M, N = int(num_simulations), int(num_time_steps)
+    model = E.gbm(S0, r, T, sigma, scheme=L.SCHEME_GBM_LOGSPACE)
+    if philox_seed is not None:
+        return eng.paths(model, M, N, "f32", E.RngSpec(seed=philox_seed, antithetic=False))
+    Z = torch.randn(N, M, device=eng.tdev, dtype=torch.float32)
+    return eng.paths(model, M, N, "f32", E.RngSpec(z1=Z, antithetic=False))
+
+
+def simulate_heston_paths_torch(S0: float, r: float, T: float, v0: float, kappa: float, theta: float, xi: float,
+                                rho: float, num_simulations: int, num_time_steps: int, device,
+                                philox_seed: Optional[int] = None):
+    """om3gpu:187-248.  fp32 absorption Euler; per step z1_half then z2_half from torch.randn (om3gpu:209-210)."""
+    import torch
+
+    eng = _engine(_dev_index(device))
+    M = num_simulations // 2 * 2
+    N = int(num_time_steps)
+    model = E.heston(S0, r, T, v0, kappa, theta, xi, rho)
+    if philox_seed is not None:
+        S = eng.paths(model, M, N, "f32", E.RngSpec(seed=philox_seed))
+    else:
+        Z1 = torch.empty(N, M // 2, device=eng.tdev); Z2 = torch.empty(N, M // 2, device=eng.tdev)
+        for t in range(N):
+            Z1[t] = torch.randn(M // 2, device=eng.tdev)
+            Z2[t] = torch.randn(M // 2, device=eng.tdev)
+        S = eng.paths(model, M, N, "f32", E.RngSpec(z1=Z1, z2=Z2))
+    if num_simulations % 2 != 0:  # om3gpu:228-246
+        Zo = torch.empty(2, N, 1, device=eng.tdev)
+        for t in range(N):
+            Zo[0, t] = torch.randn(1, device=eng.tdev)
+            Zo[1, t] = torch.randn(1, device=eng.tdev)
+        So = eng.paths(model, 1, N, "f32", E.RngSpec(z1=Zo[0].contiguous(), z2=Zo[1].contiguous(), antithetic=False))
+        S = torch.cat([S, So], dim=1)
+    return S
+
+
+def create_regression_features(S, K, r, T, t_current):
+    """om3:105-121: numpy in, numpy [n, 7] fp64 out (computed by the features kernel)."""
+    import torch
+
+    eng = _engine()
+    Sd = torch.as_tensor(np.ascontiguousarray(np.asarray(S, dtype=np.float64))).to(eng.tdev)
+    return eng.features_ref7(Sd, K, r, T, t_current).cpu().numpy()
+
+
+def create_regression_features_torch(S_t, K: float, r: float, T: float, t_current: float):
+    """om3gpu:342-359: device tensor in, [n, 7] device tensor out, dtype preserved."""
+    eng = _engine(S_t.device.index or 0)
+    return eng.features_ref7(S_t.contiguous(), K, r, T, t_current)
+
+
+create_regression_features_torch_vectorized = create_regression_features_torch  # om3gpu:361-377 (same 7 columns)
+
+
+# ---------------------------------------------------------------------------------------------------
+# AdvancedOptionPricer (om3:339-713; GPU variant om3gpu:547-904)
+# ---------------------------------------------------------------------------------------------------
+class AdvancedOptionPricer:
+    def __init__(self, K: float, r: float, sigma: Optional[float], option_type: str = "call",
+                 rng_manager: Optional[RNGManager] = None, use_heston: bool = False,
+                 heston_params: Optional[Dict[str, Any]] = None, nn_hidden: int = 128, nn_epochs: int = 25,
+                 nn_lr: float = 1e-3, verbose: bool = False, iv_model=None, use_streaming: bool = True,
+                 chunk_size: int = 500, european_approximation: bool = False, use_control_variate: bool = True,
+                 nn_layers: int = 3, nn_dropout: float = 0.10,
+                 # engine extensions (not in the reference)
+                 lsm_regressor: str = "poly2", semantics: str = "reference", dtype: str = "f32", device: int = 0,
+                 gpu_reference_quirks: bool = False):
+        self.K = K
+        self.r = r
+        self.sigma = sigma
+        self.option_type = option_type
+        self.rng_manager = rng_manager or RNGManager()
+        self.use_heston = use_heston
+        self.heston_params = heston_params
+        self.nn_hidden, self.nn_epochs, self.nn_lr = nn_hidden, nn_epochs, nn_lr
+        self.nn_layers, self.nn_dropout = nn_layers, nn_dropout
+        self.verbose = verbose
+        self.iv_model = iv_model
+        self.use_streaming = use_streaming
+        self.chunk_size = chunk_size
+        self.european_approximation = european_approximation
+        self.use_control_variate = use_control_variate
+        self.lsm_regressor = lsm_regressor
+        self.semantics = semantics
+        self.dtype = dtype
+        self.device = device
+        self.gpu_reference_quirks = gpu_reference_quirks
+        self.last_result: Optional[E.SweepResult] = None
+
+    # om3:461-472 model routing
+    def _model(self, S0: float, T: float) -> E.ModelSpec:
+        if self.iv_model is not None:
+            raise NotImplementedError("local-volatility paths (iv_model) are not part of this round (SURVEY.md 8(f) n3)")
+        if self.use_heston and self.heston_params is not None:
+            hp = self.heston_params
+            return E.heston(S0, self.r, T, hp["v0"], hp["kappa"], hp["theta"], hp["xi"], hp["rho"])
+        if self.sigma is None:
+            raise ValueError("sigma is None: provide sigma, iv_model, or heston configuration")
+        return E.gbm(S0, self.r, T, self.sigma)
+
+    def price_american_enhanced_lsm(self, S0: float, T: float, num_simulations: int = 10000,
+                                    num_time_steps: int = 50) -> float:
+        """om3:439-651 with the polynomial regressor.  One path launch + one persistent sweep launch."""
+        if S0 <= 0 or self.K <= 0 or T <= 0:
+            raise ValueError("S0, K, T must be positive.")
+        if self.r < 0:
+            raise ValueError("r must be non-negative.")
+        if num_simulations <= 0 or num_time_steps <= 0:
+            raise ValueError("num_simulations and num_time_steps must be positive integers.")
+        seed = int(self.rng_manager.master_rng.integers(0, 2**31 - 1))  # om3:454: the child generator's seed
+        self.rng_manager.get_child_seed()                               # om3:455: torch.manual_seed draw
+        M = num_simulations // 2 * 2
+        if M == 0:
+            return float("nan")  # the reference averages an empty cash-flow vector
+        model = self._model(S0, T)
+        res = _engine(self.device).price_american(model, M, int(num_time_steps), self.K, self.option_type, self.dtype,
+                                                  E.RngSpec(seed=seed), basis=self.lsm_regressor,
+                                                  semantics=self.semantics, arrays=self.verbose)
+        self.last_result = res
+        return float(res.price)
+
+    def price_american_enhanced_lsm_gpu(self, S0: float, T: float, num_simulations: int = 10000,
+                                        num_time_steps: int = 50) -> float:
+        """om3gpu:655-839.  With gpu_reference_quirks=True also applies om3gpu:667-669 (step override for
+        T < 10 days) and om3gpu:675 (50 000-path cap); both are memory work-arounds of the reference."""
+        if S0 <= 0 or self.K <= 0 or T <= 0:
+            raise ValueError("S0, K, T must be positive.")
+        if self.gpu_reference_quirks:
+            if T < 10 / 365.0:
+                num_time_steps = max(10, min(25, int(T * 365 * 2)))
+            num_simulations = min(num_simulations, 50000)
+        return self.price_american_enhanced_lsm(S0, T, num_simulations, num_time_steps)
+
+    def price_european_streaming(self, S0: float, T: float, num_simulations: int = 10000,
+                                 num_time_steps: int = 50) -> float:
+        """om3:382-437.  One fused no-store launch replaces the 500-path chunk loop; the master generator
+        advances once per reference chunk (om3:392) so later calls see the same seed tree."""
+        n_chunks = max(1, -(-int(num_simulations) // int(self.chunk_size)))
+        seeds = [int(self.rng_manager.get_child_seed()) for _ in range(n_chunks)]
+        model = self._model(S0, T)
+        n = int(num_simulations)
+        anti = n % 2 == 0
+        mean, se = _engine(self.device).price_european_batch(model, n, int(num_time_steps), [self.K], [T],
+                                                             [1 if self.option_type == "put" else 0], self.dtype,
+                                                             E.RngSpec(seed=seeds[0], stream=0x45, antithetic=anti))
+        if self.verbose:
+            print(f"European streaming MC: {mean[0]:.4f} ± {se[0]:.4f} (n={n})")
+        return float(mean[0])
+
+    price_european_gpu = price_european_streaming  # om3gpu:605-653
+
+    def price_american_with_control_variate(self, S0: float, T: float, num_simulations: int = 10000,
+                                            num_time_steps: int = 50) -> float:
+        """om3:653-677: american + 1.0 * (BS_analytic - european_MC), European leg on independent paths."""
+        american_price = self.price_american_enhanced_lsm(S0, T, num_simulations, num_time_steps)
+        if not self.use_control_variate or self.sigma is None:
+            return american_price
+        european_mc = self.price_european_streaming(S0, T, num_simulations, num_time_steps)
+        european_analytical = BlackScholesGreeks.black_scholes_price(S0, self.K, T, self.r, self.sigma, self.option_type)
+        american_cv = american_price + 1.0 * (european_analytical - european_mc)
+        if self.verbose:
+            print(f"American: {american_price:.4f}, European MC: {european_mc:.4f}, "
+                  f"European Analytical: {european_analytical:.4f}, CV Adjusted: {american_cv:.4f}")
+        return american_cv
+
+    def price_american_option(self, S0: float, T: float, num_simulations: int = 10000, num_time_steps: int = 50,
+                              plot_paths: bool = False) -> float:
+        """om3:679-695 routing."""
+        if self.use_streaming and self.european_approximation:
+            if self.verbose:
+                print("WARNING: Using European approximation for American option (streaming mode)")
+            return self.price_european_streaming(S0, T, num_simulations, num_time_steps)
+        if self.use_control_variate and self.sigma is not None:
+            return self.price_american_with_control_variate(S0, T, num_simulations, num_time_steps)
+        return self.price_american_enhanced_lsm(S0, T, num_simulations, num_time_steps)
+
+    def compute_curve_for_S0(self, S0: float, intervals_per_day: int, total_points: int, num_simulations: int,
+                             plot_paths: bool) -> List[Dict[str, Any]]:
+        """om3:697-713."""
+        records = []
+        for i in range(total_points, 0, -1):
+            d = i / intervals_per_day
+            T = d / 365
+            steps = max(10, min(130, int(np.ceil(d))))
+            est_price = self.price_american_option(S0, T, num_simulations, steps, plot_paths)
+            records.append({"S0": S0, "Days to Expiry": d, "Option Value": est_price})
+        return records
+
+
+def compute_curve_worker_enhanced(S0, K, r, sigma, option_type, worker_seed, intervals_per_day, total_points,
+                                  num_simulations, plot_paths, use_heston, heston_params, nn_hidden=128, nn_epochs=25,
+                                  nn_lr=1e-3, verbose=False, european_approximation=False, use_control_variate=True):
+    """om3:719-739: errors are logged and an empty list is returned, as in the reference."""
+    try:
+        pricer = AdvancedOptionPricer(K, r, sigma, option_type, RNGManager(worker_seed), use_heston, heston_params,
+                                      nn_hidden=nn_hidden, nn_epochs=nn_epochs, nn_lr=nn_lr, verbose=verbose,
+                                      european_approximation=european_approximation,
+                                      use_control_variate=use_control_variate)
+        return pricer.compute_curve_for_S0(S0, intervals_per_day, total_points, num_simulations, plot_paths)
+    except Exception as e:  # noqa: BLE001 -- reference behaviour (om3:737-739)
+        logging.error(f"Error in enhanced worker for S0={S0}: {e}")
+        return []
+
+
+compute_curve_worker_gpu = compute_curve_worker_enhanced  # om3gpu:910-932 (same argument list)
+
+
+def compute_multiple_S0_gpu_batch(s0_list, K, r, sigma, option_type, intervals_per_day, total_points,
+                                  num_simulations, nn_hidden=128, nn_epochs=25, nn_lr=1e-3, verbose=False,
+                                  european_approximation=False, use_control_variate=True, seed=42):
+    """om3gpu:934-956: one pricer reused across the S0 list."""
+    pricer = AdvancedOptionPricer(K, r, sigma, option_type, RNGManager(seed), nn_hidden=nn_hidden,
+                                  nn_epochs=nn_epochs, nn_lr=nn_lr, verbose=verbose,
+                                  european_approximation=european_approximation,
+                                  use_control_variate=use_control_variate)
+    records = []
+    for S0 in s0_list:
+        records.extend(pricer.compute_curve_for_S0(S0, intervals_per_day, total_points, num_simulations, False))
+    return records
+
+
+# ---------------------------------------------------------------------------------------------------
+# older API the Streamlit UIs import (om2:176-457, om1:44-211)
+# ---------------------------------------------------------------------------------------------------
+class OptionPricer:
+    """om2:176-355.  lsm_poly_degree is honoured here (2 or 3); the reference validates and ignores it."""
+
+    def __init__(self, K: float, r: float, sigma: Optional[float], option_type: str = "call",
+                 lsm_poly_degree: int = 2, seed: int = 42, use_heston: bool = False,
+                 heston_params: Optional[Dict[str, Any]] = None, nn_hidden: int = 32, nn_epochs: int = 10,
+                 nn_lr: float = 1e-3, verbose: bool = False):
+        self.K, self.r, self.sigma, self.option_type = K, r, sigma, option_type
+        self.lsm_poly_degree, self.seed = lsm_poly_degree, seed
+        self.use_heston, self.heston_params = use_heston, heston_params
+        self.nn_hidden, self.nn_epochs, self.nn_lr, self.verbose = nn_hidden, nn_epochs, nn_lr, verbose
+
+    def price_american_option(self, S0: float, T: float, num_simulations: int = 10000, num_time_steps: int = 50,
+                              plot_paths: bool = False) -> float:
+        if S0 <= 0 or self.K <= 0 or T <= 0 or (self.sigma is None and not self.use_heston):
+            raise ValueError("S0, K, T, and sigma must be positive.")
+        if self.r < 0:
+            raise ValueError("r must be non-negative.")
+        if num_simulations <= 0 or num_time_steps <= 0:
+            raise ValueError("num_simulations and num_time_steps must be positive integers.")
+        if self.lsm_poly_degree < 0 or not isinstance(self.lsm_poly_degree, int):
+            raise ValueError("lsm_poly_degree must be a non-negative integer.")
+        if self.option_type not in ("call", "put"):
+            raise ValueError("option_type must be 'call' or 'put'.")
+        M = num_simulations // 2 * 2
+        if self.use_heston and self.heston_params is not None:
+            hp = self.heston_params
+            model = E.heston(S0, self.r, T, hp["v0"], hp["kappa"], hp["theta"], hp["xi"], hp["rho"])
+        else:
+            model = E.gbm(S0, self.r, T, self.sigma)
+        basis = "poly3" if self.lsm_poly_degree >= 3 else "poly2"
+        res = _engine().price_american(model, M, int(num_time_steps), self.K, self.option_type, "f32",
+                                       E.RngSpec(seed=int(self.seed)), basis=basis)
+        return float(res.price)
+
+    def compute_curve_for_S0(self, S0, intervals_per_day, total_points, num_simulations, plot_paths):
+        records = []
+        for i in range(total_points, 0, -1):  # om2:346-354
+            d = i / intervals_per_day
+            T = d / 365
+            steps = max(10, min(130, int(np.ceil(d))))
+            records.append({"S0": S0, "Days to Expiry": d,
+                            "Option Value": self.price_american_option(S0, T, num_simulations, steps, plot_paths)})
+        return records
+
+
+def compute_curve_worker(S0, K, r, sigma, option_type, lsm_poly_degree, seed, intervals_per_day, total_points,
+                         num_simulations, plot_paths, use_heston, heston_params, nn_hidden=32, nn_epochs=10,
+                         nn_lr=1e-3, verbose=False):
+    """om2:443-457."""
+    try:
+        pricer = OptionPricer(K, r, sigma, option_type, lsm_poly_degree, seed, use_heston, heston_params, nn_hidden,
+                              nn_epochs, nn_lr, verbose)
+        return pricer.compute_curve_for_S0(S0, intervals_per_day, total_points, num_simulations, plot_paths)
+    except Exception as e:  # noqa: BLE001 -- om2:455-457
+        logging.error(f"Error in worker for S0={S0}: {e}")
+        return []
+
+
+# ---------------------------------------------------------------------------------------------------
+# Heston calibration pricer (hc:34-90, hc:197-312)
+# ---------------------------------------------------------------------------------------------------
+@dataclass
+class HestonParams:
+    kappa: float
+    theta: float
+    sigma: float
+    rho: float
+    v0: float
+
+    def __post_init__(self):  # hc:43-54
+        if not (0 < self.kappa < 20):
+            raise ValueError(f"kappa={self.kappa} must be in (0, 20)")
+        if not (0 < self.theta < 2):
+            raise ValueError(f"theta={self.theta} must be in (0, 2)")
+        if not (0 < self.sigma < 3):
+            raise ValueError(f"sigma={self.sigma} must be in (0, 3)")
+        if not (-1 < self.rho < 1):
+            raise ValueError(f"rho={self.rho} must be in (-1, 1)")
+        if not (0 < self.v0 < 2):
+            raise ValueError(f"v0={self.v0} must be in (0, 2)")
+
+    def to_array(self) -> np.ndarray:
+        return np.array([self.kappa, self.theta, self.sigma, self.rho, self.v0])
+
+    @classmethod
+    def from_array(cls, x: np.ndarray) -> "HestonParams":
+        return cls(kappa=x[0], theta=x[1], sigma=x[2], rho=x[3], v0=x[4])
+
+    def feller_condition(self) -> bool:
+        return 2 * self.kappa * self.theta >= self.sigma**2
+
+
+@dataclass
+class CalibrationConfig:  # hc:75-90
+    use_vega_weighting: bool = True
+    min_vega_weight: float = 0.01
+    max_iterations: int = 2000
+    tolerance: float = 1e-8
+    n_mc_paths: int = 100000
+    n_time_steps: int = 100
+    use_antithetic: bool = True
+    seed: int = 42
+    verbose: bool = True
+    plot_results: bool = True
+    optimization_methods: List[str] = field(default_factory=lambda: ["L-BFGS-B", "differential_evolution", "dual_annealing"])
+    fallback_enabled: bool = True
+    regime_detection: bool = True
+
+
+class HestonPricer:
+    """hc:197-312.  simulate_paths draws from the persistent numpy generator exactly as the reference
+    (hc:226-227) and returns path-major arrays; the pricing methods use the fused no-store kernel with
+    Philox keyed from that generator (one integer draw per call), unless reference_draws=True."""
+
+    def __init__(self, config: CalibrationConfig, reference_draws: bool = False, dtype: str = "f32", device: int = 0):
+        self.config = config
+        self.rng = np.random.default_rng(config.seed)
+        self.reference_draws = reference_draws
+        self.dtype = dtype
+        self.device = device
+
+    def _model(self, params: HestonParams, S0: float, T: float, r: float) -> E.ModelSpec:
+        return E.heston(S0, r, T, params.v0, params.kappa, params.theta, params.sigma, params.rho,
+                        scheme=L.SCHEME_HESTON_REF_CALIB)
+
+    def _simulate_device(self, params: HestonParams, S0: float, T: float, r: float):
+        """Draw (Z1, Z2_indep) from the persistent generator as hc:226-227 does, step the calibrator
+        scheme on the device in fp64.  Returns step-major device slabs S, V [(N+1), M] and M."""
+        import torch
+
+        eng = _engine(self.device)
+        n_paths, N = self.config.n_mc_paths, self.config.n_time_steps
+        anti = bool(self.config.use_antithetic)
+        n_sim = n_paths // 2 if anti else n_paths
+        Z1 = self.rng.standard_normal((n_sim, N))
+        Z2i = self.rng.standard_normal((n_sim, N))
+        z1 = torch.from_numpy(Z1).to(eng.tdev).t().contiguous()   # step-major [N][n_sim]
+        z2 = torch.from_numpy(Z2i).to(eng.tdev).t().contiguous()
+        M = 2 * n_sim if anti else n_sim
+        S, V = eng.paths(self._model(params, S0, T, r), M, N, "f64", E.RngSpec(z1=z1, z2=z2, antithetic=anti),
+                         return_v=True)
+        return S, V, M
+
+    def simulate_paths(self, params: HestonParams, S0: float, T: float, r: float = 0.05) -> Tuple[np.ndarray, np.ndarray]:
+        n_paths, N = self.config.n_mc_paths, self.config.n_time_steps
+        S, V, M = self._simulate_device(params, S0, T, r)
+        Sh = np.zeros((n_paths, N + 1)); Vh = np.zeros((n_paths, N + 1))
+        Sh[:M] = S.t().cpu().numpy(); Vh[:M] = V.t().cpu().numpy()   # path-major, as hc:216-217
+        if M < n_paths:  # odd n_paths with antithetic: the reference's vstack would fail; keep the row at S0/v0
+            Sh[M:, 0] = S0; Vh[M:, 0] = params.v0
+        return Sh, Vh
+
+    def price_european_option(self, params: HestonParams, S0: float, K: float, T: float, r: float = 0.05,
+                              option_type: str = "call") -> float:
+        try:
+            ot = option_type.lower()
+            if ot not in ("call", "put"):
+                raise ValueError(f"Unknown option type: {option_type}")
+            if self.reference_draws:
+                S, _, M = self._simulate_device(params, S0, T, r)
+                mean, _ = _engine(self.device).european_from_slab(S[self.config.n_time_steps].contiguous(), K, r, T, ot)
+                return float(mean)
+            seed = int(self.rng.integers(0, 2**63 - 1))
+            mean, _ = _engine(self.device).price_european_batch(
+                self._model(params, S0, T, r), self.config.n_mc_paths // 2 * 2 if self.config.use_antithetic
+                else self.config.n_mc_paths, self.config.n_time_steps, [K], [T], [1 if ot == "put" else 0], self.dtype,
+                E.RngSpec(seed=seed, antithetic=bool(self.config.use_antithetic)))
+            return float(mean[0])
+        except Exception as e:  # noqa: BLE001 -- hc:279-281
+            print(f"Warning: Pricing failed for K={K}, T={T}: {e}")
+            return float("nan")
+
+    def price_options_batch(self, params: HestonParams, S0: float, K_array: np.ndarray, T_array: np.ndarray,
+                            r: float = 0.05) -> np.ndarray:
+        """hc:283-312: call options only (hc:305); options with the same T share one set of paths."""
+        K_array = np.asarray(K_array, dtype=np.float64)
+        T_array = np.asarray(T_array, dtype=np.float64)
+        prices = np.zeros(len(K_array))
+        if len(K_array) == 0:
+            return prices
+        try:
+            uniq, inv = np.unique(T_array, return_inverse=True)
+            seed = int(self.rng.integers(0, 2**63 - 1))
+            M = self.config.n_mc_paths // 2 * 2 if self.config.use_antithetic else self.config.n_mc_paths
+            mean, _ = _engine(self.device).price_european_batch(
+                self._model(params, S0, float(T_array[0]), r), M, self.config.n_time_steps, K_array, T_array,
+                np.zeros(len(K_array), dtype=np.int32), self.dtype,
+                E.RngSpec(seed=seed, antithetic=bool(self.config.use_antithetic)), stream_id=inv.astype(np.int32))
+            prices[:] = mean
+        except Exception as e:  # noqa: BLE001 -- hc:308-310
+            print(f"Warning: Batch pricing failed: {e}")
+            prices[:] = np.nan
+        return prices

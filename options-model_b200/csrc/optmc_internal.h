@@ -1,0 +1,102 @@
+// optmc_internal.h -- context layout and launcher prototypes shared by the translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/optmc.h"
+
+namespace optmc {
+
+constexpr int kXchgSlotDoubles = 16;  // one 128-byte line per CTA: [0..14] payload, [15] epoch
+constexpr int kMaxResidentCtas = 160; // gather handles 5 slots per lane
+constexpr int kResThreads = 512;
+constexpr int kMaxBeta = 4;
+
+struct SweepDesc {  // the sweep currently bound to the context (begin/gram/update/finish/fetch)
+  const void* S = nullptr;
+  int64_t ld = 0, M = 0;
+  int32_t N = 0, dtype = 0;
+  optmc_lsm_params lp{};
+  int deg = 2;
+  double disc = 1.0, final_scale = 1.0;
+  int impl_used = 0;
+  int n_launches = 0;
+  bool have_results = false;
+  bool finals_on_device = false;
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define OPTMC_CUDA(call)                                        \
+  do {                                                          \
+    cudaError_t _e = (call);                                    \
+    if (_e != cudaSuccess) return ::optmc::cuda_fail(_e, #call); \
+  } while (0)
+
+}  // namespace optmc
+
+struct optmc_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int64_t l2_bytes = 0;
+  int max_smem_optin = 0;
+  int cc = 0;
+  int64_t launches = 0;
+
+  // grow-only device workspaces
+  void* slab = nullptr;      size_t slab_bytes = 0;      // price_american path slab
+  void* cf = nullptr;        size_t cf_bytes = 0;        // split sweep cash-flows
+  double* partials = nullptr; size_t partials_bytes = 0; // [grid][Q] block partials (gram / final / european)
+  unsigned int* tickets = nullptr;                        // last-block tickets [1024]
+  double* gram = nullptr;                                 // [16] reduced moments of the current date
+  double* d_betas = nullptr;   // [(N+1)][kMaxBeta]
+  unsigned long long* d_bnd = nullptr;  // [(N+1)] boundary as double bits
+  unsigned long long* d_exc = nullptr;  // [(N+1)]
+  long long* d_nitm = nullptr;          // [(N+1)]
+  int* d_valid = nullptr;               // [(N+1)]
+  size_t per_date_cap = 0;              // N+1 capacity of the per-date arrays
+  double* d_final = nullptr;            // [4] price, stderr, sum, sumsq
+  double* xchg = nullptr;               // [2][kMaxResidentCtas][kXchgSlotDoubles]
+  unsigned long long epoch = 0;
+  double* eu_out = nullptr; size_t eu_out_cap = 0;  // [n_options][3]
+  double* eu_par = nullptr; size_t eu_par_cap = 0;  // [n_options][4] K, T, is_put, pad
+  unsigned int* eu_tickets = nullptr; size_t eu_tickets_cap = 0;
+
+  optmc::SweepDesc sw;
+};
+
+namespace optmc {
+
+int ensure_bytes(void** p, size_t* cap, size_t need);
+int ensure_per_date(optmc_ctx* ctx, int N);
+
+// paths.cu
+int launch_paths(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M, int32_t N,
+                 int32_t dtype, void* S, void* V, int64_t ld);
+int launch_philox_normals(optmc_ctx* ctx, const optmc_rng_params* rng, int32_t model, int64_t M, int32_t N,
+                          int32_t which, int32_t dtype, void* Z);
+int launch_philox_kat(optmc_ctx* ctx, int n, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
+int launch_features(optmc_ctx* ctx, const void* S, int64_t n, int32_t dtype, double K, double T, double t_current,
+                    void* F);
+
+// lsm.cu
+int sweep_begin(optmc_ctx* ctx);                                    // split: cf = payoff(S[N])
+int sweep_gram_date(optmc_ctx* ctx, int t, double* gram_out);       // split: local moments of date t
+int sweep_update_date(optmc_ctx* ctx, int t, const double* gram);   // split: solve + decide + discount
+int sweep_finish(optmc_ctx* ctx, double* sums_out);                 // split: sum(cf), sum(cf^2), n
+int sweep_finalize_price(optmc_ctx* ctx, const double* sums);       // split: d_final from sums
+bool resident_eligible(optmc_ctx* ctx, const SweepDesc& sw, std::string* why);
+int sweep_resident(optmc_ctx* ctx);                                 // one cooperative launch, all dates
+
+// european.cu
+int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                          int32_t N, int32_t dtype, int32_t n_options, const double* K, const double* T,
+                          const int32_t* is_put, const int32_t* stream_id, optmc_european_result* results);
+int launch_european_slab(optmc_ctx* ctx, const void* ST, int64_t M, int32_t dtype, double K, double r, double T,
+                         int32_t is_put, optmc_european_result* out);
+
+}  // namespace optmc

@@ -1,0 +1,265 @@
+// optmc_math.cuh -- scalar building blocks shared by every kernel (and host-compilable for unit tests).
+//
+// Everything here is per-path arithmetic: Philox4x32-10, uniform->normal transforms, the one-step
+// updates of each path scheme, payoff, the Gram accumulators and the guarded LDL^T solve.
+// Reference citations: om3 = options_model_3/options_model_3.py, om3gpu = option_model_3_gpu.py,
+// hc = heston_calibration.py (all under the reference tree).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define OPTMC_HD __host__ __device__ __forceinline__
+#else
+#define OPTMC_HD inline
+#endif
+
+namespace optmc {
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., Random123).  KATs: SURVEY.md App. A-7 / tests/test_philox.py.
+// ------------------------------------------------------------------------------------------------
+struct Philox4 {
+  uint32_t v[4];
+};
+
+OPTMC_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+OPTMC_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox4 r;
+  r.v[0] = c0; r.v[1] = c1; r.v[2] = c2; r.v[3] = c3;
+  return r;
+}
+
+// Counter layout (results are independent of launch geometry and GPU count):
+//   ctr = (pair_lo, pair_hi, step_block, stream), key = (seed_lo, seed_hi).
+//   Heston: step_block b yields (z1,z2) for steps 2b+1 and 2b+2;  GBM: z for steps 4b+1..4b+4.
+OPTMC_HD Philox4 philox_for(uint64_t pair, uint32_t step_block, uint32_t stream, uint64_t seed) {
+  return philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), step_block, stream, (uint32_t)seed,
+                       (uint32_t)(seed >> 32));
+}
+
+// ------------------------------------------------------------------------------------------------
+// small float helpers
+// ------------------------------------------------------------------------------------------------
+OPTMC_HD float u32_as_f32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float(x);
+#else
+  union { uint32_t u; float f; } c; c.u = x; return c.f;
+#endif
+}
+
+template <typename R> struct Real;  // per-precision math: device fast paths for float, IEEE for double
+
+template <> struct Real<float> {
+  static OPTMC_HD float exp_(float x) {
+#if defined(__CUDA_ARCH__)
+    return __expf(x);
+#else
+    return expf(x);
+#endif
+  }
+  static OPTMC_HD float sqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+#else
+    return sqrtf(x);
+#endif
+  }
+  // Box-Muller on two 32-bit words -> two N(0,1).  Uniforms built by mantissa stuffing (no I2F):
+  // u in (0,1] with 2^-23 resolution (|z| <= 5.65), angle v in [0,1).
+  static OPTMC_HD void normal2(uint32_t a, uint32_t b, float& n0, float& n1) {
+    float u = 2.0f - u32_as_f32(0x3f800000u | (a >> 9));
+    float v = u32_as_f32(0x3f800000u | (b >> 9)) - 1.0f;
+#if defined(__CUDA_ARCH__)
+    float rad = sqrt_(-1.3862943611198906f * __log2f(u));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
+    float s, c;
+    __sincosf(6.283185307179586f * v, &s, &c);
+#else
+    float rad = sqrtf(-2.0f * logf(u));
+    float s = sinf(6.283185307179586f * v), c = cosf(6.283185307179586f * v);
+#endif
+    n0 = rad * c;
+    n1 = rad * s;
+  }
+};
+
+template <> struct Real<double> {
+  static OPTMC_HD double exp_(double x) { return exp(x); }
+  static OPTMC_HD double sqrt_(double x) { return sqrt(x); }
+  static OPTMC_HD void normal2(uint32_t a, uint32_t b, double& n0, double& n1) {
+    double u = ((double)a + 1.0) * 2.3283064365386963e-10;  // (0,1]
+    double v = (double)b * 2.3283064365386963e-10;          // [0,1)
+    double rad = sqrt(-2.0 * log(u));
+    double s, c;
+#if defined(__CUDA_ARCH__)
+    sincospi(2.0 * v, &s, &c);
+#else
+    s = sin(6.283185307179586 * v); c = cos(6.283185307179586 * v);
+#endif
+    n0 = rad * c;
+    n1 = rad * s;
+  }
+};
+
+template <typename R> OPTMC_HD R rmax(R a, R b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------
+// one-step path updates
+// ------------------------------------------------------------------------------------------------
+template <typename R> struct GbmConsts {
+  R drift, diffusion;  // (r - sigma^2/2) dt, sigma sqrt(dt)   (om3:473-474)
+};
+
+// om3:480  S[t] = S[t-1] * exp(drift + diffusion * Z[t-1])
+template <typename R> OPTMC_HD R gbm_step(R S, R z, const GbmConsts<R>& c) {
+  return S * Real<R>::exp_(c.drift + c.diffusion * z);
+}
+
+template <typename R> struct HestonConsts {
+  R dt, sqrt_dt, r, kappa, theta, xi, rho, rho_c;  // rho_c = sqrt(1 - rho^2)
+};
+
+// om3:228-233 (absorption Euler).  z1, z2 independent N(0,1); w2 = rho z1 + sqrt(1-rho^2) z2.
+template <typename R> OPTMC_HD void heston_absorb_step(R& S, R& v, R z1, R z2, const HestonConsts<R>& c) {
+  R w2 = c.rho * z1 + c.rho_c * z2;
+  R vp = rmax(v, (R)0);
+  R sq = Real<R>::sqrt_(vp * c.dt);
+  R vn = vp + c.kappa * (c.theta - vp) * c.dt + c.xi * sq * w2;
+  v = rmax(vn, (R)0);
+  S = S * Real<R>::exp_((c.r - (R)0.5 * vp) * c.dt + sq * z1);
+}
+
+// Lord-Koekkoek-van Dijk full truncation: v may go negative, v+ enters drift and diffusion.
+template <typename R> OPTMC_HD void heston_fulltrunc_step(R& S, R& v, R z1, R z2, const HestonConsts<R>& c) {
+  R w2 = c.rho * z1 + c.rho_c * z2;
+  R vp = rmax(v, (R)0);
+  R sq = Real<R>::sqrt_(vp * c.dt);
+  S = S * Real<R>::exp_((c.r - (R)0.5 * vp) * c.dt + sq * z1);
+  v = v + c.kappa * (c.theta - vp) * c.dt + c.xi * sq * w2;
+}
+
+// hc:240-255 (calibrator): variance floored at 1e-8, arithmetic Euler on S.
+template <typename R> OPTMC_HD void heston_calib_step(R& S, R& v, R z1, R z2, const HestonConsts<R>& c) {
+  R w2 = c.rho * z1 + c.rho_c * z2;
+  R vp = rmax(v, (R)1e-8);
+  R sqv = Real<R>::sqrt_(vp);
+  R dV = c.kappa * (c.theta - vp) * c.dt + c.xi * sqv * c.sqrt_dt * w2;
+  v = rmax(vp + dV, (R)1e-8);
+  R dS = c.r * S * c.dt + sqv * S * c.sqrt_dt * z1;
+  S = S + dS;
+}
+
+// om3:376-380
+template <typename R> OPTMC_HD R payoff(R S, R K, bool is_put) {
+  R d = is_put ? K - S : S - K;
+  return d > (R)0 ? d : (R)0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Polynomial-basis Gram moments and the guarded solve.
+//   basis phi_i = x^i, i = 0..DEG, x = S/K.   G_ij = m[i+j], g_i = gy[i].
+//   moment vector layout (length 3*DEG+2):  m[0..2DEG] = sum x^k,  then gy[0..DEG] = sum x^k y.
+// ------------------------------------------------------------------------------------------------
+template <int DEG> struct Moments {
+  static constexpr int NM = 2 * DEG + 1;
+  static constexpr int NG = DEG + 1;
+  static constexpr int Q = NM + NG;
+};
+
+template <int DEG> OPTMC_HD void moments_accumulate(double (&acc)[Moments<DEG>::Q], double x, double y) {
+  double p = 1.0;
+#pragma unroll
+  for (int k = 0; k <= 2 * DEG; ++k) {
+    acc[k] += p;
+    if (k <= DEG) acc[Moments<DEG>::NM + k] += p * y;
+    p *= x;
+  }
+}
+
+#define OPTMC_PIVOT_RTOL 1e-14
+
+// LDL^T without pivoting; returns false (no exercise at this date) when n < p or a pivot
+// d_k <= 1e-14 * trace(G).  Identical recurrence to oracle.lsm_oracle.cholesky_solve_guarded.
+template <int DEG> OPTMC_HD bool solve_poly(const double* mom, double* beta) {
+  constexpr int P = DEG + 1;
+  constexpr int NM = 2 * DEG + 1;
+  if (!(mom[0] >= (double)P)) return false;
+  double L[P][P];
+  double d[P];
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < P; ++i) tr += mom[2 * i];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    double s = mom[2 * k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) s -= L[k][j] * L[k][j] * d[j];
+    if (!(s > OPTMC_PIVOT_RTOL * tr)) return false;
+    d[k] = s;
+#pragma unroll
+    for (int i = k + 1; i < P; ++i) {
+      double u = mom[i + k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) u -= L[i][j] * L[k][j] * d[j];
+      L[i][k] = u / s;
+    }
+  }
+  double z[P];
+#pragma unroll
+  for (int i = 0; i < P; ++i) {
+    double a = mom[NM + i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) a -= L[i][j] * z[j];
+    z[i] = a;
+  }
+#pragma unroll
+  for (int i = 0; i < P; ++i) z[i] = z[i] / d[i];
+#pragma unroll
+  for (int i = P - 1; i >= 0; --i) {
+    double a = z[i];
+#pragma unroll
+    for (int j = i + 1; j < P; ++j) a -= L[j][i] * beta[j];
+    beta[i] = a;
+  }
+  return true;
+}
+
+template <int DEG> OPTMC_HD double poly_eval(const double* beta, double x) {
+  double c = beta[DEG];
+#pragma unroll
+  for (int i = DEG - 1; i >= 0; --i) c = c * x + beta[i];
+  return c;
+}
+
+// om3:105-121 -- the seven reference features of one path.
+template <typename R> OPTMC_HD void features_ref7(R S, R K, R tau_sqrt, R* f) {
+  R x = S / K;
+  f[0] = (R)1;
+  f[1] = x;
+  f[2] = x * x;
+  f[3] = x * x * x;
+  f[4] = rmax(x - (R)1, (R)0);
+  f[5] = tau_sqrt;
+  f[6] = x * tau_sqrt;
+}
+
+}  // namespace optmc

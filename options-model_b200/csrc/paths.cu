@@ -1,0 +1,286 @@
+// paths.cu -- K1: path generation.  One thread owns VEC antithetic pairs for all N steps; the Philox
+// counter, Box-Muller normals, the variance and the running price live in registers; the only HBM
+// traffic is one coalesced (128-bit when aligned) store of S[t][j] per path per step.
+//
+// Replaces: om3:473-480 (GBM), om3:211-233 (Heston, absorption Euler), om3gpu:117-248 (fp32 variants),
+// hc:204-257 (calibrator scheme, step-major here).
+#include "optmc_device.cuh"
+#include "optmc_internal.h"
+#include "optmc_math.cuh"
+
+namespace optmc {
+
+struct PathArgs {
+  void* S;
+  void* V;
+  long long ld, Mh;
+  int N, anti;
+  const void* z1;
+  const void* z2;
+  int z_f64;
+  unsigned long long seed;
+  unsigned int stream;
+  long long pair_offset;
+  double S0, v0;
+  double g_drift, g_diff;
+  double dt, sqrt_dt, r, kappa, theta, xi, rho, rho_c;
+};
+
+template <typename R>
+__device__ __forceinline__ void philox_block_normals(unsigned long long pair, unsigned int blk, unsigned int stream,
+                                                     unsigned long long seed, R (&n)[4]) {
+  Philox4 p = philox_for(pair, blk, stream, seed);
+  Real<R>::normal2(p.v[0], p.v[1], n[0], n[1]);
+  Real<R>::normal2(p.v[2], p.v[3], n[2], n[3]);
+}
+
+__device__ __forceinline__ double load_z(const void* z, int is_f64, long long idx) {
+  return is_f64 ? static_cast<const double*>(z)[idx] : (double)static_cast<const float*>(z)[idx];
+}
+
+template <typename R, int SCHEME> __device__ __forceinline__ void heston_step(R& S, R& v, R z1, R z2,
+                                                                              const HestonConsts<R>& c) {
+  if (SCHEME == OPTMC_SCHEME_HESTON_REF_ABSORB) heston_absorb_step<R>(S, v, z1, z2, c);
+  else if (SCHEME == OPTMC_SCHEME_HESTON_FULL_TRUNC) heston_fulltrunc_step<R>(S, v, z1, z2, c);
+  else heston_calib_step<R>(S, v, z1, z2, c);
+}
+
+template <typename R, int SCHEME, int VEC, bool EXTZ>
+__global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
+  constexpr bool HES = (SCHEME >= OPTMC_SCHEME_HESTON_REF_ABSORB);
+  constexpr bool LOGSPACE = (SCHEME == OPTMC_SCHEME_GBM_LOGSPACE);
+  constexpr int SPB = HES ? 2 : 4;  // steps served by one Philox block
+  const long long c0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (c0 >= a.Mh) return;
+  const bool anti = a.anti != 0;
+
+  GbmConsts<R> gc;
+  gc.drift = (R)a.g_drift;
+  gc.diffusion = (R)a.g_diff;
+  HestonConsts<R> hc;
+  hc.dt = (R)a.dt; hc.sqrt_dt = (R)a.sqrt_dt; hc.r = (R)a.r; hc.kappa = (R)a.kappa; hc.theta = (R)a.theta;
+  hc.xi = (R)a.xi; hc.rho = (R)a.rho; hc.rho_c = (R)a.rho_c;
+
+  R sp[VEC], sm[VEC], vp[VEC], vm[VEC], out[VEC];
+  const R s_init = LOGSPACE ? (R)log(fmax(a.S0, 1e-12)) : (R)a.S0;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    sp[i] = s_init; sm[i] = s_init; vp[i] = (R)a.v0; vm[i] = (R)a.v0;
+  }
+  R* Srow = static_cast<R*>(a.S) + c0;
+  R* Vrow = a.V ? static_cast<R*>(a.V) + c0 : nullptr;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) out[i] = LOGSPACE ? Real<R>::exp_(sp[i]) : sp[i];
+  VecIO<R, VEC>::store(Srow, out);
+  if (anti) VecIO<R, VEC>::store(Srow + a.Mh, out);
+  if (HES && Vrow) {
+    VecIO<R, VEC>::store(Vrow, vp);
+    if (anti) VecIO<R, VEC>::store(Vrow + a.Mh, vp);
+  }
+
+  for (int t0 = 0; t0 < a.N; t0 += SPB) {
+    R nrm[VEC][4];
+    if (!EXTZ) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i)
+        philox_block_normals<R>((unsigned long long)(a.pair_offset + c0 + i), (unsigned int)(t0 / SPB), a.stream,
+                                a.seed, nrm[i]);
+    }
+#pragma unroll
+    for (int s = 0; s < SPB; ++s) {
+      const int t = t0 + s + 1;
+      if (t > a.N) break;
+      R z1[VEC], z2[VEC];
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        if (EXTZ) {
+          const long long idx = (long long)(t - 1) * a.Mh + c0 + i;
+          z1[i] = (R)load_z(a.z1, a.z_f64, idx);
+          z2[i] = HES ? (R)load_z(a.z2, a.z_f64, idx) : (R)0;
+        } else {
+          z1[i] = HES ? nrm[i][2 * s] : nrm[i][s];
+          z2[i] = HES ? nrm[i][2 * s + 1] : (R)0;
+        }
+      }
+      Srow += a.ld;
+      if (Vrow) Vrow += a.ld;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        if (HES) heston_step<R, SCHEME>(sp[i], vp[i], z1[i], z2[i], hc);
+        else if (LOGSPACE) sp[i] = sp[i] + (gc.drift + gc.diffusion * z1[i]);
+        else sp[i] = gbm_step<R>(sp[i], z1[i], gc);
+        out[i] = LOGSPACE ? Real<R>::exp_(sp[i]) : sp[i];
+      }
+      VecIO<R, VEC>::store(Srow, out);
+      if (HES && Vrow) VecIO<R, VEC>::store(Vrow, vp);
+      if (anti) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          if (HES) heston_step<R, SCHEME>(sm[i], vm[i], -z1[i], -z2[i], hc);
+          else if (LOGSPACE) sm[i] = sm[i] + (gc.drift - gc.diffusion * z1[i]);
+          else sm[i] = gbm_step<R>(sm[i], -z1[i], gc);
+          out[i] = LOGSPACE ? Real<R>::exp_(sm[i]) : sm[i];
+        }
+        VecIO<R, VEC>::store(Srow + a.Mh, out);
+        if (HES && Vrow) VecIO<R, VEC>::store(Vrow + a.Mh, vm);
+      }
+    }
+  }
+}
+
+template <typename R, int SCHEME, int VEC> static int launch_t3(optmc_ctx* ctx, const PathArgs& a, bool extz) {
+  const long long threads = (a.Mh + VEC - 1) / VEC;
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  if (extz) paths_kernel<R, SCHEME, VEC, true><<<grid, 256, 0, ctx->stream>>>(a);
+  else paths_kernel<R, SCHEME, VEC, false><<<grid, 256, 0, ctx->stream>>>(a);
+  ctx->launches++;
+  OPTMC_CUDA(cudaGetLastError());
+  return OPTMC_OK;
+}
+
+template <typename R, int SCHEME> static int launch_t2(optmc_ctx* ctx, const PathArgs& a, bool extz, bool vec4) {
+  return vec4 ? launch_t3<R, SCHEME, 4>(ctx, a, extz) : launch_t3<R, SCHEME, 1>(ctx, a, extz);
+}
+
+template <typename R> static int launch_t1(optmc_ctx* ctx, int scheme, const PathArgs& a, bool extz, bool vec4) {
+  switch (scheme) {
+    case OPTMC_SCHEME_GBM_LOG_EULER: return launch_t2<R, OPTMC_SCHEME_GBM_LOG_EULER>(ctx, a, extz, vec4);
+    case OPTMC_SCHEME_GBM_LOGSPACE: return launch_t2<R, OPTMC_SCHEME_GBM_LOGSPACE>(ctx, a, extz, vec4);
+    case OPTMC_SCHEME_HESTON_REF_ABSORB: return launch_t2<R, OPTMC_SCHEME_HESTON_REF_ABSORB>(ctx, a, extz, vec4);
+    case OPTMC_SCHEME_HESTON_FULL_TRUNC: return launch_t2<R, OPTMC_SCHEME_HESTON_FULL_TRUNC>(ctx, a, extz, vec4);
+    case OPTMC_SCHEME_HESTON_REF_CALIB: return launch_t2<R, OPTMC_SCHEME_HESTON_REF_CALIB>(ctx, a, extz, vec4);
+  }
+  set_error("unknown scheme");
+  return OPTMC_EINVAL;
+}
+
+static int fill_path_args(const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M, int32_t N, PathArgs* a,
+                          bool* extz) {
+  if (!mp || !rng) { set_error("null params"); return OPTMC_EINVAL; }
+  if (!(mp->S0 > 0) || !(mp->T > 0)) { set_error("S0, K, T must be positive."); return OPTMC_EINVAL; }
+  if (M <= 0 || N <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
+  const bool hes = mp->scheme >= OPTMC_SCHEME_HESTON_REF_ABSORB;
+  if (hes != (mp->model == OPTMC_MODEL_HESTON)) { set_error("scheme does not belong to model"); return OPTMC_EINVAL; }
+  if (rng->antithetic && (M % 2)) { set_error("antithetic layout needs an even path count"); return OPTMC_EINVAL; }
+  if (hes && !(mp->rho > -1.0 && mp->rho < 1.0)) { set_error("rho must be in (-1, 1)"); return OPTMC_EINVAL; }
+  if (!hes && !(mp->sigma >= 0)) { set_error("sigma must be non-negative"); return OPTMC_EINVAL; }
+  *extz = rng->z1_dev != nullptr;
+  if (*extz && hes && !rng->z2_dev) { set_error("Heston external normals need z1 and z2"); return OPTMC_EINVAL; }
+  const double dt = mp->T / N;
+  a->N = N;
+  a->anti = rng->antithetic ? 1 : 0;
+  a->Mh = rng->antithetic ? M / 2 : M;
+  a->z1 = rng->z1_dev; a->z2 = rng->z2_dev; a->z_f64 = rng->z_dtype == OPTMC_F64;
+  a->seed = rng->seed; a->stream = (unsigned int)rng->stream; a->pair_offset = rng->pair_offset;
+  a->S0 = mp->S0; a->v0 = mp->v0;
+  a->g_drift = (mp->r - 0.5 * mp->sigma * mp->sigma) * dt;
+  a->g_diff = mp->sigma * sqrt(dt);
+  a->dt = dt; a->sqrt_dt = sqrt(dt); a->r = mp->r; a->kappa = mp->kappa; a->theta = mp->theta; a->xi = mp->xi;
+  a->rho = mp->rho; a->rho_c = sqrt(1.0 - mp->rho * mp->rho);
+  return OPTMC_OK;
+}
+
+int launch_paths(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M, int32_t N,
+                 int32_t dtype, void* S, void* V, int64_t ld) {
+  PathArgs a{};
+  bool extz = false;
+  int rc = fill_path_args(mp, rng, M, N, &a, &extz);
+  if (rc) return rc;
+  if (!S) { set_error("S_dev is null"); return OPTMC_EINVAL; }
+  if (ld < M) { set_error("ld must be >= M"); return OPTMC_EINVAL; }
+  if (dtype != OPTMC_F32 && dtype != OPTMC_F64) { set_error("bad dtype"); return OPTMC_EINVAL; }
+  a.S = S; a.V = V; a.ld = ld;
+  const size_t es = dtype == OPTMC_F64 ? 8 : 4;
+  bool vec4 = (a.Mh % 4 == 0) && (ld % 4 == 0) && ((uintptr_t)S % 16 == 0) && (!V || (uintptr_t)V % 16 == 0) &&
+              ((a.Mh * es) % 16 == 0);
+  if (dtype == OPTMC_F64) return launch_t1<double>(ctx, mp->scheme, a, extz, vec4);
+  return launch_t1<float>(ctx, mp->scheme, a, extz, vec4);
+}
+
+// ---- the normals the Philox path kernels consume (test aid) ---------------------------------------------
+template <typename R> __global__ void normals_kernel(PathArgs a, int hes, int which, R* Z) {
+  const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= a.Mh) return;
+  const int spb = hes ? 2 : 4;
+  for (int t0 = 0; t0 < a.N; t0 += spb) {
+    R n[4];
+    philox_block_normals<R>((unsigned long long)(a.pair_offset + col), (unsigned int)(t0 / spb), a.stream, a.seed, n);
+    for (int s = 0; s < spb; ++s) {
+      const int t = t0 + s + 1;
+      if (t > a.N) break;
+      Z[(long long)(t - 1) * a.Mh + col] = hes ? n[2 * s + which] : n[s];
+    }
+  }
+}
+
+int launch_philox_normals(optmc_ctx* ctx, const optmc_rng_params* rng, int32_t model, int64_t M, int32_t N,
+                          int32_t which, int32_t dtype, void* Z) {
+  if (!rng || !Z || M <= 0 || N <= 0 || which < 0 || which > 1) { set_error("bad arguments"); return OPTMC_EINVAL; }
+  const int hes = model == OPTMC_MODEL_HESTON;
+  if (!hes && which != 0) { set_error("GBM has a single normal stream"); return OPTMC_EINVAL; }
+  PathArgs a{};
+  a.N = N; a.Mh = rng->antithetic ? M / 2 : M; a.seed = rng->seed; a.stream = (unsigned int)rng->stream;
+  a.pair_offset = rng->pair_offset;
+  const unsigned grid = (unsigned)((a.Mh + 255) / 256);
+  if (dtype == OPTMC_F64) normals_kernel<double><<<grid, 256, 0, ctx->stream>>>(a, hes, which, static_cast<double*>(Z));
+  else normals_kernel<float><<<grid, 256, 0, ctx->stream>>>(a, hes, which, static_cast<float*>(Z));
+  ctx->launches++;
+  OPTMC_CUDA(cudaGetLastError());
+  return OPTMC_OK;
+}
+
+// ---- Philox KAT ------------------------------------------------------------------------------------------
+__global__ void philox_kat_kernel(int n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Philox4 p = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1]);
+  for (int k = 0; k < 4; ++k) out[4 * i + k] = p.v[k];
+}
+
+int launch_philox_kat(optmc_ctx* ctx, int n, const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  if (n <= 0 || !ctr || !key || !out) { set_error("bad arguments"); return OPTMC_EINVAL; }
+  uint32_t* d = nullptr;
+  OPTMC_CUDA(cudaMalloc(&d, sizeof(uint32_t) * 10 * n));
+  cudaError_t e = cudaMemcpyAsync(d, ctr, sizeof(uint32_t) * 4 * n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + 4 * n, key, sizeof(uint32_t) * 2 * n, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    philox_kat_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, d, d + 4 * n, d + 6 * n);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 6 * n, sizeof(uint32_t) * 4 * n, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "philox_kat");
+  return OPTMC_OK;
+}
+
+// ---- create_regression_features (om3:105-121) ----------------------------------------------------------------
+template <typename R> __global__ void features_kernel(const R* S, long long n, R K, R tau_sqrt, R* F) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  R f[7];
+  features_ref7<R>(S[i], K, tau_sqrt, f);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) F[i * 7 + k] = f[k];
+}
+
+int launch_features(optmc_ctx* ctx, const void* S, int64_t n, int32_t dtype, double K, double T, double t_current,
+                    void* F) {
+  if (!S || !F || n < 0) { set_error("bad arguments"); return OPTMC_EINVAL; }
+  if (n == 0) return OPTMC_OK;
+  const double tau = T - t_current;
+  const double tau_sqrt = sqrt(tau > 1e-6 ? tau : 1e-6);  // om3:109
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == OPTMC_F64)
+    features_kernel<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const double*>(S), n, K, tau_sqrt,
+                                                           static_cast<double*>(F));
+  else
+    features_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(S), n, (float)K, (float)tau_sqrt,
+                                                          static_cast<float*>(F));
+  ctx->launches++;
+  OPTMC_CUDA(cudaGetLastError());
+  return OPTMC_OK;
+}
+
+}  // namespace optmc

@@ -1,0 +1,335 @@
+"""Thin Python handle over the C ABI (include/optmc.h).  torch is used only to own device memory and
+streams; every computation happens in liboptmc.so's CUDA kernels.  No CPU fallback: constructing an
+``Engine`` without the built library or without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+@dataclass
+class ModelSpec:
+    """Mirror of optmc_model_params."""
+    model: int
+    scheme: int
+    S0: float
+    r: float
+    T: float
+    sigma: float = 0.0
+    v0: float = 0.0
+    kappa: float = 0.0
+    theta: float = 0.0
+    xi: float = 0.0
+    rho: float = 0.0
+
+    def c(self) -> L.ModelParams:
+        return L.ModelParams(self.model, self.scheme, self.S0, self.r, self.T, self.sigma, self.v0, self.kappa,
+                             self.theta, self.xi, self.rho)
+
+
+def gbm(S0, r, T, sigma, scheme=L.SCHEME_GBM_LOG_EULER) -> ModelSpec:
+    return ModelSpec(L.MODEL_GBM, scheme, float(S0), float(r), float(T), sigma=float(sigma))
+
+
+def heston(S0, r, T, v0, kappa, theta, xi, rho, scheme=L.SCHEME_HESTON_REF_ABSORB) -> ModelSpec:
+    return ModelSpec(L.MODEL_HESTON, scheme, float(S0), float(r), float(T), v0=float(v0), kappa=float(kappa),
+                     theta=float(theta), xi=float(xi), rho=float(rho))
+
+
+@dataclass
+class RngSpec:
+    """Mirror of optmc_rng_params.  z1/z2: optional torch CUDA tensors of external normals [N][M/2]."""
+    seed: int = 42
+    stream: int = 0
+    z1: object = None
+    z2: object = None
+    antithetic: bool = True
+    pair_offset: int = 0
+
+    def c(self) -> L.RngParams:
+        zd = L.F32
+        p1 = p2 = None
+        if self.z1 is not None:
+            import torch
+
+            assert self.z1.is_cuda and self.z1.is_contiguous()
+            zd = L.F64 if self.z1.dtype == torch.float64 else L.F32
+            p1 = self.z1.data_ptr()
+            if self.z2 is not None:
+                assert self.z2.is_cuda and self.z2.is_contiguous() and self.z2.dtype == self.z1.dtype
+                p2 = self.z2.data_ptr()
+        return L.RngParams(self.seed & 0xFFFFFFFFFFFFFFFF, self.stream & 0xFFFFFFFFFFFFFFFF, p1, p2, zd,
+                           1 if self.antithetic else 0, self.pair_offset)
+
+
+@dataclass
+class SweepResult:
+    price: float
+    stderr: float
+    n_paths: int
+    impl_used: int
+    n_launches: int
+    betas: Optional[np.ndarray] = field(default=None, repr=False)
+    boundary: Optional[np.ndarray] = field(default=None, repr=False)
+    ex_count: Optional[np.ndarray] = field(default=None, repr=False)
+    n_itm: Optional[np.ndarray] = field(default=None, repr=False)
+
+
+def _dtype_code(dtype) -> int:
+    """Accepts "f32"/"f64", numpy / torch dtypes or the C enum value."""
+    if isinstance(dtype, int):
+        return L.F64 if dtype == L.F64 else L.F32
+    return L.F64 if str(dtype).replace("torch.", "") in ("f64", "float64", "double", "<class 'numpy.float64'>") else L.F32
+
+
+def _torch_dtype(code: int):
+    import torch
+
+    return torch.float64 if code == L.F64 else torch.float32
+
+
+class Engine:
+    """One context per (device, host thread).  Not thread-safe (SURVEY.md 8(b) threading)."""
+
+    def __init__(self, device: int = 0, follow_torch_stream: bool = True):
+        self.lib = L.load_library()
+        import torch
+
+        if not torch.cuda.is_available():
+            raise L.OptmcError("no CUDA device visible to torch; options_model_b200 has no CPU fallback")
+        self.torch = torch
+        self.device = int(device)
+        self.tdev = torch.device("cuda", self.device)
+        h = C.c_void_p()
+        L.check(self.lib.optmc_ctx_create(self.device, C.byref(h)))
+        self._h = h
+        self.follow_torch_stream = follow_torch_stream
+        info = (C.c_int64 * 4)()
+        L.check(self.lib.optmc_ctx_device_info(self._h, info))
+        self.sm_count, self.l2_bytes, self.max_smem, self.cc = (int(x) for x in info)
+
+    # -- lifecycle ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.optmc_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _sync_stream(self):
+        """Issue work on torch's current stream so torch-side copies/events order with our kernels."""
+        if self.follow_torch_stream:
+            ptr = self.torch.cuda.current_stream(self.tdev).cuda_stream
+            L.check(self.lib.optmc_ctx_set_stream(self._h, C.c_void_p(ptr if ptr else 1)))  # 1 == cudaStreamLegacy
+
+    def synchronize(self):
+        L.check(self.lib.optmc_ctx_synchronize(self._h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.optmc_ctx_launch_count(self._h))
+
+    # -- path simulation ---------------------------------------------------------------------------
+    def alloc_slab(self, M: int, N: int, dtype):
+        """Step-major slab [(N+1)][ld]; ld padded to 64 elements so every row is 256-byte aligned."""
+        ld = (M + 63) // 64 * 64
+        return self.torch.empty((N + 1, ld), dtype=_torch_dtype(_dtype_code(dtype)), device=self.tdev)
+
+    def paths(self, model: ModelSpec, M: int, N: int, dtype="f32", rng: Optional[RngSpec] = None, out=None,
+              return_v: bool = False):
+        """Returns the slab view S[(N+1), M] (and V when return_v) -- om3:211-251 / om3:473-480 layout."""
+        rng = rng or RngSpec()
+        code = _dtype_code(dtype)
+        self._sync_stream()
+        S = out if out is not None else self.alloc_slab(M, N, dtype)
+        assert S.is_cuda and S.dim() == 2 and S.stride(1) == 1 and S.shape[0] >= N + 1
+        ld = S.stride(0)
+        mp, rp = model.c(), rng.c()
+        V = None
+        if model.model == L.MODEL_HESTON:
+            if return_v:
+                V = self.torch.empty_like(S)
+            L.check(self.lib.optmc_paths_heston(self._h, C.byref(mp), C.byref(rp), M, N, code, S.data_ptr(),
+                                                V.data_ptr() if V is not None else None, ld))
+        else:
+            L.check(self.lib.optmc_paths_gbm(self._h, C.byref(mp), C.byref(rp), M, N, code, S.data_ptr(), ld))
+        if return_v:
+            return S[: N + 1, :M], (V[: N + 1, :M] if V is not None else None)
+        return S[: N + 1, :M]
+
+    def philox_normals(self, model_id: int, M: int, N: int, which: int = 0, dtype="f32",
+                       rng: Optional[RngSpec] = None):
+        rng = rng or RngSpec()
+        code = _dtype_code(dtype)
+        self._sync_stream()
+        cols = M // 2 if rng.antithetic else M
+        Z = self.torch.empty((N, cols), dtype=_torch_dtype(code), device=self.tdev)
+        rp = rng.c()
+        L.check(self.lib.optmc_philox_normals(self._h, C.byref(rp), model_id, M, N, which, code, Z.data_ptr()))
+        return Z
+
+    def philox_kat(self, ctr: Sequence[Sequence[int]], key: Sequence[Sequence[int]]) -> np.ndarray:
+        n = len(ctr)
+        c = np.ascontiguousarray(np.array(ctr, dtype=np.uint32).reshape(n, 4))
+        k = np.ascontiguousarray(np.array(key, dtype=np.uint32).reshape(n, 2))
+        o = np.zeros((n, 4), dtype=np.uint32)
+        u32p = C.POINTER(C.c_uint32)
+        self._sync_stream()
+        L.check(self.lib.optmc_philox_kat(self._h, n, c.ctypes.data_as(u32p), k.ctypes.data_as(u32p),
+                                          o.ctypes.data_as(u32p)))
+        return o
+
+    # -- LSM sweep ------------------------------------------------------------------------------------
+    @staticmethod
+    def _lsm_params(K, r, T, option_type, basis, semantics, impl) -> L.LsmParams:
+        b = {"poly2": L.BASIS_POLY2, "poly3": L.BASIS_POLY3}.get(basis, basis)
+        s = {"reference": L.SEM_REFERENCE, "textbook": L.SEM_TEXTBOOK}.get(semantics, semantics)
+        i = {"auto": L.SWEEP_AUTO, "resident": L.SWEEP_RESIDENT, "split": L.SWEEP_SPLIT}.get(impl, impl)
+        return L.LsmParams(float(K), float(r), float(T), 1 if option_type == "put" else 0, int(b), int(s), int(i))
+
+    def _result_block(self, N: int, p: int, arrays: bool):
+        res = L.LsmResult()
+        keep = {}
+        if arrays:
+            keep["betas"] = np.full((N + 1, p), np.nan)
+            keep["boundary"] = np.full(N + 1, np.nan)
+            keep["ex_count"] = np.zeros(N + 1, dtype=np.int64)
+            keep["n_itm"] = np.zeros(N + 1, dtype=np.int64)
+            res.betas = keep["betas"].ctypes.data_as(C.POINTER(C.c_double))
+            res.boundary = keep["boundary"].ctypes.data_as(C.POINTER(C.c_double))
+            res.ex_count = keep["ex_count"].ctypes.data_as(C.POINTER(C.c_int64))
+            res.n_itm = keep["n_itm"].ctypes.data_as(C.POINTER(C.c_int64))
+        return res, keep
+
+    @staticmethod
+    def _to_result(res: L.LsmResult, keep) -> SweepResult:
+        return SweepResult(res.price, res.stderr_, int(res.n_paths), int(res.impl_used), int(res.n_launches),
+                           keep.get("betas"), keep.get("boundary"), keep.get("ex_count"), keep.get("n_itm"))
+
+    def lsm(self, S, K, r, T, option_type="put", basis="poly2", semantics="reference", impl="auto", arrays=True,
+            M: Optional[int] = None, asynchronous: bool = False):
+        """Sweep an existing slab S[(N+1), M] (torch CUDA tensor, row stride = ld)."""
+        assert S.is_cuda and S.dim() == 2 and S.stride(1) == 1
+        N = S.shape[0] - 1
+        M = int(M if M is not None else S.shape[1])
+        lp = self._lsm_params(K, r, T, option_type, basis, semantics, impl)
+        code = L.F64 if S.dtype == self.torch.float64 else L.F32
+        self._sync_stream()
+        if asynchronous:
+            L.check(self.lib.optmc_lsm_poly(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), None))
+            return None
+        p = 3 if lp.basis == L.BASIS_POLY2 else 4
+        res, keep = self._result_block(N, p, arrays)
+        L.check(self.lib.optmc_lsm_poly(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), C.byref(res)))
+        return self._to_result(res, keep)
+
+    def lsm_fetch(self, N: int, basis="poly2", arrays=True) -> SweepResult:
+        p = 3 if basis in ("poly2", L.BASIS_POLY2) else 4
+        res, keep = self._result_block(N, p, arrays)
+        L.check(self.lib.optmc_lsm_fetch(self._h, C.byref(res)))
+        return self._to_result(res, keep)
+
+    # per-date building blocks (path-sharded multi-GPU sweep; see sharded.py)
+    def lsm_begin(self, S, K, r, T, option_type="put", basis="poly2", semantics="reference", M=None):
+        N = S.shape[0] - 1
+        M = int(M if M is not None else S.shape[1])
+        lp = self._lsm_params(K, r, T, option_type, basis, semantics, "split")
+        code = L.F64 if S.dtype == self.torch.float64 else L.F32
+        self._sync_stream()
+        L.check(self.lib.optmc_lsm_begin(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp)))
+
+    def lsm_gram_date(self, t: int, gram):
+        self._sync_stream()
+        L.check(self.lib.optmc_lsm_gram_date(self._h, t, gram.data_ptr()))
+
+    def lsm_update_date(self, t: int, gram):
+        self._sync_stream()
+        L.check(self.lib.optmc_lsm_update_date(self._h, t, gram.data_ptr()))
+
+    def lsm_finish(self, sums):
+        self._sync_stream()
+        L.check(self.lib.optmc_lsm_finish(self._h, sums.data_ptr()))
+
+    def gram_len(self, basis="poly2") -> int:
+        b = {"poly2": L.BASIS_POLY2, "poly3": L.BASIS_POLY3}.get(basis, basis)
+        return int(self.lib.optmc_lsm_gram_len(b))
+
+    # -- fused host-facing calls ---------------------------------------------------------------------
+    def price_american(self, model: ModelSpec, M: int, N: int, K, option_type="put", dtype="f32",
+                       rng: Optional[RngSpec] = None, basis="poly2", semantics="reference", impl="auto",
+                       arrays=False, asynchronous=False):
+        """price_american_enhanced_lsm (om3:439-651): host scalars in, host results out."""
+        rng = rng or RngSpec()
+        lp = self._lsm_params(K, model.r, model.T, option_type, basis, semantics, impl)
+        mp, rp = model.c(), rng.c()
+        self._sync_stream()
+        if asynchronous:
+            L.check(self.lib.optmc_price_american(self._h, C.byref(mp), C.byref(rp), M, N, _dtype_code(dtype),
+                                                  C.byref(lp), None))
+            return None
+        p = 3 if lp.basis == L.BASIS_POLY2 else 4
+        res, keep = self._result_block(N, p, arrays)
+        L.check(self.lib.optmc_price_american(self._h, C.byref(mp), C.byref(rp), M, N, _dtype_code(dtype),
+                                              C.byref(lp), C.byref(res)))
+        return self._to_result(res, keep)
+
+    def price_european_batch(self, model: ModelSpec, M: int, N: int, K, T, is_put, dtype="f32",
+                             rng: Optional[RngSpec] = None, stream_id=None):
+        """Fused no-store European pricing of n options (om3:382-437, hc:259-281).  -> (mean[n], stderr[n])."""
+        rng = rng or RngSpec()
+        K = np.ascontiguousarray(np.atleast_1d(np.asarray(K, dtype=np.float64)))
+        T = np.ascontiguousarray(np.atleast_1d(np.asarray(T, dtype=np.float64)))
+        P = np.ascontiguousarray(np.atleast_1d(np.asarray(is_put, dtype=np.int32)))
+        n = K.size
+        assert T.size == n and P.size == n
+        out = (L.EuropeanResult * n)()
+        mp, rp = model.c(), rng.c()
+        self._sync_stream()
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        sid = None
+        if stream_id is not None:
+            sid_arr = np.ascontiguousarray(np.asarray(stream_id, dtype=np.int32))
+            assert sid_arr.size == n
+            sid = sid_arr.ctypes.data_as(ip)
+        L.check(self.lib.optmc_price_european_batch(self._h, C.byref(mp), C.byref(rp), M, N, _dtype_code(dtype), n,
+                                                    K.ctypes.data_as(dp), T.ctypes.data_as(dp), P.ctypes.data_as(ip),
+                                                    sid, out))
+        return (np.array([o.mean for o in out]), np.array([o.stderr_ for o in out]))
+
+    def european_from_slab(self, S_T, K, r, T, option_type="put"):
+        assert S_T.is_cuda and S_T.is_contiguous()
+        out = L.EuropeanResult()
+        code = L.F64 if S_T.dtype == self.torch.float64 else L.F32
+        self._sync_stream()
+        L.check(self.lib.optmc_european_from_slab(self._h, S_T.data_ptr(), S_T.numel(), code, float(K), float(r),
+                                                  float(T), 1 if option_type == "put" else 0, C.byref(out)))
+        return out.mean, out.stderr_
+
+    def features_ref7(self, S, K, r, T, t_current):
+        """create_regression_features (om3:105-121) on the device -> [n, 7]."""
+        assert S.is_cuda and S.is_contiguous()
+        F = self.torch.empty((S.numel(), 7), dtype=S.dtype, device=S.device)
+        code = L.F64 if S.dtype == self.torch.float64 else L.F32
+        self._sync_stream()
+        L.check(self.lib.optmc_features_ref7(self._h, S.data_ptr(), S.numel(), code, float(K), float(r), float(T),
+                                             float(t_current), F.data_ptr()))
+        return F
+
+
+_DEFAULT = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device (the compat layer's pricer objects share it)."""
+    if device not in _DEFAULT:
+        _DEFAULT[device] = Engine(device)
+    return _DEFAULT[device]

@@ -1,0 +1,67 @@
+"""Path-sharded multi-GPU sweep: one process per GPU, each rank owns a contiguous block
+of antithetic pairs (Philox counters stay global through ``pair_offset``), and the only data-path
+collective is the per-date all-reduce of the Gram moment vector (8 doubles for poly2) plus the final
+(sum, sum^2, n) reduction.  ``engine`` is an ``engine.Engine`` (CUDA); ``dist`` is ``torch.distributed``
+with NCCL on GPUs.  The host logic is backend-agnostic, so the CPU test-suite drives it over gloo with a
+stand-in engine.
+
+Option-sharding (independent options per rank, no collective at all) needs no code here: each rank
+simply prices its slice of the option list (bench.py --gpus N does exactly that).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+
+def shard_pairs(M: int, rank: int, world: int):
+    """Contiguous block of antithetic pairs for ``rank``: returns (pair_offset, local_M).  Both members of a
+    pair live on the same rank (local columns j and j + local_M/2)."""
+    pairs = M // 2
+    base, extra = divmod(pairs, world)
+    lo = rank * base + min(rank, extra)
+    n = base + (1 if rank < extra else 0)
+    return lo, 2 * n
+
+
+@dataclass
+class ShardedResult:
+    price: float
+    stderr: float
+    n_paths: int
+    n_collectives: int
+
+
+def sweep_sharded(engine, dist, S_local, K, r, T, option_type="put", basis="poly2", semantics="reference",
+                  group=None, torch_mod=None) -> ShardedResult:
+    """Run the LSM sweep over this rank's slab ``S_local[(N+1), M_local]``; every rank returns the global price.
+
+    Per date: local Gram moments (device) -> all_reduce(SUM) -> every rank solves the same p x p system
+    redundantly (bit-identical beta because the reduced vector is identical) -> local update.
+    """
+    torch = torch_mod
+    if torch is None:
+        import torch  # type: ignore
+    N = S_local.shape[0] - 1
+    q = engine.gram_len(basis)
+    gram = torch.zeros(q, dtype=torch.float64, device=S_local.device)
+    sums = torch.zeros(3, dtype=torch.float64, device=S_local.device)
+    engine.lsm_begin(S_local, K, r, T, option_type, basis, semantics)
+    ncoll = 0
+    for t in range(N - 1, 0, -1):
+        engine.lsm_gram_date(t, gram)
+        dist.all_reduce(gram, op=dist.ReduceOp.SUM, group=group)
+        ncoll += 1
+        engine.lsm_update_date(t, gram)
+    engine.lsm_finish(sums)
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    ncoll += 1
+    s, ss, n = (float(x) for x in sums.cpu().tolist())
+    mean = s / n
+    var = max((ss - n * mean * mean) / (n - 1.0), 0.0) if n > 1 else 0.0
+    dt = T / N
+    scale = 1.0 if semantics in ("reference", 3) else math.exp(-r * dt)
+    return ShardedResult(mean * scale, math.sqrt(var / n) * scale, int(round(n)), ncoll)

@@ -1,0 +1,448 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against (a) fixtures produced by the
+real reference (tests/golden, see oracle/gen_golden.py) and (b) the numpy oracle on identical Gaussian draws.
+
+Tolerances (north star): fed identical draws, prices / betas / boundary within 1e-5 relative in fp64 and
+1e-4 in fp32 -- the fp64 assertions below are far tighter (1e-9 or better); integer outputs (exercise
+counts, ITM counts) and the boundary (a selected input value) are compared exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+HP = dict(v0=0.04, kappa=2.0, theta=0.04, xi=0.5, rho=-0.7)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from options_model_b200 import engine as E
+
+    e = E.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from options_model_b200 import _lib as L
+    from options_model_b200 import engine as E
+    from oracle import lsm_oracle as orc
+
+    return L, E, orc
+
+
+def _dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def _slab(eng, S_np, dtype):
+    """Upload a host [(N+1), M] array into a padded step-major slab; returns the [:, :M] view."""
+    N1, M = S_np.shape
+    slab = eng.alloc_slab(M, N1 - 1, "f64" if dtype == torch.float64 else "f32")
+    slab[:, :M] = _dev(S_np, dtype)
+    return slab[:, :M]
+
+
+# ------------------------------------------------------------------------------------------------------
+# RNG
+# ------------------------------------------------------------------------------------------------------
+def test_philox_kat_on_device(eng):
+    """Random123 known-answer vectors."""
+    ctr = [[0, 0, 0, 0], [0xFFFFFFFF] * 4, [0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344]]
+    key = [[0, 0], [0xFFFFFFFF, 0xFFFFFFFF], [0xA4093822, 0x299F31D0]]
+    out = eng.philox_kat(ctr, key)
+    exp = np.array([[0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8], [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD],
+                    [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]], dtype=np.uint32)
+    assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f64"])
+def test_philox_normal_moments(eng, mods, dtype):
+    L, E, _ = mods
+    z = eng.philox_normals(L.MODEL_HESTON, 1 << 20, 8, 0, dtype, E.RngSpec(seed=7)).double().cpu().numpy().ravel()
+    n = z.size
+    assert abs(z.mean()) < 5 / np.sqrt(n)
+    assert abs(z.var() - 1) < 5 * np.sqrt(2 / n)
+    assert abs((z**3).mean()) < 5 * np.sqrt(15 / n)
+    assert abs((z**4).mean() - 3) < 5 * np.sqrt(96 / n)
+    z2 = eng.philox_normals(L.MODEL_HESTON, 1 << 20, 8, 1, dtype, E.RngSpec(seed=7)).double().cpu().numpy().ravel()
+    assert abs(np.corrcoef(z, z2)[0, 1]) < 5 / np.sqrt(n)
+
+
+def test_philox_paths_invariant_to_sharding(eng, mods):
+    """Counters are global pair indices: generating [0,M) at once or as two shards gives identical bits."""
+    L, E, _ = mods
+    M, N = 4096, 9
+    model = E.heston(100, 0.05, 1.0, **HP)
+    full = eng.paths(model, M, N, "f32", E.RngSpec(seed=3)).clone()
+    h = M // 4  # pairs per shard (M/2 pairs split in two)
+    a = eng.paths(model, M // 2, N, "f32", E.RngSpec(seed=3, pair_offset=0)).clone()
+    b = eng.paths(model, M // 2, N, "f32", E.RngSpec(seed=3, pair_offset=h)).clone()
+    # shard columns: [+z block | -z block] locally
+    assert torch.equal(a[:, :h], full[:, :h]) and torch.equal(b[:, :h], full[:, h:2 * h])
+    assert torch.equal(a[:, h:], full[:, M // 2:M // 2 + h]) and torch.equal(b[:, h:], full[:, M // 2 + h:])
+
+
+# ------------------------------------------------------------------------------------------------------
+# path schemes vs the REAL reference (golden fixtures)
+# ------------------------------------------------------------------------------------------------------
+def test_heston_paths_vs_reference_golden(eng, mods, golden_dir):
+    L, E, _ = mods
+    g = np.load(os.path.join(golden_dir, "ref_heston_paths_even.npz"))
+    S0, r, T, v0, kappa, theta, xi, rho = g["args"]
+    M, N = int(g["M"]), int(g["N"])
+    S = eng.paths(E.heston(S0, r, T, v0, kappa, theta, xi, rho), M, N, "f64",
+                  E.RngSpec(z1=_dev(g["Z1"]), z2=_dev(g["Z2"])))
+    np.testing.assert_allclose(S.cpu().numpy(), g["S"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("tag", ["even", "odd"])
+def test_compat_simulate_heston_is_drop_in(golden_dir, tag):
+    """Same call as om3.simulate_heston_paths_antithetic(..., rng): identical draws, identical paths."""
+    from options_model_b200 import compat
+
+    g = np.load(os.path.join(golden_dir, f"ref_heston_paths_{tag}.npz"))
+    S0, r, T, v0, kappa, theta, xi, rho = g["args"]
+    S = compat.simulate_heston_paths_antithetic(S0, r, T, v0, kappa, theta, xi, rho, int(g["M"]), int(g["N"]),
+                                                np.random.default_rng(int(g["seed"])))
+    assert S.shape == g["S"].shape
+    np.testing.assert_allclose(S, g["S"], rtol=1e-12)
+
+
+def test_torch_fp32_variants_vs_reference_golden(eng, mods, golden_dir):
+    """om3gpu:117-248 run for real on CPU torch (fixtures) vs the fp32 kernels on the same torch.randn draws."""
+    L, E, _ = mods
+    g = np.load(os.path.join(golden_dir, "ref_torch_paths.npz"))
+    M, N = int(g["M"]), int(g["N"])
+    S = eng.paths(E.gbm(100, 0.05, 1.0, 0.2), M, N, "f32", E.RngSpec(z1=_dev(g["Zh"])))
+    np.testing.assert_allclose(S.cpu().numpy(), g["S_bs"], rtol=2e-5)
+    S = eng.paths(E.gbm(100, 0.05, 1.0, 0.2, scheme=L.SCHEME_GBM_LOGSPACE), M, N, "f32",
+                  E.RngSpec(z1=_dev(g["Zbw"]), antithetic=False))
+    np.testing.assert_allclose(S.cpu().numpy(), g["S_bw"], rtol=2e-5)
+    S = eng.paths(E.heston(100, 0.05, 1.0, **HP), M, N, "f32", E.RngSpec(z1=_dev(g["Z1"]), z2=_dev(g["Z2"])))
+    np.testing.assert_allclose(S.cpu().numpy(), g["S_h"], rtol=5e-5)
+
+
+def test_calibrator_scheme_vs_reference_golden(golden_dir):
+    """hc.HestonPricer(seed=42): simulate_paths and two consecutive price_european_option calls."""
+    from options_model_b200 import compat
+
+    g = np.load(os.path.join(golden_dir, "ref_hc_paths.npz"))
+    kappa, theta, sigma, rho, v0 = g["params"]
+    cfg = compat.CalibrationConfig(n_mc_paths=64, n_time_steps=10, seed=42, verbose=False, plot_results=False)
+    params = compat.HestonParams(kappa=kappa, theta=theta, sigma=sigma, rho=rho, v0=v0)
+    S, V = compat.HestonPricer(cfg).simulate_paths(params, 100.0, 0.75, 0.03)
+    np.testing.assert_allclose(S, g["S"], rtol=1e-12)
+    np.testing.assert_allclose(V, g["V"], rtol=1e-10, atol=1e-18)
+    pr = compat.HestonPricer(cfg, reference_draws=True)
+    assert pr.price_european_option(params, 100.0, 95.0, 0.75, 0.03, "call") == pytest.approx(float(g["call_95"]), rel=1e-12)
+    assert pr.price_european_option(params, 100.0, 105.0, 0.75, 0.03, "put") == pytest.approx(float(g["put_105"]), rel=1e-12)
+
+
+def test_features_vs_reference_golden(golden_dir):
+    from options_model_b200 import compat
+
+    g = np.load(os.path.join(golden_dir, "ref_features.npz"))
+    np.testing.assert_allclose(compat.create_regression_features(g["S"], 100.0, 0.05, 1.0, 0.3), g["F"], rtol=1e-15)
+    np.testing.assert_allclose(compat.create_regression_features(g["S"], 100.0, 0.05, 1.0, 1.0), g["F_end"], rtol=1e-15)
+    f = np.load(os.path.join(golden_dir, "ref_features_torch.npz"))
+    F = compat.create_regression_features_torch(torch.as_tensor(f["S"]).cuda(), 100.0, 0.05, 1.0, 0.3)
+    np.testing.assert_allclose(F.cpu().numpy(), f["F"], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------------
+# LSM sweep vs the oracle on identical paths
+# ------------------------------------------------------------------------------------------------------
+def _check_sweep(res, ref, price_rtol, beta_rtol=1e-6):
+    assert res.price == pytest.approx(ref.price, rel=price_rtol)
+    assert res.stderr == pytest.approx(ref.stderr, rel=max(price_rtol, 1e-9))
+    np.testing.assert_array_equal(res.n_itm, ref.n_itm)
+    np.testing.assert_array_equal(res.ex_count, ref.ex_count)
+    np.testing.assert_array_equal(np.isnan(res.boundary), np.isnan(ref.boundary))
+    np.testing.assert_array_equal(np.nan_to_num(res.boundary), np.nan_to_num(ref.boundary))
+    np.testing.assert_array_equal(np.isnan(res.betas), np.isnan(ref.betas))
+    # betas are ill-conditioned individually; compare the fitted continuation over the ITM range instead
+    x = np.linspace(0.6, 1.0, 9) if True else None
+    for t in range(res.betas.shape[0]):
+        if not np.isnan(ref.betas[t, 0]):
+            p = ref.betas.shape[1]
+            fit_ref = sum(ref.betas[t, i] * x**i for i in range(p))
+            fit_gpu = sum(res.betas[t, i] * x**i for i in range(p))
+            np.testing.assert_allclose(fit_gpu, fit_ref, rtol=beta_rtol, atol=beta_rtol)
+
+
+@pytest.mark.parametrize("impl", ["resident", "split"])
+@pytest.mark.parametrize("semantics", ["reference", "textbook"])
+@pytest.mark.parametrize("basis", ["poly2", "poly3"])
+def test_sweep_fp64_vs_oracle_small(eng, mods, golden_dir, impl, semantics, basis):
+    L, E, orc = mods
+    res_o, S, _ = orc.price_american_lsm(100.0, 100.0, 0.05, 1.0, "put", 4096, 20, orc.RNGManager(1),
+                                         heston_params=HP, return_paths=True)
+    if basis == "poly2" and semantics == "reference":  # the committed golden of the restatement
+        g = np.load(os.path.join(golden_dir, "oracle_heston_poly2_small.npz"))
+        assert res_o.price == pytest.approx(float(g["price"]), rel=1e-13)
+    ref = orc.lsm_sweep(S, 100.0, 0.05, 1.0, "put", basis=basis, semantics=semantics)
+    res = eng.lsm(_slab(eng, S, torch.float64), 100.0, 0.05, 1.0, "put", basis, semantics, impl)
+    assert res.impl_used == {"resident": L.SWEEP_RESIDENT, "split": L.SWEEP_SPLIT}[impl]
+    _check_sweep(res, ref, 1e-11)
+
+
+@pytest.mark.parametrize("impl", ["resident", "split"])
+def test_sweep_call_and_gbm(eng, mods, impl):
+    L, E, orc = mods
+    rng = np.random.default_rng(5)
+    M, N = 6000, 15
+    S = orc.gbm_paths_antithetic(100.0, 0.05, 0.3, 1.0, M, N, orc.draw_gbm_normals(rng, N, M))
+    for ot, K in (("call", 95.0), ("put", 110.0)):
+        ref = orc.lsm_sweep(S, K, 0.05, 1.0, ot)
+        res = eng.lsm(_slab(eng, S, torch.float64), K, 0.05, 1.0, ot, impl=impl)
+        _check_sweep(res, ref, 1e-11)
+
+
+def test_config1_full_size_fp64_and_pins(eng, mods, golden_meta):
+    """BASELINE config 1: GBM put 100k x 50, RNGManager(42) child-0 draws; survey pins (6.542437 / 6.042107)."""
+    L, E, orc = mods
+    mgr = orc.RNGManager(42)
+    rng = mgr.get_child_rng()
+    M, N = 100_000, 50
+    Zh = orc.draw_gbm_normals(rng, N, M)
+    S_gpu = eng.paths(E.gbm(100.0, 0.05, 1.0, 0.2), M, N, "f64", E.RngSpec(z1=_dev(Zh)))
+    S = orc.gbm_paths_antithetic(100.0, 0.05, 0.2, 1.0, M, N, Zh)
+    np.testing.assert_allclose(S_gpu.cpu().numpy(), S, rtol=1e-12)
+    pins = golden_meta["poly_pins"]["c1_gbm_put_100k_50"]
+    for sem in ("reference", "textbook"):
+        ref = orc.lsm_sweep(S, 100.0, 0.05, 1.0, "put", semantics=sem)
+        assert ref.price == pytest.approx(pins[sem]["price"], rel=1e-12)
+        for impl in ("resident", "split"):
+            res = eng.lsm(S_gpu, 100.0, 0.05, 1.0, "put", "poly2", sem, impl)
+            _check_sweep(res, ref, 1e-10)
+            assert res.boundary[25] == pytest.approx(pins[sem]["boundary_25"], rel=1e-12)
+            assert res.boundary[45] == pytest.approx(pins[sem]["boundary_45"], rel=1e-12)
+
+
+@pytest.mark.parametrize("impl", ["resident", "split"])
+def test_sweep_fp32_vs_oracle(eng, mods, impl):
+    """fp32 storage: the same fp32 path values go to the kernel and (widened) to the oracle; tolerance 1e-4."""
+    L, E, orc = mods
+    rng = np.random.default_rng(11)
+    M, N = 50_000, 40
+    Z1, Z2 = orc.draw_heston_normals(rng, N, M)
+    S32 = orc.heston_paths_antithetic(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N,
+                                      Z1, Z2).astype(np.float32)
+    ref = orc.lsm_sweep(S32.astype(np.float64), 100.0, 0.05, 1.0, "put")
+    res = eng.lsm(_slab(eng, S32, torch.float32), 100.0, 0.05, 1.0, "put", impl=impl)
+    assert res.price == pytest.approx(ref.price, rel=1e-4)
+    assert res.stderr == pytest.approx(ref.stderr, rel=1e-4)
+    assert np.abs(res.ex_count - ref.ex_count).sum() <= 1e-4 * M  # a handful of borderline decisions may flip
+    np.testing.assert_array_equal(res.n_itm[N - 1], ref.n_itm[N - 1])
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-10), ("f32", 1e-4)])
+def test_price_american_philox_vs_oracle_same_draws(eng, mods, dtype, tol):
+    """Whole fused call (Philox paths + sweep) vs the oracle fed the kernel's own normals."""
+    L, E, orc = mods
+    M, N, K = 32768, 24, 100.0
+    rng = E.RngSpec(seed=99, stream=3)
+    res = eng.price_american(E.heston(100.0, 0.05, 1.0, **HP), M, N, K, "put", dtype, rng, arrays=True)
+    z1 = eng.philox_normals(L.MODEL_HESTON, M, N, 0, dtype, rng).double().cpu().numpy()
+    z2 = eng.philox_normals(L.MODEL_HESTON, M, N, 1, dtype, rng).double().cpu().numpy()
+    S = orc.heston_paths_antithetic(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, z1, z2)
+    ref = orc.lsm_sweep(S, K, 0.05, 1.0, "put")
+    assert res.price == pytest.approx(ref.price, rel=tol)
+    if dtype == "f64":
+        _check_sweep(res, ref, tol)
+
+
+def test_independent_rng_within_3_se(eng, mods):
+    """Config 1 with in-kernel Philox vs the oracle on numpy PCG64 draws: |diff| < 3 combined standard errors."""
+    L, E, orc = mods
+    ref = orc.price_american_lsm(100.0, 100.0, 0.05, 1.0, "put", 100_000, 50, orc.RNGManager(42), sigma=0.2)
+    res = eng.price_american(E.gbm(100.0, 0.05, 1.0, 0.2), 100_000, 50, 100.0, "put", "f32", E.RngSpec(seed=2024))
+    assert abs(res.price - ref.price) < 3 * np.hypot(res.stderr, ref.stderr)
+    ref_h = orc.price_american_lsm(100.0, 100.0, 0.05, 1.0, "put", 100_000, 50, orc.RNGManager(42), heston_params=HP)
+    res_h = eng.price_american(E.heston(100.0, 0.05, 1.0, **HP), 100_000, 50, 100.0, "put", "f32", E.RngSpec(seed=2025))
+    assert abs(res_h.price - ref_h.price) < 3 * np.hypot(res_h.stderr, ref_h.stderr)
+
+
+# ------------------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", ["resident", "split"])
+def test_edge_cases(eng, mods, impl):
+    L, E, orc = mods
+    rng = np.random.default_rng(2)
+    # (a) never in the money: deep OTM put -> no regression at any date, price = discounted terminal payoff = 0
+    M, N = 1000, 6
+    S = orc.gbm_paths_antithetic(100.0, 0.05, 0.1, 0.5, M, N, orc.draw_gbm_normals(rng, N, M))
+    ref = orc.lsm_sweep(S, 1.0, 0.05, 0.5, "put")
+    res = eng.lsm(_slab(eng, S, torch.float64), 1.0, 0.05, 0.5, "put", impl=impl)
+    assert res.price == 0.0 == ref.price and np.all(np.isnan(res.betas)) and res.n_itm.sum() == 0
+    # (b) N = 1: no exercise date at all (range(N-1, 0, -1) is empty) -> mean terminal payoff, zero discounts
+    S = orc.gbm_paths_antithetic(100.0, 0.05, 0.2, 1.0, M, 1, orc.draw_gbm_normals(rng, 1, M))
+    ref = orc.lsm_sweep(S, 100.0, 0.05, 1.0, "put")
+    res = eng.lsm(_slab(eng, S, torch.float64), 100.0, 0.05, 1.0, "put", impl=impl)
+    assert res.price == pytest.approx(ref.price, rel=1e-13)
+    # (c) ragged sizes: M = 2, M % 4 == 2, N = 2; fewer ITM rows than basis columns -> "no exercise" (8(c))
+    for M2, N2 in ((2, 2), (1002, 3), (514, 7)):
+        S = orc.gbm_paths_antithetic(100.0, 0.05, 0.2, 1.0, M2, N2, orc.draw_gbm_normals(rng, N2, M2))
+        ref = orc.lsm_sweep(S, 100.0, 0.05, 1.0, "put")
+        res = eng.lsm(_slab(eng, S, torch.float64), 100.0, 0.05, 1.0, "put", impl=impl)
+        _check_sweep(res, ref, 1e-12)
+    # (d) degenerate regression: every path identical -> pivot guard -> no exercise, price = discounted payoff
+    S = np.tile(np.linspace(100.0, 90.0, 5)[:, None], (1, 64))
+    ref = orc.lsm_sweep(S, 100.0, 0.05, 1.0, "put")
+    res = eng.lsm(_slab(eng, S, torch.float64), 100.0, 0.05, 1.0, "put", impl=impl)
+    _check_sweep(res, ref, 1e-13)
+    assert res.ex_count.sum() == 0
+
+
+def test_unaligned_slab_falls_back_to_split(eng, mods):
+    """ld = M with M % 4 == 2 breaks the 16-byte rule of the bulk copies: AUTO must pick SPLIT, RESIDENT must refuse."""
+    L, E, orc = mods
+    rng = np.random.default_rng(8)
+    M, N = 1002, 5
+    S = orc.gbm_paths_antithetic(100.0, 0.05, 0.2, 1.0, M, N, orc.draw_gbm_normals(rng, N, M))
+    Sd = _dev(S)  # contiguous: ld == M
+    ref = orc.lsm_sweep(S, 100.0, 0.05, 1.0, "put")
+    res = eng.lsm(Sd, 100.0, 0.05, 1.0, "put", impl="auto")
+    assert res.impl_used == L.SWEEP_SPLIT
+    _check_sweep(res, ref, 1e-12)
+    with pytest.raises(NotImplementedError):
+        eng.lsm(Sd, 100.0, 0.05, 1.0, "put", impl="resident")
+
+
+def test_error_behaviour_matches_reference():
+    """om3:447-452, om3:471-472: ValueError with the reference's messages; no silent CPU path."""
+    from options_model_b200 import compat
+
+    p = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, option_type="put", use_control_variate=False)
+    with pytest.raises(ValueError, match="S0, K, T must be positive"):
+        p.price_american_enhanced_lsm(-1.0, 1.0, 100, 10)
+    with pytest.raises(ValueError, match="positive integers"):
+        p.price_american_enhanced_lsm(100.0, 1.0, 0, 10)
+    with pytest.raises(ValueError, match="r must be non-negative"):
+        compat.AdvancedOptionPricer(K=100.0, r=-0.01, sigma=0.2).price_american_enhanced_lsm(100.0, 1.0, 100, 10)
+    with pytest.raises(ValueError, match="sigma is None"):
+        compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=None).price_american_enhanced_lsm(100.0, 1.0, 100, 10)
+    assert compat.compute_curve_worker_enhanced(-5.0, 100.0, 0.05, 0.2, "put", 1, 1, 2, 100, False, False, None) == []
+
+
+# ------------------------------------------------------------------------------------------------------
+# European reductions
+# ------------------------------------------------------------------------------------------------------
+def test_european_fused_equals_slab_reduction(eng, mods):
+    """The no-store kernel consumes the same Philox counters as the path kernel: identical terminal values."""
+    L, E, orc = mods
+    M, N = 20000, 30
+    model = E.heston(100.0, 0.05, 0.7, **HP)
+    rng = E.RngSpec(seed=5, stream=11)
+    mean, se = eng.price_european_batch(model, M, N, [100.0], [0.7], [1], "f64", rng, stream_id=[0])
+    S = eng.paths(model, M, N, "f64", rng)
+    m2, s2 = eng.european_from_slab(S[N].contiguous(), 100.0, 0.05, 0.7, "put")
+    assert mean[0] == pytest.approx(m2, rel=1e-12) and se[0] == pytest.approx(s2, rel=1e-10)
+    ref = orc.european_from_paths(S[N].cpu().numpy(), 100.0, 0.05, 0.7, "put")
+    assert m2 == pytest.approx(ref[0], rel=1e-12) and s2 == pytest.approx(ref[1], rel=1e-10)
+
+
+def test_european_batch_calibration_grid(eng, mods):
+    """Config-5 shape at reduced size: per-option K, T; options with equal stream ids share their paths."""
+    L, E, orc = mods
+    K = np.array([90.0, 100.0, 110.0, 100.0])
+    T = np.array([0.5, 0.5, 0.5, 1.0])
+    model = E.heston(100.0, 0.05, 1.0, **HP, scheme=L.SCHEME_HESTON_REF_CALIB)
+    mean, se = eng.price_european_batch(model, 50_000, 50, K, T, [0, 0, 0, 0], "f32", E.RngSpec(seed=1),
+                                        stream_id=[0, 0, 0, 1])
+    assert mean[0] > mean[1] > mean[2] > 0  # same paths, decreasing in strike: strictly monotone
+    # against the calibrator scheme on numpy draws (independent RNG): 4 standard errors
+    Z1, Z2i = orc.hc_draw_normals(np.random.default_rng(0), 50_000, 50)
+    Sh, _ = orc.hc_simulate_paths(HP["kappa"], HP["theta"], HP["xi"], HP["rho"], HP["v0"], 100.0, 0.5, 0.05, 50_000, 50, Z1, Z2i)
+    for i in range(3):
+        ref = orc.hc_price_european(Sh[:, -1], K[i], 0.5, 0.05, "call")
+        assert abs(mean[i] - ref) < 4 * np.hypot(se[i], se[i])
+
+
+def test_compat_pricer_end_to_end(mods):
+    """AdvancedOptionPricer through the compat layer: control-variate route, European route, curve driver."""
+    from options_model_b200 import compat
+
+    L, E, orc = mods
+    p = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, option_type="put", rng_manager=compat.RNGManager(42),
+                                    use_control_variate=False)
+    v = p.price_american_enhanced_lsm(100.0, 1.0, 100_000, 50)
+    assert abs(v - 6.5424) < 4 * 0.0255 * np.sqrt(2)  # reference-semantics value of config 1
+    bs = compat.BlackScholesGreeks.black_scholes_price(100.0, 100.0, 1.0, 0.05, 0.2, "put")
+    assert bs == pytest.approx(5.573526, abs=1e-6)
+    eu = p.price_european_streaming(100.0, 1.0, 200_000, 50)
+    assert abs(eu - bs) < 0.06
+    pc = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, option_type="put", rng_manager=compat.RNGManager(1))
+    rec = pc.compute_curve_for_S0(100.0, 1, 3, 20000, False)
+    assert [r["Days to Expiry"] for r in rec] == [3.0, 2.0, 1.0] and all(r["Option Value"] > 0 for r in rec)
+
+
+# ------------------------------------------------------------------------------------------------------
+# multi-GPU building blocks on one device: two contexts each own half the pairs
+# ------------------------------------------------------------------------------------------------------
+def test_path_sharded_sweep_equals_single(mods):
+    from options_model_b200 import engine as E2
+    from options_model_b200.sharded import shard_pairs
+
+    L, E, orc = mods
+    M, N, K = 8192, 12, 100.0
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    e0, e1 = E2.Engine(0), E2.Engine(0)
+    try:
+        full = e0.paths(model, M, N, "f64", E.RngSpec(seed=77)).clone()
+        single = e0.lsm(full, K, 0.05, 1.0, "put", impl="split")
+        shards = []
+        for rank, e in enumerate((e0, e1)):
+            off, m_loc = shard_pairs(M, rank, 2)
+            shards.append(e.paths(model, m_loc, N, "f64", E.RngSpec(seed=77, pair_offset=off)).clone())
+        q = e0.gram_len("poly2")
+        g = [torch.zeros(q, dtype=torch.float64, device="cuda") for _ in range(2)]
+        for e, S in zip((e0, e1), shards):
+            e.lsm_begin(S, K, 0.05, 1.0, "put")
+        for t in range(N - 1, 0, -1):
+            for e, gi in zip((e0, e1), g):
+                e.lsm_gram_date(t, gi)
+            tot = g[0] + g[1]  # stands in for the NCCL all-reduce
+            for e in (e0, e1):
+                e.lsm_update_date(t, tot)
+        s = [torch.zeros(3, dtype=torch.float64, device="cuda") for _ in range(2)]
+        for e, si in zip((e0, e1), s):
+            e.lsm_finish(si)
+        tot = (s[0] + s[1]).cpu().numpy()
+        assert tot[2] == M
+        assert tot[0] / tot[2] == pytest.approx(single.price, rel=1e-12)
+    finally:
+        e0.close(); e1.close()
+
+
+# ------------------------------------------------------------------------------------------------------
+# full BASELINE size: size-independent properties
+# ------------------------------------------------------------------------------------------------------
+def test_config2_full_size_properties(eng, mods):
+    """Config 2 (Heston put, 1M x 252, fp32): resident == split, American >= European, terminal-row checksum,
+    and the documented reference-semantics value (5.83 at N=252) within Monte-Carlo error."""
+    L, E, orc = mods
+    M, N, K = 1_000_000, 252, 100.0
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    S = eng.paths(model, M, N, "f32", E.RngSpec(seed=42))
+    assert torch.all(S[0] == 100.0) and torch.isfinite(S[N]).all() and (S[N] > 0).all()
+    a = eng.lsm(S, K, 0.05, 1.0, "put", impl="resident")
+    b = eng.lsm(S, K, 0.05, 1.0, "put", impl="split")
+    assert a.impl_used == L.SWEEP_RESIDENT and b.impl_used == L.SWEEP_SPLIT
+    assert a.price == pytest.approx(b.price, rel=1e-6)
+    assert np.abs(a.ex_count - b.ex_count).sum() <= 1e-5 * M * N
+    np.testing.assert_array_equal(a.n_itm[N - 1], b.n_itm[N - 1])
+    eu, eu_se = eng.european_from_slab(S[N].contiguous(), K, 0.05, 1.0, "put")
+    assert a.price > eu
+    assert abs(eu - 5.3234) < 0.05 and abs(a.price - 5.83) < 0.06
+    tb = eng.lsm(S, K, 0.05, 1.0, "put", semantics="textbook")
+    assert eu < tb.price < a.price  # look-ahead bias of the sticky mask (App. A, Q1)
