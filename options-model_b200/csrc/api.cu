@@ -194,9 +194,8 @@ int optmc_ctx_create(int device, optmc_ctx** out) {
   OPTMC_CUDA(cudaMemset(c->tickets, 0, 1024 * sizeof(unsigned int)));
   OPTMC_CUDA(cudaMalloc((void**)&c->gram, 16 * sizeof(double)));
   OPTMC_CUDA(cudaMalloc((void**)&c->d_final, 4 * sizeof(double)));
-  const size_t xb = (size_t)2 * kMaxResidentCtas * kXchgSlotDoubles * sizeof(double);
-  OPTMC_CUDA(cudaMalloc((void**)&c->xchg, xb));
-  OPTMC_CUDA(cudaMemset(c->xchg, 0, xb));
+  OPTMC_CUDA(cudaMalloc(&c->xchg, xchg_bytes()));
+  OPTMC_CUDA(cudaMemset(c->xchg, 0, xchg_bytes()));
   c->epoch = 0;
   *out = c;
   return OPTMC_OK;

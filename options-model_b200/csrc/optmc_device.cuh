@@ -33,6 +33,62 @@ template <int Q, int NWARPS> __device__ __forceinline__ void block_reduce_sum(do
   }
 }
 
+// Recursive-halving warp reduce-scatter of QP (power of two) doubles: QP + 3 adds instead of 5*QP.
+// On exit a[0] holds the warp total of quantity `reduce_scatter_index<QP>(lane)`; lanes that differ only
+// in the low log2(32/QP) lane bits hold identical copies.  Fixed pattern => deterministic.
+template <int QP> __device__ __forceinline__ void warp_reduce_scatter(double (&a)[QP], int lane) {
+  int width = QP;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    if (width > 1) {
+      const int half = width / 2;
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int i = 0; i < QP / 2; ++i) {
+        if (i < half) {
+          const double send = up ? a[i] : a[i + half];
+          const double keep = up ? a[i + half] : a[i];
+          a[i] = keep + shfl_xor_f64(send, m);
+        }
+      }
+      width = half;
+    } else {
+      a[0] += shfl_xor_f64(a[0], m);
+    }
+  }
+}
+template <int QP> __device__ __forceinline__ int reduce_scatter_index(int lane) {
+  int q = 0, width = QP;
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    if (width > 1) { q = q * 2 + ((lane & m) ? 1 : 0); width /= 2; }
+  }
+  return q;
+}
+template <int QP> __device__ __forceinline__ bool reduce_scatter_owner(int lane) {
+  return (lane & ((32 / QP) - 1)) == 0;  // one writer per quantity (QP <= 32)
+}
+
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+    v = o > v ? o : v;
+  }
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, v, m);
+    v = o < v ? o : v;
+  }
+  return v;
+}
+// Exercise-boundary bookkeeping: put -> max exercised S (bits of a positive double order like integers),
+// call -> min exercised S.  "none" is 0 for max and ~0 for min.
+__device__ __forceinline__ unsigned long long bnd_none(int is_put) { return is_put ? 0ull : ~0ull; }
+
 // ---- vector store / load of VEC consecutive elements -------------------------------------------------
 template <typename R, int VEC> struct VecIO;
 template <> struct VecIO<float, 4> {
@@ -101,6 +157,14 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
+}
+// LL-style exchange words: {payload32, epoch32} in one 8-byte scalar (single-copy atomic), two words per double.
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_v2u64(const unsigned long long* p, unsigned long long& a,
+                                                 unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");

@@ -8,8 +8,10 @@
 
 namespace optmc {
 
-constexpr int kXchgSlotDoubles = 16;  // one 128-byte line per CTA: [0..14] payload, [15] epoch
-constexpr int kMaxResidentCtas = 160; // gather handles 5 slots per lane
+constexpr int kXchgMaxQ = 16;         // quantities per exchange (poly3 needs 11)
+constexpr int kMaxResidentCtas = 160; // CTAs of the persistent sweep (B200: 148 SMs)
+// LL exchange buffer: [2 parities][kXchgMaxQ][kMaxResidentCtas][2 words of {payload32, epoch32}]
+inline size_t xchg_bytes() { return (size_t)2 * kXchgMaxQ * kMaxResidentCtas * 2 * sizeof(unsigned long long); }
 constexpr int kResThreads = 512;
 constexpr int kMaxBeta = 4;
 
@@ -60,7 +62,7 @@ struct optmc_ctx {
   int* d_valid = nullptr;               // [(N+1)]
   size_t per_date_cap = 0;              // N+1 capacity of the per-date arrays
   double* d_final = nullptr;            // [4] price, stderr, sum, sumsq
-  double* xchg = nullptr;               // [2][kMaxResidentCtas][kXchgSlotDoubles]
+  void* xchg = nullptr;                 // LL exchange words, xchg_bytes()
   unsigned long long epoch = 0;
   double* eu_out = nullptr; size_t eu_out_cap = 0;  // [n_options][3]
   double* eu_par = nullptr; size_t eu_par_cap = 0;  // [n_options][4] K, T, is_put, pad
@@ -89,6 +91,7 @@ int sweep_gram_date(optmc_ctx* ctx, int t, double* gram_out);       // split: lo
 int sweep_update_date(optmc_ctx* ctx, int t, const double* gram);   // split: solve + decide + discount
 int sweep_finish(optmc_ctx* ctx, double* sums_out);                 // split: sum(cf), sum(cf^2), n
 int sweep_finalize_price(optmc_ctx* ctx, const double* sums);       // split: d_final from sums
+int sweep_reset_stats(optmc_ctx* ctx);                              // NaN/none-initialise the per-date outputs
 bool resident_eligible(optmc_ctx* ctx, const SweepDesc& sw, std::string* why);
 int sweep_resident(optmc_ctx* ctx);                                 // one cooperative launch, all dates
 

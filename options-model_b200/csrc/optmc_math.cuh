@@ -106,7 +106,7 @@ template <> struct Real<double> {
   static OPTMC_HD double exp_(double x) { return exp(x); }
   static OPTMC_HD double sqrt_(double x) { return sqrt(x); }
   static OPTMC_HD void normal2(uint32_t a, uint32_t b, double& n0, double& n1) {
-    double u = ((double)a + 1.0) * 2.3283064365386963e-10;  // (0,1]
+    double u = ((double)(~a) + 1.0) * 2.3283064365386963e-10;  // 1 - a/2^32 in (0,1]: same map as the fp32 path
     double v = (double)b * 2.3283064365386963e-10;          // [0,1)
     double rad = sqrt(-2.0 * log(u));
     double s, c;
@@ -185,14 +185,21 @@ template <int DEG> struct Moments {
   static constexpr int Q = NM + NG;
 };
 
+// One row (x, y) into the moment vector with the fewest fp64 operations: powers up to DEG explicitly,
+// higher moments as one FMA each (x^k = x^DEG * x^(k-DEG)).
 template <int DEG> OPTMC_HD void moments_accumulate(double (&acc)[Moments<DEG>::Q], double x, double y) {
-  double p = 1.0;
+  double p[DEG + 1];
+  p[0] = 1.0;
 #pragma unroll
-  for (int k = 0; k <= 2 * DEG; ++k) {
-    acc[k] += p;
-    if (k <= DEG) acc[Moments<DEG>::NM + k] += p * y;
-    p *= x;
-  }
+  for (int k = 1; k <= DEG; ++k) p[k] = p[k - 1] * x;
+  acc[0] += 1.0;
+#pragma unroll
+  for (int k = 1; k <= DEG; ++k) acc[k] += p[k];
+#pragma unroll
+  for (int k = DEG + 1; k <= 2 * DEG; ++k) acc[k] = fma(p[DEG], p[k - DEG], acc[k]);
+  acc[Moments<DEG>::NM] += y;
+#pragma unroll
+  for (int k = 1; k <= DEG; ++k) acc[Moments<DEG>::NM + k] = fma(p[k], y, acc[Moments<DEG>::NM + k]);
 }
 
 #define OPTMC_PIVOT_RTOL 1e-14
@@ -204,7 +211,7 @@ template <int DEG> OPTMC_HD bool solve_poly(const double* mom, double* beta) {
   constexpr int NM = 2 * DEG + 1;
   if (!(mom[0] >= (double)P)) return false;
   double L[P][P];
-  double d[P];
+  double d[P], rd[P];
   double tr = 0.0;
 #pragma unroll
   for (int i = 0; i < P; ++i) tr += mom[2 * i];
@@ -215,12 +222,14 @@ template <int DEG> OPTMC_HD bool solve_poly(const double* mom, double* beta) {
     for (int j = 0; j < k; ++j) s -= L[k][j] * L[k][j] * d[j];
     if (!(s > OPTMC_PIVOT_RTOL * tr)) return false;
     d[k] = s;
+    const double rs = 1.0 / s;
+    rd[k] = rs;
 #pragma unroll
     for (int i = k + 1; i < P; ++i) {
       double u = mom[i + k];
 #pragma unroll
       for (int j = 0; j < k; ++j) u -= L[i][j] * L[k][j] * d[j];
-      L[i][k] = u / s;
+      L[i][k] = u * rs;
     }
   }
   double z[P];
@@ -232,7 +241,7 @@ template <int DEG> OPTMC_HD bool solve_poly(const double* mom, double* beta) {
     z[i] = a;
   }
 #pragma unroll
-  for (int i = 0; i < P; ++i) z[i] = z[i] / d[i];
+  for (int i = 0; i < P; ++i) z[i] = z[i] * rd[i];
 #pragma unroll
   for (int i = P - 1; i >= 0; --i) {
     double a = z[i];

@@ -1,0 +1,121 @@
+"""CPU: the per-path arithmetic shared by all kernels (csrc/optmc_math.cuh, host-compiled by g++) against the
+numpy oracle and the Random123 known-answer vectors.  The harness is test infrastructure, not a product path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import lsm_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HP = dict(v0=0.04, kappa=2.0, theta=0.04, xi=0.5, rho=-0.7)
+DP = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module")
+def hs(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("hostsim") / "libhostsim.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                    os.path.join(HERE, "hostsim", "host_math.cpp"), "-o", out], check=True)
+    return C.CDLL(out)
+
+
+def _p(a):
+    return a.ctypes.data_as(DP)
+
+
+def test_philox_kat(hs):
+    """Random123 Philox4x32-10 vectors."""
+    kats = [([0] * 4, [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+            ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+            ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+             [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1])]
+    for ctr, key, exp in kats:
+        c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
+        hs.hs_philox(c, k, o)
+        assert list(o) == exp
+
+
+@pytest.mark.parametrize("scheme", [2, 3, 4])
+def test_heston_step_functions_vs_oracle(hs, scheme):
+    rng = np.random.default_rng(4)
+    M, N = 256, 40
+    Z1, Z2 = orc.draw_heston_normals(rng, N, M)
+    S = np.zeros((N + 1, M)); V = np.zeros((N + 1, M))
+    hs.hs_heston_paths.argtypes = [C.c_int] + [C.c_double] * 8 + [C.c_long, C.c_int, DP, DP, DP, DP]
+    hs.hs_heston_paths(scheme, 100.0, HP["v0"], 0.05, 1.0, HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N,
+                       _p(Z1), _p(Z2), _p(S), _p(V))
+    if scheme == 2:
+        ref = orc.heston_paths_antithetic(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2)
+    elif scheme == 3:
+        ref = orc.heston_paths_full_truncation(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2)
+    else:  # calibrator: path-major, Z given path-major (n_sim, N)
+        Sp, _ = orc.hc_simulate_paths(HP["kappa"], HP["theta"], HP["xi"], HP["rho"], HP["v0"], 100.0, 1.0, 0.05, M, N,
+                                      np.ascontiguousarray(Z1.T), np.ascontiguousarray(Z2.T))
+        ref = Sp.T
+    np.testing.assert_allclose(S, ref, rtol=1e-12)
+    if scheme == 2:
+        assert (V >= 0).all() and (V == 0).any()  # the absorption at zero is exercised (Feller violated)
+
+
+def test_gbm_step_vs_oracle(hs):
+    rng = np.random.default_rng(5)
+    M, N = 128, 50
+    Z = orc.draw_gbm_normals(rng, N, M)
+    S = np.zeros((N + 1, M))
+    hs.hs_gbm_paths.argtypes = [C.c_double] * 4 + [C.c_long, C.c_int, DP, DP]
+    hs.hs_gbm_paths(100.0, 0.05, 0.2, 1.0, M, N, _p(Z), _p(S))
+    np.testing.assert_allclose(S, orc.gbm_paths_antithetic(100.0, 0.05, 0.2, 1.0, M, N, Z), rtol=1e-13)
+
+
+@pytest.mark.parametrize("deg", [2, 3])
+def test_moments_and_guarded_solve_vs_oracle(hs, deg):
+    rng = np.random.default_rng(6)
+    n = 20000
+    x = rng.uniform(0.55, 1.0, n); y = np.maximum(1 - x, 0) * 100 * rng.uniform(0.8, 1.2, n)
+    Q = 3 * deg + 2
+    mom = np.zeros(Q); beta = np.zeros(deg + 1)
+    hs.hs_fit.argtypes = [C.c_int, C.c_long, DP, DP, DP, DP]
+    assert hs.hs_fit(deg, n, _p(x), _p(y), _p(mom), _p(beta)) == 1
+    Phi = np.column_stack([x**i for i in range(deg + 1)])
+    G = Phi.T @ Phi
+    for i in range(deg + 1):
+        for j in range(deg + 1):
+            assert mom[i + j] == pytest.approx(G[i, j], rel=1e-12)
+    np.testing.assert_allclose(mom[2 * deg + 1:], Phi.T @ y, rtol=1e-12)
+    ref = orc.cholesky_solve_guarded(G, Phi.T @ y)
+    np.testing.assert_allclose(Phi @ beta, Phi @ ref, rtol=1e-8, atol=1e-8)
+    hs.hs_poly_eval.restype = C.c_double
+    hs.hs_poly_eval.argtypes = [C.c_int, DP, C.c_double]
+    assert hs.hs_poly_eval(deg, _p(beta), 0.8) == pytest.approx(float(np.polyval(beta[::-1], 0.8)), rel=1e-13)
+    # guard: fewer rows than columns, and a rank-deficient design
+    assert hs.hs_fit(deg, deg, _p(x), _p(y), _p(mom), _p(beta)) == 0
+    xc = np.full(100, 0.9)
+    assert hs.hs_fit(deg, 100, _p(xc), _p(y), _p(mom), _p(beta)) == 0
+
+
+def test_box_muller_transforms(hs):
+    rng = np.random.default_rng(7)
+    w = rng.integers(0, 2**32, size=(200000, 2), dtype=np.uint64)
+    o32 = (C.c_float * 2)(); o64 = (C.c_double * 2)()
+    hs.hs_normal2_f32.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]
+    hs.hs_normal2_f64.argtypes = [C.c_uint32, C.c_uint32, DP]
+    z32 = np.empty((20000, 2)); z64 = np.empty((20000, 2))
+    for i in range(20000):
+        hs.hs_normal2_f32(int(w[i, 0]), int(w[i, 1]), o32); z32[i] = o32[0], o32[1]
+        hs.hs_normal2_f64(int(w[i, 0]), int(w[i, 1]), o64); z64[i] = o64[0], o64[1]
+    for z in (z32, z64):
+        assert abs(z.mean()) < 0.03 and abs(z.var() - 1) < 0.04 and np.isfinite(z).all()
+    np.testing.assert_allclose(z32, z64, atol=2e-3)  # same words -> same normals up to the 2^-23 uniform grid
+    # extremes stay finite: u = 1 (a = 0) gives 0, the smallest u gives |z| < 6
+    hs.hs_normal2_f32(0, 0, o32); assert o32[0] == 0.0
+    hs.hs_normal2_f32(0xFFFFFFFF, 0, o32); assert 5 < o32[0] < 6
+
+
+def test_features_ref7(hs):
+    f = np.zeros(7)
+    hs.hs_features.argtypes = [C.c_double] * 3 + [DP]
+    hs.hs_features(130.0, 100.0, np.sqrt(0.7), _p(f))
+    np.testing.assert_allclose(f, orc.features_ref7(np.array([130.0]), 100.0, 0.05, 1.0, 0.3)[0], rtol=1e-15)

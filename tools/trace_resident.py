@@ -1,0 +1,33 @@
+"""Dump per-date phase clocks of the resident sweep (OPTMC_TRACE) and print a per-phase summary (cycles)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/trace.txt"
+M = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 252
+from options_model_b200 import engine as E  # noqa: E402
+
+eng = E.Engine(0)
+model = E.heston(100.0, 0.05, 1.0, v0=0.04, kappa=2.0, theta=0.04, xi=0.5, rho=-0.7)
+S = eng.paths(model, M, N, "f32", E.RngSpec(seed=1))
+eng.lsm(S, 100.0, 0.05, 1.0, "put", impl="resident")  # warm
+os.environ["OPTMC_TRACE"] = out
+r = eng.lsm(S, 100.0, 0.05, 1.0, "put", impl="resident")
+del os.environ["OPTMC_TRACE"]
+print("price", r.price)
+rows = np.loadtxt(out, comments="#")
+names = ["gram loop", "reduce-scatter+sync", "block total+publish", "gather (spin)", "sync+totals+stats", "solve+sync",
+         "update + next wait"]
+for c in (0, 1):
+    a = rows[rows[:, 0] == c][:, 2:]
+    per_date = a[1:, 0] - a[:-1, 0]
+    print(f"cta {'first' if c == 0 else 'last'}: per-date total {np.median(per_date):.0f} cycles; spins median "
+          f"{np.median(a[:, 7]):.0f} p90 {np.percentile(a[:, 7], 90):.0f}")
+    d = np.diff(a[:, :7], axis=1)
+    for k in range(6):
+        print(f"   {names[k]:24s} median {np.median(d[:, k]):8.0f}  p90 {np.percentile(d[:, k], 90):8.0f}")
+    nxt = a[1:, 0] - a[:-1, 6]
+    print(f"   {names[6]:24s} median {np.median(nxt):8.0f}  p90 {np.percentile(nxt, 90):8.0f}")
