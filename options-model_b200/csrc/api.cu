@@ -113,6 +113,25 @@ static int fetch_results(optmc_ctx* ctx, optmc_lsm_result* out) {
   std::vector<double> hb;
   std::vector<unsigned long long> hbnd, hexc;
   std::vector<long long> hn;
+  if (sw.impl_used == OPTMC_SWEEP_RESIDENT) {
+    // The persistent sweep sums Gram moments in fixed point (|moment| < 2^43).  On overflow (or NaN/Inf
+    // prices) AUTO repeats the sweep with the split kernels; an explicit RESIDENT request fails loudly.
+    int flags[4] = {0, 0, 0, 0};
+    OPTMC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (flags[0]) {
+      if (sw.lp.impl != OPTMC_SWEEP_AUTO) {
+        set_error("resident sweep: a Gram moment left the fixed-point exchange range (|m| < 2^43) or is not finite; use impl = SPLIT");
+        return OPTMC_EUNSUPPORTED;
+      }
+      const int launches = sw.n_launches;
+      sw.lp.impl = OPTMC_SWEEP_SPLIT;
+      int rc = run_sweep(ctx);
+      sw.lp.impl = OPTMC_SWEEP_AUTO;
+      if (rc) return rc;
+      sw.n_launches += launches;
+    }
+  }
   OPTMC_CUDA(cudaMemcpyAsync(fin, ctx->d_final, sizeof(fin), cudaMemcpyDeviceToHost, ctx->stream));
   if (out->betas) { hb.resize((size_t)n1 * kMaxBeta); OPTMC_CUDA(cudaMemcpyAsync(hb.data(), ctx->d_betas, hb.size() * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
   if (out->boundary) { hbnd.resize(n1); OPTMC_CUDA(cudaMemcpyAsync(hbnd.data(), ctx->d_bnd, (size_t)n1 * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
@@ -196,7 +215,8 @@ int optmc_ctx_create(int device, optmc_ctx** out) {
   OPTMC_CUDA(cudaMalloc((void**)&c->d_final, 4 * sizeof(double)));
   OPTMC_CUDA(cudaMalloc(&c->xchg, xchg_bytes()));
   OPTMC_CUDA(cudaMemset(c->xchg, 0, xchg_bytes()));
-  c->epoch = 0;
+  OPTMC_CUDA(cudaMalloc((void**)&c->d_flags, 4 * sizeof(int)));
+  OPTMC_CUDA(cudaMemset(c->d_flags, 0, 4 * sizeof(int)));
   *out = c;
   return OPTMC_OK;
   OPTMC_TRY_END
@@ -208,7 +228,7 @@ int optmc_ctx_destroy(optmc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->slab); cudaFree(ctx->cf); cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->gram);
   cudaFree(ctx->d_betas); cudaFree(ctx->d_bnd); cudaFree(ctx->d_exc); cudaFree(ctx->d_nitm); cudaFree(ctx->d_valid);
-  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
+  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return OPTMC_OK;

@@ -173,8 +173,12 @@ __global__ void lsm_price_from_sums_kernel(const double* sums, double scale, dou
 }
 
 __global__ void lsm_reset_stats_kernel(int n1, int is_put, double* betas, unsigned long long* bnd,
-                                       unsigned long long* exc, long long* nitm, int* valid) {
+                                       unsigned long long* exc, long long* nitm, int* valid,
+                                       unsigned long long* xchg, int xchg_words, int* flags) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // the persistent sweep's exchange accumulators and overflow flag start every sweep at zero
+  for (int i = t; i < xchg_words; i += gridDim.x * blockDim.x) xchg[i] = 0ull;
+  if (t < 4) flags[t] = 0;
   if (t >= n1) return;
   for (int i = 0; i < kMaxBeta; ++i) betas[t * kMaxBeta + i] = nan("");
   bnd[t] = bnd_none(is_put);
@@ -195,7 +199,9 @@ int sweep_reset_stats(optmc_ctx* ctx) {
   const SweepDesc& sw = ctx->sw;
   const int n1 = sw.N + 1;
   lsm_reset_stats_kernel<<<(n1 + 127) / 128, 128, 0, ctx->stream>>>(n1, sw.lp.is_put, ctx->d_betas, ctx->d_bnd,
-                                                                    ctx->d_exc, ctx->d_nitm, ctx->d_valid);
+                                                                    ctx->d_exc, ctx->d_nitm, ctx->d_valid,
+                                                                    reinterpret_cast<unsigned long long*>(ctx->xchg),
+                                                                    (int)(xchg_bytes() / 8), ctx->d_flags);
   ctx->launches++; ctx->sw.n_launches++;
   OPTMC_CUDA(cudaGetLastError());
   return OPTMC_OK;

@@ -5,13 +5,14 @@
 //     (PPT values per thread; the reference's `exercised` flag, om3:617/649, is the sign bit);
 //   * each date's slice of the step-major price slab is staged into shared memory by the TMA engine
 //     (1-D cp.async.bulk + mbarrier), 2-3 dates ahead of use, so HBM sees S exactly once;
-//   * per date: masked Gram moments in fp64 (thread) -> recursive-halving reduce-scatter (warp) -> shared
-//     memory (block) -> all-gather of the CTA totals through L2 -> guarded LDL^T solve -> fused
-//     exercise decision / cash-flow update.
-//   * the cross-CTA exchange is an LL-style protocol: every double travels as two 8-byte words
-//     {payload32, epoch32}; a word is valid when its epoch matches, so there are no fences, no atomics and
-//     no grid-wide barrier on the data path, and all 16 warps gather in parallel.  Summation order is fixed
-//     => bit-reproducible betas on every CTA and from run to run.
+//   * per date: masked Gram moments of the raw price in fp64 (thread) -> recursive-halving reduce-scatter
+//     (warp) -> shared memory (block) -> grid-wide sum -> guarded LDL^T solve (warp 0) -> fused exercise
+//     decision / cash-flow update.
+//   * the grid-wide sum is ORDER-INDEPENDENT: every block total is split into two 48-bit fixed-point
+//     chunks (optmc_math.cuh: fx_encode) and added with one integer `red` per chunk into a per-parity
+//     accumulator word whose top 8 bits count arrivals.  Sum and completion flag are the same word, so
+//     there is no fence, no second flag and no grid-wide barrier on the data path; one lane polls each
+//     word.  Integer addition commutes => betas are bit-reproducible on every CTA and from run to run.
 //
 // Replaces the Python loop of om3:615-651 (= om3:485-500, om2:278-310) for the polynomial regressor of
 // SURVEY.md 8(c).  Semantics flags: sticky mask (om3:621,649), N-1 discounts (om3:619-620,651).
@@ -28,8 +29,6 @@
 namespace optmc {
 
 constexpr int kResWarps = kResThreads / 32;
-constexpr int kGatherChunk = 96;                                  // CTAs per gather item: 3 per lane
-constexpr int kGatherParts = (kMaxResidentCtas + kGatherChunk - 1) / kGatherChunk;  // 2
 
 struct ResArgs {
   const void* S;
@@ -38,9 +37,9 @@ struct ResArgs {
   unsigned int stage_stride;  // bytes between stages in shared memory
   double K, invK, disc, final_scale;
   double Kcmp;                // float-exact threshold equivalent to K for the fp32 ITM test
-  int is_put, sticky;
-  unsigned long long* xw;     // exchange words [2][kXchgMaxQ][kMaxResidentCtas][2]
-  unsigned int epoch_base;
+  int is_put, sticky, k_exact;  // k_exact: K is representable in the storage type
+  unsigned long long* xw;     // exchange accumulators [2][kXchgWords][kXchgStride]
+  int* flags;                 // [0] = exchange overflow
   double* betas;              // [(N+1)][kMaxBeta]
   unsigned long long* bnd;    // [(N+1)]
   unsigned long long* exc;    // [(N+1)]
@@ -49,34 +48,45 @@ struct ResArgs {
   long long* trace;           // optional [2][(N+1)][8] phase clocks of the first and last CTA (OPTMC_TRACE)
 };
 
-#define OPTMC_TRACE_AT(ph)                                                                         \
-  do {                                                                                             \
-    if (a.trace && tid == 0 && (cta == 0 || cta == ncta - 1))                                      \
-      a.trace[((size_t)(cta == 0 ? 0 : 1) * (N + 1) + t) * 8 + (ph)] = clock64();                  \
-  } while (0)
-
 template <int QN> struct Pow2 { static constexpr int v = QN <= 2 ? 2 : QN <= 4 ? 4 : QN <= 8 ? 8 : 16; };
 
-__device__ __forceinline__ size_t xw_index(int par, int q, int cta) {
-  return (((size_t)par * kXchgMaxQ + q) * kMaxResidentCtas + cta) * 2;
-}
+// ---- storage-type helpers ------------------------------------------------------------------------------
+template <typename R> struct Store;
+template <> struct Store<float> {
+  static __device__ __forceinline__ bool itm(float s, double, double Kcmp, bool is_put) {
+    return is_put ? s < (float)Kcmp : s > (float)Kcmp;  // exact: Kcmp is the float bracket of K on the right side
+  }
+  // payoff rounded to storage exactly as (float)(K - (double)s): the fp32 subtraction is the correctly
+  // rounded exact difference when K is a float, otherwise go through fp64.
+  static __device__ __forceinline__ float pay(float s, double K, bool is_put, bool k_exact) {
+    if (k_exact) return is_put ? (float)K - s : s - (float)K;
+    return (float)(is_put ? K - (double)s : (double)s - K);
+  }
+  // order-preserving map of a float onto unsigned integers (boundary statistics)
+  static __device__ __forceinline__ unsigned int key(float s) {
+    const unsigned int b = __float_as_uint(s);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  }
+  static __device__ __forceinline__ double unkey(unsigned int k) {
+    const unsigned int b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return (double)__uint_as_float(b);
+  }
+};
+template <> struct Store<double> {
+  static __device__ __forceinline__ bool itm(double s, double K, double, bool is_put) { return is_put ? s < K : s > K; }
+  static __device__ __forceinline__ double pay(double s, double K, bool is_put, bool) { return is_put ? K - s : s - K; }
+};
 
-// Block-wide sum of QN per-thread doubles followed by the grid-wide all-gather.  Every thread calls it.
-// On return s_tot[0..QN) holds the GRID totals (visible to every thread).  Shared scratch: s_red
-// [kResWarps][QP], s_part [QN][kGatherParts].
-template <int QN>
-__device__ __forceinline__ void grid_allreduce(double (&acc)[Pow2<QN>::v], double* s_red, double* s_part,
-                                               double* s_tot, unsigned long long* xw, int par, int cta, int ncta,
-                                               unsigned int epoch, long long* tr = nullptr) {
-  constexpr int QP = Pow2<QN>::v;
+// Block-wide sum of QP (power of two) per-thread doubles.  Every thread calls it; contains one
+// __syncthreads.  On return, in warp 0, lane l < 2*QP holds the CTA total of quantity l >> 1.
+template <int QP>
+__device__ __forceinline__ double block_totals(double (&acc)[QP], double* s_red) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // 1. warp: recursive-halving reduce-scatter (QP + 3 adds per lane instead of 5 QP)
   warp_reduce_scatter<QP>(acc, lane);
   if (reduce_scatter_owner<QP>(lane)) s_red[warp * QP + reduce_scatter_index<QP>(lane)] = acc[0];
   __syncthreads();
-  if (tr) tr[2] = clock64();
-  // 2. warp 0: block total and publish.  lane -> quantity lane % QP, group lane / QP sums warps g, g+G, ...
-  if (warp == 0) {
+  double t = 0.0;
+  if (warp == 0) {  // lane -> quantity lane % QP; group lane / QP sums warps g, g+G, ...
     constexpr int G = 32 / QP;
     const int q = lane % QP, g = lane / QP;
     double v = 0.0;
@@ -85,69 +95,46 @@ __device__ __forceinline__ void grid_allreduce(double (&acc)[Pow2<QN>::v], doubl
       if (w + g < kResWarps) v += s_red[(w + g) * QP + q];
 #pragma unroll
     for (int m = QP; m <= 16; m <<= 1) v += shfl_xor_f64(v, m);
-    const double t = __shfl_sync(0xffffffffu, v, (lane >> 1) % QP);  // lane l publishes half (l & 1) of quantity l >> 1
-    if (lane < 2 * QN) {
-      const unsigned long long bits = (unsigned long long)__double_as_longlong(t);
-      const unsigned int payload = (lane & 1) ? (unsigned int)(bits >> 32) : (unsigned int)bits;
-      st_relaxed_u64(xw + xw_index(par, lane >> 1, cta) + (lane & 1), ((unsigned long long)epoch << 32) | payload);
-    }
+    t = __shfl_sync(0xffffffffu, v, (lane >> 1) % QP);
   }
-  if (tr) tr[3] = clock64();
-  int spins = 0;
-  // 3. every warp gathers: item = (quantity, part); lane handles CTAs part*96 + lane + 32 i
-  for (int item = warp; item < QN * kGatherParts; item += kResWarps) {
-    const int q = item / kGatherParts, part = item % kGatherParts;
-    const unsigned long long* base = xw + xw_index(par, q, 0);
-    double val[3];
-    bool ready[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int c = part * kGatherChunk + lane + 32 * i;
-      ready[i] = c >= ncta;
-      val[i] = 0.0;
-    }
-    bool all;
-    do {
-      all = true;
-      ++spins;
-      unsigned long long w0[3], w1[3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-        if (!ready[i]) ld_relaxed_v2u64(base + (size_t)(part * kGatherChunk + lane + 32 * i) * 2, w0[i], w1[i]);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (!ready[i]) {
-          if ((unsigned int)(w0[i] >> 32) == epoch && (unsigned int)(w1[i] >> 32) == epoch) {
-            val[i] = __longlong_as_double((long long)((w1[i] << 32) | (w0[i] & 0xffffffffull)));
-            ready[i] = true;
-          } else {
-            all = false;
-          }
-        }
-      }
-    } while (!all);
-    double s = (val[0] + val[1]) + val[2];
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) s += shfl_xor_f64(s, m);
-    if (lane == 0) s_part[q * kGatherParts + part] = s;
-  }
-  if (tr) { tr[4] = clock64(); tr[7] = spins; }
-  __syncthreads();
-  if (tid < QN) {
-    double s = s_part[tid * kGatherParts];
-#pragma unroll
-    for (int p = 1; p < kGatherParts; ++p) s += s_part[tid * kGatherParts + p];
-    s_tot[tid] = s;
-  }
+  return t;
 }
 
-template <typename R> __device__ __forceinline__ bool itm_test(R s, double K, double Kcmp, bool is_put);
-template <> __device__ __forceinline__ bool itm_test<float>(float s, double, double Kcmp, bool is_put) {
-  return is_put ? s < (float)Kcmp : s > (float)Kcmp;  // exact: Kcmp is the float bracket of K on the right side
+// Warp 0 only.  `mine`: this CTA's total of quantity lane >> 1 (lanes < 2*QN), already in its final
+// units.  Adds it into the parity's accumulators, waits until all `ncta` CTAs have arrived and returns
+// the grid total of quantity `lane` in lanes < QN.  prev = this lane's accumulator value after the last
+// completed exchange of the same parity (0 at launch).
+template <int QN>
+__device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long* xw, int par, int ncta,
+                                                 unsigned long long& prev, int* flags, int* spins_out) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long sum = 0ull;
+  int spins = 0;
+  if (lane < 2 * QN) {
+    unsigned long long hi, lo;
+    if (!fx_encode(mine, hi, lo)) atomicExch(flags, 1);
+    unsigned long long* w = xw + ((size_t)par * kXchgWords + lane) * kXchgStride;
+    red_relaxed_add_u64(w, (1ull << kFxCountShift) | ((lane & 1) ? lo : hi));
+    unsigned long long d;
+    do {
+      d = ld_relaxed_u64(w) - prev;
+      ++spins;
+    } while ((d >> kFxCountShift) != (unsigned long long)ncta);
+    prev += d;
+    sum = d & kFxValueMask;
+  }
+  __syncwarp();
+  const unsigned long long other = __shfl_down_sync(0xffffffffu, sum, 1);
+  double tot = fx_decode(sum, other, ncta);                 // meaningful on even lanes < 2*QN
+  tot = __shfl_sync(0xffffffffu, tot, (2 * lane) & 31);     // quantity q: lane 2q -> lane q
+  if (spins_out) *spins_out = spins;
+  return tot;
 }
-template <> __device__ __forceinline__ bool itm_test<double>(double s, double K, double, bool is_put) {
-  return is_put ? s < K : s > K;
-}
+
+#define OPTMC_TRACE_AT(ph)            \
+  do {                                \
+    if (tr) tr[(ph)] = clock64();     \
+  } while (0)
 
 template <typename R, int DEG, int PPT>
 __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResArgs a) {
@@ -156,15 +143,13 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
   static_assert(Q <= kXchgMaxQ, "Gram vector must fit the exchange buffer");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t mbar[3];
-  __shared__ double s_red[kResWarps * QP];
-  __shared__ double s_part[Q * kGatherParts];
-  __shared__ double s_tot[Q];
-  __shared__ double s_beta[DEG + 1];
+  __shared__ double s_red[kResWarps * 16];
+  __shared__ double s_dec[DEG + 1];   // exercise iff s_dec(s) > 0  (payoff - continuation as a polynomial in S)
   __shared__ int s_valid;
   __shared__ unsigned long long s_bnd[2];
   __shared__ unsigned int s_cnt[2];
 
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const long long base = (long long)cta * a.chunk;
   const long long rem = a.M - base;
@@ -172,6 +157,7 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
   const unsigned int bytes = (unsigned int)(((size_t)n_local * sizeof(R) + 15) / 16 * 16);
   const bool is_put = a.is_put != 0;
   const bool sticky = a.sticky != 0;
+  const bool k_exact = a.k_exact != 0;
   const R disc = (R)a.disc;
   const int N = a.N, nstage = a.nstage;
   const R* Sbase = static_cast<const R*>(a.S) + base;
@@ -179,7 +165,7 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
   auto stage_ptr = [&](int t) -> const R* {
     return reinterpret_cast<const R*>(smem_raw + (size_t)(t % nstage) * a.stage_stride);
   };
-  auto issue_load = [&](int t) {  // thread 0 only
+  auto issue_load = [&](int t) {  // one thread
     uint64_t* bar = &mbar[t % nstage];
     mbar_arrive_expect_tx(bar, bytes);
     bulk_load_1d(smem_raw + (size_t)(t % nstage) * a.stage_stride, Sbase + (size_t)t * a.ld, bytes, bar);
@@ -198,6 +184,17 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
       if (N - i >= 1) issue_load(N - i);
   }
 
+  // warp-0 lane constants: lane l serves quantity l >> 1; raw-price moments are rescaled to x = S/K
+  // (the regressor of SURVEY.md 8(c)) by invK^power before they enter the exchange.
+  double qscale = 1.0;
+  {
+    const int pw = moment_power<DEG>(lane >> 1);
+    for (int i = 0; i < pw; ++i) qscale *= a.invK;
+  }
+  unsigned long long prev0 = 0ull, prev1 = 0ull;  // warp 0: accumulator baselines of the two parities
+  long long* const tr_base = (a.trace && tid == 0 && (cta == 0 || cta == ncta - 1))
+                                 ? a.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * 8 : nullptr;
+
   // ---- date N: cash-flows = payoff(S[N]) (om3:616) ----
   R cf[PPT];
   wait_stage(N);
@@ -206,22 +203,28 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       const int j = tid + k * kResThreads;
-      cf[k] = (j < n_local) ? (R)payoff<double>((double)st[j], a.K, is_put) : (R)0;
+      R c = (R)0;
+      if (j < n_local) {
+        const R s = st[j];
+        if (Store<R>::itm(s, a.K, a.Kcmp, is_put)) c = Store<R>::pay(s, a.K, is_put, k_exact);
+      }
+      cf[k] = c;
     }
   }
 
-  for (int t = N - 1; t >= 1; --t) {
+  int seq = 0;
+  for (int t = N - 1; t >= 1; --t, ++seq) {
+    long long* tr = tr_base ? tr_base + (size_t)t * 8 : nullptr;
     wait_stage(t);
     OPTMC_TRACE_AT(0);
     const R* st = stage_ptr(t);
-    // -- discount every path (om3:620), then the ITM-masked Gram moments in fp64 (om3:621 mask) --
+    // -- discount every path (om3:620), then the ITM-masked moments of the raw price in fp64 (om3:621 mask) --
     double acc[QP];
-#pragma unroll
-    for (int q = 0; q < QP; ++q) acc[q] = 0.0;
     {
       double mom[Q];
 #pragma unroll
       for (int q = 0; q < Q; ++q) mom[q] = 0.0;
+      unsigned int rows = 0;
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         const int j = tid + k * kResThreads;
@@ -231,18 +234,21 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
           const R y = fabs(c) * disc;
           cf[k] = ex ? -y : y;
           const R s = st[j];
-          if (!ex && itm_test<R>(s, a.K, a.Kcmp, is_put)) moments_accumulate<DEG>(mom, (double)s * a.invK, (double)y);
+          if (!ex && Store<R>::itm(s, a.K, a.Kcmp, is_put)) {
+            ++rows;
+            moments_accumulate_nocount<DEG>(mom, (double)s, (double)y);
+          }
         }
       }
+      mom[0] = (double)rows;
 #pragma unroll
-      for (int q = 0; q < Q; ++q) acc[q] = mom[q];
+      for (int q = 0; q < QP; ++q) acc[q] = q < Q ? mom[q] : 0.0;
     }
     OPTMC_TRACE_AT(1);
-    // the first __syncthreads inside grid_allreduce also proves every thread is done with stage (t+1)
-    long long* tr = (a.trace && tid == 0 && (cta == 0 || cta == ncta - 1))
-                        ? a.trace + ((size_t)(cta == 0 ? 0 : 1) * (N + 1) + t) * 8 : nullptr;
-    grid_allreduce<Q>(acc, s_red, s_part, s_tot, a.xw, t & 1, cta, ncta, a.epoch_base + (unsigned int)(N - t), tr);
-    if (tid == 0) {
+    // the __syncthreads inside block_totals also proves every thread is done with stage (t+1)
+    const double mine = block_totals<QP>(acc, s_red) * qscale;
+    OPTMC_TRACE_AT(2);
+    if (tid == 32) {  // bookkeeping off the critical path (warp 1)
       if (t + 1 <= N - 1) {  // flush the exercise statistics of date t+1
         const int p = (t + 1) & 1;
         if (s_cnt[p]) {
@@ -254,54 +260,71 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
       }
       if (t + 1 - nstage >= 1) issue_load(t + 1 - nstage);  // refill the stage date t+1 vacated
     }
-    __syncthreads();  // s_tot visible
-    OPTMC_TRACE_AT(5);
-    if (tid == 0) {
+    if (warp == 0) {
+      int spins = 0;
+      unsigned long long pv = (seq & 1) ? prev1 : prev0;
+      const double tot_l = warp0_grid_sum<Q>(mine, a.xw, seq & 1, ncta, pv, a.flags, &spins);
+      if (seq & 1) prev1 = pv; else prev0 = pv;
+      OPTMC_TRACE_AT(4);
+      if (tr) tr[7] = spins;
       double tot[Q], beta[DEG + 1];
 #pragma unroll
-      for (int q = 0; q < Q; ++q) tot[q] = s_tot[q];
-      const bool ok = solve_poly<DEG>(tot, beta);
-      s_valid = ok ? 1 : 0;
+      for (int q = 0; q < Q; ++q) tot[q] = __shfl_sync(0xffffffffu, tot_l, q);
+      const bool ok = solve_poly<DEG>(tot, beta);  // every lane, identical inputs: no divergence
+      if (lane == 0) {
+        s_valid = ok ? 1 : 0;
+        if (ok) {
+          // payoff - continuation = (+-K - b0) + (-+1 - b1/K) S - (b2/K^2) S^2 ...  (x = S/K)
+          double sc = 1.0;
 #pragma unroll
-      for (int i = 0; i <= DEG; ++i) s_beta[i] = ok ? beta[i] : 0.0;
-      if (cta == 0) {
+          for (int i = 0; i <= DEG; ++i) {
+            double d = -beta[i] * sc;
+            if (i == 0) d += is_put ? a.K : -a.K;
+            if (i == 1) d += is_put ? -1.0 : 1.0;
+            s_dec[i] = d;
+            sc *= a.invK;
+          }
+        }
+        if (cta == 0) {
 #pragma unroll
-        for (int i = 0; i <= DEG; ++i) a.betas[(size_t)t * kMaxBeta + i] = ok ? beta[i] : nan("");
-        a.nitm[t] = (long long)(tot[0] + 0.5);
+          for (int i = 0; i <= DEG; ++i) a.betas[(size_t)t * kMaxBeta + i] = ok ? beta[i] : nan("");
+          a.nitm[t] = (long long)(tot[0] + 0.5);
+        }
       }
+      OPTMC_TRACE_AT(5);
     }
-    __syncthreads();  // beta visible
+    __syncthreads();  // decision polynomial visible
     OPTMC_TRACE_AT(6);
     if (s_valid) {
-      double beta[DEG + 1];
+      double dec[DEG + 1];
 #pragma unroll
-      for (int i = 0; i <= DEG; ++i) beta[i] = s_beta[i];
+      for (int i = 0; i <= DEG; ++i) dec[i] = s_dec[i];
       unsigned int cnt = 0;
-      unsigned long long bnd = bnd_none(a.is_put);
+      R ext = is_put ? (R)-INFINITY : (R)INFINITY;  // max (put) / min (call) exercised price
 #pragma unroll
       for (int k = 0; k < PPT; ++k) {
         const int j = tid + k * kResThreads;
         if (j < n_local) {
           const R c = cf[k];
           const R sr = st[j];
-          if (!(sticky && signbit(c)) && itm_test<R>(sr, a.K, a.Kcmp, is_put)) {
-            const double s = (double)sr;
-            const double pay = is_put ? a.K - s : s - a.K;
-            if (pay > poly_eval<DEG>(beta, s * a.invK)) {   // strict '>' (om3:644)
-              cf[k] = sticky ? -(R)pay : (R)pay;            // sticky flag = sign bit (om3:649)
+          if (!(sticky && signbit(c)) && Store<R>::itm(sr, a.K, a.Kcmp, is_put)) {
+            if (poly_eval<DEG>(dec, (double)sr) > 0.0) {   // strict '>' (om3:644)
+              const R pay = Store<R>::pay(sr, a.K, is_put, k_exact);
+              cf[k] = sticky ? -pay : pay;                 // sticky flag = sign bit (om3:649)
               cnt++;
-              const unsigned long long b = (unsigned long long)__double_as_longlong(s);
-              bnd = is_put ? (b > bnd ? b : bnd) : (b < bnd ? b : bnd);
+              ext = is_put ? (sr > ext ? sr : ext) : (sr < ext ? sr : ext);
             }
           }
         }
       }
       cnt = __reduce_add_sync(0xffffffffu, cnt);
       if (cnt) {  // warp-uniform
-        bnd = is_put ? warp_max_u64(bnd) : warp_min_u64(bnd);
+        unsigned long long b = (unsigned long long)__double_as_longlong((double)ext);
+        if (!isfinite((double)ext)) b = bnd_none(a.is_put);
+        b = is_put ? warp_max_u64(b) : warp_min_u64(b);
         if (lane == 0) {
           atomicAdd(&s_cnt[t & 1], cnt);
-          if (is_put) atomicMax(&s_bnd[t & 1], bnd); else atomicMin(&s_bnd[t & 1], bnd);
+          if (is_put) atomicMax(&s_bnd[t & 1], b); else atomicMin(&s_bnd[t & 1], b);
         }
       }
     }
@@ -318,23 +341,27 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
       fin[1] += c * c;
     }
   }
-  grid_allreduce<2>(fin, s_red, s_part, s_tot, a.xw, 0, cta, ncta, a.epoch_base + (unsigned int)N);
-  if (tid == 0 && N - 1 >= 1) {  // statistics of date 1 (all update loops are behind the barriers above)
+  const double mine = block_totals<2>(fin, s_red);
+  if (tid == 32 && N - 1 >= 1) {  // statistics of date 1 (all update loops are behind the barrier above)
     if (s_cnt[1]) {
       atomicAdd(a.exc + 1, (unsigned long long)s_cnt[1]);
       if (is_put) atomicMax(a.bnd + 1, s_bnd[1]); else atomicMin(a.bnd + 1, s_bnd[1]);
     }
   }
-  __syncthreads();
-  if (cta == 0 && tid == 0) {
-    const double n = (double)a.M;
-    const double mean = s_tot[0] / n;
-    double var = n > 1.0 ? (s_tot[1] - n * mean * mean) / (n - 1.0) : 0.0;
-    if (var < 0.0) var = 0.0;
-    a.final_out[0] = mean * a.final_scale;
-    a.final_out[1] = sqrt(var / n) * a.final_scale;
-    a.final_out[2] = s_tot[0];
-    a.final_out[3] = s_tot[1];
+  if (warp == 0) {
+    unsigned long long pv = (seq & 1) ? prev1 : prev0;
+    const double tot_l = warp0_grid_sum<2>(mine, a.xw, seq & 1, ncta, pv, a.flags, nullptr);
+    const double s1 = __shfl_sync(0xffffffffu, tot_l, 0), s2 = __shfl_sync(0xffffffffu, tot_l, 1);
+    if (cta == 0 && lane == 0) {
+      const double n = (double)a.M;
+      const double mean = s1 / n;
+      double var = n > 1.0 ? (s2 - n * mean * mean) / (n - 1.0) : 0.0;
+      if (var < 0.0) var = 0.0;
+      a.final_out[0] = mean * a.final_scale;
+      a.final_out[1] = sqrt(var / n) * a.final_scale;
+      a.final_out[2] = s1;
+      a.final_out[3] = s2;
+    }
   }
 }
 
@@ -408,26 +435,22 @@ int sweep_resident(optmc_ctx* ctx) {
   ResPlan p;
   std::string why;
   if (!plan_resident(ctx, sw, &p, &why)) { set_error("resident sweep unavailable: " + why); return OPTMC_EUNSUPPORTED; }
-  int rc = sweep_reset_stats(ctx);
+  int rc = sweep_reset_stats(ctx);  // also zeroes the exchange accumulators and the overflow flag
   if (rc) return rc;
-  if (ctx->epoch > 0xFFFF0000u - (unsigned)sw.N) {  // 32-bit epoch about to wrap: start a fresh era
-    OPTMC_CUDA(cudaMemsetAsync(ctx->xchg, 0, xchg_bytes(), ctx->stream));
-    ctx->epoch = 0;
-  }
   ResArgs a{};
   a.S = sw.S; a.ld = sw.ld; a.M = sw.M; a.chunk = p.chunk; a.N = sw.N; a.nstage = p.nstage;
   a.stage_stride = p.stage_stride;
   a.K = sw.lp.K; a.invK = 1.0 / sw.lp.K; a.disc = sw.disc; a.final_scale = sw.final_scale;
   {  // float threshold with (s < K) <=> (s < Kcmp) for every float s (puts); mirrored for calls
     float kf = (float)sw.lp.K;
+    a.k_exact = sw.dtype == OPTMC_F64 ? 1 : ((double)kf == sw.lp.K ? 1 : 0);
     if (sw.lp.is_put) { if ((double)kf < sw.lp.K) kf = nextafterf(kf, INFINITY); }
     else { if ((double)kf > sw.lp.K) kf = nextafterf(kf, -INFINITY); }
     a.Kcmp = (double)kf;
   }
   a.is_put = sw.lp.is_put; a.sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) ? 1 : 0;
-  a.xw = reinterpret_cast<unsigned long long*>(ctx->xchg); a.epoch_base = (unsigned int)ctx->epoch;
+  a.xw = reinterpret_cast<unsigned long long*>(ctx->xchg); a.flags = ctx->d_flags;
   a.betas = ctx->d_betas; a.bnd = ctx->d_bnd; a.exc = ctx->d_exc; a.nitm = ctx->d_nitm; a.final_out = ctx->d_final;
-  ctx->epoch += (unsigned long long)sw.N + 2ull;
   // Debug aid: OPTMC_TRACE=<file> dumps per-date phase clocks (SM cycles) of the first and last CTA.
   const char* trace_path = getenv("OPTMC_TRACE");
   long long* d_trace = nullptr;

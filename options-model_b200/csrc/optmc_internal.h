@@ -9,9 +9,12 @@
 namespace optmc {
 
 constexpr int kXchgMaxQ = 16;         // quantities per exchange (poly3 needs 11)
-constexpr int kMaxResidentCtas = 160; // CTAs of the persistent sweep (B200: 148 SMs)
-// LL exchange buffer: [2 parities][kXchgMaxQ][kMaxResidentCtas][2 words of {payload32, epoch32}]
-inline size_t xchg_bytes() { return (size_t)2 * kXchgMaxQ * kMaxResidentCtas * 2 * sizeof(unsigned long long); }
+constexpr int kMaxResidentCtas = 160; // CTAs of the persistent sweep (B200: 148 SMs); < 255 (8-bit arrival count)
+// Exchange buffer of the persistent sweep: [2 parities][kXchgWords] 64-bit accumulator words, one per
+// 128-byte line (kXchgStride u64 apart) so the atomics of different words land on different L2 slices.
+constexpr int kXchgWords = 2 * kXchgMaxQ;
+constexpr int kXchgStride = 16;
+inline size_t xchg_bytes() { return (size_t)2 * kXchgWords * kXchgStride * sizeof(unsigned long long); }
 constexpr int kResThreads = 512;
 constexpr int kMaxBeta = 4;
 
@@ -26,6 +29,7 @@ struct SweepDesc {  // the sweep currently bound to the context (begin/gram/upda
   int n_launches = 0;
   bool have_results = false;
   bool finals_on_device = false;
+  bool rerun_done = false;  // AUTO: the split sweep already replaced an overflowed resident sweep
 };
 
 void set_error(const std::string& msg);
@@ -62,8 +66,8 @@ struct optmc_ctx {
   int* d_valid = nullptr;               // [(N+1)]
   size_t per_date_cap = 0;              // N+1 capacity of the per-date arrays
   double* d_final = nullptr;            // [4] price, stderr, sum, sumsq
-  void* xchg = nullptr;                 // LL exchange words, xchg_bytes()
-  unsigned long long epoch = 0;
+  void* xchg = nullptr;                 // exchange accumulators of the persistent sweep, xchg_bytes()
+  int* d_flags = nullptr;               // [4]: [0] = fixed-point exchange overflow
   double* eu_out = nullptr; size_t eu_out_cap = 0;  // [n_options][3]
   double* eu_par = nullptr; size_t eu_par_cap = 0;  // [n_options][4] K, T, is_put, pad
   unsigned int* eu_tickets = nullptr; size_t eu_tickets_cap = 0;

@@ -202,6 +202,53 @@ template <int DEG> OPTMC_HD void moments_accumulate(double (&acc)[Moments<DEG>::
   for (int k = 1; k <= DEG; ++k) acc[Moments<DEG>::NM + k] = fma(p[k], y, acc[Moments<DEG>::NM + k]);
 }
 
+// The same row without the count (the caller counts rows with an integer): acc[1..Q) only.
+template <int DEG> OPTMC_HD void moments_accumulate_nocount(double (&acc)[Moments<DEG>::Q], double x, double y) {
+  double p[DEG + 1];
+  p[1] = x;
+#pragma unroll
+  for (int k = 2; k <= DEG; ++k) p[k] = p[k - 1] * x;
+#pragma unroll
+  for (int k = 1; k <= DEG; ++k) acc[k] += p[k];
+#pragma unroll
+  for (int k = DEG + 1; k <= 2 * DEG; ++k) acc[k] = fma(p[DEG], p[k - DEG], acc[k]);
+  acc[Moments<DEG>::NM] += y;
+#pragma unroll
+  for (int k = 1; k <= DEG; ++k) acc[Moments<DEG>::NM + k] = fma(p[k], y, acc[Moments<DEG>::NM + k]);
+}
+
+// Power of the regressor carried by moment q: m[k] = sum x^k -> k;  gy[k] = sum x^k y -> k.
+template <int DEG> OPTMC_HD int moment_power(int q) { return q < Moments<DEG>::NM ? q : q - Moments<DEG>::NM; }
+
+// ------------------------------------------------------------------------------------------------
+// Order-independent cross-CTA summation: a double is split into two non-negative 48-bit fixed-point
+// chunks (resolution 2^-52, range |v| < 2^43) that are summed with INTEGER atomics, so the total does
+// not depend on arrival order.  Each chunk travels in the low 56 bits of a 64-bit word whose top 8
+// bits count arrivals (<= 255 contributors): sum and completion flag are one single-copy-atomic word.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFxCountShift = 56;
+constexpr unsigned long long kFxValueMask = (1ull << kFxCountShift) - 1ull;
+
+OPTMC_HD bool fx_encode(double v, unsigned long long& hi, unsigned long long& lo) {
+  const double s = v * 16.0;   // exact
+  const double h = floor(s);   // integer part in units of 2^-4
+  if (!(fabs(h) < 140737488355328.0)) {  // 2^47; also catches NaN/Inf
+    hi = 1ull << 47;
+    lo = 0ull;
+    return false;
+  }
+  const double l = (s - h) * 281474976710656.0;  // exact, in [0, 2^48)
+  hi = (unsigned long long)((long long)h + (1ll << 47));
+  lo = (unsigned long long)l;  // truncation: error < 2^-52
+  return true;
+}
+
+// sum_hi / sum_lo: the value fields after n contributors were added.
+OPTMC_HD double fx_decode(unsigned long long sum_hi, unsigned long long sum_lo, int n) {
+  const long long H = (long long)sum_hi - ((long long)n << 47);
+  return (double)H * 0.0625 + (double)sum_lo * 2.220446049250313e-16;  // 2^-4, 2^-52
+}
+
 #define OPTMC_PIVOT_RTOL 1e-14
 
 // LDL^T without pivoting; returns false (no exercise at this date) when n < p or a pivot

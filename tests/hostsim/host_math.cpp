@@ -70,4 +70,20 @@ void hs_normal2_f32(uint32_t a, uint32_t b, float* out) { Real<float>::normal2(a
 void hs_normal2_f64(uint32_t a, uint32_t b, double* out) { Real<double>::normal2(a, b, out[0], out[1]); }
 
 void hs_features(double S, double K, double tau_sqrt, double* f) { features_ref7<double>(S, K, tau_sqrt, f); }
+
+// fixed-point exchange: sum n doubles through fx_encode + 64-bit integer accumulation (arrival counts in the
+// top 8 bits, exactly as the persistent sweep does) and decode.  Returns 0 on overflow, else 1.
+int hs_fx_sum(long n, const double* v, double* out, unsigned long long* words) {
+  unsigned long long whi = 0, wlo = 0;
+  int ok = 1;
+  for (long i = 0; i < n; ++i) {
+    unsigned long long hi, lo;
+    if (!fx_encode(v[i], hi, lo)) ok = 0;
+    whi += (1ull << kFxCountShift) | hi;
+    wlo += (1ull << kFxCountShift) | lo;
+  }
+  words[0] = whi; words[1] = wlo;
+  *out = fx_decode(whi & kFxValueMask, wlo & kFxValueMask, (int)n);
+  return ok;
+}
 }

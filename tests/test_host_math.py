@@ -119,3 +119,35 @@ def test_features_ref7(hs):
     hs.hs_features.argtypes = [C.c_double] * 3 + [DP]
     hs.hs_features(130.0, 100.0, np.sqrt(0.7), _p(f))
     np.testing.assert_allclose(f, orc.features_ref7(np.array([130.0]), 100.0, 0.05, 1.0, 0.3)[0], rtol=1e-15)
+
+
+def test_fixed_point_exchange_is_exact_and_order_independent(hs):
+    """The persistent sweep sums CTA totals as two 48-bit fixed-point chunks with integer adds
+    (optmc_math.cuh: fx_encode / fx_decode): any arrival order gives the same bits, the arrival count sits
+    in the top byte, and the decoded total is within n * 2^-52 of the exact sum."""
+    hs.hs_fx_sum.argtypes = [C.c_long, DP, DP, C.POINTER(C.c_uint64)]
+    hs.hs_fx_sum.restype = C.c_int
+    rng = np.random.default_rng(3)
+    from fractions import Fraction
+
+    for n, scale in ((1, 1.0), (148, 1.0), (148, 1e6), (160, 1e9), (148, 1e-6), (37, 3.0)):
+        v = rng.standard_normal(n) * scale
+        if scale == 3.0:
+            v = np.abs(v).round()  # integers (row counts) are exact
+        out = C.c_double()
+        words = (C.c_uint64 * 2)()
+        assert hs.hs_fx_sum(n, _p(v), C.byref(out), words) == 1
+        assert words[0] >> 56 == n % 256 and words[1] >> 56 == n % 256
+        exact = sum(Fraction(float(x)) for x in v)
+        assert abs(Fraction(out.value) - exact) <= n * Fraction(1, 2**52) + abs(exact) * Fraction(1, 2**52)
+        if scale == 3.0:
+            assert out.value == float(exact)
+        perm = rng.permutation(n)
+        out2 = C.c_double()
+        words2 = (C.c_uint64 * 2)()
+        hs.hs_fx_sum(n, _p(np.ascontiguousarray(v[perm])), C.byref(out2), words2)
+        assert (words2[0], words2[1]) == (words[0], words[1]) and out2.value == out.value
+    # out of range / non-finite values are reported, never silently wrapped
+    for bad in (1e13, -1e13, np.inf, np.nan):
+        v = np.array([1.0, bad])
+        assert hs.hs_fx_sum(2, _p(v), C.byref(out), words) == 0
