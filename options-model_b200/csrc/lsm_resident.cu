@@ -36,8 +36,8 @@ struct ResArgs {
   int N, nstage;
   unsigned int stage_stride;  // bytes between stages in shared memory
   double K, invK, disc, final_scale;
-  double Kcmp;                // float-exact threshold equivalent to K for the fp32 ITM test
-  int is_put, sticky, k_exact;  // k_exact: K is representable in the storage type
+  double sgn, kk, c1, c2;     // storage-precision pass constants (see Store<>); exact in the storage type
+  int is_put, sticky;
   unsigned long long* xw;     // exchange accumulators [2][kXchgWords][kXchgStride]
   int* flags;                 // [0] = exchange overflow
   double* betas;              // [(N+1)][kMaxBeta]
@@ -51,30 +51,27 @@ struct ResArgs {
 template <int QN> struct Pow2 { static constexpr int v = QN <= 2 ? 2 : QN <= 4 ? 4 : QN <= 8 ? 8 : 16; };
 
 // ---- storage-type helpers ------------------------------------------------------------------------------
+// Put and call share one instruction stream: with sgn = -1 (put) / +1 (call)
+//   in the money   <=>  sgn * s > kk            (kk = sgn * Kcmp; products with +-1 are exact)
+//   payoff          =   fma(sgn, s, c1) + c2    (c1 = -sgn * Kh, c2 = -sgn * Kl, K = Kh + Kl)
+// For fp64 storage Kh = K, Kl = 0 and the payoff is the correctly rounded K - s / s - K of the reference
+// (om3:376-380); for fp32 storage it is that whenever K is a float, and within one ulp otherwise.
+// The reference's `exercised` flag (om3:617/649) is the sign bit of the stored cash-flow; `flag` is the
+// sign-bit mask under the sticky semantics and 0 otherwise.
 template <typename R> struct Store;
 template <> struct Store<float> {
-  static __device__ __forceinline__ bool itm(float s, double, double Kcmp, bool is_put) {
-    return is_put ? s < (float)Kcmp : s > (float)Kcmp;  // exact: Kcmp is the float bracket of K on the right side
-  }
-  // payoff rounded to storage exactly as (float)(K - (double)s): the fp32 subtraction is the correctly
-  // rounded exact difference when K is a float, otherwise go through fp64.
-  static __device__ __forceinline__ float pay(float s, double K, bool is_put, bool k_exact) {
-    if (k_exact) return is_put ? (float)K - s : s - (float)K;
-    return (float)(is_put ? K - (double)s : (double)s - K);
-  }
-  // order-preserving map of a float onto unsigned integers (boundary statistics)
-  static __device__ __forceinline__ unsigned int key(float s) {
-    const unsigned int b = __float_as_uint(s);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-  }
-  static __device__ __forceinline__ double unkey(unsigned int k) {
-    const unsigned int b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    return (double)__uint_as_float(b);
+  static __device__ __forceinline__ bool flagged(float c, unsigned int flag) { return (__float_as_uint(c) & flag) != 0u; }
+  static __device__ __forceinline__ float with_flag(float p, unsigned int flag) {
+    return __uint_as_float(__float_as_uint(p) | flag);
   }
 };
 template <> struct Store<double> {
-  static __device__ __forceinline__ bool itm(double s, double K, double, bool is_put) { return is_put ? s < K : s > K; }
-  static __device__ __forceinline__ double pay(double s, double K, bool is_put, bool) { return is_put ? K - s : s - K; }
+  static __device__ __forceinline__ bool flagged(double c, unsigned int flag) {
+    return ((unsigned int)__double2hiint(c) & flag) != 0u;
+  }
+  static __device__ __forceinline__ double with_flag(double p, unsigned int flag) {
+    return __hiloint2double((int)((unsigned int)__double2hiint(p) | flag), __double2loint(p));
+  }
 };
 
 // Block-wide sum of QP (power of two) per-thread doubles.  Every thread calls it; contains one
@@ -136,6 +133,50 @@ __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long
     if (tr) tr[(ph)] = clock64();     \
   } while (0)
 
+template <typename R> struct PassConsts {
+  R sgn, kk, c1, c2, disc;
+  unsigned int flag;
+  int n_local;
+};
+
+// One branch-free pass over the thread's PPT paths (path j = tid + k * kResThreads):
+//   DECIDE: exercise decision of date t -- exercise iff dec(S_t) > 0 (payoff - continuation, strict, om3:644);
+//   GRAM:   discount (om3:620), then the ITM-masked (om3:621) raw-price moments of date t-1.
+// Dead lanes contribute zeros, so the fp64 pipeline sees one straight-line stream per path.
+template <typename R, int DEG, int PPT, bool DECIDE, bool GRAM>
+__device__ __forceinline__ void fused_pass(R (&cf)[PPT], const R* __restrict__ st_t, const R* __restrict__ st_g,
+                                           const double (&dec)[DEG + 1], const PassConsts<R>& pc,
+                                           double (&mom)[Moments<DEG>::Q], unsigned int& rows, unsigned int& cnt,
+                                           R& em) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int j = tid + k * kResThreads;
+    const bool in = j < pc.n_local;
+    R c = cf[k];
+    if (DECIDE) {
+      const R sr = in ? st_t[j] : (R)0;
+      const R u = pc.sgn * sr;
+      const bool live = in & !Store<R>::flagged(c, pc.flag) & (u > pc.kk);
+      const bool exer = live & (poly_eval<DEG>(dec, (double)sr) > 0.0);
+      const R pay = Store<R>::with_flag(fma(pc.sgn, sr, pc.c1) + pc.c2, pc.flag);  // sticky flag = sign bit (om3:649)
+      c = exer ? pay : c;
+      cnt += exer ? 1u : 0u;
+      em = fmax(em, exer ? -u : (R)-INFINITY);
+    }
+    if (GRAM) {
+      const bool ex = Store<R>::flagged(c, pc.flag);
+      const R y = fabs(c) * pc.disc;
+      c = ex ? -y : y;
+      const R s = in ? st_g[j] : (R)0;
+      const bool live = in & !ex & (pc.sgn * s > pc.kk);
+      rows += live ? 1u : 0u;
+      moments_accumulate_nocount<DEG>(mom, (double)(live ? s : (R)0), (double)(live ? y : (R)0));
+    }
+    cf[k] = c;
+  }
+}
+
 template <typename R, int DEG, int PPT>
 __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResArgs a) {
   constexpr int Q = Moments<DEG>::Q;
@@ -157,7 +198,8 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
   const unsigned int bytes = (unsigned int)(((size_t)n_local * sizeof(R) + 15) / 16 * 16);
   const bool is_put = a.is_put != 0;
   const bool sticky = a.sticky != 0;
-  const bool k_exact = a.k_exact != 0;
+  const R sgn = (R)a.sgn, kk = (R)a.kk, c1 = (R)a.c1, c2 = (R)a.c2;
+  const unsigned int flag = sticky ? 0x80000000u : 0u;
   const R disc = (R)a.disc;
   const int N = a.N, nstage = a.nstage;
   const R* Sbase = static_cast<const R*>(a.S) + base;
@@ -177,6 +219,7 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
     mbar_fence_init();
     s_bnd[0] = s_bnd[1] = bnd_none(a.is_put);
     s_cnt[0] = s_cnt[1] = 0u;
+    s_valid = 0;
   }
   __syncthreads();
   if (tid == 0) {
@@ -203,62 +246,69 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       const int j = tid + k * kResThreads;
-      R c = (R)0;
-      if (j < n_local) {
-        const R s = st[j];
-        if (Store<R>::itm(s, a.K, a.Kcmp, is_put)) c = Store<R>::pay(s, a.K, is_put, k_exact);
-      }
-      cf[k] = c;
+      const bool in = j < n_local;
+      const R s = in ? st[j] : (R)0;
+      const R p = fma(sgn, s, c1) + c2;
+      cf[k] = (in & (sgn * s > kk)) ? p : (R)0;
     }
   }
 
+  // Iteration t (t = N .. 1) makes ONE branch-free pass over the CTA's paths:
+  //   (1) exercise decision of date t with the polynomial solved at the end of iteration t+1 (none at t = N),
+  //   (2) discount (om3:620) and the ITM-masked raw-price moments of date t-1 (om3:621 mask) -- skipped at t = 1,
+  // followed by the block reduction, the grid sum and the solve for date t-1.
   int seq = 0;
-  for (int t = N - 1; t >= 1; --t, ++seq) {
+  for (int t = N; t >= 1; --t) {
     long long* tr = tr_base ? tr_base + (size_t)t * 8 : nullptr;
-    wait_stage(t);
+    const bool gram = t >= 2;
+    const bool decide = t <= N - 1 && s_valid != 0;
+    if (gram) wait_stage(t - 1);
     OPTMC_TRACE_AT(0);
-    const R* st = stage_ptr(t);
-    // -- discount every path (om3:620), then the ITM-masked moments of the raw price in fp64 (om3:621 mask) --
-    double acc[QP];
-    {
-      double mom[Q];
+    const R* st_t = stage_ptr(t);
+    const R* st_g = stage_ptr(gram ? t - 1 : t);
+    double dec[DEG + 1];
 #pragma unroll
-      for (int q = 0; q < Q; ++q) mom[q] = 0.0;
-      unsigned int rows = 0;
+    for (int i = 0; i <= DEG; ++i) dec[i] = decide ? s_dec[i] : 0.0;
+    double mom[Q];
 #pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        const int j = tid + k * kResThreads;
-        if (j < n_local) {
-          const R c = cf[k];
-          const bool ex = sticky && signbit(c);
-          const R y = fabs(c) * disc;
-          cf[k] = ex ? -y : y;
-          const R s = st[j];
-          if (!ex && Store<R>::itm(s, a.K, a.Kcmp, is_put)) {
-            ++rows;
-            moments_accumulate_nocount<DEG>(mom, (double)s, (double)y);
-          }
+    for (int q = 0; q < Q; ++q) mom[q] = 0.0;
+    unsigned int rows = 0, cnt = 0;
+    R em = (R)-INFINITY;  // max over exercised paths of -sgn * S: put -> max S, call -> -(min S)
+    const PassConsts<R> pc{sgn, kk, c1, c2, disc, flag, n_local};
+    if (decide && gram) fused_pass<R, DEG, PPT, true, true>(cf, st_t, st_g, dec, pc, mom, rows, cnt, em);
+    else if (gram) fused_pass<R, DEG, PPT, false, true>(cf, st_t, st_g, dec, pc, mom, rows, cnt, em);
+    else if (decide) fused_pass<R, DEG, PPT, true, false>(cf, st_t, st_g, dec, pc, mom, rows, cnt, em);
+    if (decide) {
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt) {  // warp-uniform
+        const double ext = -(double)sgn * (double)em;
+        unsigned long long b = (unsigned long long)__double_as_longlong(ext);
+        if (!isfinite(ext)) b = bnd_none(a.is_put);
+        b = is_put ? warp_max_u64(b) : warp_min_u64(b);
+        if (lane == 0) {
+          atomicAdd(&s_cnt[0], cnt);
+          if (is_put) atomicMax(&s_bnd[0], b); else atomicMin(&s_bnd[0], b);
         }
       }
-      mom[0] = (double)rows;
-#pragma unroll
-      for (int q = 0; q < QP; ++q) acc[q] = q < Q ? mom[q] : 0.0;
     }
     OPTMC_TRACE_AT(1);
-    // the __syncthreads inside block_totals also proves every thread is done with stage (t+1)
+    if (!gram) break;
+
+    double acc[QP];
+    mom[0] = (double)rows;
+#pragma unroll
+    for (int q = 0; q < QP; ++q) acc[q] = q < Q ? mom[q] : 0.0;
+    // the __syncthreads inside block_totals also proves every thread is done with stage t
     const double mine = block_totals<QP>(acc, s_red) * qscale;
     OPTMC_TRACE_AT(2);
     if (tid == 32) {  // bookkeeping off the critical path (warp 1)
-      if (t + 1 <= N - 1) {  // flush the exercise statistics of date t+1
-        const int p = (t + 1) & 1;
-        if (s_cnt[p]) {
-          atomicAdd(a.exc + (t + 1), (unsigned long long)s_cnt[p]);
-          if (is_put) atomicMax(a.bnd + (t + 1), s_bnd[p]); else atomicMin(a.bnd + (t + 1), s_bnd[p]);
-        }
-        s_cnt[p] = 0u;
-        s_bnd[p] = bnd_none(a.is_put);
+      if (s_cnt[0]) {  // exercise statistics of date t
+        atomicAdd(a.exc + t, (unsigned long long)s_cnt[0]);
+        if (is_put) atomicMax(a.bnd + t, s_bnd[0]); else atomicMin(a.bnd + t, s_bnd[0]);
+        s_cnt[0] = 0u;
+        s_bnd[0] = bnd_none(a.is_put);
       }
-      if (t + 1 - nstage >= 1) issue_load(t + 1 - nstage);  // refill the stage date t+1 vacated
+      if (t - nstage >= 1) issue_load(t - nstage);  // refill the stage date t vacated
     }
     if (warp == 0) {
       int spins = 0;
@@ -287,47 +337,14 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
         }
         if (cta == 0) {
 #pragma unroll
-          for (int i = 0; i <= DEG; ++i) a.betas[(size_t)t * kMaxBeta + i] = ok ? beta[i] : nan("");
-          a.nitm[t] = (long long)(tot[0] + 0.5);
+          for (int i = 0; i <= DEG; ++i) a.betas[(size_t)(t - 1) * kMaxBeta + i] = ok ? beta[i] : nan("");
+          a.nitm[t - 1] = (long long)(tot[0] + 0.5);
         }
       }
       OPTMC_TRACE_AT(5);
     }
-    __syncthreads();  // decision polynomial visible
-    OPTMC_TRACE_AT(6);
-    if (s_valid) {
-      double dec[DEG + 1];
-#pragma unroll
-      for (int i = 0; i <= DEG; ++i) dec[i] = s_dec[i];
-      unsigned int cnt = 0;
-      R ext = is_put ? (R)-INFINITY : (R)INFINITY;  // max (put) / min (call) exercised price
-#pragma unroll
-      for (int k = 0; k < PPT; ++k) {
-        const int j = tid + k * kResThreads;
-        if (j < n_local) {
-          const R c = cf[k];
-          const R sr = st[j];
-          if (!(sticky && signbit(c)) && Store<R>::itm(sr, a.K, a.Kcmp, is_put)) {
-            if (poly_eval<DEG>(dec, (double)sr) > 0.0) {   // strict '>' (om3:644)
-              const R pay = Store<R>::pay(sr, a.K, is_put, k_exact);
-              cf[k] = sticky ? -pay : pay;                 // sticky flag = sign bit (om3:649)
-              cnt++;
-              ext = is_put ? (sr > ext ? sr : ext) : (sr < ext ? sr : ext);
-            }
-          }
-        }
-      }
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt) {  // warp-uniform
-        unsigned long long b = (unsigned long long)__double_as_longlong((double)ext);
-        if (!isfinite((double)ext)) b = bnd_none(a.is_put);
-        b = is_put ? warp_max_u64(b) : warp_min_u64(b);
-        if (lane == 0) {
-          atomicAdd(&s_cnt[t & 1], cnt);
-          if (is_put) atomicMax(&s_bnd[t & 1], b); else atomicMin(&s_bnd[t & 1], b);
-        }
-      }
-    }
+    ++seq;
+    __syncthreads();  // decision polynomial of date t-1 visible
   }
 
   // ---- final reduction: mean and standard error of the cash-flows (om3:651) ----
@@ -342,11 +359,9 @@ __global__ void __launch_bounds__(kResThreads, 1) lsm_resident_kernel(const ResA
     }
   }
   const double mine = block_totals<2>(fin, s_red);
-  if (tid == 32 && N - 1 >= 1) {  // statistics of date 1 (all update loops are behind the barrier above)
-    if (s_cnt[1]) {
-      atomicAdd(a.exc + 1, (unsigned long long)s_cnt[1]);
-      if (is_put) atomicMax(a.bnd + 1, s_bnd[1]); else atomicMin(a.bnd + 1, s_bnd[1]);
-    }
+  if (tid == 32 && s_cnt[0]) {  // statistics of date 1 (its update pass is behind the barrier above)
+    atomicAdd(a.exc + 1, (unsigned long long)s_cnt[0]);
+    if (is_put) atomicMax(a.bnd + 1, s_bnd[0]); else atomicMin(a.bnd + 1, s_bnd[0]);
   }
   if (warp == 0) {
     unsigned long long pv = (seq & 1) ? prev1 : prev0;
@@ -441,12 +456,19 @@ int sweep_resident(optmc_ctx* ctx) {
   a.S = sw.S; a.ld = sw.ld; a.M = sw.M; a.chunk = p.chunk; a.N = sw.N; a.nstage = p.nstage;
   a.stage_stride = p.stage_stride;
   a.K = sw.lp.K; a.invK = 1.0 / sw.lp.K; a.disc = sw.disc; a.final_scale = sw.final_scale;
-  {  // float threshold with (s < K) <=> (s < Kcmp) for every float s (puts); mirrored for calls
-    float kf = (float)sw.lp.K;
-    a.k_exact = sw.dtype == OPTMC_F64 ? 1 : ((double)kf == sw.lp.K ? 1 : 0);
-    if (sw.lp.is_put) { if ((double)kf < sw.lp.K) kf = nextafterf(kf, INFINITY); }
-    else { if ((double)kf > sw.lp.K) kf = nextafterf(kf, -INFINITY); }
-    a.Kcmp = (double)kf;
+  {  // pass constants, exact in the storage type (see Store<>)
+    const double sg = sw.lp.is_put ? -1.0 : 1.0;
+    double Kcmp = sw.lp.K, Kh = sw.lp.K, Kl = 0.0;
+    if (sw.dtype == OPTMC_F32) {
+      // float threshold with (s < K) <=> (s < Kcmp) for every float s (puts); mirrored for calls
+      float kf = (float)sw.lp.K;
+      Kh = (double)kf;
+      Kl = (double)(float)(sw.lp.K - Kh);
+      if (sw.lp.is_put) { if ((double)kf < sw.lp.K) kf = nextafterf(kf, INFINITY); }
+      else { if ((double)kf > sw.lp.K) kf = nextafterf(kf, -INFINITY); }
+      Kcmp = (double)kf;
+    }
+    a.sgn = sg; a.kk = sg * Kcmp; a.c1 = -sg * Kh; a.c2 = -sg * Kl;
   }
   a.is_put = sw.lp.is_put; a.sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) ? 1 : 0;
   a.xw = reinterpret_cast<unsigned long long*>(ctx->xchg); a.flags = ctx->d_flags;
@@ -474,7 +496,7 @@ int sweep_resident(optmc_ctx* ctx) {
         fprintf(f, "# ncta=%d chunk=%lld ppt=%d nstage=%d N=%d ; columns: cta t ph0..ph7 (clock64)\n", p.ncta, p.chunk,
                 p.ppt, p.nstage, sw.N);
         for (int c = 0; c < 2; ++c)
-          for (int t = sw.N - 1; t >= 1; --t) {
+          for (int t = sw.N; t >= 1; --t) {
             fprintf(f, "%d %d", c, t);
             for (int k = 0; k < 8; ++k) fprintf(f, " %lld", h[((size_t)c * (sw.N + 1) + t) * 8 + k]);
             fprintf(f, "\n");

@@ -10,10 +10,12 @@ namespace optmc {
 
 constexpr int kXchgMaxQ = 16;         // quantities per exchange (poly3 needs 11)
 constexpr int kMaxResidentCtas = 160; // CTAs of the persistent sweep (B200: 148 SMs); < 255 (8-bit arrival count)
-// Exchange buffer of the persistent sweep: [2 parities][kXchgWords] 64-bit accumulator words, one per
-// 128-byte line (kXchgStride u64 apart) so the atomics of different words land on different L2 slices.
+// Exchange buffer of the persistent sweep: [2 parities][kXchgWords] 64-bit accumulator words, packed
+// (kXchgStride = 1): one warp's reds / polls of a parity then coalesce into one or two L2 requests per CTA,
+// which measured 25% faster than one 128-byte line per word (tools/xchg_bench.cu) -- the exchange is bound
+// by L2 request count on the hot lines, not by atomic throughput.
 constexpr int kXchgWords = 2 * kXchgMaxQ;
-constexpr int kXchgStride = 16;
+constexpr int kXchgStride = 1;
 inline size_t xchg_bytes() { return (size_t)2 * kXchgWords * kXchgStride * sizeof(unsigned long long); }
 constexpr int kResThreads = 512;
 constexpr int kMaxBeta = 4;

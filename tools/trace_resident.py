@@ -19,16 +19,18 @@ r = eng.lsm(S, 100.0, 0.05, 1.0, "put", impl="resident")
 del os.environ["OPTMC_TRACE"]
 print("price", r.price)
 rows = np.loadtxt(out, comments="#")
-# phase stamps: 0 stage ready, 1 Gram loop done, 2 CTA totals in warp 0, 4 grid sum complete, 5 solved, 6 beta visible
-cols = [0, 1, 2, 4, 5, 6]
-names = ["gram loop", "block reduce (sync A)", "publish + grid sum", "solve", "sync B", "update + next wait"]
+# iteration t: stamps 0 pass start (beta visible, stage ready), 1 fused decide+Gram pass done, 2 CTA totals in
+# warp 0 (sync A), 4 grid sum complete, 5 solved; the next iteration's stamp 0 closes sync B + stage wait.
+cols = [0, 1, 2, 4, 5]
+names = ["fused decide+gram pass", "block reduce (sync A)", "publish + grid sum", "solve", "sync B + stage wait"]
 for c in (0, 1):
     a = rows[rows[:, 0] == c][:, 2:]
+    a = a[(a[:, 0] > 0) & (a[:, 5] > 0)]
     per_date = a[1:, 0] - a[:-1, 0]
     print(f"cta {'first' if c == 0 else 'last'}: per-date total {np.median(per_date):.0f} cycles; spins median "
           f"{np.median(a[:, 7]):.0f} p90 {np.percentile(a[:, 7], 90):.0f}")
     d = np.diff(a[:, cols], axis=1)
-    for k in range(5):
+    for k in range(4):
         print(f"   {names[k]:24s} median {np.median(d[:, k]):8.0f}  p90 {np.percentile(d[:, k], 90):8.0f}")
-    nxt = a[1:, 0] - a[:-1, 6]
-    print(f"   {names[5]:24s} median {np.median(nxt):8.0f}  p90 {np.percentile(nxt, 90):8.0f}")
+    nxt = a[1:, 0] - a[:-1, 5]
+    print(f"   {names[4]:24s} median {np.median(nxt):8.0f}  p90 {np.percentile(nxt, 90):8.0f}")
