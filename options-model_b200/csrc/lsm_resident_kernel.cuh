@@ -1,0 +1,478 @@
+// lsm_resident_kernel.cuh -- device code of the persistent LSM sweep (see lsm_resident.cu for the design).
+// Included by the per-precision translation units lsm_resident_f32.cu / lsm_resident_f64.cu.
+#pragma once
+#include <math.h>
+
+#include "optmc_device.cuh"
+#include "optmc_internal.h"
+#include "optmc_math.cuh"
+
+namespace optmc {
+
+struct ResArgs {
+  const void* S;
+  long long ld, M, chunk;
+  int N, nstage;
+  unsigned int stage_stride;  // bytes between stages in shared memory
+  double K, invK, disc, inv_disc, final_scale;
+  double sgn, kk, c1, c2;     // storage-precision pass constants (see Store<>); exact in the storage type
+  int is_put, sticky;
+  unsigned long long* xw;     // exchange accumulators [2][kXchgWords][kXchgStride]
+  int* flags;                 // [0] = exchange overflow
+  double* betas;              // [(N+1)][kMaxBeta]
+  unsigned long long* bnd;    // [(N+1)]
+  unsigned long long* exc;    // [(N+1)]
+  long long* nitm;            // [(N+1)]
+  double* final_out;          // [4]
+  long long* trace;           // optional [2][(N+1)][8] phase clocks of the first and last CTA (OPTMC_TRACE)
+};
+
+template <int QN> struct Pow2 { static constexpr int v = QN <= 2 ? 2 : QN <= 4 ? 4 : QN <= 8 ? 8 : 16; };
+
+// ---- storage-type helpers ------------------------------------------------------------------------------
+// Put and call share one instruction stream: with sgn = -1 (put) / +1 (call)
+//   in the money   <=>  sgn * s > kk            (kk = sgn * Kcmp; products with +-1 are exact)
+//   payoff          =   fma(sgn, s, c1) + c2    (c1 = -sgn * Kh, c2 = -sgn * Kl, K = Kh + Kl)
+// For fp64 storage Kh = K, Kl = 0 and the payoff is the correctly rounded K - s / s - K of the reference
+// (om3:376-380); for fp32 storage it is that whenever K is a float, and within one ulp otherwise.
+// The reference's `exercised` flag (om3:617/649) is the sign bit of the stored cash-flow; `flag` is the
+// sign-bit mask under the sticky semantics and 0 otherwise.
+template <typename R> struct Store;
+template <> struct Store<float> {
+  static __device__ __forceinline__ bool flagged(float c, unsigned int flag) { return (__float_as_uint(c) & flag) != 0u; }
+  static __device__ __forceinline__ float with_flag(float p, unsigned int flag) {
+    return __uint_as_float(__float_as_uint(p) | flag);
+  }
+};
+template <> struct Store<double> {
+  static __device__ __forceinline__ bool flagged(double c, unsigned int flag) {
+    return ((unsigned int)__double2hiint(c) & flag) != 0u;
+  }
+  static __device__ __forceinline__ double with_flag(double p, unsigned int flag) {
+    return __hiloint2double((int)((unsigned int)__double2hiint(p) | flag), __double2loint(p));
+  }
+};
+
+// Block-wide sum of QP (power of two) per-thread doubles.  Every thread calls it; contains one
+// __syncthreads.  On return, in warp 0, lane l < 2*QP holds the CTA total of quantity l >> 1.
+template <int QP, int NW>
+__device__ __forceinline__ double block_totals(double (&acc)[QP], double* s_red) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  warp_reduce_scatter<QP>(acc, lane);
+  if (reduce_scatter_owner<QP>(lane)) s_red[warp * QP + reduce_scatter_index<QP>(lane)] = acc[0];
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {  // lane -> quantity lane % QP; group lane / QP sums warps g, g+G, ...
+    constexpr int G = 32 / QP;
+    const int q = lane % QP, g = lane / QP;
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; w += G)
+      if (w + g < NW) v += s_red[(w + g) * QP + q];
+#pragma unroll
+    for (int m = QP; m <= 16; m <<= 1) v += shfl_xor_f64(v, m);
+    t = __shfl_sync(0xffffffffu, v, (lane >> 1) % QP);
+  }
+  return t;
+}
+
+// Warp 0 only.  `mine`: this CTA's total of quantity lane >> 1 (lanes < 2*QN), already in its final
+// units.  Adds it into the parity's accumulators, waits until all `ncta` CTAs have arrived and returns
+// the grid total of quantity `lane` in lanes < QN.  prev = this lane's accumulator value after the last
+// completed exchange of the same parity (0 at launch).
+template <int QN>
+__device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long* xw, int par, int ncta,
+                                                 unsigned long long& prev, int* flags, int* spins_out) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long sum = 0ull;
+  int spins = 0;
+  if (lane < 2 * QN) {
+    unsigned long long hi, lo;
+    if (!fx_encode(mine, hi, lo)) atomicExch(flags, 1);
+    unsigned long long* w = xw + ((size_t)par * kXchgWords + lane) * kXchgStride;
+    red_relaxed_add_u64(w, (1ull << kFxCountShift) | ((lane & 1) ? lo : hi));
+    unsigned long long d;
+    do {
+      d = ld_relaxed_u64(w) - prev;
+      ++spins;
+    } while ((d >> kFxCountShift) != (unsigned long long)ncta);
+    prev += d;
+    sum = d & kFxValueMask;
+  }
+  __syncwarp();
+  const unsigned long long other = __shfl_down_sync(0xffffffffu, sum, 1);
+  double tot = fx_decode(sum, other, ncta);                 // meaningful on even lanes < 2*QN
+  tot = __shfl_sync(0xffffffffu, tot, (2 * lane) & 31);     // quantity q: lane 2q -> lane q
+  if (spins_out) *spins_out = spins;
+  return tot;
+}
+
+#define OPTMC_TRACE_AT(ph)            \
+  do {                                \
+    if (tr) tr[(ph)] = clock64();     \
+  } while (0)
+
+// Cash-flows are kept in "date-N money": the stored value is c~ = c_t / D_t with D_t = disc^(N - t), so
+// the reference's per-date `cashflows *= discount` (om3:620) costs nothing for paths that are not in the
+// regression: the value at date t is c~ * D_t (dg below), an exercise at date t stores payoff / D_t
+// (payoff * dinv), and the price is mean(c~) * D_1.
+template <typename R> struct PassConsts {
+  R sgn, kk, c1, c2;
+  R dinv;  // 1 / D_t of the decision date
+  R dg;    // D_(t-1) of the Gram date
+  unsigned int flag;
+  int n_local;
+};
+
+// Exercise test  dec(S) > 0  (payoff - continuation as a polynomial in the raw price; strict, om3:644).
+// fp64 storage evaluates it in fp64.  fp32 storage first evaluates it in fp32 together with a rigorous
+// bound on the fp32 evaluation error (coefficient rounding + Horner: <= 4 u * sum |d_i| S^i, u = 2^-24;
+// the filter uses 8 u); only paths whose fp32 value is inside the bound are re-decided in fp64, so the
+// decisions are identical to the fp64 evaluation while the fp64 pipe sees a handful of paths per date.
+template <typename R, int DEG> struct Decider;
+template <int DEG> struct Decider<double, DEG> {
+  double d[DEG + 1];
+  __device__ __forceinline__ void load(const double* src, bool on) {
+#pragma unroll
+    for (int i = 0; i <= DEG; ++i) d[i] = on ? src[i] : 0.0;
+  }
+  __device__ __forceinline__ bool exact(double s) const { return poly_eval<DEG>(d, s) > 0.0; }
+  __device__ __forceinline__ bool fast(double s, bool& sure) const { sure = true; return exact(s); }
+};
+template <int DEG> struct Decider<float, DEG> {
+  double d[DEG + 1];
+  float f[DEG + 1], b[DEG + 1];
+  __device__ __forceinline__ void load(const double* src, bool on) {
+#pragma unroll
+    for (int i = 0; i <= DEG; ++i) {
+      d[i] = on ? src[i] : 0.0;
+      f[i] = (float)d[i];
+      b[i] = fabsf(f[i]) * 4.76837158203125e-7f;  // 8 * 2^-24
+    }
+  }
+  __device__ __forceinline__ bool exact(float s) const { return poly_eval<DEG>(d, (double)s) > 0.0; }
+  __device__ __forceinline__ bool fast(float s, bool& sure) const {
+    float p = f[DEG], e = b[DEG];
+    const float as = fabsf(s);
+#pragma unroll
+    for (int i = DEG - 1; i >= 0; --i) { p = fmaf(p, s, f[i]); e = fmaf(e, as, b[i]); }
+    sure = fabsf(p) > e;
+    return p > 0.0f;
+  }
+};
+
+// Passes over the thread's PPT paths (path j = tid + k * NT); dead lanes contribute zeros.
+//   decide_pass: exercise decision of date t (sticky flag = sign bit of the stored cash-flow, om3:649);
+//   gram_pass:   the ITM-masked (om3:621) raw-price moments of date t-1.
+// SPARSE = true skips a warp's step when none of its 32 paths is in the regression -- under the reference's
+// sticky mask most in-the-money paths are already flagged, so only ~0.5% of the paths are live per date.
+// SPARSE = false is fully branch-free (textbook semantics: ~40% of the paths are live at every date).
+template <typename R, int DEG, int PPT, int NT, bool SPARSE>
+__device__ __forceinline__ void decide_pass(R (&cf)[PPT], const R* __restrict__ st_t, const Decider<R, DEG>& dec,
+                                            const PassConsts<R>& pc, unsigned int& cnt, R& em) {
+  const int tid = threadIdx.x;
+  unsigned long long amb = 0ull;  // paths the fp32 filter could not decide
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int j = tid + k * NT;
+    const bool in = j < pc.n_local;
+    const R c = cf[k];
+    const R sr = in ? st_t[j] : (R)0;
+    const R u = pc.sgn * sr;
+    const bool live = in & !Store<R>::flagged(c, pc.flag) & (u > pc.kk);
+    if (!SPARSE || __any_sync(0xffffffffu, live)) {
+      bool sure;
+      const bool pos = dec.fast(sr, sure);
+      const bool exer = live & sure & pos;
+      amb |= (live & !sure) ? (1ull << k) : 0ull;
+      const R pay = Store<R>::with_flag((fma(pc.sgn, sr, pc.c1) + pc.c2) * pc.dinv, pc.flag);
+      cf[k] = exer ? pay : c;
+      cnt += exer ? 1u : 0u;
+      em = fmax(em, exer ? -u : (R)-INFINITY);
+    }
+  }
+  if (amb) {  // rare: a handful of paths per date sit within fp32 rounding of the exercise boundary
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      if (amb & (1ull << k)) {
+        const R sr = st_t[tid + k * NT];
+        if (dec.exact(sr)) {
+          cf[k] = Store<R>::with_flag((fma(pc.sgn, sr, pc.c1) + pc.c2) * pc.dinv, pc.flag);
+          cnt += 1u;
+          em = fmax(em, -(pc.sgn * sr));
+        }
+      }
+    }
+  }
+}
+
+template <typename R, int DEG, int PPT, int NT, bool SPARSE>
+__device__ __forceinline__ void gram_pass(const R (&cf)[PPT], const R* __restrict__ st_g, const PassConsts<R>& pc,
+                                          double (&mom)[Moments<DEG>::Q], unsigned int& rows) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int j = tid + k * NT;
+    const bool in = j < pc.n_local;
+    const R c = cf[k];
+    const R s = in ? st_g[j] : (R)0;
+    const bool live = in & !Store<R>::flagged(c, pc.flag) & (pc.sgn * s > pc.kk);
+    if (!SPARSE || __any_sync(0xffffffffu, live)) {
+      const R y = c * pc.dg;  // live lanes are unflagged: c >= 0
+      rows += live ? 1u : 0u;
+      moments_accumulate_nocount<DEG>(mom, (double)(live ? s : (R)0), (double)(live ? y : (R)0));
+    }
+  }
+}
+
+template <typename R, int DEG, int PPT, int NT, bool SPARSE>
+__global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
+  constexpr int Q = Moments<DEG>::Q;
+  constexpr int QP = Pow2<Q>::v;
+  constexpr int NW = NT / 32;
+  static_assert(Q <= kXchgMaxQ, "Gram vector must fit the exchange buffer");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t mbar[3];
+  __shared__ double s_red[NW * 16];
+  __shared__ double s_dec[DEG + 1];   // exercise iff s_dec(s) > 0  (payoff - continuation as a polynomial in S)
+  __shared__ int s_valid;
+  __shared__ unsigned long long s_bnd[2];
+  __shared__ unsigned int s_cnt[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const long long base = (long long)cta * a.chunk;
+  const long long rem = a.M - base;
+  const int n_local = (int)(rem < a.chunk ? rem : a.chunk);
+  const unsigned int bytes = (unsigned int)(((size_t)n_local * sizeof(R) + 15) / 16 * 16);
+  const bool is_put = a.is_put != 0;
+  const bool sticky = a.sticky != 0;
+  const R sgn = (R)a.sgn, kk = (R)a.kk, c1 = (R)a.c1, c2 = (R)a.c2;
+  const unsigned int flag = sticky ? 0x80000000u : 0u;
+  const int N = a.N, nstage = a.nstage;
+  const R* Sbase = static_cast<const R*>(a.S) + base;
+
+  auto stage_ptr = [&](int t) -> const R* {
+    return reinterpret_cast<const R*>(smem_raw + (size_t)(t % nstage) * a.stage_stride);
+  };
+  auto issue_load = [&](int t) {  // one thread
+    uint64_t* bar = &mbar[t % nstage];
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_load_1d(smem_raw + (size_t)(t % nstage) * a.stage_stride, Sbase + (size_t)t * a.ld, bytes, bar);
+  };
+  auto wait_stage = [&](int t) { mbar_wait(&mbar[t % nstage], (unsigned)(((N - t) / nstage) & 1)); };
+
+  if (tid == 0) {
+    for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
+    mbar_fence_init();
+    s_bnd[0] = s_bnd[1] = bnd_none(a.is_put);
+    s_cnt[0] = s_cnt[1] = 0u;
+    s_valid = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < nstage; ++i)
+      if (N - i >= 1) issue_load(N - i);
+  }
+
+  // warp-0 lane constants: lane l serves quantity l >> 1; raw-price moments are rescaled to x = S/K
+  // (the regressor of SURVEY.md 8(c)) by invK^power before they enter the exchange.
+  double qscale = 1.0;
+  {
+    const int pw = moment_power<DEG>(lane >> 1);
+    for (int i = 0; i < pw; ++i) qscale *= a.invK;
+  }
+  unsigned long long prev0 = 0ull, prev1 = 0ull;  // warp 0: accumulator baselines of the two parities
+  long long* const tr_base = (a.trace && tid == 0 && (cta == 0 || cta == ncta - 1))
+                                 ? a.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * 8 : nullptr;
+
+  // ---- date N: cash-flows = payoff(S[N]) (om3:616) ----
+  R cf[PPT];
+  wait_stage(N);
+  {
+    const R* st = stage_ptr(N);
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const int j = tid + k * NT;
+      const bool in = j < n_local;
+      const R s = in ? st[j] : (R)0;
+      const R p = fma(sgn, s, c1) + c2;
+      cf[k] = (in & (sgn * s > kk)) ? p : (R)0;
+    }
+  }
+
+  // Iteration t (t = N .. 1) makes ONE branch-free pass over the CTA's paths:
+  //   (1) exercise decision of date t with the polynomial solved at the end of iteration t+1 (none at t = N),
+  //   (2) discount (om3:620) and the ITM-masked raw-price moments of date t-1 (om3:621 mask) -- skipped at t = 1,
+  // followed by the block reduction, the grid sum and the solve for date t-1.
+  int seq = 0;
+  double d_t = 1.0, dinv_t = 1.0;  // D_t and 1 / D_t of the iteration's decision date
+  for (int t = N; t >= 1; --t) {
+    long long* tr = tr_base ? tr_base + (size_t)t * 8 : nullptr;
+    const bool gram = t >= 2;
+    const bool decide = t <= N - 1 && s_valid != 0;
+    if (gram) wait_stage(t - 1);
+    OPTMC_TRACE_AT(0);
+    const R* st_t = stage_ptr(t);
+    const R* st_g = stage_ptr(gram ? t - 1 : t);
+    double mom[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) mom[q] = 0.0;
+    unsigned int rows = 0, cnt = 0;
+    R em = (R)-INFINITY;  // max over exercised paths of -sgn * S: put -> max S, call -> -(min S)
+    // D_t = disc^(N - t): every thread advances the same fp64 products, so they agree bit for bit
+    const PassConsts<R> pc{sgn, kk, c1, c2, (R)dinv_t, (R)(d_t * a.disc), flag, n_local};
+    if (decide) {
+      Decider<R, DEG> dec;
+      dec.load(s_dec, true);
+      decide_pass<R, DEG, PPT, NT, SPARSE>(cf, st_t, dec, pc, cnt, em);
+    }
+    if (gram) gram_pass<R, DEG, PPT, NT, SPARSE>(cf, st_g, pc, mom, rows);
+    d_t *= a.disc;
+    dinv_t *= a.inv_disc;
+    if (decide) {
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt) {  // warp-uniform
+        const double ext = -(double)sgn * (double)em;
+        unsigned long long b = (unsigned long long)__double_as_longlong(ext);
+        if (!isfinite(ext)) b = bnd_none(a.is_put);
+        b = is_put ? warp_max_u64(b) : warp_min_u64(b);
+        if (lane == 0) {
+          atomicAdd(&s_cnt[0], cnt);
+          if (is_put) atomicMax(&s_bnd[0], b); else atomicMin(&s_bnd[0], b);
+        }
+      }
+    }
+    OPTMC_TRACE_AT(1);
+    if (!gram) break;
+
+    double acc[QP];
+    mom[0] = (double)rows;
+#pragma unroll
+    for (int q = 0; q < QP; ++q) acc[q] = q < Q ? mom[q] : 0.0;
+    // the __syncthreads inside block_totals also proves every thread is done with stage t
+    const double mine = block_totals<QP, NW>(acc, s_red) * qscale;
+    OPTMC_TRACE_AT(2);
+    if (tid == 32) {  // bookkeeping off the critical path (warp 1)
+      if (s_cnt[0]) {  // exercise statistics of date t
+        atomicAdd(a.exc + t, (unsigned long long)s_cnt[0]);
+        if (is_put) atomicMax(a.bnd + t, s_bnd[0]); else atomicMin(a.bnd + t, s_bnd[0]);
+        s_cnt[0] = 0u;
+        s_bnd[0] = bnd_none(a.is_put);
+      }
+      if (t - nstage >= 1) issue_load(t - nstage);  // refill the stage date t vacated
+    }
+    if (warp == 0) {
+      int spins = 0;
+      unsigned long long pv = (seq & 1) ? prev1 : prev0;
+      const double tot_l = warp0_grid_sum<Q>(mine, a.xw, seq & 1, ncta, pv, a.flags, &spins);
+      if (seq & 1) prev1 = pv; else prev0 = pv;
+      OPTMC_TRACE_AT(4);
+      if (tr) tr[7] = spins;
+      double tot[Q], beta[DEG + 1];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) tot[q] = __shfl_sync(0xffffffffu, tot_l, q);
+      const bool ok = solve_poly<DEG>(tot, beta);  // every lane, identical inputs: no divergence
+      if (lane == 0) {
+        s_valid = ok ? 1 : 0;
+        if (ok) {
+          // payoff - continuation = (+-K - b0) + (-+1 - b1/K) S - (b2/K^2) S^2 ...  (x = S/K)
+          double sc = 1.0;
+#pragma unroll
+          for (int i = 0; i <= DEG; ++i) {
+            double d = -beta[i] * sc;
+            if (i == 0) d += is_put ? a.K : -a.K;
+            if (i == 1) d += is_put ? -1.0 : 1.0;
+            s_dec[i] = d;
+            sc *= a.invK;
+          }
+        }
+        if (cta == 0) {
+#pragma unroll
+          for (int i = 0; i <= DEG; ++i) a.betas[(size_t)(t - 1) * kMaxBeta + i] = ok ? beta[i] : nan("");
+          a.nitm[t - 1] = (long long)(tot[0] + 0.5);
+        }
+      }
+      OPTMC_TRACE_AT(5);
+    }
+    ++seq;
+    __syncthreads();  // decision polynomial of date t-1 visible
+  }
+
+  // ---- final reduction: mean and standard error of the cash-flows (om3:651) ----
+  double fin[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int j = tid + k * NT;
+    if (j < n_local) {
+      const double c = fabs((double)cf[k]);
+      fin[0] += c;
+      fin[1] += c * c;
+    }
+  }
+  const double mine = block_totals<2, NW>(fin, s_red);
+  if (tid == 32 && s_cnt[0]) {  // statistics of date 1 (its update pass is behind the barrier above)
+    atomicAdd(a.exc + 1, (unsigned long long)s_cnt[0]);
+    if (is_put) atomicMax(a.bnd + 1, s_bnd[0]); else atomicMin(a.bnd + 1, s_bnd[0]);
+  }
+  if (warp == 0) {
+    unsigned long long pv = (seq & 1) ? prev1 : prev0;
+    const double tot_l = warp0_grid_sum<2>(mine, a.xw, seq & 1, ncta, pv, a.flags, nullptr);
+    const double s1 = __shfl_sync(0xffffffffu, tot_l, 0), s2 = __shfl_sync(0xffffffffu, tot_l, 1);
+    if (cta == 0 && lane == 0) {
+      const double n = (double)a.M;
+      const double mean = s1 / n;
+      double var = n > 1.0 ? (s2 - n * mean * mean) / (n - 1.0) : 0.0;
+      if (var < 0.0) var = 0.0;
+      const double scale = d_t * a.inv_disc * a.final_scale;  // D_1 (N - 1 discounts, om3:651), one more under TEXTBOOK
+      a.final_out[0] = mean * scale;
+      a.final_out[1] = sqrt(var / n) * scale;
+      a.final_out[2] = s1;
+      a.final_out[3] = s2;
+    }
+  }
+}
+
+
+// ---- launch table (one translation unit per storage precision) -------------------------------------------
+struct ResPlan {
+  int ncta = 0, ppt = 0, nstage = 0, nt = 0;
+  bool sparse = false;  // vote-skip passes (sticky semantics: few live paths per date)
+  long long chunk = 0;
+  unsigned int stage_stride = 0;
+  size_t smem = 0;
+};
+
+template <typename R, int DEG, int PPT, int NT, bool SPARSE>
+int launch_resident_t(optmc_ctx* ctx, const ResPlan& p, ResArgs& a) {
+  auto kern = lsm_resident_kernel<R, DEG, PPT, NT, SPARSE>;
+  OPTMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  void* args[] = {(void*)&a};
+  OPTMC_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(p.ncta), dim3(NT), args, p.smem, ctx->stream));
+  ctx->launches++; ctx->sw.n_launches++;
+  return OPTMC_OK;
+}
+
+// (threads, paths-per-thread) shapes compiled for every precision / degree / sparsity.  512-thread CTAs
+// (<= 128 registers per thread); 1024-thread CTAs measured slower (barrier cost) and are not built.
+#define OPTMC_RES_SHAPES(X) \
+  X(512, 1) X(512, 2) X(512, 4) X(512, 8) X(512, 12) X(512, 14) X(512, 16) X(512, 20) X(512, 24) X(512, 28) \
+  X(512, 32) X(512, 40) X(512, 48) X(512, 56)
+
+template <typename R, int DEG> int launch_resident_shape(optmc_ctx* ctx, const ResPlan& p, ResArgs& a) {
+#define X(NT_, PPT_)                                                                       \
+  if (p.nt == NT_ && p.ppt == PPT_)                                                        \
+    return p.sparse ? launch_resident_t<R, DEG, PPT_, NT_, true>(ctx, p, a)                \
+                    : launch_resident_t<R, DEG, PPT_, NT_, false>(ctx, p, a);
+  OPTMC_RES_SHAPES(X)
+#undef X
+  set_error("no resident instantiation for this slice size");
+  return OPTMC_EUNSUPPORTED;
+}
+
+int launch_resident_f32_deg2(optmc_ctx* ctx, const ResPlan& p, ResArgs& a);
+int launch_resident_f32_deg3(optmc_ctx* ctx, const ResPlan& p, ResArgs& a);
+int launch_resident_f64_deg2(optmc_ctx* ctx, const ResPlan& p, ResArgs& a);
+int launch_resident_f64_deg3(optmc_ctx* ctx, const ResPlan& p, ResArgs& a);
+
+}  // namespace optmc

@@ -17,7 +17,6 @@ constexpr int kMaxResidentCtas = 160; // CTAs of the persistent sweep (B200: 148
 constexpr int kXchgWords = 2 * kXchgMaxQ;
 constexpr int kXchgStride = 1;
 inline size_t xchg_bytes() { return (size_t)2 * kXchgWords * kXchgStride * sizeof(unsigned long long); }
-constexpr int kResThreads = 512;
 constexpr int kMaxBeta = 4;
 
 struct SweepDesc {  // the sweep currently bound to the context (begin/gram/update/finish/fetch)

@@ -8,14 +8,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/trace.txt"
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 252
+SEM = sys.argv[4] if len(sys.argv) > 4 else "reference"
 from options_model_b200 import engine as E  # noqa: E402
 
 eng = E.Engine(0)
 model = E.heston(100.0, 0.05, 1.0, v0=0.04, kappa=2.0, theta=0.04, xi=0.5, rho=-0.7)
 S = eng.paths(model, M, N, "f32", E.RngSpec(seed=1))
-eng.lsm(S, 100.0, 0.05, 1.0, "put", impl="resident")  # warm
+eng.lsm(S, 100.0, 0.05, 1.0, "put", semantics=SEM, impl="resident")  # warm
 os.environ["OPTMC_TRACE"] = out
-r = eng.lsm(S, 100.0, 0.05, 1.0, "put", impl="resident")
+r = eng.lsm(S, 100.0, 0.05, 1.0, "put", semantics=SEM, impl="resident")
 del os.environ["OPTMC_TRACE"]
 print("price", r.price)
 rows = np.loadtxt(out, comments="#")

@@ -121,25 +121,24 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&chk, ncta * 8));
   struct Cfg { int mode, nw, R, stride, pollkind, sleep_ns, work; const char* name; };
   std::vector<Cfg> cfgs = {
-      {0, 16, 1, 16, 0, 0, 0, "mode0 nw16 stride128B ld.relaxed"},
-      {0, 16, 1, 16, 1, 0, 0, "mode0 nw16 stride128B ld.volatile"},
       {0, 16, 1, 1, 0, 0, 0, "mode0 nw16 stride8B (one line)"},
-      {0, 16, 1, 4, 0, 0, 0, "mode0 nw16 stride32B"},
+      {0, 16, 1, 2, 0, 0, 0, "mode0 nw16 stride16B (two lines)"},
+      {0, 16, 1, 16, 0, 0, 0, "mode0 nw16 stride128B"},
+      {0, 16, 1, 32, 0, 0, 0, "mode0 nw16 stride256B"},
+      {0, 16, 1, 64, 0, 0, 0, "mode0 nw16 stride512B"},
+      {0, 16, 1, 128, 0, 0, 0, "mode0 nw16 stride1KB"},
+      {0, 16, 1, 256, 0, 0, 0, "mode0 nw16 stride2KB"},
       {0, 16, 1, 512, 0, 0, 0, "mode0 nw16 stride4KB"},
-      {0, 16, 1, 16, 0, 100, 0, "mode0 nw16 stride128B sleep100"},
-      {0, 16, 1, 16, 0, 400, 0, "mode0 nw16 stride128B sleep400"},
-      {0, 1, 1, 16, 0, 0, 0, "mode0 nw1"},
-      {0, 4, 1, 16, 0, 0, 0, "mode0 nw4"},
-      {0, 22, 1, 16, 0, 0, 0, "mode0 nw22"},
-      {1, 16, 2, 16, 0, 0, 0, "mode1 R2"},
-      {1, 16, 4, 16, 0, 0, 0, "mode1 R4"},
-      {1, 16, 8, 16, 0, 0, 0, "mode1 R8"},
-      {1, 16, 16, 16, 0, 0, 0, "mode1 R16"},
-      {2, 16, 1, 16, 0, 0, 0, "mode2 last-arriver broadcast"},
-      {2, 16, 1, 16, 1, 0, 0, "mode2 last-arriver broadcast ld.volatile"},
-      {0, 16, 1, 16, 0, 0, 3000, "mode0 + 3000-cycle work"},
-      {1, 16, 4, 16, 0, 0, 3000, "mode1 R4 + 3000-cycle work"},
-      {2, 16, 1, 16, 0, 0, 3000, "mode2 + 3000-cycle work"},
+      {0, 1, 1, 1, 0, 0, 0, "mode0 nw1"},
+      {0, 2, 1, 1, 0, 0, 0, "mode0 nw2 one line"},
+      {0, 4, 1, 1, 0, 0, 0, "mode0 nw4 one line"},
+      {0, 8, 1, 1, 0, 0, 0, "mode0 nw8 one line"},
+      {0, 22, 1, 1, 0, 0, 0, "mode0 nw22 packed"},
+      {0, 4, 1, 512, 0, 0, 0, "mode0 nw4 stride4KB"},
+      {0, 8, 1, 512, 0, 0, 0, "mode0 nw8 stride4KB"},
+      {1, 16, 2, 1, 0, 0, 0, "mode1 R2 packed"},
+      {1, 16, 4, 1, 0, 0, 0, "mode1 R4 packed"},
+      {0, 16, 1, 1, 0, 0, 3000, "mode0 packed + 3000-cycle work"},
   };
   for (const Cfg& c : cfgs) {
     CK(cudaMemset(acc, 0, acc_words * 8));
