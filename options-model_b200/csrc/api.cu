@@ -71,6 +71,15 @@ static int bind_sweep(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   const double dt = lp->T / N;
   sw.disc = exp(-lp->r * dt);
   sw.final_scale = (lp->semantics & OPTMC_SEM_REF_DISCOUNT) ? 1.0 : sw.disc;
+  sw.Dt.assign((size_t)N + 1, 1.0);
+  sw.Dinv.assign((size_t)N + 1, 1.0);
+  {
+    const double inv_disc = 1.0 / sw.disc;
+    double d = 1.0, di = 1.0;
+    for (int t = N; t >= 0; --t) { sw.Dt[t] = d; sw.Dinv[t] = di; d *= sw.disc; di *= inv_disc; }
+  }
+  sw.Kh = lp->K; sw.Kl = 0.0;
+  if (dtype == OPTMC_F32) { sw.Kh = (double)(float)lp->K; sw.Kl = (double)(float)(lp->K - sw.Kh); }
   return OPTMC_OK;
 }
 

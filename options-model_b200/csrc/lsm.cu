@@ -29,9 +29,13 @@ constexpr int kSplitThreads = 256;
 constexpr int kSplitWarps = kSplitThreads / 32;
 
 template <typename R> __global__ void lsm_init_kernel(const R* __restrict__ S_N, R* __restrict__ cf, long long M,
-                                                      double K, int is_put) {
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x)
-    cf[j] = (R)payoff<double>((double)S_N[j], K, is_put != 0);
+                                                      double K, double Kh, double Kl, int is_put) {
+  const R sgn = is_put ? (R)-1 : (R)1;
+  const R c1 = (R)(is_put ? Kh : -Kh), c2 = (R)(is_put ? Kl : -Kl);
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x) {
+    const R sr = S_N[j];
+    cf[j] = payoff<double>((double)sr, K, is_put != 0) > 0.0 ? fma(sgn, sr, c1) + c2 : (R)0;
+  }
 }
 
 // Sum the per-block partials in a fixed order (lane-strided, then butterfly): deterministic.
@@ -48,9 +52,11 @@ __device__ __forceinline__ void reduce_partials_last_block(const double* partial
   }
 }
 
+// Cash-flows are stored in "date-N money" (c~ = c_t / D_t, D_t = disc^(N - t); see lsm_resident_kernel.cuh):
+// the value of path j at date t is cf[j] * D_t (dg), so the per-date discount (om3:620) never touches HBM.
 template <typename R, int DEG>
 __global__ void __launch_bounds__(kSplitThreads)
-lsm_gram_kernel(const R* __restrict__ S_t, const R* __restrict__ cf, long long M, R disc, double K, double invK,
+lsm_gram_kernel(const R* __restrict__ S_t, const R* __restrict__ cf, long long M, R dg, double K, double invK,
                 int is_put, int sticky, double* partials, unsigned int* ticket, double* gram_out) {
   constexpr int Q = Moments<DEG>::Q;
   __shared__ double red[kSplitWarps * Q];
@@ -64,7 +70,7 @@ lsm_gram_kernel(const R* __restrict__ S_t, const R* __restrict__ cf, long long M
     const double s = (double)S_t[j];
     const double pay = payoff<double>(s, K, is_put != 0);
     if (pay > 0.0 && !ex) {
-      const R y = fabs(c) * disc;  // the discounted cash-flow exactly as the update kernel will store it
+      const R y = fabs(c) * dg;  // the cash-flow at date t exactly as the persistent sweep forms it
       moments_accumulate<DEG>(acc, s * invK, (double)y);
     }
   }
@@ -101,31 +107,43 @@ __global__ void lsm_solve_kernel(const double* __restrict__ gram, double* beta_t
 
 template <typename R, int DEG>
 __global__ void __launch_bounds__(kSplitThreads)
-lsm_update_kernel(const R* __restrict__ S_t, R* __restrict__ cf, long long M, R disc, double K, double invK,
-                  int is_put, int sticky, const double* __restrict__ beta_t, const int* __restrict__ valid_t,
-                  unsigned long long* bnd_t, unsigned long long* exc_t) {
+lsm_update_kernel(const R* __restrict__ S_t, R* __restrict__ cf, long long M, R dinv, double K, double Kh, double Kl,
+                  double invK, int is_put, int sticky, const double* __restrict__ beta_t,
+                  const int* __restrict__ valid_t, unsigned long long* bnd_t, unsigned long long* exc_t) {
+  if (*valid_t == 0) return;  // no regression at this date: nothing changes (cash-flows are in date-N money)
   double beta[DEG + 1];
 #pragma unroll
   for (int i = 0; i <= DEG; ++i) beta[i] = beta_t[i];
-  const bool valid = *valid_t != 0;
+  // decision polynomial in the raw price, exactly as the persistent sweep forms it
+  double dec[DEG + 1];
+  {
+    double sc = 1.0;
+#pragma unroll
+    for (int i = 0; i <= DEG; ++i) {
+      double d = -beta[i] * sc;
+      if (i == 0) d += is_put ? K : -K;
+      if (i == 1) d += is_put ? -1.0 : 1.0;
+      dec[i] = d;
+      sc *= invK;
+    }
+  }
+  const R sgn = is_put ? (R)-1 : (R)1;
+  const R c1 = (R)(is_put ? Kh : -Kh), c2 = (R)(is_put ? Kl : -Kl);
   unsigned long long bnd = bnd_none(is_put);
   unsigned int cnt = 0;
   for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x) {
     const R c = cf[j];
-    bool ex = sticky && signbit(c);
-    R a = fabs(c) * disc;
-    if (valid && !ex) {
-      const double s = (double)S_t[j];
-      const double pay = payoff<double>(s, K, is_put != 0);
-      if (pay > 0.0 && pay > poly_eval<DEG>(beta, s * invK)) {  // strict '>' (om3:644)
-        a = (R)pay;
-        ex = true;
-        cnt++;
-        const unsigned long long b = (unsigned long long)__double_as_longlong(s);
-        bnd = is_put ? (b > bnd ? b : bnd) : (b < bnd ? b : bnd);
-      }
+    if (sticky && signbit(c)) continue;
+    const R sr = S_t[j];
+    const double s = (double)sr;
+    const double pay = payoff<double>(s, K, is_put != 0);
+    if (pay > 0.0 && poly_eval<DEG>(dec, s) > 0.0) {  // strict '>' (om3:644)
+      const R a = (fma(sgn, sr, c1) + c2) * dinv;     // payoff in date-N money
+      cf[j] = sticky ? -a : a;
+      cnt++;
+      const unsigned long long b = (unsigned long long)__double_as_longlong(s);
+      bnd = is_put ? (b > bnd ? b : bnd) : (b < bnd ? b : bnd);
     }
-    cf[j] = (sticky && ex) ? -a : a;
   }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
   bnd = is_put ? warp_max_u64(bnd) : warp_min_u64(bnd);
@@ -137,7 +155,8 @@ lsm_update_kernel(const R* __restrict__ S_t, R* __restrict__ cf, long long M, R 
 
 template <typename R>
 __global__ void __launch_bounds__(kSplitThreads)
-lsm_final_kernel(const R* __restrict__ cf, long long M, double* partials, unsigned int* ticket, double* sums_out) {
+lsm_final_kernel(const R* __restrict__ cf, long long M, double d1, double* partials, unsigned int* ticket,
+                 double* sums_out) {
   __shared__ double red[kSplitWarps * 2];
   __shared__ bool is_last;
   double acc[2] = {0.0, 0.0};
@@ -157,7 +176,13 @@ lsm_final_kernel(const R* __restrict__ cf, long long M, double* partials, unsign
   if (is_last) {
     __threadfence();
     reduce_partials_last_block<2>(partials, gridDim.x, sums_out, kSplitWarps);
-    if (threadIdx.x == 0) { sums_out[2] = (double)M; *ticket = 0u; }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // date-N money -> value after N - 1 discounts (om3:651)
+      sums_out[0] *= d1;
+      sums_out[1] *= d1 * d1;
+      sums_out[2] = (double)M;
+      *ticket = 0u;
+    }
   }
 }
 
@@ -218,7 +243,7 @@ template <typename R> static int sweep_begin_t(optmc_ctx* ctx) {
   if (rc) return rc;
   const R* S_N = static_cast<const R*>(sw.S) + (size_t)sw.N * sw.ld;
   lsm_init_kernel<R><<<grid, kSplitThreads, 0, ctx->stream>>>(S_N, static_cast<R*>(ctx->cf), sw.M, sw.lp.K,
-                                                              sw.lp.is_put);
+                                                              sw.Kh, sw.Kl, sw.lp.is_put);
   ctx->launches++; sw.n_launches++;
   OPTMC_CUDA(cudaGetLastError());
   return OPTMC_OK;
@@ -234,7 +259,7 @@ template <typename R, int DEG> static int gram_date_t(optmc_ctx* ctx, int t, dou
   const R* S_t = static_cast<const R*>(sw.S) + (size_t)t * sw.ld;
   const bool sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) != 0;
   lsm_gram_kernel<R, DEG><<<grid, kSplitThreads, 0, ctx->stream>>>(S_t, static_cast<const R*>(ctx->cf), sw.M,
-                                                                   (R)sw.disc, sw.lp.K, 1.0 / sw.lp.K, sw.lp.is_put,
+                                                                   (R)sw.Dt[t], sw.lp.K, 1.0 / sw.lp.K, sw.lp.is_put,
                                                                    sticky, ctx->partials, ctx->tickets, gram_out);
   ctx->launches++; sw.n_launches++;
   OPTMC_CUDA(cudaGetLastError());
@@ -255,7 +280,7 @@ template <typename R, int DEG> static int update_date_t(optmc_ctx* ctx, int t, c
   lsm_solve_kernel<DEG><<<1, 32, 0, ctx->stream>>>(gram, ctx->d_betas + (size_t)t * kMaxBeta, ctx->d_nitm + t,
                                                    ctx->d_valid + t);
   lsm_update_kernel<R, DEG><<<grid, kSplitThreads, 0, ctx->stream>>>(
-      S_t, static_cast<R*>(ctx->cf), sw.M, (R)sw.disc, sw.lp.K, 1.0 / sw.lp.K, sw.lp.is_put, sticky,
+      S_t, static_cast<R*>(ctx->cf), sw.M, (R)sw.Dinv[t], sw.lp.K, sw.Kh, sw.Kl, 1.0 / sw.lp.K, sw.lp.is_put, sticky,
       ctx->d_betas + (size_t)t * kMaxBeta, ctx->d_valid + t, ctx->d_bnd + t, ctx->d_exc + t);
   ctx->launches += 2; sw.n_launches += 2;
   OPTMC_CUDA(cudaGetLastError());
@@ -273,10 +298,12 @@ int sweep_finish(optmc_ctx* ctx, double* sums_out) {
   const int grid = split_grid(ctx, sw.M);
   if (sw.dtype == OPTMC_F64)
     lsm_final_kernel<double><<<grid, kSplitThreads, 0, ctx->stream>>>(static_cast<const double*>(ctx->cf), sw.M,
-                                                                      ctx->partials, ctx->tickets, sums_out);
+                                                                      sw.Dt[sw.N >= 1 ? 1 : 0], ctx->partials, ctx->tickets,
+                                                                      sums_out);
   else
     lsm_final_kernel<float><<<grid, kSplitThreads, 0, ctx->stream>>>(static_cast<const float*>(ctx->cf), sw.M,
-                                                                     ctx->partials, ctx->tickets, sums_out);
+                                                                     sw.Dt[sw.N >= 1 ? 1 : 0], ctx->partials, ctx->tickets,
+                                                                     sums_out);
   ctx->launches++; sw.n_launches++;
   OPTMC_CUDA(cudaGetLastError());
   return OPTMC_OK;

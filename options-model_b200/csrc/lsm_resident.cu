@@ -36,6 +36,7 @@ static const ResShape kShapes[] = {OPTMC_RES_SHAPES(X)};
 static bool plan_resident(optmc_ctx* ctx, const SweepDesc& sw, ResPlan* p, std::string* why) {
   const size_t es = sw.dtype == OPTMC_F64 ? 8 : 4;
   if ((uintptr_t)sw.S % 16 != 0 || (sw.ld * es) % 16 != 0) { *why = "slab not 16-byte aligned"; return false; }
+  if ((sw.M * es) % 16 != 0) { *why = "path count is not a multiple of 16 bytes (bulk copies move whole 16-byte units)"; return false; }
   if (ctx->cc < 90) { *why = "bulk async copy needs sm_90+"; return false; }
   const int ncta_cap = ctx->sm_count < kMaxResidentCtas ? ctx->sm_count : kMaxResidentCtas;
   long long ncta = (sw.M + 511) / 512;  // at least one path per thread before adding CTAs
@@ -48,7 +49,8 @@ static bool plan_resident(optmc_ctx* ctx, const SweepDesc& sw, ResPlan* p, std::
   for (const ResShape& c : kShapes)
     if ((long long)c.nt * c.ppt >= chunk) { shape = &c; break; }
   if (!shape) { *why = "slice exceeds the register-resident capacity"; return false; }
-  const size_t stride = (chunk * es + 127) / 128 * 128;
+  // every stage holds the full NT x PPT slot grid: the tail behind the slice is an out-of-the-money sentinel
+  const size_t stride = ((size_t)shape->nt * shape->ppt * es + 127) / 128 * 128;
   const size_t avail = (size_t)ctx->max_smem_optin - 8192;  // static shared + slack
   int nstage = 3;
   if (stride * 3 > avail) nstage = 2;

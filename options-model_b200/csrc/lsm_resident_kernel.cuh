@@ -39,15 +39,14 @@ template <int QN> struct Pow2 { static constexpr int v = QN <= 2 ? 2 : QN <= 4 ?
 // sign-bit mask under the sticky semantics and 0 otherwise.
 template <typename R> struct Store;
 template <> struct Store<float> {
-  static __device__ __forceinline__ bool flagged(float c, unsigned int flag) { return (__float_as_uint(c) & flag) != 0u; }
+  // exercised payoffs are > 0, so "sign bit set" is simply c < 0 (never true without the sticky mask)
+  static __device__ __forceinline__ bool flagged(float c, unsigned int) { return c < 0.0f; }
   static __device__ __forceinline__ float with_flag(float p, unsigned int flag) {
     return __uint_as_float(__float_as_uint(p) | flag);
   }
 };
 template <> struct Store<double> {
-  static __device__ __forceinline__ bool flagged(double c, unsigned int flag) {
-    return ((unsigned int)__double2hiint(c) & flag) != 0u;
-  }
+  static __device__ __forceinline__ bool flagged(double c, unsigned int) { return c < 0.0; }
   static __device__ __forceinline__ double with_flag(double p, unsigned int flag) {
     return __hiloint2double((int)((unsigned int)__double2hiint(p) | flag), __double2loint(p));
   }
@@ -129,6 +128,9 @@ template <typename R> struct PassConsts {
 // bound on the fp32 evaluation error (coefficient rounding + Horner: <= 4 u * sum |d_i| S^i, u = 2^-24;
 // the filter uses 8 u); only paths whose fp32 value is inside the bound are re-decided in fp64, so the
 // decisions are identical to the fp64 evaluation while the fp64 pipe sees a handful of paths per date.
+template <bool WIDE> struct MaskOf { typedef unsigned int type; };
+template <> struct MaskOf<true> { typedef unsigned long long type; };
+
 template <typename R, int DEG> struct Decider;
 template <int DEG> struct Decider<double, DEG> {
   double d[DEG + 1];
@@ -161,40 +163,39 @@ template <int DEG> struct Decider<float, DEG> {
   }
 };
 
-// Passes over the thread's PPT paths (path j = tid + k * NT); dead lanes contribute zeros.
-//   decide_pass: exercise decision of date t (sticky flag = sign bit of the stored cash-flow, om3:649);
-//   gram_pass:   the ITM-masked (om3:621) raw-price moments of date t-1.
-// SPARSE = true skips a warp's step when none of its 32 paths is in the regression -- under the reference's
-// sticky mask most in-the-money paths are already flagged, so only ~0.5% of the paths are live per date.
-// SPARSE = false is fully branch-free (textbook semantics: ~40% of the paths are live at every date).
-template <typename R, int DEG, int PPT, int NT, bool SPARSE>
+// Passes over the thread's PPT paths (path j = tid + k * NT).  Slots past the end of the CTA's slice read an
+// out-of-the-money sentinel from shared memory and hold a zero cash-flow, so no bounds predicate is needed.
+//   decision of date t: exercise iff dec(S_t) > 0; the sticky flag is the sign bit of the stored cash-flow
+//                       (om3:649);
+//   Gram of date t-1:   ITM-masked (om3:621) raw-price moments, after the decision of date t.
+//
+// DENSE (textbook semantics, ~40% of the paths live at every date): two straight-line loops, dead lanes
+// contribute zeros, paths the fp32 filter cannot decide are collected in a mask and re-decided afterwards.
+template <typename R, int DEG, int PPT, int NT>
 __device__ __forceinline__ void decide_pass(R (&cf)[PPT], const R* __restrict__ st_t, const Decider<R, DEG>& dec,
                                             const PassConsts<R>& pc, unsigned int& cnt, R& em) {
   const int tid = threadIdx.x;
-  unsigned long long amb = 0ull;  // paths the fp32 filter could not decide
+  typedef typename MaskOf<(PPT > 32)>::type Mask;
+  Mask amb = 0;  // paths the fp32 filter could not decide
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
-    const int j = tid + k * NT;
-    const bool in = j < pc.n_local;
     const R c = cf[k];
-    const R sr = in ? st_t[j] : (R)0;
+    const R sr = st_t[tid + k * NT];
     const R u = pc.sgn * sr;
-    const bool live = in & !Store<R>::flagged(c, pc.flag) & (u > pc.kk);
-    if (!SPARSE || __any_sync(0xffffffffu, live)) {
-      bool sure;
-      const bool pos = dec.fast(sr, sure);
-      const bool exer = live & sure & pos;
-      amb |= (live & !sure) ? (1ull << k) : 0ull;
-      const R pay = Store<R>::with_flag((fma(pc.sgn, sr, pc.c1) + pc.c2) * pc.dinv, pc.flag);
-      cf[k] = exer ? pay : c;
-      cnt += exer ? 1u : 0u;
-      em = fmax(em, exer ? -u : (R)-INFINITY);
-    }
+    const bool live = !Store<R>::flagged(c, pc.flag) & (u > pc.kk);
+    bool sure;
+    const bool pos = dec.fast(sr, sure);
+    const bool exer = live & sure & pos;
+    amb |= (live & !sure) ? ((Mask)1 << k) : (Mask)0;
+    const R pay = Store<R>::with_flag((fma(pc.sgn, sr, pc.c1) + pc.c2) * pc.dinv, pc.flag);
+    cf[k] = exer ? pay : c;
+    cnt += exer ? 1u : 0u;
+    em = fmax(em, exer ? -u : (R)-INFINITY);
   }
   if (amb) {  // rare: a handful of paths per date sit within fp32 rounding of the exercise boundary
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-      if (amb & (1ull << k)) {
+      if (amb & ((Mask)1 << k)) {
         const R sr = st_t[tid + k * NT];
         if (dec.exact(sr)) {
           cf[k] = Store<R>::with_flag((fma(pc.sgn, sr, pc.c1) + pc.c2) * pc.dinv, pc.flag);
@@ -206,21 +207,57 @@ __device__ __forceinline__ void decide_pass(R (&cf)[PPT], const R* __restrict__ 
   }
 }
 
-template <typename R, int DEG, int PPT, int NT, bool SPARSE>
+template <typename R, int DEG, int PPT, int NT>
 __device__ __forceinline__ void gram_pass(const R (&cf)[PPT], const R* __restrict__ st_g, const PassConsts<R>& pc,
                                           double (&mom)[Moments<DEG>::Q], unsigned int& rows) {
   const int tid = threadIdx.x;
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
-    const int j = tid + k * NT;
-    const bool in = j < pc.n_local;
     const R c = cf[k];
-    const R s = in ? st_g[j] : (R)0;
-    const bool live = in & !Store<R>::flagged(c, pc.flag) & (pc.sgn * s > pc.kk);
-    if (!SPARSE || __any_sync(0xffffffffu, live)) {
-      const R y = c * pc.dg;  // live lanes are unflagged: c >= 0
-      rows += live ? 1u : 0u;
-      moments_accumulate_nocount<DEG>(mom, (double)(live ? s : (R)0), (double)(live ? y : (R)0));
+    const R s = st_g[tid + k * NT];
+    const bool live = !Store<R>::flagged(c, pc.flag) & (pc.sgn * s > pc.kk);
+    const R y = c * pc.dg;  // live lanes are unflagged: c >= 0
+    rows += live ? 1u : 0u;
+    moments_accumulate_nocount<DEG>(mom, (double)(live ? s : (R)0), (double)(live ? y : (R)0));
+  }
+}
+
+// SPARSE (the reference's sticky mask: most in-the-money paths are already flagged, ~0.5% of the paths are in
+// the regression per date): one loop; a warp skips step k when none of its 32 paths is live at date t or t-1.
+template <typename R, int DEG, int PPT, int NT, bool DECIDE, bool GRAM>
+__device__ __forceinline__ void sparse_pass(R (&cf)[PPT], const R* __restrict__ st_t, const R* __restrict__ st_g,
+                                            const Decider<R, DEG>& dec, const PassConsts<R>& pc,
+                                            double (&mom)[Moments<DEG>::Q], unsigned int& rows, unsigned int& cnt,
+                                            R& em) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int j = tid + k * NT;
+    R c = cf[k];
+    const bool open = !Store<R>::flagged(c, pc.flag);
+    const R st = DECIDE ? st_t[j] : (R)0;
+    const R sg = GRAM ? st_g[j] : (R)0;
+    const R ut = pc.sgn * st;
+    const bool lt = DECIDE & open & (ut > pc.kk);
+    const bool lg = GRAM & open & (pc.sgn * sg > pc.kk);
+    if (__any_sync(0xffffffffu, lt | lg)) {
+      if (DECIDE) {
+        bool sure;
+        bool pos = dec.fast(st, sure);
+        if (lt & !sure) pos = dec.exact(st);  // rare: within fp32 rounding of the exercise boundary
+        const bool exer = lt & pos;
+        const R pay = Store<R>::with_flag((fma(pc.sgn, st, pc.c1) + pc.c2) * pc.dinv, pc.flag);
+        c = exer ? pay : c;
+        cf[k] = c;
+        cnt += exer ? 1u : 0u;
+        em = fmax(em, exer ? -ut : (R)-INFINITY);
+      }
+      if (GRAM) {
+        const bool live = lg & !Store<R>::flagged(c, pc.flag);  // not exercised just now (sticky mask)
+        const R y = c * pc.dg;                                   // live lanes are unflagged: c >= 0
+        rows += live ? 1u : 0u;
+        moments_accumulate_nocount<DEG>(mom, (double)(live ? sg : (R)0), (double)(live ? y : (R)0));
+      }
     }
   }
 }
@@ -244,7 +281,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
   const long long base = (long long)cta * a.chunk;
   const long long rem = a.M - base;
   const int n_local = (int)(rem < a.chunk ? rem : a.chunk);
-  const unsigned int bytes = (unsigned int)(((size_t)n_local * sizeof(R) + 15) / 16 * 16);
+  const unsigned int bytes = (unsigned int)((size_t)n_local * sizeof(R));  // multiple of 16 (planner)
   const bool is_put = a.is_put != 0;
   const bool sticky = a.sticky != 0;
   const R sgn = (R)a.sgn, kk = (R)a.kk, c1 = (R)a.c1, c2 = (R)a.c2;
@@ -252,15 +289,14 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
   const int N = a.N, nstage = a.nstage;
   const R* Sbase = static_cast<const R*>(a.S) + base;
 
-  auto stage_ptr = [&](int t) -> const R* {
-    return reinterpret_cast<const R*>(smem_raw + (size_t)(t % nstage) * a.stage_stride);
-  };
-  auto issue_load = [&](int t) {  // one thread
-    uint64_t* bar = &mbar[t % nstage];
+  // Stage ring: date t lives in slot (N - t) % nstage; the slots of the dates in use are tracked
+  // incrementally (no integer division on the per-date path).
+  auto slot_ptr = [&](int slot) -> R* { return reinterpret_cast<R*>(smem_raw + (size_t)slot * a.stage_stride); };
+  auto issue_load = [&](int t, int slot) {  // one thread
+    uint64_t* bar = &mbar[slot];
     mbar_arrive_expect_tx(bar, bytes);
-    bulk_load_1d(smem_raw + (size_t)(t % nstage) * a.stage_stride, Sbase + (size_t)t * a.ld, bytes, bar);
+    bulk_load_1d(smem_raw + (size_t)slot * a.stage_stride, Sbase + (size_t)t * a.ld, bytes, bar);
   };
-  auto wait_stage = [&](int t) { mbar_wait(&mbar[t % nstage], (unsigned)(((N - t) / nstage) & 1)); };
 
   if (tid == 0) {
     for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
@@ -269,10 +305,16 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
     s_cnt[0] = s_cnt[1] = 0u;
     s_valid = 0;
   }
+  // out-of-the-money sentinel behind the slice in every stage (the bulk copies never touch it)
+  {
+    const R sentinel = is_put ? (R)INFINITY : (R)-INFINITY;
+    for (int s = 0; s < nstage; ++s)
+      for (int i = n_local + tid; i < PPT * NT; i += NT) slot_ptr(s)[i] = sentinel;
+  }
   __syncthreads();
   if (tid == 0) {
     for (int i = 0; i < nstage; ++i)
-      if (N - i >= 1) issue_load(N - i);
+      if (N - i >= 1) issue_load(N - i, i);
   }
 
   // warp-0 lane constants: lane l serves quantity l >> 1; raw-price moments are rescaled to x = S/K
@@ -288,16 +330,20 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
 
   // ---- date N: cash-flows = payoff(S[N]) (om3:616) ----
   R cf[PPT];
-  wait_stage(N);
+  int slot_t = 0;           // ring slot of the iteration's decision date
+  unsigned int phase = 0u;  // bit s: mbarrier phase parity the next wait on slot s expects
+  auto wait_slot = [&](int slot) {
+    mbar_wait(&mbar[slot], (phase >> slot) & 1u);
+    phase ^= 1u << slot;
+  };
+  wait_slot(0);
   {
-    const R* st = stage_ptr(N);
+    const R* st = slot_ptr(0);
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
-      const int j = tid + k * NT;
-      const bool in = j < n_local;
-      const R s = in ? st[j] : (R)0;
+      const R s = st[tid + k * NT];  // sentinel past the slice: out of the money -> 0
       const R p = fma(sgn, s, c1) + c2;
-      cf[k] = (in & (sgn * s > kk)) ? p : (R)0;
+      cf[k] = (sgn * s > kk) ? p : (R)0;
     }
   }
 
@@ -311,10 +357,11 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
     long long* tr = tr_base ? tr_base + (size_t)t * 8 : nullptr;
     const bool gram = t >= 2;
     const bool decide = t <= N - 1 && s_valid != 0;
-    if (gram) wait_stage(t - 1);
+    const int slot_g = slot_t + 1 == nstage ? 0 : slot_t + 1;  // ring slot of the Gram date t-1
+    if (gram) wait_slot(slot_g);
     OPTMC_TRACE_AT(0);
-    const R* st_t = stage_ptr(t);
-    const R* st_g = stage_ptr(gram ? t - 1 : t);
+    const R* st_t = slot_ptr(slot_t);
+    const R* st_g = slot_ptr(gram ? slot_g : slot_t);
     double mom[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) mom[q] = 0.0;
@@ -322,12 +369,16 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
     R em = (R)-INFINITY;  // max over exercised paths of -sgn * S: put -> max S, call -> -(min S)
     // D_t = disc^(N - t): every thread advances the same fp64 products, so they agree bit for bit
     const PassConsts<R> pc{sgn, kk, c1, c2, (R)dinv_t, (R)(d_t * a.disc), flag, n_local};
-    if (decide) {
-      Decider<R, DEG> dec;
-      dec.load(s_dec, true);
-      decide_pass<R, DEG, PPT, NT, SPARSE>(cf, st_t, dec, pc, cnt, em);
+    Decider<R, DEG> dec;
+    dec.load(s_dec, decide);
+    if (SPARSE) {
+      if (decide && gram) sparse_pass<R, DEG, PPT, NT, true, true>(cf, st_t, st_g, dec, pc, mom, rows, cnt, em);
+      else if (gram) sparse_pass<R, DEG, PPT, NT, false, true>(cf, st_t, st_g, dec, pc, mom, rows, cnt, em);
+      else if (decide) sparse_pass<R, DEG, PPT, NT, true, false>(cf, st_t, st_g, dec, pc, mom, rows, cnt, em);
+    } else {
+      if (decide) decide_pass<R, DEG, PPT, NT>(cf, st_t, dec, pc, cnt, em);
+      if (gram) gram_pass<R, DEG, PPT, NT>(cf, st_g, pc, mom, rows);
     }
-    if (gram) gram_pass<R, DEG, PPT, NT, SPARSE>(cf, st_g, pc, mom, rows);
     d_t *= a.disc;
     dinv_t *= a.inv_disc;
     if (decide) {
@@ -360,7 +411,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
         s_cnt[0] = 0u;
         s_bnd[0] = bnd_none(a.is_put);
       }
-      if (t - nstage >= 1) issue_load(t - nstage);  // refill the stage date t vacated
+      if (t - nstage >= 1) issue_load(t - nstage, slot_t);  // refill the slot date t vacated
     }
     if (warp == 0) {
       int spins = 0;
@@ -396,6 +447,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
       OPTMC_TRACE_AT(5);
     }
     ++seq;
+    slot_t = slot_g;
     __syncthreads();  // decision polynomial of date t-1 visible
   }
 
@@ -403,12 +455,9 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
   double fin[2] = {0.0, 0.0};
 #pragma unroll
   for (int k = 0; k < PPT; ++k) {
-    const int j = tid + k * NT;
-    if (j < n_local) {
-      const double c = fabs((double)cf[k]);
-      fin[0] += c;
-      fin[1] += c * c;
-    }
+    const double c = fabs((double)cf[k]);  // slots past the slice hold 0
+    fin[0] += c;
+    fin[1] += c * c;
   }
   const double mine = block_totals<2, NW>(fin, s_red);
   if (tid == 32 && s_cnt[0]) {  // statistics of date 1 (its update pass is behind the barrier above)
@@ -457,7 +506,7 @@ int launch_resident_t(optmc_ctx* ctx, const ResPlan& p, ResArgs& a) {
 // (<= 128 registers per thread); 1024-thread CTAs measured slower (barrier cost) and are not built.
 #define OPTMC_RES_SHAPES(X) \
   X(512, 1) X(512, 2) X(512, 4) X(512, 8) X(512, 12) X(512, 14) X(512, 16) X(512, 20) X(512, 24) X(512, 28) \
-  X(512, 32) X(512, 40) X(512, 48) X(512, 56)
+  X(512, 32) X(512, 40) X(512, 48) X(512, 54)
 
 template <typename R, int DEG> int launch_resident_shape(optmc_ctx* ctx, const ResPlan& p, ResArgs& a) {
 #define X(NT_, PPT_)                                                                       \

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/optmc.h"
 
@@ -26,6 +27,10 @@ struct SweepDesc {  // the sweep currently bound to the context (begin/gram/upda
   optmc_lsm_params lp{};
   int deg = 2;
   double disc = 1.0, final_scale = 1.0;
+  // cash-flows live in "date-N money": Dt[t] = disc^(N - t) and Dinv[t] = disc^-(N - t), built by the same
+  // running fp64 products the persistent kernel forms on the device (bit-identical factors)
+  std::vector<double> Dt, Dinv;
+  double Kh = 0.0, Kl = 0.0;  // K = Kh + Kl with Kh exact in the storage type (Kl = 0 for fp64 storage)
   int impl_used = 0;
   int n_launches = 0;
   bool have_results = false;
