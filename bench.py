@@ -33,6 +33,20 @@ METRIC = "path-steps/sec, Heston American put LSM"
 UNIT = "path-steps/s"
 
 
+def load_traffic(kernel_substr):
+    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/ncu_r1_summary.json)."""
+    p = os.path.join(ROOT, "profiles", "ncu_r1_summary.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        for name, ks in d.get("kernels", {}).items():
+            if kernel_substr in name:
+                return float(ks[0]["dram_bytes"])
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -130,7 +144,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:  # noqa: BLE001
                 pass
-            self.stop.wait(0.02)
+            self.stop.wait(0.005)
 
     def __enter__(self):
         if self.nv is not None:
@@ -248,9 +262,11 @@ def run_own_arm(args):
         bytes_sweep = 3 * b * M * (N - 1) + b * M
         kern = {
             "paths_kernel<f32,heston_ref_absorb,vec4,philox>": {
-                "ms": ms_paths, "alg_bytes": bytes_paths, "GBps": bytes_paths / (ms_paths * 1e-3) / 1e9},
-            "lsm_resident_kernel<f32,poly2>": {
-                "ms": ms_sweep, "alg_bytes": bytes_sweep, "GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9},
+                "ms": ms_paths, "alg_bytes": bytes_paths, "GBps": bytes_paths / (ms_paths * 1e-3) / 1e9,
+                "dram_bytes_ncu": load_traffic("paths_kernel")},
+            "lsm_resident_kernel<f32,poly2,sparse>": {
+                "ms": ms_sweep, "alg_bytes": bytes_sweep, "GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9,
+                "dram_bytes_ncu": load_traffic("lsm_resident_kernel")},
         }
         dom = max(kern, key=lambda k: kern[k]["ms"])
         ach = kern[dom]["GBps"]
@@ -268,7 +284,10 @@ def run_own_arm(args):
                        "l2": f"slab {b * M * (N + 1) / 1e6:.0f} MB per step > L2 ({eng.l2_bytes / 1e6:.0f} MB): no flush needed",
                        "price": res.price, "stderr": res.stderr},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": None, "kernel": dom, "peak_source": peak_src,
+                         "traffic": kern[dom]["dram_bytes_ncu"], "kernel": dom, "peak_source": peak_src,
+                         "note": "achieved = algorithmic bytes (SURVEY 8d: 3b per path per exercise date for the sweep, "
+                                 "b per path-step for generation) / CUDA-event time of that kernel; traffic = DRAM bytes "
+                                 "per launch from the committed ncu capture (profiles/)",
                          "pipeline_frac": (4 * b * M * N * world * args.steps) / (ms_total * 1e-3) / 1e9 / (peak * world),
                          "kernels": kern},
             "e2e": {"value": world * M * N * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -290,12 +309,12 @@ def run_own_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--paths", type=int, default=1_000_000)
     ap.add_argument("--dates", type=int, default=252)
-    ap.add_argument("--cpu-paths", type=int, default=400_000, help="CPU-baseline sample size (paths)")
+    ap.add_argument("--cpu-paths", type=int, default=1_000_000, help="CPU-baseline sample size (paths)")
     ap.add_argument("--ref-paths", type=int, default=50_000, help="reference arm: paths per worker per step")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

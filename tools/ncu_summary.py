@@ -1,0 +1,103 @@
+"""Turn the ncu artefacts a gpurun call brought back (gpurun_out/) into the tracked summaries under profiles/.
+
+  python tools/ncu_summary.py [round_tag]
+
+Inputs : gpurun_out/launches_<tag>.csv  (ncu --metrics gpu__time_duration.sum launch list)
+         gpurun_out/prof_<tag>.ncu-rep  (ncu --set full capture of the two hot kernels)
+Outputs: profiles/launches_<tag>.csv (copy), profiles/ncu_<tag>_summary.json, profiles/ncu_<tag>_summary.md
+bench.py reads profiles/ncu_<tag>_summary.json for roofline.traffic (DRAM bytes per launch of the dominant kernel).
+"""
+import csv
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+from collections import defaultdict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+summary = {"tag": tag, "launches": {}, "kernels": {}}
+
+launch_csv = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
+if os.path.exists(launch_csv):
+    shutil.copy(launch_csv, os.path.join(out_dir, f"launches_{tag}.csv"))
+    rows = list(csv.reader(l for l in open(launch_csv) if l.startswith('"')))
+    ix = {h: i for i, h in enumerate(rows[0])}
+    agg = defaultdict(list)
+    for r in rows[1:]:
+        agg[r[ix["Kernel Name"]]].append(float(r[ix["Metric Value"]]))
+    tot = sum(sum(v) for v in agg.values())
+    for k, v in agg.items():
+        summary["launches"][k] = {"n": len(v), "mean_us": sum(v) / len(v) / 1e3, "share": sum(v) / tot}
+
+rep = os.path.join(ROOT, "gpurun_out", f"prof_{tag}.ncu-rep")
+WANT = {
+    "gpu__time_duration.sum": "duration",
+    "dram__bytes_read.sum": "dram_read",
+    "dram__bytes_write.sum": "dram_write",
+    "launch__registers_per_thread": "registers",
+    "launch__grid_size": "grid",
+    "launch__block_size": "block",
+    "smsp__inst_executed.sum": "warp_instructions",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active": "pipe_alu_pct",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active": "pipe_fma_pct",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "pipe_fp64_pct",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active": "pipe_xu_pct",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "pipe_lsu_pct",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio": "stall_barrier",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio": "stall_wait",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio": "stall_math_pipe",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio": "stall_no_instruction",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio": "stall_short_scoreboard",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio": "stall_not_selected",
+}
+UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}
+if os.path.exists(rep):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        k = {}
+        for i, h in enumerate(hdr):
+            if h in WANT and r[i] != "":
+                try:
+                    v = float(r[i].replace(",", ""))
+                except ValueError:
+                    continue
+                k[WANT[h]] = v * UNIT.get(units[i], 1.0) if WANT[h] in ("duration", "dram_read", "dram_write") else v
+        k["dram_bytes"] = k.get("dram_read", 0.0) + k.get("dram_write", 0.0)
+        summary["kernels"].setdefault(name, []).append(k)
+
+with open(os.path.join(out_dir, f"ncu_{tag}_summary.json"), "w") as f:
+    json.dump(summary, f, indent=1)
+
+lines = [f"# ncu summary ({tag})", "",
+         "Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`; cold-cache, serialised: compare shares):", "",
+         "| kernel | launches | mean us | share |", "|---|---|---|---|"]
+for k, v in summary["launches"].items():
+    lines.append(f"| `{re.sub(r'[|]', '/', k)[:90]}` | {v['n']} | {v['mean_us']:.1f} | {v['share']:.3f} |")
+lines += ["", "Full capture (`ncu --set full --clock-control none --import-source on`), per launch:", ""]
+for name, ks in summary["kernels"].items():
+    k = ks[0]
+    lines.append(f"## `{name}`")
+    lines.append("")
+    for key in ("duration", "dram_read", "dram_write", "dram_bytes", "registers", "warp_instructions", "issue_active_pct",
+                "warps_active_pct", "pipe_alu_pct", "pipe_fma_pct", "pipe_fp64_pct", "pipe_xu_pct", "pipe_lsu_pct",
+                "stall_barrier", "stall_wait", "stall_math_pipe", "stall_no_instruction", "stall_long_scoreboard",
+                "stall_short_scoreboard", "stall_not_selected"):
+        if key in k:
+            lines.append(f"* {key}: {k[key]:.6g}")
+    lines.append("")
+with open(os.path.join(out_dir, f"ncu_{tag}_summary.md"), "w") as f:
+    f.write("\n".join(lines) + "\n")
+print("\n".join(lines))
