@@ -67,35 +67,42 @@ OPTMC_HD float u32_as_f32(uint32_t x) {
 
 template <typename R> struct Real;  // per-precision math: device fast paths for float, IEEE for double
 
+// Device fast-math primitives (MUFU, flush-to-zero: none of the arguments below can be denormal).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+
 template <> struct Real<float> {
   static OPTMC_HD float exp_(float x) {
 #if defined(__CUDA_ARCH__)
-    return __expf(x);
+    return mufu_ex2(x * 1.4426950408889634f);
 #else
     return expf(x);
 #endif
   }
   static OPTMC_HD float sqrt_(float x) {
 #if defined(__CUDA_ARCH__)
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
+    return mufu_sqrt(x);
 #else
     return sqrtf(x);
 #endif
   }
   // Box-Muller on two 32-bit words -> two N(0,1).  Uniforms built by mantissa stuffing (no I2F):
-  // u in (0,1] with 2^-23 resolution (|z| <= 5.65), angle v in [0,1).
+  // u in (0,1] with 2^-23 resolution (|z| <= 5.65); the angle is 2 pi w with w in [1,2) (one period, so no
+  // subtraction is needed).
   static OPTMC_HD void normal2(uint32_t a, uint32_t b, float& n0, float& n1) {
     float u = 2.0f - u32_as_f32(0x3f800000u | (a >> 9));
-    float v = u32_as_f32(0x3f800000u | (b >> 9)) - 1.0f;
+    float ang = 6.283185307179586f * u32_as_f32(0x3f800000u | (b >> 9));
 #if defined(__CUDA_ARCH__)
-    float rad = sqrt_(-1.3862943611198906f * __log2f(u));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
-    float s, c;
-    __sincosf(6.283185307179586f * v, &s, &c);
+    float rad = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u));  // sqrt(-2 ln u) = sqrt(-2 ln2 log2 u)
+    float s = mufu_sin(ang), c = mufu_cos(ang);
 #else
     float rad = sqrtf(-2.0f * logf(u));
-    float s = sinf(6.283185307179586f * v), c = cosf(6.283185307179586f * v);
+    float s = sinf(ang), c = cosf(ang);
 #endif
     n0 = rad * c;
     n1 = rad * s;
@@ -166,6 +173,58 @@ template <typename R> OPTMC_HD void heston_calib_step(R& S, R& v, R z1, R z2, co
   v = rmax(vp + dV, (R)1e-8);
   R dS = c.r * S * c.dt + sqv * S * c.sqrt_dt * z1;
   S = S + dS;
+}
+
+// fp32 production form of the two Euler schemes for one antithetic pair (+z, -z): the drift / diffusion
+// constants are pre-folded (log2 e into the exponent so the exponential is one MUFU.EX2), and everything the
+// two partners share (w2, z1 log2 e) is computed once.  Algebraically identical to heston_absorb_step /
+// heston_fulltrunc_step; rounding differs in the last ulp.  10 instructions + 2 MUFU per path-step.
+struct HestonPairF32 {
+  float dt, a_v, b_v, xi, c_s, r_s, rho, rho_c, l2e;
+};
+OPTMC_HD HestonPairF32 heston_pair_consts(const HestonConsts<float>& c) {
+  HestonPairF32 f;
+  f.dt = c.dt;
+  f.a_v = 1.0f - c.kappa * c.dt;        // v + kappa (theta - v) dt = v (1 - kappa dt) + kappa theta dt
+  f.b_v = c.kappa * c.theta * c.dt;
+  f.xi = c.xi;
+  f.l2e = 1.4426950408889634f;
+  f.c_s = -0.5f * c.dt * f.l2e;         // exp(x) = 2^(x log2 e)
+  f.r_s = c.r * c.dt * f.l2e;
+  f.rho = c.rho; f.rho_c = c.rho_c;
+  return f;
+}
+OPTMC_HD float exp2_fast(float x) {
+#if defined(__CUDA_ARCH__)
+  return mufu_ex2(x);
+#else
+  return exp2f(x);
+#endif
+}
+// ABSORB: requires vp, vm >= 0 on entry (the stored variance is already truncated, om3:233)
+template <bool ABSORB>
+OPTMC_HD void heston_pair_step_f32(float& sp, float& vp, float& sm, float& vm, float z1, float z2,
+                                   const HestonPairF32& f) {
+  const float w2 = fmaf(f.rho, z1, f.rho_c * z2);
+  const float z1l = z1 * f.l2e;
+  {
+    const float v = ABSORB ? vp : rmax(vp, 0.0f);
+    const float sq = Real<float>::sqrt_(v * f.dt);
+    const float e = fmaf(sq, z1l, fmaf(v, f.c_s, f.r_s));
+    const float vn = ABSORB ? fmaf(f.xi * sq, w2, fmaf(v, f.a_v, f.b_v))
+                            : fmaf(f.xi * sq, w2, vp + fmaf(v, f.a_v - 1.0f, f.b_v));
+    vp = ABSORB ? rmax(vn, 0.0f) : vn;
+    sp *= exp2_fast(e);
+  }
+  {
+    const float v = ABSORB ? vm : rmax(vm, 0.0f);
+    const float sq = Real<float>::sqrt_(v * f.dt);
+    const float e = fmaf(-sq, z1l, fmaf(v, f.c_s, f.r_s));
+    const float vn = ABSORB ? fmaf(-(f.xi * sq), w2, fmaf(v, f.a_v, f.b_v))
+                            : fmaf(-(f.xi * sq), w2, vm + fmaf(v, f.a_v - 1.0f, f.b_v));
+    vm = ABSORB ? rmax(vn, 0.0f) : vn;
+    sm *= exp2_fast(e);
+  }
 }
 
 // om3:376-380

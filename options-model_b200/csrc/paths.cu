@@ -45,10 +45,15 @@ template <typename R, int SCHEME> __device__ __forceinline__ void heston_step(R&
   else heston_calib_step<R>(S, v, z1, z2, c);
 }
 
+template <typename R, int SCHEME> struct FastPair { static constexpr bool value = false; };
+template <> struct FastPair<float, OPTMC_SCHEME_HESTON_REF_ABSORB> { static constexpr bool value = true; };
+template <> struct FastPair<float, OPTMC_SCHEME_HESTON_FULL_TRUNC> { static constexpr bool value = true; };
+
 template <typename R, int SCHEME, int VEC, bool EXTZ>
 __global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
   constexpr bool HES = (SCHEME >= OPTMC_SCHEME_HESTON_REF_ABSORB);
   constexpr bool LOGSPACE = (SCHEME == OPTMC_SCHEME_GBM_LOGSPACE);
+  constexpr bool FAST = FastPair<R, SCHEME>::value;  // fp32 Heston: both partners of a pair in one fused step
   constexpr int SPB = HES ? 2 : 4;  // steps served by one Philox block
   const long long c0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (c0 >= a.Mh) return;
@@ -60,6 +65,8 @@ __global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
   HestonConsts<R> hc;
   hc.dt = (R)a.dt; hc.sqrt_dt = (R)a.sqrt_dt; hc.r = (R)a.r; hc.kappa = (R)a.kappa; hc.theta = (R)a.theta;
   hc.xi = (R)a.xi; hc.rho = (R)a.rho; hc.rho_c = (R)a.rho_c;
+  HestonPairF32 hf{};
+  if constexpr (FAST) hf = heston_pair_consts(hc);
 
   R sp[VEC], sm[VEC], vp[VEC], vm[VEC], out[VEC];
   const R s_init = LOGSPACE ? (R)log(fmax(a.S0, 1e-12)) : (R)a.S0;
@@ -76,6 +83,10 @@ __global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
   if (HES && Vrow) {
     VecIO<R, VEC>::store(Vrow, vp);
     if (anti) VecIO<R, VEC>::store(Vrow + a.Mh, vp);
+  }
+  if (FAST && SCHEME == OPTMC_SCHEME_HESTON_REF_ABSORB) {  // the fused step assumes the truncated state (om3:229)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { vp[i] = rmax(vp[i], (R)0); vm[i] = rmax(vm[i], (R)0); }
   }
 
   for (int t0 = 0; t0 < a.N; t0 += SPB) {
@@ -104,6 +115,20 @@ __global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
       }
       Srow += a.ld;
       if (Vrow) Vrow += a.ld;
+      if constexpr (FAST) {
+        if (anti) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i)
+            heston_pair_step_f32<SCHEME == OPTMC_SCHEME_HESTON_REF_ABSORB>(sp[i], vp[i], sm[i], vm[i], z1[i], z2[i], hf);
+          VecIO<R, VEC>::store(Srow, sp);
+          VecIO<R, VEC>::store(Srow + a.Mh, sm);
+          if (Vrow) {
+            VecIO<R, VEC>::store(Vrow, vp);
+            VecIO<R, VEC>::store(Vrow + a.Mh, vm);
+          }
+          continue;
+        }
+      }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         if (HES) heston_step<R, SCHEME>(sp[i], vp[i], z1[i], z2[i], hc);
@@ -128,11 +153,23 @@ __global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
   }
 }
 
+// Grid shape: one wave of (4 CTAs per SM) with the work split evenly across the CTAs, so every SM carries the
+// same number of threads (a plain ceil(units / 256) grid leaves some SMs with 4 CTAs and others with 3).
+static void path_grid(optmc_ctx* ctx, long long units, unsigned* grid, unsigned* block) {
+  const long long ctas = (long long)ctx->sm_count * 4;
+  long long tpc = (units + ctas - 1) / ctas;
+  if (tpc > 256) tpc = 256;  // several waves
+  if (tpc < 64) tpc = 64;
+  *block = (unsigned)tpc;
+  *grid = (unsigned)((units + tpc - 1) / tpc);
+}
+
 template <typename R, int SCHEME, int VEC> static int launch_t3(optmc_ctx* ctx, const PathArgs& a, bool extz) {
   const long long threads = (a.Mh + VEC - 1) / VEC;
-  const unsigned grid = (unsigned)((threads + 255) / 256);
-  if (extz) paths_kernel<R, SCHEME, VEC, true><<<grid, 256, 0, ctx->stream>>>(a);
-  else paths_kernel<R, SCHEME, VEC, false><<<grid, 256, 0, ctx->stream>>>(a);
+  unsigned grid, block;
+  path_grid(ctx, threads, &grid, &block);
+  if (extz) paths_kernel<R, SCHEME, VEC, true><<<grid, block, 0, ctx->stream>>>(a);
+  else paths_kernel<R, SCHEME, VEC, false><<<grid, block, 0, ctx->stream>>>(a);
   ctx->launches++;
   OPTMC_CUDA(cudaGetLastError());
   return OPTMC_OK;
