@@ -172,6 +172,27 @@ int optmc_lsm_finish(optmc_ctx* ctx, double* sums_dev);
  * host results out. */
 int optmc_price_american(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                          int32_t N, int32_t dtype, const optmc_lsm_params* lp, optmc_lsm_result* out);
+/* Batched American pricing: the S0 x maturity curve drivers (om3:697-713 compute_curve_for_S0, om3gpu:934-956
+ * compute_multiple_S0_gpu_batch, om2:336-457) and strike x maturity grids call price_american_option once per
+ * grid point; this entry point prices the whole list in a few launches.  Every option simulates its own
+ * M paths (as the reference does) with Philox stream rng->stream + opts[i].stream; mp supplies r and the
+ * model parameters (mp->S0 / mp->T are ignored).  Options are swept G at a time by one grouped persistent
+ * kernel: the SMs are split into G groups, each sweeping one option with no cross-group synchronisation. */
+typedef struct optmc_american_option {
+  double S0, K, T;
+  int32_t N;       /* exercise dates / time steps (may differ per option: om3:709) */
+  int32_t is_put;
+  uint64_t stream; /* added to rng->stream */
+} optmc_american_option;
+
+typedef struct optmc_price_result {
+  double price, stderr_;
+} optmc_price_result;
+
+int optmc_price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                               int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
+                               const optmc_american_option* opts, optmc_price_result* results);
+
 /* price_european_streaming / price_european_gpu / HestonPricer.price_european_option
  * (om3:382-437, om3gpu:605-653, hc:259-281): paths are generated and reduced in registers, nothing is
  * stored.  n_options options share mp/rng except K[i], T[i], is_put[i]; option i uses Philox stream

@@ -44,6 +44,15 @@ class LsmResult(C.Structure):
                 ("ex_count", C.POINTER(C.c_int64)), ("n_itm", C.POINTER(C.c_int64))]
 
 
+class AmericanOption(C.Structure):
+    _fields_ = [("S0", C.c_double), ("K", C.c_double), ("T", C.c_double), ("N", C.c_int32), ("is_put", C.c_int32),
+                ("stream", C.c_uint64)]
+
+
+class PriceResult(C.Structure):
+    _fields_ = [("price", C.c_double), ("stderr_", C.c_double)]
+
+
 class EuropeanResult(C.Structure):
     _fields_ = [("mean", C.c_double), ("stderr_", C.c_double), ("n_paths", C.c_int64)]
 
@@ -76,6 +85,8 @@ PROTOTYPES = {
     "optmc_lsm_finish": (C.c_int, [C.c_void_p, C.c_void_p]),
     "optmc_price_american": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
                                        _P(LsmParams), _P(LsmResult)]),
+    "optmc_price_american_batch": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
+                                             C.c_uint32, C.c_int32, _P(AmericanOption), _P(PriceResult)]),
     "optmc_price_european_batch": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32,
                                              C.c_int32, C.c_int32, _P(C.c_double), _P(C.c_double), _P(C.c_int32),
                                              _P(C.c_int32), _P(EuropeanResult)]),

@@ -203,7 +203,7 @@ class AdvancedOptionPricer:
                  nn_layers: int = 3, nn_dropout: float = 0.10,
                  # engine extensions (not in the reference)
                  lsm_regressor: str = "poly2", semantics: str = "reference", dtype: str = "f32", device: int = 0,
-                 gpu_reference_quirks: bool = False):
+                 gpu_reference_quirks: bool = False, batched: bool = True):
         self.K = K
         self.r = r
         self.sigma = sigma
@@ -224,6 +224,7 @@ class AdvancedOptionPricer:
         self.dtype = dtype
         self.device = device
         self.gpu_reference_quirks = gpu_reference_quirks
+        self.batched = batched
         self.last_result: Optional[E.SweepResult] = None
 
     # om3:461-472 model routing
@@ -313,9 +314,44 @@ class AdvancedOptionPricer:
             return self.price_american_with_control_variate(S0, T, num_simulations, num_time_steps)
         return self.price_american_enhanced_lsm(S0, T, num_simulations, num_time_steps)
 
+    def price_american_grid(self, S0, T, num_time_steps, num_simulations: int = 10000, K=None):
+        """Engine extension: price a whole grid (arrays S0 / T / steps / K broadcast against each other) with
+        optmc_price_american_batch -- what the reference does with one price_american_enhanced_lsm call per
+        grid point (om3:706-712).  The master generator advances exactly as in the per-point loop (om3:454-455);
+        point i draws from Philox stream = its child seed."""
+        S0a, Ta, Na, Ka = np.broadcast_arrays(np.asarray(S0, dtype=np.float64), np.asarray(T, dtype=np.float64),
+                                              np.asarray(num_time_steps, dtype=np.int64),
+                                              np.asarray(self.K if K is None else K, dtype=np.float64))
+        shape = S0a.shape
+        S0a, Ta, Na, Ka = (np.atleast_1d(a).ravel() for a in (S0a, Ta, Na, Ka))
+        if np.any(S0a <= 0) or np.any(Ka <= 0) or np.any(Ta <= 0):
+            raise ValueError("S0, K, T must be positive.")
+        if self.r < 0:
+            raise ValueError("r must be non-negative.")
+        if num_simulations <= 0 or np.any(Na <= 0):
+            raise ValueError("num_simulations and num_time_steps must be positive integers.")
+        seeds = []
+        for _ in range(S0a.size):
+            seeds.append(int(self.rng_manager.master_rng.integers(0, 2**31 - 1)))  # om3:454
+            self.rng_manager.get_child_seed()                                      # om3:455
+        M = num_simulations // 2 * 2
+        model = self._model(float(S0a[0]), float(Ta[0]))
+        price, se = _engine(self.device).price_american_batch(
+            model, M, S0a, Ka, Ta, Na, 1 if self.option_type == "put" else 0, self.dtype,
+            E.RngSpec(seed=self.rng_manager.master_seed), basis=self.lsm_regressor, semantics=self.semantics,
+            streams=seeds)
+        return price.reshape(shape), se.reshape(shape)
+
     def compute_curve_for_S0(self, S0: float, intervals_per_day: int, total_points: int, num_simulations: int,
                              plot_paths: bool) -> List[Dict[str, Any]]:
-        """om3:697-713."""
+        """om3:697-713.  Without the control variate the whole curve is one batched engine call."""
+        cv = self.use_control_variate and self.sigma is not None
+        eu = self.use_streaming and self.european_approximation
+        if self.batched and not cv and not eu and total_points > 0:
+            days = np.array([i / intervals_per_day for i in range(total_points, 0, -1)])
+            steps = np.maximum(10, np.minimum(130, np.ceil(days))).astype(np.int64)
+            prices, _ = self.price_american_grid(S0, days / 365, steps, num_simulations)
+            return [{"S0": S0, "Days to Expiry": float(d), "Option Value": float(p)} for d, p in zip(days, prices)]
         records = []
         for i in range(total_points, 0, -1):
             d = i / intervals_per_day

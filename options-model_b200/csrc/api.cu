@@ -237,7 +237,7 @@ int optmc_ctx_destroy(optmc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->slab); cudaFree(ctx->cf); cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->gram);
   cudaFree(ctx->d_betas); cudaFree(ctx->d_bnd); cudaFree(ctx->d_exc); cudaFree(ctx->d_nitm); cudaFree(ctx->d_valid);
-  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
+  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return OPTMC_OK;
@@ -382,6 +382,15 @@ int optmc_price_american(optmc_ctx* ctx, const optmc_model_params* mp, const opt
   if (rc) return rc;
   ctx->sw.n_launches += 1;  // the path kernel
   return out ? fetch_results(ctx, out) : OPTMC_OK;
+  OPTMC_TRY_END
+}
+
+int optmc_price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                               int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
+                               const optmc_american_option* opts, optmc_price_result* results) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return price_american_batch(ctx, mp, rng, M, dtype, basis, semantics, n_options, opts, results);
   OPTMC_TRY_END
 }
 

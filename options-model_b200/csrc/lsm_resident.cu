@@ -31,20 +31,20 @@ struct ResShape { int nt, ppt; };
 static const ResShape kShapes[] = {OPTMC_RES_SHAPES(X)};
 #undef X
 
-// Slice the M paths over at most one CTA per SM and pick the smallest compiled (threads, paths-per-thread)
-// shape that holds a slice.
-static bool plan_resident(optmc_ctx* ctx, const SweepDesc& sw, ResPlan* p, std::string* why) {
-  const size_t es = sw.dtype == OPTMC_F64 ? 8 : 4;
-  if ((uintptr_t)sw.S % 16 != 0 || (sw.ld * es) % 16 != 0) { *why = "slab not 16-byte aligned"; return false; }
-  if ((sw.M * es) % 16 != 0) { *why = "path count is not a multiple of 16 bytes (bulk copies move whole 16-byte units)"; return false; }
+// Slice the M paths of ONE option over at most `max_ctas` CTAs and pick the smallest compiled (threads,
+// paths-per-thread) shape that holds a slice.
+static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int max_ctas, ResPlan* p, std::string* why) {
+  const size_t es = dtype == OPTMC_F64 ? 8 : 4;
+  if ((M * es) % 16 != 0) { *why = "path count is not a multiple of 16 bytes (bulk copies move whole 16-byte units)"; return false; }
   if (ctx->cc < 90) { *why = "bulk async copy needs sm_90+"; return false; }
-  const int ncta_cap = ctx->sm_count < kMaxResidentCtas ? ctx->sm_count : kMaxResidentCtas;
-  long long ncta = (sw.M + 511) / 512;  // at least one path per thread before adding CTAs
+  int ncta_cap = ctx->sm_count < kMaxResidentCtas ? ctx->sm_count : kMaxResidentCtas;
+  if (max_ctas < ncta_cap) ncta_cap = max_ctas;
+  long long ncta = (M + 511) / 512;  // at least one path per thread before adding CTAs
   if (ncta > ncta_cap) ncta = ncta_cap;
   if (ncta < 1) ncta = 1;
-  long long chunk = (sw.M + ncta - 1) / ncta;
+  long long chunk = (M + ncta - 1) / ncta;
   chunk = (chunk + 3) / 4 * 4;
-  ncta = (sw.M + chunk - 1) / chunk;
+  ncta = (M + chunk - 1) / chunk;
   const ResShape* shape = nullptr;
   for (const ResShape& c : kShapes)
     if ((long long)c.nt * c.ppt >= chunk) { shape = &c; break; }
@@ -55,18 +55,48 @@ static bool plan_resident(optmc_ctx* ctx, const SweepDesc& sw, ResPlan* p, std::
   int nstage = 3;
   if (stride * 3 > avail) nstage = 2;
   if (stride * 2 > avail) { *why = "slice exceeds shared memory"; return false; }
-  p->ncta = (int)ncta; p->ppt = shape->ppt; p->nt = shape->nt; p->nstage = nstage; p->chunk = chunk;
+  p->ncta = (int)ncta; p->ngroups = 1; p->ppt = shape->ppt; p->nt = shape->nt; p->nstage = nstage; p->chunk = chunk;
   p->stage_stride = (unsigned int)stride; p->smem = stride * nstage;
   // sticky mask => only a small fraction of the paths is in the regression at any date: vote-skip passes.
   // Tuning aid: OPTMC_RES_SPARSE=0|1 overrides.
-  p->sparse = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) != 0;
+  p->sparse = sticky;
   if (const char* e = getenv("OPTMC_RES_SPARSE")) p->sparse = atoi(e) != 0;
   return true;
+}
+
+static bool plan_resident(optmc_ctx* ctx, const SweepDesc& sw, ResPlan* p, std::string* why) {
+  const size_t es = sw.dtype == OPTMC_F64 ? 8 : 4;
+  if ((uintptr_t)sw.S % 16 != 0 || (sw.ld * es) % 16 != 0) { *why = "slab not 16-byte aligned"; return false; }
+  return plan_shape(ctx, sw.M, sw.dtype, (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) != 0, ctx->sm_count, p, why);
 }
 
 bool resident_eligible(optmc_ctx* ctx, const SweepDesc& sw, std::string* why) {
   ResPlan p;
   return plan_resident(ctx, sw, &p, why);
+}
+
+// Option-level constants of one group (see Store<> in lsm_resident_kernel.cuh).
+static void fill_group(ResGroup* g, const void* S, long long ld, long long M, long long chunk, int N, int dtype,
+                       double K, int is_put, double disc, double final_scale) {
+  g->S = S; g->ld = ld; g->M = M; g->chunk = chunk; g->N = N; g->is_put = is_put;
+  g->K = K; g->invK = 1.0 / K; g->disc = disc; g->inv_disc = 1.0 / disc; g->final_scale = final_scale;
+  const double sg = is_put ? -1.0 : 1.0;
+  double Kcmp = K, Kh = K, Kl = 0.0;
+  if (dtype == OPTMC_F32) {
+    // float threshold with (s < K) <=> (s < Kcmp) for every float s (puts); mirrored for calls
+    float kf = (float)K;
+    Kh = (double)kf;
+    Kl = (double)(float)(K - Kh);
+    if (is_put) { if ((double)kf < K) kf = nextafterf(kf, INFINITY); }
+    else { if ((double)kf > K) kf = nextafterf(kf, -INFINITY); }
+    Kcmp = (double)kf;
+  }
+  g->sgn = sg; g->kk = sg * Kcmp; g->c1 = -sg * Kh; g->c2 = -sg * Kl;
+}
+
+static int launch_resident(optmc_ctx* ctx, const ResPlan& p, ResArgs& a, int dtype, int deg) {
+  if (dtype == OPTMC_F64) return deg == 2 ? launch_resident_f64_deg2(ctx, p, a) : launch_resident_f64_deg3(ctx, p, a);
+  return deg == 2 ? launch_resident_f32_deg2(ctx, p, a) : launch_resident_f32_deg3(ctx, p, a);
 }
 
 int sweep_resident(optmc_ctx* ctx) {
@@ -77,26 +107,12 @@ int sweep_resident(optmc_ctx* ctx) {
   int rc = sweep_reset_stats(ctx);  // also zeroes the exchange accumulators and the overflow flag
   if (rc) return rc;
   ResArgs a{};
-  a.S = sw.S; a.ld = sw.ld; a.M = sw.M; a.chunk = p.chunk; a.N = sw.N; a.nstage = p.nstage;
-  a.stage_stride = p.stage_stride;
-  a.K = sw.lp.K; a.invK = 1.0 / sw.lp.K; a.disc = sw.disc; a.inv_disc = 1.0 / sw.disc; a.final_scale = sw.final_scale;
-  {  // pass constants, exact in the storage type (see Store<>)
-    const double sg = sw.lp.is_put ? -1.0 : 1.0;
-    double Kcmp = sw.lp.K, Kh = sw.lp.K, Kl = 0.0;
-    if (sw.dtype == OPTMC_F32) {
-      // float threshold with (s < K) <=> (s < Kcmp) for every float s (puts); mirrored for calls
-      float kf = (float)sw.lp.K;
-      Kh = (double)kf;
-      Kl = (double)(float)(sw.lp.K - Kh);
-      if (sw.lp.is_put) { if ((double)kf < sw.lp.K) kf = nextafterf(kf, INFINITY); }
-      else { if ((double)kf > sw.lp.K) kf = nextafterf(kf, -INFINITY); }
-      Kcmp = (double)kf;
-    }
-    a.sgn = sg; a.kk = sg * Kcmp; a.c1 = -sg * Kh; a.c2 = -sg * Kl;
-  }
-  a.is_put = sw.lp.is_put; a.sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) ? 1 : 0;
-  a.xw = reinterpret_cast<unsigned long long*>(ctx->xchg); a.flags = ctx->d_flags;
-  a.betas = ctx->d_betas; a.bnd = ctx->d_bnd; a.exc = ctx->d_exc; a.nitm = ctx->d_nitm; a.final_out = ctx->d_final;
+  fill_group(&a.one, sw.S, sw.ld, sw.M, p.chunk, sw.N, sw.dtype, sw.lp.K, sw.lp.is_put, sw.disc, sw.final_scale);
+  a.groups = nullptr; a.cpg = p.ncta; a.nstage = p.nstage; a.stage_stride = p.stage_stride;
+  a.sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) ? 1 : 0;
+  a.one.xw = reinterpret_cast<unsigned long long*>(ctx->xchg); a.one.flags = ctx->d_flags;
+  a.one.betas = ctx->d_betas; a.one.bnd = ctx->d_bnd; a.one.exc = ctx->d_exc; a.one.nitm = ctx->d_nitm;
+  a.one.final_out = ctx->d_final;
   // Debug aid: OPTMC_TRACE=<file> dumps per-date phase clocks (SM cycles) of the first and last CTA.
   const char* trace_path = getenv("OPTMC_TRACE");
   long long* d_trace = nullptr;
@@ -106,8 +122,7 @@ int sweep_resident(optmc_ctx* ctx) {
     OPTMC_CUDA(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), ctx->stream));
     a.trace = d_trace;
   }
-  if (sw.dtype == OPTMC_F64) rc = sw.deg == 2 ? launch_resident_f64_deg2(ctx, p, a) : launch_resident_f64_deg3(ctx, p, a);
-  else rc = sw.deg == 2 ? launch_resident_f32_deg2(ctx, p, a) : launch_resident_f32_deg3(ctx, p, a);
+  rc = launch_resident(ctx, p, a, sw.dtype, sw.deg);
   if (d_trace) {
     std::vector<long long> h(trace_n);
     cudaError_t e = cudaMemcpyAsync(h.data(), d_trace, trace_n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
@@ -128,6 +143,130 @@ int sweep_resident(optmc_ctx* ctx) {
     }
   }
   return rc;
+}
+
+// ---- batched pricing: G options per grouped launch ---------------------------------------------------------
+__global__ void batch_reset_kernel(unsigned long long* words, int n_words, double* finals, int n_finals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int k = i; k < n_words; k += gridDim.x * blockDim.x) words[k] = 0ull;
+  for (int k = i; k < n_finals; k += gridDim.x * blockDim.x) finals[k] = 0.0;
+}
+
+int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                         int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
+                         const optmc_american_option* opts, optmc_price_result* results) {
+  if (!mp || !rng || !opts || !results) { set_error("null argument"); return OPTMC_EINVAL; }
+  if (n_options <= 0) { set_error("n_options must be positive"); return OPTMC_EINVAL; }
+  if (M <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
+  if (dtype != OPTMC_F32 && dtype != OPTMC_F64) { set_error("bad dtype"); return OPTMC_EINVAL; }
+  if (basis != OPTMC_BASIS_POLY2 && basis != OPTMC_BASIS_POLY3) { set_error("basis must be POLY2 or POLY3"); return OPTMC_EINVAL; }
+  if (mp->r < 0) { set_error("r must be non-negative."); return OPTMC_EINVAL; }
+  if (rng->z1_dev) { set_error("batched pricing generates its own normals"); return OPTMC_EUNSUPPORTED; }
+  int n_max = 0;
+  for (int i = 0; i < n_options; ++i) {
+    if (!(opts[i].S0 > 0) || !(opts[i].K > 0) || !(opts[i].T > 0)) { set_error("S0, K, T must be positive."); return OPTMC_EINVAL; }
+    if (opts[i].N <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
+    if (opts[i].N > n_max) n_max = opts[i].N;
+  }
+  const size_t es = dtype == OPTMC_F64 ? 8 : 4;
+  const int deg = basis == OPTMC_BASIS_POLY3 ? 3 : 2;
+  const bool sticky = (semantics & OPTMC_SEM_STICKY_MASK) != 0;
+  const int64_t ld = (M + 63) / 64 * 64;
+
+  // CTAs per option: the fewest that hold a slice on chip (throughput falls with more: DESIGN.md 4), but use the
+  // whole machine when there are fewer options than groups.
+  ResPlan p;
+  std::string why;
+  int cpg = 0;
+  for (int c = 1; c <= ctx->sm_count; ++c) {
+    if (plan_shape(ctx, M, dtype, sticky, c, &p, &why) && p.ncta <= c) { cpg = c; break; }
+  }
+  if (cpg == 0) {  // does not fit on chip: one option at a time through the single-option entry (split sweep)
+    for (int i = 0; i < n_options; ++i) {
+      optmc_model_params m = *mp; m.S0 = opts[i].S0; m.T = opts[i].T;
+      optmc_rng_params r = *rng; r.stream = rng->stream + opts[i].stream;
+      optmc_lsm_params lp{opts[i].K, mp->r, opts[i].T, opts[i].is_put, basis, semantics, OPTMC_SWEEP_AUTO};
+      optmc_lsm_result res{};
+      int rc = optmc_price_american(ctx, &m, &r, M, opts[i].N, dtype, &lp, &res);
+      if (rc) return rc;
+      results[i].price = res.price; results[i].stderr_ = res.stderr_;
+    }
+    return OPTMC_OK;
+  }
+  int G = ctx->sm_count / cpg;
+  if (G > n_options) G = n_options;
+  {  // spread the SMs over the groups actually used
+    const int c2 = ctx->sm_count / G;
+    ResPlan p2;
+    if (c2 > cpg && plan_shape(ctx, M, dtype, sticky, c2, &p2, &why)) p = p2;
+  }
+  cpg = p.ncta;
+  p.ngroups = G;
+
+  // workspaces: G slabs + per-wave descriptors / accumulators / results in one device block
+  const size_t slab_stride = ((size_t)(n_max + 1) * ld * es + 255) / 256 * 256;
+  int rc = ensure_bytes(&ctx->slab, &ctx->slab_bytes, slab_stride * G);
+  if (rc) return rc;
+  const size_t off_groups = 0;
+  const size_t off_paths = off_groups + ((sizeof(ResGroup) * G + 255) / 256 * 256);
+  const size_t off_words = off_paths + ((path_args_bytes() * G + 255) / 256 * 256);
+  const size_t n_words = (size_t)G * 2 * kXchgWords * kXchgStride + (size_t)G * 2;  // accumulators + flags (as u64 pairs)
+  const size_t off_final = off_words + ((n_words * 8 + 255) / 256 * 256);
+  const size_t total = off_final + (size_t)G * 4 * sizeof(double);
+  rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, total);
+  if (rc) return rc;
+  char* dev = static_cast<char*>(ctx->batch_dev);
+  ResGroup* d_groups = reinterpret_cast<ResGroup*>(dev + off_groups);
+  unsigned long long* d_words = reinterpret_cast<unsigned long long*>(dev + off_words);
+  int* d_flags = reinterpret_cast<int*>(d_words + (size_t)G * 2 * kXchgWords * kXchgStride);
+  double* d_final = reinterpret_cast<double*>(dev + off_final);
+
+  std::vector<ResGroup> hg(G);
+  std::vector<char> hp(path_args_bytes() * G);
+  std::vector<double> hfin((size_t)G * 4);
+  std::vector<int> hflags((size_t)G * 4);
+  for (int w0 = 0; w0 < n_options; w0 += G) {
+    const int g_now = n_options - w0 < G ? n_options - w0 : G;
+    for (int g = 0; g < g_now; ++g) {
+      const optmc_american_option& o = opts[w0 + g];
+      const double disc = exp(-mp->r * (o.T / o.N));
+      fill_group(&hg[g], static_cast<char*>(ctx->slab) + (size_t)g * slab_stride, ld, M, p.chunk, o.N, dtype, o.K, o.is_put,
+                 disc, (semantics & OPTMC_SEM_REF_DISCOUNT) ? 1.0 : disc);
+      hg[g].xw = d_words + (size_t)g * 2 * kXchgWords * kXchgStride;
+      hg[g].flags = d_flags + (size_t)g * 4;
+      hg[g].betas = nullptr; hg[g].bnd = nullptr; hg[g].exc = nullptr; hg[g].nitm = nullptr;
+      hg[g].final_out = d_final + (size_t)g * 4;
+    }
+    OPTMC_CUDA(cudaMemcpyAsync(d_groups, hg.data(), sizeof(ResGroup) * g_now, cudaMemcpyHostToDevice, ctx->stream));
+    batch_reset_kernel<<<8, 256, 0, ctx->stream>>>(d_words, (int)n_words, d_final, G * 4);
+    ctx->launches++;
+    rc = launch_paths_batch(ctx, mp, rng, M, dtype, g_now, opts + w0, ctx->slab, slab_stride, ld, dev + off_paths, hp.data());
+    if (rc) return rc;
+    ResPlan pw = p;
+    pw.ngroups = g_now;
+    ResArgs a{};
+    a.groups = d_groups; a.cpg = cpg; a.nstage = p.nstage; a.stage_stride = p.stage_stride; a.sticky = sticky ? 1 : 0;
+    rc = launch_resident(ctx, pw, a, dtype, deg);
+    if (rc) return rc;
+    OPTMC_CUDA(cudaMemcpyAsync(hfin.data(), d_final, sizeof(double) * 4 * g_now, cudaMemcpyDeviceToHost, ctx->stream));
+    OPTMC_CUDA(cudaMemcpyAsync(hflags.data(), d_flags, sizeof(int) * 4 * g_now, cudaMemcpyDeviceToHost, ctx->stream));
+    OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int g = 0; g < g_now; ++g) {
+      results[w0 + g].price = hfin[(size_t)g * 4];
+      results[w0 + g].stderr_ = hfin[(size_t)g * 4 + 1];
+      if (hflags[(size_t)g * 4]) {  // fixed-point exchange overflow: redo this option with the split kernels
+        const optmc_american_option& o = opts[w0 + g];
+        optmc_model_params m = *mp; m.S0 = o.S0; m.T = o.T;
+        optmc_rng_params r = *rng; r.stream = rng->stream + o.stream;
+        optmc_lsm_params lp{o.K, mp->r, o.T, o.is_put, basis, semantics, OPTMC_SWEEP_SPLIT};
+        optmc_lsm_result res{};
+        rc = optmc_price_american(ctx, &m, &r, M, o.N, dtype, &lp, &res);
+        if (rc) return rc;
+        results[w0 + g].price = res.price; results[w0 + g].stderr_ = res.stderr_;
+      }
+    }
+  }
+  return OPTMC_OK;
 }
 
 }  // namespace optmc

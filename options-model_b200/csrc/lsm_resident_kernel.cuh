@@ -9,21 +9,31 @@
 
 namespace optmc {
 
-struct ResArgs {
+// One option of a (possibly grouped) sweep.  A launch sweeps G independent options at once: CTAs
+// [g * cpg, (g + 1) * cpg) form group g, which owns its slab, its exchange accumulators and its outputs;
+// groups never synchronise with each other.  All groups of a launch share the storage type, the basis, the
+// semantics, the path count and hence the CTA shape; the number of exercise dates may differ.
+struct ResGroup {
   const void* S;
   long long ld, M, chunk;
-  int N, nstage;
-  unsigned int stage_stride;  // bytes between stages in shared memory
+  int N, is_put;
   double K, invK, disc, inv_disc, final_scale;
   double sgn, kk, c1, c2;     // storage-precision pass constants (see Store<>); exact in the storage type
-  int is_put, sticky;
   unsigned long long* xw;     // exchange accumulators [2][kXchgWords][kXchgStride]
   int* flags;                 // [0] = exchange overflow
-  double* betas;              // [(N+1)][kMaxBeta]
-  unsigned long long* bnd;    // [(N+1)]
-  unsigned long long* exc;    // [(N+1)]
-  long long* nitm;            // [(N+1)]
+  double* betas;              // [(N+1)][kMaxBeta] or NULL
+  unsigned long long* bnd;    // [(N+1)] or NULL
+  unsigned long long* exc;    // [(N+1)] or NULL
+  long long* nitm;            // [(N+1)] or NULL
   double* final_out;          // [4]
+};
+
+struct ResArgs {
+  ResGroup one;               // the group of a single-option launch (groups == NULL)
+  const ResGroup* groups;     // device array [G] for grouped launches
+  int cpg;                    // CTAs per group
+  int nstage, sticky;
+  unsigned int stage_stride;  // bytes between stages in shared memory
   long long* trace;           // optional [2][(N+1)][8] phase clocks of the first and last CTA (OPTMC_TRACE)
 };
 
@@ -83,6 +93,10 @@ template <int QN>
 __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long* xw, int par, int ncta,
                                                  unsigned long long& prev, int* flags, int* spins_out) {
   const int lane = threadIdx.x & 31;
+  if (ncta == 1) {  // the option fits one CTA: its totals are the grid totals
+    if (spins_out) *spins_out = 0;
+    return __shfl_sync(0xffffffffu, mine, (2 * lane) & 31);
+  }
   unsigned long long sum = 0ull;
   int spins = 0;
   if (lane < 2 * QN) {
@@ -263,7 +277,7 @@ __device__ __forceinline__ void sparse_pass(R (&cf)[PPT], const R* __restrict__ 
 }
 
 template <typename R, int DEG, int PPT, int NT, bool SPARSE>
-__global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
+__global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
   constexpr int Q = Moments<DEG>::Q;
   constexpr int QP = Pow2<Q>::v;
   constexpr int NW = NT / 32;
@@ -277,25 +291,27 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
   __shared__ unsigned int s_cnt[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int grp = blockIdx.x / ga.cpg;
+  const ResGroup a = ga.groups ? ga.groups[grp] : ga.one;
+  const int cta = blockIdx.x - grp * ga.cpg, ncta = ga.cpg;
   const long long base = (long long)cta * a.chunk;
   const long long rem = a.M - base;
   const int n_local = (int)(rem < a.chunk ? rem : a.chunk);
   const unsigned int bytes = (unsigned int)((size_t)n_local * sizeof(R));  // multiple of 16 (planner)
   const bool is_put = a.is_put != 0;
-  const bool sticky = a.sticky != 0;
+  const bool sticky = ga.sticky != 0;
   const R sgn = (R)a.sgn, kk = (R)a.kk, c1 = (R)a.c1, c2 = (R)a.c2;
   const unsigned int flag = sticky ? 0x80000000u : 0u;
-  const int N = a.N, nstage = a.nstage;
+  const int N = a.N, nstage = ga.nstage;
   const R* Sbase = static_cast<const R*>(a.S) + base;
 
   // Stage ring: date t lives in slot (N - t) % nstage; the slots of the dates in use are tracked
   // incrementally (no integer division on the per-date path).
-  auto slot_ptr = [&](int slot) -> R* { return reinterpret_cast<R*>(smem_raw + (size_t)slot * a.stage_stride); };
+  auto slot_ptr = [&](int slot) -> R* { return reinterpret_cast<R*>(smem_raw + (size_t)slot * ga.stage_stride); };
   auto issue_load = [&](int t, int slot) {  // one thread
     uint64_t* bar = &mbar[slot];
     mbar_arrive_expect_tx(bar, bytes);
-    bulk_load_1d(smem_raw + (size_t)slot * a.stage_stride, Sbase + (size_t)t * a.ld, bytes, bar);
+    bulk_load_1d(smem_raw + (size_t)slot * ga.stage_stride, Sbase + (size_t)t * a.ld, bytes, bar);
   };
 
   if (tid == 0) {
@@ -325,8 +341,8 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
     for (int i = 0; i < pw; ++i) qscale *= a.invK;
   }
   unsigned long long prev0 = 0ull, prev1 = 0ull;  // warp 0: accumulator baselines of the two parities
-  long long* const tr_base = (a.trace && tid == 0 && (cta == 0 || cta == ncta - 1))
-                                 ? a.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * 8 : nullptr;
+  long long* const tr_base = (ga.trace && grp == 0 && tid == 0 && (cta == 0 || cta == ncta - 1))
+                                 ? ga.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * 8 : nullptr;
 
   // ---- date N: cash-flows = payoff(S[N]) (om3:616) ----
   R cf[PPT];
@@ -406,8 +422,10 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
     OPTMC_TRACE_AT(2);
     if (tid == 32) {  // bookkeeping off the critical path (warp 1)
       if (s_cnt[0]) {  // exercise statistics of date t
-        atomicAdd(a.exc + t, (unsigned long long)s_cnt[0]);
-        if (is_put) atomicMax(a.bnd + t, s_bnd[0]); else atomicMin(a.bnd + t, s_bnd[0]);
+        if (a.exc) atomicAdd(a.exc + t, (unsigned long long)s_cnt[0]);
+        if (a.bnd) {
+          if (is_put) atomicMax(a.bnd + t, s_bnd[0]); else atomicMin(a.bnd + t, s_bnd[0]);
+        }
         s_cnt[0] = 0u;
         s_bnd[0] = bnd_none(a.is_put);
       }
@@ -438,7 +456,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
             sc *= a.invK;
           }
         }
-        if (cta == 0) {
+        if (cta == 0 && a.betas) {
 #pragma unroll
           for (int i = 0; i <= DEG; ++i) a.betas[(size_t)(t - 1) * kMaxBeta + i] = ok ? beta[i] : nan("");
           a.nitm[t - 1] = (long long)(tot[0] + 0.5);
@@ -461,8 +479,10 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
   }
   const double mine = block_totals<2, NW>(fin, s_red);
   if (tid == 32 && s_cnt[0]) {  // statistics of date 1 (its update pass is behind the barrier above)
-    atomicAdd(a.exc + 1, (unsigned long long)s_cnt[0]);
-    if (is_put) atomicMax(a.bnd + 1, s_bnd[0]); else atomicMin(a.bnd + 1, s_bnd[0]);
+    if (a.exc) atomicAdd(a.exc + 1, (unsigned long long)s_cnt[0]);
+    if (a.bnd) {
+      if (is_put) atomicMax(a.bnd + 1, s_bnd[0]); else atomicMin(a.bnd + 1, s_bnd[0]);
+    }
   }
   if (warp == 0) {
     unsigned long long pv = (seq & 1) ? prev1 : prev0;
@@ -485,7 +505,9 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs a) {
 
 // ---- launch table (one translation unit per storage precision) -------------------------------------------
 struct ResPlan {
-  int ncta = 0, ppt = 0, nstage = 0, nt = 0;
+  int ncta = 0;     // CTAs per option (group)
+  int ngroups = 1;  // options swept by one launch
+  int ppt = 0, nstage = 0, nt = 0;
   bool sparse = false;  // vote-skip passes (sticky semantics: few live paths per date)
   long long chunk = 0;
   unsigned int stage_stride = 0;
@@ -497,7 +519,7 @@ int launch_resident_t(optmc_ctx* ctx, const ResPlan& p, ResArgs& a) {
   auto kern = lsm_resident_kernel<R, DEG, PPT, NT, SPARSE>;
   OPTMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
   void* args[] = {(void*)&a};
-  OPTMC_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(p.ncta), dim3(NT), args, p.smem, ctx->stream));
+  OPTMC_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(p.ncta * p.ngroups), dim3(NT), args, p.smem, ctx->stream));
   ctx->launches++; ctx->sw.n_launches++;
   return OPTMC_OK;
 }

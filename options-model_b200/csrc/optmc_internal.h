@@ -74,6 +74,7 @@ struct optmc_ctx {
   double* d_final = nullptr;            // [4] price, stderr, sum, sumsq
   void* xchg = nullptr;                 // exchange accumulators of the persistent sweep, xchg_bytes()
   int* d_flags = nullptr;               // [4]: [0] = fixed-point exchange overflow
+  void* batch_dev = nullptr; size_t batch_dev_cap = 0;  // per-wave descriptors / accumulators / results
   double* eu_out = nullptr; size_t eu_out_cap = 0;  // [n_options][3]
   double* eu_par = nullptr; size_t eu_par_cap = 0;  // [n_options][4] K, T, is_put, pad
   unsigned int* eu_tickets = nullptr; size_t eu_tickets_cap = 0;
@@ -89,6 +90,10 @@ int ensure_per_date(optmc_ctx* ctx, int N);
 // paths.cu
 int launch_paths(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M, int32_t N,
                  int32_t dtype, void* S, void* V, int64_t ld);
+size_t path_args_bytes();
+int launch_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                       int32_t dtype, int G, const optmc_american_option* opts, void* slab, size_t slab_stride_bytes,
+                       int64_t ld, void* d_args, void* h_args);
 int launch_philox_normals(optmc_ctx* ctx, const optmc_rng_params* rng, int32_t model, int64_t M, int32_t N,
                           int32_t which, int32_t dtype, void* Z);
 int launch_philox_kat(optmc_ctx* ctx, int n, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
@@ -104,6 +109,10 @@ int sweep_finalize_price(optmc_ctx* ctx, const double* sums);       // split: d_
 int sweep_reset_stats(optmc_ctx* ctx);                              // NaN/none-initialise the per-date outputs
 bool resident_eligible(optmc_ctx* ctx, const SweepDesc& sw, std::string* why);
 int sweep_resident(optmc_ctx* ctx);                                 // one cooperative launch, all dates
+// grouped persistent sweep of a batch (lsm_resident.cu)
+int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                         int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
+                         const optmc_american_option* opts, optmc_price_result* results);
 
 // european.cu
 int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,

@@ -50,7 +50,7 @@ template <> struct FastPair<float, OPTMC_SCHEME_HESTON_REF_ABSORB> { static cons
 template <> struct FastPair<float, OPTMC_SCHEME_HESTON_FULL_TRUNC> { static constexpr bool value = true; };
 
 template <typename R, int SCHEME, int VEC, bool EXTZ>
-__global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
+__device__ __forceinline__ void paths_body(const PathArgs& a) {
   constexpr bool HES = (SCHEME >= OPTMC_SCHEME_HESTON_REF_ABSORB);
   constexpr bool LOGSPACE = (SCHEME == OPTMC_SCHEME_GBM_LOGSPACE);
   constexpr bool FAST = FastPair<R, SCHEME>::value;  // fp32 Heston: both partners of a pair in one fused step
@@ -151,6 +151,18 @@ __global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
       }
     }
   }
+}
+
+template <typename R, int SCHEME, int VEC, bool EXTZ>
+__global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
+  paths_body<R, SCHEME, VEC, EXTZ>(a);
+}
+
+// Batched form: blockIdx.y selects the option (its own slab, S0, dt, step count and Philox stream).
+template <typename R, int SCHEME, int VEC>
+__global__ void __launch_bounds__(256) paths_batch_kernel(const PathArgs* __restrict__ args) {
+  const PathArgs a = args[blockIdx.y];
+  paths_body<R, SCHEME, VEC, false>(a);
 }
 
 // Grid shape: one wave of (4 CTAs per SM) with the work split evenly across the CTAs, so every SM carries the
@@ -315,6 +327,62 @@ int launch_features(optmc_ctx* ctx, const void* S, int64_t n, int32_t dtype, dou
   else
     features_kernel<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(S), n, (float)K, (float)tau_sqrt,
                                                           static_cast<float*>(F));
+  ctx->launches++;
+  OPTMC_CUDA(cudaGetLastError());
+  return OPTMC_OK;
+}
+
+
+// ---- batched generation: G options, one slab each (optmc_price_american_batch) ---------------------------
+template <typename R, int VEC> static void launch_batch_scheme(int scheme, dim3 grid, unsigned block, cudaStream_t st,
+                                                               const PathArgs* d) {
+  switch (scheme) {
+    case OPTMC_SCHEME_GBM_LOG_EULER: paths_batch_kernel<R, OPTMC_SCHEME_GBM_LOG_EULER, VEC><<<grid, block, 0, st>>>(d); break;
+    case OPTMC_SCHEME_GBM_LOGSPACE: paths_batch_kernel<R, OPTMC_SCHEME_GBM_LOGSPACE, VEC><<<grid, block, 0, st>>>(d); break;
+    case OPTMC_SCHEME_HESTON_REF_ABSORB: paths_batch_kernel<R, OPTMC_SCHEME_HESTON_REF_ABSORB, VEC><<<grid, block, 0, st>>>(d); break;
+    case OPTMC_SCHEME_HESTON_FULL_TRUNC: paths_batch_kernel<R, OPTMC_SCHEME_HESTON_FULL_TRUNC, VEC><<<grid, block, 0, st>>>(d); break;
+    default: paths_batch_kernel<R, OPTMC_SCHEME_HESTON_REF_CALIB, VEC><<<grid, block, 0, st>>>(d); break;
+  }
+}
+
+size_t path_args_bytes() { return sizeof(PathArgs); }
+
+int launch_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                       int32_t dtype, int G, const optmc_american_option* opts, void* slab, size_t slab_stride_bytes,
+                       int64_t ld, void* d_args, void* h_args) {
+  PathArgs* h = static_cast<PathArgs*>(h_args);
+  for (int g = 0; g < G; ++g) {
+    optmc_model_params m = *mp;
+    m.S0 = opts[g].S0; m.T = opts[g].T;
+    optmc_rng_params r = *rng;
+    r.stream = rng->stream + opts[g].stream;
+    r.z1_dev = nullptr; r.z2_dev = nullptr;
+    bool extz = false;
+    int rc = fill_path_args(&m, &r, M, opts[g].N, &h[g], &extz);
+    if (rc) return rc;
+    h[g].S = static_cast<char*>(slab) + (size_t)g * slab_stride_bytes;
+    h[g].V = nullptr;
+    h[g].ld = ld;
+  }
+  OPTMC_CUDA(cudaMemcpyAsync(d_args, h, sizeof(PathArgs) * G, cudaMemcpyHostToDevice, ctx->stream));
+  const long long Mh = h[0].Mh;
+  const bool vec4 = (Mh % 4 == 0) && (ld % 4 == 0) && ((uintptr_t)slab % 16 == 0) && (slab_stride_bytes % 16 == 0);
+  const long long units = vec4 ? Mh / 4 : Mh;
+  // G options share the machine: split each option's work over ~ (4 CTAs per SM) / G blocks
+  long long per_opt = ((long long)ctx->sm_count * 4 + G - 1) / G;
+  if (per_opt < 1) per_opt = 1;
+  long long tpc = (units + per_opt - 1) / per_opt;
+  if (tpc > 256) tpc = 256;
+  if (tpc < 64) tpc = 64;
+  dim3 grid((unsigned)((units + tpc - 1) / tpc), (unsigned)G);
+  const PathArgs* d = static_cast<const PathArgs*>(d_args);
+  if (dtype == OPTMC_F64) {
+    if (vec4) launch_batch_scheme<double, 4>(mp->scheme, grid, (unsigned)tpc, ctx->stream, d);
+    else launch_batch_scheme<double, 1>(mp->scheme, grid, (unsigned)tpc, ctx->stream, d);
+  } else {
+    if (vec4) launch_batch_scheme<float, 4>(mp->scheme, grid, (unsigned)tpc, ctx->stream, d);
+    else launch_batch_scheme<float, 1>(mp->scheme, grid, (unsigned)tpc, ctx->stream, d);
+  }
   ctx->launches++;
   OPTMC_CUDA(cudaGetLastError());
   return OPTMC_OK;

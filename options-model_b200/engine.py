@@ -282,6 +282,29 @@ class Engine:
                                               C.byref(lp), C.byref(res)))
         return self._to_result(res, keep)
 
+    def price_american_batch(self, model: ModelSpec, M: int, S0, K, T, N, is_put, dtype="f32",
+                             rng: Optional[RngSpec] = None, basis="poly2", semantics="reference", streams=None):
+        """Grid of American options in a few grouped launches (om3:697-713 / om3gpu:934-956 curve drivers,
+        BASELINE config 4).  S0, K, T, N, is_put: scalars or arrays of length n.  -> (price[n], stderr[n])."""
+        rng = rng or RngSpec()
+        arrs = np.broadcast_arrays(np.asarray(S0, dtype=np.float64), np.asarray(K, dtype=np.float64),
+                                   np.asarray(T, dtype=np.float64), np.asarray(N, dtype=np.int64),
+                                   np.asarray(is_put, dtype=np.int64))
+        S0a, Ka, Ta, Na, Pa = (np.atleast_1d(a).ravel() for a in arrs)
+        n = S0a.size
+        sid = np.arange(n, dtype=np.uint64) if streams is None else np.asarray(streams, dtype=np.uint64).ravel()
+        assert sid.size == n
+        opts = (L.AmericanOption * n)()
+        for i in range(n):
+            opts[i] = L.AmericanOption(float(S0a[i]), float(Ka[i]), float(Ta[i]), int(Na[i]), int(Pa[i]), int(sid[i]))
+        out = (L.PriceResult * n)()
+        lp = self._lsm_params(1.0, model.r, 1.0, "put", basis, semantics, "auto")
+        mp, rp = model.c(), rng.c()
+        self._sync_stream()
+        L.check(self.lib.optmc_price_american_batch(self._h, C.byref(mp), C.byref(rp), int(M), _dtype_code(dtype),
+                                                    int(lp.basis), int(lp.semantics), n, opts, out))
+        return np.array([o.price for o in out]), np.array([o.stderr_ for o in out])
+
     def price_european_batch(self, model: ModelSpec, M: int, N: int, K, T, is_put, dtype="f32",
                              rng: Optional[RngSpec] = None, stream_id=None):
         """Fused no-store European pricing of n options (om3:382-437, hc:259-281).  -> (mean[n], stderr[n])."""

@@ -451,3 +451,79 @@ def test_config2_full_size_properties(eng, mods):
     assert abs(eu - 5.3234) < 0.05 and abs(a.price - 5.83) < 0.06
     tb = eng.lsm(S, K, 0.05, 1.0, "put", semantics="textbook")
     assert eu < tb.price < a.price  # look-ahead bias of the sticky mask (App. A, Q1)
+
+
+# ------------------------------------------------------------------------------------------------------
+# batched pricing (grouped persistent sweep)
+# ------------------------------------------------------------------------------------------------------
+def _oracle_price_philox(eng, mods, model_fn, S0, K, T, N, M, ot, seed, stream, dtype="f64", semantics="reference"):
+    """Oracle sweep on the kernel's own Philox normals for one option."""
+    L, E, orc = mods
+    rng = E.RngSpec(seed=seed, stream=stream)
+    z1 = eng.philox_normals(L.MODEL_HESTON, M, N, 0, dtype, rng).double().cpu().numpy()
+    z2 = eng.philox_normals(L.MODEL_HESTON, M, N, 1, dtype, rng).double().cpu().numpy()
+    S = orc.heston_paths_antithetic(S0, 0.05, T, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, z1, z2)
+    return orc.lsm_sweep(S, K, 0.05, T, ot, semantics=semantics)
+
+
+@pytest.mark.parametrize("M", [4096, 40_000])
+def test_batch_matches_oracle_and_single(eng, mods, M):
+    """optmc_price_american_batch: heterogeneous S0 / K / T / N / put-call options, each on its own Philox
+    stream.  fp64: every price equals the oracle fed the same normals; it also equals the single-option call.
+    M = 4096 -> one CTA per option (no exchange), M = 40 000 -> several CTAs per option and several waves."""
+    L, E, orc = mods
+    S0 = np.array([100.0, 95.0, 105.0, 100.0, 110.0, 90.0, 100.0])
+    K = np.array([100.0, 100.0, 100.0, 105.0, 100.0, 100.0, 98.0])
+    T = np.array([1.0, 0.5, 0.25, 1.0, 0.75, 0.1, 1.0])
+    N = np.array([20, 13, 10, 24, 16, 10, 11])
+    put = np.array([1, 1, 1, 1, 0, 0, 1])
+    streams = np.array([3, 5, 8, 13, 21, 34, 55])
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    for sem in ("reference", "textbook"):
+        price, se = eng.price_american_batch(model, M, S0, K, T, N, put, "f64", E.RngSpec(seed=77), semantics=sem,
+                                             streams=streams)
+        for i in range(len(S0)):
+            ot = "put" if put[i] else "call"
+            ref = _oracle_price_philox(eng, mods, None, S0[i], K[i], T[i], int(N[i]), M, ot, 77, int(streams[i]),
+                                       semantics=sem)
+            assert price[i] == pytest.approx(ref.price, rel=1e-10), (sem, i)
+            assert se[i] == pytest.approx(ref.stderr, rel=1e-8, abs=1e-12)
+            single = eng.price_american(E.heston(S0[i], 0.05, T[i], **HP), M, int(N[i]), K[i], ot, "f64",
+                                        E.RngSpec(seed=77, stream=int(streams[i])), semantics=sem)
+            assert price[i] == pytest.approx(single.price, rel=1e-12)
+
+
+def test_batch_many_small_options_fp32(eng, mods):
+    """The curve-driver shape (om3:697-713): hundreds of small pricings, N = max(10, min(130, ceil(days)))."""
+    L, E, orc = mods
+    days = np.arange(200, 0, -1, dtype=np.float64)
+    N = np.maximum(10, np.minimum(130, np.ceil(days))).astype(np.int64)
+    T = days / 365
+    model = E.gbm(100.0, 0.05, 1.0, 0.2)
+    price, se = eng.price_american_batch(model, 10_000, 100.0, 100.0, T, N, 1, "f32", E.RngSpec(seed=5))
+    assert np.isfinite(price).all() and (se > 0).all()
+    # American put >= European put (Black-Scholes) within Monte-Carlo error, and values grow with maturity overall
+    from options_model_b200 import compat
+
+    bs = np.array([compat.BlackScholesGreeks.black_scholes_price(100.0, 100.0, t, 0.05, 0.2, "put") for t in T])
+    assert np.all(price > bs - 4 * se)
+    assert price[0] > price[-1]
+    # spot-check three grid points against the single-option entry on the same stream
+    for i in (0, 77, 199):
+        single = eng.price_american(E.gbm(100.0, 0.05, T[i], 0.2), 10_000, int(N[i]), 100.0, "put", "f32",
+                                    E.RngSpec(seed=5, stream=i))
+        assert price[i] == pytest.approx(single.price, rel=1e-5)
+
+
+def test_compat_curve_uses_batch(mods):
+    from options_model_b200 import compat
+
+    kw = dict(K=100.0, r=0.05, sigma=None, option_type="put", use_heston=True, heston_params=HP,
+              use_control_variate=False)
+    a = compat.AdvancedOptionPricer(rng_manager=compat.RNGManager(9), **kw).compute_curve_for_S0(100.0, 1, 12, 20_000, False)
+    b = compat.AdvancedOptionPricer(rng_manager=compat.RNGManager(9), batched=False, **kw).compute_curve_for_S0(
+        100.0, 1, 12, 20_000, False)
+    assert [r["Days to Expiry"] for r in a] == [r["Days to Expiry"] for r in b]
+    va = np.array([r["Option Value"] for r in a]); vb = np.array([r["Option Value"] for r in b])
+    assert np.all(np.abs(va - vb) < 0.25)  # different Philox streams, same distribution
+    assert np.all(va > 0)
