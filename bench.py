@@ -4,12 +4,13 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--paths M] [--dates T]
 
 Own arm (default): one process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A "step" is
-one pass of the hot path over one option: K1 path generation (Philox in-register, step-major fp32 slab) +
-the persistent LSM sweep + the final payoff reduction, for BASELINE config 2 (Heston kappa=2 theta=0.04
-xi=0.5 rho=-0.7, 252 steps, 1M paths, quadratic-polynomial LSM).  With N GPUs every rank prices its own
-independent option (option-sharding, no data-path collective: weak scaling).  Timing: CUDA events on the
-launching stream, barrier + synchronize on both sides, max over ranks.  The 1 GB slab is 8x the L2, so no
-explicit L2 flush is needed between iterations.
+one pass of the hot path over one batch of --batch (4) independent options of BASELINE config 2 (Heston
+kappa=2 theta=0.04 xi=0.5 rho=-0.7, 252 steps, 1M paths each, quadratic-polynomial LSM): one batched K1 path
+launch (Philox in-register, step-major fp32 slabs) + one grouped persistent LSM sweep launch (each option on
+its own group of SMs) + the final payoff reductions, through optmc_price_american_batch.  With N GPUs every
+rank prices its own batches (option-sharding, no data-path collective: weak scaling).  Timing: CUDA events on
+the launching stream, barrier + synchronize on both sides, max over ranks; per-kernel times from CUDA events the
+library records around its two launches.  The 4 GB of slabs are 30x the L2, so no explicit L2 flush is needed.
 
 Reference arm (--impl reference): the reference is pure Python and cannot travel to the GPU box, so this
 times its restatement (oracle/lsm_oracle.py, numpy) on the host cores, reference-style: a process pool
@@ -190,55 +191,59 @@ def run_own_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    M, N = args.paths, args.dates
+    M, N, B = args.paths, args.dates, args.batch
     eng = E.Engine(local)
     stream = torch.cuda.Stream(device=local)
     model = E.heston(S0, R, T, **HP)
     b = 4  # fp32 storage
-    with torch.cuda.stream(stream):
-        slab = eng.alloc_slab(M, N, "f32")
-        view = slab[:, :M]
+    import numpy as np
 
-        def step(i, ev=None):
-            rng = E.RngSpec(seed=42, stream=rank * 1_000_003 + i)  # a fresh option (stream) per step and rank
-            if ev:
-                ev[0].record()
-            eng.paths(model, M, N, "f32", rng, out=slab)
-            if ev:
-                ev[1].record()
-            eng.lsm(view, K, R, T, "put", "poly2", "reference", "auto", asynchronous=True)
-            if ev:
-                ev[2].record()
+    Ns = np.full(B, N, dtype=np.int64)
+    with torch.cuda.stream(stream):
+        def step(i):
+            # B fresh options (Philox streams) per step and rank; host scalars in, host prices out
+            streams = (rank * 1_000_003 + i) * B + np.arange(B)
+            return eng.price_american_batch(model, M, S0, K, T, Ns, 1, "f32", E.RngSpec(seed=42), "poly2", "reference",
+                                            streams=streams)
 
         for i in range(args.warmup):
             step(i)
         barrier()
-        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
         l0 = eng.launch_count()
+        ms_paths = ms_sweep = 0.0
         with ClockSampler(local) as clocks:
             t_start = torch.cuda.Event(enable_timing=True)
             t_end = torch.cuda.Event(enable_timing=True)
             t_start.record()
             for i in range(args.steps):
-                step(args.warmup + i, evs[i])
+                price, se = step(args.warmup + i)
+                kp, ks = eng.kernel_times()  # CUDA events around the kernels, recorded inside the library
+                ms_paths += kp
+                ms_sweep += ks
             t_end.record()
             barrier()
         launches = eng.launch_count() - l0
         ms_total = t_start.elapsed_time(t_end)
-        res = eng.lsm_fetch(N, "poly2", arrays=False)
-        ms_paths = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-        ms_sweep = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+        ms_paths /= args.steps
+        ms_sweep /= args.steps
 
-        # end-to-end through the reference-facing call: host scalars in, host float out, every step
+        class _Res:
+            pass
+
+        res = _Res()
+        res.price, res.stderr = float(price[0]), float(se[0])
+
+        # end-to-end through the reference-facing call: host scalars in, host floats out, every step
         pricer = compat.AdvancedOptionPricer(K=K, r=R, sigma=None, option_type="put", rng_manager=compat.RNGManager(42),
                                              use_heston=True, heston_params=HP, use_control_variate=False,
                                              device=local)
+        grid_S0, grid_T, grid_N = np.full(B, S0), np.full(B, T), Ns
         for _ in range(max(1, args.warmup // 2)):
-            pricer.price_american_enhanced_lsm(S0, T, M, N)
+            pricer.price_american_grid(grid_S0, grid_T, grid_N, M)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            price_e2e = pricer.price_american_enhanced_lsm(S0, T, M, N)
+            price_e2e = float(pricer.price_american_grid(grid_S0, grid_T, grid_N, M)[0][0])
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         barrier()
@@ -254,16 +259,16 @@ def run_own_arm(args):
         import ctypes
 
         peak, peak_src = load_peaks()
-        path_steps = world * M * N * args.steps
+        path_steps = world * B * M * N * args.steps
         value = path_steps / (ms_total * 1e-3)
         # algorithmic bytes: generation b per path-step (rows 0..N stored); sweep 3b per path
         # per exercise date (+ b for the terminal row); pipeline 4b per path-step.
-        bytes_paths = b * M * (N + 1)
-        bytes_sweep = 3 * b * M * (N - 1) + b * M
+        bytes_paths = B * b * M * (N + 1)                     # one batched launch generates B slabs
+        bytes_sweep = B * (3 * b * M * (N - 1) + b * M)       # one grouped launch sweeps B options
         kern = {
-            "paths_kernel<f32,heston_ref_absorb,vec4,philox>": {
+            "paths_batch_kernel<f32,heston_ref_absorb,vec4>": {
                 "ms": ms_paths, "alg_bytes": bytes_paths, "GBps": bytes_paths / (ms_paths * 1e-3) / 1e9,
-                "dram_bytes_ncu": load_traffic("paths_kernel")},
+                "dram_bytes_ncu": load_traffic("paths_batch_kernel")},
             "lsm_resident_kernel<f32,poly2,sparse>": {
                 "ms": ms_sweep, "alg_bytes": bytes_sweep, "GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9,
                 "dram_bytes_ncu": load_traffic("lsm_resident_kernel")},
@@ -271,29 +276,31 @@ def run_own_arm(args):
         dom = max(kern, key=lambda k: kern[k]["ms"])
         ach = kern[dom]["GBps"]
         cpu = cpu_baseline_single(args.cpu_paths, N) if world == 1 and not args.no_cpu else None
-        h2d = ctypes.sizeof(L.ModelParams) + ctypes.sizeof(L.RngParams) + ctypes.sizeof(L.LsmParams)
+        h2d = ctypes.sizeof(L.ModelParams) + ctypes.sizeof(L.RngParams) + B * ctypes.sizeof(L.AmericanOption)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"BASELINE config 2: American put, Heston (kappa=2, theta=0.04, xi=0.5, rho=-0.7), "
-                                   f"{N} steps, {M} paths per option, poly2 LSM (reference semantics), one option per "
-                                   f"GPU per step",
+                                   f"{N} steps, {M} paths per option, poly2 LSM (reference semantics); a step prices a batch "
+                                   f"of {B} independent options of that size per GPU in one grouped launch",
+                       "batch": B,
                        "storage": "fp32 step-major slab, fp64 Gram/solve/decision", "rng": "Philox4x32-10 in-register",
                        "sharding": "options across ranks (no data-path collective)",
-                       "l2": f"slab {b * M * (N + 1) / 1e6:.0f} MB per step > L2 ({eng.l2_bytes / 1e6:.0f} MB): no flush needed",
+                       "l2": f"slabs {B * b * M * (N + 1) / 1e6:.0f} MB per step > L2 ({eng.l2_bytes / 1e6:.0f} MB): no flush needed",
                        "price": res.price, "stderr": res.stderr},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": kern[dom]["dram_bytes_ncu"], "kernel": dom, "peak_source": peak_src,
                          "note": "achieved = algorithmic bytes (SURVEY 8d: 3b per path per exercise date for the sweep, "
                                  "b per path-step for generation) / CUDA-event time of that kernel; traffic = DRAM bytes "
                                  "per launch from the committed ncu capture (profiles/)",
-                         "pipeline_frac": (4 * b * M * N * world * args.steps) / (ms_total * 1e-3) / 1e9 / (peak * world),
+                         "pipeline_frac": (4 * b * B * M * N * world * args.steps) / (ms_total * 1e-3) / 1e9 / (peak * world),
                          "kernels": kern},
-            "e2e": {"value": world * M * N * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 32, "ms_per_step": e2e_ms / args.steps, "price": price_e2e,
-                    "call": "compat.AdvancedOptionPricer.price_american_enhanced_lsm (host scalars in, host float out; "
-                            "the path's inputs are option/model scalars, normals are generated in-kernel)"},
+            "e2e": {"value": world * B * M * N * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 48 * B, "ms_per_step": e2e_ms / args.steps, "price": price_e2e,
+                    "call": "compat.AdvancedOptionPricer.price_american_grid -> optmc_price_american_batch (host option "
+                            "scalars in, host prices out; the path's inputs are option/model scalars, normals are "
+                            "generated in-kernel)"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
@@ -309,11 +316,12 @@ def run_own_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--paths", type=int, default=1_000_000)
     ap.add_argument("--dates", type=int, default=252)
+    ap.add_argument("--batch", type=int, default=4, help="independent options priced per step (one grouped launch)")
     ap.add_argument("--cpu-paths", type=int, default=1_000_000, help="CPU-baseline sample size (paths)")
     ap.add_argument("--ref-paths", type=int, default=50_000, help="reference arm: paths per worker per step")
     ap.add_argument("--no-cpu", action="store_true")

@@ -132,6 +132,10 @@ int optmc_ctx_set_stream(optmc_ctx* ctx, void* cuda_stream);
 int optmc_ctx_synchronize(optmc_ctx* ctx);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t optmc_ctx_launch_count(optmc_ctx* ctx);
+/* Device time of the path kernel(s) and the sweep kernel(s) of the last optmc_price_american /
+ * optmc_price_american_batch call on this context, measured with CUDA events on the context's stream
+ * (bench.py's per-kernel roofline). */
+int optmc_ctx_kernel_times(optmc_ctx* ctx, double* paths_ms, double* sweep_ms);
 /* Device properties the host layer needs for grid sizing / reporting: out[0]=SM count,
  * out[1]=L2 bytes, out[2]=max opt-in shared memory per block, out[3]=compute capability major*10+minor. */
 int optmc_ctx_device_info(optmc_ctx* ctx, int64_t out[4]);

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "optmc_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "optmc_ctx_synchronize": (C.c_int, [C.c_void_p]),
     "optmc_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "optmc_ctx_kernel_times": (C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_double)]),
     "optmc_ctx_device_info": (C.c_int, [C.c_void_p, _P(C.c_int64)]),
     "optmc_paths_gbm": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_int64]),

@@ -224,6 +224,7 @@ int optmc_ctx_create(int device, optmc_ctx** out) {
   OPTMC_CUDA(cudaMalloc((void**)&c->d_final, 4 * sizeof(double)));
   OPTMC_CUDA(cudaMalloc(&c->xchg, xchg_bytes()));
   OPTMC_CUDA(cudaMemset(c->xchg, 0, xchg_bytes()));
+  for (int i = 0; i < 3; ++i) OPTMC_CUDA(cudaEventCreate(&c->ev[i]));
   OPTMC_CUDA(cudaMalloc((void**)&c->d_flags, 4 * sizeof(int)));
   OPTMC_CUDA(cudaMemset(c->d_flags, 0, 4 * sizeof(int)));
   *out = c;
@@ -238,6 +239,7 @@ int optmc_ctx_destroy(optmc_ctx* ctx) {
   cudaFree(ctx->slab); cudaFree(ctx->cf); cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->gram);
   cudaFree(ctx->d_betas); cudaFree(ctx->d_bnd); cudaFree(ctx->d_exc); cudaFree(ctx->d_nitm); cudaFree(ctx->d_valid);
   cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
+  for (int i = 0; i < 3; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
   return OPTMC_OK;
@@ -256,6 +258,13 @@ int optmc_ctx_synchronize(optmc_ctx* ctx) {
 }
 
 int64_t optmc_ctx_launch_count(optmc_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int optmc_ctx_kernel_times(optmc_ctx* ctx, double* paths_ms, double* sweep_ms) {
+  if (!ctx) { set_error("null context"); return OPTMC_EINVAL; }
+  if (paths_ms) *paths_ms = ctx->last_paths_ms;
+  if (sweep_ms) *sweep_ms = ctx->last_sweep_ms;
+  return OPTMC_OK;
+}
 
 int optmc_ctx_device_info(optmc_ctx* ctx, int64_t out[4]) {
   if (!ctx || !out) { set_error("null argument"); return OPTMC_EINVAL; }
@@ -374,14 +383,23 @@ int optmc_price_american(optmc_ctx* ctx, const optmc_model_params* mp, const opt
   const int64_t ld = (M + 63) / 64 * 64;  // rows start on 256-byte boundaries: 128-bit stores and bulk copies
   int rc = ensure_bytes(&ctx->slab, &ctx->slab_bytes, (size_t)(N + 1) * ld * es);
   if (rc) return rc;
+  OPTMC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   rc = launch_paths(ctx, mp, rng, M, N, dtype, ctx->slab, nullptr, ld);
   if (rc) return rc;
+  OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   rc = bind_sweep(ctx, ctx->slab, ld, M, N, dtype, lp);
   if (rc) return rc;
   rc = run_sweep(ctx);
   if (rc) return rc;
+  OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
   ctx->sw.n_launches += 1;  // the path kernel
-  return out ? fetch_results(ctx, out) : OPTMC_OK;
+  if (!out) return OPTMC_OK;
+  rc = fetch_results(ctx, out);
+  if (rc) return rc;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_paths_ms = ms;
+  if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) ctx->last_sweep_ms = ms;
+  return OPTMC_OK;
   OPTMC_TRY_END
 }
 

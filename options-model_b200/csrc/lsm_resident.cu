@@ -225,6 +225,7 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
   std::vector<char> hp(path_args_bytes() * G);
   std::vector<double> hfin((size_t)G * 4);
   std::vector<int> hflags((size_t)G * 4);
+  ctx->last_paths_ms = 0.0; ctx->last_sweep_ms = 0.0;
   for (int w0 = 0; w0 < n_options; w0 += G) {
     const int g_now = n_options - w0 < G ? n_options - w0 : G;
     for (int g = 0; g < g_now; ++g) {
@@ -240,17 +241,25 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
     OPTMC_CUDA(cudaMemcpyAsync(d_groups, hg.data(), sizeof(ResGroup) * g_now, cudaMemcpyHostToDevice, ctx->stream));
     batch_reset_kernel<<<8, 256, 0, ctx->stream>>>(d_words, (int)n_words, d_final, G * 4);
     ctx->launches++;
+    OPTMC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
     rc = launch_paths_batch(ctx, mp, rng, M, dtype, g_now, opts + w0, ctx->slab, slab_stride, ld, dev + off_paths, hp.data());
     if (rc) return rc;
+    OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     ResPlan pw = p;
     pw.ngroups = g_now;
     ResArgs a{};
     a.groups = d_groups; a.cpg = cpg; a.nstage = p.nstage; a.stage_stride = p.stage_stride; a.sticky = sticky ? 1 : 0;
     rc = launch_resident(ctx, pw, a, dtype, deg);
     if (rc) return rc;
+    OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
     OPTMC_CUDA(cudaMemcpyAsync(hfin.data(), d_final, sizeof(double) * 4 * g_now, cudaMemcpyDeviceToHost, ctx->stream));
     OPTMC_CUDA(cudaMemcpyAsync(hflags.data(), d_flags, sizeof(int) * 4 * g_now, cudaMemcpyDeviceToHost, ctx->stream));
     OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_paths_ms += ms;
+      if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) ctx->last_sweep_ms += ms;
+    }
     for (int g = 0; g < g_now; ++g) {
       results[w0 + g].price = hfin[(size_t)g * 4];
       results[w0 + g].stderr_ = hfin[(size_t)g * 4 + 1];

@@ -75,6 +75,8 @@ struct optmc_ctx {
   void* xchg = nullptr;                 // exchange accumulators of the persistent sweep, xchg_bytes()
   int* d_flags = nullptr;               // [4]: [0] = fixed-point exchange overflow
   void* batch_dev = nullptr; size_t batch_dev_cap = 0;  // per-wave descriptors / accumulators / results
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};      // kernel timing of the fused calls (optmc_ctx_kernel_times)
+  double last_paths_ms = 0.0, last_sweep_ms = 0.0;
   double* eu_out = nullptr; size_t eu_out_cap = 0;  // [n_options][3]
   double* eu_par = nullptr; size_t eu_par_cap = 0;  // [n_options][4] K, T, is_put, pad
   unsigned int* eu_tickets = nullptr; size_t eu_tickets_cap = 0;

@@ -135,6 +135,12 @@ class Engine:
     def synchronize(self):
         L.check(self.lib.optmc_ctx_synchronize(self._h))
 
+    def kernel_times(self):
+        """(paths_ms, sweep_ms) of the last fused pricing call (CUDA events inside the library)."""
+        a, b = C.c_double(), C.c_double()
+        L.check(self.lib.optmc_ctx_kernel_times(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def launch_count(self) -> int:
         return int(self.lib.optmc_ctx_launch_count(self._h))
 

@@ -1,0 +1,44 @@
+"""Throughput of optmc_price_american_batch on the BASELINE batch shapes (development tool)."""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import options_model_b200  # noqa: E402,F401
+from options_model_b200 import engine as E  # noqa: E402
+
+HP = dict(v0=0.04, kappa=2.0, theta=0.04, xi=0.5, rho=-0.7)
+eng = E.Engine(0)
+model = E.heston(100.0, 0.05, 1.0, **HP)
+
+
+def run(name, M, S0, K, T, N, reps=3, sem="reference"):
+    S0, K, T, N = np.broadcast_arrays(np.asarray(S0, float), np.asarray(K, float), np.asarray(T, float), np.asarray(N))
+    n = S0.size
+    eng.price_american_batch(model, M, S0, K, T, N, 1, "f32", E.RngSpec(seed=1), semantics=sem)  # warm
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for r in range(reps):
+        p, se = eng.price_american_batch(model, M, S0, K, T, N, 1, "f32", E.RngSpec(seed=2 + r), semantics=sem)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    ps = float(np.sum(N)) * M
+    kp, ks = eng.kernel_times()
+    print(f"{name:48s} n={n:5d} M={M:8d} {dt * 1e3:9.2f} ms  {ps / dt / 1e9:8.1f} G path-steps/s  "
+          f"{dt / n * 1e6:9.1f} us/option  kernels: paths {kp:.3f} ms sweep {ks:.3f} ms  price[0]={p[0]:.4f} +- {se[0]:.4f}", flush=True)
+
+
+for n in (1, 2, 4, 8):
+    run(f"config-2 options x{n}", 1_000_000, 100.0, 100.0, 1.0, np.full(n, 252))
+run("config-2 x4 textbook", 1_000_000, 100.0, 100.0, 1.0, np.full(4, 252), sem="textbook")
+Kg, Tg = np.meshgrid(np.linspace(70, 130, 8), np.linspace(1 / 12, 2, 7))
+run("config-4 slice: 56 options x 256k", 262_144, 100.0, Kg.ravel(), Tg.ravel(), np.full(56, 252), reps=2)
+days = np.arange(360, 0, -1.0)
+run("curve driver: 360 points x 10k paths", 10_000, 100.0, 100.0, days / 365,
+    np.maximum(10, np.minimum(130, np.ceil(days))).astype(int))
+run("curve driver: 360 points x 100k paths", 100_000, 100.0, 100.0, days / 365,
+    np.maximum(10, np.minimum(130, np.ceil(days))).astype(int), reps=2)
