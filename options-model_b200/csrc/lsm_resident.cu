@@ -46,8 +46,11 @@ static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int 
   chunk = (chunk + 3) / 4 * 4;
   ncta = (M + chunk - 1) / chunk;
   const ResShape* shape = nullptr;
+  int only_nt = 0;  // tuning aid: OPTMC_RES_NT restricts the thread count considered
+  if (const char* e = getenv("OPTMC_RES_NT")) only_nt = atoi(e);
   for (const ResShape& c : kShapes)
-    if ((long long)c.nt * c.ppt >= chunk) { shape = &c; break; }
+    if ((long long)c.nt * c.ppt >= chunk && (!only_nt || c.nt == only_nt) &&
+        (c.nt == 512 || (sticky && dtype == OPTMC_F32))) { shape = &c; break; }
   if (!shape) { *why = "slice exceeds the register-resident capacity"; return false; }
   // every stage holds the full NT x PPT slot grid: the tail behind the slice is an out-of-the-money sentinel
   const size_t stride = ((size_t)shape->nt * shape->ppt * es + 127) / 128 * 128;
@@ -67,7 +70,9 @@ static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int 
 static bool plan_resident(optmc_ctx* ctx, const SweepDesc& sw, ResPlan* p, std::string* why) {
   const size_t es = sw.dtype == OPTMC_F64 ? 8 : 4;
   if ((uintptr_t)sw.S % 16 != 0 || (sw.ld * es) % 16 != 0) { *why = "slab not 16-byte aligned"; return false; }
-  return plan_shape(ctx, sw.M, sw.dtype, (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) != 0, ctx->sm_count, p, why);
+  int max_ctas = ctx->sm_count;  // tuning aid: OPTMC_RES_MAXCTAS emulates one group of a batched launch
+  if (const char* e = getenv("OPTMC_RES_MAXCTAS")) { const int v = atoi(e); if (v >= 1 && v < max_ctas) max_ctas = v; }
+  return plan_shape(ctx, sw.M, sw.dtype, (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) != 0, max_ctas, p, why);
 }
 
 bool resident_eligible(optmc_ctx* ctx, const SweepDesc& sw, std::string* why) {
