@@ -55,7 +55,8 @@ enum optmc_scheme {
 
 enum optmc_basis {
   OPTMC_BASIS_POLY2 = 2, /* [1, x, x^2], x = S/K : first three reference features (om3:112-115) */
-  OPTMC_BASIS_POLY3 = 3  /* [1, x, x^2, x^3]     : first four reference features */
+  OPTMC_BASIS_POLY3 = 3, /* [1, x, x^2, x^3]     : first four reference features */
+  OPTMC_BASIS_REF7 = 7   /* all seven reference features (om3:105-121); global fit only (optmc_lsm_global) */
 };
 
 /* LSM loop semantics.  REFERENCE = STICKY | REF_DISCOUNT reproduces om3:616-651. */
@@ -160,6 +161,28 @@ int optmc_lsm_poly(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int
                    const optmc_lsm_params* lp, optmc_lsm_result* out /* NULL: asynchronous, fetch later */);
 /* Synchronise and copy the last sweep's results to the host. */
 int optmc_lsm_fetch(optmc_ctx* ctx, optmc_lsm_result* out);
+
+/* ---- LSM with ONE global regression over all (date, path) rows: the structure of the reference's v3 pricer
+ *      (om3:482-651 / om3gpu:695-833) with its network replaced by linear least squares on the seven reference
+ *      features.  Pass 1 (om3:485-516): targets are the discounted TERMINAL payoffs of every in-the-money path at
+ *      every date (`exercised` is never set in pass 1).  The target / feature z-scoring of om3:550-563 is an affine
+ *      change of variables, under which a linear model with intercept is invariant, so it is not materialised.
+ *      Pass 2 (om3:615-651): the usual loop (sticky mask, strict '>', N-1 discounts) with the global model.
+ *      Both passes stream the slab once and are independent across paths: no per-date regression, no grid
+ *      synchronisation. */
+typedef struct optmc_global_result {
+  double price, stderr_;
+  int64_t n_paths;
+  int64_t n_rows;    /* regression rows = sum over dates of in-the-money paths */
+  int32_t n_launches;
+  int32_t rank;      /* columns kept by the guarded solve (redundant columns get beta = 0) */
+  double beta[7];    /* coefficients of [1, x, x^2, x^3, max(x-1,0), sqrt(tau), x sqrt(tau)] (om3:112-121) */
+  double* boundary;  /* host [N+1] or NULL: put -> max exercised S, call -> min exercised S, NaN if none */
+  int64_t* ex_count; /* host [N+1] or NULL */
+} optmc_global_result;
+
+int optmc_lsm_global(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                     const optmc_lsm_params* lp /* basis ignored (REF7) */, optmc_global_result* out);
 
 /* Per-date building blocks for path-sharded multi-GPU sweeps: the host all-reduces `gram_dev`
  * (optmc_lsm_gram_len doubles) between the two calls. */

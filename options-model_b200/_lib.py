@@ -12,7 +12,7 @@ OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 MODEL_GBM, MODEL_HESTON = 0, 1
 SCHEME_GBM_LOG_EULER, SCHEME_GBM_LOGSPACE, SCHEME_HESTON_REF_ABSORB, SCHEME_HESTON_FULL_TRUNC, SCHEME_HESTON_REF_CALIB = range(5)
-BASIS_POLY2, BASIS_POLY3 = 2, 3
+BASIS_POLY2, BASIS_POLY3, BASIS_REF7 = 2, 3, 7
 SEM_STICKY_MASK, SEM_REF_DISCOUNT = 1, 2
 SEM_REFERENCE, SEM_TEXTBOOK = 3, 0
 SWEEP_AUTO, SWEEP_RESIDENT, SWEEP_SPLIT = 0, 1, 2
@@ -53,6 +53,12 @@ class PriceResult(C.Structure):
     _fields_ = [("price", C.c_double), ("stderr_", C.c_double)]
 
 
+class GlobalResult(C.Structure):
+    _fields_ = [("price", C.c_double), ("stderr_", C.c_double), ("n_paths", C.c_int64), ("n_rows", C.c_int64),
+                ("n_launches", C.c_int32), ("rank", C.c_int32), ("beta", C.c_double * 7),
+                ("boundary", C.POINTER(C.c_double)), ("ex_count", C.POINTER(C.c_int64))]
+
+
 class EuropeanResult(C.Structure):
     _fields_ = [("mean", C.c_double), ("stderr_", C.c_double), ("n_paths", C.c_int64)]
 
@@ -79,6 +85,8 @@ PROTOTYPES = {
     "optmc_lsm_poly": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
                                  _P(LsmResult)]),
     "optmc_lsm_fetch": (C.c_int, [C.c_void_p, _P(LsmResult)]),
+    "optmc_lsm_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
+                                   _P(GlobalResult)]),
     "optmc_lsm_gram_len": (C.c_int, [C.c_int32]),
     "optmc_lsm_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams)]),
     "optmc_lsm_gram_date": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

@@ -324,6 +324,14 @@ int optmc_lsm_fetch(optmc_ctx* ctx, optmc_lsm_result* out) {
   OPTMC_TRY_END
 }
 
+int optmc_lsm_global(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                     const optmc_lsm_params* lp, optmc_global_result* out) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return lsm_global(ctx, S_dev, ld, M, N, dtype, lp, out);
+  OPTMC_TRY_END
+}
+
 int optmc_lsm_gram_len(int32_t basis) {
   if (basis == OPTMC_BASIS_POLY2) return 8;
   if (basis == OPTMC_BASIS_POLY3) return 11;

@@ -116,6 +116,10 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
                          int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
                          const optmc_american_option* opts, optmc_price_result* results);
 
+// lsm_global.cu
+int lsm_global(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+               const optmc_lsm_params* lp, optmc_global_result* out);
+
 // european.cu
 int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                           int32_t N, int32_t dtype, int32_t n_options, const double* K, const double* T,

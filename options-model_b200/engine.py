@@ -238,6 +238,27 @@ class Engine:
         L.check(self.lib.optmc_lsm_poly(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), C.byref(res)))
         return self._to_result(res, keep)
 
+    def lsm_global(self, S, K, r, T, option_type="put", semantics="reference", arrays=True, M: Optional[int] = None):
+        """Global-regression LSM (the reference's v3 structure, om3:482-651, with a linear model on the seven
+        reference features).  Returns a dict: price, stderr, n_rows, rank, beta[7], boundary, ex_count."""
+        assert S.is_cuda and S.dim() == 2 and S.stride(1) == 1
+        N = S.shape[0] - 1
+        M = int(M if M is not None else S.shape[1])
+        lp = self._lsm_params(K, r, T, option_type, L.BASIS_REF7, semantics, "auto")
+        code = L.F64 if S.dtype == self.torch.float64 else L.F32
+        res = L.GlobalResult()
+        bnd = exc = None
+        if arrays:
+            bnd = np.full(N + 1, np.nan)
+            exc = np.zeros(N + 1, dtype=np.int64)
+            res.boundary = bnd.ctypes.data_as(C.POINTER(C.c_double))
+            res.ex_count = exc.ctypes.data_as(C.POINTER(C.c_int64))
+        self._sync_stream()
+        L.check(self.lib.optmc_lsm_global(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), C.byref(res)))
+        return dict(price=res.price, stderr=res.stderr_, n_paths=int(res.n_paths), n_rows=int(res.n_rows),
+                    rank=int(res.rank), n_launches=int(res.n_launches), beta=np.array(list(res.beta)), boundary=bnd,
+                    ex_count=exc)
+
     def lsm_fetch(self, N: int, basis="poly2", arrays=True) -> SweepResult:
         p = 3 if basis in ("poly2", L.BASIS_POLY2) else 4
         res, keep = self._result_block(N, p, arrays)

@@ -482,6 +482,8 @@ def lsm_global(S, K, r, T, option_type, fit: Callable, target_ddof=0):
 
     cf = payoff(S[-1], K, option_type).astype(np.float64)
     exercised = np.zeros(M, dtype=bool)
+    ex_count = np.zeros(N + 1, dtype=np.int64)
+    boundary = np.full(N + 1, np.nan)
     for t in range(N - 1, 0, -1):
         cf *= discount
         itm = (payoff(S[t], K, option_type) > 0) & (~exercised)
@@ -495,8 +497,20 @@ def lsm_global(S, K, r, T, option_type, fit: Callable, target_ddof=0):
         idx = np.where(itm)[0][to_ex]
         cf[idx] = immediate[to_ex]
         exercised[idx] = True
-    stats = dict(Y_mean=float(Y_mean), Y_std=float(Y_std), f_mean=f_mean, f_std=f_std, n_rows=int(X_all.shape[0]))
+        ex_count[t] = idx.size
+        if idx.size:
+            boundary[t] = X[to_ex].max() if option_type == "put" else X[to_ex].min()
+    stats = dict(Y_mean=float(Y_mean), Y_std=float(Y_std), f_mean=f_mean, f_std=f_std, n_rows=int(X_all.shape[0]),
+                 ex_count=ex_count, boundary=boundary, stderr=float(cf.std(ddof=1) / math.sqrt(M)) if M > 1 else 0.0)
     return float(cf.mean()), stats
+
+
+def linear_fit(Xn, Ys):
+    """Least squares with intercept on the (z-scored) reference features: the regressor optmc_lsm_global
+    implements.  Minimum-norm solution, so all-zero / duplicated columns are harmless."""
+    A = np.column_stack([np.ones(len(Xn)), np.asarray(Xn, dtype=np.float64)])
+    w, *_ = np.linalg.lstsq(A, np.asarray(Ys, dtype=np.float64).ravel(), rcond=None)
+    return lambda fn: np.column_stack([np.ones(len(fn)), np.asarray(fn, dtype=np.float64)]) @ w
 
 
 # --------------------------------------------------------------------------------------

@@ -527,3 +527,72 @@ def test_compat_curve_uses_batch(mods):
     va = np.array([r["Option Value"] for r in a]); vb = np.array([r["Option Value"] for r in b])
     assert np.all(np.abs(va - vb) < 0.25)  # different Philox streams, same distribution
     assert np.all(va > 0)
+
+
+# ------------------------------------------------------------------------------------------------------
+# global-regression LSM (the reference's v3 structure with a linear model on the seven reference features)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["heston_put", "gbm_call", "heston_put_f32"])
+def test_global_lsm_vs_oracle(eng, mods, case):
+    """optmc_lsm_global vs oracle.lsm_global (pinned against the real om3 loop by tests/test_oracle_golden.py)
+    with a least-squares fit on the z-scored reference features, same paths."""
+    L, E, orc = mods
+    rng = np.random.default_rng(23)
+    M, N = 20_000, 25
+    if case.startswith("heston"):
+        Z1, Z2 = orc.draw_heston_normals(rng, N, M)
+        S = orc.heston_paths_antithetic(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2)
+        K, ot = 100.0, "put"
+    else:
+        S = orc.gbm_paths_antithetic(100.0, 0.05, 0.25, 1.0, M, N, orc.draw_gbm_normals(rng, N, M))
+        K, ot = 97.5, "call"
+    f32 = case.endswith("f32")
+    if f32:
+        S = S.astype(np.float32).astype(np.float64)
+    price, st = orc.lsm_global(S, K, 0.05, 1.0, ot, orc.linear_fit)
+    res = eng.lsm_global(_slab(eng, S, torch.float32 if f32 else torch.float64), K, 0.05, 1.0, ot)
+    assert res["n_rows"] == st["n_rows"]
+    assert res["price"] == pytest.approx(price, rel=1e-4 if f32 else 1e-7)
+    assert res["stderr"] == pytest.approx(st["stderr"], rel=1e-4 if f32 else 1e-6)
+    assert np.abs(res["ex_count"] - st["ex_count"]).sum() <= (20 if f32 else 2)
+    same = res["ex_count"] == st["ex_count"]
+    both = same & ~np.isnan(st["boundary"])
+    np.testing.assert_allclose(res["boundary"][both], st["boundary"][both], rtol=1e-6 if f32 else 1e-9)
+    # the model itself: evaluate both on a few (x, tau) points through the reference features
+    assert res["rank"] == 6 and res["beta"][4] == 0.0
+    xs = np.linspace(0.7, 0.99, 5) if ot == "put" else np.linspace(1.01, 1.3, 5)
+    for t_cur in (0.2, 0.6):
+        F = orc.features_ref7(xs * K, K, 0.05, 1.0, t_cur)
+        got = F @ res["beta"]
+        # oracle predictor in its normalised space
+        import numpy.linalg as la  # noqa: F401
+
+        feats, targs = [], []
+        dt = 1.0 / N
+        cf = orc.payoff(S[-1], K, ot).astype(np.float64)
+        for t in range(N - 1, 0, -1):
+            cf *= np.exp(-0.05 * dt)
+            itm = orc.payoff(S[t], K, ot) > 0
+            feats.append(orc.features_ref7(S[t, itm], K, 0.05, 1.0, t * dt)); targs.append(cf[itm])
+        X_all = np.vstack(feats); Y_all = np.concatenate(targs)
+        A = np.column_stack([X_all[:, 1:4], X_all[:, 5:7]])  # [x, x^2, x^3, s, x s] + intercept
+        A = np.column_stack([np.ones(len(A)), A])
+        w, *_ = np.linalg.lstsq(A, Y_all, rcond=None)
+        want = np.column_stack([np.ones(len(F)), F[:, 1:4], F[:, 5:7]]) @ w
+        np.testing.assert_allclose(got, want, rtol=2e-4 if f32 else 1e-6, atol=1e-6)
+
+
+def test_global_lsm_full_size_streams_at_hbm_rate(eng, mods):
+    """Config-2-sized slab through both streaming passes: all six informative columns are kept, the regression
+    sees every ITM (date, path) row, the sticky-mask price exceeds the textbook one (look-ahead bias, App. A Q1),
+    and both stay near the European value -- the regression target is the European payoff (App. A Q4), so the
+    exercise rule is far from optimal and the textbook value may even fall below the European one."""
+    L, E, orc = mods
+    M, N, K = 1_000_000, 252, 100.0
+    S = eng.paths(E.heston(100.0, 0.05, 1.0, **HP), M, N, "f32", E.RngSpec(seed=11))
+    g = eng.lsm_global(S, K, 0.05, 1.0, "put", arrays=False)
+    gt = eng.lsm_global(S, K, 0.05, 1.0, "put", semantics="textbook", arrays=False)
+    eu, _ = eng.european_from_slab(S[N].contiguous(), K, 0.05, 1.0, "put")
+    assert g["rank"] == 6 and g["n_rows"] > 0.3 * M * (N - 1)
+    assert gt["price"] < g["price"] and np.isfinite(g["stderr"])
+    assert abs(gt["price"] - eu) < 0.3
