@@ -299,7 +299,7 @@ struct WalkArgs {
 
 // VEC consecutive paths per thread; cash-flows in date-N money; exercised flag = sign bit (sticky semantics).
 template <typename R, int VEC, bool STATS>
-__global__ void __launch_bounds__(kGThreads) global_walk_kernel(const WalkArgs a) {
+__global__ void __launch_bounds__(kGThreads, 4) global_walk_kernel(const WalkArgs a) {
   // dynamic shared memory: [N+1] decision entries (when they fit), then STATS: [N+1] counts, [N+1] boundary keys
   extern __shared__ unsigned long long s_dyn[];
   __shared__ double red[kGWarps * 2];
