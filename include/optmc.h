@@ -184,6 +184,25 @@ typedef struct optmc_global_result {
 int optmc_lsm_global(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
                      const optmc_lsm_params* lp /* basis ignored (REF7) */, optmc_global_result* out);
 
+/* ---- per-date neural-network LSM: the reference's v1/v2 loop (om2:277-310, om15:145-186, om1:107-150).  At every
+ *      exercise date a fresh ContNet (1 -> hidden -> hidden -> 1, ReLU; om2:114-126) is trained for `epochs`
+ *      full-batch Adam steps on the standardised prices of the live paths and its in-sample prediction is the
+ *      continuation value.  Initial weights come from Philox (torch's default Linear range), so prices agree with
+ *      the reference statistically; fed the same initial weights (optmc_mlp_init_params) the fit is reproducible
+ *      to fp32 rounding.  Results through optmc_lsm_result (betas are NaN). */
+typedef struct optmc_mlp_params {
+  int32_t hidden;  /* 32 (om2 default nn_hidden) */
+  int32_t epochs;  /* om2 default nn_epochs = 10 */
+  double lr;       /* om2 default nn_lr = 1e-3 */
+  uint64_t seed;   /* Philox key of the per-date initial weights */
+} optmc_mlp_params;
+
+int optmc_lsm_mlp(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                  const optmc_lsm_params* lp /* basis ignored */, const optmc_mlp_params* np, optmc_lsm_result* out);
+/* The initial parameters of date `date`: host out[3 H + H^2 + H + 1] in the order w1[H] b1[H] W2[H][H] b2[H] w3[H] b3.
+ * Returns the parameter count, or a negative status. */
+int optmc_mlp_init_params(int32_t hidden, uint64_t seed, int32_t date, float* out);
+
 /* Per-date building blocks for path-sharded multi-GPU sweeps: the host all-reduces `gram_dev`
  * (optmc_lsm_gram_len doubles) between the two calls. */
 int optmc_lsm_gram_len(int32_t basis);

@@ -53,6 +53,10 @@ class PriceResult(C.Structure):
     _fields_ = [("price", C.c_double), ("stderr_", C.c_double)]
 
 
+class MlpParams(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("epochs", C.c_int32), ("lr", C.c_double), ("seed", C.c_uint64)]
+
+
 class GlobalResult(C.Structure):
     _fields_ = [("price", C.c_double), ("stderr_", C.c_double), ("n_paths", C.c_int64), ("n_rows", C.c_int64),
                 ("n_launches", C.c_int32), ("rank", C.c_int32), ("beta", C.c_double * 7),
@@ -87,6 +91,9 @@ PROTOTYPES = {
     "optmc_lsm_fetch": (C.c_int, [C.c_void_p, _P(LsmResult)]),
     "optmc_lsm_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
                                    _P(GlobalResult)]),
+    "optmc_lsm_mlp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
+                                _P(MlpParams), _P(LsmResult)]),
+    "optmc_mlp_init_params": (C.c_int, [C.c_int32, C.c_uint64, C.c_int32, _P(C.c_float)]),
     "optmc_lsm_gram_len": (C.c_int, [C.c_int32]),
     "optmc_lsm_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams)]),
     "optmc_lsm_gram_date": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

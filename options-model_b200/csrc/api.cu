@@ -332,6 +332,27 @@ int optmc_lsm_global(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, i
   OPTMC_TRY_END
 }
 
+int optmc_lsm_mlp(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                  const optmc_lsm_params* lp, const optmc_mlp_params* np, optmc_lsm_result* out) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  if (!lp) { set_error("null argument"); return OPTMC_EINVAL; }
+  optmc_lsm_params l2 = *lp;
+  l2.basis = OPTMC_BASIS_POLY2;  // unused by the network; keeps the shared validation
+  l2.impl = OPTMC_SWEEP_SPLIT;
+  int rc = bind_sweep(ctx, S_dev, ld, M, N, dtype, &l2);
+  if (rc) return rc;
+  rc = lsm_mlp(ctx, np, out);
+  if (rc) return rc;
+  return out ? fetch_results(ctx, out) : OPTMC_OK;
+  OPTMC_TRY_END
+}
+
+int optmc_mlp_init_params(int32_t hidden, uint64_t seed, int32_t date, float* out) {
+  if (hidden != 32 || !out) { set_error("hidden width must be 32"); return OPTMC_EINVAL; }
+  return mlp_init_params_host(seed, date, out);
+}
+
 int optmc_lsm_gram_len(int32_t basis) {
   if (basis == OPTMC_BASIS_POLY2) return 8;
   if (basis == OPTMC_BASIS_POLY3) return 11;

@@ -120,6 +120,10 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
 int lsm_global(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype,
                const optmc_lsm_params* lp, optmc_global_result* out);
 
+// lsm_mlp.cu
+int lsm_mlp(optmc_ctx* ctx, const optmc_mlp_params* np, optmc_lsm_result* out);
+int mlp_init_params_host(unsigned long long seed, int date, float* out);
+
 // european.cu
 int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                           int32_t N, int32_t dtype, int32_t n_options, const double* K, const double* T,

@@ -259,6 +259,30 @@ class Engine:
                     rank=int(res.rank), n_launches=int(res.n_launches), beta=np.array(list(res.beta)), boundary=bnd,
                     ex_count=exc)
 
+    def lsm_mlp(self, S, K, r, T, option_type="put", semantics="reference", hidden=32, epochs=10, lr=1e-3, seed=42,
+                arrays=True, M: Optional[int] = None) -> SweepResult:
+        """Per-date neural-network LSM (om2:277-310): a fresh ContNet per exercise date, full-batch Adam."""
+        assert S.is_cuda and S.dim() == 2 and S.stride(1) == 1
+        N = S.shape[0] - 1
+        M = int(M if M is not None else S.shape[1])
+        lp = self._lsm_params(K, r, T, option_type, "poly2", semantics, "split")
+        npar = L.MlpParams(int(hidden), int(epochs), float(lr), int(seed) & 0xFFFFFFFFFFFFFFFF)
+        code = L.F64 if S.dtype == self.torch.float64 else L.F32
+        res, keep = self._result_block(N, 3, arrays)
+        self._sync_stream()
+        L.check(self.lib.optmc_lsm_mlp(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), C.byref(npar),
+                                       C.byref(res)))
+        return self._to_result(res, keep)
+
+    def mlp_init_params(self, seed: int, date: int, hidden: int = 32) -> np.ndarray:
+        n = 3 * hidden + hidden * hidden + hidden + 1
+        out = np.zeros(n, dtype=np.float32)
+        got = self.lib.optmc_mlp_init_params(hidden, int(seed) & 0xFFFFFFFFFFFFFFFF, int(date),
+                                             out.ctypes.data_as(C.POINTER(C.c_float)))
+        if got != n:
+            L.check(got if got < 0 else L.EINVAL)
+        return out
+
     def lsm_fetch(self, N: int, basis="poly2", arrays=True) -> SweepResult:
         p = 3 if basis in ("poly2", L.BASIS_POLY2) else 4
         res, keep = self._result_block(N, p, arrays)

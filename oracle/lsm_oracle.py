@@ -364,6 +364,49 @@ class PolyRegressor:
         return Phi @ beta, beta
 
 
+class ContNetRegressor:
+    """The reference's per-date network fit (om2:289-306 = om15:159-181 = om1:121-145): standardise the ITM
+    prices (population std), train a fresh ContNet(1 -> H -> H -> 1, ReLU; om2:114-126) with `epochs` full-batch
+    Adam steps on the raw discounted cash-flows, return its in-sample prediction.  Runs on torch CPU in fp32 like
+    the reference.  `init_fn(t)` supplies the flat initial parameters [w1[H] b1[H] W2[H][H] b2[H] w3[H] b3] of date
+    t (the reference uses torch's default initialisation; parity tests pass the engine's Philox weights)."""
+
+    p = 1
+
+    def __init__(self, init_fn, hidden=32, epochs=10, lr=1e-3):
+        self.init_fn, self.H, self.epochs, self.lr = init_fn, hidden, epochs, lr
+        self.last_loss = {}
+
+    def __call__(self, t, t_current, S_itm, Y):
+        import torch
+        from torch import nn, optim
+
+        H = self.H
+        X = np.asarray(S_itm, dtype=np.float64)
+        Xs = (X - X.mean()) / X.std() if X.std() > 0 else X - X.mean()  # om2:289
+        net = nn.Sequential(nn.Linear(1, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU(), nn.Linear(H, 1))
+        p0 = np.asarray(self.init_fn(t), dtype=np.float32)
+        with torch.no_grad():
+            net[0].weight.copy_(torch.from_numpy(p0[0:H].reshape(H, 1)))
+            net[0].bias.copy_(torch.from_numpy(p0[H:2 * H]))
+            net[2].weight.copy_(torch.from_numpy(p0[2 * H:2 * H + H * H].reshape(H, H)))
+            net[2].bias.copy_(torch.from_numpy(p0[2 * H + H * H:3 * H + H * H]))
+            net[4].weight.copy_(torch.from_numpy(p0[3 * H + H * H:4 * H + H * H].reshape(1, H)))
+            net[4].bias.copy_(torch.from_numpy(p0[4 * H + H * H:4 * H + H * H + 1]))
+        opt = optim.Adam(net.parameters(), lr=self.lr)
+        Xt = torch.from_numpy(Xs.reshape(-1, 1)).float()
+        Yt = torch.from_numpy(np.asarray(Y, dtype=np.float64).reshape(-1, 1)).float()
+        for _ in range(self.epochs):
+            loss = nn.MSELoss()(net(Xt), Yt)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            self.last_loss[t] = float(loss.detach())
+        with torch.no_grad():
+            cont = net(Xt).numpy().flatten()
+        return cont.astype(np.float64), None
+
+
 @dataclass
 class SweepResult:
     price: float

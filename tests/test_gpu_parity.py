@@ -596,3 +596,38 @@ def test_global_lsm_full_size_streams_at_hbm_rate(eng, mods):
     assert g["rank"] == 6 and g["n_rows"] > 0.3 * M * (N - 1)
     assert gt["price"] < g["price"] and np.isfinite(g["stderr"])
     assert abs(gt["price"] - eu) < 0.3
+
+
+# ------------------------------------------------------------------------------------------------------
+# per-date neural-network LSM (om2:277-310)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("semantics,epochs", [("reference", 10), ("textbook", 10), ("reference", 40)])
+def test_mlp_lsm_vs_torch_oracle_same_init(eng, mods, semantics, epochs):
+    """optmc_lsm_mlp vs the oracle loop with the reference's torch ContNet fit, both started from the same
+    per-date initial weights (optmc_mlp_init_params).  fp32 network arithmetic on both sides: the fits agree to
+    rounding, so prices match closely and only borderline paths may decide differently."""
+    L, E, orc = mods
+    rng = np.random.default_rng(31)
+    M, N = 8192, 12
+    Z1, Z2 = orc.draw_heston_normals(rng, N, M)
+    S = orc.heston_paths_antithetic(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2)
+    reg = orc.ContNetRegressor(lambda t: eng.mlp_init_params(1234, t), hidden=32, epochs=epochs, lr=1e-3)
+    ref = orc.lsm_sweep(S, 100.0, 0.05, 1.0, "put", regressor=reg, semantics=semantics)
+    res = eng.lsm_mlp(_slab(eng, S, torch.float64), 100.0, 0.05, 1.0, "put", semantics, hidden=32, epochs=epochs, lr=1e-3,
+                      seed=1234)
+    np.testing.assert_array_equal(res.n_itm[N - 1], ref.n_itm[N - 1])
+    assert np.abs(res.ex_count - ref.ex_count).sum() <= 0.002 * M
+    assert res.price == pytest.approx(ref.price, rel=2e-3)
+    assert res.stderr == pytest.approx(ref.stderr, rel=1e-2)
+
+
+def test_mlp_init_matches_torch_default_range(eng):
+    """Initial weights are uniform in torch's default nn.Linear range: (-1, 1) for fan-in 1, +-1/sqrt(32) else."""
+    p = np.concatenate([eng.mlp_init_params(7, t) for t in range(1, 40)]).reshape(39, -1)
+    H = 32
+    first, rest = p[:, :2 * H], p[:, 2 * H:]
+    assert np.abs(first).max() < 1.0 and np.abs(first).max() > 0.95
+    b = 1 / np.sqrt(H)
+    assert np.abs(rest).max() < b and np.abs(rest).max() > 0.95 * b
+    assert abs(rest.mean()) < 0.01 * b and abs(rest.std() - b / np.sqrt(3)) < 0.01 * b
+    assert not np.array_equal(p[0], p[1])  # a fresh network per date
