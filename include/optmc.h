@@ -191,7 +191,7 @@ int optmc_lsm_global(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, i
  *      the reference statistically; fed the same initial weights (optmc_mlp_init_params) the fit is reproducible
  *      to fp32 rounding.  Results through optmc_lsm_result (betas are NaN). */
 typedef struct optmc_mlp_params {
-  int32_t hidden;  /* 32 (om2 default nn_hidden) */
+  int32_t hidden;  /* 32 (om2 default nn_hidden; fp32 CUDA cores) or 128 (om3 default nn_hidden; bf16 tcgen05) */
   int32_t epochs;  /* om2 default nn_epochs = 10 */
   double lr;       /* om2 default nn_lr = 1e-3 */
   uint64_t seed;   /* Philox key of the per-date initial weights */
@@ -202,6 +202,11 @@ int optmc_lsm_mlp(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int3
 /* The initial parameters of date `date`: host out[3 H + H^2 + H + 1] in the order w1[H] b1[H] W2[H][H] b2[H] w3[H] b3.
  * Returns the parameter count, or a negative status. */
 int optmc_mlp_init_params(int32_t hidden, uint64_t seed, int32_t date, float* out);
+/* Test aid: one full-batch gradient evaluation of the ContNet on n host rows (xs, ys) at host `params`:
+ * grads[P] = d(mean squared error)/d(params), cont[n] = forward output.  hidden = 32 runs the fp32 CUDA-core
+ * kernels, hidden = 128 the bf16 tcgen05 kernels (fp32 accumulation in tensor memory). */
+int optmc_mlp_grad_debug(optmc_ctx* ctx, int32_t hidden, int64_t n, const float* xs, const float* ys, const float* params,
+                         float* grads, float* cont);
 
 /* Per-date building blocks for path-sharded multi-GPU sweeps: the host all-reduces `gram_dev`
  * (optmc_lsm_gram_len doubles) between the two calls. */

@@ -94,6 +94,8 @@ PROTOTYPES = {
     "optmc_lsm_mlp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
                                 _P(MlpParams), _P(LsmResult)]),
     "optmc_mlp_init_params": (C.c_int, [C.c_int32, C.c_uint64, C.c_int32, _P(C.c_float)]),
+    "optmc_mlp_grad_debug": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, _P(C.c_float), _P(C.c_float), _P(C.c_float),
+                                       _P(C.c_float), _P(C.c_float)]),
     "optmc_lsm_gram_len": (C.c_int, [C.c_int32]),
     "optmc_lsm_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams)]),
     "optmc_lsm_gram_date": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

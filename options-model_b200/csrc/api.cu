@@ -349,8 +349,16 @@ int optmc_lsm_mlp(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int3
 }
 
 int optmc_mlp_init_params(int32_t hidden, uint64_t seed, int32_t date, float* out) {
-  if (hidden != 32 || !out) { set_error("hidden width must be 32"); return OPTMC_EINVAL; }
-  return mlp_init_params_host(seed, date, out);
+  if ((hidden != 32 && hidden != 128) || !out) { set_error("hidden width must be 32 or 128"); return OPTMC_EINVAL; }
+  return mlp_init_params_host(hidden, seed, date, out);
+}
+
+int optmc_mlp_grad_debug(optmc_ctx* ctx, int32_t hidden, int64_t n, const float* xs, const float* ys, const float* params,
+                         float* grads, float* cont) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return mlp_grad_debug(ctx, hidden, n, xs, ys, params, grads, cont);
+  OPTMC_TRY_END
 }
 
 int optmc_lsm_gram_len(int32_t basis) {

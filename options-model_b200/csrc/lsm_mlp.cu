@@ -15,6 +15,7 @@
 //              mlp_adam_kernel  one CTA: decode the gradient sums, Adam step, clear the accumulators }
 //   mlp_decide_kernel   continuation = net(x); exercise iff payoff > continuation; scatter to the cash-flows
 // The network arithmetic is fp32, as in the reference (`.float()`, om2:296-297).
+#include <cuda_bf16.h>
 #include <math.h>
 #include <string.h>
 
@@ -82,7 +83,8 @@ mlp_count_kernel(const R* __restrict__ S_t, const R* __restrict__ cf, long long 
 // ---- 2. scan + standardisation + fresh network ------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 mlp_scan_kernel(unsigned int* block_count, int nblocks, unsigned long long* mom_fx, MlpState* st, float* params,
-                float* adam_m, float* adam_v, unsigned long long* grad_fx, unsigned long long seed, int date) {
+                float* adam_m, float* adam_v, unsigned long long* grad_fx, unsigned long long seed, int date, int H) {
+  const int P = 3 * H + H * H + H + 1;
   __shared__ unsigned long long s_part[1024];
   __shared__ unsigned long long s_base;
   const int tid = threadIdx.x;
@@ -122,15 +124,16 @@ mlp_scan_kernel(unsigned int* block_count, int nblocks, unsigned long long* mom_
     for (int i = 0; i < 5; ++i) mom_fx[i] = 0ull;
   }
   // fresh parameters: torch.nn.Linear default init = U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weights and biases
-  for (int i = tid; i < kMP; i += blockDim.x) {
+  const float hb = rsqrtf((float)H);
+  for (int i = tid; i < P; i += blockDim.x) {
     const Philox4 p = philox_for((unsigned long long)i, (unsigned int)date, 0x4D4C50u, seed);
     const float u = ((float)(p.v[0] >> 8) + 0.5f) * (2.0f / 16777216.0f) - 1.0f;  // (-1, 1)
-    const float bound = (i < oW2) ? 1.0f : 0.17677669529663687f;                   // fan_in 1 | fan_in H = 32
+    const float bound = (i < 2 * H) ? 1.0f : hb;                                   // fan_in 1 | fan_in H
     params[i] = u * bound;
     adam_m[i] = 0.f; adam_v[i] = 0.f;
-    grad_fx[2 * i] = 0ull; grad_fx[2 * i + 1] = 0ull;
+    if (grad_fx) { grad_fx[2 * i] = 0ull; grad_fx[2 * i + 1] = 0ull; }
   }
-  if (tid == 0) { grad_fx[2 * kMP] = 0ull; grad_fx[2 * kMP + 1] = 0ull; grad_fx[2 * kMP + 2] = 0ull; }
+  if (tid == 0 && grad_fx) { grad_fx[2 * P] = 0ull; grad_fx[2 * P + 1] = 0ull; grad_fx[2 * P + 2] = 0ull; }
 }
 
 // ---- 3. compaction ----------------------------------------------------------------------------------------
@@ -362,9 +365,425 @@ mlp_decide_kernel(const float* __restrict__ params, const float* __restrict__ xs
   }
 }
 
+__global__ void __launch_bounds__(kMThreads, 1)
+mlp_forward_kernel(const float* __restrict__ params, const float* __restrict__ xs, const MlpState* __restrict__ st, float* cont) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MlpSmem& sm = *reinterpret_cast<MlpSmem*>(smem_raw);
+  const long long n = st->n_live;
+  if ((long long)blockIdx.x * kMTile >= n) return;
+  mlp_load_params(sm, params);
+  __syncthreads();
+  for (long long r = (long long)blockIdx.x * kMTile + threadIdx.x; r < n; r += (long long)gridDim.x * kMTile) {
+    float h1[kMH], h2[kMH];
+    cont[r] = mlp_forward_row(sm, xs[r], h1, h2);
+  }
+}
+
 __global__ void mlp_nitm_kernel(const MlpState* st, long long* nitm_t, double* loss_t) {
   *nitm_t = st->n_live;
   if (loss_t) *loss_t = st->loss;
+}
+
+
+// =================================================================================================================
+// Tensor-core path: hidden = 128 (the reference's default nn_hidden in om3:340-358).  The three 128 x 128 x 128
+// contractions of a 128-row tile run on tcgen05 (bf16 operands staged in shared memory, fp32 accumulators in
+// tensor memory); the vector gradients are three more N = 16 MMAs against a small [1, x, dout] panel:
+//   Z2   = H1 W2^T          (A = H1 tile K-major,  B = W2 tile K-major)           -> TMEM cols [0,128)
+//   dH1  = dZ2 W2           (A = dZ2 tile K-major, B = W2 tile MN-major view)     -> TMEM cols [0,128) (Z2 is consumed)
+//   dW2 += dZ2^T H1         (A = dZ2 MN-major view, B = H1 MN-major view)         -> TMEM cols [128,256), across tiles
+//   [db2 .]       += dZ2^T P,  [. . dw3] += H2^T P,  [db1 dw1 .] += dH1'^T P      -> TMEM cols [256,304)
+// Every tile is stored once in the NO-SWIZZLE core-matrix layout (8 x 8 cores of 128 contiguous bytes, k-cores 128 B
+// apart, 8-row groups 2048 B apart), which serves as a K-major operand [row][col] and, with LBO / SBO exchanged, as
+// an MN-major operand [col][row] -- no transposed copies (validated by tools/umma_test.cu).  One thread per row
+// (TMEM lane), one elected thread issues the MMAs, completion through tcgen05.commit -> mbarrier.
+// =================================================================================================================
+constexpr int kTH = 128;
+constexpr int kTP = 3 * kTH + kTH * kTH + kTH + 1;  // 16897
+constexpr int tW1 = 0, tB1 = kTH, tW2 = 2 * kTH, tB2 = 2 * kTH + kTH * kTH, tW3 = tB2 + kTH, tB3 = tW3 + kTH;
+constexpr int kTcThreads = 128;
+constexpr int kTileBytes = kTH * kTH * 2;  // 32 KB
+constexpr int kAuxBytes = 128 * 16 * 2;    // 4 KB panel [row][16]
+
+struct TcSmem {
+  unsigned char T1[kTileBytes], T2[kTileBytes], T3[kTileBytes], T4[kTileBytes], W2[kTileBytes];
+  unsigned char aux[2][kAuxBytes];
+  float w1[kTH], b1[kTH], b2[kTH], w3[kTH];
+  float b3;
+  float red[8];
+  unsigned long long bar;
+  unsigned int tmem;
+};
+
+__device__ __forceinline__ int core_off(int row, int col) {  // bytes; [128][128] bf16 tile
+  return (row >> 3) * 2048 + (col >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2;
+}
+__device__ __forceinline__ int aux_off(int row, int col) {   // bytes; [128][16] bf16 panel
+  return (row >> 3) * 256 + (col >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2;
+}
+__device__ __forceinline__ unsigned long long umma_desc(unsigned int saddr, unsigned int lbo, unsigned int sbo) {
+  return (unsigned long long)((saddr >> 4) & 0x3fff) | ((unsigned long long)((lbo >> 4) & 0x3fff) << 16) |
+         ((unsigned long long)((sbo >> 4) & 0x3fff) << 32) | (1ull << 46);  // version 1, no swizzle
+}
+__device__ __forceinline__ unsigned int umma_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(a_mn & 1) << 15) | ((unsigned)(b_mn & 1) << 16) |
+         ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);  // f32 accumulate, bf16 x bf16
+}
+__device__ __forceinline__ void umma_f16(unsigned int d_tmem, unsigned long long a, unsigned long long b, unsigned int idesc,
+                                         unsigned int acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned int taddr, float (&v)[32]) {
+  unsigned int r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(unsigned int taddr, float (&v)[16]) {
+  unsigned int r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
+  uint4 u;
+  u.x = ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v[1])) << 16) | __bfloat16_as_ushort(__float2bfloat16_rn(v[0]));
+  u.y = ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v[3])) << 16) | __bfloat16_as_ushort(__float2bfloat16_rn(v[2]));
+  u.z = ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v[5])) << 16) | __bfloat16_as_ushort(__float2bfloat16_rn(v[4]));
+  u.w = ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v[7])) << 16) | __bfloat16_as_ushort(__float2bfloat16_rn(v[6]));
+  return u;
+}
+__device__ __forceinline__ void tc_bar_wait(unsigned long long* bar, unsigned int parity) {
+  mbar_wait(reinterpret_cast<uint64_t*>(bar), parity);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// order this thread's shared-memory tile writes (generic proxy) and TMEM reads before the barrier that precedes the
+// next MMA issue (async proxy)
+__device__ __forceinline__ void tc_publish() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+}
+
+// setup shared by the training and the inference kernel: weights -> bf16 core layout, TMEM allocation, mbarrier
+__device__ __forceinline__ unsigned int tc_setup(TcSmem& sm, const float* __restrict__ params, int tmem_cols_log) {
+  const int tid = threadIdx.x;
+  {  // thread j stages row j of W2
+#pragma unroll 4
+    for (int c = 0; c < 16; ++c) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = params[tW2 + tid * kTH + c * 8 + k];
+      *reinterpret_cast<uint4*>(sm.W2 + core_off(tid, c * 8)) = pack8_bf16(v);
+    }
+    sm.w1[tid] = params[tW1 + tid]; sm.b1[tid] = params[tB1 + tid]; sm.b2[tid] = params[tB2 + tid]; sm.w3[tid] = params[tW3 + tid];
+    if (tid == 0) sm.b3 = params[tB3];
+    // panels: [1, x, dout, 0 ...]; the constant and zero columns are written once
+    for (int b = 0; b < 2; ++b) {
+      *reinterpret_cast<uint4*>(sm.aux[b] + aux_off(tid, 0)) = make_uint4(0x00003f80u, 0u, 0u, 0u);  // bf16 1.0 in column 0
+      *reinterpret_cast<uint4*>(sm.aux[b] + aux_off(tid, 8)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  if ((tid >> 5) == 0) {
+    if (tmem_cols_log == 9)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem)), "n"(512));
+    else
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem)), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(reinterpret_cast<uint64_t*>(&sm.bar), 1);
+    mbar_fence_init();
+  }
+  tc_publish();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return sm.tmem;
+}
+
+// S1: h1 = relu(w1 x + b1) -> bf16 H1 tile; returns the h1 > 0 mask
+__device__ __forceinline__ void tc_layer1(TcSmem& sm, float x, int row, unsigned int (&mask1)[4]) {
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float h = fmaf(sm.w1[c * 8 + k], x, sm.b1[c * 8 + k]);
+      v[k] = fmaxf(h, 0.f);
+      if (h > 0.f) mask1[c >> 2] |= 1u << ((c & 3) * 8 + k);
+    }
+    *reinterpret_cast<uint4*>(sm.T1 + core_off(row, c * 8)) = pack8_bf16(v);
+  }
+}
+
+__device__ __forceinline__ void tc_issue_layer2(TcSmem& sm, unsigned int tmem) {  // Z2 = H1 W2^T
+  const unsigned int a0 = smem_u32(sm.T1), b0 = smem_u32(sm.W2);
+  const unsigned int id = umma_idesc(128, 128, 0, 0);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) umma_f16(tmem, umma_desc(a0 + k * 256, 128, 2048), umma_desc(b0 + k * 256, 128, 2048), id, k > 0);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+mlp_tc_grad_kernel(const float* __restrict__ params, const float* __restrict__ xs, const float* __restrict__ ys,
+                   const MlpState* __restrict__ st, float* __restrict__ gpart) {
+  extern __shared__ __align__(1024) unsigned char smem_tc[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_tc);
+  const long long n = st->n_live;
+  const long long ntiles = (n + 127) / 128;
+  if ((long long)blockIdx.x >= ntiles) return;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const unsigned int tmem = tc_setup(sm, params, 9);
+  const unsigned int lane_base = (unsigned int)(warp * 32) << 16;
+  const unsigned int cZ = 0, cW = 128, cV1 = 256, cV2 = 272, cV3 = 288;
+  const float inv_n2 = (float)(2.0 / (double)n);
+  unsigned int phase = 0;
+  float loss = 0.f, gb3 = 0.f;
+  int local = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++local) {
+    const long long r = tile * 128 + tid;
+    const bool act = r < n;
+    const float x = act ? xs[r] : 0.f, y = act ? ys[r] : 0.f;
+    unsigned char* aux = sm.aux[local & 1];
+    unsigned int mask1[4] = {0u, 0u, 0u, 0u}, mask2[4] = {0u, 0u, 0u, 0u};
+    tc_layer1(sm, x, tid, mask1);
+    *reinterpret_cast<unsigned short*>(aux + aux_off(tid, 1)) = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+    tc_publish();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (local > 0) {  // vector gradients of the previous tile's first layer: [db1 dw1 .] += dH1'^T P(prev)
+        const unsigned int a0 = smem_u32(sm.T4), p0 = smem_u32(sm.aux[(local - 1) & 1]);
+        const unsigned int idv = umma_idesc(128, 16, 1, 1);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_f16(tmem + cV1, umma_desc(a0 + k * 4096, 2048, 128), umma_desc(p0 + k * 512, 256, 128), idv, (local > 1) || k > 0);
+      }
+      tc_issue_layer2(sm, tmem + cZ);
+      umma_commit(&sm.bar);
+    }
+    tc_bar_wait(&sm.bar, phase); phase ^= 1u;
+    // S2a: output and H2 tile
+    float out = sm.b3;
+#pragma unroll
+    for (int c0 = 0; c0 < 4; ++c0) {
+      float z[32];
+      tmem_ld32(tmem + lane_base + cZ + c0 * 32, z);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int j = c0 * 32 + q * 8 + k;
+          const float h = z[q * 8 + k] + sm.b2[j];
+          v[k] = fmaxf(h, 0.f);
+          if (h > 0.f) mask2[c0] |= 1u << (q * 8 + k);
+          out = fmaf(sm.w3[j], v[k], out);
+        }
+        *reinterpret_cast<uint4*>(sm.T3 + core_off(tid, c0 * 32 + q * 8)) = pack8_bf16(v);
+      }
+    }
+    const float err = act ? out - y : 0.f;
+    const float dout = err * inv_n2;
+    loss = fmaf(err, err, loss);
+    gb3 += dout;
+    // S2b: dZ2 tile and the dout column of the panel
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = ((mask2[c >> 2] >> ((c & 3) * 8 + k)) & 1u) ? dout * sm.w3[c * 8 + k] : 0.f;
+      *reinterpret_cast<uint4*>(sm.T2 + core_off(tid, c * 8)) = pack8_bf16(v);
+    }
+    *reinterpret_cast<unsigned short*>(aux + aux_off(tid, 2)) = __bfloat16_as_ushort(__float2bfloat16_rn(dout));
+    tc_publish();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const unsigned int t1 = smem_u32(sm.T1), t2 = smem_u32(sm.T2), t3 = smem_u32(sm.T3), w2 = smem_u32(sm.W2), p0 = smem_u32(aux);
+      const unsigned int id_kmn = umma_idesc(128, 128, 0, 1), id_mm = umma_idesc(128, 128, 1, 1), idv = umma_idesc(128, 16, 1, 1);
+      const unsigned int accT = local > 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // dH1 = dZ2 W2
+        umma_f16(tmem + cZ, umma_desc(t2 + k * 256, 128, 2048), umma_desc(w2 + k * 4096, 2048, 128), id_kmn, k > 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // dW2 += dZ2^T H1
+        umma_f16(tmem + cW, umma_desc(t2 + k * 4096, 2048, 128), umma_desc(t1 + k * 4096, 2048, 128), id_mm, accT || k > 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // [db2 . .] += dZ2^T P
+        umma_f16(tmem + cV2, umma_desc(t2 + k * 4096, 2048, 128), umma_desc(p0 + k * 512, 256, 128), idv, accT || k > 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)  // [. . dw3] += H2^T P
+        umma_f16(tmem + cV3, umma_desc(t3 + k * 4096, 2048, 128), umma_desc(p0 + k * 512, 256, 128), idv, accT || k > 0);
+      umma_commit(&sm.bar);
+    }
+    tc_bar_wait(&sm.bar, phase); phase ^= 1u;
+    // S3: dH1' = dH1 (h1 > 0) tile
+#pragma unroll
+    for (int c0 = 0; c0 < 4; ++c0) {
+      float d[32];
+      tmem_ld32(tmem + lane_base + cZ + c0 * 32, d);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = ((mask1[c0] >> (q * 8 + k)) & 1u) ? d[q * 8 + k] : 0.f;
+        *reinterpret_cast<uint4*>(sm.T4 + core_off(tid, c0 * 32 + q * 8)) = pack8_bf16(v);
+      }
+    }
+  }
+  // tail: first-layer vector gradients of the last tile
+  tc_publish();
+  if (tid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned int a0 = smem_u32(sm.T4), p0 = smem_u32(sm.aux[(local - 1) & 1]);
+    const unsigned int idv = umma_idesc(128, 16, 1, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      umma_f16(tmem + cV1, umma_desc(a0 + k * 4096, 2048, 128), umma_desc(p0 + k * 512, 256, 128), idv, (local > 1) || k > 0);
+    umma_commit(&sm.bar);
+  }
+  tc_bar_wait(&sm.bar, phase); phase ^= 1u;
+  // read-out: thread j owns TMEM lane j = unit j
+  float* gp = gpart + (size_t)blockIdx.x * (kTP + 1);
+#pragma unroll
+  for (int c0 = 0; c0 < 4; ++c0) {
+    float w[32];
+    tmem_ld32(tmem + lane_base + cW + c0 * 32, w);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) gp[tW2 + tid * kTH + c0 * 32 + i] = w[i];
+  }
+  {
+    float v1[16], v2[16], v3[16];
+    tmem_ld16(tmem + lane_base + cV1, v1);
+    tmem_ld16(tmem + lane_base + cV2, v2);
+    tmem_ld16(tmem + lane_base + cV3, v3);
+    gp[tB1 + tid] = v1[0]; gp[tW1 + tid] = v1[1]; gp[tB2 + tid] = v2[0]; gp[tW3 + tid] = v3[2];
+  }
+  {  // scalars: db3 and the loss
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) { gb3 += __shfl_xor_sync(0xffffffffu, gb3, m); loss += __shfl_xor_sync(0xffffffffu, loss, m); }
+    if ((tid & 31) == 0) { sm.red[warp] = gb3; sm.red[4 + warp] = loss; }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tid == 0) {
+    gp[tB3] = (sm.red[0] + sm.red[1]) + (sm.red[2] + sm.red[3]);
+    gp[kTP] = (sm.red[4] + sm.red[5]) + (sm.red[6] + sm.red[7]);
+  }
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// Adam for the tensor-core path: deterministic fixed-order sum of the per-CTA partial gradients
+__global__ void __launch_bounds__(256)
+mlp_tc_adam_kernel(float* params, float* adam_m, float* adam_v, const float* __restrict__ gpart, MlpState* st, float lr,
+                   int grid_rows) {
+  const long long n = st->n_live;
+  if (n <= 0) return;
+  const long long ntiles = (n + 127) / 128;
+  const int nb = (int)(ntiles < grid_rows ? ntiles : grid_rows);
+  const int step = st->step + 1;
+  const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+  const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kTP) {
+    float g = 0.f;
+    for (int b = 0; b < nb; ++b) g += gpart[(size_t)b * (kTP + 1) + i];
+    const float m = b1 * adam_m[i] + (1.0f - b1) * g;
+    const float v = b2 * adam_v[i] + (1.0f - b2) * g * g;
+    adam_m[i] = m; adam_v[i] = v;
+    params[i] -= (lr / bc1) * (m / (sqrtf(v) / sqrtf(bc2) + eps));
+  }
+}
+__global__ void mlp_tc_step_kernel(MlpState* st, const float* __restrict__ gpart, int grid_rows) {
+  const long long n = st->n_live;
+  if (n <= 0) return;
+  const long long ntiles = (n + 127) / 128;
+  const int nb = (int)(ntiles < grid_rows ? ntiles : grid_rows);
+  double l = 0.0;
+  for (int b = 0; b < nb; ++b) l += (double)gpart[(size_t)b * (kTP + 1) + kTP];
+  st->loss = l / (double)n;
+  st->step += 1;
+}
+
+// continuation = net(x) on tensor cores, then the exercise decision (strict '>', om2:304)
+template <typename R>
+__global__ void __launch_bounds__(kTcThreads, 1)
+mlp_tc_decide_kernel(const float* __restrict__ params, const float* __restrict__ xs, const unsigned int* __restrict__ idx,
+                     const MlpState* __restrict__ st, const R* __restrict__ S_t, R* cf, double K, double Kh, double Kl,
+                     int is_put, int sticky, R dinv, float* cont_out, unsigned long long* exc_t, unsigned long long* bnd_t) {
+  extern __shared__ __align__(1024) unsigned char smem_tc[];
+  TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_tc);
+  const long long n = st->n_live;
+  const long long ntiles = (n + 127) / 128;
+  if ((long long)blockIdx.x >= ntiles) return;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const unsigned int tmem = tc_setup(sm, params, 7);
+  const unsigned int lane_base = (unsigned int)(warp * 32) << 16;
+  const R sgn = is_put ? (R)-1 : (R)1;
+  const R c1 = (R)(is_put ? Kh : -Kh), c2 = (R)(is_put ? Kl : -Kl);
+  unsigned int phase = 0, cnt = 0;
+  unsigned long long bnd = bnd_none(is_put);
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long r = tile * 128 + tid;
+    const bool act = r < n;
+    unsigned int mask1[4] = {0u, 0u, 0u, 0u};
+    tc_layer1(sm, act ? xs[r] : 0.f, tid, mask1);
+    tc_publish();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tc_issue_layer2(sm, tmem);
+      umma_commit(&sm.bar);
+    }
+    tc_bar_wait(&sm.bar, phase); phase ^= 1u;
+    float out = sm.b3;
+#pragma unroll
+    for (int c0 = 0; c0 < 4; ++c0) {
+      float z[32];
+      tmem_ld32(tmem + lane_base + c0 * 32, z);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) out = fmaf(sm.w3[c0 * 32 + k], fmaxf(z[k] + sm.b2[c0 * 32 + k], 0.f), out);
+    }
+    if (act) {
+      if (cont_out) cont_out[r] = out;
+      if (idx) {
+        const unsigned int j = idx[r];
+        const R sr = S_t[j];
+        const double s = (double)sr;
+        const double pay = payoff<double>(s, K, is_put != 0);
+        if (pay > (double)out) {
+          const R a = (fma(sgn, sr, c1) + c2) * dinv;  // payoff in date-N money
+          cf[j] = sticky ? -a : a;
+          cnt++;
+          const unsigned long long b = (unsigned long long)__double_as_longlong(s);
+          bnd = is_put ? (b > bnd ? b : bnd) : (b < bnd ? b : bnd);
+        }
+      }
+    }
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  bnd = is_put ? warp_max_u64(bnd) : warp_min_u64(bnd);
+  if ((tid & 31) == 0 && cnt && exc_t) {
+    atomicAdd(exc_t, (unsigned long long)cnt);
+    if (is_put) atomicMax(bnd_t, bnd); else atomicMin(bnd_t, bnd);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(128));
 }
 
 // ---- host driver --------------------------------------------------------------------------------------------
@@ -410,7 +829,7 @@ template <typename R> static int lsm_mlp_t(optmc_ctx* ctx, const optmc_mlp_param
   for (int t = N - 1; t >= 1; --t) {
     const R* S_t = Sr + (size_t)t * sw.ld;
     mlp_count_kernel<R><<<nblocks, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, d_cnt, d_mom);
-    mlp_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, nblocks, d_mom, d_st, d_par, d_m, d_v, d_g, np_->seed, t);
+    mlp_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, nblocks, d_mom, d_st, d_par, d_m, d_v, d_g, np_->seed, t, kMH);
     mlp_compact_kernel<R><<<nblocks, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, sw.Dt[t], d_cnt,
                                                                   d_st, d_xs, d_ys, d_idx);
     for (int e = 0; e < np_->epochs; ++e) {
@@ -434,23 +853,163 @@ template <typename R> static int lsm_mlp_t(optmc_ctx* ctx, const optmc_mlp_param
   return OPTMC_OK;
 }
 
+
+template <typename R> static int lsm_mlp_tc_t(optmc_ctx* ctx, const optmc_mlp_params* np_, optmc_lsm_result* out) {
+  SweepDesc& sw = ctx->sw;
+  const long long M = sw.M;
+  const int N = sw.N;
+  const int nblocks = (int)((M + kMThreads - 1) / kMThreads);
+  const bool sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) != 0;
+  long long tiles = (M + 127) / 128;
+  const int grid_rows = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);  // one CTA per SM (tiles + TMEM)
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_cnt = take((size_t)nblocks * 4), o_xs = take((size_t)M * 4), o_ys = take((size_t)M * 4),
+               o_idx = take((size_t)M * 4), o_par = take(kTP * 4), o_m = take(kTP * 4), o_v = take(kTP * 4),
+               o_g = take((size_t)grid_rows * (kTP + 1) * 4), o_mom = take(5 * 8), o_st = take(sizeof(MlpState)),
+               o_loss = take((size_t)(N + 1) * 8);
+  int rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
+  if (rc) return rc;
+  char* dev = static_cast<char*>(ctx->batch_dev);
+  unsigned int* d_cnt = reinterpret_cast<unsigned int*>(dev + o_cnt);
+  float* d_xs = reinterpret_cast<float*>(dev + o_xs);
+  float* d_ys = reinterpret_cast<float*>(dev + o_ys);
+  unsigned int* d_idx = reinterpret_cast<unsigned int*>(dev + o_idx);
+  float* d_par = reinterpret_cast<float*>(dev + o_par);
+  float* d_m = reinterpret_cast<float*>(dev + o_m);
+  float* d_v = reinterpret_cast<float*>(dev + o_v);
+  float* d_g = reinterpret_cast<float*>(dev + o_g);
+  unsigned long long* d_mom = reinterpret_cast<unsigned long long*>(dev + o_mom);
+  MlpState* d_st = reinterpret_cast<MlpState*>(dev + o_st);
+  double* d_loss = reinterpret_cast<double*>(dev + o_loss);
+  OPTMC_CUDA(cudaMemsetAsync(d_mom, 0, 5 * 8, ctx->stream));
+  OPTMC_CUDA(cudaMemsetAsync(d_loss, 0, (size_t)(N + 1) * 8, ctx->stream));
+  rc = sweep_begin(ctx);
+  if (rc) return rc;
+  const R* Sr = static_cast<const R*>(sw.S);
+  R* cf = static_cast<R*>(ctx->cf);
+  const size_t smem = sizeof(TcSmem) + 1024;
+  OPTMC_CUDA(cudaFuncSetAttribute(mlp_tc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  OPTMC_CUDA(cudaFuncSetAttribute(mlp_tc_decide_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int adam_grid = (kTP + 255) / 256;
+  for (int t = N - 1; t >= 1; --t) {
+    const R* S_t = Sr + (size_t)t * sw.ld;
+    mlp_count_kernel<R><<<nblocks, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, d_cnt, d_mom);
+    mlp_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, nblocks, d_mom, d_st, d_par, d_m, d_v, nullptr, np_->seed, t, kTH);
+    mlp_compact_kernel<R><<<nblocks, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, sw.Dt[t], d_cnt,
+                                                                  d_st, d_xs, d_ys, d_idx);
+    for (int e = 0; e < np_->epochs; ++e) {
+      mlp_tc_grad_kernel<<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_xs, d_ys, d_st, d_g);
+      mlp_tc_adam_kernel<<<adam_grid, 256, 0, ctx->stream>>>(d_par, d_m, d_v, d_g, d_st, (float)np_->lr, grid_rows);
+      mlp_tc_step_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_g, grid_rows);
+    }
+    mlp_tc_decide_kernel<R><<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_xs, d_idx, d_st, S_t, cf, sw.lp.K, sw.Kh,
+                                                                         sw.Kl, sw.lp.is_put, sticky, (R)sw.Dinv[t], nullptr,
+                                                                         ctx->d_exc + t, ctx->d_bnd + t);
+    mlp_nitm_kernel<<<1, 1, 0, ctx->stream>>>(d_st, ctx->d_nitm + t, d_loss + t);
+    ctx->launches += 5 + 3 * np_->epochs; sw.n_launches += 5 + 3 * np_->epochs;
+  }
+  OPTMC_CUDA(cudaGetLastError());
+  rc = sweep_finish(ctx, ctx->gram);
+  if (rc) return rc;
+  rc = sweep_finalize_price(ctx, ctx->gram);
+  if (rc) return rc;
+  sw.impl_used = OPTMC_SWEEP_SPLIT;
+  sw.have_results = true;
+  (void)out;
+  return OPTMC_OK;
+}
+
+__global__ void mlp_set_state_kernel(MlpState* st, long long n) { st->n_live = n; st->mean = 0.0; st->inv_std = 1.0; st->loss = 0.0; st->step = 0; }
+__global__ void mlp_fx_to_float_kernel(const unsigned long long* grad_fx, float* out, int P) {
+  const int nb = (int)grad_fx[2 * P + 2];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) out[i] = nb ? (float)fx_decode(grad_fx[2 * i], grad_fx[2 * i + 1], nb) : 0.f;
+}
+__global__ void mlp_sum_partials_kernel(const float* gpart, int nb, float* out, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  float g = 0.f;
+  for (int b = 0; b < nb; ++b) g += gpart[(size_t)b * (P + 1) + i];
+  out[i] = g;
+}
+
+// Test aid (optmc_mlp_grad_debug): one gradient evaluation + forward on n host rows.
+int mlp_grad_debug(optmc_ctx* ctx, int H, long long n, const float* xs, const float* ys, const float* params, float* grads,
+                   float* cont) {
+  if ((H != kMH && H != kTH) || n <= 0 || !xs || !ys || !params) { set_error("bad arguments"); return OPTMC_EINVAL; }
+  const int P = 3 * H + H * H + H + 1;
+  const int tile = H == kTH ? 128 : kMTile;
+  long long tiles = (n + tile - 1) / tile;
+  const int grid_rows = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_xs = take((size_t)n * 4), o_ys = take((size_t)n * 4), o_cont = take((size_t)n * 4), o_par = take((size_t)P * 4),
+               o_out = take((size_t)P * 4), o_g = take(H == kTH ? (size_t)grid_rows * (P + 1) * 4 : (size_t)(2 * P + 3) * 8),
+               o_st = take(sizeof(MlpState));
+  int rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
+  if (rc) return rc;
+  char* dev = static_cast<char*>(ctx->batch_dev);
+  float* d_xs = reinterpret_cast<float*>(dev + o_xs);
+  float* d_ys = reinterpret_cast<float*>(dev + o_ys);
+  float* d_cont = reinterpret_cast<float*>(dev + o_cont);
+  float* d_par = reinterpret_cast<float*>(dev + o_par);
+  float* d_out = reinterpret_cast<float*>(dev + o_out);
+  MlpState* d_st = reinterpret_cast<MlpState*>(dev + o_st);
+  OPTMC_CUDA(cudaMemcpyAsync(d_xs, xs, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  OPTMC_CUDA(cudaMemcpyAsync(d_ys, ys, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  OPTMC_CUDA(cudaMemcpyAsync(d_par, params, (size_t)P * 4, cudaMemcpyHostToDevice, ctx->stream));
+  mlp_set_state_kernel<<<1, 1, 0, ctx->stream>>>(d_st, n);
+  if (H == kTH) {
+    float* d_g = reinterpret_cast<float*>(dev + o_g);
+    const size_t smem = sizeof(TcSmem) + 1024;
+    OPTMC_CUDA(cudaFuncSetAttribute(mlp_tc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OPTMC_CUDA(cudaFuncSetAttribute(mlp_tc_decide_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_tc_grad_kernel<<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_xs, d_ys, d_st, d_g);
+    mlp_sum_partials_kernel<<<(P + 255) / 256, 256, 0, ctx->stream>>>(d_g, grid_rows, d_out, P);
+    mlp_tc_decide_kernel<float><<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_xs, nullptr, d_st, nullptr, nullptr, 1.0, 1.0,
+                                                                             0.0, 1, 0, 1.0f, d_cont, nullptr, nullptr);
+    ctx->launches += 4;
+  } else {
+    unsigned long long* d_g = reinterpret_cast<unsigned long long*>(dev + o_g);
+    OPTMC_CUDA(cudaMemsetAsync(d_g, 0, (size_t)(2 * P + 3) * 8, ctx->stream));
+    const size_t smem = sizeof(MlpSmem);
+    OPTMC_CUDA(cudaFuncSetAttribute(mlp_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OPTMC_CUDA(cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_grad_kernel<<<grid_rows, kMThreads, smem, ctx->stream>>>(d_par, d_xs, d_ys, d_st, d_g);
+    mlp_fx_to_float_kernel<<<1, 256, 0, ctx->stream>>>(d_g, d_out, P);
+    mlp_forward_kernel<<<grid_rows, kMThreads, smem, ctx->stream>>>(d_par, d_xs, d_st, d_cont);
+    ctx->launches += 4;
+  }
+  OPTMC_CUDA(cudaGetLastError());
+  if (grads) OPTMC_CUDA(cudaMemcpyAsync(grads, d_out, (size_t)P * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cont) OPTMC_CUDA(cudaMemcpyAsync(cont, d_cont, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OPTMC_OK;
+}
+
 int lsm_mlp(optmc_ctx* ctx, const optmc_mlp_params* np_, optmc_lsm_result* out) {
   if (!np_) { set_error("null argument"); return OPTMC_EINVAL; }
-  if (np_->hidden != kMH) { set_error("per-date MLP: hidden width must be 32 (om2 default nn_hidden)"); return OPTMC_EUNSUPPORTED; }
+  if (np_->hidden != kMH && np_->hidden != kTH) {
+    set_error("per-date MLP: hidden width must be 32 (CUDA cores; om2 default nn_hidden) or 128 (tcgen05 tensor cores)");
+    return OPTMC_EUNSUPPORTED;
+  }
   if (np_->epochs < 0 || np_->epochs > 10000 || !(np_->lr > 0)) { set_error("per-date MLP: bad epochs / lr"); return OPTMC_EINVAL; }
   if (ctx->sw.M >= (1ll << 32)) { set_error("per-date MLP: too many paths"); return OPTMC_EUNSUPPORTED; }
+  if (np_->hidden == kTH) return ctx->sw.dtype == OPTMC_F64 ? lsm_mlp_tc_t<double>(ctx, np_, out) : lsm_mlp_tc_t<float>(ctx, np_, out);
   return ctx->sw.dtype == OPTMC_F64 ? lsm_mlp_t<double>(ctx, np_, out) : lsm_mlp_t<float>(ctx, np_, out);
 }
 
 // The fresh parameters of date `date` (test aid: lets the oracle start from the same network).
-int mlp_init_params_host(unsigned long long seed, int date, float* out) {
-  for (int i = 0; i < kMP; ++i) {
+int mlp_init_params_host(int H, unsigned long long seed, int date, float* out) {
+  const int P = 3 * H + H * H + H + 1;
+  const float hb = 1.0f / sqrtf((float)H);
+  for (int i = 0; i < P; ++i) {
     const Philox4 p = philox_for((unsigned long long)i, (unsigned int)date, 0x4D4C50u, seed);
     const float u = ((float)(p.v[0] >> 8) + 0.5f) * (2.0f / 16777216.0f) - 1.0f;
-    const float bound = (i < oW2) ? 1.0f : 0.17677669529663687f;
+    const float bound = (i < 2 * H) ? 1.0f : hb;
     out[i] = u * bound;
   }
-  return kMP;
+  return P;
 }
 
 }  // namespace optmc

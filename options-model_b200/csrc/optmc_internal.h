@@ -122,7 +122,9 @@ int lsm_global(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, 
 
 // lsm_mlp.cu
 int lsm_mlp(optmc_ctx* ctx, const optmc_mlp_params* np, optmc_lsm_result* out);
-int mlp_init_params_host(unsigned long long seed, int date, float* out);
+int mlp_init_params_host(int H, unsigned long long seed, int date, float* out);
+int mlp_grad_debug(optmc_ctx* ctx, int H, long long n, const float* xs, const float* ys, const float* params, float* grads,
+                   float* cont);
 
 // european.cu
 int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,

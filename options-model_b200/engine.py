@@ -274,6 +274,21 @@ class Engine:
                                        C.byref(res)))
         return self._to_result(res, keep)
 
+    def mlp_grad_debug(self, hidden: int, xs: np.ndarray, ys: np.ndarray, params: np.ndarray):
+        """One full-batch gradient + forward of the ContNet on host rows (test aid).  -> (grads[P], cont[n])."""
+        xs = np.ascontiguousarray(xs, dtype=np.float32)
+        ys = np.ascontiguousarray(ys, dtype=np.float32)
+        params = np.ascontiguousarray(params, dtype=np.float32)
+        P = 3 * hidden + hidden * hidden + hidden + 1
+        assert params.size == P and xs.size == ys.size
+        grads = np.zeros(P, dtype=np.float32)
+        cont = np.zeros(xs.size, dtype=np.float32)
+        fp = C.POINTER(C.c_float)
+        self._sync_stream()
+        L.check(self.lib.optmc_mlp_grad_debug(self._h, int(hidden), xs.size, xs.ctypes.data_as(fp), ys.ctypes.data_as(fp),
+                                              params.ctypes.data_as(fp), grads.ctypes.data_as(fp), cont.ctypes.data_as(fp)))
+        return grads, cont
+
     def mlp_init_params(self, seed: int, date: int, hidden: int = 32) -> np.ndarray:
         n = 3 * hidden + hidden * hidden + hidden + 1
         out = np.zeros(n, dtype=np.float32)

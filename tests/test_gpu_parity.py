@@ -631,3 +631,60 @@ def test_mlp_init_matches_torch_default_range(eng):
     assert np.abs(rest).max() < b and np.abs(rest).max() > 0.95 * b
     assert abs(rest.mean()) < 0.01 * b and abs(rest.std() - b / np.sqrt(3)) < 0.01 * b
     assert not np.array_equal(p[0], p[1])  # a fresh network per date
+
+
+def _torch_contnet_grads(H, xs, ys, p0):
+    from torch import nn
+
+    net = nn.Sequential(nn.Linear(1, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU(), nn.Linear(H, 1))
+    with torch.no_grad():
+        net[0].weight.copy_(torch.from_numpy(p0[0:H].reshape(H, 1)))
+        net[0].bias.copy_(torch.from_numpy(p0[H:2 * H]))
+        net[2].weight.copy_(torch.from_numpy(p0[2 * H:2 * H + H * H].reshape(H, H)))
+        net[2].bias.copy_(torch.from_numpy(p0[2 * H + H * H:3 * H + H * H]))
+        net[4].weight.copy_(torch.from_numpy(p0[3 * H + H * H:4 * H + H * H].reshape(1, H)))
+        net[4].bias.copy_(torch.from_numpy(p0[4 * H + H * H:4 * H + H * H + 1]))
+    X = torch.from_numpy(xs.reshape(-1, 1)); Y = torch.from_numpy(ys.reshape(-1, 1))
+    out = net(X)
+    loss = nn.MSELoss()(out, Y)
+    loss.backward()
+    g = np.concatenate([net[0].weight.grad.numpy().ravel(), net[0].bias.grad.numpy().ravel(),
+                        net[2].weight.grad.numpy().ravel(), net[2].bias.grad.numpy().ravel(),
+                        net[4].weight.grad.numpy().ravel(), net[4].bias.grad.numpy().ravel()])
+    return g, out.detach().numpy().ravel()
+
+
+@pytest.mark.parametrize("H,n", [(32, 1000), (32, 70_000), (128, 1000), (128, 70_000)])
+def test_mlp_gradients_vs_torch(eng, H, n):
+    """One full-batch ContNet gradient: hidden 32 = fp32 CUDA cores (tight), hidden 128 = bf16 tcgen05 MMAs with
+    fp32 accumulation in tensor memory (bf16 tolerance).  n is not a multiple of the tile size on purpose."""
+    rng = np.random.default_rng(H + n)
+    xs = rng.standard_normal(n).astype(np.float32)
+    ys = (np.maximum(0.0, 3.0 - 2.0 * xs) + 0.3 * rng.standard_normal(n)).astype(np.float32)
+    p0 = eng.mlp_init_params(99, 5, H)
+    g_ref, out_ref = _torch_contnet_grads(H, xs, ys, p0)
+    g, out = eng.mlp_grad_debug(H, xs, ys, p0)
+    tol_out, tol_g = (2e-6, 2e-5) if H == 32 else (2e-2, 3e-2)
+    assert np.abs(out - out_ref).max() <= tol_out * max(1.0, np.abs(out_ref).max())
+    # per-block relative L2 error (weights and biases of each layer have very different scales)
+    b = [0, H, 2 * H, 2 * H + H * H, 3 * H + H * H, 4 * H + H * H, 4 * H + H * H + 1]
+    for lo, hi in zip(b[:-1], b[1:]):
+        den = np.linalg.norm(g_ref[lo:hi]) + 1e-12
+        assert np.linalg.norm(g[lo:hi] - g_ref[lo:hi]) / den <= tol_g, (lo, hi)
+
+
+def test_mlp_lsm_tensor_core_hidden128(eng, mods):
+    """Per-date NN-LSM with hidden = 128 on tcgen05 vs the torch fp32 oracle from the same initial weights: bf16
+    operands perturb the fit slightly, so the comparison is statistical (price within 1%, few decisions differ)."""
+    L, E, orc = mods
+    rng = np.random.default_rng(37)
+    M, N = 8192, 10
+    Z1, Z2 = orc.draw_heston_normals(rng, N, M)
+    S = orc.heston_paths_antithetic(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2)
+    reg = orc.ContNetRegressor(lambda t: eng.mlp_init_params(4321, t, 128), hidden=128, epochs=10, lr=1e-3)
+    ref = orc.lsm_sweep(S, 100.0, 0.05, 1.0, "put", regressor=reg, semantics="textbook")
+    res = eng.lsm_mlp(_slab(eng, S, torch.float64), 100.0, 0.05, 1.0, "put", "textbook", hidden=128, epochs=10, lr=1e-3,
+                      seed=4321)
+    np.testing.assert_array_equal(res.n_itm[N - 1], ref.n_itm[N - 1])
+    assert res.price == pytest.approx(ref.price, rel=1e-2)
+    assert np.abs(res.ex_count - ref.ex_count).sum() <= 0.03 * M
