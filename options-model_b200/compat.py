@@ -398,16 +398,20 @@ def compute_multiple_S0_gpu_batch(s0_list, K, r, sigma, option_type, intervals_p
 # older API the Streamlit UIs import (om2:176-457, om1:44-211)
 # ---------------------------------------------------------------------------------------------------
 class OptionPricer:
-    """om2:176-355.  lsm_poly_degree is honoured here (2 or 3); the reference validates and ignores it."""
+    """om2:176-355.  regressor="nn" (default, the reference's behaviour, om2:277-310): a fresh ContNet per exercise
+    date trained with nn_epochs full-batch Adam steps (optmc_lsm_mlp; nn_hidden 32 -> fp32 CUDA cores, 128 -> bf16
+    tcgen05 tensor cores).  regressor="poly": the polynomial of SURVEY.md 8(c) with lsm_poly_degree 2 or 3 (the
+    reference validates lsm_poly_degree and then ignores it, om2:176-180)."""
 
     def __init__(self, K: float, r: float, sigma: Optional[float], option_type: str = "call",
                  lsm_poly_degree: int = 2, seed: int = 42, use_heston: bool = False,
                  heston_params: Optional[Dict[str, Any]] = None, nn_hidden: int = 32, nn_epochs: int = 10,
-                 nn_lr: float = 1e-3, verbose: bool = False):
+                 nn_lr: float = 1e-3, verbose: bool = False, regressor: str = "nn"):
         self.K, self.r, self.sigma, self.option_type = K, r, sigma, option_type
         self.lsm_poly_degree, self.seed = lsm_poly_degree, seed
         self.use_heston, self.heston_params = use_heston, heston_params
         self.nn_hidden, self.nn_epochs, self.nn_lr, self.verbose = nn_hidden, nn_epochs, nn_lr, verbose
+        self.regressor = regressor
 
     def price_american_option(self, S0: float, T: float, num_simulations: int = 10000, num_time_steps: int = 50,
                               plot_paths: bool = False) -> float:
@@ -427,6 +431,12 @@ class OptionPricer:
             model = E.heston(S0, self.r, T, hp["v0"], hp["kappa"], hp["theta"], hp["xi"], hp["rho"])
         else:
             model = E.gbm(S0, self.r, T, self.sigma)
+        if self.regressor == "nn":
+            eng = _engine()
+            S = eng.paths(model, M, int(num_time_steps), "f32", E.RngSpec(seed=int(self.seed)))
+            res = eng.lsm_mlp(S, self.K, self.r, T, self.option_type, "reference", hidden=int(self.nn_hidden),
+                              epochs=int(self.nn_epochs), lr=float(self.nn_lr), seed=int(self.seed), arrays=False)
+            return float(res.price)
         basis = "poly3" if self.lsm_poly_degree >= 3 else "poly2"
         res = _engine().price_american(model, M, int(num_time_steps), self.K, self.option_type, "f32",
                                        E.RngSpec(seed=int(self.seed)), basis=basis)
@@ -445,11 +455,11 @@ class OptionPricer:
 
 def compute_curve_worker(S0, K, r, sigma, option_type, lsm_poly_degree, seed, intervals_per_day, total_points,
                          num_simulations, plot_paths, use_heston, heston_params, nn_hidden=32, nn_epochs=10,
-                         nn_lr=1e-3, verbose=False):
+                         nn_lr=1e-3, verbose=False, regressor="nn"):
     """om2:443-457."""
     try:
         pricer = OptionPricer(K, r, sigma, option_type, lsm_poly_degree, seed, use_heston, heston_params, nn_hidden,
-                              nn_epochs, nn_lr, verbose)
+                              nn_epochs, nn_lr, verbose, regressor)
         return pricer.compute_curve_for_S0(S0, intervals_per_day, total_points, num_simulations, plot_paths)
     except Exception as e:  # noqa: BLE001 -- om2:455-457
         logging.error(f"Error in worker for S0={S0}: {e}")

@@ -183,14 +183,15 @@ __device__ __forceinline__ float mlp_forward_row(const MlpSmem& sm, float x, flo
 #pragma unroll
   for (int i = 0; i < kMH; ++i) h1[i] = fmaxf(fmaf(sm.w1[i], x, sm.b1[i]), 0.f);
   float out = sm.b3;
-#pragma unroll
+#pragma unroll 2
   for (int j = 0; j < kMH; ++j) {
     float z = sm.b2[j];
 #pragma unroll
     for (int i = 0; i < kMH; ++i) z = fmaf(sm.W2[j * kMPad + i], h1[i], z);
-    h2[j] = fmaxf(z, 0.f);
-    out = fmaf(sm.w3[j], h2[j], out);
+    const float h = fmaxf(z, 0.f);
+    out = fmaf(sm.w3[j], h, out);
   }
+  (void)h2;
   return out;
 }
 
@@ -213,29 +214,43 @@ mlp_grad_kernel(const float* __restrict__ params, const float* __restrict__ xs, 
   for (long long r0 = (long long)blockIdx.x * kMTile; r0 < n; r0 += (long long)gridDim.x * kMTile) {
     const long long r = r0 + tid;
     const bool act = r < n;
-    {  // forward + output-side backward of this thread's row
-      float h1[kMH], h2[kMH];
+    {  // forward + backward of this thread's row; only h1 (then dh1) lives in registers, the rest goes to the tiles
       const float x = act ? xs[r] : 0.f;
-      const float out = mlp_forward_row(sm, x, h1, h2);
+      float h1[kMH];
+      unsigned int m1 = 0u, m2 = 0u;  // h1 > 0, h2 > 0
+#pragma unroll
+      for (int i = 0; i < kMH; ++i) {
+        h1[i] = fmaxf(fmaf(sm.w1[i], x, sm.b1[i]), 0.f);
+        m1 |= (h1[i] > 0.f ? 1u : 0u) << i;
+        sm.H1[tid * kMPad + i] = h1[i];
+      }
+      float out = sm.b3;
+#pragma unroll 2
+      for (int j = 0; j < kMH; ++j) {  // partial unroll: a full 32 x 32 unroll front-loads 1024 shared loads and spills
+        float z = sm.b2[j];
+#pragma unroll
+        for (int i = 0; i < kMH; ++i) z = fmaf(sm.W2[j * kMPad + i], h1[i], z);
+        const float h2 = fmaxf(z, 0.f);
+        m2 |= (h2 > 0.f ? 1u : 0u) << j;
+        sm.H2[tid * kMPad + j] = h2;
+        out = fmaf(sm.w3[j], h2, out);
+      }
       const float err = act ? out - ys[r] : 0.f;
       const float dout = err * inv_n2;
       loss = fmaf(err, err, loss);
       sm.xs[tid] = x; sm.dout[tid] = dout;
+      float dh[kMH];
 #pragma unroll
-      for (int i = 0; i < kMH; ++i) { sm.H1[tid * kMPad + i] = h1[i]; sm.H2[tid * kMPad + i] = h2[i]; }
-      float dz2[kMH];
-#pragma unroll
+      for (int i = 0; i < kMH; ++i) dh[i] = 0.f;
+#pragma unroll 2
       for (int j = 0; j < kMH; ++j) {
-        dz2[j] = h2[j] > 0.f ? dout * sm.w3[j] : 0.f;
-        sm.DZ2[tid * kMPad + j] = dz2[j];
+        const float dz = ((m2 >> j) & 1u) ? dout * sm.w3[j] : 0.f;
+        sm.DZ2[tid * kMPad + j] = dz;
+#pragma unroll
+        for (int i = 0; i < kMH; ++i) dh[i] = fmaf(sm.W2[j * kMPad + i], dz, dh[i]);
       }
 #pragma unroll
-      for (int i = 0; i < kMH; ++i) {
-        float d = 0.f;
-#pragma unroll
-        for (int j = 0; j < kMH; ++j) d = fmaf(sm.W2[j * kMPad + i], dz2[j], d);
-        sm.DH1[tid * kMPad + i] = h1[i] > 0.f ? d : 0.f;
-      }
+      for (int i = 0; i < kMH; ++i) sm.DH1[tid * kMPad + i] = ((m1 >> i) & 1u) ? dh[i] : 0.f;
     }
     __syncthreads();
     // parameter gradients of the tile: small GEMMs over the 256 rows held in shared memory
@@ -463,13 +478,12 @@ __device__ __forceinline__ void tmem_ld16(unsigned int taddr, float (&v)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ unsigned int pack2_bf16(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);  // one packed conversion (low half = first argument)
+  return *reinterpret_cast<const unsigned int*>(&h);
+}
 __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
-  uint4 u;
-  u.x = ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v[1])) << 16) | __bfloat16_as_ushort(__float2bfloat16_rn(v[0]));
-  u.y = ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v[3])) << 16) | __bfloat16_as_ushort(__float2bfloat16_rn(v[2]));
-  u.z = ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v[5])) << 16) | __bfloat16_as_ushort(__float2bfloat16_rn(v[4]));
-  u.w = ((unsigned int)__bfloat16_as_ushort(__float2bfloat16_rn(v[7])) << 16) | __bfloat16_as_ushort(__float2bfloat16_rn(v[6]));
-  return u;
+  return make_uint4(pack2_bf16(v[0], v[1]), pack2_bf16(v[2], v[3]), pack2_bf16(v[4], v[5]), pack2_bf16(v[6], v[7]));
 }
 __device__ __forceinline__ void tc_bar_wait(unsigned long long* bar, unsigned int parity) {
   mbar_wait(reinterpret_cast<uint64_t*>(bar), parity);

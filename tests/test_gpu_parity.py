@@ -688,3 +688,19 @@ def test_mlp_lsm_tensor_core_hidden128(eng, mods):
     np.testing.assert_array_equal(res.n_itm[N - 1], ref.n_itm[N - 1])
     assert res.price == pytest.approx(ref.price, rel=1e-2)
     assert np.abs(res.ex_count - ref.ex_count).sum() <= 0.03 * M
+
+
+def test_compat_om2_option_pricer_nn_and_poly(mods):
+    """om2.OptionPricer.price_american_option: the reference's per-date network by default, polynomial on request."""
+    from options_model_b200 import compat
+
+    L, E, orc = mods
+    nn = compat.OptionPricer(100.0, 0.05, 0.2, "put", seed=3, nn_hidden=32, nn_epochs=10).price_american_option(100.0, 1.0, 20_000, 20)
+    nn128 = compat.OptionPricer(100.0, 0.05, 0.2, "put", seed=3, nn_hidden=128, nn_epochs=10).price_american_option(100.0, 1.0, 20_000, 20)
+    poly = compat.OptionPricer(100.0, 0.05, 0.2, "put", seed=3, regressor="poly").price_american_option(100.0, 1.0, 20_000, 20)
+    bs = compat.BlackScholesGreeks.black_scholes_price(100.0, 100.0, 1.0, 0.05, 0.2, "put")
+    for v in (nn, nn128, poly):
+        assert np.isfinite(v) and bs - 0.5 < v < bs + 2.5
+    with pytest.raises(NotImplementedError):
+        compat.OptionPricer(100.0, 0.05, 0.2, "put", nn_hidden=64).price_american_option(100.0, 1.0, 1000, 5)
+    assert compat.compute_curve_worker(-1.0, 100.0, 0.05, 0.2, "put", 2, 1, 1, 2, 100, False, False, None) == []

@@ -89,3 +89,17 @@ p1, p2 = eng.kernel_times()
 print(f"   pass 1 (moments + solve) {p1:.3f} ms, pass 2 (walk) {p2:.3f} ms")
 print(f"global LSM (ref7 linear) 1M x 252 fp32: {ms:.3f} ms per sweep (2 slab reads = 2.02 GB -> {2.024 / ms:.2f} TB/s), "
       f"price {g['price']:.4f} rank {g['rank']} rows {g['n_rows']}", flush=True)
+
+# ---- BASELINE config 3: per-date NN-LSM, 4M paths x 252 steps (hidden 128 on tcgen05; hidden 32 on CUDA cores) ----------
+for Mn, H, sem, ep in ((1_000_000, 32, "reference", 10), (1_000_000, 128, "reference", 10), (4_000_000, 128, "reference", 10),
+                       (1_000_000, 128, "textbook", 10)):
+    S = eng.paths(model, Mn, 252, "f32", E.RngSpec(seed=5))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = eng.lsm_mlp(S, 100.0, 0.05, 1.0, "put", sem, hidden=H, epochs=ep, lr=1e-3, seed=1, arrays=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    rows = int(r.n_itm.sum())
+    print(f"config 3: NN-LSM {Mn} x 252, hidden {H}, {ep} epochs, {sem}: {dt * 1e3:9.1f} ms  price {r.price:.4f} +- {r.stderr:.4f}  "
+          f"rows {rows}  {rows * ep / dt / 1e6:8.1f} M row-epochs/s  {Mn * 252 / dt / 1e9:6.2f} G path-steps/s", flush=True)
+    del S

@@ -50,6 +50,11 @@ WANT = {
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "pipe_fp64_pct",
     "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active": "pipe_xu_pct",
     "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active": "pipe_lsu_pct",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "pipe_tensor_pct",
+    "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active": "pipe_tc_pct",
+    "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active": "pipe_tmem_pct",
+    "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active": "pipe_tc_cycles_pct",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active": "pipe_tensor_hmma_pct",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed": "dram_throughput_pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed": "sm_throughput_pct",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio": "stall_barrier",
@@ -88,11 +93,12 @@ for k, v in summary["launches"].items():
     lines.append(f"| `{re.sub(r'[|]', '/', k)[:90]}` | {v['n']} | {v['mean_us']:.1f} | {v['share']:.3f} |")
 lines += ["", "Full capture (`ncu --set full --clock-control none --import-source on`), per launch:", ""]
 for name, ks in summary["kernels"].items():
-    k = ks[0]
-    lines.append(f"## `{name}`")
+    k = ks[-1]
+    lines.append(f"## `{name}`  ({len(ks)} captured launch(es); last one shown)")
     lines.append("")
     for key in ("duration", "dram_read", "dram_write", "dram_bytes", "registers", "warp_instructions", "issue_active_pct",
                 "warps_active_pct", "pipe_alu_pct", "pipe_fma_pct", "pipe_fp64_pct", "pipe_xu_pct", "pipe_lsu_pct",
+                "pipe_tensor_pct", "pipe_tc_pct", "pipe_tc_cycles_pct", "pipe_tensor_hmma_pct", "pipe_tmem_pct",
                 "stall_barrier", "stall_wait", "stall_math_pipe", "stall_no_instruction", "stall_long_scoreboard",
                 "stall_short_scoreboard", "stall_not_selected"):
         if key in k:

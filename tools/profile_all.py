@@ -1,0 +1,36 @@
+"""Runs every kernel family once (after a warm-up) so that one ncu invocation can capture them all:
+batched paths + grouped persistent sweep (the bench step), single-option sweep, global-regression LSM passes,
+per-date NN-LSM on CUDA cores (hidden 32) and on tcgen05 (hidden 128), fused European batch."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import options_model_b200  # noqa: E402,F401
+from options_model_b200 import _lib as L  # noqa: E402
+from options_model_b200 import engine as E  # noqa: E402
+
+HP = dict(v0=0.04, kappa=2.0, theta=0.04, xi=0.5, rho=-0.7)
+eng = E.Engine(0)
+model = E.heston(100.0, 0.05, 1.0, **HP)
+M, N = 1_000_000, 252
+for rep in range(2):  # rep 0 = warm-up, rep 1 = the captured launches (ncu -s skips the first pass)
+    eng.price_american_batch(model, M, 100.0, 100.0, 1.0, np.full(4, N), 1, "f32", E.RngSpec(seed=1 + rep))
+    S = eng.paths(model, M, N, "f32", E.RngSpec(seed=3 + rep))
+    eng.lsm(S, 100.0, 0.05, 1.0, "put", arrays=False)
+    eng.lsm(S, 100.0, 0.05, 1.0, "put", semantics="textbook", arrays=False)
+    eng.lsm_global(S, 100.0, 0.05, 1.0, "put", arrays=False)
+    rng = np.random.default_rng(rep)
+    n = 1_000_000
+    xs = rng.standard_normal(n).astype(np.float32)
+    ys = np.maximum(0.0, 3.0 - 2.0 * xs).astype(np.float32)
+    for H in (32, 128):
+        eng.mlp_grad_debug(H, xs, ys, eng.mlp_init_params(1, 1, H))
+    Kc, Tc = np.meshgrid(np.linspace(80, 120, 20), np.linspace(0.1, 1.0, 10))
+    calib = E.heston(100.0, 0.05, 1.0, scheme=L.SCHEME_HESTON_REF_CALIB, **HP)
+    eng.price_european_batch(calib, 50_000, 100, Kc.ravel(), Tc.ravel(), np.zeros(200, dtype=np.int32), "f32", E.RngSpec(seed=1))
+    torch.cuda.synchronize()
+print("profile_all done")
