@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) paths_kernel(const PathArgs a) {
 
 // Batched form: blockIdx.y selects the option (its own slab, S0, dt, step count and Philox stream).
 template <typename R, int SCHEME, int VEC>
-__global__ void __launch_bounds__(256) paths_batch_kernel(const PathArgs* __restrict__ args) {
+__global__ void __launch_bounds__(256, 4) paths_batch_kernel(const PathArgs* __restrict__ args) {
   const PathArgs a = args[blockIdx.y];
   paths_body<R, SCHEME, VEC, false>(a);
 }
