@@ -248,6 +248,46 @@ def run_own_arm(args):
         e2e_s = time.perf_counter() - t0
         barrier()
 
+    # the other BASELINE configs, one short measurement each (rank 0 only; reported as context, not as `value`)
+    others = {}
+    if rank == 0 and not args.no_other_configs:
+        def timed(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                out = fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps, out
+
+        with torch.cuda.stream(stream):
+            gbm = E.gbm(S0, R, T, 0.2)
+            dt1, r1 = timed(lambda: eng.price_american(gbm, 100_000, 50, K, "put", "f32", E.RngSpec(seed=7)), 20)
+            others["config1_gbm_100k_x50"] = {"ms": dt1 * 1e3, "path_steps_per_s": 100_000 * 50 / dt1, "price": r1.price}
+            Kg, Tg = np.meshgrid(np.linspace(70, 130, 32), np.linspace(1 / 12, 2, 32))
+            n4 = 128  # one GPU's share of the 1024-option grid at 8 GPUs
+            dt4, r4 = timed(lambda: eng.price_american_batch(model, 262_144, S0, Kg.ravel()[:n4], Tg.ravel()[:n4],
+                                                             np.full(n4, 252), 1, "f32", E.RngSpec(seed=9)), 1)
+            others["config4_128_options_x_256k_x252"] = {"ms": dt4 * 1e3, "path_steps_per_s": n4 * 262_144 * 252 / dt4,
+                                                         "us_per_option": dt4 / n4 * 1e6}
+            S4 = eng.paths(model, 4_000_000, 252, "f32", E.RngSpec(seed=11))
+            dt3, r3 = timed(lambda: eng.lsm_mlp(S4, K, R, T, "put", "reference", hidden=128, epochs=10, lr=1e-3, seed=1,
+                                                arrays=False), 1)
+            others["config3_nn_lsm_4M_x252_hidden128_tcgen05"] = {"ms": dt3 * 1e3, "path_steps_per_s": 4_000_000 * 252 / dt3,
+                                                                   "price": r3.price, "note": "sweep only (paths resident)"}
+            del S4
+            Kc, Tc = np.meshgrid(np.linspace(80, 120, 20), np.linspace(0.1, 1.0, 10))
+            calib = E.heston(S0, R, T, scheme=L.SCHEME_HESTON_REF_CALIB, **HP)
+            dt5, r5 = timed(lambda: eng.price_european_batch(calib, 50_000, 100, Kc.ravel(), Tc.ravel(),
+                                                             np.zeros(200, dtype=np.int32), "f32", E.RngSpec(seed=13)), 3)
+            others["config5_calibration_objective_200x50k_x100"] = {"ms": dt5 * 1e3, "path_steps_per_s": 1e9 / dt5}
+            Sg = eng.paths(model, M, N, "f32", E.RngSpec(seed=15))
+            dtg, rg = timed(lambda: eng.lsm_global(Sg, K, R, T, "put", arrays=False), 3)
+            others["global_regression_lsm_1M_x252"] = {"ms": dtg * 1e3, "slab_GBps": 2 * b * M * (N + 1) / dtg / 1e9,
+                                                       "price": rg["price"], "note": "two streaming passes over the slab"}
+            del Sg
+    barrier()
+
     if dist is not None:
         t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -304,6 +344,8 @@ def run_own_arm(args):
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
+        if others:
+            line["other_configs"] = others
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -325,6 +367,7 @@ def main():
     ap.add_argument("--cpu-paths", type=int, default=1_000_000, help="CPU-baseline sample size (paths)")
     ap.add_argument("--ref-paths", type=int, default=50_000, help="reference arm: paths per worker per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of BASELINE configs 1/3/4/5")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3
