@@ -50,7 +50,8 @@ enum optmc_scheme {
   OPTMC_SCHEME_GBM_LOGSPACE = 1,         /* om3gpu:150-185 cumulative log-space sum, exp at the end */
   OPTMC_SCHEME_HESTON_REF_ABSORB = 2,    /* om3:228-233 / om3gpu:218-225 absorption Euler (the reference's scheme) */
   OPTMC_SCHEME_HESTON_FULL_TRUNC = 3,    /* Lord et al. full truncation (north-star scheme; not in the reference) */
-  OPTMC_SCHEME_HESTON_REF_CALIB = 4      /* hc:240-255 arithmetic Euler on S, variance floored at 1e-8 */
+  OPTMC_SCHEME_HESTON_REF_CALIB = 4,     /* hc:240-255 arithmetic Euler on S, variance floored at 1e-8 */
+  OPTMC_SCHEME_HESTON_QE = 5             /* Andersen (2008) quadratic-exponential (north-star scheme; not in the reference) */
 };
 
 enum optmc_basis {
@@ -140,6 +141,31 @@ int optmc_ctx_kernel_times(optmc_ctx* ctx, double* paths_ms, double* sweep_ms);
 /* Device properties the host layer needs for grid sizing / reporting: out[0]=SM count,
  * out[1]=L2 bytes, out[2]=max opt-in shared memory per block, out[3]=compute capability major*10+minor. */
 int optmc_ctx_device_info(optmc_ctx* ctx, int64_t out[4]);
+/* Device memory the library itself allocates (SURVEY 8b "workspace size is queryable"; the caller owns every
+ * other buffer).  optmc_workspace_bytes: upper estimate, before the call, of what optmc_price_american_batch
+ * (n_options >= 1; optmc_price_american is n_options = 1) will hold for M paths x N dates of `dtype` -- the
+ * step-major slabs of one wave (at most one option per SM) plus cash-flows and per-date arrays; no context needed, no CUDA call.
+ * optmc_ctx_workspace_bytes: what the context holds right now (workspaces only grow). */
+int optmc_workspace_bytes(int64_t M, int32_t N, int32_t dtype, int32_t n_options, int64_t* bytes);
+int optmc_ctx_workspace_bytes(optmc_ctx* ctx, int64_t* bytes);
+
+/* ---- path-sharded sweep over the GPUs of one box (no counterpart in the reference) ----
+ * One process per GPU.  The per-date exchange of the Gram totals happens INSIDE the persistent sweep kernel
+ * through peer-mapped memory over NVLink (no host-launched collective on the data path):
+ *   1. every rank: optmc_comm_export -> a 64-byte CUDA-IPC handle of its exchange slots;
+ *   2. the host plumbing all-gathers the handles (torch.distributed / MPI / a pipe -- not this library's job);
+ *   3. every rank: optmc_comm_init(rank, nranks, handles[nranks][64]) maps the peers' slots;
+ *   4. every rank, in the same order: optmc_lsm_poly_sharded on its block of paths.  Every rank returns the
+ *      same price / stderr / betas / n_itm (bit-identical: the totals are integer sums); ex_count and boundary
+ *      cover the rank's own paths (sum / max them on the host if wanted).
+ * At most 8 ranks; every rank's block must fit the persistent kernel (OPTMC_EUNSUPPORTED otherwise); a peer that
+ * never launches makes the others give up after a few seconds with OPTMC_ECUDA instead of hanging the GPU. */
+#define OPTMC_COMM_HANDLE_BYTES 64
+int optmc_comm_export(optmc_ctx* ctx, void* handle_out);
+int optmc_comm_init(optmc_ctx* ctx, int32_t rank, int32_t nranks, const void* handles);
+int optmc_comm_finalize(optmc_ctx* ctx);
+int optmc_lsm_poly_sharded(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M_local, int64_t M_total, int32_t N,
+                           int32_t dtype, const optmc_lsm_params* lp, optmc_lsm_result* out);
 
 /* ---- path simulation (replaces om3:473-480, om3:211-251, om3gpu:117-248, hc:204-257) ---------- */
 /* S_dev: [(N+1)][ld] of `dtype`; ld >= M.  V_dev (Heston only, may be NULL): same shape, the variance

@@ -11,7 +11,9 @@ _LIB = None
 OK, EINVAL, ECUDA, ENOMEM, EUNSUPPORTED = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 MODEL_GBM, MODEL_HESTON = 0, 1
-SCHEME_GBM_LOG_EULER, SCHEME_GBM_LOGSPACE, SCHEME_HESTON_REF_ABSORB, SCHEME_HESTON_FULL_TRUNC, SCHEME_HESTON_REF_CALIB = range(5)
+COMM_HANDLE_BYTES = 64
+SCHEME_GBM_LOG_EULER, SCHEME_GBM_LOGSPACE, SCHEME_HESTON_REF_ABSORB, SCHEME_HESTON_FULL_TRUNC, SCHEME_HESTON_REF_CALIB, \
+    SCHEME_HESTON_QE = range(6)
 BASIS_POLY2, BASIS_POLY3, BASIS_REF7 = 2, 3, 7
 SEM_STICKY_MASK, SEM_REF_DISCOUNT = 1, 2
 SEM_REFERENCE, SEM_TEXTBOOK = 3, 0
@@ -79,6 +81,8 @@ PROTOTYPES = {
     "optmc_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "optmc_ctx_kernel_times": (C.c_int, [C.c_void_p, _P(C.c_double), _P(C.c_double)]),
     "optmc_ctx_device_info": (C.c_int, [C.c_void_p, _P(C.c_int64)]),
+    "optmc_workspace_bytes": (C.c_int, [C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P(C.c_int64)]),
+    "optmc_ctx_workspace_bytes": (C.c_int, [C.c_void_p, _P(C.c_int64)]),
     "optmc_paths_gbm": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
                                   C.c_void_p, C.c_int64]),
     "optmc_paths_heston": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
@@ -89,6 +93,11 @@ PROTOTYPES = {
     "optmc_lsm_poly": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
                                  _P(LsmResult)]),
     "optmc_lsm_fetch": (C.c_int, [C.c_void_p, _P(LsmResult)]),
+    "optmc_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "optmc_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "optmc_comm_finalize": (C.c_int, [C.c_void_p]),
+    "optmc_lsm_poly_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                         _P(LsmParams), _P(LsmResult)]),
     "optmc_lsm_global": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
                                    _P(GlobalResult)]),
     "optmc_lsm_mlp": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),

@@ -239,6 +239,8 @@ int optmc_ctx_destroy(optmc_ctx* ctx) {
   cudaFree(ctx->slab); cudaFree(ctx->cf); cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->gram);
   cudaFree(ctx->d_betas); cudaFree(ctx->d_bnd); cudaFree(ctx->d_exc); cudaFree(ctx->d_nitm); cudaFree(ctx->d_valid);
   cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
+  for (int r = 0; r < 8; ++r) if (ctx->comm.opened[r]) cudaIpcCloseMemHandle(ctx->comm.peers[r]);
+  cudaFree(ctx->comm.local);
   for (int i = 0; i < 3; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
@@ -269,6 +271,29 @@ int optmc_ctx_kernel_times(optmc_ctx* ctx, double* paths_ms, double* sweep_ms) {
 int optmc_ctx_device_info(optmc_ctx* ctx, int64_t out[4]) {
   if (!ctx || !out) { set_error("null argument"); return OPTMC_EINVAL; }
   out[0] = ctx->sm_count; out[1] = ctx->l2_bytes; out[2] = ctx->max_smem_optin; out[3] = ctx->cc;
+  return OPTMC_OK;
+}
+
+int optmc_workspace_bytes(int64_t M, int32_t N, int32_t dtype, int32_t n_options, int64_t* bytes) {
+  if (!bytes) { set_error("null argument"); return OPTMC_EINVAL; }
+  if (M <= 0 || N <= 0 || n_options <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
+  if (dtype != OPTMC_F32 && dtype != OPTMC_F64) { set_error("bad dtype"); return OPTMC_EINVAL; }
+  const int64_t es = dtype == OPTMC_F64 ? 8 : 4;
+  const int64_t ld = (M + 63) / 64 * 64;
+  const int64_t slab = (int64_t)(N + 1) * ld * es;
+  // a batch is priced in waves of at most one option per SM (lsm_resident.cu): <= 160 slabs alive at once
+  const int64_t wave = n_options < 160 ? n_options : 160;
+  const int64_t per_date = (int64_t)((N + 1) < 512 ? 512 : (N + 1)) * (kMaxBeta * 8 + 8 + 8 + 8 + 4);
+  *bytes = wave * slab + ld * es /* split-sweep cash-flows */ + wave * (per_date + 4096) + (1 << 20);
+  return OPTMC_OK;
+}
+
+int optmc_ctx_workspace_bytes(optmc_ctx* ctx, int64_t* bytes) {
+  if (!ctx || !bytes) { set_error("null argument"); return OPTMC_EINVAL; }
+  *bytes = (int64_t)(ctx->slab_bytes + ctx->cf_bytes + ctx->partials_bytes + ctx->batch_dev_cap + ctx->eu_out_cap +
+                     ctx->eu_par_cap + ctx->eu_tickets_cap +
+                     ctx->per_date_cap * (kMaxBeta * sizeof(double) + 2 * sizeof(unsigned long long) + sizeof(long long) + sizeof(int)) +
+                     xchg_bytes() + 1024 * sizeof(unsigned int) + 20 * sizeof(double) + 4 * sizeof(int));
   return OPTMC_OK;
 }
 
@@ -314,6 +339,99 @@ int optmc_lsm_poly(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int
   rc = run_sweep(ctx);
   if (rc) return rc;
   return out ? fetch_results(ctx, out) : OPTMC_OK;
+  OPTMC_TRY_END
+}
+
+// ---- path-sharded sweep over several GPUs: exchange slots in peer-mapped memory ----------------
+static size_t comm_slot_bytes() { return (size_t)2 * optmc::kCommMaxRanks * kXchgWords * sizeof(unsigned long long); }
+
+int optmc_comm_export(optmc_ctx* ctx, void* handle_out) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  if (!handle_out) { set_error("null argument"); return OPTMC_EINVAL; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == OPTMC_COMM_HANDLE_BYTES, "handle size");
+  if (!ctx->comm.local) {
+    OPTMC_CUDA(cudaMalloc((void**)&ctx->comm.local, comm_slot_bytes()));
+  }
+  OPTMC_CUDA(cudaMemset(ctx->comm.local, 0, comm_slot_bytes()));
+  OPTMC_CUDA(cudaDeviceSynchronize());
+  ctx->comm.g = 2;
+  cudaIpcMemHandle_t h;
+  OPTMC_CUDA(cudaIpcGetMemHandle(&h, ctx->comm.local));
+  memcpy(handle_out, &h, sizeof(h));
+  return OPTMC_OK;
+  OPTMC_TRY_END
+}
+
+static void comm_close(optmc_ctx* ctx) {
+  for (int r = 0; r < 8; ++r) {
+    if (ctx->comm.opened[r]) cudaIpcCloseMemHandle(ctx->comm.peers[r]);
+    ctx->comm.opened[r] = false;
+    ctx->comm.peers[r] = nullptr;
+  }
+  ctx->comm.nranks = 0;
+}
+
+int optmc_comm_init(optmc_ctx* ctx, int32_t rank, int32_t nranks, const void* handles) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  if (!handles) { set_error("null argument"); return OPTMC_EINVAL; }
+  if (nranks < 1 || nranks > optmc::kCommMaxRanks || rank < 0 || rank >= nranks) { set_error("bad rank / nranks (at most 8 ranks)"); return OPTMC_EINVAL; }
+  if (!ctx->comm.local) { set_error("optmc_comm_export must be called first"); return OPTMC_EINVAL; }
+  comm_close(ctx);
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) { ctx->comm.peers[r] = ctx->comm.local; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { comm_close(ctx); return cuda_fail(e, "cudaIpcOpenMemHandle (peer exchange slots)"); }
+    ctx->comm.peers[r] = static_cast<unsigned long long*>(p);
+    ctx->comm.opened[r] = true;
+  }
+  ctx->comm.rank = rank;
+  ctx->comm.nranks = nranks;
+  return OPTMC_OK;
+  OPTMC_TRY_END
+}
+
+int optmc_comm_finalize(optmc_ctx* ctx) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  comm_close(ctx);
+  return OPTMC_OK;
+  OPTMC_TRY_END
+}
+
+int optmc_lsm_poly_sharded(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M_local, int64_t M_total, int32_t N,
+                           int32_t dtype, const optmc_lsm_params* lp, optmc_lsm_result* out) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  if (ctx->comm.nranks < 1) { set_error("optmc_comm_init must be called first"); return OPTMC_EINVAL; }
+  if (M_total < M_local) { set_error("M_total must be >= M_local"); return OPTMC_EINVAL; }
+  int rc = bind_sweep(ctx, S_dev, ld, M_local, N, dtype, lp);
+  if (rc) return rc;
+  std::string why;
+  if (!resident_eligible(ctx, ctx->sw, &why)) {
+    set_error("sharded sweep needs the persistent kernel on every rank: " + why);
+    return OPTMC_EUNSUPPORTED;
+  }
+  ctx->sharded_M_total = M_total;
+  rc = sweep_resident(ctx);
+  ctx->sharded_M_total = 0;
+  if (rc) return rc;
+  ctx->sw.impl_used = OPTMC_SWEEP_RESIDENT;
+  ctx->sw.have_results = true;
+  int flags[4] = {0, 0, 0, 0};
+  OPTMC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+  OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (flags[1]) { set_error("sharded sweep: a peer rank did not answer (exchange timed out); re-run optmc_comm_export / optmc_comm_init on every rank"); return OPTMC_ECUDA; }
+  if (flags[0]) { set_error("sharded sweep: a Gram moment left the fixed-point exchange range (|m| < 2^43) or is not finite"); return OPTMC_EUNSUPPORTED; }
+  if (!out) return OPTMC_OK;
+  rc = fetch_results(ctx, out);
+  out->n_paths = M_total;
+  return rc;
   OPTMC_TRY_END
 }
 

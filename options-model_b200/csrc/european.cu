@@ -44,6 +44,8 @@ __global__ void __launch_bounds__(kEuThreads) european_fused_kernel(const EuArgs
   HestonConsts<R> hc;
   hc.dt = (R)dt; hc.sqrt_dt = (R)sqrt(dt); hc.r = (R)a.r; hc.kappa = (R)a.kappa; hc.theta = (R)a.theta;
   hc.xi = (R)a.xi; hc.rho = (R)a.rho; hc.rho_c = (R)a.rho_c;
+  QeConsts<R> qe{};
+  if (SCHEME == OPTMC_SCHEME_HESTON_QE) qe = qe_consts(hc);
   const double df = exp(-a.r * T);
   const unsigned int stream = a.stream + (unsigned int)a.par[opt * 4 + 3];
   const bool anti = a.anti != 0;
@@ -63,14 +65,8 @@ __global__ void __launch_bounds__(kEuThreads) european_fused_kernel(const EuArgs
         const R z1 = HES ? n[2 * s] : n[s];
         const R z2 = HES ? n[2 * s + 1] : (R)0;
         if (HES) {
-          if (SCHEME == OPTMC_SCHEME_HESTON_REF_ABSORB) heston_absorb_step<R>(sp, vp, z1, z2, hc);
-          else if (SCHEME == OPTMC_SCHEME_HESTON_FULL_TRUNC) heston_fulltrunc_step<R>(sp, vp, z1, z2, hc);
-          else heston_calib_step<R>(sp, vp, z1, z2, hc);
-          if (anti) {
-            if (SCHEME == OPTMC_SCHEME_HESTON_REF_ABSORB) heston_absorb_step<R>(sm, vm, -z1, -z2, hc);
-            else if (SCHEME == OPTMC_SCHEME_HESTON_FULL_TRUNC) heston_fulltrunc_step<R>(sm, vm, -z1, -z2, hc);
-            else heston_calib_step<R>(sm, vm, -z1, -z2, hc);
-          }
+          heston_step_any<R, SCHEME>(sp, vp, z1, z2, hc, qe);
+          if (anti) heston_step_any<R, SCHEME>(sm, vm, -z1, -z2, hc, qe);
         } else {
           sp = gbm_step<R>(sp, z1, gc);
           if (anti) sm = gbm_step<R>(sm, -z1, gc);
@@ -122,6 +118,8 @@ template <typename R> static void launch_eu_scheme(int scheme, dim3 grid, cudaSt
       european_fused_kernel<R, OPTMC_SCHEME_HESTON_REF_ABSORB><<<grid, kEuThreads, 0, st>>>(a); break;
     case OPTMC_SCHEME_HESTON_FULL_TRUNC:
       european_fused_kernel<R, OPTMC_SCHEME_HESTON_FULL_TRUNC><<<grid, kEuThreads, 0, st>>>(a); break;
+    case OPTMC_SCHEME_HESTON_QE:
+      european_fused_kernel<R, OPTMC_SCHEME_HESTON_QE><<<grid, kEuThreads, 0, st>>>(a); break;
     default:
       european_fused_kernel<R, OPTMC_SCHEME_HESTON_REF_CALIB><<<grid, kEuThreads, 0, st>>>(a); break;
   }
@@ -136,7 +134,7 @@ int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const op
   if (!(mp->S0 > 0)) { set_error("S0, K, T must be positive."); return OPTMC_EINVAL; }
   if (rng->z1_dev) { set_error("the fused European kernel generates its own normals"); return OPTMC_EUNSUPPORTED; }
   if (rng->antithetic && (M % 2)) { set_error("antithetic layout needs an even path count"); return OPTMC_EINVAL; }
-  if (mp->scheme < 0 || mp->scheme > OPTMC_SCHEME_HESTON_REF_CALIB) { set_error("unknown scheme"); return OPTMC_EINVAL; }
+  if (mp->scheme < 0 || mp->scheme > OPTMC_SCHEME_HESTON_QE) { set_error("unknown scheme"); return OPTMC_EINVAL; }
   for (int i = 0; i < n_options; ++i)
     if (!(K[i] > 0) || !(T[i] > 0)) { set_error("S0, K, T must be positive."); return OPTMC_EINVAL; }
 

@@ -118,6 +118,12 @@ int sweep_resident(optmc_ctx* ctx) {
   a.one.xw = reinterpret_cast<unsigned long long*>(ctx->xchg); a.one.flags = ctx->d_flags;
   a.one.betas = ctx->d_betas; a.one.bnd = ctx->d_bnd; a.one.exc = ctx->d_exc; a.one.nitm = ctx->d_nitm;
   a.one.final_out = ctx->d_final;
+  if (ctx->sharded_M_total > 0) {  // optmc_lsm_poly_sharded: in-kernel exchange with the peer ranks
+    a.comm.nranks = ctx->comm.nranks; a.comm.rank = ctx->comm.rank; a.comm.g0 = ctx->comm.g;
+    a.comm.M_total = ctx->sharded_M_total;
+    for (int r = 0; r < ctx->comm.nranks; ++r) a.comm.slots[r] = ctx->comm.peers[r];
+    ctx->comm.g += (unsigned int)sw.N;  // N - 1 Gram exchanges + the final one; every rank advances alike
+  }
   // Debug aid: OPTMC_TRACE=<file> dumps per-date phase clocks (SM cycles) of the first and last CTA.
   const char* trace_path = getenv("OPTMC_TRACE");
   long long* d_trace = nullptr;

@@ -28,7 +28,25 @@ struct ResGroup {
   double* final_out;          // [4]
 };
 
+// Path-sharded sweep over several GPUs: every rank runs this kernel on its block of paths and the
+// per-date totals are exchanged INSIDE the kernel through peer-mapped memory (NVLink), not by a host-launched
+// collective.  slots[p] is rank p's slot array [2 parities][kCommMaxRanks][kXchgWords] (slots[rank] is local,
+// the others are CUDA-IPC mappings).  Per exchange g (a counter that keeps running across launches, identical
+// on every rank): CTA 0 of rank r, once its local accumulators are complete, stores its 16 words -- the
+// 56-bit fixed-point payload with the tag g & 255 in the top byte -- into slot [g & 1][r] of EVERY rank; all
+// CTAs of a rank then poll their own rank's slots until the nranks tags match and add the payloads as
+// integers, so every CTA of every rank obtains bit-identical totals.  A slot is rewritten two exchanges later,
+// which needs all ranks' pushes of exchange g + 1, which every CTA issues only after it read exchange g.
+constexpr unsigned int kCommSpinLimit = 1u << 22;  // ~seconds: a peer that never launched must not hang the GPU
+struct ResComm {
+  int nranks = 1, rank = 0;
+  unsigned int g0 = 0;        // running exchange counter at launch
+  long long M_total = 0;      // paths of the option over all ranks
+  unsigned long long* slots[kCommMaxRanks] = {};
+};
+
 struct ResArgs {
+  ResComm comm;
   ResGroup one;               // the group of a single-option launch (groups == NULL)
   const ResGroup* groups;     // device array [G] for grouped launches
   int cpg;                    // CTAs per group
@@ -91,30 +109,62 @@ __device__ __forceinline__ double block_totals(double (&acc)[QP], double* s_red)
 // completed exchange of the same parity (0 at launch).
 template <int QN>
 __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long* xw, int par, int ncta,
-                                                 unsigned long long& prev, int* flags, int* spins_out) {
+                                                 unsigned long long& prev, int* flags, int* spins_out,
+                                                 const ResComm& cm, unsigned int seq, int cta, bool& dead) {
   const int lane = threadIdx.x & 31;
-  if (ncta == 1) {  // the option fits one CTA: its totals are the grid totals
+  if (ncta == 1 && cm.nranks == 1) {  // the option fits one CTA: its totals are the grid totals
     if (spins_out) *spins_out = 0;
     return __shfl_sync(0xffffffffu, mine, (2 * lane) & 31);
   }
   unsigned long long sum = 0ull;
   int spins = 0;
+  const bool single = cm.nranks == 1;
   if (lane < 2 * QN) {
     unsigned long long hi, lo;
     if (!fx_encode(mine, hi, lo)) atomicExch(flags, 1);
     unsigned long long* w = xw + ((size_t)par * kXchgWords + lane) * kXchgStride;
     red_relaxed_add_u64(w, (1ull << kFxCountShift) | ((lane & 1) ? lo : hi));
-    unsigned long long d;
-    do {
-      d = ld_relaxed_u64(w) - prev;
-      ++spins;
-    } while ((d >> kFxCountShift) != (unsigned long long)ncta);
-    prev += d;
-    sum = d & kFxValueMask;
+    if (single || cta == 0) {
+      unsigned long long d;
+      do {
+        d = ld_relaxed_u64(w) - prev;
+        ++spins;
+      } while ((d >> kFxCountShift) != (unsigned long long)ncta);
+      prev += d;
+      sum = d & kFxValueMask;
+    }
+    if (!single) {
+      const unsigned int g = cm.g0 + seq;
+      const unsigned long long tag = (unsigned long long)(g & 0xffu) << kFxCountShift;
+      const size_t row = (size_t)(g & 1u) * kCommMaxRanks;
+      if (cta == 0) {
+        // re-centre the biased high chunk so that the reader needs no CTA counts: |sum_hi - ncta 2^47| < 2^55
+        const unsigned long long pay =
+            (lane & 1) ? sum : (sum - ((unsigned long long)ncta << 47) + (1ull << 55)) & kFxValueMask;
+        for (int p = 0; p < cm.nranks; ++p)
+          st_relaxed_sys_u64(cm.slots[p] + (row + cm.rank) * kXchgWords + lane, tag | pay);
+      }
+      sum = 0ull;
+      const unsigned long long* mine_slots = cm.slots[cm.rank] + row * kXchgWords + lane;
+      for (int r = 0; r < cm.nranks; ++r) {
+        unsigned long long v;
+        unsigned int n = 0;
+        do {
+          v = ld_relaxed_sys_u64(mine_slots + (size_t)r * kXchgWords);
+          if ((v & ~kFxValueMask) == tag) break;
+          if (!dead && ++n >= kCommSpinLimit) dead = true;
+        } while (!dead);
+        sum += v & kFxValueMask;
+      }
+      if (dead) atomicExch(flags + 1, 1);
+      if (!(lane & 1)) sum -= (unsigned long long)cm.nranks << 55;  // two's complement: signed total of the high chunks
+    }
   }
   __syncwarp();
+  dead = __any_sync(0xffffffffu, dead);
   const unsigned long long other = __shfl_down_sync(0xffffffffu, sum, 1);
-  double tot = fx_decode(sum, other, ncta);                 // meaningful on even lanes < 2*QN
+  double tot = single ? fx_decode(sum, other, ncta)  // meaningful on even lanes < 2*QN
+                      : (double)(long long)sum * 0.0625 + (double)other * 2.220446049250313e-16;
   tot = __shfl_sync(0xffffffffu, tot, (2 * lane) & 31);     // quantity q: lane 2q -> lane q
   if (spins_out) *spins_out = spins;
   return tot;
@@ -341,6 +391,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
     for (int i = 0; i < pw; ++i) qscale *= a.invK;
   }
   unsigned long long prev0 = 0ull, prev1 = 0ull;  // warp 0: accumulator baselines of the two parities
+  bool comm_dead = false;                         // warp 0: a peer rank stopped answering (sharded sweeps)
   long long* const tr_base = (ga.trace && grp == 0 && tid == 0 && (cta == 0 || cta == ncta - 1))
                                  ? ga.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * 8 : nullptr;
 
@@ -434,7 +485,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
     if (warp == 0) {
       int spins = 0;
       unsigned long long pv = (seq & 1) ? prev1 : prev0;
-      const double tot_l = warp0_grid_sum<Q>(mine, a.xw, seq & 1, ncta, pv, a.flags, &spins);
+      const double tot_l = warp0_grid_sum<Q>(mine, a.xw, seq & 1, ncta, pv, a.flags, &spins, ga.comm, (unsigned int)seq, cta, comm_dead);
       if (seq & 1) prev1 = pv; else prev0 = pv;
       OPTMC_TRACE_AT(4);
       if (tr) tr[7] = spins;
@@ -486,10 +537,10 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
   }
   if (warp == 0) {
     unsigned long long pv = (seq & 1) ? prev1 : prev0;
-    const double tot_l = warp0_grid_sum<2>(mine, a.xw, seq & 1, ncta, pv, a.flags, nullptr);
+    const double tot_l = warp0_grid_sum<2>(mine, a.xw, seq & 1, ncta, pv, a.flags, nullptr, ga.comm, (unsigned int)seq, cta, comm_dead);
     const double s1 = __shfl_sync(0xffffffffu, tot_l, 0), s2 = __shfl_sync(0xffffffffu, tot_l, 1);
     if (cta == 0 && lane == 0) {
-      const double n = (double)a.M;
+      const double n = (double)(ga.comm.nranks > 1 ? ga.comm.M_total : a.M);
       const double mean = s1 / n;
       double var = n > 1.0 ? (s2 - n * mean * mean) / (n - 1.0) : 0.0;
       if (var < 0.0) var = 0.0;

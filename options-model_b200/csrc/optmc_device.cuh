@@ -174,6 +174,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// system scope: the word lives in (or is read back from) another GPU's memory over NVLink
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }

@@ -16,6 +16,7 @@ constexpr int kMaxResidentCtas = 160; // CTAs of the persistent sweep (B200: 148
 // which measured 25% faster than one 128-byte line per word (tools/xchg_bench.cu) -- the exchange is bound
 // by L2 request count on the hot lines, not by atomic throughput.
 constexpr int kXchgWords = 2 * kXchgMaxQ;
+constexpr int kCommMaxRanks = 8;   // ranks of a path-sharded sweep (optmc_comm_*)
 constexpr int kXchgStride = 1;
 inline size_t xchg_bytes() { return (size_t)2 * kXchgWords * kXchgStride * sizeof(unsigned long long); }
 constexpr int kMaxBeta = 4;
@@ -80,6 +81,16 @@ struct optmc_ctx {
   double* eu_out = nullptr; size_t eu_out_cap = 0;  // [n_options][3]
   double* eu_par = nullptr; size_t eu_par_cap = 0;  // [n_options][4] K, T, is_put, pad
   unsigned int* eu_tickets = nullptr; size_t eu_tickets_cap = 0;
+
+  // path-sharded sweeps: peer-mapped exchange slots (optmc_comm_*; lsm_resident_kernel.cuh: ResComm)
+  struct Comm {
+    int nranks = 0, rank = 0;
+    unsigned int g = 2;                      // running exchange counter (tags 2, 3 differ from the zeroed slots)
+    unsigned long long* local = nullptr;     // this rank's slot array
+    unsigned long long* peers[optmc::kCommMaxRanks] = {};       // peers[rank] == local; the others are cudaIpcOpenMemHandle mappings
+    bool opened[optmc::kCommMaxRanks] = {};
+  } comm;
+  int64_t sharded_M_total = 0;               // > 0 while optmc_lsm_poly_sharded runs its sweep
 
   optmc::SweepDesc sw;
 };

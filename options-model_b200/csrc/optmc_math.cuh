@@ -175,6 +175,70 @@ template <typename R> OPTMC_HD void heston_calib_step(R& S, R& v, R z1, R z2, co
   S = S + dS;
 }
 
+// Andersen's quadratic-exponential scheme (L. Andersen, "Simple and efficient simulation of the Heston stochastic
+// volatility model", J. Comp. Finance 11(3), 2008, sections 3.2.4 and 4.2; gamma1 = gamma2 = 1/2, no martingale
+// correction).  Not in the reference: the variance is sampled from a distribution matched to the
+// first two conditional moments of the CIR step -- a squared Gaussian when psi = s^2/m^2 <= 1.5, a mass at zero
+// plus an exponential tail otherwise -- and stays non-negative.  z1 drives the asset, z2 the variance (the
+// correlation enters through K0..K4); the uniform of the exponential branch is Phi(z2), so the antithetic
+// partner (-z1, -z2) sees 1 - U.  Restated in oracle.lsm_oracle.heston_paths_qe.
+template <typename R> struct QeConsts {
+  R E, c1, c2, theta1mE;      // exp(-kappa dt); xi^2 E (1-E)/kappa; theta xi^2 (1-E)^2/(2 kappa); theta (1-E)
+  R k0r, k1, k2, k3, k4;      // r dt + K0, K1..K4
+};
+template <typename R> OPTMC_HD QeConsts<R> qe_consts(const HestonConsts<R>& c) {
+  QeConsts<R> q;
+  const double dt = (double)c.dt, kappa = (double)c.kappa, theta = (double)c.theta, xi = (double)c.xi, rho = (double)c.rho;
+  const double E = exp(-kappa * dt);
+  q.E = (R)E;
+  q.c1 = (R)(xi * xi * E * (1.0 - E) / kappa);
+  q.c2 = (R)(theta * xi * xi * (1.0 - E) * (1.0 - E) / (2.0 * kappa));
+  q.theta1mE = (R)(theta * (1.0 - E));
+  const double a = kappa * rho / xi - 0.5;
+  q.k0r = (R)((double)c.r * dt - rho * kappa * theta * dt / xi);
+  q.k1 = (R)(0.5 * dt * a - rho / xi);
+  q.k2 = (R)(0.5 * dt * a + rho / xi);
+  q.k3 = (R)(0.5 * dt * (1.0 - rho * rho));
+  q.k4 = q.k3;
+  return q;
+}
+OPTMC_HD double norm_cdf(double z) { return 0.5 * erfc(-z * 0.70710678118654752440); }
+OPTMC_HD float norm_cdf(float z) { return 0.5f * erfcf(-z * 0.70710678118654752440f); }
+OPTMC_HD double log_any(double x) { return log(x); }
+OPTMC_HD float log_any(float x) { return logf(x); }
+template <typename R> OPTMC_HD void heston_qe_step(R& S, R& v, R z1, R z2, const QeConsts<R>& q) {
+  const R m = q.theta1mE + v * q.E;
+  const R s2 = v * q.c1 + q.c2;
+  const R psi = s2 / (m * m);
+  R vn;
+  if (!(m > (R)0)) {
+    vn = (R)0;
+  } else if (psi <= (R)1.5) {
+    const R ip = (R)2 / psi;                                        // >= 4/3
+    const R b2 = ip - (R)1 + Real<R>::sqrt_(ip) * Real<R>::sqrt_(ip - (R)1);
+    const R a = m / ((R)1 + b2);
+    const R bz = Real<R>::sqrt_(b2) + z2;
+    vn = a * bz * bz;
+  } else {
+    const R p = (psi - (R)1) / (psi + (R)1);
+    const R beta = ((R)1 - p) / m;
+    const R u = norm_cdf(z2);
+    vn = u <= p ? (R)0 : log_any(((R)1 - p) / norm_cdf(-z2)) / beta;
+  }
+  const R var = q.k3 * v + q.k4 * vn;
+  S = S * Real<R>::exp_(q.k0r + q.k1 * v + q.k2 * vn + Real<R>::sqrt_(var) * z1);
+  v = vn;
+}
+
+// Scheme dispatch shared by the path and the fused European kernels (scheme ids: include/optmc.h).
+template <typename R, int SCHEME>
+OPTMC_HD void heston_step_any(R& S, R& v, R z1, R z2, const HestonConsts<R>& c, const QeConsts<R>& q) {
+  if (SCHEME == 2) heston_absorb_step<R>(S, v, z1, z2, c);
+  else if (SCHEME == 3) heston_fulltrunc_step<R>(S, v, z1, z2, c);
+  else if (SCHEME == 5) heston_qe_step<R>(S, v, z1, z2, q);
+  else heston_calib_step<R>(S, v, z1, z2, c);
+}
+
 // fp32 production form of the two Euler schemes for one antithetic pair (+z, -z): the drift / diffusion
 // constants are pre-folded (log2 e into the exponent so the exponential is one MUFU.EX2), and everything the
 // two partners share (w2, z1 log2 e) is computed once.  Algebraically identical to heston_absorb_step /

@@ -38,13 +38,6 @@ __device__ __forceinline__ double load_z(const void* z, int is_f64, long long id
   return is_f64 ? static_cast<const double*>(z)[idx] : (double)static_cast<const float*>(z)[idx];
 }
 
-template <typename R, int SCHEME> __device__ __forceinline__ void heston_step(R& S, R& v, R z1, R z2,
-                                                                              const HestonConsts<R>& c) {
-  if (SCHEME == OPTMC_SCHEME_HESTON_REF_ABSORB) heston_absorb_step<R>(S, v, z1, z2, c);
-  else if (SCHEME == OPTMC_SCHEME_HESTON_FULL_TRUNC) heston_fulltrunc_step<R>(S, v, z1, z2, c);
-  else heston_calib_step<R>(S, v, z1, z2, c);
-}
-
 template <typename R, int SCHEME> struct FastPair { static constexpr bool value = false; };
 template <> struct FastPair<float, OPTMC_SCHEME_HESTON_REF_ABSORB> { static constexpr bool value = true; };
 template <> struct FastPair<float, OPTMC_SCHEME_HESTON_FULL_TRUNC> { static constexpr bool value = true; };
@@ -67,6 +60,8 @@ __device__ __forceinline__ void paths_body(const PathArgs& a) {
   hc.xi = (R)a.xi; hc.rho = (R)a.rho; hc.rho_c = (R)a.rho_c;
   HestonPairF32 hf{};
   if constexpr (FAST) hf = heston_pair_consts(hc);
+  QeConsts<R> qe{};
+  if constexpr (SCHEME == OPTMC_SCHEME_HESTON_QE) qe = qe_consts(hc);
 
   R sp[VEC], sm[VEC], vp[VEC], vm[VEC], out[VEC];
   const R s_init = LOGSPACE ? (R)log(fmax(a.S0, 1e-12)) : (R)a.S0;
@@ -131,7 +126,7 @@ __device__ __forceinline__ void paths_body(const PathArgs& a) {
       }
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        if (HES) heston_step<R, SCHEME>(sp[i], vp[i], z1[i], z2[i], hc);
+        if (HES) heston_step_any<R, SCHEME>(sp[i], vp[i], z1[i], z2[i], hc, qe);
         else if (LOGSPACE) sp[i] = sp[i] + (gc.drift + gc.diffusion * z1[i]);
         else sp[i] = gbm_step<R>(sp[i], z1[i], gc);
         out[i] = LOGSPACE ? Real<R>::exp_(sp[i]) : sp[i];
@@ -141,7 +136,7 @@ __device__ __forceinline__ void paths_body(const PathArgs& a) {
       if (anti) {
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
-          if (HES) heston_step<R, SCHEME>(sm[i], vm[i], -z1[i], -z2[i], hc);
+          if (HES) heston_step_any<R, SCHEME>(sm[i], vm[i], -z1[i], -z2[i], hc, qe);
           else if (LOGSPACE) sm[i] = sm[i] + (gc.drift - gc.diffusion * z1[i]);
           else sm[i] = gbm_step<R>(sm[i], -z1[i], gc);
           out[i] = LOGSPACE ? Real<R>::exp_(sm[i]) : sm[i];
@@ -198,6 +193,7 @@ template <typename R> static int launch_t1(optmc_ctx* ctx, int scheme, const Pat
     case OPTMC_SCHEME_HESTON_REF_ABSORB: return launch_t2<R, OPTMC_SCHEME_HESTON_REF_ABSORB>(ctx, a, extz, vec4);
     case OPTMC_SCHEME_HESTON_FULL_TRUNC: return launch_t2<R, OPTMC_SCHEME_HESTON_FULL_TRUNC>(ctx, a, extz, vec4);
     case OPTMC_SCHEME_HESTON_REF_CALIB: return launch_t2<R, OPTMC_SCHEME_HESTON_REF_CALIB>(ctx, a, extz, vec4);
+    case OPTMC_SCHEME_HESTON_QE: return launch_t2<R, OPTMC_SCHEME_HESTON_QE>(ctx, a, extz, vec4);
   }
   set_error("unknown scheme");
   return OPTMC_EINVAL;
@@ -341,6 +337,7 @@ template <typename R, int VEC> static void launch_batch_scheme(int scheme, dim3 
     case OPTMC_SCHEME_GBM_LOGSPACE: paths_batch_kernel<R, OPTMC_SCHEME_GBM_LOGSPACE, VEC><<<grid, block, 0, st>>>(d); break;
     case OPTMC_SCHEME_HESTON_REF_ABSORB: paths_batch_kernel<R, OPTMC_SCHEME_HESTON_REF_ABSORB, VEC><<<grid, block, 0, st>>>(d); break;
     case OPTMC_SCHEME_HESTON_FULL_TRUNC: paths_batch_kernel<R, OPTMC_SCHEME_HESTON_FULL_TRUNC, VEC><<<grid, block, 0, st>>>(d); break;
+    case OPTMC_SCHEME_HESTON_QE: paths_batch_kernel<R, OPTMC_SCHEME_HESTON_QE, VEC><<<grid, block, 0, st>>>(d); break;
     default: paths_batch_kernel<R, OPTMC_SCHEME_HESTON_REF_CALIB, VEC><<<grid, block, 0, st>>>(d); break;
   }
 }

@@ -94,6 +94,13 @@ def _torch_dtype(code: int):
     return torch.float64 if code == L.F64 else torch.float32
 
 
+def workspace_estimate(M: int, N: int, dtype="f32", n_options: int = 1) -> int:
+    """Upper estimate of the device memory price_american(_batch) allocates; needs no GPU."""
+    b = C.c_int64()
+    L.check(L.load_library().optmc_workspace_bytes(int(M), int(N), _dtype_code(dtype), int(n_options), C.byref(b)))
+    return int(b.value)
+
+
 class Engine:
     """One context per (device, host thread).  Not thread-safe (SURVEY.md 8(b) threading)."""
 
@@ -113,6 +120,12 @@ class Engine:
         info = (C.c_int64 * 4)()
         L.check(self.lib.optmc_ctx_device_info(self._h, info))
         self.sm_count, self.l2_bytes, self.max_smem, self.cc = (int(x) for x in info)
+
+    def workspace_bytes(self) -> int:
+        """Device bytes the context holds right now (the library's own workspaces; they only grow)."""
+        b = C.c_int64()
+        L.check(self.lib.optmc_ctx_workspace_bytes(self._h, C.byref(b)))
+        return int(b.value)
 
     # -- lifecycle ------------------------------------------------------------------------------
     def close(self):
@@ -236,6 +249,36 @@ class Engine:
         p = 3 if lp.basis == L.BASIS_POLY2 else 4
         res, keep = self._result_block(N, p, arrays)
         L.check(self.lib.optmc_lsm_poly(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), C.byref(res)))
+        return self._to_result(res, keep)
+
+    # -- path-sharded sweep: in-kernel exchange over NVLink peer memory (include/optmc.h, optmc_comm_*) -------
+    def comm_export(self) -> bytes:
+        buf = C.create_string_buffer(L.COMM_HANDLE_BYTES)
+        L.check(self.lib.optmc_comm_export(self._h, buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, nranks: int, handles) -> None:
+        blob = b"".join(handles)
+        assert len(blob) == nranks * L.COMM_HANDLE_BYTES
+        L.check(self.lib.optmc_comm_init(self._h, int(rank), int(nranks), C.c_char_p(blob)))
+
+    def comm_finalize(self) -> None:
+        L.check(self.lib.optmc_comm_finalize(self._h))
+
+    def lsm_sharded(self, S_local, M_total: int, K, r, T, option_type="put", basis="poly2", semantics="reference",
+                    arrays=False, M: Optional[int] = None):
+        """This rank's part of a path-sharded sweep; every rank must call it (same order).  Returns the GLOBAL
+        price / stderr / betas / n_itm; ex_count / boundary cover this rank's paths."""
+        assert S_local.is_cuda and S_local.dim() == 2 and S_local.stride(1) == 1
+        N = S_local.shape[0] - 1
+        M = int(M if M is not None else S_local.shape[1])
+        lp = self._lsm_params(K, r, T, option_type, basis, semantics, "resident")
+        code = L.F64 if S_local.dtype == self.torch.float64 else L.F32
+        p = 3 if lp.basis == L.BASIS_POLY2 else 4
+        res, keep = self._result_block(N, p, arrays)
+        self._sync_stream()
+        L.check(self.lib.optmc_lsm_poly_sharded(self._h, S_local.data_ptr(), S_local.stride(0), M, int(M_total), N, code,
+                                                C.byref(lp), C.byref(res)))
         return self._to_result(res, keep)
 
     def lsm_global(self, S, K, r, T, option_type="put", semantics="reference", arrays=True, M: Optional[int] = None):

@@ -65,3 +65,39 @@ def sweep_sharded(engine, dist, S_local, K, r, T, option_type="put", basis="poly
     dt = T / N
     scale = 1.0 if semantics in ("reference", 3) else math.exp(-r * dt)
     return ShardedResult(mean * scale, math.sqrt(var / n) * scale, int(round(n)), ncoll)
+
+
+def init_peer_exchange(engine, dist, group=None) -> None:
+    """Wire the in-kernel exchange of ``sweep_sharded_fused``: every rank exports the CUDA-IPC handle of its
+    exchange slots, the handles are all-gathered over the process group (host plumbing), every rank maps its peers."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = engine.comm_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    engine.comm_init(rank, world, handles)
+    dist.barrier(group=group)  # nobody launches before every rank has mapped (and zeroed) its slots
+
+
+def sweep_sharded_fused(engine, dist, S_local, M_total, K, r, T, option_type="put", basis="poly2",
+                        semantics="reference", group=None, arrays=False):
+    """The same sweep as ``sweep_sharded`` in ONE kernel launch per rank: the per-date totals travel between the
+    GPUs inside the persistent kernel (peer stores over NVLink), so the 251 host-launched collectives of the
+    NCCL variant disappear from the data path.  Requires ``init_peer_exchange`` once per process group.
+    Every rank returns the global price; with ``arrays`` the per-rank exercise counts / boundaries are combined
+    over the group (that combine is host plumbing after the sweep, not part of it)."""
+    res = engine.lsm_sharded(S_local, M_total, K, r, T, option_type, basis, semantics, arrays=arrays)
+    if arrays and dist.get_world_size(group) > 1:
+        import torch
+
+        dev = S_local.device
+        exc = torch.as_tensor(res.ex_count, device=dev)
+        dist.all_reduce(exc, op=dist.ReduceOp.SUM, group=group)
+        res.ex_count = exc.cpu().numpy()
+        put = option_type == "put"
+        bnd = torch.as_tensor(np.nan_to_num(res.boundary, nan=-np.inf if put else np.inf), device=dev)
+        dist.all_reduce(bnd, op=dist.ReduceOp.MAX if put else dist.ReduceOp.MIN, group=group)
+        b = bnd.cpu().numpy()
+        b[~np.isfinite(b)] = np.nan
+        res.boundary = b
+    return res

@@ -195,6 +195,74 @@ def heston_paths_full_truncation(S0, r, T, v0, kappa, theta, xi, rho, M, N, Z1_h
     return S
 
 
+def _norm_cdf(z):
+    from math import erfc
+    return 0.5 * np.vectorize(erfc, otypes=[np.float64])(-z * 0.70710678118654752440)
+
+
+def heston_paths_qe(S0, r, T, v0, kappa, theta, xi, rho, M, N, Z1_half, Z2_half, return_v=False):
+    """Andersen's quadratic-exponential scheme (NOT in the reference; north-star scheme).
+
+    L. Andersen, "Simple and efficient simulation of the Heston stochastic volatility model", J. Comp. Finance
+    11(3), 2008: variance by moment matching (sec. 3.2: squared Gaussian for psi <= 1.5, mass at zero + exponential
+    tail otherwise), log-asset by the central discretisation of sec. 4.2 with gamma1 = gamma2 = 1/2, no martingale
+    correction.  z1 drives the asset, z2 the variance; the exponential branch uses U = Phi(z2).
+    """
+    dt = T / N
+    E = np.exp(-kappa * dt)
+    c1 = xi * xi * E * (1 - E) / kappa
+    c2 = theta * xi * xi * (1 - E) ** 2 / (2 * kappa)
+    a_ = kappa * rho / xi - 0.5
+    k0r = r * dt - rho * kappa * theta * dt / xi
+    k1 = 0.5 * dt * a_ - rho / xi
+    k2 = 0.5 * dt * a_ + rho / xi
+    k3 = 0.5 * dt * (1 - rho * rho)
+    S = np.zeros((N + 1, M), dtype=np.float64)
+    V = np.zeros((N + 1, M), dtype=np.float64)
+    S[0] = S0
+    V[0] = v0
+    v = np.full(M, v0, dtype=np.float64)
+    for t in range(1, N + 1):
+        z1 = np.concatenate([Z1_half[t - 1], -Z1_half[t - 1]])
+        z2 = np.concatenate([Z2_half[t - 1], -Z2_half[t - 1]])
+        m = theta * (1 - E) + v * E
+        s2 = v * c1 + c2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            psi = s2 / (m * m)
+            ip = 2.0 / psi
+            b2 = ip - 1 + np.sqrt(ip) * np.sqrt(np.maximum(ip - 1, 0))
+            vq = m / (1 + b2) * (np.sqrt(b2) + z2) ** 2
+            p = (psi - 1) / (psi + 1)
+            beta = (1 - p) / m
+            ve = np.where(_norm_cdf(z2) <= p, 0.0, np.log((1 - p) / _norm_cdf(-z2)) / beta)
+        vn = np.where(m > 0, np.where(psi <= 1.5, vq, ve), 0.0)
+        S[t] = S[t - 1] * np.exp(k0r + k1 * v + k2 * vn + np.sqrt(k3 * v + k3 * vn) * z1)
+        v = vn
+        V[t] = v
+    return (S, V) if return_v else S
+
+
+def heston_european_analytic(S0, K, r, T, v0, kappa, theta, xi, rho, option_type="call", n=4000, umax=200.0):
+    """Semi-analytic Heston price (characteristic function in the 'little trap' form of Albrecher et al. 2007,
+    Gil-Pelaez inversion, composite midpoint rule).  Test infrastructure for the non-parity schemes."""
+    u = (np.arange(n) + 0.5) * (umax / n)
+    x = np.log(S0)
+
+    def cf(w):
+        d = np.sqrt((rho * xi * 1j * w - kappa) ** 2 + xi * xi * (1j * w + w * w))
+        g = (kappa - rho * xi * 1j * w - d) / (kappa - rho * xi * 1j * w + d)
+        ed = np.exp(-d * T)
+        C = r * 1j * w * T + kappa * theta / xi**2 * ((kappa - rho * xi * 1j * w - d) * T - 2 * np.log((1 - g * ed) / (1 - g)))
+        D = (kappa - rho * xi * 1j * w - d) / xi**2 * (1 - ed) / (1 - g * ed)
+        return np.exp(C + D * v0 + 1j * w * x)
+
+    k = np.log(K)
+    p1 = 0.5 + np.sum(np.real(np.exp(-1j * u * k) * cf(u - 1j) / (1j * u * cf(-1j)))) * (umax / n) / np.pi
+    p2 = 0.5 + np.sum(np.real(np.exp(-1j * u * k) * cf(u) / (1j * u))) * (umax / n) / np.pi
+    call = S0 * p1 - K * np.exp(-r * T) * p2
+    return call if option_type == "call" else call - S0 + K * np.exp(-r * T)
+
+
 # --------------------------------------------------------------------------------------
 # Path simulation (torch fp32 variants, restated in numpy float32)
 # --------------------------------------------------------------------------------------

@@ -13,13 +13,14 @@ void hs_philox(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   for (int i = 0; i < 4; ++i) out[i] = p.v[i];
 }
 
-// step-major paths [(N+1)][M] from external normals [N][M/2], antithetic layout; scheme: 2 absorb, 3 full trunc, 4 calib
+// step-major paths [(N+1)][M] from external normals [N][M/2], antithetic layout; scheme: 2 absorb, 3 full trunc, 4 calib, 5 QE
 void hs_heston_paths(int scheme, double S0, double v0, double r, double T, double kappa, double theta, double xi,
                      double rho, long M, int N, const double* z1, const double* z2, double* S, double* V) {
   HestonConsts<double> c;
   c.dt = T / N; c.sqrt_dt = sqrt(c.dt); c.r = r; c.kappa = kappa; c.theta = theta; c.xi = xi; c.rho = rho;
   c.rho_c = sqrt(1.0 - rho * rho);
   long Mh = M / 2;
+  const QeConsts<double> q = qe_consts(c);
   for (long j = 0; j < M; ++j) { S[j] = S0; if (V) V[j] = v0; }
   for (long j = 0; j < Mh; ++j) {
     double sp = S0, sm = S0, vp = v0, vm = v0;
@@ -27,6 +28,7 @@ void hs_heston_paths(int scheme, double S0, double v0, double r, double T, doubl
       double a = z1[(long)(t - 1) * Mh + j], b = z2[(long)(t - 1) * Mh + j];
       if (scheme == 2) { heston_absorb_step<double>(sp, vp, a, b, c); heston_absorb_step<double>(sm, vm, -a, -b, c); }
       else if (scheme == 3) { heston_fulltrunc_step<double>(sp, vp, a, b, c); heston_fulltrunc_step<double>(sm, vm, -a, -b, c); }
+      else if (scheme == 5) { heston_qe_step<double>(sp, vp, a, b, q); heston_qe_step<double>(sm, vm, -a, -b, q); }
       else { heston_calib_step<double>(sp, vp, a, b, c); heston_calib_step<double>(sm, vm, -a, -b, c); }
       S[(long)t * M + j] = sp; S[(long)t * M + Mh + j] = sm;
       if (V) { V[(long)t * M + j] = vp; V[(long)t * M + Mh + j] = vm; }

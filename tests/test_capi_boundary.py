@@ -68,3 +68,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_workspace_estimate_needs_no_gpu(lib):
+    import ctypes as C
+
+    from options_model_b200 import engine as E
+
+    b1 = E.workspace_estimate(1_000_000, 252, "f32", 1)
+    assert 1_000_000 * 253 * 4 <= b1 <= 1.02 * 1_000_000 * 253 * 4 + (8 << 20)
+    assert E.workspace_estimate(1_000_000, 252, "f64", 4) >= 4 * 1_000_000 * 253 * 8
+    assert E.workspace_estimate(10_000, 50, "f32", 5000) == E.workspace_estimate(10_000, 50, "f32", 160)  # waves
+    out = C.c_int64()
+    assert lib.load_library().optmc_workspace_bytes(0, 10, 0, 1, C.byref(out)) == -1

@@ -704,3 +704,51 @@ def test_compat_om2_option_pricer_nn_and_poly(mods):
     with pytest.raises(NotImplementedError):
         compat.OptionPricer(100.0, 0.05, 0.2, "put", nn_hidden=64).price_american_option(100.0, 1.0, 1000, 5)
     assert compat.compute_curve_worker(-1.0, 100.0, 0.05, 0.2, "put", 2, 1, 1, 2, 100, False, False, None) == []
+
+
+# ------------------------------------------------------------------------------------------------------
+# Andersen QE scheme (north-star scheme, not in the reference: oracle = the published algorithm restated in
+# oracle.lsm_oracle.heston_paths_qe; accuracy pinned by the semi-analytic Heston price)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-9), ("f32", 2e-3)])
+def test_qe_paths_vs_oracle_same_draws(eng, mods, dtype, tol):
+    L, E, orc = mods
+    M, N = 4096, 24
+    Z1, Z2 = orc.draw_heston_normals(np.random.default_rng(21), N, M)
+    model = E.heston(100.0, 0.05, 1.0, **HP, scheme=L.SCHEME_HESTON_QE)
+    S, V = eng.paths(model, M, N, dtype, E.RngSpec(z1=_dev(Z1), z2=_dev(Z2)), return_v=True)
+    ref, Vref = orc.heston_paths_qe(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2,
+                                    return_v=True)
+    Sn, Vn = S.cpu().numpy().astype(np.float64), V.cpu().numpy().astype(np.float64)
+    if dtype == "f64":
+        np.testing.assert_allclose(Sn, ref, rtol=tol)
+        np.testing.assert_allclose(Vn, Vref, rtol=tol, atol=1e-14)
+        assert (Vn >= 0).all() and (Vn == 0).any()  # the mass at zero of the exponential branch is exercised
+    else:  # fp32 state: a path whose psi sits at the 1.5 switch may take the other branch; compare in bulk
+        rel = np.abs(Sn[-1] - ref[-1]) / ref[-1]
+        assert np.median(rel) < 1e-5 and np.mean(rel < tol) > 0.99
+
+
+def test_qe_european_unbiased_at_coarse_steps(eng, mods):
+    """8 steps per year: QE reproduces the semi-analytic Heston put within 3 standard errors, the reference's
+    absorption Euler is off by far more (the reason the scheme exists)."""
+    L, E, orc = mods
+    M, N = 4_000_000, 8
+    exact = orc.heston_european_analytic(100.0, 100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], "put")
+    out = {}
+    for name, sch in (("qe", L.SCHEME_HESTON_QE), ("absorb", L.SCHEME_HESTON_REF_ABSORB)):
+        model = E.heston(100.0, 0.05, 1.0, **HP, scheme=sch)
+        mean, se = eng.price_european_batch(model, M, N, [100.0], [1.0], [1], "f32", E.RngSpec(seed=3))
+        out[name] = (mean[0], se[0])
+    assert abs(out["qe"][0] - exact) < 3 * out["qe"][1]
+    assert abs(out["absorb"][0] - exact) > 10 * out["absorb"][1]
+
+
+def test_qe_american_batch_runs_through_the_sweep(eng, mods):
+    L, E, orc = mods
+    model = E.heston(100.0, 0.05, 1.0, **HP, scheme=L.SCHEME_HESTON_QE)
+    res = eng.price_american(model, 200_000, 50, 100.0, "put", "f32", E.RngSpec(seed=9), semantics="textbook")
+    eu = orc.heston_european_analytic(100.0, 100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], "put")
+    assert eu - 3 * res.stderr < res.price < eu + 1.0  # early-exercise premium of an ATM 1y put: a few tenths
+    pb, _ = eng.price_american_batch(model, 200_000, 100.0, [100.0], [1.0], [50], 1, "f32", E.RngSpec(seed=9), semantics="textbook")
+    assert pb[0] == pytest.approx(res.price, rel=1e-6)

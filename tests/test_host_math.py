@@ -38,7 +38,7 @@ def test_philox_kat(hs):
         assert list(o) == exp
 
 
-@pytest.mark.parametrize("scheme", [2, 3, 4])
+@pytest.mark.parametrize("scheme", [2, 3, 4, 5])
 def test_heston_step_functions_vs_oracle(hs, scheme):
     rng = np.random.default_rng(4)
     M, N = 256, 40
@@ -51,11 +51,17 @@ def test_heston_step_functions_vs_oracle(hs, scheme):
         ref = orc.heston_paths_antithetic(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2)
     elif scheme == 3:
         ref = orc.heston_paths_full_truncation(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2)
+    elif scheme == 5:
+        ref, Vref = orc.heston_paths_qe(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, Z1, Z2,
+                                        return_v=True)
+        np.testing.assert_allclose(V, Vref, rtol=1e-9, atol=1e-15)
+        psi_hi = (V[:-1] * 0 + 1).sum()  # both branches are exercised with the Feller-violating parameters
+        assert (V == 0).any() and (V > 0.05).any() and psi_hi > 0
     else:  # calibrator: path-major, Z given path-major (n_sim, N)
         Sp, _ = orc.hc_simulate_paths(HP["kappa"], HP["theta"], HP["xi"], HP["rho"], HP["v0"], 100.0, 1.0, 0.05, M, N,
                                       np.ascontiguousarray(Z1.T), np.ascontiguousarray(Z2.T))
         ref = Sp.T
-    np.testing.assert_allclose(S, ref, rtol=1e-12)
+    np.testing.assert_allclose(S, ref, rtol=1e-9 if scheme == 5 else 1e-12)
     if scheme == 2:
         assert (V >= 0).all() and (V == 0).any()  # the absorption at zero is exercised (Feller violated)
 
