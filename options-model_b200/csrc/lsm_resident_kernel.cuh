@@ -144,18 +144,23 @@ __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long
         for (int p = 0; p < cm.nranks; ++p)
           st_relaxed_sys_u64(cm.slots[p] + (row + cm.rank) * kXchgWords + lane, tag | pay);
       }
-      sum = 0ull;
+      // all ranks' words are polled together (independent loads in flight: one L2 round trip per sweep of the slots)
       const unsigned long long* mine_slots = cm.slots[cm.rank] + row * kXchgWords + lane;
-      for (int r = 0; r < cm.nranks; ++r) {
-        unsigned long long v;
-        unsigned int n = 0;
-        do {
-          v = ld_relaxed_sys_u64(mine_slots + (size_t)r * kXchgWords);
-          if ((v & ~kFxValueMask) == tag) break;
-          if (!dead && ++n >= kCommSpinLimit) dead = true;
-        } while (!dead);
-        sum += v & kFxValueMask;
+      unsigned long long v[kCommMaxRanks];
+      unsigned int n = 0;
+      for (;;) {
+#pragma unroll
+        for (int r = 0; r < kCommMaxRanks; ++r)
+          v[r] = r < cm.nranks ? ld_relaxed_sys_u64(mine_slots + (size_t)r * kXchgWords) : tag;
+        bool all = true;
+#pragma unroll
+        for (int r = 0; r < kCommMaxRanks; ++r) all &= (v[r] & ~kFxValueMask) == tag;
+        if (all || dead) break;
+        if (++n >= kCommSpinLimit) dead = true;
       }
+      sum = 0ull;
+#pragma unroll
+      for (int r = 0; r < kCommMaxRanks; ++r) sum += v[r] & kFxValueMask;
       if (dead) atomicExch(flags + 1, 1);
       if (!(lane & 1)) sum -= (unsigned long long)cm.nranks << 55;  // two's complement: signed total of the high chunks
     }

@@ -69,14 +69,26 @@ def sweep_sharded(engine, dist, S_local, K, r, T, option_type="put", basis="poly
 
 def init_peer_exchange(engine, dist, group=None) -> None:
     """Wire the in-kernel exchange of ``sweep_sharded_fused``: every rank exports the CUDA-IPC handle of its
-    exchange slots, the handles are all-gathered over the process group (host plumbing), every rank maps its peers."""
+    exchange slots, the handles are all-gathered over the process group (host plumbing), every rank maps its peers.
+    Raises on EVERY rank if any rank failed to map a peer (so no rank is left waiting for the others)."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    mine = engine.comm_export()
+    err = None
+    try:
+        mine = engine.comm_export()
+    except Exception as e:  # noqa: BLE001 -- reported collectively below
+        mine, err = b"", e
     handles = [None] * world
     dist.all_gather_object(handles, mine, group=group)
-    engine.comm_init(rank, world, handles)
-    dist.barrier(group=group)  # nobody launches before every rank has mapped (and zeroed) its slots
+    if err is None and all(len(h) == len(mine) for h in handles):
+        try:
+            engine.comm_init(rank, world, handles)
+        except Exception as e:  # noqa: BLE001
+            err = e
+    oks = [None] * world
+    dist.all_gather_object(oks, err is None, group=group)  # also the barrier: nobody launches before all mapped
+    if not all(oks):
+        raise RuntimeError(f"peer exchange unavailable (ranks ok: {oks}): {err}")
 
 
 def sweep_sharded_fused(engine, dist, S_local, M_total, K, r, T, option_type="put", basis="poly2",
