@@ -234,6 +234,57 @@ int optmc_mlp_init_params(int32_t hidden, uint64_t seed, int32_t date, float* ou
 int optmc_mlp_grad_debug(optmc_ctx* ctx, int32_t hidden, int64_t n, const float* xs, const float* ys, const float* params,
                          float* grads, float* cont);
 
+/* ---- global network LSM: the reference's v3 algorithm with its own regressor (om3:482-651, om3gpu:695-833) ----
+ * Pass 1 collects the in-the-money rows of every date (features om3:105-121, targets = discounted terminal
+ * payoffs), the features and the target are z-scored (om3:550-563), ONE SingleLSMNet(7, 128, 3) (om3:85-103) is
+ * trained on all rows by mini-batch Adam (om3:565-613), pass 2 decides with the network (om3:615-651).  The 128x128
+ * layers, forward and backward, run on the tcgen05 tensor cores (bf16 operands, fp32 accumulation).  Defaults of
+ * the two reference variants:
+ *   CPU  (om3:565-613):     batch 256, Adam + L2 weight decay 1e-5, ReduceLROnPlateau(patience 5, factor 0.5,
+ *                           min_lr 1e-6), <= 25 epochs, early stop after 8 epochs without a 1e-6 improvement of
+ *                           the mean training loss, best weights restored, population std of the target;
+ *   GPU  (om3gpu:740-798):  batch <= 8192, AdamW (decoupled) 1e-4, no scheduler, patience 3, sample std.
+ * Initial weights (torch's default Linear range), the per-epoch shuffle and the dropout masks come from counter-based
+ * generators keyed by `seed`: runs are reproducible, and agree with the reference statistically (its streams are
+ * torch's global RNG). */
+typedef struct optmc_gnet_params {
+  int32_t hidden;             /* 128 (nn_hidden default, om3:347) */
+  int32_t layers;             /* 3 hidden layers (SingleLSMNet num_layers) */
+  int32_t epochs;             /* nn_epochs, default 25 */
+  int32_t batch;              /* 256 (CPU variant) .. 8192 (GPU variant); <= 131072 */
+  double lr;                  /* nn_lr, default 1e-3 */
+  double weight_decay;        /* 1e-5 (Adam L2) / 1e-4 (AdamW) */
+  int32_t decoupled_wd;       /* 0 = torch.optim.Adam(weight_decay), 1 = AdamW */
+  int32_t sched_patience;     /* ReduceLROnPlateau patience; 0 = no scheduler */
+  double sched_factor;        /* 0.5 */
+  double min_lr;              /* 1e-6 */
+  int32_t stop_patience;      /* early stopping patience (8 / 3); 0 = never */
+  int32_t target_ddof;        /* 0 = population std (np.std, om3:552), 1 = sample std (torch.std, om3gpu:731) */
+  double min_delta;           /* improvement threshold of the best-weights snapshot, 1e-6 (om3:599) */
+  double dropout;             /* 0.1; realised as the nearest multiple of 1/256 */
+  int32_t inference_dropout;  /* pass 2 with dropout active: 1 / 0; -1 = as the reference under reference semantics
+                                 (the net is never switched to eval mode), off under textbook */
+  int32_t reserved;
+  uint64_t seed;
+} optmc_gnet_params;
+
+typedef struct optmc_gnet_result {
+  double price, stderr_;
+  int64_t n_paths, n_rows;    /* n_rows = regression rows collected in pass 1 */
+  int32_t epochs_run, n_launches;
+  double best_loss, final_lr; /* mean batch MSE (normalised target) of the restored weights; learning rate at the end */
+  double* boundary;           /* host [(N+1)] or NULL */
+  int64_t* ex_count;          /* host [(N+1)] or NULL */
+} optmc_gnet_result;
+
+int optmc_lsm_gnet(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                   const optmc_lsm_params* lp /* basis ignored */, const optmc_gnet_params* gp, optmc_gnet_result* out);
+/* Test aid: mean-squared-error loss and its gradient for one batch of n <= 16384 host rows given as NORMALISED
+ * features feat[n][7] and targets ys[n], at host params[34177] in the order W1[128][7] b1 W2[128][128] b2
+ * W3[128][128] b3 w4[128] b4 (torch state_dict order), without dropout. */
+int optmc_gnet_grad_debug(optmc_ctx* ctx, int64_t n, const float* feat, const float* ys, const float* params, float* grads,
+                          float* loss);
+
 /* Per-date building blocks for path-sharded multi-GPU sweeps: the host all-reduces `gram_dev`
  * (optmc_lsm_gram_len doubles) between the two calls. */
 int optmc_lsm_gram_len(int32_t basis);

@@ -59,6 +59,20 @@ class MlpParams(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("epochs", C.c_int32), ("lr", C.c_double), ("seed", C.c_uint64)]
 
 
+class GnetParams(C.Structure):  # optmc_gnet_params
+    _fields_ = [("hidden", C.c_int32), ("layers", C.c_int32), ("epochs", C.c_int32), ("batch", C.c_int32),
+                ("lr", C.c_double), ("weight_decay", C.c_double), ("decoupled_wd", C.c_int32), ("sched_patience", C.c_int32),
+                ("sched_factor", C.c_double), ("min_lr", C.c_double), ("stop_patience", C.c_int32), ("target_ddof", C.c_int32),
+                ("min_delta", C.c_double), ("dropout", C.c_double), ("inference_dropout", C.c_int32), ("reserved", C.c_int32),
+                ("seed", C.c_uint64)]
+
+
+class GnetResult(C.Structure):  # optmc_gnet_result
+    _fields_ = [("price", C.c_double), ("stderr_", C.c_double), ("n_paths", C.c_int64), ("n_rows", C.c_int64),
+                ("epochs_run", C.c_int32), ("n_launches", C.c_int32), ("best_loss", C.c_double), ("final_lr", C.c_double),
+                ("boundary", C.POINTER(C.c_double)), ("ex_count", C.POINTER(C.c_int64))]
+
+
 class GlobalResult(C.Structure):
     _fields_ = [("price", C.c_double), ("stderr_", C.c_double), ("n_paths", C.c_int64), ("n_rows", C.c_int64),
                 ("n_launches", C.c_int32), ("rank", C.c_int32), ("beta", C.c_double * 7),
@@ -105,6 +119,10 @@ PROTOTYPES = {
     "optmc_mlp_init_params": (C.c_int, [C.c_int32, C.c_uint64, C.c_int32, _P(C.c_float)]),
     "optmc_mlp_grad_debug": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, _P(C.c_float), _P(C.c_float), _P(C.c_float),
                                        _P(C.c_float), _P(C.c_float)]),
+    "optmc_lsm_gnet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
+                                 _P(GnetParams), _P(GnetResult)]),
+    "optmc_gnet_grad_debug": (C.c_int, [C.c_void_p, C.c_int64, _P(C.c_float), _P(C.c_float), _P(C.c_float), _P(C.c_float),
+                                        _P(C.c_float)]),
     "optmc_lsm_gram_len": (C.c_int, [C.c_int32]),
     "optmc_lsm_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams)]),
     "optmc_lsm_gram_date": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

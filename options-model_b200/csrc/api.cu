@@ -238,7 +238,7 @@ int optmc_ctx_destroy(optmc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->slab); cudaFree(ctx->cf); cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->gram);
   cudaFree(ctx->d_betas); cudaFree(ctx->d_bnd); cudaFree(ctx->d_exc); cudaFree(ctx->d_nitm); cudaFree(ctx->d_valid);
-  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
+  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->gnet_rows); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
   for (int r = 0; r < 8; ++r) if (ctx->comm.opened[r]) cudaIpcCloseMemHandle(ctx->comm.peers[r]);
   cudaFree(ctx->comm.local);
   for (int i = 0; i < 3; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -290,7 +290,7 @@ int optmc_workspace_bytes(int64_t M, int32_t N, int32_t dtype, int32_t n_options
 
 int optmc_ctx_workspace_bytes(optmc_ctx* ctx, int64_t* bytes) {
   if (!ctx || !bytes) { set_error("null argument"); return OPTMC_EINVAL; }
-  *bytes = (int64_t)(ctx->slab_bytes + ctx->cf_bytes + ctx->partials_bytes + ctx->batch_dev_cap + ctx->eu_out_cap +
+  *bytes = (int64_t)(ctx->slab_bytes + ctx->cf_bytes + ctx->partials_bytes + ctx->batch_dev_cap + ctx->gnet_rows_cap + ctx->eu_out_cap +
                      ctx->eu_par_cap + ctx->eu_tickets_cap +
                      ctx->per_date_cap * (kMaxBeta * sizeof(double) + 2 * sizeof(unsigned long long) + sizeof(long long) + sizeof(int)) +
                      xchg_bytes() + 1024 * sizeof(unsigned int) + 20 * sizeof(double) + 4 * sizeof(int));
@@ -447,6 +447,22 @@ int optmc_lsm_global(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, i
   OPTMC_TRY_BEGIN
   OPTMC_ENTER(ctx);
   return lsm_global(ctx, S_dev, ld, M, N, dtype, lp, out);
+  OPTMC_TRY_END
+}
+
+int optmc_lsm_gnet(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                   const optmc_lsm_params* lp, const optmc_gnet_params* gp, optmc_gnet_result* out) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return lsm_gnet(ctx, S_dev, ld, M, N, dtype, lp, gp, out);
+  OPTMC_TRY_END
+}
+
+int optmc_gnet_grad_debug(optmc_ctx* ctx, int64_t n, const float* feat, const float* ys, const float* params, float* grads,
+                          float* loss) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return gnet_grad_debug(ctx, n, feat, ys, params, grads, loss);
   OPTMC_TRY_END
 }
 

@@ -76,6 +76,7 @@ struct optmc_ctx {
   void* xchg = nullptr;                 // exchange accumulators of the persistent sweep, xchg_bytes()
   int* d_flags = nullptr;               // [4]: [0] = fixed-point exchange overflow
   void* batch_dev = nullptr; size_t batch_dev_cap = 0;  // per-wave descriptors / accumulators / results
+  void* gnet_rows = nullptr; size_t gnet_rows_cap = 0;  // global network LSM: regression rows of all dates (x, t, y)
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};      // kernel timing of the fused calls (optmc_ctx_kernel_times)
   double last_paths_ms = 0.0, last_sweep_ms = 0.0;
   double* eu_out = nullptr; size_t eu_out_cap = 0;  // [n_options][3]
@@ -133,6 +134,10 @@ int lsm_global(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, 
 
 // lsm_mlp.cu
 int lsm_mlp(optmc_ctx* ctx, const optmc_mlp_params* np, optmc_lsm_result* out);
+// lsm_gnet.cu
+int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
+             const optmc_gnet_params* gp, optmc_gnet_result* out);
+int gnet_grad_debug(optmc_ctx* ctx, long long n, const float* feat, const float* ys, const float* params, float* grads, float* loss);
 int mlp_init_params_host(int H, unsigned long long seed, int date, float* out);
 int mlp_grad_debug(optmc_ctx* ctx, int H, long long n, const float* xs, const float* ys, const float* params, float* grads,
                    float* cont);

@@ -332,6 +332,53 @@ class Engine:
                                               params.ctypes.data_as(fp), grads.ctypes.data_as(fp), cont.ctypes.data_as(fp)))
         return grads, cont
 
+    GNET_PARAMS = 7 * 128 + 128 + 2 * (128 * 128 + 128) + 128 + 1  # SingleLSMNet(7, 128, 3): 34177
+
+    def lsm_gnet(self, S, K, r, T, option_type="put", semantics="reference", variant="cpu", epochs=25, batch=None, lr=1e-3,
+                 weight_decay=None, dropout=0.1, seed=42, inference_dropout=-1, arrays=True, M: Optional[int] = None, **over):
+        """The reference's v3 algorithm with its own regressor (om3:482-651): one SingleLSMNet(7,128,3) trained on the
+        rows of all dates (tcgen05), then the decision pass.  ``variant`` picks the defaults of the CPU file
+        (om3:565-613: batch 256, Adam + L2 1e-5, ReduceLROnPlateau, patience 8, population std) or of the torch-GPU
+        file (om3gpu:740-798: batch 8192, AdamW 1e-4, no scheduler, patience 3, sample std).  Returns a dict."""
+        assert S.is_cuda and S.dim() == 2 and S.stride(1) == 1
+        N = S.shape[0] - 1
+        M = int(M if M is not None else S.shape[1])
+        lp = self._lsm_params(K, r, T, option_type, L.BASIS_REF7, semantics, "auto")
+        cpu = variant == "cpu"
+        gp = L.GnetParams(128, 3, int(epochs), int(batch if batch is not None else (256 if cpu else 8192)), float(lr),
+                          float(weight_decay if weight_decay is not None else (1e-5 if cpu else 1e-4)), 0 if cpu else 1,
+                          5 if cpu else 0, 0.5, 1e-6, 8 if cpu else 3, 0 if cpu else 1, 1e-6, float(dropout),
+                          int(inference_dropout), 0, int(seed) & 0xFFFFFFFFFFFFFFFF)
+        for k, v in over.items():
+            setattr(gp, k, v)
+        code = L.F64 if S.dtype == self.torch.float64 else L.F32
+        res = L.GnetResult()
+        bnd = exc = None
+        if arrays:
+            bnd = np.full(N + 1, np.nan)
+            exc = np.zeros(N + 1, dtype=np.int64)
+            res.boundary = bnd.ctypes.data_as(C.POINTER(C.c_double))
+            res.ex_count = exc.ctypes.data_as(C.POINTER(C.c_int64))
+        self._sync_stream()
+        L.check(self.lib.optmc_lsm_gnet(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), C.byref(gp), C.byref(res)))
+        return dict(price=res.price, stderr=res.stderr_, n_paths=int(res.n_paths), n_rows=int(res.n_rows),
+                    epochs_run=int(res.epochs_run), n_launches=int(res.n_launches), best_loss=res.best_loss,
+                    final_lr=res.final_lr, boundary=bnd, ex_count=exc)
+
+    def gnet_grad_debug(self, feat: np.ndarray, ys: np.ndarray, params: np.ndarray):
+        """MSE loss and gradient of SingleLSMNet(7,128,3) on host rows (normalised features [n,7]) -- test aid."""
+        feat = np.ascontiguousarray(feat, dtype=np.float32)
+        ys = np.ascontiguousarray(ys, dtype=np.float32)
+        params = np.ascontiguousarray(params, dtype=np.float32)
+        assert feat.ndim == 2 and feat.shape[1] == 7 and ys.size == feat.shape[0] and params.size == self.GNET_PARAMS
+        grads = np.zeros(self.GNET_PARAMS, dtype=np.float32)
+        loss = C.c_float()
+        fp = C.POINTER(C.c_float)
+        self._sync_stream()
+        L.check(self.lib.optmc_gnet_grad_debug(self._h, feat.shape[0], feat.ctypes.data_as(fp), ys.ctypes.data_as(fp),
+                                               params.ctypes.data_as(fp), grads.ctypes.data_as(fp), C.byref(loss)))
+        return grads, float(loss.value)
+
     def mlp_init_params(self, seed: int, date: int, hidden: int = 32) -> np.ndarray:
         n = 3 * hidden + hidden * hidden + hidden + 1
         out = np.zeros(n, dtype=np.float32)

@@ -616,6 +616,72 @@ def lsm_global(S, K, r, T, option_type, fit: Callable, target_ddof=0):
     return float(cf.mean()), stats
 
 
+def single_lsm_net_fit(variant="cpu", hidden=128, epochs=25, lr=1e-3, batch=None, dropout=0.1, seed=0,
+                       inference_dropout=True, log=None):
+    """``fit`` for :func:`lsm_global` restating the reference's global network regression in torch (CPU, fp32).
+
+    variant "cpu" = om3:565-613: SingleLSMNet(7, hidden, 3) (om3:85-103), DataLoader(batch 256, shuffle), Adam(lr,
+    weight_decay 1e-5), ReduceLROnPlateau(patience 5, factor 0.5, min_lr 1e-6) on the mean batch loss, best-weights
+    snapshot on an improvement > 1e-6, early stop after 8 epochs without one, best weights restored.
+    variant "gpu" = om3gpu:740-798: batch min(8192, n), AdamW(weight_decay 1e-4), no scheduler, patience 3.
+    The returned predictor keeps dropout ACTIVE when ``inference_dropout`` (the reference never calls net.eval(),
+    SURVEY App. A).  Streams come from torch's RNG seeded with ``seed``: comparable with the engine statistically.
+    """
+    import copy
+
+    import torch
+    from torch import nn, optim
+
+    def fit(Xn, Ys):
+        torch.manual_seed(seed)
+        layers = [nn.Linear(Xn.shape[1], hidden), nn.ReLU(), nn.Dropout(dropout)]
+        for _ in range(2):
+            layers += [nn.Linear(hidden, hidden), nn.ReLU(), nn.Dropout(dropout)]
+        layers += [nn.Linear(hidden, 1)]
+        net = nn.Sequential(*layers)
+        X = torch.from_numpy(np.asarray(Xn)).float()
+        Y = torch.from_numpy(np.asarray(Ys)).float().reshape(-1, 1)
+        n = X.shape[0]
+        cpu = variant == "cpu"
+        B = int(batch if batch is not None else (min(256, n) if cpu else min(8192, n)))
+        opt = optim.Adam(net.parameters(), lr=lr, weight_decay=1e-5) if cpu else optim.AdamW(net.parameters(), lr=lr, weight_decay=1e-4)
+        sched = optim.lr_scheduler.ReduceLROnPlateau(opt, patience=5, factor=0.5, min_lr=1e-6) if cpu else None
+        best, best_sd, bad = float("inf"), None, 0
+        for ep in range(epochs):
+            perm = torch.randperm(n)
+            tot, nb = 0.0, 0
+            for b0 in range(0, n, B):
+                idx = perm[b0:b0 + B]
+                loss = nn.functional.mse_loss(net(X[idx]), Y[idx])
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+                tot += float(loss.detach())
+                nb += 1
+            avg = tot / nb
+            if sched is not None:
+                sched.step(avg)
+            if log is not None:
+                log.append(avg)
+            if avg < best - 1e-6:
+                best, best_sd, bad = avg, copy.deepcopy(net.state_dict()), 0
+            else:
+                bad += 1
+                if bad >= (8 if cpu else 3):
+                    break
+        if best_sd is not None:
+            net.load_state_dict(best_sd)
+        net.train(bool(inference_dropout))
+
+        def predict(fn):
+            with torch.no_grad():
+                return net(torch.from_numpy(np.asarray(fn)).float()).numpy().reshape(-1).astype(np.float64)
+
+        return predict
+
+    return fit
+
+
 def linear_fit(Xn, Ys):
     """Least squares with intercept on the (z-scored) reference features: the regressor optmc_lsm_global
     implements.  Minimum-norm solution, so all-zero / duplicated columns are harmless."""
