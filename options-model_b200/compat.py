@@ -5,8 +5,11 @@ om3 = options_model_3/options_model_3.py, om3gpu = options_model_3/option_model_
 om2 = options_model_2.py, om1 = Options_model.py, hc = options_model_3/heston_calibration.py.
 
 What differs from the reference, by design:
-  * The continuation regressor is the polynomial least-squares fit of SURVEY.md 8(c) (``lsm_regressor``
-    keyword, default "poly2") instead of a torch network; ``nn_*`` arguments are accepted and ignored.
+  * The continuation regressor defaults to the polynomial least-squares fit of SURVEY.md 8(c) (``lsm_regressor``
+    keyword: "poly2" | "poly3"): deterministic and one persistent launch.  ``lsm_regressor="nn"`` runs the
+    reference's own algorithm -- one SingleLSMNet(7, 128, 3) trained on the rows of all dates with the
+    reference's optimiser settings, on the tensor cores (optmc_lsm_gnet); ``nn_epochs``, ``nn_lr``,
+    ``nn_dropout`` then mean what they mean in the reference.
   * Random numbers: functions that receive an explicit numpy ``Generator`` / rely on torch's global
     generator (simulate_heston_paths_antithetic, simulate_*_torch, HestonPricer.simulate_paths) draw
     from it exactly as the reference does and feed the draws to the kernels, so results match the
@@ -226,6 +229,7 @@ class AdvancedOptionPricer:
         self.gpu_reference_quirks = gpu_reference_quirks
         self.batched = batched
         self.last_result: Optional[E.SweepResult] = None
+        self._nn_variant = "cpu"  # training defaults of om3:565-613; the *_gpu entry point switches to om3gpu:740-798
 
     # om3:461-472 model routing
     def _model(self, S0: float, T: float) -> E.ModelSpec:
@@ -248,11 +252,21 @@ class AdvancedOptionPricer:
         if num_simulations <= 0 or num_time_steps <= 0:
             raise ValueError("num_simulations and num_time_steps must be positive integers.")
         seed = int(self.rng_manager.master_rng.integers(0, 2**31 - 1))  # om3:454: the child generator's seed
-        self.rng_manager.get_child_seed()                               # om3:455: torch.manual_seed draw
+        torch_seed = self.rng_manager.get_child_seed()                  # om3:455: torch.manual_seed draw
         M = num_simulations // 2 * 2
         if M == 0:
             return float("nan")  # the reference averages an empty cash-flow vector
         model = self._model(S0, T)
+        if self.lsm_regressor == "nn":  # the reference's own regressor: one SingleLSMNet for all dates (om3:482-651)
+            if self.nn_hidden != 128 or self.nn_layers != 3:
+                raise ValueError("lsm_regressor='nn' is built for SingleLSMNet(7, 128, 3) (nn_hidden=128, nn_layers=3)")
+            eng = _engine(self.device)
+            S = eng.paths(model, M, int(num_time_steps), self.dtype, E.RngSpec(seed=seed))
+            out = eng.lsm_gnet(S, self.K, self.r, T, self.option_type, self.semantics, variant=self._nn_variant,
+                               epochs=self.nn_epochs, lr=self.nn_lr, dropout=self.nn_dropout, seed=int(torch_seed or 0),
+                               arrays=self.verbose)
+            self.last_result = out
+            return float(out["price"])
         res = _engine(self.device).price_american(model, M, int(num_time_steps), self.K, self.option_type, self.dtype,
                                                   E.RngSpec(seed=seed), basis=self.lsm_regressor,
                                                   semantics=self.semantics, arrays=self.verbose)
@@ -269,7 +283,11 @@ class AdvancedOptionPricer:
             if T < 10 / 365.0:
                 num_time_steps = max(10, min(25, int(T * 365 * 2)))
             num_simulations = min(num_simulations, 50000)
-        return self.price_american_enhanced_lsm(S0, T, num_simulations, num_time_steps)
+        prev, self._nn_variant = self._nn_variant, "gpu"
+        try:
+            return self.price_american_enhanced_lsm(S0, T, num_simulations, num_time_steps)
+        finally:
+            self._nn_variant = prev
 
     def price_european_streaming(self, S0: float, T: float, num_simulations: int = 10000,
                                  num_time_steps: int = 50) -> float:

@@ -752,3 +752,88 @@ def test_qe_american_batch_runs_through_the_sweep(eng, mods):
     assert eu - 3 * res.stderr < res.price < eu + 1.0  # early-exercise premium of an ATM 1y put: a few tenths
     pb, _ = eng.price_american_batch(model, 200_000, 100.0, [100.0], [1.0], [50], 1, "f32", E.RngSpec(seed=9), semantics="textbook")
     assert pb[0] == pytest.approx(res.price, rel=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Global network LSM: SingleLSMNet(7,128,3) on the tensor cores
+# ------------------------------------------------------------------------------------------------------
+def _single_lsm_net():
+    layers = [torch.nn.Linear(7, 128), torch.nn.ReLU()]
+    for _ in range(2):
+        layers += [torch.nn.Linear(128, 128), torch.nn.ReLU()]
+    return torch.nn.Sequential(*layers, torch.nn.Linear(128, 1))
+
+
+@pytest.mark.parametrize("n", [100, 128, 1000, 5000])
+def test_gnet_gradients_vs_torch(eng, n):
+    """Loss and gradient of one batch against torch autograd (fp32) -- the 128x128 contractions run in bf16 with fp32
+    accumulation, so the tolerance is bf16's (relative L2 per parameter block); targets are shifted so that the
+    gradient is a coherent sum (with zero-mean errors it is cancellation noise that amplifies ReLU sign flips)."""
+    torch.manual_seed(n)
+    net = _single_lsm_net()
+    X, y = torch.randn(n, 7), torch.randn(n) - 5.0
+    loss = torch.nn.functional.mse_loss(net(X).squeeze(1), y)
+    loss.backward()
+    flat = lambda g: np.concatenate([(p.grad if g else p.data).detach().reshape(-1).numpy() for p in net.parameters()])  # noqa: E731
+    g, l = eng.gnet_grad_debug(X.numpy(), y.numpy(), flat(False))
+    g_ref = flat(True)
+    assert l == pytest.approx(float(loss.detach()), rel=2e-4)
+    seg = {"W1": (0, 896), "b1": (896, 1024), "W2": (1024, 17408), "b2": (17408, 17536), "W3": (17536, 33920),
+           "b3": (33920, 34048), "w4": (34048, 34176), "b4": (34176, 34177)}
+    for k, (a, b) in seg.items():
+        err = np.linalg.norm(g[a:b] - g_ref[a:b]) / np.linalg.norm(g_ref[a:b])
+        assert err < 4e-2, (k, err)
+
+
+def test_gnet_training_and_prices_vs_torch_restatement(eng, mods):
+    """The whole v3 algorithm against its torch restatement (oracle.single_lsm_net_fit) on the same paths.  The
+    reference's initialisation / shuffle / dropout streams are torch's global RNG, so agreement is statistical: the
+    training loss (a smooth functional of the fit) within 1 %, the price within the seed-to-seed spread of the
+    estimator itself."""
+    L, E, orc = mods
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    S = eng.paths(model, 40_000, 25, "f64", E.RngSpec(seed=8))
+    Sn = S.cpu().numpy()
+    got = [eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "reference", variant="gpu", epochs=12, seed=sd, stop_patience=0) for sd in (1, 2, 3, 4)]
+    ref, ref_loss, ref_rows = [], [], 0
+    for sd in (1, 2):
+        log = []
+        p, st = orc.lsm_global(Sn, 100.0, 0.05, 1.0, "put", orc.single_lsm_net_fit("gpu", epochs=12, seed=sd, log=log), target_ddof=1)
+        ref.append(p); ref_loss.append(min(log)); ref_rows = st["n_rows"]
+    assert got[0]["n_rows"] == ref_rows
+    assert np.mean([r["best_loss"] for r in got]) == pytest.approx(np.mean(ref_loss), rel=1e-2)
+    assert abs(np.mean([r["price"] for r in got]) - np.mean(ref)) < 0.35
+    # reproducible: same seed, same price, bit for bit
+    again = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "reference", variant="gpu", epochs=12, seed=1, stop_patience=0)
+    assert again["price"] == got[0]["price"] and again["best_loss"] == got[0]["best_loss"]
+    # exercise statistics are consistent with the price pass
+    assert got[0]["ex_count"][1:25].sum() > 0 and np.isnan(got[0]["boundary"][0])
+
+
+def test_gnet_textbook_policy_is_sane_and_edge_cases(eng, mods):
+    L, E, orc = mods
+    gbm = E.gbm(100.0, 0.05, 1.0, 0.2)
+    S = eng.paths(gbm, 100_000, 50, "f32", E.RngSpec(seed=4))
+    r = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "textbook", variant="gpu", epochs=15, seed=3)
+    # American put, GBM: binomial value 6.09; an in-sample network policy lands near it
+    assert 5.85 < r["price"] < 6.35
+    assert r["epochs_run"] >= 3 and r["n_rows"] > 1_000_000
+    # no in-the-money row at all (deep OTM call): the price is the discounted terminal payoff mean, no training
+    r0 = eng.lsm_gnet(S, 1e6, 0.05, 1.0, "call", "reference", variant="gpu", epochs=3)
+    assert r0["n_rows"] == 0 and r0["epochs_run"] == 0 and r0["price"] == 0.0
+    # N = 1: no exercise date before maturity
+    S1 = eng.paths(gbm, 4096, 1, "f64", E.RngSpec(seed=4))
+    r1 = eng.lsm_gnet(S1, 100.0, 0.05, 1.0, "put", "reference", variant="cpu", epochs=2)
+    pay = np.maximum(100.0 - S1[1].cpu().numpy(), 0.0)
+    assert r1["n_rows"] == 0 and r1["price"] == pytest.approx(pay.mean(), rel=1e-12)
+
+
+def test_compat_pricer_nn_regressor(mods):
+    from options_model_b200 import compat
+
+    p = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, option_type="put", rng_manager=compat.RNGManager(42),
+                                    lsm_regressor="nn", nn_epochs=3)
+    v = p.price_american_enhanced_lsm_gpu(100.0, 1.0, num_simulations=50_000, num_time_steps=30)
+    assert 5.5 < v < 8.5 and p.last_result["epochs_run"] >= 1
+    with pytest.raises(ValueError):
+        compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, lsm_regressor="nn", nn_hidden=64).price_american_enhanced_lsm(100.0, 1.0, 1000, 10)
