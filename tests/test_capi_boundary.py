@@ -81,3 +81,34 @@ def test_workspace_estimate_needs_no_gpu(lib):
     assert E.workspace_estimate(10_000, 50, "f32", 5000) == E.workspace_estimate(10_000, 50, "f32", 160)  # waves
     out = C.c_int64()
     assert lib.load_library().optmc_workspace_bytes(0, 10, 0, 1, C.byref(out)) == -1
+
+
+def test_ctypes_mirrors_match_the_compiled_header(lib, tmp_path):
+    """Compile include/optmc.h with gcc and compare sizeof / offsetof of every public struct with the ctypes mirror."""
+    import subprocess
+
+    pairs = {"optmc_model_params": lib.ModelParams, "optmc_rng_params": lib.RngParams, "optmc_lsm_params": lib.LsmParams,
+             "optmc_lsm_result": lib.LsmResult, "optmc_european_result": lib.EuropeanResult,
+             "optmc_global_result": lib.GlobalResult, "optmc_mlp_params": lib.MlpParams, "optmc_gnet_params": lib.GnetParams,
+             "optmc_gnet_result": lib.GnetResult, "optmc_american_option": lib.AmericanOption,
+             "optmc_price_result": lib.PriceResult}
+    src = open(os.path.join(ROOT, "include", "optmc.h")).read()
+    declared = set(re.findall(r"typedef struct (optmc_[a-z_]+) \{", src))
+    assert declared == set(pairs), declared ^ set(pairs)
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "optmc.h"', "int main(void) {"]
+    for cname, ct in pairs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    c = tmp_path / "probe.c"
+    c.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    for line in out:
+        name, size, *offs = line.split()
+        ct = pairs[name]
+        assert ctypes.sizeof(ct) == int(size), name
+        assert [getattr(ct, f).offset for f, _ in ct._fields_] == [int(o) for o in offs], name

@@ -202,3 +202,19 @@ def test_textbook_vs_reference_semantics_differ():
     tb = orc.lsm_sweep(S, 100.0, 0.05, 1.0, "put", semantics="textbook")
     assert res.price > tb.price + 0.2  # look-ahead bias of the sticky mask (App. A, Q1)
     assert 5.9 < tb.price < 6.25       # binomial value ~6.09
+
+
+def test_single_lsm_net_fit_runs_the_reference_training_loop():
+    """The torch restatement of om3:565-613 / om3gpu:740-798 used as the checker of optmc_lsm_gnet: tiny problem,
+    both variants; the fit must reduce the loss and produce a price between the European value and the strike."""
+    torch = pytest.importorskip("torch")  # noqa: F841
+    rng = np.random.default_rng(3)
+    M, N = 2000, 8
+    Z = orc.draw_gbm_normals(rng, N, M)
+    S = orc.gbm_paths_antithetic(100.0, 0.05, 0.2, 1.0, M, N, Z)
+    for variant in ("cpu", "gpu"):
+        log = []
+        price, st = orc.lsm_global(S, 100.0, 0.05, 1.0, "put", orc.single_lsm_net_fit(variant, epochs=4, seed=1, log=log),
+                                   target_ddof=0 if variant == "cpu" else 1)
+        assert st["n_rows"] > 0 and len(log) >= 1 and log[-1] <= log[0] + 1e-9
+        assert 4.0 < price < 12.0
