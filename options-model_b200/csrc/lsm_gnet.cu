@@ -217,7 +217,8 @@ struct GnetSmem {
   float b1[kGH], b2[kGH], b3[kGH], w4[kGH];
   float b4;
   float red[8];
-  unsigned long long bar;
+  unsigned int mask[3][4][kGThreads];  // per layer: 128 "unit is active" bits of each row (word-major: conflict-free)
+  unsigned long long bar, wbar;
   unsigned int tmem;
   int any;
 };
@@ -238,15 +239,30 @@ __device__ __forceinline__ unsigned int drop_keep8(const Drop& d, unsigned int r
          (((k1 & 1u) | ((k1 >> 7) & 2u) | ((k1 >> 14) & 4u) | ((k1 >> 21) & 8u)) << 4);
 }
 
-__device__ __forceinline__ unsigned int gnet_setup(GnetSmem& sm, const float* __restrict__ params) {
+// bf16 core-layout images of W2 and W3 (2 x 32 KB), kept in step with the fp32 parameters by the optimiser kernel:
+// a CTA stages them with two bulk async copies instead of re-packing 32768 floats.
+__device__ __forceinline__ int gnet_pack_index(int i) {  // parameter index -> bf16 element index in the images, or -1
+  if (i >= gW2 && i < gB2) { const int k = i - gW2; return core_off(k >> 7, k & 127) >> 1; }
+  if (i >= gW3 && i < gB3) { const int k = i - gW3; return (kTcTileBytes >> 1) + (core_off(k >> 7, k & 127) >> 1); }
+  return -1;
+}
+__global__ void gnet_pack_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ wpack) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kGP) return;
+  const int k = gnet_pack_index(i);
+  if (k >= 0) wpack[k] = __float2bfloat16_rn(params[i]);
+}
+
+__device__ __forceinline__ unsigned int gnet_setup(GnetSmem& sm, const float* __restrict__ params,
+                                                   const __nv_bfloat16* __restrict__ wpack) {
   const int tid = threadIdx.x;
-#pragma unroll 2
-  for (int c = 0; c < 16; ++c) {  // thread j stages row j of W2 and W3
-    float v[8], w[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { v[k] = params[gW2 + tid * kGH + c * 8 + k]; w[k] = params[gW3 + tid * kGH + c * 8 + k]; }
-    *reinterpret_cast<uint4*>(sm.W2 + core_off(tid, c * 8)) = pack8_bf16(v);
-    *reinterpret_cast<uint4*>(sm.W3 + core_off(tid, c * 8)) = pack8_bf16(w);
+  if (tid == 0) {
+    mbar_init(reinterpret_cast<uint64_t*>(&sm.bar), 1);
+    mbar_init(reinterpret_cast<uint64_t*>(&sm.wbar), 1);
+    mbar_fence_init();
+    mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.wbar), 2 * kTcTileBytes);
+    bulk_load_1d(sm.W2, wpack, kTcTileBytes, reinterpret_cast<uint64_t*>(&sm.wbar));
+    bulk_load_1d(sm.W3, wpack + (kTcTileBytes >> 1), kTcTileBytes, reinterpret_cast<uint64_t*>(&sm.wbar));
   }
 #pragma unroll
   for (int k = 0; k < kGIn; ++k) sm.W1[k][tid] = params[gW1 + tid * kGIn + k];
@@ -258,14 +274,12 @@ __device__ __forceinline__ unsigned int gnet_setup(GnetSmem& sm, const float* __
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (tid == 0) {
-    mbar_init(reinterpret_cast<uint64_t*>(&sm.bar), 1);
-    mbar_fence_init();
-  }
   tc_publish();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   return sm.tmem;
 }
+// the MMA-issuing thread calls this once before its first MMA: the weight images have landed
+__device__ __forceinline__ void gnet_weights_ready(GnetSmem& sm) { mbar_wait(reinterpret_cast<uint64_t*>(&sm.wbar), 0u); }
 
 // normalised features of (x, sqrt(tau)) -- om3:105-121 then om3:559-563
 __device__ __forceinline__ void gnet_features(float x, float stau, const GnetNorm& nm, float (&fn)[kGIn]) {
@@ -275,10 +289,14 @@ __device__ __forceinline__ void gnet_features(float x, float stau, const GnetNor
   for (int k = 0; k < kGIn; ++k) fn[k] = (f[k] - nm.fmean[k]) * nm.finv[k];
 }
 
+// The tile kernels run each stage ONCE per CTA, so straight-line code would be fetched cold from the instruction
+// cache end to end (ncu: "no instruction" was the top stall); the stage loops below are deliberately NOT unrolled
+// and the per-row activity masks live in shared memory (dynamic word index) instead of registers.
+
 // layer 1 on the CUDA cores (fp32): h1 = drop(relu(W1 fn + b1)) -> bf16 tile A1; mask bit = h1 > 0
-__device__ __forceinline__ void gnet_layer1(GnetSmem& sm, const float (&fn)[kGIn], int row, unsigned int r, const Drop& d,
-                                            unsigned int (&mask)[4]) {
-#pragma unroll 4
+__device__ __forceinline__ void gnet_layer1(GnetSmem& sm, const float (&fn)[kGIn], int row, unsigned int r, const Drop& d) {
+  unsigned int word = 0u;
+#pragma unroll 1
   for (int c = 0; c < 16; ++c) {
     float v[8];
 #pragma unroll
@@ -293,22 +311,23 @@ __device__ __forceinline__ void gnet_layer1(GnetSmem& sm, const float (&fn)[kGIn
     for (int k = 0; k < 8; ++k) {
       const bool on = v[k] > 0.f && ((keep >> k) & 1u);
       v[k] = on ? v[k] * d.scale : 0.f;
-      if (on) mask[c >> 2] |= 1u << ((c & 3) * 8 + k);
+      word |= (on ? 1u : 0u) << ((c & 3) * 8 + k);
     }
     *reinterpret_cast<uint4*>(sm.A1 + core_off(row, c * 8)) = pack8_bf16(v);
+    if ((c & 3) == 3) { sm.mask[0][c >> 2][row] = word; word = 0u; }
   }
 }
 
 // hidden epilogue: h = drop(relu(z + b)) from TMEM columns [col0, col0 + 128) -> bf16 tile; optional dot with w4
 template <bool DOT, bool STORE = true>
-__device__ __forceinline__ float gnet_hidden(unsigned int taddr, const float* __restrict__ bias, const float* __restrict__ w4,
-                                             unsigned char* tile, int row, unsigned int r, int layer, const Drop& d,
-                                             unsigned int (&mask)[4]) {
+__device__ __forceinline__ float gnet_hidden(GnetSmem& sm, unsigned int taddr, const float* __restrict__ bias, unsigned char* tile,
+                                             int row, unsigned int r, int layer, const Drop& d) {
   float out = 0.f;
-#pragma unroll
+#pragma unroll 1
   for (int c0 = 0; c0 < 4; ++c0) {
     float z[32];
     tmem_ld32(taddr + c0 * 32, z);
+    unsigned int word = 0u;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const unsigned int keep = drop_keep8(d, r, layer, c0 * 4 + q);
@@ -319,26 +338,28 @@ __device__ __forceinline__ float gnet_hidden(unsigned int taddr, const float* __
         const float h = z[q * 8 + k] + bias[j];
         const bool on = h > 0.f && ((keep >> k) & 1u);
         v[k] = on ? h * d.scale : 0.f;
-        if (on) mask[c0] |= 1u << (q * 8 + k);
-        if (DOT) out = fmaf(w4[j], v[k], out);
+        word |= (on ? 1u : 0u) << (q * 8 + k);
+        if (DOT) out = fmaf(sm.w4[j], v[k], out);
       }
       if (STORE) *reinterpret_cast<uint4*>(tile + core_off(row, c0 * 32 + q * 8)) = pack8_bf16(v);
     }
+    if (STORE) sm.mask[layer][c0][row] = word;
   }
   return out;
 }
 
 // masked copy of a TMEM accumulator: tile = mask ? acc * scale : 0
-__device__ __forceinline__ void gnet_masked(unsigned int taddr, unsigned char* tile, int row, const unsigned int (&mask)[4], float scale) {
-#pragma unroll
+__device__ __forceinline__ void gnet_masked(GnetSmem& sm, unsigned int taddr, unsigned char* tile, int row, int layer, float scale) {
+#pragma unroll 1
   for (int c0 = 0; c0 < 4; ++c0) {
     float z[32];
     tmem_ld32(taddr + c0 * 32, z);
+    const unsigned int word = sm.mask[layer][c0][row];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = ((mask[c0] >> (q * 8 + k)) & 1u) ? z[q * 8 + k] * scale : 0.f;
+      for (int k = 0; k < 8; ++k) v[k] = ((word >> (q * 8 + k)) & 1u) ? z[q * 8 + k] * scale : 0.f;
       *reinterpret_cast<uint4*>(tile + core_off(row, c0 * 32 + q * 8)) = pack8_bf16(v);
     }
   }
@@ -347,25 +368,25 @@ __device__ __forceinline__ void gnet_masked(unsigned int taddr, unsigned char* t
 // D[row][n] = sum_k A[row][k] B[n][k]   (A, B K-major tiles)
 __device__ __forceinline__ void mma_ab_t(unsigned int d, const unsigned char* A, const unsigned char* B) {
   const unsigned int a0 = smem_u32(A), b0 = smem_u32(B), id = umma_idesc(128, 128, 0, 0);
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 8; ++k) umma_f16(d, umma_desc(a0 + k * 256, 128, 2048), umma_desc(b0 + k * 256, 128, 2048), id, k > 0);
 }
 // D[row][n] = sum_k A[row][k] B[k][n]   (A K-major, B stored [k][n] -> MN-major view)
 __device__ __forceinline__ void mma_ab(unsigned int d, const unsigned char* A, const unsigned char* B) {
   const unsigned int a0 = smem_u32(A), b0 = smem_u32(B), id = umma_idesc(128, 128, 0, 1);
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 8; ++k) umma_f16(d, umma_desc(a0 + k * 256, 128, 2048), umma_desc(b0 + k * 4096, 2048, 128), id, k > 0);
 }
 // D[m][n] = sum_row A[row][m] B[row][n]  (both stored [row][.] -> MN-major views)
 __device__ __forceinline__ void mma_at_b(unsigned int d, const unsigned char* A, const unsigned char* B) {
   const unsigned int a0 = smem_u32(A), b0 = smem_u32(B), id = umma_idesc(128, 128, 1, 1);
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 8; ++k) umma_f16(d, umma_desc(a0 + k * 4096, 2048, 128), umma_desc(b0 + k * 4096, 2048, 128), id, k > 0);
 }
 // D[m][c] = sum_row A[row][m] P[row][c]  (panel, 16 columns)
 __device__ __forceinline__ void mma_at_panel(unsigned int d, const unsigned char* A, const unsigned char* P) {
   const unsigned int a0 = smem_u32(A), p0 = smem_u32(P), id = umma_idesc(128, 16, 1, 1);
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 8; ++k) umma_f16(d, umma_desc(a0 + k * 4096, 2048, 128), umma_desc(p0 + k * 512, 256, 128), id, k > 0);
 }
 
@@ -390,6 +411,7 @@ __device__ __forceinline__ unsigned long long perm_apply(const Perm& p, unsigned
 
 struct GradArgs {
   const float* params;
+  const __nv_bfloat16* wpack;
   const float* xs; const int* ts; const float* ys;   // row table
   const float* feat;                                  // debug: normalised features [n][7] (then xs/ts unused, ys = targets)
   const double* sqrt_tau;
@@ -404,7 +426,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
   extern __shared__ __align__(1024) unsigned char smem_g[];
   GnetSmem& sm = *reinterpret_cast<GnetSmem*>(smem_g);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const unsigned int tmem = gnet_setup(sm, a.params);
+  const unsigned int tmem = gnet_setup(sm, a.params, a.wpack);
   const unsigned int lane_base = (unsigned int)(warp * 32) << 16;
   const unsigned int cA = 0, cB = 128, cC = 256, cV1 = 384, cV2 = 400, cV3 = 416, cV4 = 432;
   const long long r = a.start + (long long)blockIdx.x * 128 + tid;
@@ -426,9 +448,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
       y = (a.ys[src] - nm.ymean) * nm.yinv;
     }
   }
-  unsigned int m1[4] = {0u, 0u, 0u, 0u}, m2[4] = {0u, 0u, 0u, 0u}, m3[4] = {0u, 0u, 0u, 0u};
   const unsigned int rr = (unsigned int)r;
-  gnet_layer1(sm, fn, tid, rr, a.drop, m1);
+  gnet_layer1(sm, fn, tid, rr, a.drop);
   {  // panel: fn0..fn6, 1 (inactive rows: all zero, so they add nothing to the gradients)
     float v[8];
 #pragma unroll
@@ -439,11 +460,12 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
   tc_publish();
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    gnet_weights_ready(sm);
     mma_ab_t(tmem + cA, sm.A1, sm.W2);  // Z2 = H1 W2^T
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  gnet_hidden<false>(tmem + lane_base + cA, sm.b2, nullptr, sm.A2, tid, rr, 1, a.drop, m2);
+  gnet_hidden<false>(sm, tmem + lane_base + cA, sm.b2, sm.A2, tid, rr, 1, a.drop);
   tc_publish();
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -451,39 +473,43 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  const float out = gnet_hidden<true>(tmem + lane_base + cB, sm.b3, sm.w4, sm.A3, tid, rr, 2, a.drop, m3) + sm.b4;
+  const float out = gnet_hidden<true>(sm, tmem + lane_base + cB, sm.b3, sm.A3, tid, rr, 2, a.drop) + sm.b4;
   const float err = act ? out - y : 0.f;
   const float dout = err * inv_b2;
   // D3 = dout w4 (h3 > 0) scale -> A4; dout -> panel column 8
+  {
+    const float ds = dout * a.drop.scale;
+#pragma unroll 1
+    for (int c = 0; c < 16; ++c) {
+      const unsigned int word = sm.mask[2][c >> 2][tid] >> ((c & 3) * 8);
+      float v[8];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = ((m3[c >> 2] >> ((c & 3) * 8 + k)) & 1u) ? dout * sm.w4[c * 8 + k] * a.drop.scale : 0.f;
-    *reinterpret_cast<uint4*>(sm.A4 + core_off(tid, c * 8)) = pack8_bf16(v);
+      for (int k = 0; k < 8; ++k) v[k] = ((word >> k) & 1u) ? ds * sm.w4[c * 8 + k] : 0.f;
+      *reinterpret_cast<uint4*>(sm.A4 + core_off(tid, c * 8)) = pack8_bf16(v);
+    }
   }
   *reinterpret_cast<unsigned short*>(sm.panel + aux_off(tid, 8)) = __bfloat16_as_ushort(__float2bfloat16_rn(dout));
   tc_publish();
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     mma_ab(tmem + cA, sm.A4, sm.W3);           // dH2 = D3 W3
-    mma_at_b(tmem + cC, sm.A4, sm.A2);         // dW3 = D3^T H2
+    mma_at_b(tmem + cC, sm.A2, sm.A4);         // dW3^T = H2^T D3 (lane = input unit: coalesced read-out)
     mma_at_panel(tmem + cV3, sm.A4, sm.panel); // column 7: db3
     mma_at_panel(tmem + cV4, sm.A3, sm.panel); // column 8: dw4 = H3^T dout
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  gnet_masked(tmem + lane_base + cA, sm.A3, tid, m2, a.drop.scale);  // D2 -> A3 (H3 is done)
+  gnet_masked(sm, tmem + lane_base + cA, sm.A3, tid, 1, a.drop.scale);  // D2 -> A3 (H3 is done)
   tc_publish();
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     mma_ab(tmem + cA, sm.A3, sm.W2);           // dH1 = D2 W2
-    mma_at_b(tmem + cB, sm.A3, sm.A1);         // dW2 = D2^T H1
+    mma_at_b(tmem + cB, sm.A1, sm.A3);         // dW2^T = H1^T D2
     mma_at_panel(tmem + cV2, sm.A3, sm.panel); // column 7: db2
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  gnet_masked(tmem + lane_base + cA, sm.A4, tid, m1, a.drop.scale);  // D1 -> A4 (D3 is done)
+  gnet_masked(sm, tmem + lane_base + cA, sm.A4, tid, 0, a.drop.scale);  // D1 -> A4 (D3 is done)
   tc_publish();
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -491,17 +517,18 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  // read-out: thread j owns TMEM lane j = unit j
+  // read-out.  dW2 / dW3 sit transposed in TMEM (lane = input unit i, column = output unit j): for a fixed j the 128
+  // threads write consecutive addresses of row j.  The vector gradients have lane = unit.
   float* gp = a.gpart + (size_t)blockIdx.x * (kGP + 1);
-#pragma unroll
+#pragma unroll 1
   for (int c0 = 0; c0 < 4; ++c0) {
     float w[32];
     tmem_ld32(tmem + lane_base + cB + c0 * 32, w);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) gp[gW2 + tid * kGH + c0 * 32 + i] = w[i];
+    for (int i = 0; i < 32; ++i) gp[gW2 + (c0 * 32 + i) * kGH + tid] = w[i];
     tmem_ld32(tmem + lane_base + cC + c0 * 32, w);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) gp[gW3 + tid * kGH + c0 * 32 + i] = w[i];
+    for (int i = 0; i < 32; ++i) gp[gW3 + (c0 * 32 + i) * kGH + tid] = w[i];
   }
   {
     float v1[16], v2[16], v3[16], v4[16];
@@ -528,7 +555,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
 
 // Adam (torch.optim.Adam with L2 weight decay, om3:579) or AdamW (decoupled, om3gpu:753): fixed-order sum of the
 // per-tile partial gradients; block 0 also adds the batch's mean squared error to the epoch accumulator.
-__global__ void __launch_bounds__(256) gnet_adam_kernel(float* params, float* adam_m, float* adam_v, const float* __restrict__ gpart,
+__global__ void __launch_bounds__(256) gnet_adam_kernel(float* params, __nv_bfloat16* wpack, float* adam_m, float* adam_v, const float* __restrict__ gpart,
                                                         int ntiles, float lr, float wd, int decoupled, int step, float inv_batch,
                                                         double* epoch_loss) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
@@ -542,7 +569,10 @@ __global__ void __launch_bounds__(256) gnet_adam_kernel(float* params, float* ad
     const float m = b1 * adam_m[i] + (1.0f - b1) * g;
     const float v = b2 * adam_v[i] + (1.0f - b2) * g * g;
     adam_m[i] = m; adam_v[i] = v;
-    params[i] = p - (lr / bc1) * (m / (sqrtf(v) / sqrtf(bc2) + eps));
+    p -= (lr / bc1) * (m / (sqrtf(v) / sqrtf(bc2) + eps));
+    params[i] = p;
+    const int k = gnet_pack_index(i);
+    if (k >= 0) wpack[k] = __float2bfloat16_rn(p);
   }
   if (i == 0 && epoch_loss) {
     float l = 0.f;
@@ -563,7 +593,7 @@ __global__ void gnet_sum_partials_kernel(const float* __restrict__ gpart, int nt
 struct WalkGArgs {
   const void* S; long long ld, M; int N, is_put, sticky;
   double K, invK;
-  const float* params; const GnetNorm* nm;
+  const float* params; const __nv_bfloat16* wpack; const GnetNorm* nm;
   const double* sqrt_tau; const double* Dm;     // Dm[t] = disc^(t-1): value today of a payoff taken at date t (N-1 convention)
   Drop drop;                                     // inference dropout (reference: the net is never put in eval mode)
   unsigned long long* fin;                       // fixed-point sums: value, value^2 (signed, bias-free)
@@ -576,7 +606,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_walk_kernel(const WalkGArgs
   extern __shared__ __align__(1024) unsigned char smem_g[];
   GnetSmem& sm = *reinterpret_cast<GnetSmem*>(smem_g);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const unsigned int tmem = gnet_setup(sm, a.params);
+  const unsigned int tmem = gnet_setup(sm, a.params, a.wpack);
+  if (tid == 0) gnet_weights_ready(sm);
   const unsigned int lane_base = (unsigned int)(warp * 32) << 16;
   const long long j = (long long)blockIdx.x * 128 + tid;
   const bool act = j < a.M;
@@ -593,9 +624,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_walk_kernel(const WalkGArgs
     if (!__syncthreads_or(live)) continue;  // nothing to decide for these 128 paths at this date
     float fn[kGIn];
     gnet_features((float)(s * a.invK), (float)a.sqrt_tau[t], nm, fn);
-    unsigned int m1[4] = {0u, 0u, 0u, 0u}, m2[4] = {0u, 0u, 0u, 0u}, m3[4] = {0u, 0u, 0u, 0u};
     const unsigned int rr = (unsigned int)j * 0x01000193u + (unsigned int)t;
-    gnet_layer1(sm, fn, tid, rr, a.drop, m1);
+    gnet_layer1(sm, fn, tid, rr, a.drop);
     tc_publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -603,7 +633,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_walk_kernel(const WalkGArgs
       umma_commit(&sm.bar);
     }
     tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-    gnet_hidden<false>(tmem + lane_base, sm.b2, nullptr, sm.A2, tid, rr, 1, a.drop, m2);
+    gnet_hidden<false>(sm, tmem + lane_base, sm.b2, sm.A2, tid, rr, 1, a.drop);
     tc_publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -611,7 +641,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_walk_kernel(const WalkGArgs
       umma_commit(&sm.bar);
     }
     tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-    const float out = gnet_hidden<true, false>(tmem + lane_base + 128, sm.b3, sm.w4, sm.A3, tid, rr, 2, a.drop, m3) + sm.b4;
+    const float out = gnet_hidden<true, false>(sm, tmem + lane_base + 128, sm.b3, sm.A3, tid, rr, 2, a.drop) + sm.b4;
     const double cont = (double)(out * nm.ystd + nm.ymean);  // om3:640
     const bool ex = live && pay > cont;                       // strict, om3:644
     if (ex) { value = pay * a.Dm[t]; exercised = true; }
@@ -711,7 +741,7 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   const size_t o_tab = take(tab.size() * 8), o_counts = take((size_t)(ncounts > 0 ? ncounts : 1) * 8), o_sums = take(2 * kGQ * 8 + 4 * 8),
                o_nrows = take(8), o_norm = take(sizeof(GnetNorm)), o_params = take((size_t)kGP * 4), o_best = take((size_t)kGP * 4),
                o_m = take((size_t)kGP * 4), o_v = take((size_t)kGP * 4), o_gpart = take((size_t)max_tiles * (kGP + 1) * 4),
-               o_loss = take(8);
+               o_loss = take(8), o_pack = take(2 * kTcTileBytes);
   rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
   if (rc) return rc;
   char* dev = static_cast<char*>(ctx->batch_dev);
@@ -727,6 +757,7 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   float* d_v = reinterpret_cast<float*>(dev + o_v);
   float* d_gpart = reinterpret_cast<float*>(dev + o_gpart);
   double* d_loss = reinterpret_cast<double*>(dev + o_loss);
+  __nv_bfloat16* d_pack = reinterpret_cast<__nv_bfloat16*>(dev + o_pack);
   OPTMC_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   OPTMC_CUDA(cudaMemsetAsync(d_sums, 0, 2 * kGQ * 8 + 4 * 8, ctx->stream));
   OPTMC_CUDA(cudaMemsetAsync(d_nrows, 0, 8, ctx->stream));
@@ -768,7 +799,8 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
     OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   gnet_init_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(d_params, d_m, d_v, gp->seed);
-  ++n_launches; ctx->launches++;
+  gnet_pack_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(d_params, d_pack);
+  n_launches += 2; ctx->launches += 2;
   OPTMC_CUDA(cudaFuncSetAttribute(gnet_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gnet_smem_bytes()));
   OPTMC_CUDA(cudaFuncSetAttribute(gnet_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gnet_smem_bytes()));
 
@@ -782,7 +814,7 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
     for (int ep = 0; ep < gp->epochs; ++ep) {
       OPTMC_CUDA(cudaMemsetAsync(d_loss, 0, 8, ctx->stream));
       GradArgs ga{};
-      ga.params = d_params; ga.xs = d_xs; ga.ts = d_ts; ga.ys = d_ys; ga.feat = nullptr; ga.sqrt_tau = d_tab + (N + 1); ga.nm = d_norm;
+      ga.params = d_params; ga.wpack = d_pack; ga.xs = d_xs; ga.ts = d_ts; ga.ys = d_ys; ga.feat = nullptr; ga.sqrt_tau = d_tab + (N + 1); ga.nm = d_norm;
       ga.perm = make_perm((unsigned long long)n_rows, (unsigned int)(gp->seed * 0x9e3779b97f4a7c15ull >> 32) + 0x632be5abu * (unsigned int)(ep + 1));
       ga.gpart = d_gpart;
       for (long long b = 0; b < nb; ++b) {
@@ -792,7 +824,7 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
         ga.drop = make_drop(gp->dropout, (unsigned int)gp->seed * 0x2545f491u + (unsigned int)step * 0x9e3779b1u);
         const int tiles = (int)((ga.end - ga.start + 127) / 128);
         gnet_grad_kernel<<<tiles, kGThreads, gnet_smem_bytes(), ctx->stream>>>(ga);
-        gnet_adam_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(d_params, d_m, d_v, d_gpart, tiles, (float)lr, (float)gp->weight_decay,
+        gnet_adam_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(d_params, d_pack, d_m, d_v, d_gpart, tiles, (float)lr, (float)gp->weight_decay,
                                                                      gp->decoupled_wd, step, 1.0f / (float)(ga.end - ga.start), d_loss);
         n_launches += 2; ctx->launches += 2;
       }
@@ -818,7 +850,11 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
         break;
       }
     }
-    if (have_best) OPTMC_CUDA(cudaMemcpyAsync(d_params, d_best, (size_t)kGP * 4, cudaMemcpyDeviceToDevice, ctx->stream));  // om3:611-613
+    if (have_best) {  // om3:611-613
+      OPTMC_CUDA(cudaMemcpyAsync(d_params, d_best, (size_t)kGP * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      gnet_pack_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(d_params, d_pack);
+      ++n_launches; ctx->launches++;
+    }
   }
   OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   out->epochs_run = epochs_run; out->best_loss = have_best ? best : nan(""); out->final_lr = lr;
@@ -826,7 +862,7 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   // ---- pass 2 ----
   WalkGArgs wa{};
   wa.S = S; wa.ld = ld; wa.M = M; wa.N = N; wa.is_put = lp->is_put; wa.sticky = sticky ? 1 : 0;
-  wa.K = lp->K; wa.invK = 1.0 / lp->K; wa.params = d_params; wa.nm = d_norm;
+  wa.K = lp->K; wa.invK = 1.0 / lp->K; wa.params = d_params; wa.wpack = d_pack; wa.nm = d_norm;
   wa.sqrt_tau = d_tab + (N + 1); wa.Dm = d_tab + 2 * (N + 1);
   const int inf_drop = gp->inference_dropout < 0 ? (refdisc && sticky ? 1 : 0) : gp->inference_dropout;
   wa.drop = make_drop(inf_drop ? gp->dropout : 0.0, (unsigned int)gp->seed * 0x2545f491u + 0x51ed270bu);
@@ -890,7 +926,7 @@ int gnet_grad_debug(optmc_ctx* ctx, long long n, const float* feat, const float*
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   const size_t o_feat = take((size_t)n * kGIn * 4), o_ys = take((size_t)n * 4), o_par = take((size_t)kGP * 4),
-               o_gpart = take((size_t)tiles * (kGP + 1) * 4), o_out = take((size_t)(kGP + 1) * 4);
+               o_gpart = take((size_t)tiles * (kGP + 1) * 4), o_out = take((size_t)(kGP + 1) * 4), o_pack = take(2 * kTcTileBytes);
   int rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
   if (rc) return rc;
   char* dev = static_cast<char*>(ctx->batch_dev);
@@ -900,6 +936,8 @@ int gnet_grad_debug(optmc_ctx* ctx, long long n, const float* feat, const float*
   OPTMC_CUDA(cudaFuncSetAttribute(gnet_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gnet_smem_bytes()));
   GradArgs ga{};
   ga.params = reinterpret_cast<float*>(dev + o_par); ga.feat = reinterpret_cast<float*>(dev + o_feat);
+  ga.wpack = reinterpret_cast<__nv_bfloat16*>(dev + o_pack);
+  gnet_pack_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(ga.params, reinterpret_cast<__nv_bfloat16*>(dev + o_pack));
   ga.ys = reinterpret_cast<float*>(dev + o_ys); ga.start = 0; ga.end = n; ga.perm = make_perm(1, 0); ga.drop = make_drop(0.0, 0);
   ga.gpart = reinterpret_cast<float*>(dev + o_gpart);
   gnet_grad_kernel<<<tiles, kGThreads, gnet_smem_bytes(), ctx->stream>>>(ga);
