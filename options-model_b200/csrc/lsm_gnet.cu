@@ -46,7 +46,7 @@ constexpr int gB3 = gW3 + kGH * kGH;
 constexpr int gW4 = gB3 + kGH;              // [128]
 constexpr int gB4 = gW4 + kGH;
 constexpr int kGP = gB4 + 1;                // 34177 parameters
-constexpr int kGThreads = 128;
+constexpr int kGThreads = 256;              // tile kernels: thread = (row = tid & 127, column half = tid >> 7)
 constexpr int kGChunk = 1024;               // paths per compaction block (256 threads x 4)
 constexpr int kGQ = 16;                     // moment sums: 7 x (sum f, sum f^2), sum y, sum y^2
 
@@ -217,7 +217,8 @@ struct GnetSmem {
   float b1[kGH], b2[kGH], b3[kGH], w4[kGH];
   float b4;
   float red[8];
-  unsigned int mask[3][4][kGThreads];  // per layer: 128 "unit is active" bits of each row (word-major: conflict-free)
+  float dot[2][128];                   // partial output-layer dot products of the two column halves
+  unsigned int mask[3][4][128];  // per layer: 128 "unit is active" bits of each row (word-major: conflict-free)
   unsigned long long bar, wbar;
   unsigned int tmem;
   int any;
@@ -264,12 +265,17 @@ __device__ __forceinline__ unsigned int gnet_setup(GnetSmem& sm, const float* __
     bulk_load_1d(sm.W2, wpack, kTcTileBytes, reinterpret_cast<uint64_t*>(&sm.wbar));
     bulk_load_1d(sm.W3, wpack + (kTcTileBytes >> 1), kTcTileBytes, reinterpret_cast<uint64_t*>(&sm.wbar));
   }
+  if (tid < 128) {
 #pragma unroll
-  for (int k = 0; k < kGIn; ++k) sm.W1[k][tid] = params[gW1 + tid * kGIn + k];
-  sm.b1[tid] = params[gB1 + tid]; sm.b2[tid] = params[gB2 + tid]; sm.b3[tid] = params[gB3 + tid]; sm.w4[tid] = params[gW4 + tid];
+    for (int k = 0; k < kGIn; ++k) sm.W1[k][tid] = params[gW1 + tid * kGIn + k];
+    sm.b1[tid] = params[gB1 + tid]; sm.b2[tid] = params[gB2 + tid];
+    *reinterpret_cast<uint4*>(sm.panel + aux_off(tid, 0)) = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    const int u = tid - 128;
+    sm.b3[u] = params[gB3 + u]; sm.w4[u] = params[gW4 + u];
+    *reinterpret_cast<uint4*>(sm.panel + aux_off(u, 8)) = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (tid == 0) sm.b4 = params[gB4];
-  *reinterpret_cast<uint4*>(sm.panel + aux_off(tid, 0)) = make_uint4(0u, 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(sm.panel + aux_off(tid, 8)) = make_uint4(0u, 0u, 0u, 0u);
   if ((tid >> 5) == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -294,10 +300,10 @@ __device__ __forceinline__ void gnet_features(float x, float stau, const GnetNor
 // and the per-row activity masks live in shared memory (dynamic word index) instead of registers.
 
 // layer 1 on the CUDA cores (fp32): h1 = drop(relu(W1 fn + b1)) -> bf16 tile A1; mask bit = h1 > 0
-__device__ __forceinline__ void gnet_layer1(GnetSmem& sm, const float (&fn)[kGIn], int row, unsigned int r, const Drop& d) {
+__device__ __forceinline__ void gnet_layer1(GnetSmem& sm, const float (&fn)[kGIn], int row, int half, unsigned int r, const Drop& d) {
   unsigned int word = 0u;
 #pragma unroll 1
-  for (int c = 0; c < 16; ++c) {
+  for (int c = half * 8; c < half * 8 + 8; ++c) {
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) v[k] = sm.b1[c * 8 + k];
@@ -321,10 +327,10 @@ __device__ __forceinline__ void gnet_layer1(GnetSmem& sm, const float (&fn)[kGIn
 // hidden epilogue: h = drop(relu(z + b)) from TMEM columns [col0, col0 + 128) -> bf16 tile; optional dot with w4
 template <bool DOT, bool STORE = true>
 __device__ __forceinline__ float gnet_hidden(GnetSmem& sm, unsigned int taddr, const float* __restrict__ bias, unsigned char* tile,
-                                             int row, unsigned int r, int layer, const Drop& d) {
+                                             int row, int half, unsigned int r, int layer, const Drop& d) {
   float out = 0.f;
 #pragma unroll 1
-  for (int c0 = 0; c0 < 4; ++c0) {
+  for (int c0 = half * 2; c0 < half * 2 + 2; ++c0) {
     float z[32];
     tmem_ld32(taddr + c0 * 32, z);
     unsigned int word = 0u;
@@ -349,9 +355,9 @@ __device__ __forceinline__ float gnet_hidden(GnetSmem& sm, unsigned int taddr, c
 }
 
 // masked copy of a TMEM accumulator: tile = mask ? acc * scale : 0
-__device__ __forceinline__ void gnet_masked(GnetSmem& sm, unsigned int taddr, unsigned char* tile, int row, int layer, float scale) {
+__device__ __forceinline__ void gnet_masked(GnetSmem& sm, unsigned int taddr, unsigned char* tile, int row, int half, int layer, float scale) {
 #pragma unroll 1
-  for (int c0 = 0; c0 < 4; ++c0) {
+  for (int c0 = half * 2; c0 < half * 2 + 2; ++c0) {
     float z[32];
     tmem_ld32(taddr + c0 * 32, z);
     const unsigned int word = sm.mask[layer][c0][row];
@@ -363,6 +369,13 @@ __device__ __forceinline__ void gnet_masked(GnetSmem& sm, unsigned int taddr, un
       *reinterpret_cast<uint4*>(tile + core_off(row, c0 * 32 + q * 8)) = pack8_bf16(v);
     }
   }
+}
+
+// output layer: the two column halves of a row add their partial dot products through shared memory
+__device__ __forceinline__ float gnet_join_dot(GnetSmem& sm, float part, int row, int half) {
+  sm.dot[half][row] = part;
+  __syncthreads();
+  return (sm.dot[0][row] + sm.dot[1][row]) + sm.b4;
 }
 
 // D[row][n] = sum_k A[row][k] B[n][k]   (A, B K-major tiles)
@@ -425,11 +438,11 @@ struct GradArgs {
 __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_g[];
   GnetSmem& sm = *reinterpret_cast<GnetSmem*>(smem_g);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
   const unsigned int tmem = gnet_setup(sm, a.params, a.wpack);
-  const unsigned int lane_base = (unsigned int)(warp * 32) << 16;
+  const unsigned int lane_base = (unsigned int)((warp & 3) * 32) << 16;  // a warp reads TMEM lanes 32 (warp % 4) ..
   const unsigned int cA = 0, cB = 128, cC = 256, cV1 = 384, cV2 = 400, cV3 = 416, cV4 = 432;
-  const long long r = a.start + (long long)blockIdx.x * 128 + tid;
+  const long long r = a.start + (long long)blockIdx.x * 128 + row;
   const bool act = r < a.end;
   const float inv_b2 = 2.0f / (float)(a.end - a.start);
   unsigned int phase = 0;
@@ -449,13 +462,13 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
     }
   }
   const unsigned int rr = (unsigned int)r;
-  gnet_layer1(sm, fn, tid, rr, a.drop);
-  {  // panel: fn0..fn6, 1 (inactive rows: all zero, so they add nothing to the gradients)
+  gnet_layer1(sm, fn, row, half, rr, a.drop);
+  if (half == 0) {  // panel: fn0..fn6, 1 (inactive rows: all zero, so they add nothing to the gradients)
     float v[8];
 #pragma unroll
     for (int k = 0; k < kGIn; ++k) v[k] = fn[k];
     v[7] = act ? 1.f : 0.f;
-    *reinterpret_cast<uint4*>(sm.panel + aux_off(tid, 0)) = pack8_bf16(v);
+    *reinterpret_cast<uint4*>(sm.panel + aux_off(row, 0)) = pack8_bf16(v);
   }
   tc_publish();
   if (tid == 0) {
@@ -465,7 +478,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  gnet_hidden<false>(sm, tmem + lane_base + cA, sm.b2, sm.A2, tid, rr, 1, a.drop);
+  gnet_hidden<false>(sm, tmem + lane_base + cA, sm.b2, sm.A2, row, half, rr, 1, a.drop);
   tc_publish();
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -473,22 +486,23 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  const float out = gnet_hidden<true>(sm, tmem + lane_base + cB, sm.b3, sm.A3, tid, rr, 2, a.drop) + sm.b4;
+  const float part = gnet_hidden<true>(sm, tmem + lane_base + cB, sm.b3, sm.A3, row, half, rr, 2, a.drop);
+  const float out = gnet_join_dot(sm, part, row, half);
   const float err = act ? out - y : 0.f;
   const float dout = err * inv_b2;
   // D3 = dout w4 (h3 > 0) scale -> A4; dout -> panel column 8
   {
     const float ds = dout * a.drop.scale;
 #pragma unroll 1
-    for (int c = 0; c < 16; ++c) {
-      const unsigned int word = sm.mask[2][c >> 2][tid] >> ((c & 3) * 8);
+    for (int c = half * 8; c < half * 8 + 8; ++c) {
+      const unsigned int word = sm.mask[2][c >> 2][row] >> ((c & 3) * 8);
       float v[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = ((word >> k) & 1u) ? ds * sm.w4[c * 8 + k] : 0.f;
-      *reinterpret_cast<uint4*>(sm.A4 + core_off(tid, c * 8)) = pack8_bf16(v);
+      *reinterpret_cast<uint4*>(sm.A4 + core_off(row, c * 8)) = pack8_bf16(v);
     }
   }
-  *reinterpret_cast<unsigned short*>(sm.panel + aux_off(tid, 8)) = __bfloat16_as_ushort(__float2bfloat16_rn(dout));
+  if (half == 0) *reinterpret_cast<unsigned short*>(sm.panel + aux_off(row, 8)) = __bfloat16_as_ushort(__float2bfloat16_rn(dout));
   tc_publish();
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -499,7 +513,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  gnet_masked(sm, tmem + lane_base + cA, sm.A3, tid, 1, a.drop.scale);  // D2 -> A3 (H3 is done)
+  gnet_masked(sm, tmem + lane_base + cA, sm.A3, row, half, 1, a.drop.scale);  // D2 -> A3 (H3 is done)
   tc_publish();
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -509,7 +523,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  gnet_masked(sm, tmem + lane_base + cA, sm.A4, tid, 0, a.drop.scale);  // D1 -> A4 (D3 is done)
+  gnet_masked(sm, tmem + lane_base + cA, sm.A4, row, half, 0, a.drop.scale);  // D1 -> A4 (D3 is done)
   tc_publish();
   if (tid == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -517,33 +531,36 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  // read-out.  dW2 / dW3 sit transposed in TMEM (lane = input unit i, column = output unit j): for a fixed j the 128
-  // threads write consecutive addresses of row j.  The vector gradients have lane = unit.
+  // read-out.  dW2 / dW3 sit transposed in TMEM (lane = input unit i, column = output unit j): for a fixed j the
+  // threads of a warp write consecutive addresses of row j.  The vector gradients have lane = unit.
   float* gp = a.gpart + (size_t)blockIdx.x * (kGP + 1);
 #pragma unroll 1
-  for (int c0 = 0; c0 < 4; ++c0) {
+  for (int c0 = half * 2; c0 < half * 2 + 2; ++c0) {
     float w[32];
     tmem_ld32(tmem + lane_base + cB + c0 * 32, w);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) gp[gW2 + (c0 * 32 + i) * kGH + tid] = w[i];
+    for (int i = 0; i < 32; ++i) gp[gW2 + (c0 * 32 + i) * kGH + row] = w[i];
     tmem_ld32(tmem + lane_base + cC + c0 * 32, w);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) gp[gW3 + (c0 * 32 + i) * kGH + tid] = w[i];
+    for (int i = 0; i < 32; ++i) gp[gW3 + (c0 * 32 + i) * kGH + row] = w[i];
   }
-  {
-    float v1[16], v2[16], v3[16], v4[16];
+  if (half == 0) {
+    float v1[16], v2[16];
     tmem_ld16(tmem + lane_base + cV1, v1);
     tmem_ld16(tmem + lane_base + cV2, v2);
+#pragma unroll
+    for (int k = 0; k < kGIn; ++k) gp[gW1 + row * kGIn + k] = v1[k];
+    gp[gB1 + row] = v1[7]; gp[gB2 + row] = v2[7];
+  } else {
+    float v3[16], v4[16];
     tmem_ld16(tmem + lane_base + cV3, v3);
     tmem_ld16(tmem + lane_base + cV4, v4);
-#pragma unroll
-    for (int k = 0; k < kGIn; ++k) gp[gW1 + tid * kGIn + k] = v1[k];
-    gp[gB1 + tid] = v1[7]; gp[gB2 + tid] = v2[7]; gp[gB3 + tid] = v3[7]; gp[gW4 + tid] = v4[8];
+    gp[gB3 + row] = v3[7]; gp[gW4 + row] = v4[8];
   }
-  float gb4 = dout, loss = err * err;
+  float gb4 = half == 0 ? dout : 0.f, loss = half == 0 ? err * err : 0.f;
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) { gb4 += __shfl_xor_sync(0xffffffffu, gb4, m); loss += __shfl_xor_sync(0xffffffffu, loss, m); }
-  if ((tid & 31) == 0) { sm.red[warp] = gb4; sm.red[4 + warp] = loss; }
+  if (half == 0 && (tid & 31) == 0) { sm.red[warp] = gb4; sm.red[4 + warp] = loss; }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid == 0) {
@@ -605,11 +622,11 @@ template <typename R>
 __global__ void __launch_bounds__(kGThreads, 1) gnet_walk_kernel(const WalkGArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_g[];
   GnetSmem& sm = *reinterpret_cast<GnetSmem*>(smem_g);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
   const unsigned int tmem = gnet_setup(sm, a.params, a.wpack);
   if (tid == 0) gnet_weights_ready(sm);
-  const unsigned int lane_base = (unsigned int)(warp * 32) << 16;
-  const long long j = (long long)blockIdx.x * 128 + tid;
+  const unsigned int lane_base = (unsigned int)((warp & 3) * 32) << 16;
+  const long long j = (long long)blockIdx.x * 128 + row;
   const bool act = j < a.M;
   const R* Sp = static_cast<const R*>(a.S);
   const GnetNorm nm = *a.nm;
@@ -625,7 +642,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_walk_kernel(const WalkGArgs
     float fn[kGIn];
     gnet_features((float)(s * a.invK), (float)a.sqrt_tau[t], nm, fn);
     const unsigned int rr = (unsigned int)j * 0x01000193u + (unsigned int)t;
-    gnet_layer1(sm, fn, tid, rr, a.drop);
+    gnet_layer1(sm, fn, row, half, rr, a.drop);
     tc_publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -633,7 +650,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_walk_kernel(const WalkGArgs
       umma_commit(&sm.bar);
     }
     tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-    gnet_hidden<false>(sm, tmem + lane_base, sm.b2, sm.A2, tid, rr, 1, a.drop);
+    gnet_hidden<false>(sm, tmem + lane_base, sm.b2, sm.A2, row, half, rr, 1, a.drop);
     tc_publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -641,11 +658,11 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_walk_kernel(const WalkGArgs
       umma_commit(&sm.bar);
     }
     tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-    const float out = gnet_hidden<true, false>(sm, tmem + lane_base + 128, sm.b3, sm.A3, tid, rr, 2, a.drop) + sm.b4;
+    const float out = gnet_join_dot(sm, gnet_hidden<true, false>(sm, tmem + lane_base + 128, sm.b3, sm.A3, row, half, rr, 2, a.drop), row, half);
     const double cont = (double)(out * nm.ystd + nm.ymean);  // om3:640
     const bool ex = live && pay > cont;                       // strict, om3:644
     if (ex) { value = pay * a.Dm[t]; exercised = true; }
-    if (a.exc) {
+    if (a.exc && half == 0) {
       const unsigned int cnt = __reduce_add_sync(0xffffffffu, ex ? 1u : 0u);
       if (cnt) {
         unsigned long long b = ex ? (unsigned long long)__double_as_longlong(s) : bnd_none(a.is_put);
@@ -661,7 +678,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_walk_kernel(const WalkGArgs
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) { f0 += __shfl_xor_sync(0xffffffffu, f0, m); f1 += __shfl_xor_sync(0xffffffffu, f1, m); }
   __shared__ double fred[2][4];
-  if ((tid & 31) == 0) { fred[0][warp] = f0; fred[1][warp] = f1; }
+  if (half == 0 && (tid & 31) == 0) { fred[0][warp] = f0; fred[1][warp] = f1; }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (tid < 2) {
