@@ -307,6 +307,16 @@ def run_own_arm(args):
                                                              np.full(n4, 252), 1, "f32", E.RngSpec(seed=9)), 1)
             others["config4_128_options_x_256k_x252"] = {"ms": dt4 * 1e3, "path_steps_per_s": n4 * 262_144 * 252 / dt4,
                                                          "us_per_option": dt4 / n4 * 1e6}
+            Sg1 = eng.paths(gbm, 100_000, 50, "f32", E.RngSpec(seed=7))
+            for variant in ("gpu", "cpu"):
+                dtn, rn = timed(lambda: eng.lsm_gnet(Sg1, K, R, T, "put", "reference", variant=variant, epochs=25, seed=1,
+                                                     arrays=False), 1)
+                others[f"config1_global_network_lsm_{variant}_variant"] = {
+                    "ms": dtn * 1e3, "rows": rn["n_rows"], "epochs_run": rn["epochs_run"], "price": rn["price"],
+                    "note": "the reference's v3 algorithm: SingleLSMNet(7,128,3) on all dates' rows, tcgen05 forward/backward; "
+                            + ("batch 8192 AdamW (om3gpu:740-798)" if variant == "gpu" else
+                               "batch 256 Adam + ReduceLROnPlateau (om3:565-613; reference CPU: 174 s per epoch)")}
+            del Sg1
             S4 = eng.paths(model, 4_000_000, 252, "f32", E.RngSpec(seed=11))
             dt3, r3 = timed(lambda: eng.lsm_mlp(S4, K, R, T, "put", "reference", hidden=128, epochs=10, lr=1e-3, seed=1,
                                                 arrays=False), 1)
