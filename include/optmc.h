@@ -174,6 +174,26 @@ int optmc_paths_gbm(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rn
                     int32_t dtype, void* S_dev, int64_t ld);
 int optmc_paths_heston(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                        int32_t N, int32_t dtype, void* S_dev, void* V_dev, int64_t ld);
+/* Local-volatility paths (om3:263-333, om3gpu:250-298): the implied-volatility network is evaluated inside the step.
+ * `weights` = the ImprovedIVNetwork (nniv:109-155) state_dict flattened in its own order, host fp32:
+ *   input_proj.weight [H][2], input_proj.bias [H], then per hidden layer l: Linear weight [H][H], bias [H],
+ *   LayerNorm weight [H], bias [H]; output.weight [H], output.bias [1]   (3 H + L (H^2 + 3 H) + H + 1 values).
+ * m_scale / tau_scale: the fitted DataScaler's stds (the pricer divides by them without centring, om3:285-288);
+ * epsilon: the network's output clamp (TrainingConfig.epsilon, 1e-4); K: the strike entering ln(K / S).
+ * Uses mp->S0, mp->r, mp->T; rng as for optmc_paths_gbm (external normals: z1_dev [N][M/2]). */
+typedef struct optmc_ivnet {
+  int32_t hidden;      /* H: 32 or 64 (TrainingConfig.hidden_dim default 64) */
+  int32_t layers;      /* L: TrainingConfig.num_hidden_layers, default 4 */
+  int32_t n_weights;   /* length of weights, checked against H and L */
+  float epsilon;
+  const float* weights;
+  double m_scale, tau_scale, K;
+} optmc_ivnet;
+int optmc_paths_localvol(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, const optmc_ivnet* net,
+                         int64_t M, int32_t N, int32_t dtype, void* S_dev, int64_t ld);
+/* IVModel.get_volatility_batch (om3:277-298): sigma_dev[i] = max(net(ln(K / S_dev[i]) / m_scale, tau / tau_scale), epsilon,
+ * 1e-6) for n device spots (fp64 in and out, like the reference's numpy arrays). */
+int optmc_ivnet_sigma(optmc_ctx* ctx, const optmc_ivnet* net, double tau, const double* S_dev, int64_t n, double* sigma_dev);
 /* The standard normals the Philox path kernels consume, written step-major [N][M/2] (test aid: feed
  * them to the oracle).  which = 0 -> z1 (asset), 1 -> z2 (variance, Heston only). */
 int optmc_philox_normals(optmc_ctx* ctx, const optmc_rng_params* rng, int32_t model, int64_t M, int32_t N,

@@ -59,6 +59,11 @@ class MlpParams(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("epochs", C.c_int32), ("lr", C.c_double), ("seed", C.c_uint64)]
 
 
+class IvNet(C.Structure):  # optmc_ivnet
+    _fields_ = [("hidden", C.c_int32), ("layers", C.c_int32), ("n_weights", C.c_int32), ("epsilon", C.c_float),
+                ("weights", C.POINTER(C.c_float)), ("m_scale", C.c_double), ("tau_scale", C.c_double), ("K", C.c_double)]
+
+
 class GnetParams(C.Structure):  # optmc_gnet_params
     _fields_ = [("hidden", C.c_int32), ("layers", C.c_int32), ("epochs", C.c_int32), ("batch", C.c_int32),
                 ("lr", C.c_double), ("weight_decay", C.c_double), ("decoupled_wd", C.c_int32), ("sched_patience", C.c_int32),
@@ -101,6 +106,9 @@ PROTOTYPES = {
                                   C.c_void_p, C.c_int64]),
     "optmc_paths_heston": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_int64]),
+    "optmc_paths_localvol": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), _P(IvNet), C.c_int64, C.c_int32, C.c_int32,
+                                       C.c_void_p, C.c_int64]),
+    "optmc_ivnet_sigma": (C.c_int, [C.c_void_p, _P(IvNet), C.c_double, C.c_void_p, C.c_int64, C.c_void_p]),
     "optmc_philox_normals": (C.c_int, [C.c_void_p, _P(RngParams), C.c_int32, C.c_int64, C.c_int32, C.c_int32,
                                        C.c_int32, C.c_void_p]),
     "optmc_philox_kat": (C.c_int, [C.c_void_p, C.c_int32, _P(C.c_uint32), _P(C.c_uint32), _P(C.c_uint32)]),

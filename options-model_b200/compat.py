@@ -15,7 +15,8 @@ What differs from the reference, by design:
     from it exactly as the reference does and feed the draws to the kernels, so results match the
     reference draw-for-draw.  The pricer methods use in-kernel Philox keyed by the RNGManager child
     seed; they consume the same number of master draws as the reference (om3:454-455, om3:392).
-  * iv_model (local volatility) is out of scope for this round: NotImplementedError.
+  * iv_model (local volatility, om3:263-333): ``IVModel`` flattens the reference's trained network once; the kernel
+    evaluates it inside every path step (price_american_enhanced_lsm / simulate_local_vol_paths_antithetic).
 """
 from __future__ import annotations
 
@@ -107,6 +108,59 @@ def simulate_heston_paths_antithetic(S0: float, r: float, T: float, v0: float, k
             Zo[1, t] = rng.standard_normal(1)
         z = torch.from_numpy(Zo).to(eng.tdev)
         S = eng.paths(model, 1, N, "f64", E.RngSpec(z1=z[0].contiguous(), z2=z[1].contiguous(), antithetic=False))
+        out[:, M:] = S.cpu().numpy()
+    return out
+
+
+class IVModel:
+    """om3:263-298.  Wraps the reference's trained ``ImprovedIVNetwork`` (any torch module with the same state_dict
+    layout and a fitted ``.scaler``); the weights are flattened once and the network is evaluated by the CUDA
+    kernels -- inside the path step (``simulate_local_vol_paths_antithetic``) or for a batch of spots
+    (``get_volatility_batch``)."""
+
+    def __init__(self, nn_model):
+        self.model = nn_model.eval()
+        if hasattr(nn_model, "scaler") and nn_model.scaler is not None:
+            self.m_scale = nn_model.scaler.m_scale
+            self.tau_scale = nn_model.scaler.tau_scale
+        else:
+            raise ValueError("Model does not have a fitted scaler")
+        sd = nn_model.state_dict()
+        H = int(sd["input_proj.weight"].shape[0])
+        layers = len({k.split(".")[1] for k in sd if k.startswith("layers.")})
+        weights = np.concatenate([v.detach().cpu().numpy().reshape(-1) for v in sd.values()]).astype(np.float32)
+        eps = float(getattr(getattr(nn_model, "config", None), "epsilon", 1e-4))
+        self.net = dict(hidden=H, layers=layers, weights=weights, m_scale=float(self.m_scale), tau_scale=float(self.tau_scale),
+                        epsilon=eps)
+
+    def get_volatility_batch(self, K: float, S_batch: np.ndarray, tau: float) -> np.ndarray:
+        S_batch = np.asarray(S_batch, dtype=np.float64)
+        if K <= 0:
+            raise ValueError(f"K must be positive, got {K}")
+        if np.any(S_batch <= 0):
+            raise ValueError("All S_batch values must be positive")
+        return _engine().ivnet_sigma(self.net, K, S_batch.ravel(), tau).cpu().numpy().reshape(S_batch.shape)
+
+
+def simulate_local_vol_paths_antithetic(S0: float, r: float, T: float, num_simulations: int, num_time_steps: int,
+                                        iv_model: "IVModel", K: float, rng: np.random.Generator) -> np.ndarray:
+    """om3:300-333.  Draws Z_half from ``rng`` exactly like the reference (one (N, M/2) call, then (N, 1) for an odd
+    path), runs the local-volatility kernel in fp64 on those draws, returns S[(N+1), num_simulations] (host)."""
+    import torch
+
+    eng = _engine()
+    N = int(num_time_steps)
+    M = num_simulations // 2 * 2
+    out = np.zeros((N + 1, num_simulations), dtype=np.float64)
+    out[0] = S0
+    if M > 0:
+        Zh = rng.standard_normal((N, M // 2))
+        S = eng.paths_localvol(S0, r, T, iv_model.net, K, M, N, "f64", E.RngSpec(z1=torch.from_numpy(Zh).to(eng.tdev)))
+        out[:, :M] = S.cpu().numpy()
+    if num_simulations % 2 != 0:
+        Zo = rng.standard_normal((N, 1))
+        S = eng.paths_localvol(S0, r, T, iv_model.net, K, 1, N, "f64",
+                               E.RngSpec(z1=torch.from_numpy(Zo).to(eng.tdev), antithetic=False))
         out[:, M:] = S.cpu().numpy()
     return out
 
@@ -234,7 +288,8 @@ class AdvancedOptionPricer:
     # om3:461-472 model routing
     def _model(self, S0: float, T: float) -> E.ModelSpec:
         if self.iv_model is not None:
-            raise NotImplementedError("local-volatility paths (iv_model) are not part of this round (SURVEY.md 8(f) n3)")
+            raise NotImplementedError("iv_model prices through price_american_enhanced_lsm (slab + sweep); the fused "
+                                      "European / batched entry points take GBM or Heston models")
         if self.use_heston and self.heston_params is not None:
             hp = self.heston_params
             return E.heston(S0, self.r, T, hp["v0"], hp["kappa"], hp["theta"], hp["xi"], hp["rho"])
@@ -256,6 +311,18 @@ class AdvancedOptionPricer:
         M = num_simulations // 2 * 2
         if M == 0:
             return float("nan")  # the reference averages an empty cash-flow vector
+        if self.iv_model is not None:  # om3:461-462: local-volatility paths, then the same sweep
+            eng = _engine(self.device)
+            S = eng.paths_localvol(S0, self.r, T, self.iv_model.net, self.K, M, int(num_time_steps), self.dtype, E.RngSpec(seed=seed))
+            if self.lsm_regressor == "nn":
+                out = eng.lsm_gnet(S, self.K, self.r, T, self.option_type, self.semantics, variant=self._nn_variant,
+                                   epochs=self.nn_epochs, lr=self.nn_lr, dropout=self.nn_dropout, seed=int(torch_seed or 0),
+                                   arrays=self.verbose)
+                self.last_result = out
+                return float(out["price"])
+            res = eng.lsm(S, self.K, self.r, T, self.option_type, self.lsm_regressor, self.semantics, arrays=self.verbose)
+            self.last_result = res
+            return float(res.price)
         model = self._model(S0, T)
         if self.lsm_regressor == "nn":  # the reference's own regressor: one SingleLSMNet for all dates (om3:482-651)
             if self.nn_hidden != 128 or self.nn_layers != 3:

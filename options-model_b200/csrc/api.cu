@@ -306,6 +306,21 @@ int optmc_paths_gbm(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rn
   OPTMC_TRY_END
 }
 
+int optmc_paths_localvol(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, const optmc_ivnet* net,
+                         int64_t M, int32_t N, int32_t dtype, void* S_dev, int64_t ld) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return launch_paths_localvol(ctx, mp, rng, net, M, N, dtype, S_dev, ld);
+  OPTMC_TRY_END
+}
+
+int optmc_ivnet_sigma(optmc_ctx* ctx, const optmc_ivnet* net, double tau, const double* S_dev, int64_t n, double* sigma_dev) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return ivnet_sigma_batch(ctx, net, tau, S_dev, n, sigma_dev);
+  OPTMC_TRY_END
+}
+
 int optmc_paths_heston(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                        int32_t N, int32_t dtype, void* S_dev, void* V_dev, int64_t ld) {
   OPTMC_TRY_BEGIN

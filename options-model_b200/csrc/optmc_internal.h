@@ -105,6 +105,10 @@ int ensure_per_date(optmc_ctx* ctx, int N);
 int launch_paths(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M, int32_t N,
                  int32_t dtype, void* S, void* V, int64_t ld);
 size_t path_args_bytes();
+// paths_localvol.cu
+int ivnet_sigma_batch(optmc_ctx* ctx, const optmc_ivnet* net, double tau, const double* S_dev, int64_t n, double* sigma_dev);
+int launch_paths_localvol(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, const optmc_ivnet* net,
+                          int64_t M, int32_t N, int32_t dtype, void* S, int64_t ld);
 int launch_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                        int32_t dtype, int G, const optmc_american_option* opts, void* slab, size_t slab_stride_bytes,
                        int64_t ld, void* d_args, void* h_args);

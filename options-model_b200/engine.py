@@ -185,6 +185,39 @@ class Engine:
             return S[: N + 1, :M], (V[: N + 1, :M] if V is not None else None)
         return S[: N + 1, :M]
 
+    # -- local volatility: the IV network inside the step (om3:263-333) ---------------------------
+    @staticmethod
+    def _ivnet_c(net: dict, K: float):
+        w = np.ascontiguousarray(net["weights"], dtype=np.float32)
+        c = L.IvNet(int(net["hidden"]), int(net["layers"]), int(w.size), float(net.get("epsilon", 1e-4)),
+                    w.ctypes.data_as(C.POINTER(C.c_float)), float(net["m_scale"]), float(net["tau_scale"]), float(K))
+        return c, w  # keep `w` alive during the call
+
+    def paths_localvol(self, S0, r, T, net: dict, K, M: int, N: int, dtype="f32", rng: Optional[RngSpec] = None, out=None):
+        """simulate_local_vol_paths_antithetic (om3:300-333).  ``net`` = dict(hidden, layers, weights (the
+        ImprovedIVNetwork state_dict flattened in its own order), m_scale, tau_scale, epsilon)."""
+        rng = rng or RngSpec()
+        S = out if out is not None else self.alloc_slab(M, N, dtype)
+        mp = ModelSpec(L.MODEL_GBM, L.SCHEME_GBM_LOG_EULER, float(S0), float(r), float(T), sigma=0.0).c()
+        rp = rng.c()
+        c, keep = self._ivnet_c(net, K)
+        self._sync_stream()
+        L.check(self.lib.optmc_paths_localvol(self._h, C.byref(mp), C.byref(rp), C.byref(c), int(M), int(N), _dtype_code(dtype),
+                                              S.data_ptr(), S.stride(0)))
+        del keep
+        return S[:, :M]
+
+    def ivnet_sigma(self, net: dict, K, S_batch, tau: float):
+        """IVModel.get_volatility_batch (om3:277-298) on the device: fp64 spots in, fp64 volatilities out."""
+        t = self.torch
+        Sd = t.as_tensor(np.ascontiguousarray(S_batch, dtype=np.float64)).to(self.tdev) if not t.is_tensor(S_batch) else S_batch.to(self.tdev, t.float64).contiguous()
+        outd = t.empty_like(Sd)
+        c, keep = self._ivnet_c(net, K)
+        self._sync_stream()
+        L.check(self.lib.optmc_ivnet_sigma(self._h, C.byref(c), float(tau), Sd.data_ptr(), int(Sd.numel()), outd.data_ptr()))
+        del keep
+        return outd
+
     def philox_normals(self, model_id: int, M: int, N: int, which: int = 0, dtype="f32",
                        rng: Optional[RngSpec] = None):
         rng = rng or RngSpec()

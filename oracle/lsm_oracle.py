@@ -264,6 +264,62 @@ def heston_european_analytic(S0, K, r, T, v0, kappa, theta, xi, rho, option_type
 
 
 # --------------------------------------------------------------------------------------
+# Local volatility: the IV network inside the step (om3:263-333; network nniv:109-155)
+# --------------------------------------------------------------------------------------
+def _erf32(x):
+    from math import erf
+    return np.vectorize(erf, otypes=[np.float64])(x.astype(np.float64)).astype(np.float32)
+
+
+def ivnet_forward(net, X):
+    """ImprovedIVNetwork.forward in eval mode (nniv:146-155), fp32: h = GELU(W_in x + b_in); L times
+    h = h + GELU(LayerNorm(W h + b)) (dropout is the identity); out = clamp(W_out h + b_out, min=epsilon).
+    ``net`` = dict(hidden, layers, weights (state_dict order, flat fp32), m_scale, tau_scale, epsilon)."""
+    H, L = int(net["hidden"]), int(net["layers"])
+    w = np.asarray(net["weights"], dtype=np.float32)
+    gelu = lambda v: (np.float32(0.5) * v * (np.float32(1) + _erf32(v * np.float32(0.70710678118654752440)))).astype(np.float32)  # noqa: E731
+    o = 0
+    W_in = w[o:o + 2 * H].reshape(H, 2); o += 2 * H
+    b_in = w[o:o + H]; o += H
+    h = gelu((X.astype(np.float32) @ W_in.T + b_in).astype(np.float32))
+    for _ in range(L):
+        W = w[o:o + H * H].reshape(H, H); o += H * H
+        b = w[o:o + H]; o += H
+        g = w[o:o + H]; o += H
+        be = w[o:o + H]; o += H
+        z = (h @ W.T + b).astype(np.float32)
+        mu = z.mean(axis=1, keepdims=True, dtype=np.float32)
+        var = ((z - mu) ** 2).mean(axis=1, keepdims=True, dtype=np.float32)
+        zn = ((z - mu) / np.sqrt(var + np.float32(1e-5)) * g + be).astype(np.float32)
+        h = (h + gelu(zn)).astype(np.float32)
+    w_out = w[o:o + H]; o += H
+    out = (h @ w_out + w[o]).astype(np.float32)
+    return np.maximum(out, np.float32(net["epsilon"]))
+
+
+def ivnet_sigma(net, K, S_batch, tau):
+    """IVModel.get_volatility_batch (om3:277-298): moneyness scaled by the scaler's std but NOT centred (App. B-7)."""
+    tau = max(float(tau), 1e-6)
+    S_batch = np.asarray(S_batch, dtype=np.float64)
+    m = np.log(np.maximum(K, 1e-8) / np.maximum(S_batch, 1e-8))
+    X = np.column_stack([m / net["m_scale"], np.full_like(m, tau / net["tau_scale"])])
+    return np.maximum(ivnet_forward(net, X.astype(np.float32)), np.float32(1e-6)).astype(np.float64)
+
+
+def localvol_paths_antithetic(S0, r, T, M, N, net, K, Z_half):
+    """simulate_local_vol_paths_antithetic (om3:300-320, even M): Z = [Z_half, -Z_half]."""
+    dt = T / N
+    S = np.zeros((N + 1, M), dtype=np.float64)
+    S[0] = S0
+    Z = np.concatenate([Z_half, -Z_half], axis=1)
+    for t in range(1, N + 1):
+        tau_t = max(T - (t - 1) * dt, 1e-6)
+        sig = ivnet_sigma(net, K, S[t - 1], tau_t)
+        S[t] = S[t - 1] * np.exp((r - 0.5 * sig**2) * dt + sig * np.sqrt(dt) * Z[t - 1])
+    return S
+
+
+# --------------------------------------------------------------------------------------
 # Path simulation (torch fp32 variants, restated in numpy float32)
 # --------------------------------------------------------------------------------------
 

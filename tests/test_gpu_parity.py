@@ -837,3 +837,83 @@ def test_compat_pricer_nn_regressor(mods):
     assert 5.5 < v < 8.5 and p.last_result["epochs_run"] >= 1
     with pytest.raises(ValueError):
         compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, lsm_regressor="nn", nn_hidden=64).price_american_enhanced_lsm(100.0, 1.0, 1000, 10)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Local volatility: the IV network inside the path step against the REAL reference
+# (tests/golden/ref_localvol.npz, oracle/gen_golden_localvol.py)
+# ------------------------------------------------------------------------------------------------------
+def _lv_net(g, tag):
+    H, Lh, ms, ts, eps = g[f"{tag}_meta"]
+    return dict(hidden=int(H), layers=int(Lh), weights=g[f"{tag}_weights"], m_scale=float(ms), tau_scale=float(ts), epsilon=float(eps))
+
+
+@pytest.mark.parametrize("tag", ["h64", "h32"])
+def test_localvol_sigma_and_paths_vs_reference_golden(eng, mods, golden_dir, tag):
+    L, E, orc = mods
+    g = np.load(os.path.join(golden_dir, "ref_localvol.npz"))
+    net = _lv_net(g, tag)
+    S0, r, T, K, M, N = g[f"{tag}_args"]
+    M, N = int(M), int(N)
+    # IVModel.get_volatility_batch: fp32 network, identical inputs -> fp32 rounding of a 5-layer network
+    for i, tau in enumerate((1.0, 0.3, 1e-9)):
+        sig = eng.ivnet_sigma(net, K, g[f"{tag}_spots"], tau).cpu().numpy()
+        np.testing.assert_allclose(sig, g[f"{tag}_sigma"][i], rtol=2e-5)
+    # simulate_local_vol_paths_antithetic on the reference's own draws: fp64 state, fp32 network
+    S = eng.paths_localvol(S0, r, T, net, K, M, N, "f64", E.RngSpec(z1=_dev(g[f"{tag}_Zh"])))
+    np.testing.assert_allclose(S.cpu().numpy(), g[f"{tag}_S"], rtol=2e-5)
+    # fp32 storage (the production layout): 1e-4, the north star's fp32 tolerance
+    S32 = eng.paths_localvol(S0, r, T, net, K, M, N, "f32", E.RngSpec(z1=_dev(g[f"{tag}_Zh"])))
+    np.testing.assert_allclose(S32.cpu().numpy(), g[f"{tag}_S"], rtol=1e-4)
+
+
+def test_localvol_compat_drop_in_and_pricing(mods, golden_dir):
+    """compat.IVModel + simulate_local_vol_paths_antithetic take what the reference takes (a torch module with the
+    ImprovedIVNetwork state_dict and a fitted scaler, a numpy Generator) and return the reference's paths."""
+    from options_model_b200 import compat
+
+    g = np.load(os.path.join(golden_dir, "ref_localvol.npz"))
+    net = _lv_net(g, "h64")
+    H, Lh = net["hidden"], net["layers"]
+
+    class Net(torch.nn.Module):  # same parameter names / order as nniv.ImprovedIVNetwork
+        def __init__(self):
+            super().__init__()
+            self.input_proj = torch.nn.Linear(2, H)
+            self.layers = torch.nn.ModuleList([torch.nn.Sequential(torch.nn.Linear(H, H), torch.nn.LayerNorm(H), torch.nn.GELU(),
+                                                                   torch.nn.Identity()) for _ in range(Lh)])
+            self.output = torch.nn.Linear(H, 1)
+
+    m = Net()
+    o = 0
+    with torch.no_grad():
+        for p in m.state_dict().values():
+            n = p.numel()
+            p.copy_(torch.from_numpy(net["weights"][o:o + n].reshape(tuple(p.shape))))
+            o += n
+    m.scaler = type("S", (), dict(m_scale=net["m_scale"], tau_scale=net["tau_scale"]))()
+    m.config = type("C", (), dict(epsilon=net["epsilon"]))()
+    ivm = compat.IVModel(m)
+    S0, r, T, K, M, N = g["h64_args"]
+    S = compat.simulate_local_vol_paths_antithetic(S0, r, T, int(M), int(N), ivm, K, np.random.default_rng(11))
+    np.testing.assert_allclose(S, g["h64_S"], rtol=2e-5)
+    S_odd = compat.simulate_local_vol_paths_antithetic(S0, r, T, 5, 6, ivm, K, np.random.default_rng(1))
+    assert S_odd.shape == (7, 5) and np.isfinite(S_odd).all()
+    with pytest.raises(ValueError):
+        ivm.get_volatility_batch(K, np.array([1.0, -1.0]), 0.5)
+    # the pricer routes iv_model through the local-volatility paths and the same sweep (om3:461-462)
+    p = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=None, option_type="put", rng_manager=compat.RNGManager(42), iv_model=ivm)
+    v = p.price_american_enhanced_lsm(100.0, 1.0, num_simulations=50_000, num_time_steps=25)
+    assert np.isfinite(v) and 0.5 < v < 40.0
+
+
+def test_localvol_philox_counters_and_throughput(eng, mods, golden_dir):
+    L, E, orc = mods
+    g = np.load(os.path.join(golden_dir, "ref_localvol.npz"))
+    net = _lv_net(g, "h64")
+    M, N = 8192, 12
+    rng = E.RngSpec(seed=31)
+    S = eng.paths_localvol(100.0, 0.05, 1.0, net, 105.0, M, N, "f64", rng)
+    Z = eng.philox_normals(L.MODEL_GBM, M, N, 0, "f64", rng)  # the GBM counter layout: 4 steps per Philox block
+    ref = orc.localvol_paths_antithetic(100.0, 0.05, 1.0, M, N, net, 105.0, Z.cpu().numpy())
+    np.testing.assert_allclose(S.cpu().numpy(), ref, rtol=5e-5)

@@ -218,3 +218,17 @@ def test_single_lsm_net_fit_runs_the_reference_training_loop():
                                    target_ddof=0 if variant == "cpu" else 1)
         assert st["n_rows"] > 0 and len(log) >= 1 and log[-1] <= log[0] + 1e-9
         assert 4.0 < price < 12.0
+
+
+@pytest.mark.parametrize("tag", ["h64", "h32"])
+def test_localvol_oracle_vs_reference_golden(golden_dir, tag):
+    """The numpy restatement of IVModel.get_volatility_batch + simulate_local_vol_paths_antithetic (om3:263-333) against
+    vectors produced by the real reference (oracle/gen_golden_localvol.py)."""
+    g = np.load(os.path.join(golden_dir, "ref_localvol.npz"))
+    H, Lh, ms, ts, eps = g[f"{tag}_meta"]
+    net = dict(hidden=int(H), layers=int(Lh), weights=g[f"{tag}_weights"], m_scale=float(ms), tau_scale=float(ts), epsilon=float(eps))
+    S0, r, T, K, M, N = g[f"{tag}_args"]
+    for i, tau in enumerate((1.0, 0.3, 1e-9)):
+        np.testing.assert_allclose(orc.ivnet_sigma(net, K, g[f"{tag}_spots"], tau), g[f"{tag}_sigma"][i], rtol=1e-5)
+    S = orc.localvol_paths_antithetic(S0, r, T, int(M), int(N), net, K, g[f"{tag}_Zh"])
+    np.testing.assert_allclose(S, g[f"{tag}_S"], rtol=1e-5)
