@@ -307,6 +307,17 @@ def run_own_arm(args):
                                                              np.full(n4, 252), 1, "f32", E.RngSpec(seed=9)), 1)
             others["config4_128_options_x_256k_x252"] = {"ms": dt4 * 1e3, "path_steps_per_s": n4 * 262_144 * 252 / dt4,
                                                          "us_per_option": dt4 / n4 * 1e6}
+            # local volatility: ImprovedIVNetwork(2 -> 64, 4 residual LayerNorm/GELU blocks) inside every step
+            rs = np.random.default_rng(0)
+            Hn, Ln = 64, 4
+            wts = (0.1 * rs.standard_normal(3 * Hn + Ln * (Hn * Hn + 3 * Hn) + Hn + 1)).astype(np.float32)
+            wts[-1] = 0.2
+            ivn = dict(hidden=Hn, layers=Ln, weights=wts, m_scale=0.15, tau_scale=0.4, epsilon=1e-4)
+            dlv, _ = timed(lambda: eng.paths_localvol(S0, R, T, ivn, K, 100_000, 50, "f32", E.RngSpec(seed=3)), 5)
+            flop = 2.0 * (2 * Hn + Ln * Hn * Hn + Hn) * 100_000 * 50
+            others["local_vol_paths_100k_x50_ivnet64x4"] = {"ms": dlv * 1e3, "path_steps_per_s": 5e6 / dlv,
+                                                            "fp32_TFLOPs": flop / dlv / 1e12,
+                                                            "note": "network evaluated per path per step on the CUDA cores (fp32 parity with the reference)"}
             Sg1 = eng.paths(gbm, 100_000, 50, "f32", E.RngSpec(seed=7))
             for variant in ("gpu", "cpu"):
                 dtn, rn = timed(lambda: eng.lsm_gnet(Sg1, K, R, T, "put", "reference", variant=variant, epochs=25, seed=1,

@@ -14,6 +14,7 @@
 // 2 H + L H^2 + H fused multiply-adds per path-step (16.6 k for the default H = 64, L = 4): CUDA-core bound by
 // design -- bf16 tensor-core products would move sigma in the third digit, outside the parity tolerance.
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -23,11 +24,12 @@
 
 namespace optmc {
 
-constexpr int kLvThreads = 256;
+constexpr int kLvThreads = 256;   // sigma kernel; the path kernel runs 512 (fp32) / 384 (fp64) threads: one CTA per SM,
+                                  // weights + one pre-activation column per thread in shared memory
 
 struct LvArgs {
   void* S;
-  long long ld, M, Mh;
+  long long ld, M, Mh, per_cta;
   int N, anti;
   const void* z1;
   int z_f64;
@@ -44,7 +46,7 @@ struct LvArgs {
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // sigma = max(net([x0, x1]), epsilon, 1e-6); w = weights in shared memory, zc = this thread's pre-activation column
-template <int H>
+template <int H, int NT>
 __device__ __forceinline__ float ivnet_sigma(const float* w, int layers, float x0, float x1, float* zc, float epsilon) {
   const float* w_in = w;            // [H][2]
   const float* b_in = w + 2 * H;    // [H]
@@ -72,16 +74,16 @@ __device__ __forceinline__ float ivnet_sigma(const float* w, int layers, float x
         acc1 = fmaf(q.w, h[4 * i4 + 3], acc1);
       }
       const float zj = acc0 + acc1;
-      zc[j * kLvThreads] = zj;
+      zc[j * NT] = zj;
       sum += zj;
     }
     const float mean = sum * (1.0f / H);
     float var = 0.f;
 #pragma unroll 8
-    for (int j = 0; j < H; ++j) { const float d = zc[j * kLvThreads] - mean; var = fmaf(d, d, var); }
+    for (int j = 0; j < H; ++j) { const float d = zc[j * NT] - mean; var = fmaf(d, d, var); }
     const float rstd = rsqrtf(var * (1.0f / H) + 1e-5f);
 #pragma unroll
-    for (int j = 0; j < H; ++j) h[j] += gelu_exact(fmaf((zc[j * kLvThreads] - mean) * rstd, g[j], be[j]));
+    for (int j = 0; j < H; ++j) h[j] += gelu_exact(fmaf((zc[j * NT] - mean) * rstd, g[j], be[j]));
     wl += H * H + 3 * H;
   }
   const float* w_out = wl;
@@ -92,17 +94,18 @@ __device__ __forceinline__ float ivnet_sigma(const float* w, int layers, float x
 }
 
 // shared memory: weights (state_dict order) followed by the per-thread pre-activation columns z[H][threads]
-template <typename R, int H>
-__global__ void __launch_bounds__(kLvThreads, 1) paths_localvol_kernel(const LvArgs a) {
+template <typename R, int H, int NT>
+__global__ void __launch_bounds__(NT, 1) paths_localvol_kernel(const LvArgs a) {
   extern __shared__ __align__(16) float smem_lv[];
   const int n_w = 3 * H + a.layers * (H * H + 3 * H) + H + 1;
   const int n_w4 = (n_w + 3) & ~3;
   float* w = smem_lv;
-  float* zcol = smem_lv + n_w4;  // [H][kLvThreads]
-  for (int i = threadIdx.x; i < n_w; i += kLvThreads) w[i] = a.weights[i];
+  float* zcol = smem_lv + n_w4;  // [H][NT]
+  for (int i = threadIdx.x; i < n_w; i += NT) w[i] = a.weights[i];
   __syncthreads();
-  const long long p = (long long)blockIdx.x * kLvThreads + threadIdx.x;
-  if (p >= a.M) return;
+  // a CTA owns the contiguous paths [blockIdx.x per_cta, ...): one balanced wave of CTAs whatever the path count
+  const long long p_end = (long long)(blockIdx.x + 1) * a.per_cta < a.M ? (long long)(blockIdx.x + 1) * a.per_cta : a.M;
+  for (long long p = (long long)blockIdx.x * a.per_cta + threadIdx.x; p < p_end; p += NT) {
   const bool minus = a.anti && p >= a.Mh;
   const long long col = minus ? p - a.Mh : p;   // the pair this path belongs to (om3:308-309 column layout)
   const float sign = minus ? -1.f : 1.f;
@@ -138,11 +141,12 @@ __global__ void __launch_bounds__(kLvThreads, 1) paths_localvol_kernel(const LvA
       const double kp = a.K > 1e-8 ? a.K : 1e-8;
       const float x0 = (float)(log(kp / sp) / a.m_scale);   // float64 quotient, then .float() (om3:286-291)
       const float x1 = (float)(tau / a.tau_scale);
-      const float sig = ivnet_sigma<H>(w, a.layers, x0, x1, zc, a.epsilon);
+      const float sig = ivnet_sigma<H, NT>(w, a.layers, x0, x1, zc, a.epsilon);
       const double sg = (double)sig;
       s = (R)((double)s * exp((a.r - 0.5 * sg * sg) * a.dt + sg * a.sqrt_dt * z));
       out[(size_t)t * a.ld] = s;
     }
+  }
   }
 }
 
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(kLvThreads, 1) ivnet_sigma_kernel(const float*
   if (p >= n) return;
   if (tau < 1e-6) tau = 1e-6;
   const double sp = S[p] > 1e-8 ? S[p] : 1e-8, kp = K > 1e-8 ? K : 1e-8;
-  out[p] = (double)ivnet_sigma<H>(smem_lv, layers, (float)(log(kp / sp) / m_scale), (float)(tau / tau_scale),
+  out[p] = (double)ivnet_sigma<H, kLvThreads>(smem_lv, layers, (float)(log(kp / sp) / m_scale), (float)(tau / tau_scale),
                                   smem_lv + n_w4 + threadIdx.x, epsilon);
 }
 
@@ -190,14 +194,31 @@ int launch_paths_localvol(optmc_ctx* ctx, const optmc_model_params* mp, const op
   a.S0 = mp->S0; a.r = mp->r; a.T = mp->T; a.dt = mp->T / N; a.sqrt_dt = sqrt(a.dt); a.K = net->K;
   a.weights = static_cast<const float*>(ctx->batch_dev); a.layers = net->layers;
   a.m_scale = net->m_scale; a.tau_scale = net->tau_scale; a.epsilon = net->epsilon;
-  const unsigned grid = (unsigned)((M + kLvThreads - 1) / kLvThreads);
-#define OPTMC_LV_LAUNCH(R_, H_)                                                                                         \
+  // one wave: per_cta = ceil(M / SMs) paths per CTA, and the thread count that wastes the fewest thread slots
+  const long long per_cta = (M + ctx->sm_count - 1) / ctx->sm_count;
+  a.per_cta = per_cta;
+  const unsigned grid = (unsigned)((M + per_cta - 1) / per_cta);
+  auto waste = [&](int nt) { const long long it = (per_cta + nt - 1) / nt; return (double)(it * nt) / (double)per_cta; };
+#define OPTMC_LV_LAUNCH(R_, H_, NT_)                                                                                    \
   do {                                                                                                                  \
-    OPTMC_CUDA(cudaFuncSetAttribute(paths_localvol_kernel<R_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    paths_localvol_kernel<R_, H_><<<grid, kLvThreads, smem, ctx->stream>>>(a);                                          \
+    const size_t sm_ = (size_t)((n_w + 3) & ~3) * 4 + (size_t)H_ * NT_ * 4;                                             \
+    if (sm_ > (size_t)ctx->max_smem_optin) { set_error("IV network does not fit shared memory"); return OPTMC_EUNSUPPORTED; } \
+    OPTMC_CUDA(cudaFuncSetAttribute(paths_localvol_kernel<R_, H_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
+    paths_localvol_kernel<R_, H_, NT_><<<grid, NT_, sm_, ctx->stream>>>(a);                                             \
   } while (0)
-  if (dtype == OPTMC_F64) { if (H == 64) OPTMC_LV_LAUNCH(double, 64); else OPTMC_LV_LAUNCH(double, 32); }
-  else { if (H == 64) OPTMC_LV_LAUNCH(float, 64); else OPTMC_LV_LAUNCH(float, 32); }
+#define OPTMC_LV_PICK(R_, H_, BIG_)                                                                  \
+  do {                                                                                               \
+    int nt = 256;                                                                                    \
+    if (waste(384) <= waste(nt) + 0.02) nt = 384;                                                    \
+    if (BIG_ && waste(512) <= waste(nt) + 0.02) nt = 512;                                            \
+    if (const char* e_ = getenv("OPTMC_LV_NT")) { const int v_ = atoi(e_); if (v_ == 256 || v_ == 384 || (BIG_ && v_ == 512)) nt = v_; } \
+    if (nt == 512) OPTMC_LV_LAUNCH(R_, H_, 512);                                                     \
+    else if (nt == 384) OPTMC_LV_LAUNCH(R_, H_, 384);                                                \
+    else OPTMC_LV_LAUNCH(R_, H_, 256);                                                               \
+  } while (0)
+  if (dtype == OPTMC_F64) { if (H == 64) OPTMC_LV_PICK(double, 64, false); else OPTMC_LV_PICK(double, 32, false); }
+  else { if (H == 64) OPTMC_LV_PICK(float, 64, true); else OPTMC_LV_PICK(float, 32, true); }
+#undef OPTMC_LV_PICK
 #undef OPTMC_LV_LAUNCH
   ctx->launches++;
   OPTMC_CUDA(cudaGetLastError());
