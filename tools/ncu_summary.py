@@ -1,9 +1,12 @@
 """Turn the ncu artefacts a gpurun call brought back (gpurun_out/) into the tracked summaries under profiles/.
 
-  python tools/ncu_summary.py [round_tag]
+  python tools/ncu_summary.py [round_tag] [raw_csv ...]
 
 Inputs : gpurun_out/launches_<tag>.csv  (ncu --metrics gpu__time_duration.sum launch list)
-         gpurun_out/prof_<tag>.ncu-rep  (ncu --set full capture of the two hot kernels)
+         gpurun_out/prof_<tag>.ncu-rep  (ncu --set full capture), and / or raw CSV exports of such captures
+         (`ncu -i x.ncu-rep --page raw --csv`, made on the GPU box when the report is too large to bring back);
+         kernels found in a later input replace those of an earlier one, kernels only in the existing
+         profiles/ncu_<tag>_summary.json are kept.
 Outputs: profiles/launches_<tag>.csv (copy), profiles/ncu_<tag>_summary.json, profiles/ncu_<tag>_summary.md
 bench.py reads profiles/ncu_<tag>_summary.json for roofline.traffic (DRAM bytes per launch of the dominant kernel).
 """
@@ -21,6 +24,10 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 summary = {"tag": tag, "launches": {}, "kernels": {}}
+prev_json = os.path.join(out_dir, f"ncu_{tag}_summary.json")
+if os.path.exists(prev_json):
+    summary = json.load(open(prev_json))
+extra_csv = sys.argv[2:]
 
 launch_csv = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 if os.path.exists(launch_csv):
@@ -66,10 +73,10 @@ WANT = {
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio": "stall_not_selected",
 }
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
+def ingest(raw_text):
+    rows = list(csv.reader(raw_text.splitlines()))
     hdr, units = rows[0], rows[1]
+    fresh = {}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
         k = {}
@@ -81,7 +88,14 @@ if os.path.exists(rep):
                     continue
                 k[WANT[h]] = v * UNIT.get(units[i], 1.0) if WANT[h] in ("duration", "dram_read", "dram_write") else v
         k["dram_bytes"] = k.get("dram_read", 0.0) + k.get("dram_write", 0.0)
-        summary["kernels"].setdefault(name, []).append(k)
+        fresh.setdefault(name, []).append(k)
+    summary["kernels"].update(fresh)
+
+
+if os.path.exists(rep) and not extra_csv:
+    ingest(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
+for path in extra_csv:
+    ingest(open(path).read())
 
 with open(os.path.join(out_dir, f"ncu_{tag}_summary.json"), "w") as f:
     json.dump(summary, f, indent=1)

@@ -1,6 +1,7 @@
 """Runs every kernel family once (after a warm-up) so that one ncu invocation can capture them all:
 batched paths + grouped persistent sweep (the bench step), single-option sweep, global-regression LSM passes,
-per-date NN-LSM on CUDA cores (hidden 32) and on tcgen05 (hidden 128), fused European batch."""
+per-date NN-LSM on CUDA cores (hidden 32) and on tcgen05 (hidden 128), fused European batch, the global network LSM
+(SingleLSMNet on tcgen05: row table, training steps, decision pass) and the local-volatility path kernel."""
 import os
 import sys
 
@@ -32,5 +33,14 @@ for rep in range(2):  # rep 0 = warm-up, rep 1 = the captured launches (ncu -s s
     Kc, Tc = np.meshgrid(np.linspace(80, 120, 20), np.linspace(0.1, 1.0, 10))
     calib = E.heston(100.0, 0.05, 1.0, scheme=L.SCHEME_HESTON_REF_CALIB, **HP)
     eng.price_european_batch(calib, 50_000, 100, Kc.ravel(), Tc.ravel(), np.zeros(200, dtype=np.int32), "f32", E.RngSpec(seed=1))
+    Sg = eng.paths(E.gbm(100.0, 0.05, 1.0, 0.2), 100_000, 50, "f32", E.RngSpec(seed=7))
+    eng.lsm_gnet(Sg, 100.0, 0.05, 1.0, "put", variant="gpu", epochs=1, seed=1, arrays=False, batch=8192)
+    rs = np.random.default_rng(0)
+    w = (0.1 * rs.standard_normal(3 * 64 + 4 * (64 * 64 + 3 * 64) + 64 + 1)).astype(np.float32)
+    w[-1] = 0.2
+    eng.paths_localvol(100.0, 0.05, 1.0, dict(hidden=64, layers=4, weights=w, m_scale=0.15, tau_scale=0.4, epsilon=1e-4),
+                       100.0, 100_000, 50, "f32", E.RngSpec(seed=3))
+    qe = E.heston(100.0, 0.05, 1.0, scheme=L.SCHEME_HESTON_QE, **HP)
+    eng.paths(qe, M, 50, "f32", E.RngSpec(seed=5))
     torch.cuda.synchronize()
 print("profile_all done")
