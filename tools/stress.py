@@ -50,4 +50,23 @@ for H in (32, 128):
     t(f"lsm_mlp 2M x 40 hidden {H} textbook", lambda H=H: eng.lsm_mlp(S, 100.0, 0.05, 1.0, "put", "textbook", hidden=H, epochs=5, arrays=False).price)
 K, T = np.meshgrid(np.linspace(60, 140, 64), np.linspace(0.05, 2, 32))
 t("price_european_batch 2048 options x 100k x 64 (GBM)", lambda: eng.price_european_batch(g, 100_000, 64, K.ravel(), T.ravel(), np.ones(2048, dtype=np.int32))[0][:3])
+# global network LSM: odd sizes, both dtypes, large row tables, partial tiles / partial batches
+for M, N, dt, variant, bs in ((100_003 * 2, 37, "f32", "gpu", None), (50_000, 50, "f64", "cpu", 1000), (2_000_000, 100, "f32", "gpu", 131072),
+                              (130, 3, "f64", "gpu", None), (1_000_000, 252, "f32", "gpu", 65536)):
+    def run(M=M, N=N, dt=dt, variant=variant, bs=bs):
+        Sx = eng.paths(h, M, N, dt, E.RngSpec(seed=5))
+        r = eng.lsm_gnet(Sx, 100.0, 0.05, 1.0, "put", variant=variant, epochs=1, batch=bs, seed=2, arrays=True)
+        return f"price {r['price']:.4f} rows {r['n_rows']} loss {r['best_loss']:.4f} launches {r['n_launches']}"
+    t(f"lsm_gnet M={M} N={N} {dt} {variant} batch={bs}", run)
+# local volatility: sizes around the one-wave partition, both widths and dtypes
+rs = np.random.default_rng(0)
+for Hn, Ln in ((64, 4), (32, 1), (64, 0), (32, 8)):
+    w = (0.1 * rs.standard_normal(3 * Hn + Ln * (Hn * Hn + 3 * Hn) + Hn + 1)).astype(np.float32)
+    w[-1] = 0.2
+    net = dict(hidden=Hn, layers=Ln, weights=w, m_scale=0.15, tau_scale=0.4, epsilon=1e-4)
+    for M, N, dt in ((2, 3, "f64"), (146, 5, "f32"), (148 * 512 + 2, 7, "f32"), (300_000, 20, "f64")):
+        def run(M=M, N=N, dt=dt, net=net):
+            Sx = eng.paths_localvol(100.0, 0.05, 1.0, net, 100.0, M, N, dt, E.RngSpec(seed=5))
+            return f"S_T mean {float(Sx[N].double().mean()):.3f} finite {bool(torch.isfinite(Sx).all())}"
+        t(f"paths_localvol H={Hn} L={Ln} M={M} N={N} {dt}", run)
 print("stress done")
