@@ -254,6 +254,14 @@ int optmc_mlp_init_params(int32_t hidden, uint64_t seed, int32_t date, float* ou
 int optmc_mlp_grad_debug(optmc_ctx* ctx, int32_t hidden, int64_t n, const float* xs, const float* ys, const float* params,
                          float* grads, float* cont);
 
+/* Out-of-sample exercise (not in the reference, whose continuation is in-sample): price the policy
+ * "exercise at date t iff payoff(S) > sum_i betas[t][i] (S/K)^i" -- betas = host [(N+1)][p] exactly as optmc_lsm_poly
+ * returns them (p = 3 / 4 for POLY2 / POLY3; NaN rows = no exercise at that date) -- on a DIFFERENT slab in one
+ * streaming pass.  Semantics flags as for the sweep (sticky mask, N-1 discounts).  out->betas (if given) echoes the
+ * input, out->n_itm is zero. */
+int optmc_lsm_apply_policy(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                           const optmc_lsm_params* lp, const double* betas, optmc_lsm_result* out);
+
 /* ---- global network LSM: the reference's v3 algorithm with its own regressor (om3:482-651, om3gpu:695-833) ----
  * Pass 1 collects the in-the-money rows of every date (features om3:105-121, targets = discounted terminal
  * payoffs), the features and the target are z-scored (om3:550-563), ONE SingleLSMNet(7, 128, 3) (om3:85-103) is

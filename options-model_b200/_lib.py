@@ -127,6 +127,8 @@ PROTOTYPES = {
     "optmc_mlp_init_params": (C.c_int, [C.c_int32, C.c_uint64, C.c_int32, _P(C.c_float)]),
     "optmc_mlp_grad_debug": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, _P(C.c_float), _P(C.c_float), _P(C.c_float),
                                        _P(C.c_float), _P(C.c_float)]),
+    "optmc_lsm_apply_policy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
+                                         _P(C.c_double), _P(LsmResult)]),
     "optmc_lsm_gnet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
                                  _P(GnetParams), _P(GnetResult)]),
     "optmc_gnet_grad_debug": (C.c_int, [C.c_void_p, C.c_int64, _P(C.c_float), _P(C.c_float), _P(C.c_float), _P(C.c_float),

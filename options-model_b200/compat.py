@@ -260,7 +260,7 @@ class AdvancedOptionPricer:
                  nn_layers: int = 3, nn_dropout: float = 0.10,
                  # engine extensions (not in the reference)
                  lsm_regressor: str = "poly2", semantics: str = "reference", dtype: str = "f32", device: int = 0,
-                 gpu_reference_quirks: bool = False, batched: bool = True):
+                 gpu_reference_quirks: bool = False, batched: bool = True, out_of_sample: bool = False):
         self.K = K
         self.r = r
         self.sigma = sigma
@@ -282,6 +282,7 @@ class AdvancedOptionPricer:
         self.device = device
         self.gpu_reference_quirks = gpu_reference_quirks
         self.batched = batched
+        self.out_of_sample = out_of_sample  # fit the polynomial on one path set, exercise on an independent one
         self.last_result: Optional[E.SweepResult] = None
         self._nn_variant = "cpu"  # training defaults of om3:565-613; the *_gpu entry point switches to om3gpu:740-798
 
@@ -334,9 +335,14 @@ class AdvancedOptionPricer:
                                arrays=self.verbose)
             self.last_result = out
             return float(out["price"])
-        res = _engine(self.device).price_american(model, M, int(num_time_steps), self.K, self.option_type, self.dtype,
-                                                  E.RngSpec(seed=seed), basis=self.lsm_regressor,
-                                                  semantics=self.semantics, arrays=self.verbose)
+        eng = _engine(self.device)
+        res = eng.price_american(model, M, int(num_time_steps), self.K, self.option_type, self.dtype,
+                                 E.RngSpec(seed=seed), basis=self.lsm_regressor,
+                                 semantics=self.semantics, arrays=self.verbose or self.out_of_sample)
+        if self.out_of_sample:  # the fitted policy priced on fresh paths (Philox stream 1 of the same seed)
+            S_new = eng.paths(model, M, int(num_time_steps), self.dtype, E.RngSpec(seed=seed, stream=1))
+            res = eng.lsm_apply_policy(S_new, res.betas, self.K, self.r, T, self.option_type, self.lsm_regressor,
+                                       self.semantics, arrays=self.verbose)
         self.last_result = res
         return float(res.price)
 

@@ -465,6 +465,14 @@ int optmc_lsm_global(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, i
   OPTMC_TRY_END
 }
 
+int optmc_lsm_apply_policy(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
+                           const optmc_lsm_params* lp, const double* betas, optmc_lsm_result* out) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return lsm_apply_policy(ctx, S_dev, ld, M, N, dtype, lp, betas, out);
+  OPTMC_TRY_END
+}
+
 int optmc_lsm_gnet(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
                    const optmc_lsm_params* lp, const optmc_gnet_params* gp, optmc_gnet_result* out) {
   OPTMC_TRY_BEGIN

@@ -550,6 +550,124 @@ template <typename R> static int lsm_global_t(optmc_ctx* ctx, const void* S, int
   return OPTMC_OK;
 }
 
+// ---- out-of-sample exercise: apply per-date regression coefficients fitted on ONE set of paths to
+// ANOTHER slab.  The policy "exercise at date t iff payoff(S) > sum_i beta[t][i] (S/K)^i" is tabulated as the decision
+// polynomial of global_walk_kernel, which then prices it in one streaming pass (no regression on these paths, hence
+// no in-sample look-ahead: the estimate is biased low, the usual companion of the in-sample LSM value).
+template <typename R>
+static int lsm_apply_policy_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, const optmc_lsm_params* lp,
+                              const double* betas, optmc_lsm_result* out) {
+  const bool f32 = sizeof(R) == 4;
+  const bool sticky = (lp->semantics & OPTMC_SEM_STICKY_MASK) != 0;
+  const int p = lp->basis == OPTMC_BASIS_POLY3 ? 4 : 3;
+  const double dt = lp->T / N, disc = exp(-lp->r * dt), inv_disc = 1.0 / disc;
+  const double final_scale = (lp->semantics & OPTMC_SEM_REF_DISCOUNT) ? 1.0 : disc;
+  int rc = ensure_per_date(ctx, N);
+  if (rc) return rc;
+  std::vector<DecEntry> tab(N + 1);
+  double d1 = 1.0;
+  {
+    double d = 1.0, di = 1.0;
+    for (int t = N; t >= 0; --t) {
+      DecEntry e{};
+      const double* b = betas + (size_t)t * p;
+      bool ok = t >= 1 && t <= N - 1;
+      for (int i = 0; i < p && ok; ++i) ok = b[i] == b[i];  // NaN row: the regression of that date was skipped
+      if (ok) {
+        double sc = 1.0;
+        for (int i = 0; i < 4; ++i) {
+          double c = i < p ? -b[i] * sc : 0.0;
+          if (i == 0) c += lp->is_put ? lp->K : -lp->K;
+          if (i == 1) c += lp->is_put ? -1.0 : 1.0;
+          e.d[i] = c;
+          sc /= lp->K;
+        }
+      } else {
+        e.d[0] = -1.0;
+      }
+      for (int i = 0; i < 4; ++i) { e.f[i] = (float)e.d[i]; e.b[i] = fabsf(e.f[i]) * 4.76837158203125e-7f; }
+      e.dinv = di;
+      tab[t] = e;
+      if (t == 1) d1 = d;
+      d *= disc; di *= inv_disc;
+    }
+  }
+  const double sg = lp->is_put ? -1.0 : 1.0;
+  double Kcmp = lp->K, Kh = lp->K, Kl = 0.0;
+  if (f32) {
+    float kf = (float)lp->K;
+    Kh = (double)kf;
+    Kl = (double)(float)(lp->K - Kh);
+    if (lp->is_put) { if ((double)kf < lp->K) kf = nextafterf(kf, INFINITY); }
+    else { if ((double)kf > lp->K) kf = nextafterf(kf, -INFINITY); }
+    Kcmp = (double)kf;
+  }
+  const bool vec4 = (M % 4 == 0) && (ld % 4 == 0) && ((uintptr_t)S % 16 == 0);
+  const long long units = vec4 ? M / 4 : M;
+  const unsigned wg = (unsigned)((units + kGThreads - 1) / kGThreads);
+  const size_t off_part = ((size_t)(N + 1) * sizeof(DecEntry) + 255) / 256 * 256;
+  rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off_part + (size_t)wg * 2 * sizeof(double));
+  if (rc) return rc;
+  char* dev = static_cast<char*>(ctx->batch_dev);
+  OPTMC_CUDA(cudaMemcpyAsync(dev, tab.data(), tab.size() * sizeof(DecEntry), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->sw = SweepDesc{};
+  ctx->sw.N = N; ctx->sw.lp = *lp;
+  rc = sweep_reset_stats(ctx);
+  if (rc) return rc;
+  WalkArgs a{};
+  a.S = S; a.ld = ld; a.M = M; a.N = N; a.sticky = sticky ? 1 : 0; a.is_put = lp->is_put;
+  a.sgn = sg; a.kk = sg * Kcmp; a.c1 = -sg * Kh; a.c2 = -sg * Kl;
+  a.table = reinterpret_cast<const DecEntry*>(dev);
+  const size_t tab_bytes = (size_t)(N + 1) * sizeof(DecEntry);
+  a.tab_in_smem = tab_bytes <= 40 * 1024 ? 1 : 0;
+  a.d1_scale = d1 * final_scale;
+  a.partials = reinterpret_cast<double*>(dev + off_part); a.ticket = ctx->tickets; a.final_out = ctx->d_final;
+  a.exc = ctx->d_exc; a.bnd = ctx->d_bnd;
+  const bool stats = out->ex_count != nullptr || out->boundary != nullptr;
+  const size_t smem = (a.tab_in_smem ? tab_bytes : 0) + (stats ? (size_t)2 * (N + 1) * sizeof(unsigned long long) : 0);
+  if (smem > 46 * 1024) { set_error("policy application: too many exercise dates for the per-date statistics"); return OPTMC_EUNSUPPORTED; }
+  if (vec4) {
+    if (stats) global_walk_kernel<R, 4, true><<<wg, kGThreads, smem, ctx->stream>>>(a);
+    else global_walk_kernel<R, 4, false><<<wg, kGThreads, smem, ctx->stream>>>(a);
+  } else {
+    if (stats) global_walk_kernel<R, 1, true><<<wg, kGThreads, smem, ctx->stream>>>(a);
+    else global_walk_kernel<R, 1, false><<<wg, kGThreads, smem, ctx->stream>>>(a);
+  }
+  ctx->launches += 2;
+  OPTMC_CUDA(cudaGetLastError());
+  double fin[4];
+  std::vector<unsigned long long> hexc, hbnd;
+  OPTMC_CUDA(cudaMemcpyAsync(fin, ctx->d_final, sizeof(fin), cudaMemcpyDeviceToHost, ctx->stream));
+  if (out->ex_count) { hexc.resize(N + 1); OPTMC_CUDA(cudaMemcpyAsync(hexc.data(), ctx->d_exc, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
+  if (out->boundary) { hbnd.resize(N + 1); OPTMC_CUDA(cudaMemcpyAsync(hbnd.data(), ctx->d_bnd, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
+  OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  out->price = fin[0]; out->stderr_ = fin[1]; out->n_paths = M; out->impl_used = OPTMC_SWEEP_SPLIT; out->n_launches = 2;
+  if (out->betas) memcpy(out->betas, betas, (size_t)(N + 1) * p * sizeof(double));
+  if (out->n_itm) for (int t = 0; t <= N; ++t) out->n_itm[t] = 0;
+  if (out->ex_count) for (int t = 0; t <= N; ++t) out->ex_count[t] = (int64_t)hexc[t];
+  if (out->boundary) {
+    const unsigned long long none = lp->is_put ? 0ull : ~0ull;
+    for (int t = 0; t <= N; ++t) {
+      if (hbnd[t] == none) out->boundary[t] = nan("");
+      else memcpy(&out->boundary[t], &hbnd[t], 8);
+    }
+  }
+  return OPTMC_OK;
+}
+
+int lsm_apply_policy(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
+                     const double* betas, optmc_lsm_result* out) {
+  if (!S || !lp || !betas || !out) { set_error("null argument"); return OPTMC_EINVAL; }
+  if (!(lp->K > 0) || !(lp->T > 0)) { set_error("S0, K, T must be positive."); return OPTMC_EINVAL; }
+  if (lp->r < 0) { set_error("r must be non-negative."); return OPTMC_EINVAL; }
+  if (M <= 0 || N <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
+  if (ld < M) { set_error("ld must be >= M"); return OPTMC_EINVAL; }
+  if (dtype != OPTMC_F32 && dtype != OPTMC_F64) { set_error("bad dtype"); return OPTMC_EINVAL; }
+  if (lp->basis != OPTMC_BASIS_POLY2 && lp->basis != OPTMC_BASIS_POLY3) { set_error("basis must be POLY2 or POLY3"); return OPTMC_EINVAL; }
+  if (dtype == OPTMC_F64) return lsm_apply_policy_t<double>(ctx, S, ld, M, N, lp, betas, out);
+  return lsm_apply_policy_t<float>(ctx, S, ld, M, N, lp, betas, out);
+}
+
 int lsm_global(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype,
                const optmc_lsm_params* lp, optmc_global_result* out) {
   if (!S || !lp || !out) { set_error("null argument"); return OPTMC_EINVAL; }

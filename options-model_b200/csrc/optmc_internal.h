@@ -138,6 +138,8 @@ int lsm_global(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, 
 
 // lsm_mlp.cu
 int lsm_mlp(optmc_ctx* ctx, const optmc_mlp_params* np, optmc_lsm_result* out);
+int lsm_apply_policy(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
+                     const double* betas, optmc_lsm_result* out);
 // lsm_gnet.cu
 int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
              const optmc_gnet_params* gp, optmc_gnet_result* out);

@@ -314,6 +314,23 @@ class Engine:
                                                 C.byref(lp), C.byref(res)))
         return self._to_result(res, keep)
 
+    def lsm_apply_policy(self, S, betas, K, r, T, option_type="put", basis="poly2", semantics="textbook", arrays=True,
+                         M: Optional[int] = None) -> SweepResult:
+        """Out-of-sample exercise: price the policy given by per-date ``betas`` (as returned by ``lsm``) on another slab."""
+        assert S.is_cuda and S.dim() == 2 and S.stride(1) == 1
+        N = S.shape[0] - 1
+        M = int(M if M is not None else S.shape[1])
+        lp = self._lsm_params(K, r, T, option_type, basis, semantics, "auto")
+        p = 3 if lp.basis == L.BASIS_POLY2 else 4
+        b = np.ascontiguousarray(betas, dtype=np.float64)
+        assert b.shape == (N + 1, p)
+        code = L.F64 if S.dtype == self.torch.float64 else L.F32
+        res, keep = self._result_block(N, p, arrays)
+        self._sync_stream()
+        L.check(self.lib.optmc_lsm_apply_policy(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp),
+                                                b.ctypes.data_as(C.POINTER(C.c_double)), C.byref(res)))
+        return self._to_result(res, keep)
+
     def lsm_global(self, S, K, r, T, option_type="put", semantics="reference", arrays=True, M: Optional[int] = None):
         """Global-regression LSM (the reference's v3 structure, om3:482-651, with a linear model on the seven
         reference features).  Returns a dict: price, stderr, n_rows, rank, beta[7], boundary, ex_count."""

@@ -531,6 +531,22 @@ class ContNetRegressor:
         return cont.astype(np.float64), None
 
 
+class FixedPolicyRegressor:
+    """Out-of-sample exercise: the continuation value comes from coefficients fitted on OTHER paths
+    (``betas[t]`` as returned by :func:`lsm_sweep`; a NaN row means "no exercise at that date").  Plugged into
+    :func:`lsm_sweep` it prices that fixed policy with the same loop semantics."""
+
+    def __init__(self, K, betas):
+        self.K, self.betas, self.p = float(K), np.asarray(betas, dtype=np.float64), np.asarray(betas).shape[1]
+
+    def __call__(self, t, t_current, S_itm, Y):
+        b = self.betas[t]
+        if np.isnan(b).any():
+            return None, None
+        x = np.asarray(S_itm, dtype=np.float64) / self.K
+        return sum(b[i] * x**i for i in range(self.p)), b
+
+
 @dataclass
 class SweepResult:
     price: float

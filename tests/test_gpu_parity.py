@@ -917,3 +917,37 @@ def test_localvol_philox_counters_and_throughput(eng, mods, golden_dir):
     Z = eng.philox_normals(L.MODEL_GBM, M, N, 0, "f64", rng)  # the GBM counter layout: 4 steps per Philox block
     ref = orc.localvol_paths_antithetic(100.0, 0.05, 1.0, M, N, net, 105.0, Z.cpu().numpy())
     np.testing.assert_allclose(S.cpu().numpy(), ref, rtol=5e-5)
+
+
+# ------------------------------------------------------------------------------------------------------
+# Out-of-sample exercise: coefficients fitted on one path set applied to another
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("semantics", ["textbook", "reference"])
+@pytest.mark.parametrize("basis,dtype", [("poly2", "f64"), ("poly3", "f64"), ("poly2", "f32")])
+def test_apply_policy_out_of_sample_vs_oracle(eng, mods, semantics, basis, dtype):
+    L, E, orc = mods
+    M, N, K = 20_000, 20, 100.0
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    S_fit = eng.paths(model, M, N, "f64", E.RngSpec(seed=101))
+    fit = eng.lsm(S_fit, K, 0.05, 1.0, "put", basis, semantics)
+    S_new = eng.paths(model, M, N, dtype, E.RngSpec(seed=202))
+    got = eng.lsm_apply_policy(S_new, fit.betas, K, 0.05, 1.0, "put", basis, semantics)
+    ref = orc.lsm_sweep(S_new.cpu().numpy().astype(np.float64), K, 0.05, 1.0, "put", orc.FixedPolicyRegressor(K, fit.betas),
+                        semantics=semantics)
+    assert got.price == pytest.approx(ref.price, rel=1e-12 if dtype == "f64" else 1e-6)
+    assert got.stderr == pytest.approx(ref.stderr, rel=1e-9 if dtype == "f64" else 1e-5)
+    np.testing.assert_array_equal(got.ex_count, ref.ex_count)
+    np.testing.assert_array_equal(np.isnan(got.boundary), np.isnan(ref.boundary))
+    np.testing.assert_allclose(got.boundary[~np.isnan(ref.boundary)], ref.boundary[~np.isnan(ref.boundary)], rtol=0)
+    if semantics == "textbook":  # a fixed policy on fresh paths is a lower bound in expectation: below the in-sample value
+        assert got.price < fit.price + 3 * fit.stderr
+
+
+def test_compat_out_of_sample_flag(mods):
+    from options_model_b200 import compat
+
+    kw = dict(K=100.0, r=0.05, sigma=0.2, option_type="put", semantics="textbook")
+    a = compat.AdvancedOptionPricer(rng_manager=compat.RNGManager(7), **kw).price_american_enhanced_lsm(100.0, 1.0, 200_000, 50)
+    b = compat.AdvancedOptionPricer(rng_manager=compat.RNGManager(7), out_of_sample=True, **kw).price_american_enhanced_lsm(100.0, 1.0, 200_000, 50)
+    # American put, GBM: binomial value 6.09; in-sample slightly above the out-of-sample (low-biased) estimate, both close
+    assert 5.95 < b < 6.2 and 5.95 < a < 6.25 and abs(a - b) < 0.12
