@@ -692,3 +692,88 @@ class HestonPricer:
             print(f"Warning: Batch pricing failed: {e}")
             prices[:] = np.nan
         return prices
+
+
+# ---------------------------------------------------------------------------------------------------
+# calibration objective (hc:404-472) -- the reference prices the surface row by row (one simulation per
+# row, ~170 s per evaluation); here the whole surface is ONE fused no-store launch
+# ---------------------------------------------------------------------------------------------------
+def bs_price(S: float, K: float, T: float, r: float, sigma: float, option_type: str = "call") -> float:
+    """hc:326-345."""
+    if T <= 0 or sigma <= 0:
+        return max(S - K, 0) if option_type == "call" else max(K - S, 0)
+    return float(BlackScholesGreeks.black_scholes_price(S, K, T, r, sigma, option_type.lower()))
+
+
+def bs_vega(S: float, K: float, T: float, r: float, sigma: float) -> float:
+    """hc:314-324."""
+    if T <= 0 or sigma <= 0:
+        return 1e-8
+    d1 = (math.log(S / K) + (r + 0.5 * sigma**2) * T) / (sigma * math.sqrt(T))
+    return max(float(S * math.exp(-0.5 * d1 * d1) / math.sqrt(2.0 * math.pi) * math.sqrt(T)), 1e-8)
+
+
+def objective_from_prices(x: np.ndarray, heston_prices: np.ndarray, S0: float, r: float, K: np.ndarray, T: np.ndarray,
+                          sigma_iv: np.ndarray, use_vega_weighting: bool = True, min_vega_weight: float = 0.01) -> float:
+    """hc:420-472 given the model prices of the rows: vega-weighted RMSE of ln(P_heston / P_bs(sigma_market)) plus the
+    Feller penalty; rows with a NaN / tiny price are skipped; 1e6 for invalid parameters or an empty sum."""
+    try:
+        params = HestonParams.from_array(np.asarray(x, dtype=np.float64))
+    except (ValueError, TypeError):
+        return 1e6
+    total_error = total_weight = 0.0
+    for hp_, k, t, iv in zip(heston_prices, K, T, sigma_iv):
+        if np.isnan(hp_) or hp_ <= 1e-8:
+            continue
+        bs = bs_price(S0, float(k), float(t), r, float(iv), "call")
+        if bs <= 1e-8:
+            continue
+        w = max(bs_vega(S0, float(k), float(t), r, float(iv)) / 100.0, min_vega_weight) if use_vega_weighting else 1.0
+        total_error += w * math.log(hp_ / bs) ** 2
+        total_weight += w
+    if total_weight == 0:
+        return 1e6
+    penalty = 0.0 if params.feller_condition() else 100.0 * abs(2 * params.kappa * params.theta - params.sigma**2)
+    return math.sqrt(total_error / total_weight) + penalty
+
+
+class HestonObjective:
+    """``HestonCalibrator._objective_function`` (hc:404-472) as a callable for any optimiser (scipy.optimize etc.):
+    ``f = HestonObjective(pricer, S0, r, K, T, sigma_iv); f(x)`` with x = (kappa, theta, sigma, rho, v0).
+    One ``optmc_price_european_batch`` launch prices every row with its own paths, as the reference simulates per row.
+    common_random_numbers=True keeps the Philox key fixed across evaluations: a smooth objective for
+    gradient-based optimisers instead of the reference's re-seeded noise."""
+
+    def __init__(self, pricer: "HestonPricer", S0: float, r: float, K, T, sigma_iv, common_random_numbers: bool = False):
+        self.pricer, self.S0, self.r = pricer, float(S0), float(r)
+        self.K = np.asarray(K, dtype=np.float64).ravel()
+        self.T = np.asarray(T, dtype=np.float64).ravel()
+        self.sigma_iv = np.asarray(sigma_iv, dtype=np.float64).ravel()
+        self.crn = common_random_numbers
+        self._seed = int(pricer.rng.integers(0, 2**63 - 1))
+        self.last_prices: Optional[np.ndarray] = None
+
+    def prices(self, params: "HestonParams") -> np.ndarray:
+        cfg = self.pricer.config
+        seed = self._seed if self.crn else int(self.pricer.rng.integers(0, 2**63 - 1))
+        M = cfg.n_mc_paths // 2 * 2 if cfg.use_antithetic else cfg.n_mc_paths
+        n = len(self.K)
+        mean, _ = _engine(self.pricer.device).price_european_batch(
+            self.pricer._model(params, self.S0, float(self.T[0]), self.r), M, cfg.n_time_steps, self.K, self.T,
+            np.zeros(n, dtype=np.int32), self.pricer.dtype, E.RngSpec(seed=seed, antithetic=bool(cfg.use_antithetic)),
+            stream_id=np.arange(n, dtype=np.int32))
+        return np.asarray(mean)
+
+    def __call__(self, x) -> float:
+        try:
+            params = HestonParams.from_array(np.asarray(x, dtype=np.float64))
+        except (ValueError, TypeError):
+            return 1e6
+        try:
+            self.last_prices = self.prices(params)
+        except Exception as e:  # noqa: BLE001 -- the reference skips rows whose pricing failed (hc:456-457)
+            print(f"Warning: Batch pricing failed: {e}")
+            return 1e6
+        cfg = self.pricer.config
+        return objective_from_prices(x, self.last_prices, self.S0, self.r, self.K, self.T, self.sigma_iv,
+                                     cfg.use_vega_weighting, cfg.min_vega_weight)

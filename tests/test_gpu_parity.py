@@ -951,3 +951,38 @@ def test_compat_out_of_sample_flag(mods):
     b = compat.AdvancedOptionPricer(rng_manager=compat.RNGManager(7), out_of_sample=True, **kw).price_american_enhanced_lsm(100.0, 1.0, 200_000, 50)
     # American put, GBM: binomial value 6.09; in-sample slightly above the out-of-sample (low-biased) estimate, both close
     assert 5.95 < b < 6.2 and 5.95 < a < 6.25 and abs(a - b) < 0.12
+
+
+def test_calibration_objective_is_one_launch_and_matches_row_by_row(mods):
+    """hc:404-472 on the reference's synthetic smile (hc:751-756): the batched objective equals the row-by-row
+    restatement on the same prices, common random numbers make it deterministic, invalid parameters give 1e6."""
+    from options_model_b200 import compat
+
+    S0, r = 100.0, 0.05
+    Kg, Tg = np.meshgrid(np.linspace(80, 120, 5), np.linspace(0.25, 1.0, 3))
+    K, T = Kg.ravel(), Tg.ravel()
+    iv = 0.2 + 0.1 * np.abs(np.log(K / S0)) + 0.02 * np.sqrt(T)
+    cfg = compat.CalibrationConfig(n_mc_paths=40_000, n_time_steps=50, verbose=False)
+    f = compat.HestonObjective(compat.HestonPricer(cfg), S0, r, K, T, iv, common_random_numbers=True)
+    x = np.array([2.0, 0.04, 0.5, -0.7, 0.04])
+    eng = compat._engine()
+    n0 = eng.launch_count()
+    v = f(x)
+    assert eng.launch_count() - n0 == 1  # the whole surface in one kernel launch
+    assert 0.0 < v < 1e5 and v == f(x)   # common random numbers: bit-identical re-evaluation
+    # row-by-row restatement of the reference loop on the same model prices
+    tot = wsum = 0.0
+    for p, k, t, s in zip(f.last_prices, K, T, iv):
+        bs = compat.bs_price(S0, k, t, r, s, "call")
+        w = max(compat.bs_vega(S0, k, t, r, s) / 100.0, cfg.min_vega_weight)
+        tot += w * np.log(p / bs) ** 2
+        wsum += w
+    feller = 100.0 * abs(2 * 2.0 * 0.04 - 0.5**2)  # violated for these parameters
+    assert v == pytest.approx(np.sqrt(tot / wsum) + feller, rel=1e-12)
+    # each price within 4 SE of the calibrator scheme priced option by option
+    single = compat.HestonPricer(cfg).price_european_option(compat.HestonParams.from_array(x), S0, K[7], T[7], r, "call")
+    assert abs(single - f.last_prices[7]) < 0.25
+    assert f(np.array([-1.0, 0.04, 0.5, -0.7, 0.04])) == 1e6
+    # a fresh-noise objective (the reference's behaviour) differs from call to call
+    g = compat.HestonObjective(compat.HestonPricer(cfg), S0, r, K, T, iv)
+    assert g(x) != g(x)
