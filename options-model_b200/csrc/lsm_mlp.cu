@@ -84,7 +84,7 @@ mlp_count_kernel(const R* __restrict__ S_t, const R* __restrict__ cf, long long 
 // ---- 2. scan + standardisation + fresh network ------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 mlp_scan_kernel(unsigned int* block_count, int nblocks, unsigned long long* mom_fx, MlpState* st, float* params,
-                float* adam_m, float* adam_v, unsigned long long* grad_fx, unsigned long long seed, int date, int H) {
+                float* adam_m, float* adam_v, unsigned long long* grad_fx, unsigned long long seed, int date, int H) {  // (the tcgen05 path packs W2 afterwards: mlp_tc_pack_kernel)
   const int P = 3 * H + H * H + H + 1;
   __shared__ unsigned long long s_part[1024];
   __shared__ unsigned long long s_base;
@@ -417,108 +417,146 @@ __global__ void mlp_nitm_kernel(const MlpState* st, long long* nitm_t, double* l
 constexpr int kTH = 128;
 constexpr int kTP = 3 * kTH + kTH * kTH + kTH + 1;  // 16897
 constexpr int tW1 = 0, tB1 = kTH, tW2 = 2 * kTH, tB2 = 2 * kTH + kTH * kTH, tW3 = tB2 + kTH, tB3 = tW3 + kTH;
-constexpr int kTcThreads = 128;
-constexpr int kTileBytes = kTH * kTH * 2;  // 32 KB
-constexpr int kAuxBytes = 128 * 16 * 2;    // 4 KB panel [row][16]
+constexpr int kTcThreads = 256;            // thread = (row = tid & 127, column half = tid >> 7)
+constexpr int kTileBytes = kTcTileBytes;   // 32 KB
+constexpr int kAuxBytes = kTcPanelBytes;   // 4 KB panel [row][16]
 
 struct TcSmem {
   unsigned char T1[kTileBytes], T2[kTileBytes], T3[kTileBytes], T4[kTileBytes], W2[kTileBytes];
   unsigned char aux[2][kAuxBytes];
   float w1[kTH], b1[kTH], b2[kTH], w3[kTH];
+  float dot[2][128];              // partial output-layer dot products of the two column halves
+  unsigned int mask[2][4][128];   // per layer: 128 "unit is active" bits of each row (word-major: conflict-free)
   float b3;
   float red[8];
-  unsigned long long bar;
+  unsigned long long bar, wbar;
   unsigned int tmem;
 };
 
-// setup shared by the training and the inference kernel: weights -> bf16 core layout, TMEM allocation, mbarrier
-__device__ __forceinline__ unsigned int tc_setup(TcSmem& sm, const float* __restrict__ params, int tmem_cols_log) {
-  const int tid = threadIdx.x;
-  {  // thread j stages row j of W2
-#pragma unroll 4
-    for (int c = 0; c < 16; ++c) {
-      float v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = params[tW2 + tid * kTH + c * 8 + k];
-      *reinterpret_cast<uint4*>(sm.W2 + core_off(tid, c * 8)) = pack8_bf16(v);
-    }
-    sm.w1[tid] = params[tW1 + tid]; sm.b1[tid] = params[tB1 + tid]; sm.b2[tid] = params[tB2 + tid]; sm.w3[tid] = params[tW3 + tid];
-    if (tid == 0) sm.b3 = params[tB3];
-    // panels: [1, x, dout, 0 ...]; the constant and zero columns are written once
-    for (int b = 0; b < 2; ++b) {
-      *reinterpret_cast<uint4*>(sm.aux[b] + aux_off(tid, 0)) = make_uint4(0x00003f80u, 0u, 0u, 0u);  // bf16 1.0 in column 0
-      *reinterpret_cast<uint4*>(sm.aux[b] + aux_off(tid, 8)) = make_uint4(0u, 0u, 0u, 0u);
-    }
-  }
-  if ((tid >> 5) == 0) {
-    if (tmem_cols_log == 9)
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem)), "n"(512));
-    else
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem)), "n"(128));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
+// bf16 core-layout image of W2, kept in step with the fp32 parameters (scan / Adam kernels): a CTA stages it with one
+// bulk async copy instead of re-packing 16384 floats (the per-date fits run one tile per CTA: set-up time matters).
+__device__ __forceinline__ int tc_pack_index(int i) { const int k = i - tW2; return core_off(k >> 7, k & 127) >> 1; }
+
+// setup shared by the training and the inference kernel: W2 image by bulk copy, vectors, panels, TMEM, mbarriers
+__device__ __forceinline__ unsigned int tc_setup(TcSmem& sm, const float* __restrict__ params,
+                                                 const __nv_bfloat16* __restrict__ wpack, bool big) {
+  const int tid = threadIdx.x, row = tid & 127;
   if (tid == 0) {
     mbar_init(reinterpret_cast<uint64_t*>(&sm.bar), 1);
+    mbar_init(reinterpret_cast<uint64_t*>(&sm.wbar), 1);
     mbar_fence_init();
+    mbar_arrive_expect_tx(reinterpret_cast<uint64_t*>(&sm.wbar), kTileBytes);
+    bulk_load_1d(sm.W2, wpack, kTileBytes, reinterpret_cast<uint64_t*>(&sm.wbar));
+  }
+  if (tid < 128) { sm.w1[row] = params[tW1 + row]; sm.b1[row] = params[tB1 + row]; }
+  else { sm.b2[row] = params[tB2 + row]; sm.w3[row] = params[tW3 + row]; }
+  if (tid == 0) sm.b3 = params[tB3];
+  {  // panels: [1, x, dout, 0 ...]; the constant and zero columns are written once (thread halves take one panel each)
+    unsigned char* ax = sm.aux[tid >> 7];
+    *reinterpret_cast<uint4*>(ax + aux_off(row, 0)) = make_uint4(0x00003f80u, 0u, 0u, 0u);  // bf16 1.0 in column 0
+    *reinterpret_cast<uint4*>(ax + aux_off(row, 8)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  if ((tid >> 5) == 0) {
+    if (big) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem)), "n"(512));
+    else asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem)), "n"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_publish();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   return sm.tmem;
 }
 
-// S1: h1 = relu(w1 x + b1) -> bf16 H1 tile; returns the h1 > 0 mask
-__device__ __forceinline__ void tc_layer1(TcSmem& sm, float x, int row, unsigned int (&mask1)[4]) {
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
+// The stage loops below are NOT unrolled: with one tile per CTA (the per-date fits of the sticky sweep) straight-line
+// code would be fetched cold from the instruction cache end to end.
+
+// S1: h1 = relu(w1 x + b1) -> bf16 H1 tile (this thread's 64 columns); mask bit = h1 > 0
+__device__ __forceinline__ void tc_layer1(TcSmem& sm, float x, int row, int half) {
+  unsigned int word = 0u;
+#pragma unroll 1
+  for (int c = half * 8; c < half * 8 + 8; ++c) {
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float h = fmaf(sm.w1[c * 8 + k], x, sm.b1[c * 8 + k]);
       v[k] = fmaxf(h, 0.f);
-      if (h > 0.f) mask1[c >> 2] |= 1u << ((c & 3) * 8 + k);
+      word |= (h > 0.f ? 1u : 0u) << ((c & 3) * 8 + k);
     }
     *reinterpret_cast<uint4*>(sm.T1 + core_off(row, c * 8)) = pack8_bf16(v);
+    if ((c & 3) == 3) { sm.mask[0][c >> 2][row] = word; word = 0u; }
   }
+}
+
+// S2a: h2 = relu(z2 + b2) for this thread's 64 columns; returns the partial dot with w3; STORE: H2 tile + mask
+template <bool STORE>
+__device__ __forceinline__ float tc_layer2(TcSmem& sm, unsigned int taddr, int row, int half) {
+  float out = 0.f;
+#pragma unroll 1
+  for (int c0 = half * 2; c0 < half * 2 + 2; ++c0) {
+    float z[32];
+    tmem_ld32(taddr + c0 * 32, z);
+    unsigned int word = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int j = c0 * 32 + q * 8 + k;
+        const float h = z[q * 8 + k] + sm.b2[j];
+        v[k] = fmaxf(h, 0.f);
+        word |= (h > 0.f ? 1u : 0u) << (q * 8 + k);
+        out = fmaf(sm.w3[j], v[k], out);
+      }
+      if (STORE) *reinterpret_cast<uint4*>(sm.T3 + core_off(row, c0 * 32 + q * 8)) = pack8_bf16(v);
+    }
+    if (STORE) sm.mask[1][c0][row] = word;
+  }
+  return out;
+}
+
+__device__ __forceinline__ float tc_join_dot(TcSmem& sm, float part, int row, int half) {
+  sm.dot[half][row] = part;
+  __syncthreads();
+  return (sm.dot[0][row] + sm.dot[1][row]) + sm.b3;
 }
 
 __device__ __forceinline__ void tc_issue_layer2(TcSmem& sm, unsigned int tmem) {  // Z2 = H1 W2^T
   const unsigned int a0 = smem_u32(sm.T1), b0 = smem_u32(sm.W2);
   const unsigned int id = umma_idesc(128, 128, 0, 0);
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < 8; ++k) umma_f16(tmem, umma_desc(a0 + k * 256, 128, 2048), umma_desc(b0 + k * 256, 128, 2048), id, k > 0);
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-mlp_tc_grad_kernel(const float* __restrict__ params, const float* __restrict__ xs, const float* __restrict__ ys,
-                   const MlpState* __restrict__ st, float* __restrict__ gpart) {
+mlp_tc_grad_kernel(const float* __restrict__ params, const __nv_bfloat16* __restrict__ wpack, const float* __restrict__ xs,
+                   const float* __restrict__ ys, const MlpState* __restrict__ st, float* __restrict__ gpart) {
   extern __shared__ __align__(1024) unsigned char smem_tc[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_tc);
   const long long n = st->n_live;
   const long long ntiles = (n + 127) / 128;
   if ((long long)blockIdx.x >= ntiles) return;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const unsigned int tmem = tc_setup(sm, params, 9);
-  const unsigned int lane_base = (unsigned int)(warp * 32) << 16;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const unsigned int tmem = tc_setup(sm, params, wpack, true);
+  const unsigned int lane_base = (unsigned int)((warp & 3) * 32) << 16;
   const unsigned int cZ = 0, cW = 128, cV1 = 256, cV2 = 272, cV3 = 288;
   const float inv_n2 = (float)(2.0 / (double)n);
   unsigned int phase = 0;
   float loss = 0.f, gb3 = 0.f;
   int local = 0;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++local) {
-    const long long r = tile * 128 + tid;
+    const long long r = tile * 128 + row;
     const bool act = r < n;
     const float x = act ? xs[r] : 0.f, y = act ? ys[r] : 0.f;
     unsigned char* aux = sm.aux[local & 1];
-    unsigned int mask1[4] = {0u, 0u, 0u, 0u}, mask2[4] = {0u, 0u, 0u, 0u};
-    tc_layer1(sm, x, tid, mask1);
-    *reinterpret_cast<unsigned short*>(aux + aux_off(tid, 1)) = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+    tc_layer1(sm, x, row, half);
+    if (half == 0) *reinterpret_cast<unsigned short*>(aux + aux_off(row, 1)) = __bfloat16_as_ushort(__float2bfloat16_rn(x));
     tc_publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (local == 0) mbar_wait(reinterpret_cast<uint64_t*>(&sm.wbar), 0u);  // the W2 image has landed
       if (local > 0) {  // vector gradients of the previous tile's first layer: [db1 dw1 .] += dH1'^T P(prev)
         const unsigned int a0 = smem_u32(sm.T4), p0 = smem_u32(sm.aux[(local - 1) & 1]);
         const unsigned int idv = umma_idesc(128, 16, 1, 1);
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 8; ++k)
           umma_f16(tmem + cV1, umma_desc(a0 + k * 4096, 2048, 128), umma_desc(p0 + k * 512, 256, 128), idv, (local > 1) || k > 0);
       }
@@ -527,70 +565,53 @@ mlp_tc_grad_kernel(const float* __restrict__ params, const float* __restrict__ x
     }
     tc_bar_wait(&sm.bar, phase); phase ^= 1u;
     // S2a: output and H2 tile
-    float out = sm.b3;
-#pragma unroll
-    for (int c0 = 0; c0 < 4; ++c0) {
-      float z[32];
-      tmem_ld32(tmem + lane_base + cZ + c0 * 32, z);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int j = c0 * 32 + q * 8 + k;
-          const float h = z[q * 8 + k] + sm.b2[j];
-          v[k] = fmaxf(h, 0.f);
-          if (h > 0.f) mask2[c0] |= 1u << (q * 8 + k);
-          out = fmaf(sm.w3[j], v[k], out);
-        }
-        *reinterpret_cast<uint4*>(sm.T3 + core_off(tid, c0 * 32 + q * 8)) = pack8_bf16(v);
-      }
-    }
+    const float out = tc_join_dot(sm, tc_layer2<true>(sm, tmem + lane_base + cZ, row, half), row, half);
     const float err = act ? out - y : 0.f;
     const float dout = err * inv_n2;
-    loss = fmaf(err, err, loss);
-    gb3 += dout;
-    // S2b: dZ2 tile and the dout column of the panel
-#pragma unroll
-    for (int c = 0; c < 16; ++c) {
+    if (half == 0) { loss = fmaf(err, err, loss); gb3 += dout; }
+    // S2b: dZ2 tile (this thread's 64 columns) and the dout column of the panel
+#pragma unroll 1
+    for (int c = half * 8; c < half * 8 + 8; ++c) {
+      const unsigned int word = sm.mask[1][c >> 2][row] >> ((c & 3) * 8);
       float v[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = ((mask2[c >> 2] >> ((c & 3) * 8 + k)) & 1u) ? dout * sm.w3[c * 8 + k] : 0.f;
-      *reinterpret_cast<uint4*>(sm.T2 + core_off(tid, c * 8)) = pack8_bf16(v);
+      for (int k = 0; k < 8; ++k) v[k] = ((word >> k) & 1u) ? dout * sm.w3[c * 8 + k] : 0.f;
+      *reinterpret_cast<uint4*>(sm.T2 + core_off(row, c * 8)) = pack8_bf16(v);
     }
-    *reinterpret_cast<unsigned short*>(aux + aux_off(tid, 2)) = __bfloat16_as_ushort(__float2bfloat16_rn(dout));
+    if (half == 0) *reinterpret_cast<unsigned short*>(aux + aux_off(row, 2)) = __bfloat16_as_ushort(__float2bfloat16_rn(dout));
     tc_publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const unsigned int t1 = smem_u32(sm.T1), t2 = smem_u32(sm.T2), t3 = smem_u32(sm.T3), w2 = smem_u32(sm.W2), p0 = smem_u32(aux);
       const unsigned int id_kmn = umma_idesc(128, 128, 0, 1), id_mm = umma_idesc(128, 128, 1, 1), idv = umma_idesc(128, 16, 1, 1);
       const unsigned int accT = local > 0;
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < 8; ++k)  // dH1 = dZ2 W2
         umma_f16(tmem + cZ, umma_desc(t2 + k * 256, 128, 2048), umma_desc(w2 + k * 4096, 2048, 128), id_kmn, k > 0);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)  // dW2 += dZ2^T H1
-        umma_f16(tmem + cW, umma_desc(t2 + k * 4096, 2048, 128), umma_desc(t1 + k * 4096, 2048, 128), id_mm, accT || k > 0);
-#pragma unroll
+#pragma unroll 1
+      for (int k = 0; k < 8; ++k)  // dW2^T += H1^T dZ2  (lane = input unit: the read-out is coalesced)
+        umma_f16(tmem + cW, umma_desc(t1 + k * 4096, 2048, 128), umma_desc(t2 + k * 4096, 2048, 128), id_mm, accT || k > 0);
+#pragma unroll 1
       for (int k = 0; k < 8; ++k)  // [db2 . .] += dZ2^T P
         umma_f16(tmem + cV2, umma_desc(t2 + k * 4096, 2048, 128), umma_desc(p0 + k * 512, 256, 128), idv, accT || k > 0);
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < 8; ++k)  // [. . dw3] += H2^T P
         umma_f16(tmem + cV3, umma_desc(t3 + k * 4096, 2048, 128), umma_desc(p0 + k * 512, 256, 128), idv, accT || k > 0);
       umma_commit(&sm.bar);
     }
     tc_bar_wait(&sm.bar, phase); phase ^= 1u;
     // S3: dH1' = dH1 (h1 > 0) tile
-#pragma unroll
-    for (int c0 = 0; c0 < 4; ++c0) {
+#pragma unroll 1
+    for (int c0 = half * 2; c0 < half * 2 + 2; ++c0) {
       float d[32];
       tmem_ld32(tmem + lane_base + cZ + c0 * 32, d);
+      const unsigned int word = sm.mask[0][c0][row];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = ((mask1[c0] >> (q * 8 + k)) & 1u) ? d[q * 8 + k] : 0.f;
-        *reinterpret_cast<uint4*>(sm.T4 + core_off(tid, c0 * 32 + q * 8)) = pack8_bf16(v);
+        for (int k = 0; k < 8; ++k) v[k] = ((word >> (q * 8 + k)) & 1u) ? d[q * 8 + k] : 0.f;
+        *reinterpret_cast<uint4*>(sm.T4 + core_off(row, c0 * 32 + q * 8)) = pack8_bf16(v);
       }
     }
   }
@@ -600,32 +621,36 @@ mlp_tc_grad_kernel(const float* __restrict__ params, const float* __restrict__ x
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned int a0 = smem_u32(sm.T4), p0 = smem_u32(sm.aux[(local - 1) & 1]);
     const unsigned int idv = umma_idesc(128, 16, 1, 1);
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 8; ++k)
       umma_f16(tmem + cV1, umma_desc(a0 + k * 4096, 2048, 128), umma_desc(p0 + k * 512, 256, 128), idv, (local > 1) || k > 0);
     umma_commit(&sm.bar);
   }
   tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-  // read-out: thread j owns TMEM lane j = unit j
+  // read-out: dW2 sits transposed in TMEM (lane = input unit i, column = output unit j): for a fixed j the threads of a
+  // warp write consecutive addresses of row j of W2's gradient.  The vector gradients have lane = unit.
   float* gp = gpart + (size_t)blockIdx.x * (kTP + 1);
-#pragma unroll
-  for (int c0 = 0; c0 < 4; ++c0) {
+#pragma unroll 1
+  for (int c0 = half * 2; c0 < half * 2 + 2; ++c0) {
     float w[32];
     tmem_ld32(tmem + lane_base + cW + c0 * 32, w);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) gp[tW2 + tid * kTH + c0 * 32 + i] = w[i];
+    for (int i = 0; i < 32; ++i) gp[tW2 + (c0 * 32 + i) * kTH + row] = w[i];
   }
-  {
-    float v1[16], v2[16], v3[16];
+  if (half == 0) {
+    float v1[16];
     tmem_ld16(tmem + lane_base + cV1, v1);
+    gp[tB1 + row] = v1[0]; gp[tW1 + row] = v1[1];
+  } else {
+    float v2[16], v3[16];
     tmem_ld16(tmem + lane_base + cV2, v2);
     tmem_ld16(tmem + lane_base + cV3, v3);
-    gp[tB1 + tid] = v1[0]; gp[tW1 + tid] = v1[1]; gp[tB2 + tid] = v2[0]; gp[tW3 + tid] = v3[2];
+    gp[tB2 + row] = v2[0]; gp[tW3 + row] = v3[2];
   }
-  {  // scalars: db3 and the loss
+  {  // scalars: db3 and the loss (column half 0 carries them)
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) { gb3 += __shfl_xor_sync(0xffffffffu, gb3, m); loss += __shfl_xor_sync(0xffffffffu, loss, m); }
-    if ((tid & 31) == 0) { sm.red[warp] = gb3; sm.red[4 + warp] = loss; }
+    if (half == 0 && (tid & 31) == 0) { sm.red[warp] = gb3; sm.red[4 + warp] = loss; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -636,15 +661,25 @@ mlp_tc_grad_kernel(const float* __restrict__ params, const float* __restrict__ x
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
-// Adam for the tensor-core path: deterministic fixed-order sum of the per-CTA partial gradients
+// Adam for the tensor-core path: deterministic fixed-order sum of the per-CTA partial gradients; keeps the bf16 image
+// of W2 in step; the extra last block reduces the loss (st->loss).  `step` = 1-based optimiser step of this date.
 __global__ void __launch_bounds__(256)
-mlp_tc_adam_kernel(float* params, float* adam_m, float* adam_v, const float* __restrict__ gpart, MlpState* st, float lr,
-                   int grid_rows) {
+mlp_tc_adam_kernel(float* params, __nv_bfloat16* wpack, float* adam_m, float* adam_v, const float* __restrict__ gpart,
+                   MlpState* st, float lr, int grid_rows, int step) {
   const long long n = st->n_live;
   if (n <= 0) return;
   const long long ntiles = (n + 127) / 128;
   const int nb = (int)(ntiles < grid_rows ? ntiles : grid_rows);
-  const int step = st->step + 1;
+  if (blockIdx.x == gridDim.x - 1) {  // loss block
+    if (threadIdx.x < 32) {
+      double l = 0.0;
+      for (int b = threadIdx.x; b < nb; b += 32) l += (double)gpart[(size_t)b * (kTP + 1) + kTP];
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) l += __shfl_xor_sync(0xffffffffu, l, m);
+      if (threadIdx.x == 0) { st->loss = l / (double)n; st->step = step; }
+    }
+    return;
+  }
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
   const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -654,43 +689,40 @@ mlp_tc_adam_kernel(float* params, float* adam_m, float* adam_v, const float* __r
     const float m = b1 * adam_m[i] + (1.0f - b1) * g;
     const float v = b2 * adam_v[i] + (1.0f - b2) * g * g;
     adam_m[i] = m; adam_v[i] = v;
-    params[i] -= (lr / bc1) * (m / (sqrtf(v) / sqrtf(bc2) + eps));
+    const float p = params[i] - (lr / bc1) * (m / (sqrtf(v) / sqrtf(bc2) + eps));
+    params[i] = p;
+    if (i >= tW2 && i < tB2) wpack[tc_pack_index(i)] = __float2bfloat16_rn(p);
   }
 }
-__global__ void mlp_tc_step_kernel(MlpState* st, const float* __restrict__ gpart, int grid_rows) {
-  const long long n = st->n_live;
-  if (n <= 0) return;
-  const long long ntiles = (n + 127) / 128;
-  const int nb = (int)(ntiles < grid_rows ? ntiles : grid_rows);
-  double l = 0.0;
-  for (int b = 0; b < nb; ++b) l += (double)gpart[(size_t)b * (kTP + 1) + kTP];
-  st->loss = l / (double)n;
-  st->step += 1;
+__global__ void mlp_tc_pack_kernel(const float* __restrict__ params, __nv_bfloat16* __restrict__ wpack) {
+  const int i = tW2 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < tB2) wpack[tc_pack_index(i)] = __float2bfloat16_rn(params[i]);
 }
 
 // continuation = net(x) on tensor cores, then the exercise decision (strict '>', om2:304)
 template <typename R>
 __global__ void __launch_bounds__(kTcThreads, 1)
-mlp_tc_decide_kernel(const float* __restrict__ params, const float* __restrict__ xs, const unsigned int* __restrict__ idx,
-                     const MlpState* __restrict__ st, const R* __restrict__ S_t, R* cf, double K, double Kh, double Kl,
-                     int is_put, int sticky, R dinv, float* cont_out, unsigned long long* exc_t, unsigned long long* bnd_t) {
+mlp_tc_decide_kernel(const float* __restrict__ params, const __nv_bfloat16* __restrict__ wpack, const float* __restrict__ xs,
+                     const unsigned int* __restrict__ idx, const MlpState* __restrict__ st, const R* __restrict__ S_t, R* cf,
+                     double K, double Kh, double Kl, int is_put, int sticky, R dinv, float* cont_out,
+                     unsigned long long* exc_t, unsigned long long* bnd_t) {
   extern __shared__ __align__(1024) unsigned char smem_tc[];
   TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_tc);
   const long long n = st->n_live;
   const long long ntiles = (n + 127) / 128;
   if ((long long)blockIdx.x >= ntiles) return;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const unsigned int tmem = tc_setup(sm, params, 7);
-  const unsigned int lane_base = (unsigned int)(warp * 32) << 16;
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const unsigned int tmem = tc_setup(sm, params, wpack, false);
+  if (tid == 0) mbar_wait(reinterpret_cast<uint64_t*>(&sm.wbar), 0u);
+  const unsigned int lane_base = (unsigned int)((warp & 3) * 32) << 16;
   const R sgn = is_put ? (R)-1 : (R)1;
   const R c1 = (R)(is_put ? Kh : -Kh), c2 = (R)(is_put ? Kl : -Kl);
   unsigned int phase = 0, cnt = 0;
   unsigned long long bnd = bnd_none(is_put);
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long r = tile * 128 + tid;
+    const long long r = tile * 128 + row;
     const bool act = r < n;
-    unsigned int mask1[4] = {0u, 0u, 0u, 0u};
-    tc_layer1(sm, act ? xs[r] : 0.f, tid, mask1);
+    tc_layer1(sm, act ? xs[r] : 0.f, row, half);
     tc_publish();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -698,15 +730,8 @@ mlp_tc_decide_kernel(const float* __restrict__ params, const float* __restrict__
       umma_commit(&sm.bar);
     }
     tc_bar_wait(&sm.bar, phase); phase ^= 1u;
-    float out = sm.b3;
-#pragma unroll
-    for (int c0 = 0; c0 < 4; ++c0) {
-      float z[32];
-      tmem_ld32(tmem + lane_base + c0 * 32, z);
-#pragma unroll
-      for (int k = 0; k < 32; ++k) out = fmaf(sm.w3[c0 * 32 + k], fmaxf(z[k] + sm.b2[c0 * 32 + k], 0.f), out);
-    }
-    if (act) {
+    const float out = tc_join_dot(sm, tc_layer2<false>(sm, tmem + lane_base, row, half), row, half);
+    if (act && half == 0) {
       if (cont_out) cont_out[r] = out;
       if (idx) {
         const unsigned int j = idx[r];
@@ -722,12 +747,15 @@ mlp_tc_decide_kernel(const float* __restrict__ params, const float* __restrict__
         }
       }
     }
+    __syncthreads();  // sm.dot is rewritten by the next tile
   }
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  bnd = is_put ? warp_max_u64(bnd) : warp_min_u64(bnd);
-  if ((tid & 31) == 0 && cnt && exc_t) {
-    atomicAdd(exc_t, (unsigned long long)cnt);
-    if (is_put) atomicMax(bnd_t, bnd); else atomicMin(bnd_t, bnd);
+  if (half == 0) {
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    bnd = is_put ? warp_max_u64(bnd) : warp_min_u64(bnd);
+    if ((tid & 31) == 0 && cnt && exc_t) {
+      atomicAdd(exc_t, (unsigned long long)cnt);
+      if (is_put) atomicMax(bnd_t, bnd); else atomicMin(bnd_t, bnd);
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -815,7 +843,7 @@ template <typename R> static int lsm_mlp_tc_t(optmc_ctx* ctx, const optmc_mlp_pa
   const size_t o_cnt = take((size_t)nblocks * 4), o_xs = take((size_t)M * 4), o_ys = take((size_t)M * 4),
                o_idx = take((size_t)M * 4), o_par = take(kTP * 4), o_m = take(kTP * 4), o_v = take(kTP * 4),
                o_g = take((size_t)grid_rows * (kTP + 1) * 4), o_mom = take(5 * 8), o_st = take(sizeof(MlpState)),
-               o_loss = take((size_t)(N + 1) * 8);
+               o_loss = take((size_t)(N + 1) * 8), o_pack = take(kTileBytes);
   int rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
   if (rc) return rc;
   char* dev = static_cast<char*>(ctx->batch_dev);
@@ -830,6 +858,7 @@ template <typename R> static int lsm_mlp_tc_t(optmc_ctx* ctx, const optmc_mlp_pa
   unsigned long long* d_mom = reinterpret_cast<unsigned long long*>(dev + o_mom);
   MlpState* d_st = reinterpret_cast<MlpState*>(dev + o_st);
   double* d_loss = reinterpret_cast<double*>(dev + o_loss);
+  __nv_bfloat16* d_pack = reinterpret_cast<__nv_bfloat16*>(dev + o_pack);
   OPTMC_CUDA(cudaMemsetAsync(d_mom, 0, 5 * 8, ctx->stream));
   OPTMC_CUDA(cudaMemsetAsync(d_loss, 0, (size_t)(N + 1) * 8, ctx->stream));
   rc = sweep_begin(ctx);
@@ -846,16 +875,16 @@ template <typename R> static int lsm_mlp_tc_t(optmc_ctx* ctx, const optmc_mlp_pa
     mlp_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, nblocks, d_mom, d_st, d_par, d_m, d_v, nullptr, np_->seed, t, kTH);
     mlp_compact_kernel<R><<<nblocks, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, sw.Dt[t], d_cnt,
                                                                   d_st, d_xs, d_ys, d_idx);
+    mlp_tc_pack_kernel<<<kTH * kTH / 256, 256, 0, ctx->stream>>>(d_par, d_pack);
     for (int e = 0; e < np_->epochs; ++e) {
-      mlp_tc_grad_kernel<<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_xs, d_ys, d_st, d_g);
-      mlp_tc_adam_kernel<<<adam_grid, 256, 0, ctx->stream>>>(d_par, d_m, d_v, d_g, d_st, (float)np_->lr, grid_rows);
-      mlp_tc_step_kernel<<<1, 1, 0, ctx->stream>>>(d_st, d_g, grid_rows);
+      mlp_tc_grad_kernel<<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_pack, d_xs, d_ys, d_st, d_g);
+      mlp_tc_adam_kernel<<<adam_grid + 1, 256, 0, ctx->stream>>>(d_par, d_pack, d_m, d_v, d_g, d_st, (float)np_->lr, grid_rows, e + 1);
     }
-    mlp_tc_decide_kernel<R><<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_xs, d_idx, d_st, S_t, cf, sw.lp.K, sw.Kh,
+    mlp_tc_decide_kernel<R><<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_pack, d_xs, d_idx, d_st, S_t, cf, sw.lp.K, sw.Kh,
                                                                          sw.Kl, sw.lp.is_put, sticky, (R)sw.Dinv[t], nullptr,
                                                                          ctx->d_exc + t, ctx->d_bnd + t);
     mlp_nitm_kernel<<<1, 1, 0, ctx->stream>>>(d_st, ctx->d_nitm + t, d_loss + t);
-    ctx->launches += 5 + 3 * np_->epochs; sw.n_launches += 5 + 3 * np_->epochs;
+    ctx->launches += 6 + 2 * np_->epochs; sw.n_launches += 6 + 2 * np_->epochs;
   }
   OPTMC_CUDA(cudaGetLastError());
   rc = sweep_finish(ctx, ctx->gram);
@@ -893,7 +922,7 @@ int mlp_grad_debug(optmc_ctx* ctx, int H, long long n, const float* xs, const fl
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   const size_t o_xs = take((size_t)n * 4), o_ys = take((size_t)n * 4), o_cont = take((size_t)n * 4), o_par = take((size_t)P * 4),
                o_out = take((size_t)P * 4), o_g = take(H == kTH ? (size_t)grid_rows * (P + 1) * 4 : (size_t)(2 * P + 3) * 8),
-               o_st = take(sizeof(MlpState));
+               o_st = take(sizeof(MlpState)), o_pack = take(kTileBytes);
   int rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
   if (rc) return rc;
   char* dev = static_cast<char*>(ctx->batch_dev);
@@ -912,11 +941,13 @@ int mlp_grad_debug(optmc_ctx* ctx, int H, long long n, const float* xs, const fl
     const size_t smem = sizeof(TcSmem) + 1024;
     OPTMC_CUDA(cudaFuncSetAttribute(mlp_tc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     OPTMC_CUDA(cudaFuncSetAttribute(mlp_tc_decide_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mlp_tc_grad_kernel<<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_xs, d_ys, d_st, d_g);
+    __nv_bfloat16* d_pack = reinterpret_cast<__nv_bfloat16*>(dev + o_pack);
+    mlp_tc_pack_kernel<<<kTH * kTH / 256, 256, 0, ctx->stream>>>(d_par, d_pack);
+    mlp_tc_grad_kernel<<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_pack, d_xs, d_ys, d_st, d_g);
     mlp_sum_partials_kernel<<<(P + 255) / 256, 256, 0, ctx->stream>>>(d_g, grid_rows, d_out, P);
-    mlp_tc_decide_kernel<float><<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_xs, nullptr, d_st, nullptr, nullptr, 1.0, 1.0,
-                                                                             0.0, 1, 0, 1.0f, d_cont, nullptr, nullptr);
-    ctx->launches += 4;
+    mlp_tc_decide_kernel<float><<<grid_rows, kTcThreads, smem, ctx->stream>>>(d_par, d_pack, d_xs, nullptr, d_st, nullptr, nullptr, 1.0,
+                                                                             1.0, 0.0, 1, 0, 1.0f, d_cont, nullptr, nullptr);
+    ctx->launches += 5;
   } else {
     unsigned long long* d_g = reinterpret_cast<unsigned long long*>(dev + o_g);
     OPTMC_CUDA(cudaMemsetAsync(d_g, 0, (size_t)(2 * P + 3) * 8, ctx->stream));
