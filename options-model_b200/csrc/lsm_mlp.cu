@@ -55,30 +55,33 @@ template <typename R>
 __global__ void __launch_bounds__(kMThreads)
 mlp_count_kernel(const R* __restrict__ S_t, const R* __restrict__ cf, long long M, double K, int is_put, int sticky,
                  unsigned int* block_count, unsigned long long* mom_fx) {
+  // A CTA walks several 256-path compaction blocks (grid-stride): the per-block live counts come from one counting
+  // barrier each, the moments are reduced and added to the fixed-point accumulators ONCE per CTA (a launch of one CTA
+  // per block spent its time serialising 4 atomics per block on the same four words).
   __shared__ double red[kMWarps * 2];
-  __shared__ unsigned int s_cnt;
-  if (threadIdx.x == 0) s_cnt = 0u;
-  __syncthreads();
-  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nblocks = (int)((M + kMThreads - 1) / kMThreads);
   double acc[2] = {0.0, 0.0};
-  bool live = false;
-  if (j < M) {
-    const R s = S_t[j];
-    live = mlp_live<R>(s, cf[j], K, is_put, sticky);
-    if (live) { acc[0] = (double)s; acc[1] = (double)s * (double)s; }
+  unsigned int total = 0u;
+  for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const long long j = (long long)b * kMThreads + threadIdx.x;
+    bool live = false;
+    if (j < M) {
+      const R s = S_t[j];
+      live = mlp_live<R>(s, cf[j], K, is_put, sticky);
+      if (live) { acc[0] += (double)s; acc[1] += (double)s * (double)s; }
+    }
+    const unsigned int c = (unsigned int)__syncthreads_count(live);
+    if (threadIdx.x == 0) block_count[b] = c;
+    total += c;
   }
-  const unsigned int w = __popc(__ballot_sync(0xffffffffu, live));
-  if ((threadIdx.x & 31) == 0 && w) atomicAdd(&s_cnt, w);
   block_reduce_sum<2, kMWarps>(acc, red);
-  __syncthreads();
-  if (threadIdx.x == 0) block_count[blockIdx.x] = s_cnt;
-  if (threadIdx.x < 4 && s_cnt) {  // two quantities x (hi, lo) fixed-point chunks; every contributing block adds a bias
+  if (threadIdx.x < 4 && total) {  // two quantities x (hi, lo) fixed-point chunks; every contributing CTA adds a bias
     unsigned long long hi, lo;
     const double v = (threadIdx.x >> 1) ? acc[1] : acc[0];  // warp 0 holds the block totals in every lane
     fx_encode(v * 9.5367431640625e-7, hi, lo);  // scaled by 2^-20: sum(S^2) of 4M paths stays inside the 2^43 range
     atomicAdd(mom_fx + threadIdx.x, (threadIdx.x & 1) ? lo : hi);
   }
-  if (threadIdx.x == 0 && s_cnt) atomicAdd(mom_fx + 4, 1ull);  // contributing blocks (bias count)
+  if (threadIdx.x == 0 && total) atomicAdd(mom_fx + 4, 1ull);  // contributing CTAs (bias count)
 }
 
 // ---- 2. scan + standardisation + fresh network ------------------------------------------------------------
@@ -89,25 +92,24 @@ mlp_scan_kernel(unsigned int* block_count, int nblocks, unsigned long long* mom_
   __shared__ unsigned long long s_part[1024];
   __shared__ unsigned long long s_base;
   const int tid = threadIdx.x;
-  // exclusive scan of block_count (in place), chunked by 1024
-  if (tid == 0) s_base = 0ull;
-  __syncthreads();
-  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
-    const int b = b0 + tid;
-    const unsigned long long v = b < nblocks ? block_count[b] : 0u;
-    s_part[tid] = v;
+  // exclusive scan of block_count (in place): every thread scans a contiguous run, thread 0 scans the 1024 run totals
+  {
+    const int per = (nblocks + 1023) / 1024;
+    const int lo = tid * per, hi = lo + per < nblocks ? lo + per : nblocks;
+    unsigned long long sum = 0ull;
+    for (int i = lo; i < hi; ++i) sum += block_count[i];
+    s_part[tid] = sum;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan
-      const unsigned long long add = tid >= off ? s_part[tid - off] : 0ull;
-      __syncthreads();
-      s_part[tid] += add;
-      __syncthreads();
+    if (tid == 0) {
+      unsigned long long run = 0ull;
+      for (int i = 0; i < 1024; ++i) { const unsigned long long x = s_part[i]; s_part[i] = run; run += x; }
+      s_base = run;
     }
-    if (b < nblocks) block_count[b] = (unsigned int)(s_base + s_part[tid] - v);
     __syncthreads();
-    if (tid == 0) s_base += s_part[1023];
-    __syncthreads();
+    unsigned int run = (unsigned int)s_part[tid];
+    for (int i = lo; i < hi; ++i) { const unsigned int x = block_count[i]; block_count[i] = run; run += x; }
   }
+  __syncthreads();
   if (tid == 0) {
     const long long n = (long long)s_base;
     const int nb = (int)mom_fx[4];
@@ -768,6 +770,7 @@ template <typename R> static int lsm_mlp_t(optmc_ctx* ctx, const optmc_mlp_param
   const long long M = sw.M;
   const int N = sw.N;
   const int nblocks = (int)((M + kMThreads - 1) / kMThreads);
+  const int count_grid = nblocks < 8 * ctx->sm_count ? nblocks : 8 * ctx->sm_count;  // grid-stride over the compaction blocks
   const bool sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) != 0;
   // workspace: block counts | xs | ys | idx | params | adam m, v | grad accumulators | moments | state | cont
   size_t off = 0;
@@ -804,7 +807,7 @@ template <typename R> static int lsm_mlp_t(optmc_ctx* ctx, const optmc_mlp_param
   const int grid_rows = tiles < ctx->sm_count ? tiles : ctx->sm_count;  // one CTA per SM (135 KB of tiles each)
   for (int t = N - 1; t >= 1; --t) {
     const R* S_t = Sr + (size_t)t * sw.ld;
-    mlp_count_kernel<R><<<nblocks, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, d_cnt, d_mom);
+    mlp_count_kernel<R><<<count_grid, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, d_cnt, d_mom);
     mlp_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, nblocks, d_mom, d_st, d_par, d_m, d_v, d_g, np_->seed, t, kMH);
     mlp_compact_kernel<R><<<nblocks, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, sw.Dt[t], d_cnt,
                                                                   d_st, d_xs, d_ys, d_idx);
@@ -835,6 +838,7 @@ template <typename R> static int lsm_mlp_tc_t(optmc_ctx* ctx, const optmc_mlp_pa
   const long long M = sw.M;
   const int N = sw.N;
   const int nblocks = (int)((M + kMThreads - 1) / kMThreads);
+  const int count_grid = nblocks < 8 * ctx->sm_count ? nblocks : 8 * ctx->sm_count;  // grid-stride over the compaction blocks
   const bool sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) != 0;
   long long tiles = (M + 127) / 128;
   const int grid_rows = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);  // one CTA per SM (tiles + TMEM)
@@ -871,7 +875,7 @@ template <typename R> static int lsm_mlp_tc_t(optmc_ctx* ctx, const optmc_mlp_pa
   const int adam_grid = (kTP + 255) / 256;
   for (int t = N - 1; t >= 1; --t) {
     const R* S_t = Sr + (size_t)t * sw.ld;
-    mlp_count_kernel<R><<<nblocks, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, d_cnt, d_mom);
+    mlp_count_kernel<R><<<count_grid, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, d_cnt, d_mom);
     mlp_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_cnt, nblocks, d_mom, d_st, d_par, d_m, d_v, nullptr, np_->seed, t, kTH);
     mlp_compact_kernel<R><<<nblocks, kMThreads, 0, ctx->stream>>>(S_t, cf, M, sw.lp.K, sw.lp.is_put, sticky, sw.Dt[t], d_cnt,
                                                                   d_st, d_xs, d_ys, d_idx);
