@@ -57,7 +57,8 @@ enum optmc_scheme {
 enum optmc_basis {
   OPTMC_BASIS_POLY2 = 2, /* [1, x, x^2], x = S/K : first three reference features (om3:112-115) */
   OPTMC_BASIS_POLY3 = 3, /* [1, x, x^2, x^3]     : first four reference features */
-  OPTMC_BASIS_REF7 = 7   /* all seven reference features (om3:105-121); global fit only (optmc_lsm_global) */
+  OPTMC_BASIS_REF7 = 7   /* all seven reference features (om3:105-121): the basis of the global fits (optmc_lsm_global,
+                            optmc_lsm_gnet); in a per-date fit their span is that of POLY3, which is what runs */
 };
 
 /* LSM loop semantics.  REFERENCE = STICKY | REF_DISCOUNT reproduces om3:616-651. */

@@ -53,7 +53,10 @@ static int validate_lsm(const void* S, int64_t ld, int64_t M, int32_t N, int32_t
   if (M <= 0 || N <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
   if (ld < M) { set_error("ld must be >= M"); return OPTMC_EINVAL; }
   if (dtype != OPTMC_F32 && dtype != OPTMC_F64) { set_error("bad dtype"); return OPTMC_EINVAL; }
-  if (lp->basis != OPTMC_BASIS_POLY2 && lp->basis != OPTMC_BASIS_POLY3) { set_error("basis must be POLY2 or POLY3"); return OPTMC_EINVAL; }
+  // REF7 per date: within one date sqrt(tau) is a constant, x sqrt(tau) is a multiple of x and the hinge max(x-1, 0) is
+  // 0 (puts) or x - 1 (calls) on the in-the-money rows, so the seven reference features span exactly [1, x, x^2, x^3]:
+  // the fitted continuation values are those of POLY3 (betas are reported in that 4-term form).
+  if (lp->basis != OPTMC_BASIS_POLY2 && lp->basis != OPTMC_BASIS_POLY3 && lp->basis != OPTMC_BASIS_REF7) { set_error("basis must be POLY2, POLY3 or REF7"); return OPTMC_EINVAL; }
   if (lp->impl < OPTMC_SWEEP_AUTO || lp->impl > OPTMC_SWEEP_SPLIT) { set_error("bad sweep impl"); return OPTMC_EINVAL; }
   return OPTMC_OK;
 }
@@ -67,7 +70,7 @@ static int bind_sweep(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   SweepDesc& sw = ctx->sw;
   sw = SweepDesc{};
   sw.S = S; sw.ld = ld; sw.M = M; sw.N = N; sw.dtype = dtype; sw.lp = *lp;
-  sw.deg = lp->basis == OPTMC_BASIS_POLY3 ? 3 : 2;
+  sw.deg = lp->basis == OPTMC_BASIS_POLY2 ? 2 : 3;
   const double dt = lp->T / N;
   sw.disc = exp(-lp->r * dt);
   sw.final_scale = (lp->semantics & OPTMC_SEM_REF_DISCOUNT) ? 1.0 : sw.disc;

@@ -243,7 +243,7 @@ class Engine:
     # -- LSM sweep ------------------------------------------------------------------------------------
     @staticmethod
     def _lsm_params(K, r, T, option_type, basis, semantics, impl) -> L.LsmParams:
-        b = {"poly2": L.BASIS_POLY2, "poly3": L.BASIS_POLY3}.get(basis, basis)
+        b = {"poly2": L.BASIS_POLY2, "poly3": L.BASIS_POLY3, "ref7": L.BASIS_REF7}.get(basis, basis)
         s = {"reference": L.SEM_REFERENCE, "textbook": L.SEM_TEXTBOOK}.get(semantics, semantics)
         i = {"auto": L.SWEEP_AUTO, "resident": L.SWEEP_RESIDENT, "split": L.SWEEP_SPLIT}.get(impl, impl)
         return L.LsmParams(float(K), float(r), float(T), 1 if option_type == "put" else 0, int(b), int(s), int(i))
@@ -466,7 +466,7 @@ class Engine:
         L.check(self.lib.optmc_lsm_finish(self._h, sums.data_ptr()))
 
     def gram_len(self, basis="poly2") -> int:
-        b = {"poly2": L.BASIS_POLY2, "poly3": L.BASIS_POLY3}.get(basis, basis)
+        b = {"poly2": L.BASIS_POLY2, "poly3": L.BASIS_POLY3, "ref7": L.BASIS_REF7}.get(basis, basis)
         return int(self.lib.optmc_lsm_gram_len(b))
 
     # -- fused host-facing calls ---------------------------------------------------------------------

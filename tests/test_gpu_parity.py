@@ -986,3 +986,29 @@ def test_calibration_objective_is_one_launch_and_matches_row_by_row(mods):
     # a fresh-noise objective (the reference's behaviour) differs from call to call
     g = compat.HestonObjective(compat.HestonPricer(cfg), S0, r, K, T, iv)
     assert g(x) != g(x)
+
+
+def test_ref7_per_date_spans_poly3(eng, mods):
+    """SURVEY 8(d) C2 "poly2 and ref7 bases": within one date the seven reference features span [1, x, x^2, x^3], so a
+    per-date least-squares fit on them has the fitted values of POLY3 -- checked against numpy's minimum-norm lstsq on
+    the real seven-column design matrix (oracle.features_ref7)."""
+    L, E, orc = mods
+    M, N, K = 4096, 10, 100.0
+    S = eng.paths(E.heston(100.0, 0.05, 1.0, **HP), M, N, "f64", E.RngSpec(seed=12))
+    got = eng.lsm(S, K, 0.05, 1.0, "put", "ref7", "textbook")
+    p3 = eng.lsm(S, K, 0.05, 1.0, "put", "poly3", "textbook")
+    assert got.price == p3.price and got.betas.shape == (N + 1, 4)
+
+    class Ref7Lstsq:  # per-date regression on all seven features, minimum-norm solution
+        p = 7
+
+        def __call__(self, t, t_current, S_itm, Y):
+            F = orc.features_ref7(S_itm, K, 0.05, 1.0, t_current)
+            if len(S_itm) < 4:
+                return None, None
+            w, *_ = np.linalg.lstsq(F, np.asarray(Y, dtype=np.float64), rcond=1e-12)
+            return F @ w, w
+
+    ref = orc.lsm_sweep(S.cpu().numpy(), K, 0.05, 1.0, "put", Ref7Lstsq(), semantics="textbook")
+    assert got.price == pytest.approx(ref.price, rel=1e-7)
+    np.testing.assert_array_equal(got.ex_count, ref.ex_count)
