@@ -301,6 +301,14 @@ def run_own_arm(args):
             gbm = E.gbm(S0, R, T, 0.2)
             dt1, r1 = timed(lambda: eng.price_american(gbm, 100_000, 50, K, "put", "f32", E.RngSpec(seed=7)), 20)
             others["config1_gbm_100k_x50"] = {"ms": dt1 * 1e3, "path_steps_per_s": 100_000 * 50 / dt1, "price": r1.price}
+            # config 2 as ONE option at growing path counts (the latency -> bandwidth transition): 1 M and 4 M run the
+            # persistent sweep (cash-flows in registers), 16 M exceeds its on-chip capacity and runs the split kernels
+            for Mx in (1_000_000, 4_000_000, 16_000_000):
+                dtx, rx = timed(lambda: eng.price_american(model, Mx, N, K, "put", "f32", E.RngSpec(seed=17)), 2)
+                pk, sk = eng.kernel_times()
+                others[f"config2_single_option_{Mx // 1_000_000}M_x252"] = {
+                    "ms": dtx * 1e3, "path_steps_per_s": Mx * N / dtx, "paths_kernel_ms": pk, "sweep_ms": sk,
+                    "sweep": "persistent" if rx.impl_used == L.SWEEP_RESIDENT else "split", "price": rx.price}
             Kg, Tg = np.meshgrid(np.linspace(70, 130, 32), np.linspace(1 / 12, 2, 32))
             n4 = 128  # one GPU's share of the 1024-option grid at 8 GPUs
             dt4, r4 = timed(lambda: eng.price_american_batch(model, 262_144, S0, Kg.ravel()[:n4], Tg.ravel()[:n4],

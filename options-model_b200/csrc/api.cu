@@ -97,14 +97,8 @@ static int run_sweep(optmc_ctx* ctx) {
     int rc = sweep_resident(ctx);
     if (rc) return rc;
   } else {
-    int rc = sweep_begin(ctx);
+    int rc = sweep_split_fused(ctx);
     if (rc) return rc;
-    for (int t = sw.N - 1; t >= 1; --t) {
-      rc = sweep_gram_date(ctx, t, ctx->gram);
-      if (rc) return rc;
-      rc = sweep_update_date(ctx, t, ctx->gram);
-      if (rc) return rc;
-    }
     rc = sweep_finish(ctx, ctx->gram);
     if (rc) return rc;
     rc = sweep_finalize_price(ctx, ctx->gram);

@@ -92,6 +92,143 @@ lsm_gram_kernel(const R* __restrict__ S_t, const R* __restrict__ cf, long long M
   }
 }
 
+// ---- fused streaming pass of the internal split sweep (options whose cash-flows do not fit on chip) --------------
+// One launch per exercise date does what update(t+1) + Gram(t) + solve(t) did in three: every path is touched once
+// (128-bit loads of S[t+1], S[t] and the cash-flows: 12 bytes per path instead of 16), the exercise decision of date
+// t+1 is applied first -- with the coefficients the previous launch solved -- then the path enters the moments of date
+// t exactly as the separate kernels would see it; the last CTA to finish reduces the partials in a fixed order and
+// solves the normal equations.  Same arithmetic per path as lsm_gram_kernel / lsm_update_kernel (which remain the
+// per-date building blocks of the host-looped multi-GPU sweep).
+template <typename R, int VEC> struct VecMem;
+template <> struct VecMem<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { const float4 x = *reinterpret_cast<const float4*>(p); v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct VecMem<double, 4> {
+  static __device__ __forceinline__ void load(const double* p, double (&v)[4]) {
+    const double2 a = reinterpret_cast<const double2*>(p)[0], b = reinterpret_cast<const double2*>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(double* p, const double (&v)[4]) {
+    reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]); reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+  }
+};
+template <typename R> struct VecMem<R, 1> {
+  static __device__ __forceinline__ void load(const R* p, R (&v)[1]) { v[0] = p[0]; }
+  static __device__ __forceinline__ void store(R* p, const R (&v)[1]) { p[0] = v[0]; }
+};
+
+struct StreamArgs {
+  const void* S_dec;   // price row of the decision date t+1, or NULL (first launch: nothing to decide yet)
+  const void* S_gram;  // price row of the regression date t, or NULL (last launch: only the decision of date 1)
+  void* cf;
+  long long M;
+  double dinv, dg;     // 1 / D_(t+1), D_t
+  double K, Kh, Kl, invK;
+  double kk;           // sgn * Kcmp: (sgn * s > kk) in the storage type <=> payoff(s) > 0 in fp64 (see fill_group)
+  int is_put, sticky;
+  const double* beta_dec; const int* valid_dec;          // coefficients of date t+1 (solved by the previous launch)
+  unsigned long long* bnd_dec; unsigned long long* exc_dec;
+  double* partials; unsigned int* ticket;
+  double* beta_out; long long* nitm_out; int* valid_out; // solve of date t
+};
+
+template <typename R, int DEG, int VEC>
+__global__ void __launch_bounds__(kSplitThreads) lsm_stream_kernel(const StreamArgs a) {
+  constexpr int Q = Moments<DEG>::Q;
+  __shared__ double red[kSplitWarps * Q];
+  __shared__ bool is_last;
+  const bool have_dec = a.S_dec != nullptr && *a.valid_dec != 0;
+  const bool have_gram = a.S_gram != nullptr;
+  const bool is_put = a.is_put != 0, sticky = a.sticky != 0;
+  double dec[DEG + 1];
+#pragma unroll
+  for (int i = 0; i <= DEG; ++i) dec[i] = 0.0;
+  if (have_dec) {  // decision polynomial in the raw price, exactly as lsm_update_kernel forms it
+    double sc = 1.0;
+#pragma unroll
+    for (int i = 0; i <= DEG; ++i) {
+      double d = -a.beta_dec[i] * sc;
+      if (i == 0) d += is_put ? a.K : -a.K;
+      if (i == 1) d += is_put ? -1.0 : 1.0;
+      dec[i] = d;
+      sc *= a.invK;
+    }
+  }
+  const R sgn = is_put ? (R)-1 : (R)1;
+  const R c1 = (R)(is_put ? a.Kh : -a.Kh), c2 = (R)(is_put ? a.Kl : -a.Kl);
+  const R dinv = (R)a.dinv, dg = (R)a.dg, kk = (R)a.kk;
+  const R* Sd = static_cast<const R*>(a.S_dec);
+  const R* Sg = static_cast<const R*>(a.S_gram);
+  R* cfp = static_cast<R*>(a.cf);
+  double acc[Q];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) acc[q] = 0.0;
+  unsigned long long bnd = bnd_none(a.is_put);
+  unsigned int cnt = 0;
+  const long long units = a.M / VEC;  // M % VEC == 0 (launcher)
+  for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x) {
+    const long long j = u * VEC;
+    R c[VEC], sd[VEC], sg[VEC];
+    VecMem<R, VEC>::load(cfp + j, c);
+    if (have_dec) VecMem<R, VEC>::load(Sd + j, sd);
+    if (have_gram) VecMem<R, VEC>::load(Sg + j, sg);
+    bool changed = false;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      if (have_dec && !(sticky && signbit(c[i])) && sgn * sd[i] > kk) {  // live and in the money
+        const double s = (double)sd[i];
+        if (poly_eval<DEG>(dec, s) > 0.0) {  // strict '>' (om3:644)
+          const R v = (fma(sgn, sd[i], c1) + c2) * dinv;                                // payoff in date-N money
+          c[i] = sticky ? -v : v;
+          changed = true;
+          cnt++;
+          const unsigned long long b = (unsigned long long)__double_as_longlong(s);
+          bnd = is_put ? (b > bnd ? b : bnd) : (b < bnd ? b : bnd);
+        }
+      }
+      if (have_gram && !(sticky && signbit(c[i])) && sgn * sg[i] > kk) {
+        const R y = fabs(c[i]) * dg;
+        moments_accumulate<DEG>(acc, (double)sg[i] * a.invK, (double)y);
+      }
+    }
+    if (changed) VecMem<R, VEC>::store(cfp + j, c);
+  }
+  if (a.S_dec != nullptr) {
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    bnd = is_put ? warp_max_u64(bnd) : warp_min_u64(bnd);
+    if ((threadIdx.x & 31) == 0 && cnt) {
+      atomicAdd(a.exc_dec, (unsigned long long)cnt);
+      if (is_put) atomicMax(a.bnd_dec, bnd); else atomicMin(a.bnd_dec, bnd);
+    }
+  }
+  if (!have_gram) return;
+  block_reduce_sum<Q, kSplitWarps>(acc, red);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int q = 0; q < Q; ++q) a.partials[(size_t)blockIdx.x * Q + q] = acc[q];
+    __threadfence();
+    is_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    __shared__ double tot[Q];
+    reduce_partials_last_block<Q>(a.partials, gridDim.x, tot, kSplitWarps);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double mom[Q], beta[DEG + 1];
+      for (int q = 0; q < Q; ++q) mom[q] = tot[q];
+      const bool ok = solve_poly<DEG>(mom, beta);
+      for (int i = 0; i <= DEG; ++i) a.beta_out[i] = ok ? beta[i] : nan("");
+      for (int i = DEG + 1; i < kMaxBeta; ++i) a.beta_out[i] = nan("");
+      *a.nitm_out = (long long)(mom[0] + 0.5);
+      *a.valid_out = ok ? 1 : 0;
+      *a.ticket = 0u;
+    }
+  }
+}
+
 template <int DEG>
 __global__ void lsm_solve_kernel(const double* __restrict__ gram, double* beta_t, long long* nitm_t, int* valid_t) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -291,6 +428,59 @@ int sweep_update_date(optmc_ctx* ctx, int t, const double* gram) {
   const SweepDesc& sw = ctx->sw;
   if (sw.dtype == OPTMC_F64) return sw.deg == 2 ? update_date_t<double, 2>(ctx, t, gram) : update_date_t<double, 3>(ctx, t, gram);
   return sw.deg == 2 ? update_date_t<float, 2>(ctx, t, gram) : update_date_t<float, 3>(ctx, t, gram);
+}
+
+// The whole split sweep of the bound option with the fused streaming kernel: N launches instead of 3 (N - 1).
+template <typename R, int DEG> static int sweep_split_fused_t(optmc_ctx* ctx) {
+  SweepDesc& sw = ctx->sw;
+  int rc = sweep_begin(ctx);
+  if (rc) return rc;
+  const R* S = static_cast<const R*>(sw.S);
+  const bool vec4 = (sw.M % 4 == 0) && (sw.ld % 4 == 0) && ((uintptr_t)sw.S % 16 == 0) && ((uintptr_t)ctx->cf % 16 == 0);
+  const long long units = vec4 ? sw.M / 4 : sw.M;
+  long long g = (units + kSplitThreads - 1) / kSplitThreads;
+  const long long cap = (long long)ctx->sm_count * 8;
+  const int grid = (int)(g < 1 ? 1 : (g > cap ? cap : g));
+  rc = ensure_bytes((void**)&ctx->partials, &ctx->partials_bytes, (size_t)grid * 16 * sizeof(double));
+  if (rc) return rc;
+  StreamArgs a{};
+  a.cf = ctx->cf; a.M = sw.M; a.K = sw.lp.K; a.Kh = sw.Kh; a.Kl = sw.Kl; a.invK = 1.0 / sw.lp.K;
+  a.is_put = sw.lp.is_put; a.sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) ? 1 : 0;
+  {  // threshold in the storage type with (sgn s > kk) <=> payoff(s) > 0 for every representable s
+    const double sg = sw.lp.is_put ? -1.0 : 1.0;
+    double Kcmp = sw.lp.K;
+    if (sizeof(R) == 4) {
+      float kf = (float)sw.lp.K;
+      if (sw.lp.is_put) { if ((double)kf < sw.lp.K) kf = nextafterf(kf, INFINITY); }
+      else { if ((double)kf > sw.lp.K) kf = nextafterf(kf, -INFINITY); }
+      Kcmp = (double)kf;
+    }
+    a.kk = sg * Kcmp;
+  }
+  a.partials = ctx->partials; a.ticket = ctx->tickets;
+  for (int t = sw.N - 1; t >= 0; --t) {  // launch t: decision of date t+1 (if any) + regression of date t (if t >= 1)
+    const int td = t + 1;
+    const bool dec = td <= sw.N - 1, gram = t >= 1;
+    if (!dec && !gram) continue;
+    a.S_dec = dec ? S + (size_t)td * sw.ld : nullptr;
+    a.S_gram = gram ? S + (size_t)t * sw.ld : nullptr;
+    a.dinv = dec ? sw.Dinv[td] : 1.0;
+    a.dg = gram ? sw.Dt[t] : 1.0;
+    a.beta_dec = ctx->d_betas + (size_t)td * kMaxBeta; a.valid_dec = ctx->d_valid + td;
+    a.bnd_dec = ctx->d_bnd + td; a.exc_dec = ctx->d_exc + td;
+    a.beta_out = ctx->d_betas + (size_t)t * kMaxBeta; a.nitm_out = ctx->d_nitm + t; a.valid_out = ctx->d_valid + t;
+    if (vec4) lsm_stream_kernel<R, DEG, 4><<<grid, kSplitThreads, 0, ctx->stream>>>(a);
+    else lsm_stream_kernel<R, DEG, 1><<<grid, kSplitThreads, 0, ctx->stream>>>(a);
+    ctx->launches++; sw.n_launches++;
+  }
+  OPTMC_CUDA(cudaGetLastError());
+  return OPTMC_OK;
+}
+
+int sweep_split_fused(optmc_ctx* ctx) {
+  const SweepDesc& sw = ctx->sw;
+  if (sw.dtype == OPTMC_F64) return sw.deg == 2 ? sweep_split_fused_t<double, 2>(ctx) : sweep_split_fused_t<double, 3>(ctx);
+  return sw.deg == 2 ? sweep_split_fused_t<float, 2>(ctx) : sweep_split_fused_t<float, 3>(ctx);
 }
 
 int sweep_finish(optmc_ctx* ctx, double* sums_out) {
