@@ -1,15 +1,16 @@
 // lsm.cu -- K2/K3: the Longstaff-Schwartz backward sweep (loop of om3:615-651 with the polynomial
 // regressor of SURVEY.md 8(c)).  Two implementations with identical results:
 //
-//  * RESIDENT (default): ONE cooperative launch walks all exercise dates.  Each CTA owns a contiguous
-//    slice of paths; the slice's cash-flows live in REGISTERS for the whole sweep (the exercised flag is
-//    the sign bit), each date's price slab slice is staged into shared memory by the TMA engine
-//    (cp.async.bulk + mbarrier, 2-3 stages ahead), and the per-date regression is one block reduction
-//    plus one flag-based all-gather of 128-byte Gram slots through L2 -- no grid-wide barrier, no
-//    atomics on the data path, fixed summation order (bit-reproducible).  HBM traffic: S is read once.
-//  * SPLIT: three small launches per date (Gram / solve / update) with cash-flows in HBM.  Used when the
-//    slice does not fit on chip or the slab is not 16-byte aligned, and as the per-date building blocks
-//    of the path-sharded multi-GPU sweep (the host all-reduces the Gram vector between the calls).
+//  * RESIDENT (default, lsm_resident*.cu): ONE cooperative launch walks all exercise dates.  Each CTA owns a
+//    contiguous slice of paths; the slice's cash-flows live in REGISTERS for the whole sweep (the exercised flag is
+//    the sign bit), each date's price slab slice is staged into shared memory by the TMA engine (cp.async.bulk +
+//    mbarrier, 2-3 stages ahead), and the per-date regression is one block reduction plus an order-independent
+//    fixed-point sum of the CTA totals through L2 (integer `red`, sum and arrival count in one word) -- no grid-wide
+//    barrier, bit-reproducible.  HBM traffic: S is read once.
+//  * SPLIT (this file): cash-flows in HBM.  The internal sweep is one fused streaming launch per date
+//    (lsm_stream_kernel: decision of t+1, moments of t, last-CTA solve); the three per-date kernels (Gram / solve /
+//    update) are the building blocks of the host-looped path-sharded multi-GPU sweep, where the host all-reduces the
+//    Gram vector between the calls.  Used when a slice does not fit on chip or the slab is not 16-byte aligned.
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
