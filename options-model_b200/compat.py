@@ -260,7 +260,8 @@ class AdvancedOptionPricer:
                  nn_layers: int = 3, nn_dropout: float = 0.10,
                  # engine extensions (not in the reference)
                  lsm_regressor: str = "poly2", semantics: str = "reference", dtype: str = "f32", device: int = 0,
-                 gpu_reference_quirks: bool = False, batched: bool = True, out_of_sample: bool = False):
+                 gpu_reference_quirks: bool = False, batched: bool = True, out_of_sample: bool = False,
+                 control_variate_same_paths: bool = False):
         self.K = K
         self.r = r
         self.sigma = sigma
@@ -283,6 +284,7 @@ class AdvancedOptionPricer:
         self.gpu_reference_quirks = gpu_reference_quirks
         self.batched = batched
         self.out_of_sample = out_of_sample  # fit the polynomial on one path set, exercise on an independent one
+        self.control_variate_same_paths = control_variate_same_paths  # European leg on the American paths
         self.last_result: Optional[E.SweepResult] = None
         self._nn_variant = "cpu"  # training defaults of om3:565-613; the *_gpu entry point switches to om3gpu:740-798
 
@@ -383,6 +385,23 @@ class AdvancedOptionPricer:
     def price_american_with_control_variate(self, S0: float, T: float, num_simulations: int = 10000,
                                             num_time_steps: int = 50) -> float:
         """om3:653-677: american + 1.0 * (BS_analytic - european_MC), European leg on independent paths."""
+        if self.control_variate_same_paths and self.use_control_variate and self.sigma is not None \
+                and self.iv_model is None and not (self.use_heston and self.heston_params is not None) \
+                and self.lsm_regressor != "nn":
+            # SURVEY 8f n1: the European payoff of the SAME paths as the control -- one slab, one sweep, one reduction of
+            # its terminal row (the reference simulates the European leg independently, which adds its variance)
+            if S0 <= 0 or self.K <= 0 or T <= 0:
+                raise ValueError("S0, K, T must be positive.")
+            seed = int(self.rng_manager.master_rng.integers(0, 2**31 - 1))
+            self.rng_manager.get_child_seed()
+            M, N = num_simulations // 2 * 2, int(num_time_steps)
+            eng = _engine(self.device)
+            S = eng.paths(self._model(S0, T), M, N, self.dtype, E.RngSpec(seed=seed))
+            res = eng.lsm(S, self.K, self.r, T, self.option_type, self.lsm_regressor, self.semantics, arrays=False)
+            eu_mc, _ = eng.european_from_slab(S[N].contiguous(), self.K, self.r, T, self.option_type)
+            eu_exact = BlackScholesGreeks.black_scholes_price(S0, self.K, T, self.r, self.sigma, self.option_type)
+            self.last_result = res
+            return float(res.price + (eu_exact - eu_mc))
         american_price = self.price_american_enhanced_lsm(S0, T, num_simulations, num_time_steps)
         if not self.use_control_variate or self.sigma is None:
             return american_price

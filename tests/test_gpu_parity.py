@@ -1012,3 +1012,20 @@ def test_ref7_per_date_spans_poly3(eng, mods):
     ref = orc.lsm_sweep(S.cpu().numpy(), K, 0.05, 1.0, "put", Ref7Lstsq(), semantics="textbook")
     assert got.price == pytest.approx(ref.price, rel=1e-7)
     np.testing.assert_array_equal(got.ex_count, ref.ex_count)
+
+
+def test_compat_control_variate_on_the_same_paths(mods):
+    """the reference's control variate uses an independent European simulation (om3:653-677); the flag
+    puts the European leg on the American paths (one slab, one sweep, one reduction of the terminal row).  Both are
+    unbiased estimates of the same quantity."""
+    from options_model_b200 import compat
+
+    kw = dict(K=100.0, r=0.05, sigma=0.2, option_type="put", semantics="textbook")
+    ref, same = [], []
+    for sd in range(8):
+        ref.append(compat.AdvancedOptionPricer(rng_manager=compat.RNGManager(sd), **kw)
+                   .price_american_with_control_variate(100.0, 1.0, 20_000, 25))
+        same.append(compat.AdvancedOptionPricer(rng_manager=compat.RNGManager(sd), control_variate_same_paths=True, **kw)
+                    .price_american_with_control_variate(100.0, 1.0, 20_000, 25))
+    assert abs(np.mean(ref) - np.mean(same)) < 0.08 and 5.9 < np.mean(same) < 6.25
+    assert np.std(same) < 1.5 * np.std(ref)
