@@ -1,6 +1,6 @@
 """Turn the ncu artefacts a gpurun call brought back (gpurun_out/) into the tracked summaries under profiles/.
 
-  python tools/ncu_summary.py [round_tag] [raw_csv ...]
+  python tools/ncu_summary.py [round_tag] [--rep] [raw_csv ...]
 
 Inputs : gpurun_out/launches_<tag>.csv  (ncu --metrics gpu__time_duration.sum launch list)
          gpurun_out/prof_<tag>.ncu-rep  (ncu --set full capture), and / or raw CSV exports of such captures
@@ -27,7 +27,8 @@ summary = {"tag": tag, "launches": {}, "kernels": {}}
 prev_json = os.path.join(out_dir, f"ncu_{tag}_summary.json")
 if os.path.exists(prev_json):
     summary = json.load(open(prev_json))
-extra_csv = sys.argv[2:]
+extra_csv = [a for a in sys.argv[2:] if a != "--rep"]
+use_rep = "--rep" in sys.argv[2:]  # ingest gpurun_out/prof_<tag>.ncu-rep (off by default: a stale report must not win)
 
 launch_csv = os.path.join(ROOT, "gpurun_out", f"launches_{tag}.csv")
 if os.path.exists(launch_csv):
@@ -92,7 +93,7 @@ def ingest(raw_text):
     summary["kernels"].update(fresh)
 
 
-if os.path.exists(rep) and not extra_csv:
+if os.path.exists(rep) and use_rep:
     ingest(subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
 for path in extra_csv:
     ingest(open(path).read())
