@@ -81,8 +81,7 @@ static int bind_sweep(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
     double d = 1.0, di = 1.0;
     for (int t = N; t >= 0; --t) { sw.Dt[t] = d; sw.Dinv[t] = di; d *= sw.disc; di *= inv_disc; }
   }
-  sw.Kh = lp->K; sw.Kl = 0.0;
-  if (dtype == OPTMC_F32) { sw.Kh = (double)(float)lp->K; sw.Kl = (double)(float)(lp->K - sw.Kh); }
+  { const StrikeConsts kc = strike_consts(lp->K, lp->is_put != 0, dtype == OPTMC_F32); sw.Kh = kc.Kh; sw.Kl = kc.Kl; }
   return OPTMC_OK;
 }
 

@@ -447,17 +447,7 @@ template <typename R, int DEG> static int sweep_split_fused_t(optmc_ctx* ctx) {
   StreamArgs a{};
   a.cf = ctx->cf; a.M = sw.M; a.K = sw.lp.K; a.Kh = sw.Kh; a.Kl = sw.Kl; a.invK = 1.0 / sw.lp.K;
   a.is_put = sw.lp.is_put; a.sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) ? 1 : 0;
-  {  // threshold in the storage type with (sgn s > kk) <=> payoff(s) > 0 for every representable s
-    const double sg = sw.lp.is_put ? -1.0 : 1.0;
-    double Kcmp = sw.lp.K;
-    if (sizeof(R) == 4) {
-      float kf = (float)sw.lp.K;
-      if (sw.lp.is_put) { if ((double)kf < sw.lp.K) kf = nextafterf(kf, INFINITY); }
-      else { if ((double)kf > sw.lp.K) kf = nextafterf(kf, -INFINITY); }
-      Kcmp = (double)kf;
-    }
-    a.kk = sg * Kcmp;
-  }
+  a.kk = (sw.lp.is_put ? -1.0 : 1.0) * strike_consts(sw.lp.K, sw.lp.is_put != 0, sizeof(R) == 4).Kcmp;
   a.partials = ctx->partials; a.ticket = ctx->tickets;
   for (int t = sw.N - 1; t >= 0; --t) {  // launch t: decision of date t+1 (if any) + regression of date t (if t >= 1)
     const int td = t + 1;

@@ -438,15 +438,8 @@ template <typename R> static int lsm_global_t(optmc_ctx* ctx, const void* S, int
   }
   // pass constants, exact in the storage type (see lsm_resident_kernel.cuh: Store<>)
   const double sg = lp->is_put ? -1.0 : 1.0;
-  double Kcmp = lp->K, Kh = lp->K, Kl = 0.0;
-  if (f32) {  // float threshold with (s < K) <=> (s < Kcmp) for every float s (puts); mirrored for calls
-    float kf = (float)lp->K;
-    Kh = (double)kf;
-    Kl = (double)(float)(lp->K - Kh);
-    if (lp->is_put) { if ((double)kf < lp->K) kf = nextafterf(kf, INFINITY); }
-    else { if ((double)kf > lp->K) kf = nextafterf(kf, -INFINITY); }
-    Kcmp = (double)kf;
-  }
+  const StrikeConsts kc = strike_consts(lp->K, lp->is_put != 0, f32);
+  const double Kcmp = kc.Kcmp, Kh = kc.Kh, Kl = kc.Kl;
   const bool vec4 = (M % 4 == 0) && (ld % 4 == 0) && ((uintptr_t)S % 16 == 0);
   const long long units = vec4 ? M / 4 : M;
   const unsigned wg = (unsigned)((units + kGThreads - 1) / kGThreads);
@@ -593,15 +586,8 @@ static int lsm_apply_policy_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t
     }
   }
   const double sg = lp->is_put ? -1.0 : 1.0;
-  double Kcmp = lp->K, Kh = lp->K, Kl = 0.0;
-  if (f32) {
-    float kf = (float)lp->K;
-    Kh = (double)kf;
-    Kl = (double)(float)(lp->K - Kh);
-    if (lp->is_put) { if ((double)kf < lp->K) kf = nextafterf(kf, INFINITY); }
-    else { if ((double)kf > lp->K) kf = nextafterf(kf, -INFINITY); }
-    Kcmp = (double)kf;
-  }
+  const StrikeConsts kc = strike_consts(lp->K, lp->is_put != 0, f32);
+  const double Kcmp = kc.Kcmp, Kh = kc.Kh, Kl = kc.Kl;
   const bool vec4 = (M % 4 == 0) && (ld % 4 == 0) && ((uintptr_t)S % 16 == 0);
   const long long units = vec4 ? M / 4 : M;
   const unsigned wg = (unsigned)((units + kGThreads - 1) / kGThreads);

@@ -86,16 +86,8 @@ static void fill_group(ResGroup* g, const void* S, long long ld, long long M, lo
   g->S = S; g->ld = ld; g->M = M; g->chunk = chunk; g->N = N; g->is_put = is_put;
   g->K = K; g->invK = 1.0 / K; g->disc = disc; g->inv_disc = 1.0 / disc; g->final_scale = final_scale;
   const double sg = is_put ? -1.0 : 1.0;
-  double Kcmp = K, Kh = K, Kl = 0.0;
-  if (dtype == OPTMC_F32) {
-    // float threshold with (s < K) <=> (s < Kcmp) for every float s (puts); mirrored for calls
-    float kf = (float)K;
-    Kh = (double)kf;
-    Kl = (double)(float)(K - Kh);
-    if (is_put) { if ((double)kf < K) kf = nextafterf(kf, INFINITY); }
-    else { if ((double)kf > K) kf = nextafterf(kf, -INFINITY); }
-    Kcmp = (double)kf;
-  }
+  const StrikeConsts kc = strike_consts(K, is_put != 0, dtype == OPTMC_F32);
+  const double Kcmp = kc.Kcmp, Kh = kc.Kh, Kl = kc.Kl;
   g->sgn = sg; g->kk = sg * Kcmp; g->c1 = -sg * Kh; g->c2 = -sg * Kl;
 }
 

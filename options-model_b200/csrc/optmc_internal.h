@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
+
 #include <string>
 #include <vector>
 
@@ -38,6 +40,23 @@ struct SweepDesc {  // the sweep currently bound to the context (begin/gram/upda
   bool finals_on_device = false;
   bool rerun_done = false;  // AUTO: the split sweep already replaced an overflowed resident sweep
 };
+
+// Strike constants of a sweep in the storage type (fp32 slabs: K = Kh + Kl with Kh a float; Kcmp = the float
+// threshold for which (s < Kcmp) <=> (s < K) for every float s (puts), mirrored for calls; fp64 slabs: K itself).
+// With these the in-the-money test and the payoff run in storage precision yet agree with the fp64 formulas.
+struct StrikeConsts { double Kcmp, Kh, Kl; };
+inline StrikeConsts strike_consts(double K, bool is_put, bool f32) {
+  StrikeConsts c{K, K, 0.0};
+  if (f32) {
+    float kf = (float)K;
+    c.Kh = (double)kf;
+    c.Kl = (double)(float)(K - c.Kh);
+    if (is_put) { if ((double)kf < K) kf = nextafterf(kf, INFINITY); }
+    else { if ((double)kf > K) kf = nextafterf(kf, -INFINITY); }
+    c.Kcmp = (double)kf;
+  }
+  return c;
+}
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
