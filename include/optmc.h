@@ -208,6 +208,9 @@ int optmc_lsm_poly(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int
                    const optmc_lsm_params* lp, optmc_lsm_result* out /* NULL: asynchronous, fetch later */);
 /* Synchronise and copy the last sweep's results to the host. */
 int optmc_lsm_fetch(optmc_ctx* ctx, optmc_lsm_result* out);
+/* Number of paths whose final cash-flow is exactly zero (om1:168 `zero_prob = mean(cashflows == 0)`).  Valid after a
+ * sweep that keeps its cash-flows in device memory: optmc_lsm_poly with impl = SPLIT, optmc_lsm_mlp. */
+int optmc_lsm_zero_cashflows(optmc_ctx* ctx, int64_t* count);
 
 /* ---- LSM with ONE global regression over all (date, path) rows: the structure of the reference's v3 pricer
  *      (om3:482-651 / om3gpu:695-833) with its network replaced by linear least squares on the seven reference

@@ -115,6 +115,7 @@ PROTOTYPES = {
     "optmc_lsm_poly": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
                                  _P(LsmResult)]),
     "optmc_lsm_fetch": (C.c_int, [C.c_void_p, _P(LsmResult)]),
+    "optmc_lsm_zero_cashflows": (C.c_int, [C.c_void_p, _P(C.c_int64)]),
     "optmc_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "optmc_comm_init": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "optmc_comm_finalize": (C.c_int, [C.c_void_p]),

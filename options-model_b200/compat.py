@@ -563,6 +563,53 @@ class OptionPricer:
         return records
 
 
+class om1:
+    """Options_model.py (om1:44-211), the API `options_ui.py:13` imports: module-level functions returning
+    (mean, std, probability of expiring worthless).  Bind them on the reference side with
+    ``price_american_option = om1.price_american_option`` etc."""
+
+    @staticmethod
+    def price_american_option(S0, K, T, r, sigma, num_simulations=10000, num_time_steps=50, option_type="call",
+                              lsm_poly_degree=2, plot_paths=False, seed=42):
+        """om1:44-170: GBM antithetic paths from ``np.random.seed(seed)`` draws (replayed exactly), per-date ContNet
+        regression (10 full-batch Adam steps, lr 1e-3), sticky mask, N-1 discounts.  -> (mean, std, zero_prob)."""
+        import torch
+
+        if S0 <= 0 or K <= 0 or T <= 0 or sigma <= 0:
+            raise ValueError("S0, K, T, and sigma must be positive.")
+        if r < 0:
+            raise ValueError("r must be non-negative.")
+        if num_simulations <= 0 or num_time_steps <= 0:
+            raise ValueError("num_simulations and num_time_steps must be positive integers.")
+        if lsm_poly_degree < 0 or not isinstance(lsm_poly_degree, int):
+            raise ValueError("lsm_poly_degree must be a non-negative integer.")
+        if option_type not in ("call", "put"):
+            raise ValueError("option_type must be 'call' or 'put'.")
+        eng = _engine()
+        M, N = num_simulations // 2 * 2, int(num_time_steps)
+        if M == 0:
+            return float("nan"), float("nan"), float("nan")
+        Z = np.random.RandomState(seed).standard_normal((N, M // 2))  # = np.random.seed(seed); standard_normal (om1:73-82)
+        S = eng.paths(E.gbm(S0, r, T, sigma), M, N, "f64", E.RngSpec(z1=torch.from_numpy(Z).to(eng.tdev)))
+        res = eng.lsm_mlp(S, K, r, T, option_type, "reference", hidden=32, epochs=10, lr=1e-3, seed=int(seed), arrays=False)
+        std = res.stderr * math.sqrt(M) * math.sqrt((M - 1) / M) if M > 1 else 0.0  # np.std: population
+        return float(res.price), float(std), eng.lsm_zero_cashflows() / M
+
+    @staticmethod
+    def compute_curve_for_S0(S0, K, r, sigma, num_simulations, intervals_per_day, total_points, option_type,
+                             lsm_poly_degree, plot_paths, seed):
+        """om1:190-211."""
+        records = []
+        for i in range(total_points, 0, -1):
+            d = i / intervals_per_day
+            T = d / 365
+            steps = max(10, min(130, int(np.ceil(d))))
+            est, std, zp = om1.price_american_option(S0, K, T, r, sigma, num_simulations, steps, option_type,
+                                                     lsm_poly_degree, plot_paths, seed)
+            records.append({"S0": S0, "Days to Expiry": d, "Option Value": est, "Std Dev": std, "Zero Prob": zp})
+        return records
+
+
 def compute_curve_worker(S0, K, r, sigma, option_type, lsm_poly_degree, seed, intervals_per_day, total_points,
                          num_simulations, plot_paths, use_heston, heston_params, nn_hidden=32, nn_epochs=10,
                          nn_lr=1e-3, verbose=False, regressor="nn"):

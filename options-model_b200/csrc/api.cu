@@ -446,6 +446,13 @@ int optmc_lsm_poly_sharded(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_
   OPTMC_TRY_END
 }
 
+int optmc_lsm_zero_cashflows(optmc_ctx* ctx, int64_t* count) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return sweep_zero_count(ctx, count);
+  OPTMC_TRY_END
+}
+
 int optmc_lsm_fetch(optmc_ctx* ctx, optmc_lsm_result* out) {
   OPTMC_TRY_BEGIN
   OPTMC_ENTER(ctx);

@@ -490,6 +490,37 @@ int sweep_finish(optmc_ctx* ctx, double* sums_out) {
   return OPTMC_OK;
 }
 
+// Paths whose final cash-flow is exactly zero ("expires worthless", om1:168) -- valid after a sweep that keeps the
+// cash-flows in HBM (split / network sweeps).
+template <typename R> __global__ void lsm_zero_count_kernel(const R* __restrict__ cf, long long M, unsigned long long* out) {
+  unsigned int c = 0;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (long long)gridDim.x * blockDim.x)
+    c += cf[j] == (R)0 ? 1u : 0u;  // -0.0 (an exercised zero payoff cannot occur: exercise needs payoff > continuation)
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+int sweep_zero_count(optmc_ctx* ctx, int64_t* count) {
+  SweepDesc& sw = ctx->sw;
+  if (!count) { set_error("null argument"); return OPTMC_EINVAL; }
+  if (!sw.have_results || sw.impl_used != OPTMC_SWEEP_SPLIT || !ctx->cf) {
+    set_error("zero-cash-flow count needs a sweep that keeps its cash-flows in device memory (impl SPLIT, optmc_lsm_mlp)");
+    return OPTMC_EINVAL;
+  }
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->gram);  // scratch, 16 doubles
+  OPTMC_CUDA(cudaMemsetAsync(d, 0, 8, ctx->stream));
+  const int grid = split_grid(ctx, sw.M);
+  if (sw.dtype == OPTMC_F64) lsm_zero_count_kernel<double><<<grid, kSplitThreads, 0, ctx->stream>>>(static_cast<const double*>(ctx->cf), sw.M, d);
+  else lsm_zero_count_kernel<float><<<grid, kSplitThreads, 0, ctx->stream>>>(static_cast<const float*>(ctx->cf), sw.M, d);
+  ctx->launches++;
+  OPTMC_CUDA(cudaGetLastError());
+  unsigned long long h = 0;
+  OPTMC_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  *count = (int64_t)h;
+  return OPTMC_OK;
+}
+
 int sweep_finalize_price(optmc_ctx* ctx, const double* sums) {
   lsm_price_from_sums_kernel<<<1, 1, 0, ctx->stream>>>(sums, ctx->sw.final_scale, ctx->d_final);
   ctx->launches++; ctx->sw.n_launches++;

@@ -139,6 +139,7 @@ int launch_features(optmc_ctx* ctx, const void* S, int64_t n, int32_t dtype, dou
 
 // lsm.cu
 int sweep_begin(optmc_ctx* ctx);
+int sweep_zero_count(optmc_ctx* ctx, int64_t* count);
 int sweep_split_fused(optmc_ctx* ctx);  // begin + one fused launch per date (internal split sweep)                                    // split: cf = payoff(S[N])
 int sweep_gram_date(optmc_ctx* ctx, int t, double* gram_out);       // split: local moments of date t
 int sweep_update_date(optmc_ctx* ctx, int t, const double* gram);   // split: solve + decide + discount

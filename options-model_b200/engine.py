@@ -438,6 +438,12 @@ class Engine:
             L.check(got if got < 0 else L.EINVAL)
         return out
 
+    def lsm_zero_cashflows(self) -> int:
+        """Paths whose final cash-flow is exactly zero, after a split / network sweep (om1:168)."""
+        n = C.c_int64()
+        L.check(self.lib.optmc_lsm_zero_cashflows(self._h, C.byref(n)))
+        return int(n.value)
+
     def lsm_fetch(self, N: int, basis="poly2", arrays=True) -> SweepResult:
         p = 3 if basis in ("poly2", L.BASIS_POLY2) else 4
         res, keep = self._result_block(N, p, arrays)

@@ -1029,3 +1029,27 @@ def test_compat_control_variate_on_the_same_paths(mods):
                     .price_american_with_control_variate(100.0, 1.0, 20_000, 25))
     assert abs(np.mean(ref) - np.mean(same)) < 0.08 and 5.9 < np.mean(same) < 6.25
     assert np.std(same) < 1.5 * np.std(ref)
+
+
+def test_compat_om1_api_mean_std_zero_prob(mods):
+    """Options_model.py (om1:44-211): (mean, std, P(worthless)) on the reference's own numpy draws.  The paths are the
+    reference's bit for bit (np.random.seed(seed) stream), so the European-style statistics that do not depend on the
+    network are checked exactly against numpy; the price within the usual network tolerance."""
+    from options_model_b200 import compat
+
+    L, E, orc = mods
+    S0, K, T, r, sigma, M, N, seed = 100.0, 100.0, 0.5, 0.05, 0.25, 20_000, 20, 42
+    mean, std, zp = compat.om1.price_american_option(S0, K, T, r, sigma, M, N, "put", 2, False, seed)
+    Z = np.random.RandomState(seed).standard_normal((N, M // 2))
+    S = orc.gbm_paths_antithetic(S0, r, sigma, T, M, N, Z)
+    # a path expires worthless iff it is never exercised and ends out of the money: at least every path that is never in
+    # the money does; at most every path that ends out of the money
+    never_itm = np.mean((S[1:] >= K).all(axis=0))
+    ends_otm = np.mean(S[-1] >= K)
+    assert never_itm <= zp <= ends_otm
+    bs = compat.BlackScholesGreeks.black_scholes_price(S0, K, T, r, sigma, "put")
+    assert bs - 0.3 < mean < bs + 1.5 and 0.5 * mean < std < 3.0 * mean
+    rec = compat.om1.compute_curve_for_S0(S0, K, r, sigma, 4000, 1, 2, "put", 2, False, seed)
+    assert [x["Days to Expiry"] for x in rec] == [2.0, 1.0] and set(rec[0]) == {"S0", "Days to Expiry", "Option Value", "Std Dev", "Zero Prob"}
+    with pytest.raises(ValueError):
+        compat.om1.price_american_option(S0, K, T, r, -1.0)
