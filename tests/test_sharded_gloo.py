@@ -140,3 +140,62 @@ def test_shard_pairs_partition():
             assert m % 2 == 0
             seen += list(range(lo, lo + m // 2))
         assert seen == list(range(M // 2))  # contiguous, disjoint, complete
+
+
+class _FakeCommEngine:
+    """Stand-in for the optmc_comm_export / optmc_comm_init pair: records what the host plumbing hands over."""
+
+    def __init__(self, rank, fail_on=None):
+        self.rank, self.fail_on, self.got = rank, fail_on, None
+
+    def comm_export(self):
+        return bytes([self.rank]) * 64
+
+    def comm_init(self, rank, world, handles):
+        if self.fail_on == rank:
+            raise RuntimeError("cudaIpcOpenMemHandle failed (simulated)")
+        self.got = (rank, world, list(handles))
+
+
+def _peer_worker(rank, world, port, fail_on, out):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    import options_model_b200  # noqa: F401
+    from options_model_b200 import sharded
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _FakeCommEngine(rank, fail_on)
+    try:
+        sharded.init_peer_exchange(eng, dist)
+        out.put((rank, "ok", eng.got))
+    except RuntimeError as e:
+        out.put((rank, "raised", str(e)[:40]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_on", [None, 1])
+def test_peer_exchange_wiring_two_ranks_gloo(fail_on):
+    """Host plumbing of the in-kernel NVLink exchange (sharded.init_peer_exchange): every rank receives every rank's
+    64-byte handle in rank order; if ANY rank fails to map a peer, EVERY rank raises (nobody is left spinning on a
+    peer that never launches)."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, fail_on, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(out.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if fail_on is None:
+        for rank, status, info in got:
+            assert status == "ok" and info[0] == rank and info[1] == world
+            assert info[2] == [bytes([0]) * 64, bytes([1]) * 64]
+    else:
+        assert [g[1] for g in got] == ["raised", "raised"]
