@@ -112,3 +112,41 @@ def test_ctypes_mirrors_match_the_compiled_header(lib, tmp_path):
         ct = pairs[name]
         assert ctypes.sizeof(ct) == int(size), name
         assert [getattr(ct, f).offset for f, _ in ct._fields_] == [int(o) for o in offs], name
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+
+    exe = tmp_path / "price_american"
+    libdir = os.path.join(ROOT, "options-model_b200")
+    subprocess.run(["gcc", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "price_american.c"),
+                    "-o", str(exe), "-L", libdir, "-loptmc", f"-Wl,-rpath,{libdir}"], check=True)
+    return exe
+
+
+def test_c_client_compiles_links_and_fails_loudly_without_gpu(lib, tmp_path):
+    """The boundary is a plain C ABI: a C program (no Python, no torch) compiles against include/optmc.h and links
+    liboptmc.so.  Without a CUDA device it must refuse to run (exit code 2), never fall back to a CPU path."""
+    import subprocess
+
+    import torch
+
+    exe = _build_c_example(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu-marked run")
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == 2 and "no CPU fallback" in p.stderr
+
+
+@pytest.mark.gpu
+def test_c_client_prices_configs_1_and_2(lib, tmp_path):
+    import subprocess
+
+    exe = _build_c_example(tmp_path)
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = dict(line.split(" ", 1) for line in p.stdout.strip().splitlines())
+    c1 = float(out["config1"].split()[1])
+    c2 = float(out["config2"].split()[1])
+    assert 6.3 < c1 < 6.8 and 5.6 < c2 < 6.0  # SURVEY 8(c) pins: 6.54 (GBM, reference semantics), 5.83 (Heston)
+    assert "num_simulations and num_time_steps must be positive integers." in out["error"]
