@@ -509,14 +509,18 @@ class ContNetRegressor:
         X = np.asarray(S_itm, dtype=np.float64)
         Xs = (X - X.mean()) / X.std() if X.std() > 0 else X - X.mean()  # om2:289
         net = nn.Sequential(nn.Linear(1, H), nn.ReLU(), nn.Linear(H, H), nn.ReLU(), nn.Linear(H, 1))
-        p0 = np.asarray(self.init_fn(t), dtype=np.float32)
-        with torch.no_grad():
-            net[0].weight.copy_(torch.from_numpy(p0[0:H].reshape(H, 1)))
-            net[0].bias.copy_(torch.from_numpy(p0[H:2 * H]))
-            net[2].weight.copy_(torch.from_numpy(p0[2 * H:2 * H + H * H].reshape(H, H)))
-            net[2].bias.copy_(torch.from_numpy(p0[2 * H + H * H:3 * H + H * H]))
-            net[4].weight.copy_(torch.from_numpy(p0[3 * H + H * H:4 * H + H * H].reshape(1, H)))
-            net[4].bias.copy_(torch.from_numpy(p0[4 * H + H * H:4 * H + H * H + 1]))
+        if self.init_fn is None:  # torch's default initialisation from the global generator, as `ContNet()` (om2:291)
+            p0 = None
+        else:
+            p0 = np.asarray(self.init_fn(t), dtype=np.float32)
+        if p0 is not None:
+            with torch.no_grad():
+                net[0].weight.copy_(torch.from_numpy(p0[0:H].reshape(H, 1)))
+                net[0].bias.copy_(torch.from_numpy(p0[H:2 * H]))
+                net[2].weight.copy_(torch.from_numpy(p0[2 * H:2 * H + H * H].reshape(H, H)))
+                net[2].bias.copy_(torch.from_numpy(p0[2 * H + H * H:3 * H + H * H]))
+                net[4].weight.copy_(torch.from_numpy(p0[3 * H + H * H:4 * H + H * H].reshape(1, H)))
+                net[4].bias.copy_(torch.from_numpy(p0[4 * H + H * H:4 * H + H * H + 1]))
         opt = optim.Adam(net.parameters(), lr=self.lr)
         Xt = torch.from_numpy(Xs.reshape(-1, 1)).float()
         Yt = torch.from_numpy(np.asarray(Y, dtype=np.float64).reshape(-1, 1)).float()
@@ -689,7 +693,7 @@ def lsm_global(S, K, r, T, option_type, fit: Callable, target_ddof=0):
 
 
 def single_lsm_net_fit(variant="cpu", hidden=128, epochs=25, lr=1e-3, batch=None, dropout=0.1, seed=0,
-                       inference_dropout=True, log=None):
+                       inference_dropout=True, log=None, reference_streams=False):
     """``fit`` for :func:`lsm_global` restating the reference's global network regression in torch (CPU, fp32).
 
     variant "cpu" = om3:565-613: SingleLSMNet(7, hidden, 3) (om3:85-103), DataLoader(batch 256, shuffle), Adam(lr,
@@ -698,6 +702,10 @@ def single_lsm_net_fit(variant="cpu", hidden=128, epochs=25, lr=1e-3, batch=None
     variant "gpu" = om3gpu:740-798: batch min(8192, n), AdamW(weight_decay 1e-4), no scheduler, patience 3.
     The returned predictor keeps dropout ACTIVE when ``inference_dropout`` (the reference never calls net.eval(),
     SURVEY App. A).  Streams come from torch's RNG seeded with ``seed``: comparable with the engine statistically.
+    ``reference_streams=True`` (variant "cpu") consumes torch's GLOBAL generator in exactly the reference's order --
+    no re-seeding here (the caller did ``torch.manual_seed(rng_manager.get_child_seed())``, om3:455), network built
+    like ``SingleLSMNet.__init__``, shuffling through ``DataLoader(shuffle=True)`` (om3:577) -- so that the real
+    ``price_american_enhanced_lsm`` is reproduced bit for bit (tests/golden/ref_gnet_prices.json).
     """
     import copy
 
@@ -705,7 +713,8 @@ def single_lsm_net_fit(variant="cpu", hidden=128, epochs=25, lr=1e-3, batch=None
     from torch import nn, optim
 
     def fit(Xn, Ys):
-        torch.manual_seed(seed)
+        if not reference_streams:
+            torch.manual_seed(seed)
         layers = [nn.Linear(Xn.shape[1], hidden), nn.ReLU(), nn.Dropout(dropout)]
         for _ in range(2):
             layers += [nn.Linear(hidden, hidden), nn.ReLU(), nn.Dropout(dropout)]
@@ -719,12 +728,20 @@ def single_lsm_net_fit(variant="cpu", hidden=128, epochs=25, lr=1e-3, batch=None
         opt = optim.Adam(net.parameters(), lr=lr, weight_decay=1e-5) if cpu else optim.AdamW(net.parameters(), lr=lr, weight_decay=1e-4)
         sched = optim.lr_scheduler.ReduceLROnPlateau(opt, patience=5, factor=0.5, min_lr=1e-6) if cpu else None
         best, best_sd, bad = float("inf"), None, 0
+        loader = None
+        if reference_streams:
+            from torch.utils.data import DataLoader, TensorDataset
+
+            loader = DataLoader(TensorDataset(X, Y), batch_size=min(256, n), shuffle=True)  # om3:573-577
         for ep in range(epochs):
-            perm = torch.randperm(n)
             tot, nb = 0.0, 0
-            for b0 in range(0, n, B):
-                idx = perm[b0:b0 + B]
-                loss = nn.functional.mse_loss(net(X[idx]), Y[idx])
+            if loader is not None:
+                batches = loader
+            else:
+                perm = torch.randperm(n)
+                batches = ((X[perm[b0:b0 + B]], Y[perm[b0:b0 + B]]) for b0 in range(0, n, B))
+            for bx, by in batches:
+                loss = nn.MSELoss()(net(bx), by)
                 opt.zero_grad()
                 loss.backward()
                 opt.step()
@@ -752,6 +769,47 @@ def single_lsm_net_fit(variant="cpu", hidden=128, epochs=25, lr=1e-3, batch=None
         return predict
 
     return fit
+
+
+def price_american_om2_nn(S0, K, r, sigma, T, option_type, num_simulations, num_time_steps, seed=42, nn_hidden=32, nn_epochs=10,
+                          nn_lr=1e-3):
+    """``om2.OptionPricer(...).price_american_option`` (om2:216-310, GBM), stream for stream: ``np.random.seed`` /
+    ``torch.manual_seed`` (om2:241-242), one ``standard_normal((N, M/2))`` call, a fresh default-initialised ContNet per
+    date.  -> (mean, population std, P(cash-flow == 0)).  Reproduces the real reference bit for bit on the same numpy /
+    torch versions (tests/golden/ref_gnet_prices.json)."""
+    import torch
+
+    torch.manual_seed(seed)
+    M, N = num_simulations // 2 * 2, num_time_steps
+    Z = np.random.RandomState(seed).standard_normal((N, M // 2))
+    S = gbm_paths_antithetic(S0, r, sigma, T, M, N, Z)
+    res = lsm_sweep(S, K, r, T, option_type, ContNetRegressor(None, nn_hidden, nn_epochs, nn_lr), semantics="reference",
+                    keep_state=True)
+    cf = res.cashflows
+    return float(cf.mean()), float(cf.std()), float(np.mean(cf == 0))
+
+
+def price_american_enhanced_lsm_nn(S0, K, r, T, option_type, num_simulations, num_time_steps, master_seed, sigma=None,
+                                   heston_params=None, nn_hidden=128, nn_epochs=25, nn_lr=1e-3):
+    """``AdvancedOptionPricer(...).price_american_enhanced_lsm`` (om3:439-651) with its own network, stream for stream:
+    child generator + ``torch.manual_seed`` from the RNGManager (om3:454-455), numpy paths, global SingleLSMNet fit
+    and the decision pass with torch's global generator consumed in the reference's order.  Reproduces the real
+    reference bit for bit on the same numpy / torch versions (tests/golden/ref_gnet_prices.json)."""
+    import torch
+
+    m = RNGManager(master_seed)
+    rng = m.get_child_rng()
+    torch.manual_seed(int(m.get_child_seed()))
+    M, N = num_simulations // 2 * 2, num_time_steps
+    if heston_params is not None:
+        hp = heston_params
+        Z1, Z2 = draw_heston_normals(rng, N, M)
+        S = heston_paths_antithetic(S0, r, T, hp["v0"], hp["kappa"], hp["theta"], hp["xi"], hp["rho"], M, N, Z1, Z2)
+    else:
+        S = gbm_paths_antithetic(S0, r, sigma, T, M, N, draw_gbm_normals(rng, N, M))
+    fit = single_lsm_net_fit("cpu", hidden=nn_hidden, epochs=nn_epochs, lr=nn_lr, reference_streams=True, inference_dropout=True)
+    price, stats = lsm_global(S, K, r, T, option_type, fit, target_ddof=0)
+    return price, stats
 
 
 def linear_fit(Xn, Ys):

@@ -232,3 +232,36 @@ def test_localvol_oracle_vs_reference_golden(golden_dir, tag):
         np.testing.assert_allclose(orc.ivnet_sigma(net, K, g[f"{tag}_spots"], tau), g[f"{tag}_sigma"][i], rtol=1e-5)
     S = orc.localvol_paths_antithetic(S0, r, T, int(M), int(N), net, K, g[f"{tag}_Zh"])
     np.testing.assert_allclose(S, g[f"{tag}_S"], rtol=1e-5)
+
+
+def test_global_network_lsm_oracle_reproduces_the_real_reference(golden_dir):
+    """oracle.price_american_enhanced_lsm_nn against prices produced by the REAL AdvancedOptionPricer (om3:439-651, network
+    and all; oracle/gen_golden_gnet.py).  Same numpy draws, torch's global generator consumed in the same order: equal to
+    the last bit on the torch version that made the fixture, to training-noise level otherwise."""
+    import json
+
+    torch = pytest.importorskip("torch")
+    g = json.load(open(os.path.join(golden_dir, "ref_gnet_prices.json")))
+    same = torch.__version__ == g["torch"] and np.__version__ == g["numpy"]
+    hp = dict(v0=0.04, kappa=2.0, theta=0.04, xi=0.5, rho=-0.7)
+    for c in g["cases"]:
+        price, stats = orc.price_american_enhanced_lsm_nn(c["S0"], c["K"], c["r"], c["T"], c["option_type"], c["M"], c["N"],
+                                                          c["master_seed"], sigma=c["sigma"], heston_params=hp if c["heston"] else None,
+                                                          nn_hidden=c["nn_hidden"], nn_epochs=c["nn_epochs"], nn_lr=c["nn_lr"])
+        assert price == pytest.approx(c["reference_price"], rel=1e-12 if same else 5e-2), c["name"]
+        assert stats["n_rows"] > 0
+
+
+def test_per_date_network_lsm_oracle_reproduces_the_real_reference(golden_dir):
+    """oracle.price_american_om2_nn against prices produced by the REAL om2.OptionPricer.price_american_option (om2:216-330:
+    a default-initialised ContNet per date, 10 full-batch Adam steps)."""
+    import json
+
+    torch = pytest.importorskip("torch")
+    g = json.load(open(os.path.join(golden_dir, "ref_gnet_prices.json")))
+    same = torch.__version__ == g["torch"] and np.__version__ == g["numpy"]
+    for c in g["om2_cases"]:
+        mean, std, zp = orc.price_american_om2_nn(c["S0"], c["K"], c["r"], c["sigma"], c["T"], c["option_type"], c["M"], c["N"],
+                                                  c["seed"], c["nn_hidden"], c["nn_epochs"], 1e-3)
+        assert mean == pytest.approx(c["reference_price"], rel=1e-12 if same else 5e-2)
+        assert std > 0 and 0 <= zp <= 1
