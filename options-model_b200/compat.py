@@ -133,6 +133,16 @@ class IVModel:
         self.net = dict(hidden=H, layers=layers, weights=weights, m_scale=float(self.m_scale), tau_scale=float(self.tau_scale),
                         epsilon=eps)
 
+    def get_volatility_batch_torch(self, K: float, S_batch, tau: float):
+        """om3gpu:498-519: tensor in, fp32 tensor out on the engine's device."""
+        import torch
+
+        if K <= 0:
+            raise ValueError(f"K must be positive, got {K}")
+        if torch.any(S_batch <= 0):
+            raise ValueError("All S_batch values must be positive")
+        return _engine().ivnet_sigma(self.net, K, S_batch.reshape(-1), tau).reshape(S_batch.shape).float()
+
     def get_volatility_batch(self, K: float, S_batch: np.ndarray, tau: float) -> np.ndarray:
         S_batch = np.asarray(S_batch, dtype=np.float64)
         if K <= 0:
@@ -163,6 +173,27 @@ def simulate_local_vol_paths_antithetic(S0: float, r: float, T: float, num_simul
                                E.RngSpec(z1=torch.from_numpy(Zo).to(eng.tdev), antithetic=False))
         out[:, M:] = S.cpu().numpy()
     return out
+
+
+def simulate_local_vol_paths_torch(S0: float, r: float, T: float, num_simulations: int, num_time_steps: int, iv_model: "IVModel",
+                                   K: float, device, philox_seed: Optional[int] = None):
+    """om3gpu:250-298.  fp32 paths on ``device``; Z_half = torch.randn(N, M//2, device=device) exactly as the reference
+    draws it (torch.manual_seed reproduces its stream), or in-register Philox with ``philox_seed``.  Returns the
+    [(N+1), num_simulations] tensor; an odd path count adds one non-antithetic column (om3gpu:283-296)."""
+    import torch
+
+    eng = _engine(_dev_index(device))
+    N, M = int(num_time_steps), num_simulations // 2 * 2
+    cols = []
+    if M > 0:
+        rng = E.RngSpec(seed=int(philox_seed)) if philox_seed is not None else \
+            E.RngSpec(z1=torch.randn(N, M // 2, device=eng.tdev))
+        cols.append(eng.paths_localvol(S0, r, T, iv_model.net, K, M, N, "f32", rng))
+    if num_simulations % 2 != 0:
+        rng = E.RngSpec(seed=int(philox_seed) + 1, antithetic=False) if philox_seed is not None else \
+            E.RngSpec(z1=torch.randn(N, 1, device=eng.tdev), antithetic=False)
+        cols.append(eng.paths_localvol(S0, r, T, iv_model.net, K, 1, N, "f32", rng))
+    return torch.cat(cols, dim=1) if len(cols) > 1 else cols[0]
 
 
 def simulate_bs_paths_torch(S0: float, r: float, T: float, sigma: float, num_simulations: int, num_time_steps: int,

@@ -901,6 +901,16 @@ def test_localvol_compat_drop_in_and_pricing(mods, golden_dir):
     assert S_odd.shape == (7, 5) and np.isfinite(S_odd).all()
     with pytest.raises(ValueError):
         ivm.get_volatility_batch(K, np.array([1.0, -1.0]), 0.5)
+    # torch-file variants (om3gpu:250-298, 498-519): torch.randn draws on the device, fp32 tensors out
+    torch.manual_seed(3)
+    St = compat.simulate_local_vol_paths_torch(S0, r, T, 1001, 6, ivm, K, torch.device("cuda"))
+    torch.manual_seed(3)
+    Zh = torch.randn(6, 500, device="cuda")
+    ref32 = mods[2].localvol_paths_antithetic(S0, r, T, 1000, 6, net, K, Zh.double().cpu().numpy())
+    assert St.shape == (7, 1001) and St.dtype == torch.float32
+    np.testing.assert_allclose(St[:, :1000].cpu().numpy(), ref32, rtol=1e-4)
+    sig_t = ivm.get_volatility_batch_torch(K, torch.tensor([90.0, 100.0, 110.0], device="cuda"), 0.5)
+    np.testing.assert_allclose(sig_t.cpu().numpy(), ivm.get_volatility_batch(K, np.array([90.0, 100.0, 110.0]), 0.5), rtol=1e-6)
     # the pricer routes iv_model through the local-volatility paths and the same sweep (om3:461-462)
     p = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=None, option_type="put", rng_manager=compat.RNGManager(42), iv_model=ivm)
     v = p.price_american_enhanced_lsm(100.0, 1.0, num_simulations=50_000, num_time_steps=25)
