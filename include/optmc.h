@@ -298,6 +298,10 @@ typedef struct optmc_gnet_params {
                                  (the net is never switched to eval mode), off under textbook */
   int32_t reserved;
   uint64_t seed;
+  const float* init_params;   /* host [34177] (state_dict order) or NULL = fresh torch-default initialisation.  The torch-GPU
+                                 file keeps ONE network across pricing calls (om3gpu:741-748): pass the previous call's
+                                 final_params here to reproduce that warm start */
+  float* final_params;        /* host [34177] or NULL: the weights used by the decision pass */
 } optmc_gnet_params;
 
 typedef struct optmc_gnet_result {

@@ -317,6 +317,7 @@ class AdvancedOptionPricer:
         self.out_of_sample = out_of_sample  # fit the polynomial on one path set, exercise on an independent one
         self.control_variate_same_paths = control_variate_same_paths  # European leg on the American paths
         self.last_result: Optional[E.SweepResult] = None
+        self._lsm_net = None      # om3gpu:596: the torch-GPU file caches its network across pricing calls
         self._nn_variant = "cpu"  # training defaults of om3:565-613; the *_gpu entry point switches to om3gpu:740-798
 
     # om3:461-472 model routing
@@ -363,9 +364,12 @@ class AdvancedOptionPricer:
                 raise ValueError("lsm_regressor='nn' is built for SingleLSMNet(7, 128, 3) (nn_hidden=128, nn_layers=3)")
             eng = _engine(self.device)
             S = eng.paths(model, M, int(num_time_steps), self.dtype, E.RngSpec(seed=seed))
+            warm = self.gpu_reference_quirks and self._nn_variant == "gpu"  # om3gpu:741-748: one cached network per pricer
             out = eng.lsm_gnet(S, self.K, self.r, T, self.option_type, self.semantics, variant=self._nn_variant,
                                epochs=self.nn_epochs, lr=self.nn_lr, dropout=self.nn_dropout, seed=int(torch_seed or 0),
-                               arrays=self.verbose)
+                               arrays=self.verbose, init_params=self._lsm_net if warm else None, return_params=warm)
+            if warm:
+                self._lsm_net = out["params"]
             self.last_result = out
             return float(out["price"])
         eng = _engine(self.device)

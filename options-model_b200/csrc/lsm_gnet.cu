@@ -816,6 +816,8 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
     OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   gnet_init_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(d_params, d_m, d_v, gp->seed);
+  if (gp->init_params)  // warm start (om3gpu:741-748); the optimiser state is fresh either way (om3gpu:753)
+    OPTMC_CUDA(cudaMemcpyAsync(d_params, gp->init_params, (size_t)kGP * 4, cudaMemcpyHostToDevice, ctx->stream));
   gnet_pack_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(d_params, d_pack);
   n_launches += 2; ctx->launches += 2;
   OPTMC_CUDA(cudaFuncSetAttribute(gnet_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gnet_smem_bytes()));
@@ -897,6 +899,7 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   int flags[4];
   OPTMC_CUDA(cudaMemcpyAsync(fin, ctx->d_final, sizeof(fin), cudaMemcpyDeviceToHost, ctx->stream));
   OPTMC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+  if (gp->final_params) OPTMC_CUDA(cudaMemcpyAsync(gp->final_params, d_params, (size_t)kGP * 4, cudaMemcpyDeviceToHost, ctx->stream));
   std::vector<unsigned long long> hb, he;
   if (out->boundary) { hb.resize(N + 1); OPTMC_CUDA(cudaMemcpyAsync(hb.data(), ctx->d_bnd, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
   if (out->ex_count) { he.resize(N + 1); OPTMC_CUDA(cudaMemcpyAsync(he.data(), ctx->d_exc, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); }

@@ -385,7 +385,8 @@ class Engine:
     GNET_PARAMS = 7 * 128 + 128 + 2 * (128 * 128 + 128) + 128 + 1  # SingleLSMNet(7, 128, 3): 34177
 
     def lsm_gnet(self, S, K, r, T, option_type="put", semantics="reference", variant="cpu", epochs=25, batch=None, lr=1e-3,
-                 weight_decay=None, dropout=0.1, seed=42, inference_dropout=-1, arrays=True, M: Optional[int] = None, **over):
+                 weight_decay=None, dropout=0.1, seed=42, inference_dropout=-1, arrays=True, M: Optional[int] = None,
+                 init_params=None, return_params=False, **over):
         """The reference's v3 algorithm with its own regressor (om3:482-651): one SingleLSMNet(7,128,3) trained on the
         rows of all dates (tcgen05), then the decision pass.  ``variant`` picks the defaults of the CPU file
         (om3:565-613: batch 256, Adam + L2 1e-5, ReduceLROnPlateau, patience 8, population std) or of the torch-GPU
@@ -398,9 +399,18 @@ class Engine:
         gp = L.GnetParams(128, 3, int(epochs), int(batch if batch is not None else (256 if cpu else 8192)), float(lr),
                           float(weight_decay if weight_decay is not None else (1e-5 if cpu else 1e-4)), 0 if cpu else 1,
                           5 if cpu else 0, 0.5, 1e-6, 8 if cpu else 3, 0 if cpu else 1, 1e-6, float(dropout),
-                          int(inference_dropout), 0, int(seed) & 0xFFFFFFFFFFFFFFFF)
+                          int(inference_dropout), 0, int(seed) & 0xFFFFFFFFFFFFFFFF, None, None)
         for k, v in over.items():
             setattr(gp, k, v)
+        fp = C.POINTER(C.c_float)
+        p_in = p_out = None
+        if init_params is not None:  # warm start: the torch-GPU file keeps one network across calls (om3gpu:741-748)
+            p_in = np.ascontiguousarray(init_params, dtype=np.float32)
+            assert p_in.size == self.GNET_PARAMS
+            gp.init_params = p_in.ctypes.data_as(fp)
+        if return_params:
+            p_out = np.zeros(self.GNET_PARAMS, dtype=np.float32)
+            gp.final_params = p_out.ctypes.data_as(fp)
         code = L.F64 if S.dtype == self.torch.float64 else L.F32
         res = L.GnetResult()
         bnd = exc = None
@@ -413,7 +423,7 @@ class Engine:
         L.check(self.lib.optmc_lsm_gnet(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), C.byref(gp), C.byref(res)))
         return dict(price=res.price, stderr=res.stderr_, n_paths=int(res.n_paths), n_rows=int(res.n_rows),
                     epochs_run=int(res.epochs_run), n_launches=int(res.n_launches), best_loss=res.best_loss,
-                    final_lr=res.final_lr, boundary=bnd, ex_count=exc)
+                    final_lr=res.final_lr, boundary=bnd, ex_count=exc, params=p_out)
 
     def gnet_grad_debug(self, feat: np.ndarray, ys: np.ndarray, params: np.ndarray):
         """MSE loss and gradient of SingleLSMNet(7,128,3) on host rows (normalised features [n,7]) -- test aid."""

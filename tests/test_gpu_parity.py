@@ -1063,3 +1063,16 @@ def test_compat_om1_api_mean_std_zero_prob(mods):
     assert [x["Days to Expiry"] for x in rec] == [2.0, 1.0] and set(rec[0]) == {"S0", "Days to Expiry", "Option Value", "Std Dev", "Zero Prob"}
     with pytest.raises(ValueError):
         compat.om1.price_american_option(S0, K, T, r, -1.0)
+
+
+def test_gnet_warm_start_roundtrip(eng, mods):
+    """init_params / final_params of optmc_gnet_params: 0 epochs with given weights reproduces the decision pass of the run
+    that produced them (the torch-GPU file's cached network, om3gpu:741-748); a warm start continues from them."""
+    L, E, orc = mods
+    S = eng.paths(E.gbm(100.0, 0.05, 1.0, 0.2), 20_000, 12, "f32", E.RngSpec(seed=6))
+    a = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "textbook", variant="gpu", epochs=4, seed=5, return_params=True, stop_patience=0)
+    assert a["params"].shape == (eng.GNET_PARAMS,) and np.isfinite(a["params"]).all()
+    b = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "textbook", variant="gpu", epochs=0, seed=99, init_params=a["params"])
+    assert b["price"] == a["price"] and b["epochs_run"] == 0
+    c = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "textbook", variant="gpu", epochs=2, seed=5, init_params=a["params"], stop_patience=0)
+    assert c["best_loss"] < a["best_loss"] + 5e-3
