@@ -1,3 +1,4 @@
+"""ncu target: BASELINE config 3 (per-date tcgen05 network LSM, 4 M paths) with a reduced number of dates.  argv[1] = dates."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

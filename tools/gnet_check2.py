@@ -1,3 +1,4 @@
+"""Development check: training loss / price of the global network LSM against the torch restatement, with and without dropout."""
 import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

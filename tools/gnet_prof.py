@@ -1,3 +1,4 @@
+"""ncu target: one epoch of the global network LSM at BASELINE config-1 size.  argv: variant (gpu|cpu) [batch]."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

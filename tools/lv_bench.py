@@ -1,3 +1,4 @@
+"""Thread-count sweep of the local-volatility path kernel (OPTMC_LV_NT) at three path counts."""
 import os, sys, numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)

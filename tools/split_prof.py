@@ -1,3 +1,4 @@
+"""ncu target: the streaming (split) sweep on a 16 M-path option with few dates."""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
