@@ -230,6 +230,39 @@ template <typename R> OPTMC_HD void heston_qe_step(R& S, R& v, R z1, R z2, const
   v = vn;
 }
 
+#if defined(__CUDA_ARCH__)
+// fp32 production form of the QE step: the same algebra with MUFU reciprocals / roots / log / exp (relative error
+// ~1e-7 per operation, far below the fp32 storage step) and ONE erfc per exponential-branch draw
+// (q = Phi(-|z|); U = q or 1 - q by the sign of z).
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <> __device__ __forceinline__ void heston_qe_step<float>(float& S, float& v, float z1, float z2, const QeConsts<float>& q) {
+  const float m = fmaf(v, q.E, q.theta1mE);
+  const float s2 = fmaf(v, q.c1, q.c2);
+  float vn = 0.f;
+  if (m > 0.f) {
+    const float rm = mufu_rcp(m);
+    const float psi = s2 * rm * rm;
+    if (psi <= 1.5f) {
+      const float ip = 2.0f * mufu_rcp(psi);  // >= 4/3
+      const float b2 = ip - 1.0f + mufu_sqrt(ip * (ip - 1.0f));
+      const float a = m * mufu_rcp(1.0f + b2);
+      const float bz = mufu_sqrt(b2) + z2;
+      vn = a * bz * bz;
+    } else {
+      const float p = (psi - 1.0f) * mufu_rcp(psi + 1.0f);
+      const float tail = 0.5f * erfcf(fabsf(z2) * 0.70710678118654752440f);  // Phi(-|z2|)
+      const float u = z2 < 0.f ? tail : 1.0f - tail;                        // Phi(z2)
+      const float one_minus_u = z2 < 0.f ? 1.0f - tail : tail;
+      // ln((1 - p) / (1 - U)) / beta,  beta = (1 - p) / m
+      vn = u <= p ? 0.f : 0.6931471805599453f * (mufu_lg2(1.0f - p) - mufu_lg2(one_minus_u)) * m * mufu_rcp(1.0f - p);
+    }
+  }
+  const float var = q.k3 * (v + vn);
+  S *= mufu_ex2(1.4426950408889634f * (fmaf(q.k1, v, q.k0r) + fmaf(q.k2, vn, mufu_sqrt(var) * z1)));
+  v = vn;
+}
+#endif
+
 // Scheme dispatch shared by the path and the fused European kernels (scheme ids: include/optmc.h).
 template <typename R, int SCHEME>
 OPTMC_HD void heston_step_any(R& S, R& v, R z1, R z2, const HestonConsts<R>& c, const QeConsts<R>& q) {
