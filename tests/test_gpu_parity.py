@@ -1076,3 +1076,33 @@ def test_gnet_warm_start_roundtrip(eng, mods):
     assert b["price"] == a["price"] and b["epochs_run"] == 0
     c = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "textbook", variant="gpu", epochs=2, seed=5, init_params=a["params"], stop_patience=0)
     assert c["best_loss"] < a["best_loss"] + 5e-3
+
+
+def test_error_paths_of_the_newer_entry_points(eng, mods):
+    """Loud failures instead of silent fallbacks: argument errors map to ValueError with a message, unsupported shapes to
+    NotImplementedError / RuntimeError."""
+    L, E, orc = mods
+    gbm = E.gbm(100.0, 0.05, 1.0, 0.2)
+    S = eng.paths(gbm, 4096, 8, "f32", E.RngSpec(seed=1))
+    with pytest.raises(ValueError, match="optmc_comm_init must be called first"):
+        eng.lsm_sharded(S, 8192, 100.0, 0.05, 1.0)
+    with pytest.raises(NotImplementedError, match="SingleLSMNet"):
+        eng.lsm_gnet(S, 100.0, 0.05, 1.0, hidden=64)
+    with pytest.raises(ValueError, match="bad training parameters"):
+        eng.lsm_gnet(S, 100.0, 0.05, 1.0, lr=-1.0)
+    net = dict(hidden=64, layers=4, weights=np.zeros(100, dtype=np.float32), m_scale=0.1, tau_scale=0.3, epsilon=1e-4)
+    with pytest.raises(ValueError, match="weight count"):
+        eng.paths_localvol(100.0, 0.05, 1.0, net, 100.0, 1024, 4)
+    net48 = dict(net, hidden=48, weights=np.zeros(3 * 48 + 4 * (48 * 48 + 144) + 49, dtype=np.float32))
+    with pytest.raises(NotImplementedError, match="hidden_dim"):
+        eng.paths_localvol(100.0, 0.05, 1.0, net48, 100.0, 1024, 4)
+    with pytest.raises(ValueError, match="antithetic"):
+        eng.paths_localvol(100.0, 0.05, 1.0, dict(net, weights=np.zeros(17409, dtype=np.float32)), 100.0, 1023, 4)
+    res = eng.lsm(S, 100.0, 0.05, 1.0, "put", impl="resident", arrays=False)
+    assert np.isfinite(res.price)
+    with pytest.raises(ValueError, match="cash-flows in device memory"):
+        eng.lsm_zero_cashflows()  # the persistent sweep keeps them in registers
+    eng.lsm(S, 100.0, 0.05, 1.0, "put", impl="split", arrays=False)
+    assert 0 <= eng.lsm_zero_cashflows() <= 4096
+    with pytest.raises(AssertionError):
+        eng.lsm_apply_policy(S, np.zeros((3, 3)), 100.0, 0.05, 1.0)  # betas must be [(N+1), p]
