@@ -22,7 +22,7 @@
 // om3gpu:573-574); the input layer (7 -> 128), biases, activations, loss and Adam in fp32.  The reference's
 // initialisation / shuffling / dropout streams come from torch's global RNG and are not reproducible bit for bit
 // (SURVEY 8c); parity is (i) gradients against torch on identical inputs without dropout, (ii) prices against the
-// torch restatement of the same loop within Monte-Carlo / training noise (tests/test_gpu_parity.py).
+// torch restatement of the same loop within Monte-Carlo / training noise (tests/test_gpu_network.py).
 #include <cuda_bf16.h>
 #include <math.h>
 #include <string.h>
@@ -938,7 +938,7 @@ int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, in
 }
 
 // Test aid: loss and parameter gradients of one batch of n <= 16384 rows given as normalised features [n][7] and
-// targets [n], without dropout -- compared with torch autograd in tests/test_gpu_parity.py.  Host pointers.
+// targets [n], without dropout -- compared with torch autograd in tests/test_gpu_network.py.  Host pointers.
 int gnet_grad_debug(optmc_ctx* ctx, long long n, const float* feat, const float* ys, const float* params, float* grads, float* loss) {
   if (!feat || !ys || !params || !grads || !loss || n <= 0 || n > 16384) { set_error("bad argument"); return OPTMC_EINVAL; }
   if (ctx->cc < 100) { set_error("network LSM needs tcgen05 (sm_100)"); return OPTMC_EUNSUPPORTED; }

@@ -25,3 +25,22 @@ def golden_meta():
 
     with open(os.path.join(GOLDEN, "golden_meta.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    """One engine (context on cuda:0) per test module."""
+    from options_model_b200 import engine as E
+
+    e = E.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from options_model_b200 import _lib as L
+    from options_model_b200 import engine as E
+    from oracle import lsm_oracle as orc
+
+    return L, E, orc

@@ -2,7 +2,7 @@
 world_size 2.  The CUDA engine is replaced by a stand-in with the same per-date interface (lsm_begin /
 lsm_gram_date / lsm_update_date / lsm_finish) built from the numpy oracle's pieces, so this checks the pair
 partition, the collective sequence (one Gram all-reduce per exercise date + one final) and that every rank ends
-with the single-process price.  The real engine runs the same host code on GPUs (tests/test_gpu_parity.py).
+with the single-process price.  The real engine runs the same host code on GPUs (tests/test_gpu_sweep.py, tests/test_multi_gpu.py).
 """
 import os
 import socket
