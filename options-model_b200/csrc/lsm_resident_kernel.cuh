@@ -232,6 +232,41 @@ template <int DEG> struct Decider<float, DEG> {
   }
 };
 
+// The sparse pass of the fp32 sweep reads the per-date constants it needs on a hit -- fp32 coefficients and error
+// bounds of the decision polynomial, 1 / D_t, D_(t-1) -- from shared memory (written once per date by the solving
+// lane).  Kept as fp64 uniform registers they were re-converted (F2F.F32.F64, a quarter-rate pipe) on EVERY hit: eight
+// conversions per hit were a measurable part of the pass in grouped launches (27 k paths per CTA).
+//   layout of the float block: f[0..DEG], b[0..DEG], dinv, dg
+template <typename R, int DEG> struct HitConsts;
+template <int DEG> struct HitConsts<double, DEG> {
+  Decider<double, DEG> dec;
+  double dinv_, dg_;
+  __device__ __forceinline__ bool fast(double s, bool& sure) const { return dec.fast(s, sure); }
+  __device__ __forceinline__ bool exact(double s) const { return dec.exact(s); }
+  __device__ __forceinline__ double dinv() const { return dinv_; }
+  __device__ __forceinline__ double dg() const { return dg_; }
+};
+template <int DEG> struct HitConsts<float, DEG> {
+  const double* d;  // shared: decision polynomial in fp64 (rare exact path)
+  const float* c;   // shared float block
+  __device__ __forceinline__ bool fast(float s, bool& sure) const {
+    float p = c[DEG], e = c[2 * DEG + 1];
+    const float as = fabsf(s);
+#pragma unroll
+    for (int i = DEG - 1; i >= 0; --i) { p = fmaf(p, s, c[i]); e = fmaf(e, as, c[DEG + 1 + i]); }
+    sure = fabsf(p) > e;
+    return p > 0.0f;
+  }
+  __device__ __forceinline__ bool exact(float s) const {
+    double dd[DEG + 1];
+#pragma unroll
+    for (int i = 0; i <= DEG; ++i) dd[i] = d[i];
+    return poly_eval<DEG>(dd, (double)s) > 0.0;
+  }
+  __device__ __forceinline__ float dinv() const { return c[2 * DEG + 2]; }
+  __device__ __forceinline__ float dg() const { return c[2 * DEG + 3]; }
+};
+
 // Passes over the thread's PPT paths (path j = tid + k * NT).  Slots past the end of the CTA's slice read an
 // out-of-the-money sentinel from shared memory and hold a zero cash-flow, so no bounds predicate is needed.
 //   decision of date t: exercise iff dec(S_t) > 0; the sticky flag is the sign bit of the stored cash-flow
@@ -295,7 +330,7 @@ __device__ __forceinline__ void gram_pass(const R (&cf)[PPT], const R* __restric
 // the regression per date): one loop; a warp skips step k when none of its 32 paths is live at date t or t-1.
 template <typename R, int DEG, int PPT, int NT, bool DECIDE, bool GRAM>
 __device__ __forceinline__ void sparse_pass(R (&cf)[PPT], const R* __restrict__ st_t, const R* __restrict__ st_g,
-                                            const Decider<R, DEG>& dec, const PassConsts<R>& pc,
+                                            const HitConsts<R, DEG>& dec, const PassConsts<R>& pc,
                                             double (&mom)[Moments<DEG>::Q], unsigned int& rows, unsigned int& cnt,
                                             R& em) {
   const int tid = threadIdx.x;
@@ -315,7 +350,7 @@ __device__ __forceinline__ void sparse_pass(R (&cf)[PPT], const R* __restrict__ 
         bool pos = dec.fast(st, sure);
         if (lt & !sure) pos = dec.exact(st);  // rare: within fp32 rounding of the exercise boundary
         const bool exer = lt & pos;
-        const R pay = Store<R>::with_flag((fma(pc.sgn, st, pc.c1) + pc.c2) * pc.dinv, pc.flag);
+        const R pay = Store<R>::with_flag((fma(pc.sgn, st, pc.c1) + pc.c2) * dec.dinv(), pc.flag);
         c = exer ? pay : c;
         cf[k] = c;
         cnt += exer ? 1u : 0u;
@@ -323,7 +358,7 @@ __device__ __forceinline__ void sparse_pass(R (&cf)[PPT], const R* __restrict__ 
       }
       if (GRAM) {
         const bool live = lg & !Store<R>::flagged(c, pc.flag);  // not exercised just now (sticky mask)
-        const R y = c * pc.dg;                                   // live lanes are unflagged: c >= 0
+        const R y = c * dec.dg();                                // live lanes are unflagged: c >= 0
         rows += live ? 1u : 0u;
         moments_accumulate_nocount<DEG>(mom, (double)(live ? sg : (R)0), (double)(live ? y : (R)0));
       }
@@ -341,6 +376,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
   __shared__ __align__(8) uint64_t mbar[3];
   __shared__ double s_red[NW * 16];
   __shared__ double s_dec[DEG + 1];   // exercise iff s_dec(s) > 0  (payoff - continuation as a polynomial in S)
+  __shared__ float s_hit[2 * DEG + 4];  // fp32 sweep: f[], b[] of s_dec, 1 / D_t, D_(t-1) of the coming pass (HitConsts)
   __shared__ int s_valid;
   __shared__ unsigned long long s_bnd[2];
   __shared__ unsigned int s_cnt[2];
@@ -375,6 +411,10 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
     s_bnd[0] = s_bnd[1] = bnd_none(a.is_put);
     s_cnt[0] = s_cnt[1] = 0u;
     s_valid = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * DEG + 2; ++i) s_hit[i] = 0.f;
+    s_hit[2 * DEG + 2] = 1.0f;              // 1 / D_N
+    s_hit[2 * DEG + 3] = (float)a.disc;     // D_(N-1)
   }
   // out-of-the-money sentinel behind the slice in every stage (the bulk copies never touch it)
   {
@@ -444,9 +484,12 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
     Decider<R, DEG> dec;
     dec.load(s_dec, decide);
     if (SPARSE) {
-      if (decide && gram) sparse_pass<R, DEG, PPT, NT, true, true>(cf, st_t, st_g, dec, pc, mom, rows, cnt, em);
-      else if (gram) sparse_pass<R, DEG, PPT, NT, false, true>(cf, st_t, st_g, dec, pc, mom, rows, cnt, em);
-      else if (decide) sparse_pass<R, DEG, PPT, NT, true, false>(cf, st_t, st_g, dec, pc, mom, rows, cnt, em);
+      HitConsts<R, DEG> hc;
+      if constexpr (sizeof(R) == 4) { hc.d = s_dec; hc.c = s_hit; }
+      else { hc.dec = dec; hc.dinv_ = pc.dinv; hc.dg_ = pc.dg; }
+      if (decide && gram) sparse_pass<R, DEG, PPT, NT, true, true>(cf, st_t, st_g, hc, pc, mom, rows, cnt, em);
+      else if (gram) sparse_pass<R, DEG, PPT, NT, false, true>(cf, st_t, st_g, hc, pc, mom, rows, cnt, em);
+      else if (decide) sparse_pass<R, DEG, PPT, NT, true, false>(cf, st_t, st_g, hc, pc, mom, rows, cnt, em);
     } else {
       if (decide) decide_pass<R, DEG, PPT, NT>(cf, st_t, dec, pc, cnt, em);
       if (gram) gram_pass<R, DEG, PPT, NT>(cf, st_g, pc, mom, rows);
@@ -509,9 +552,15 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
             if (i == 0) d += is_put ? a.K : -a.K;
             if (i == 1) d += is_put ? -1.0 : 1.0;
             s_dec[i] = d;
+            const float f = (float)d;
+            s_hit[i] = f;
+            s_hit[DEG + 1 + i] = fabsf(f) * 4.76837158203125e-7f;  // 8 * 2^-24, as Decider<float>::load
             sc *= a.invK;
           }
         }
+        // d_t / dinv_t were advanced right after the pass: they are D_(t-1), 1 / D_(t-1) -- the next pass's constants
+        s_hit[2 * DEG + 2] = (float)dinv_t;
+        s_hit[2 * DEG + 3] = (float)(d_t * a.disc);
         if (cta == 0 && a.betas) {
 #pragma unroll
           for (int i = 0; i <= DEG; ++i) a.betas[(size_t)(t - 1) * kMaxBeta + i] = ok ? beta[i] : nan("");
