@@ -400,6 +400,11 @@ def run_own_arm(args):
                          "note": "achieved = algorithmic bytes (SURVEY 8d: 3b per path per exercise date for the sweep, "
                                  "b per path-step for generation) / CUDA-event time of that kernel; traffic = DRAM bytes "
                                  "per launch from the committed ncu capture (profiles/)",
+                         "dram_frac": (kern[dom]["dram_bytes_ncu"] / (kern[dom]["ms"] * 1e-3) / 1e9 / peak
+                                       if kern[dom]["dram_bytes_ncu"] else None),
+                         "dram_note": "dram_frac = measured DRAM traffic of the kernel / its time / peak: the sweep keeps the "
+                                      "cash-flows in registers, so 2b of the 3b algorithmic bytes per path-date never reach HBM "
+                                      "and frac (algorithmic) exceeds 1",
                          "pipeline_frac": (4 * b * B * M * N * world * args.steps) / (ms_total * 1e-3) / 1e9 / (peak * world),
                          "kernels": kern},
             "e2e": {"value": world * B * M * N * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
