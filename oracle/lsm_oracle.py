@@ -15,9 +15,19 @@ its I/O-only dependencies stubbed) and committed under ``tests/golden/``:
 * the LSM loop skeleton (discount order, sticky mask, strict ``>``, N-1 discounts,
   global normalisation): pinned against the real ``price_american_enhanced_lsm`` run
   with its network class swapped for a deterministic stand-in;
+* the network pricers end to end -- global ``SingleLSMNet`` (om3:439-651) and per-date ``ContNet``
+  (om2:216-330): ``price_american_enhanced_lsm_nn`` / ``price_american_om2_nn`` consume numpy's and
+  torch's generators in the reference's order and reproduce prices of the REAL pricers bit for bit
+  (``oracle/gen_golden_gnet.py`` -> ``tests/golden/ref_gnet_prices.json``);
+* local volatility (om3:263-333): pinned against the real ``IVModel`` /
+  ``simulate_local_vol_paths_antithetic`` (``oracle/gen_golden_localvol.py`` ->
+  ``tests/golden/ref_localvol.npz``);
 * the polynomial regressor itself does not exist in the reference (``lsm_poly_degree``
   is a dead parameter, options_model_2.py:176-180): its definition is SURVEY.md
-  section 8(c) and it is pinned only by this file's own goldens ("restatement").
+  section 8(c) and it is pinned only by this file's own goldens -- PARITY UNPINNED for that
+  regressor (the loop around it is pinned as above);
+* Andersen QE and full truncation are north-star schemes absent from the reference: restated from
+  the published algorithms, checked against the semi-analytic Heston price.
 
 All ``file:line`` citations are relative to /root/reference.
 om3 = options_model_3/options_model_3.py, om3gpu = options_model_3/option_model_3_gpu.py,
