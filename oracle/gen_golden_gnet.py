@@ -58,6 +58,29 @@ def main():
                                          c["nn_hidden"], c["nn_epochs"], 1e-3)
         print("om2", c["option_type"], "reference", ref, "oracle", mine, "rel diff", abs(ref - mine[0]) / ref)
         out["om2_cases"].append(dict(c, reference_price=ref, oracle_at_generation=list(mine)))
+    # the calibration objective (hc:404-472) of a fresh HestonCalibrator on a small synthetic smile
+    import pandas as pd
+
+    _, _, hc, _ = G.load_reference()
+    S0, r = 100.0, 0.05
+    Kg, Tg = np.meshgrid(np.linspace(85, 115, 4), np.array([0.25, 0.75]))
+    K, T = Kg.ravel(), Tg.ravel()
+    iv = 0.2 + 0.1 * np.abs(np.log(K / S0)) + 0.02 * np.sqrt(T)
+    cfg = hc.CalibrationConfig(n_mc_paths=4000, n_time_steps=20, verbose=False, plot_results=False)
+    cal = hc.HestonCalibrator(cfg)
+    md = object.__new__(hc.MarketData)  # the constructor reads self.S0 before setting it
+    md.S0, md.r = S0, r
+    md.df = md._validate_data(pd.DataFrame({"K": K, "T": T, "sigma_IV": iv}))
+    md.regime = md._detect_regime()
+    cal.market_data = md
+    out["hc_objective"] = []
+    for x in ([2.0, 0.04, 0.5, -0.7, 0.04], [3.0, 0.06, 0.3, -0.4, 0.05]):
+        cal.pricer = hc.HestonPricer(cfg)  # fresh generator per evaluation, as a new calibrator would have
+        ref = float(cal._objective_function(np.array(x)))
+        mine, prices = orc.hc_objective(x, S0, r, K, T, iv, cfg.n_mc_paths, cfg.n_time_steps, cfg.seed)
+        print("hc objective", x, "reference", ref, "oracle", mine, "rel diff", abs(ref - mine) / ref)
+        out["hc_objective"].append(dict(x=x, S0=S0, r=r, K=K.tolist(), T=T.tolist(), sigma_iv=iv.tolist(), n_mc_paths=cfg.n_mc_paths,
+                                        n_time_steps=cfg.n_time_steps, seed=cfg.seed, reference_value=ref, prices=[float(p) for p in prices]))
     with open(os.path.join(G.OUT, "ref_gnet_prices.json"), "w") as f:
         json.dump(out, f, indent=1)
 

@@ -432,6 +432,39 @@ def hc_price_european(S_T, K, T, r, option_type="call"):
 PIVOT_RTOL = 1e-14  # pivot < 1e-14 * trace(G) -> "no exercise at this date"
 
 
+def hc_objective(x, S0, r, K, T, sigma_iv, n_mc_paths, n_time_steps, seed=42, use_vega_weighting=True, min_vega_weight=0.01):
+    """``HestonCalibrator._objective_function`` (hc:404-472) on a fresh calibrator: one simulation per surface row from the
+    pricer's persistent generator (hc:202, 226-227), vega-weighted RMSE of ln(P_heston / P_bs(sigma_market)) plus the
+    Feller penalty.  Returns (objective, per-row Heston prices).  Reproduces the real reference bit for bit
+    (tests/golden/ref_gnet_prices.json, key "hc_objective")."""
+    from math import erf, exp, log, pi, sqrt
+
+    kappa, theta, sigma, rho, v0 = (float(v) for v in x)
+    rng = default_rng(seed)
+    ncdf = lambda z: 0.5 * (1.0 + erf(z / sqrt(2.0)))  # noqa: E731
+    prices, tot, wsum = [], 0.0, 0.0
+    for k, t, iv in zip(K, T, sigma_iv):
+        Z1, Z2i = hc_draw_normals(rng, n_mc_paths, n_time_steps)
+        S, _ = hc_simulate_paths(kappa, theta, sigma, rho, v0, S0, t, r, n_mc_paths, n_time_steps, Z1, Z2i)
+        p = hc_price_european(S[:, -1], k, t, r, "call")
+        prices.append(p)
+        if np.isnan(p) or p <= 1e-8:
+            continue
+        d1 = (log(S0 / k) + (r + 0.5 * iv**2) * t) / (iv * sqrt(t))
+        d2 = d1 - iv * sqrt(t)
+        bs = S0 * ncdf(d1) - k * exp(-r * t) * ncdf(d2)
+        if bs <= 1e-8:
+            continue
+        vega = max(S0 * exp(-0.5 * d1 * d1) / sqrt(2.0 * pi) * sqrt(t), 1e-8)
+        w = max(vega / 100.0, min_vega_weight) if use_vega_weighting else 1.0
+        tot += w * log(p / bs) ** 2
+        wsum += w
+    if wsum == 0:
+        return 1e6, prices
+    penalty = 0.0 if 2 * kappa * theta >= sigma**2 else 100.0 * abs(2 * kappa * theta - sigma**2)
+    return sqrt(tot / wsum) + penalty, prices
+
+
 def basis_matrix(S_itm, K, basis, T=None, t_current=None, r=None):
     x = np.asarray(S_itm, dtype=np.float64) / K
     if basis == "poly2":

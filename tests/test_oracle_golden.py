@@ -265,3 +265,21 @@ def test_per_date_network_lsm_oracle_reproduces_the_real_reference(golden_dir):
                                                   c["seed"], c["nn_hidden"], c["nn_epochs"], 1e-3)
         assert mean == pytest.approx(c["reference_price"], rel=1e-12 if same else 5e-2)
         assert std > 0 and 0 <= zp <= 1
+
+
+def test_calibration_objective_vs_the_real_reference(golden_dir):
+    """hc:404-472: the oracle's row-by-row restatement and the product's host-side objective (compat.objective_from_prices,
+    fed the reference's own per-row prices) against values produced by the REAL HestonCalibrator._objective_function."""
+    import json
+
+    import options_model_b200  # noqa: F401
+    from options_model_b200 import compat
+
+    g = json.load(open(os.path.join(golden_dir, "ref_gnet_prices.json")))
+    for c in g["hc_objective"]:
+        K, T, iv = np.array(c["K"]), np.array(c["T"]), np.array(c["sigma_iv"])
+        val, prices = orc.hc_objective(c["x"], c["S0"], c["r"], K, T, iv, c["n_mc_paths"], c["n_time_steps"], c["seed"])
+        assert val == pytest.approx(c["reference_value"], rel=1e-12)
+        np.testing.assert_allclose(prices, c["prices"], rtol=1e-12)
+        mine = compat.objective_from_prices(np.array(c["x"]), np.array(c["prices"]), c["S0"], c["r"], K, T, iv)
+        assert mine == pytest.approx(c["reference_value"], rel=1e-10)
