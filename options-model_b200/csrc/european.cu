@@ -31,7 +31,8 @@ struct EuArgs {
 template <typename R, int SCHEME>
 __global__ void __launch_bounds__(kEuThreads) european_fused_kernel(const EuArgs a) {
   constexpr bool HES = (SCHEME >= OPTMC_SCHEME_HESTON_REF_ABSORB);
-  constexpr int SPB = HES ? 2 : 4;
+  constexpr bool F32H = HES && sizeof(R) == 4;  // fp32 Heston draws: three steps per Philox block (optmc_math.cuh)
+  constexpr int SPB = HES ? (F32H ? kHestonF32Spb : 2) : 4;
   __shared__ double red[kEuWarps * 2];
   __shared__ bool is_last;
   const int opt = blockIdx.y;
@@ -55,10 +56,16 @@ __global__ void __launch_bounds__(kEuThreads) european_fused_kernel(const EuArgs
        col += (long long)gridDim.x * blockDim.x) {
     R sp = (R)a.S0, sm = (R)a.S0, vp = (R)a.v0, vm = (R)a.v0;
     for (int t0 = 0; t0 < a.N; t0 += SPB) {
-      R n[4];
+      R n[6];
       Philox4 p = philox_for((unsigned long long)(a.pair_offset + col), (unsigned int)(t0 / SPB), stream, a.seed);
-      Real<R>::normal2(p.v[0], p.v[1], n[0], n[1]);
-      Real<R>::normal2(p.v[2], p.v[3], n[2], n[3]);
+      if constexpr (F32H) {
+        heston_normals_f32<0>(p, n[0], n[1]);
+        heston_normals_f32<1>(p, n[2], n[3]);
+        heston_normals_f32<2>(p, n[4], n[5]);
+      } else {
+        Real<R>::normal2(p.v[0], p.v[1], n[0], n[1]);
+        Real<R>::normal2(p.v[2], p.v[3], n[2], n[3]);
+      }
 #pragma unroll
       for (int s = 0; s < SPB; ++s) {
         if (t0 + s + 1 > a.N) break;

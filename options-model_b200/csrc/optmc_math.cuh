@@ -68,7 +68,7 @@ OPTMC_HD float u32_as_f32(uint32_t x) {
 template <typename R> struct Real;  // per-precision math: device fast paths for float, IEEE for double
 
 // Device fast-math primitives (MUFU, flush-to-zero: none of the arguments below can be denormal).
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 __device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float mufu_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -323,6 +323,191 @@ OPTMC_HD void heston_pair_step_f32(float& sp, float& vp, float& sm, float& vm, f
     sm *= exp2_fast(e);
   }
 }
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------------------------
+// Packed fp32 (sm_100 f32x2: FFMA2 / FMUL2 / FADD2 -- two IEEE fp32 operations per issue slot).  The fp32 path
+// kernel is bound by issue slots and the MUFU pipe, not by HBM, so its production step runs two
+// antithetic pairs per instruction.  Each half of a packed operation rounds exactly like the scalar
+// fmaf / __fmul_rn / __fadd_rn, so packed and scalar code that use the same operation order agree bit for bit.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2_t f2_splat(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ void f2_store4(float* p, f2_t a, f2_t b) {
+  float x0, x1, x2, x3;
+  f2_unpack(a, x0, x1);
+  f2_unpack(b, x2, x3);
+  *reinterpret_cast<float4*>(p) = make_float4(x0, x1, x2, x3);
+}
+// 1.mantissa in [1, 2) from the top 23 bits of a word: (w >> 9) | 0x3f800000 as ONE funnel shift of {0x7f : w}
+__device__ __forceinline__ float mant12(uint32_t w) {
+  uint32_t r;
+  asm("shf.r.clamp.b32 %0, %1, %2, 9;" : "=r"(r) : "r"(w), "r"(0x7fu));
+  return __uint_as_float(r);
+}
+
+// ---- fp32 Heston draws: one Philox4x32-10 block serves THREE steps ------------------------------------------
+// The 128 bits of a block are cut into three 42-bit draws (126 bits used); draw s (s = 0, 1, 2) is
+//   bits [42 s, 42 s + 22)        U: 22-bit radius uniform, u = 2 - 1.U in (0, 1], |z| <= 5.52
+//   bits [42 s + 22, 42 s + 41)   A: 19-bit angle fraction,  y = 1.A - 3/2 in [-1/2, 1/2)
+//   bit   42 s + 41               sign of the cosine
+// Box-Muller on the half circle phi = pi y plus the sign bit (the same uniform law on the circle as 2 pi w),
+// with sin / cos as degree-4 polynomials in y^2 on the FMA pipe (Chebyshev-node fits, absolute error 2e-7:
+// tighter than MUFU.SIN / MUFU.COS) and the radius from MUFU.LG2 + MUFU.SQRT.  Why: measured on B200
+// (tools/paths_bench.cu, profiles/paths_bench_r2.txt) the fp32 path step is bound by the FMA pipe -- the two
+// IMAD.WIDE of a Philox round issue at quarter rate, 40 of the 93 cycles per warp pair-step -- and by the MUFU
+// pipe; three steps per block cut the Philox share by a third and the polynomials take two of the eight MUFU
+// operations of a pair-step.  The normals come out pre-scaled by log2(e) (the exponent of the step is evaluated
+// as one MUFU.EX2): z1l = z1 log2 e, z2l = z2 log2 e.  The scalar and the packed form use the same operations
+// in the same order and agree bit for bit (normals_kernel / the fused European kernel vs the path kernel).
+constexpr int kHestonF32Spb = 3;
+// 32-bit window of the block's 128-bit string starting at bit START (START < 0: shifted in from below)
+template <int START> __device__ __forceinline__ uint32_t philox_window(const Philox4& p) {
+  if constexpr (START < 0) {
+    return p.v[0] << (-START);
+  } else {
+    constexpr int W = START >> 5, SH = START & 31;
+    if constexpr (SH == 0) return p.v[W];
+    const uint32_t lo = p.v[W], hi = W < 3 ? p.v[W + 1] : 0u;
+    uint32_t v;
+    asm("shf.r.clamp.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(lo), "r"(hi), "r"(SH));
+    return v;
+  }
+}
+template <int S> __device__ __forceinline__ void heston_draw_fields(const Philox4& p, float& fu, float& fa, uint32_t& sgn) {
+  const uint32_t wu = philox_window<42 * S - 1>(p);    // U on mantissa bits [22:1]
+  const uint32_t wa = philox_window<42 * S + 18>(p);   // A on mantissa bits [22:4], sign on bit 23
+  fu = __uint_as_float((wu & 0x007ffffeu) | 0x3f800000u);
+  fa = __uint_as_float((wa & 0x007ffff0u) | 0x3f800000u);
+  sgn = (wa << 8) & 0x80000000u;
+}
+// sin / cos polynomials pre-multiplied by sqrt(2 / ln 2): with rad = sqrt(-lg2 u),  rad * PC(t) = log2(e) sqrt(-2 ln u) cos
+#define OPTMC_HALFCIRCLE_SIN                                                                 \
+  constexpr float PS0 = 5.336446285e+00f, PS1 = -8.778098106e+00f, PS2 = 4.331672668e+00f,     \
+                  PS3 = -1.016282082e+00f, PS4 = 1.319097131e-01f;
+#define OPTMC_HALFCIRCLE_COS                                                                 \
+  constexpr float PC0 = 1.698643446e+00f, PC1 = -8.382454872e+00f, PC2 = 6.893793106e+00f,     \
+                  PC3 = -2.262377501e+00f, PC4 = 3.731621504e-01f;
+__device__ __forceinline__ float mufu_sqrt_neg(float x) {  // sqrt(-x), x <= 0: the sign is cleared on the ALU pipe (LOP3)
+  return mufu_sqrt(__uint_as_float(__float_as_uint(x) & 0x7fffffffu));
+}
+template <int S> __device__ __forceinline__ void heston_normals_f32_scaled(const Philox4& p, float& z1l, float& z2l) {
+  OPTMC_HALFCIRCLE_SIN
+  OPTMC_HALFCIRCLE_COS
+  float fu, fa;
+  uint32_t sgn;
+  heston_draw_fields<S>(p, fu, fa, sgn);
+  const float u = fmaf(fu, -1.0f, 2.0f);
+  const float rad = mufu_sqrt_neg(mufu_lg2(u));
+  const float y = __fadd_rn(fa, -1.5f);
+  const float t = __fmul_rn(y, y);
+  float ps = fmaf(PS4, t, PS3), pc = fmaf(PC4, t, PC3);
+  ps = fmaf(ps, t, PS2); pc = fmaf(pc, t, PC2);
+  ps = fmaf(ps, t, PS1); pc = fmaf(pc, t, PC1);
+  ps = fmaf(ps, t, PS0); pc = fmaf(pc, t, PC0);
+  const float sn = __fmul_rn(ps, y);
+  const float cs = __uint_as_float(__float_as_uint(pc) ^ sgn);
+  z1l = __fmul_rn(rad, cs);
+  z2l = __fmul_rn(rad, sn);
+}
+// unscaled N(0,1) pair of step S of the block (kernels that step with the generic scalar schemes)
+template <int S> __device__ __forceinline__ void heston_normals_f32(const Philox4& p, float& z1, float& z2) {
+  float a, b;
+  heston_normals_f32_scaled<S>(p, a, b);
+  z1 = __fmul_rn(a, 0.6931471805599453f);
+  z2 = __fmul_rn(b, 0.6931471805599453f);
+}
+
+// Production fp32 Euler step of TWO antithetic pairs (i, j): the "+" partners of both pairs are the two halves
+// of (sP, uP), the "-" partners those of (sM, uM).  The variance is carried as u = v dt, so sqrt(v dt) is one
+// MUFU.SQRT of the state, and with the log2(e)-scaled normals the step is four packed FMAs per partner-pair:
+//     sq = +-sqrt(u+)     e  = sq * z1l + u+ * (-log2 e / 2) + r dt log2 e           S *= 2^e   (one MUFU.EX2)
+//     xw = xi dt (rho z1 + sqrt(1 - rho^2) z2)          u' = u+ (1 - kappa dt) + kappa theta dt^2 + sq * xw
+// (ABSORB: u' = max(u', 0), om3:228-233; otherwise full truncation: u keeps its sign, u+ = max(u, 0) enters).
+// The draw feeds the step directly: z2 enters only through xw, so the sine polynomial carries the factor
+// xb = sqrt(1 - rho^2) xi dt ln 2 in its coefficients and xw = rad * (xa * cos~ + sin~) costs two packed operations.
+// Algebraically heston_absorb_step / heston_fulltrunc_step on the normals heston_normals_f32 reports; rounding
+// differs in the last ulps.
+struct HestonPairX2 {
+  f2_t xa, sb0, sb1, sb2, sb3, sb4, cs, rs, av, bv;
+  float inv_dt;
+};
+__device__ __forceinline__ HestonPairX2 heston_pair_x2_consts(const HestonConsts<float>& c, bool absorb) {
+  OPTMC_HALFCIRCLE_SIN
+  HestonPairX2 f;
+  const float l2e = 1.4426950408889634f, ln2 = 0.6931471805599453f;
+  const float xb = c.rho_c * c.xi * c.dt * ln2;
+  f.xa = f2_splat(c.rho * c.xi * c.dt * ln2);     // xw from the scaled normals
+  f.sb0 = f2_splat(xb * PS0); f.sb1 = f2_splat(xb * PS1); f.sb2 = f2_splat(xb * PS2);
+  f.sb3 = f2_splat(xb * PS3); f.sb4 = f2_splat(xb * PS4);
+  f.cs = f2_splat(-0.5f * l2e);
+  f.rs = f2_splat(c.r * c.dt * l2e);
+  f.av = f2_splat(absorb ? 1.0f - c.kappa * c.dt : -(c.kappa * c.dt));
+  f.bv = f2_splat(c.kappa * c.theta * c.dt * c.dt);
+  f.inv_dt = 1.0f / c.dt;
+  return f;
+}
+// draw S of the blocks of pairs i and j -> z1l = (z1 log2 e) and xw of both pairs (halves = pair i, pair j)
+template <int S>
+__device__ __forceinline__ void heston_draw_x2(const Philox4& pi, const Philox4& pj, const HestonPairX2& f, f2_t& z1l,
+                                               f2_t& xw) {
+  OPTMC_HALFCIRCLE_COS
+  float fui, fai, fuj, faj;
+  uint32_t si, sj;
+  heston_draw_fields<S>(pi, fui, fai, si);
+  heston_draw_fields<S>(pj, fuj, faj, sj);
+  float u0, u1;
+  f2_unpack(f2_fma(f2_pack(fui, fuj), f2_splat(-1.0f), f2_splat(2.0f)), u0, u1);
+  const f2_t rad = f2_pack(mufu_sqrt_neg(mufu_lg2(u0)), mufu_sqrt_neg(mufu_lg2(u1)));
+  const f2_t y = f2_add(f2_pack(fai, faj), f2_splat(-1.5f));
+  const f2_t t = f2_mul(y, y);
+  f2_t ps = f2_fma(f.sb4, t, f.sb3), pc = f2_fma(f2_splat(PC4), t, f2_splat(PC3));
+  ps = f2_fma(ps, t, f.sb2); pc = f2_fma(pc, t, f2_splat(PC2));
+  ps = f2_fma(ps, t, f.sb1); pc = f2_fma(pc, t, f2_splat(PC1));
+  ps = f2_fma(ps, t, f.sb0); pc = f2_fma(pc, t, f2_splat(PC0));
+  const f2_t sb = f2_mul(ps, y);
+  float c0, c1;
+  f2_unpack(pc, c0, c1);
+  const f2_t cs = f2_pack(__uint_as_float(__float_as_uint(c0) ^ si), __uint_as_float(__float_as_uint(c1) ^ sj));
+  z1l = f2_mul(rad, cs);
+  xw = f2_mul(rad, f2_fma(f.xa, cs, sb));
+}
+template <bool ABSORB, bool MINUS>
+__device__ __forceinline__ void heston_half_step_x2(f2_t& s, f2_t& u, f2_t z1l, f2_t xw, const HestonPairX2& f) {
+  float u0, u1;
+  f2_unpack(u, u0, u1);
+  f2_t up = u;
+  if (!ABSORB) { u0 = fmaxf(u0, 0.0f); u1 = fmaxf(u1, 0.0f); up = f2_pack(u0, u1); }
+  float q0 = mufu_sqrt(u0), q1 = mufu_sqrt(u1);
+  if (MINUS) {  // the antithetic partner sees (-z1, -z2): fold the sign into the root (ALU pipe)
+    q0 = __uint_as_float(__float_as_uint(q0) ^ 0x80000000u);
+    q1 = __uint_as_float(__float_as_uint(q1) ^ 0x80000000u);
+  }
+  const f2_t sq = f2_pack(q0, q1);
+  const f2_t e = f2_fma(sq, z1l, f2_fma(up, f.cs, f.rs));
+  if (ABSORB) {
+    float n0, n1;
+    f2_unpack(f2_fma(sq, xw, f2_fma(up, f.av, f.bv)), n0, n1);
+    u = f2_pack(fmaxf(n0, 0.0f), fmaxf(n1, 0.0f));
+  } else {
+    u = f2_fma(sq, xw, f2_add(u, f2_fma(up, f.av, f.bv)));
+  }
+  float e0, e1;
+  f2_unpack(e, e0, e1);
+  s = f2_mul(s, f2_pack(mufu_ex2(e0), mufu_ex2(e1)));
+}
+template <bool ABSORB>
+__device__ __forceinline__ void heston_pair_step_x2(f2_t& sP, f2_t& uP, f2_t& sM, f2_t& uM, f2_t z1l, f2_t xw,
+                                                    const HestonPairX2& f) {
+  heston_half_step_x2<ABSORB, false>(sP, uP, z1l, xw, f);
+  heston_half_step_x2<ABSORB, true>(sM, uM, z1l, xw, f);
+}
+#endif  // __CUDACC__
 
 // om3:376-380
 template <typename R> OPTMC_HD R payoff(R S, R K, bool is_put) {
