@@ -357,6 +357,37 @@ int optmc_price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, con
                                int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
                                const optmc_american_option* opts, optmc_price_result* results);
 
+/* The same batch with optional extras (every pointer may be NULL):
+ *   - per-date outputs of every option, as optmc_lsm_result holds them for one option (rows of ld_dates >= max N + 1
+ *     entries; betas rows of ld_dates * 4 doubles, NaN where no regression was solved);
+ *   - european[i][0..1]: mean / stderr of exp(-r T) payoff(S_T) over option i's OWN paths -- the European leg of
+ *     price_american_with_control_variate (om3:653-677) with control_variate_same_paths=True, reduced inside the
+ *     grouped sweep launch from the terminal row it stages anyway (no second pass over the slab);
+ *   - shape[0..3] (out): compute threads per CTA, paths per thread, CTAs per option, options per grouped launch of
+ *     the persistent sweep (all 0 when the batch ran through the split sweep);
+ *   - M_total > 0: PATH-SHARDED batch.  Every rank of an optmc_comm_init group calls this with its own
+ *     block of M paths of EACH option (rng->pair_offset = the block's first antithetic pair, M_total = paths per option
+ *     over all ranks, the same options in the same order on every rank, one N for the whole batch); the per-date totals
+ *     of every option are exchanged inside the grouped sweep kernel over NVLink peer memory, prices / betas are those
+ *     of the whole option and identical on every rank.  A failure (fixed-point range, NaN) is propagated through the
+ *     exchange itself, so every rank returns the same status. */
+typedef struct optmc_batch_extras {
+  int64_t* ex_count;  /* host [n_options][ld_dates] */
+  double* boundary;   /* host [n_options][ld_dates] */
+  double* betas;      /* host [n_options][ld_dates][4] */
+  int64_t* n_itm;     /* host [n_options][ld_dates] */
+  int32_t ld_dates;
+  int32_t reserved;
+  double* european;   /* host [n_options][2] */
+  int32_t shape[4];
+  int64_t M_total;
+} optmc_batch_extras;
+
+int optmc_price_american_batch_ex(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                                  int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
+                                  const optmc_american_option* opts, optmc_price_result* results,
+                                  optmc_batch_extras* extras);
+
 /* price_european_streaming / price_european_gpu / HestonPricer.price_european_option
  * (om3:382-437, om3gpu:605-653, hc:259-281): paths are generated and reduced in registers, nothing is
  * stored.  n_options options share mp/rng except K[i], T[i], is_put[i]; option i uses Philox stream

@@ -354,7 +354,9 @@ int optmc_lsm_poly(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int
 }
 
 // ---- path-sharded sweep over several GPUs: exchange slots in peer-mapped memory ----------------
-static size_t comm_slot_bytes() { return (size_t)2 * optmc::kCommMaxRanks * kXchgWords * sizeof(unsigned long long); }
+static size_t comm_slot_bytes() {  // one slot block [2 parities][ranks][words] per option of a grouped launch
+  return (size_t)optmc::kCommMaxGroups * 2 * optmc::kCommMaxRanks * kXchgWords * sizeof(unsigned long long);
+}
 
 int optmc_comm_export(optmc_ctx* ctx, void* handle_out) {
   OPTMC_TRY_BEGIN
@@ -605,7 +607,17 @@ int optmc_price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, con
                                const optmc_american_option* opts, optmc_price_result* results) {
   OPTMC_TRY_BEGIN
   OPTMC_ENTER(ctx);
-  return price_american_batch(ctx, mp, rng, M, dtype, basis, semantics, n_options, opts, results);
+  return price_american_batch(ctx, mp, rng, M, dtype, basis, semantics, n_options, opts, results, nullptr);
+  OPTMC_TRY_END
+}
+
+int optmc_price_american_batch_ex(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                                  int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
+                                  const optmc_american_option* opts, optmc_price_result* results,
+                                  optmc_batch_extras* extras) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return price_american_batch(ctx, mp, rng, M, dtype, basis, semantics, n_options, opts, results, extras);
   OPTMC_TRY_END
 }
 

@@ -29,6 +29,7 @@ namespace optmc {
 struct ResShape { int nt, ppt; };
 #define X(NT_, PPT_) {NT_, PPT_},
 static const ResShape kShapes[] = {OPTMC_RES_SHAPES(X)};
+static const ResShape kSpecShapes[] = {OPTMC_RES_SPEC_SHAPES(X)};  // nt = compute threads (the CTA has 32 more)
 #undef X
 
 // Slice the M paths of ONE option over at most `max_ctas` CTAs and pick the smallest compiled (threads,
@@ -39,7 +40,14 @@ static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int 
   if (ctx->cc < 90) { *why = "bulk async copy needs sm_90+"; return false; }
   int ncta_cap = ctx->sm_count < kMaxResidentCtas ? ctx->sm_count : kMaxResidentCtas;
   if (max_ctas < ncta_cap) ncta_cap = max_ctas;
-  long long ncta = (M + 511) / 512;  // at least one path per thread before adding CTAs
+  // sticky mask => only a small fraction of the paths is in the regression at any date: vote-skip passes, run as the
+  // speculative, warp-specialised kernel.  Tuning aids: OPTMC_RES_SPARSE=0|1, OPTMC_RES_SPEC=0 (single-role kernel).
+  p->sparse = sticky;
+  if (const char* e = getenv("OPTMC_RES_SPARSE")) p->sparse = atoi(e) != 0;
+  p->spec = false;  // TEMP: off until the list-based candidate pass lands
+  if (const char* e = getenv("OPTMC_RES_SPEC")) p->spec = p->sparse && atoi(e) != 0;
+  const int wide = p->spec ? 736 : 768, narrow = p->spec ? 480 : 512;
+  long long ncta = (M + narrow - 1) / narrow;  // at least one path per thread before adding CTAs
   if (ncta > ncta_cap) ncta = ncta_cap;
   if (ncta < 1) ncta = 1;
   long long chunk = (M + ncta - 1) / ncta;
@@ -48,9 +56,13 @@ static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int 
   const ResShape* shape = nullptr;
   int only_nt = 0;  // tuning aid: OPTMC_RES_NT restricts the thread count considered
   if (const char* e = getenv("OPTMC_RES_NT")) only_nt = atoi(e);
-  for (const ResShape& c : kShapes)
-    if ((long long)c.nt * c.ppt >= chunk && (!only_nt || c.nt == only_nt) &&
-        (c.nt == 512 || (sticky && dtype == OPTMC_F32))) { shape = &c; break; }
+  const ResShape* tab = p->spec ? kSpecShapes : kShapes;
+  const size_t ntab = p->spec ? sizeof(kSpecShapes) / sizeof(kSpecShapes[0]) : sizeof(kShapes) / sizeof(kShapes[0]);
+  for (size_t i = 0; i < ntab; ++i) {
+    const ResShape& c = tab[i];
+    if ((long long)c.nt * c.ppt >= chunk && (!only_nt || c.nt == only_nt || c.nt + 32 == only_nt) &&
+        (c.nt == narrow || (c.nt == wide && sticky && dtype == OPTMC_F32))) { shape = &c; break; }
+  }
   if (!shape) { *why = "slice exceeds the register-resident capacity"; return false; }
   // every stage holds the full NT x PPT slot grid: the tail behind the slice is an out-of-the-money sentinel
   const size_t stride = ((size_t)shape->nt * shape->ppt * es + 127) / 128 * 128;
@@ -60,10 +72,6 @@ static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int 
   if (stride * 2 > avail) { *why = "slice exceeds shared memory"; return false; }
   p->ncta = (int)ncta; p->ngroups = 1; p->ppt = shape->ppt; p->nt = shape->nt; p->nstage = nstage; p->chunk = chunk;
   p->stage_stride = (unsigned int)stride; p->smem = stride * nstage;
-  // sticky mask => only a small fraction of the paths is in the regression at any date: vote-skip passes.
-  // Tuning aid: OPTMC_RES_SPARSE=0|1 overrides.
-  p->sparse = sticky;
-  if (const char* e = getenv("OPTMC_RES_SPARSE")) p->sparse = atoi(e) != 0;
   return true;
 }
 
@@ -83,7 +91,7 @@ bool resident_eligible(optmc_ctx* ctx, const SweepDesc& sw, std::string* why) {
 // Option-level constants of one group (see Store<> in lsm_resident_kernel.cuh).
 static void fill_group(ResGroup* g, const void* S, long long ld, long long M, long long chunk, int N, int dtype,
                        double K, int is_put, double disc, double final_scale) {
-  g->S = S; g->ld = ld; g->M = M; g->chunk = chunk; g->N = N; g->is_put = is_put;
+  g->S = S; g->ld = ld; g->M = M; g->M_total = M; g->chunk = chunk; g->N = N; g->is_put = is_put;
   g->K = K; g->invK = 1.0 / K; g->disc = disc; g->inv_disc = 1.0 / disc; g->final_scale = final_scale;
   const double sg = is_put ? -1.0 : 1.0;
   const StrikeConsts kc = strike_consts(K, is_put != 0, dtype == OPTMC_F32);
@@ -119,7 +127,7 @@ int sweep_resident(optmc_ctx* ctx) {
   // Debug aid: OPTMC_TRACE=<file> dumps per-date phase clocks (SM cycles) of the first and last CTA.
   const char* trace_path = getenv("OPTMC_TRACE");
   long long* d_trace = nullptr;
-  const size_t trace_n = (size_t)2 * (sw.N + 1) * 8;
+  const size_t trace_n = (size_t)2 * (sw.N + 1) * kTraceCols;
   if (trace_path && *trace_path) {
     OPTMC_CUDA(cudaMalloc((void**)&d_trace, trace_n * sizeof(long long)));
     OPTMC_CUDA(cudaMemsetAsync(d_trace, 0, trace_n * sizeof(long long), ctx->stream));
@@ -138,7 +146,7 @@ int sweep_resident(optmc_ctx* ctx) {
         for (int c = 0; c < 2; ++c)
           for (int t = sw.N; t >= 1; --t) {
             fprintf(f, "%d %d", c, t);
-            for (int k = 0; k < 8; ++k) fprintf(f, " %lld", h[((size_t)c * (sw.N + 1) + t) * 8 + k]);
+            for (int k = 0; k < kTraceCols; ++k) fprintf(f, " %lld", h[((size_t)c * (sw.N + 1) + t) * kTraceCols + k]);
             fprintf(f, "\n");
           }
         fclose(f);
@@ -149,15 +157,27 @@ int sweep_resident(optmc_ctx* ctx) {
 }
 
 // ---- batched pricing: G options per grouped launch ---------------------------------------------------------
-__global__ void batch_reset_kernel(unsigned long long* words, int n_words, double* finals, int n_finals) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int k = i; k < n_words; k += gridDim.x * blockDim.x) words[k] = 0ull;
-  for (int k = i; k < n_finals; k += gridDim.x * blockDim.x) finals[k] = 0.0;
+// words: exchange accumulators (zero);  finals: zero;  per-date outputs of every group: betas NaN, boundary "none",
+// exercise counts 0, regression rows 0
+__global__ void batch_reset_kernel(unsigned long long* words, int n_words, double* finals, int n_finals, double* betas,
+                                   unsigned long long* bnd, unsigned long long* exc, long long* nitm, int n_dates,
+                                   const ResGroup* groups, int dates_per_group) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+  for (int k = i; k < n_words; k += stride) words[k] = 0ull;
+  for (int k = i; k < n_finals; k += stride) finals[k] = 0.0;
+  if (betas) {
+    for (int k = i; k < n_dates; k += stride) {
+      for (int j = 0; j < kMaxBeta; ++j) betas[(size_t)k * kMaxBeta + j] = nan("");
+      bnd[k] = bnd_none(groups[k / dates_per_group].is_put);
+      exc[k] = 0ull;
+      nitm[k] = 0ll;
+    }
+  }
 }
 
 int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                          int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
-                         const optmc_american_option* opts, optmc_price_result* results) {
+                         const optmc_american_option* opts, optmc_price_result* results, optmc_batch_extras* ex) {
   if (!mp || !rng || !opts || !results) { set_error("null argument"); return OPTMC_EINVAL; }
   if (n_options <= 0) { set_error("n_options must be positive"); return OPTMC_EINVAL; }
   if (M <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
@@ -171,10 +191,21 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
     if (opts[i].N <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
     if (opts[i].N > n_max) n_max = opts[i].N;
   }
+  const bool details = ex && (ex->ex_count || ex->boundary || ex->betas || ex->n_itm);
+  const bool want_eu = ex && ex->european;
+  const int64_t M_total = ex && ex->M_total > 0 ? ex->M_total : 0;  // > 0: path-sharded batch
+  if (details && ex->ld_dates < n_max + 1) { set_error("extras: ld_dates must be >= max N + 1"); return OPTMC_EINVAL; }
+  if (ex) ex->shape[0] = ex->shape[1] = ex->shape[2] = ex->shape[3] = 0;
   const size_t es = dtype == OPTMC_F64 ? 8 : 4;
   const int deg = basis == OPTMC_BASIS_POLY3 ? 3 : 2;
   const bool sticky = (semantics & OPTMC_SEM_STICKY_MASK) != 0;
   const int64_t ld = (M + 63) / 64 * 64;
+  if (M_total) {
+    if (ctx->comm.nranks < 1) { set_error("optmc_comm_init must be called first"); return OPTMC_EINVAL; }
+    if (M_total < M) { set_error("M_total must be >= M"); return OPTMC_EINVAL; }
+    for (int i = 0; i < n_options; ++i)
+      if (opts[i].N != n_max) { set_error("a path-sharded batch needs one N for all options"); return OPTMC_EUNSUPPORTED; }
+  }
 
   // CTAs per option: the fewest that hold a slice on chip (throughput falls with more: DESIGN.md 4), but use the
   // whole machine when there are fewer options than groups.
@@ -184,20 +215,54 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
   for (int c = 1; c <= ctx->sm_count; ++c) {
     if (plan_shape(ctx, M, dtype, sticky, c, &p, &why) && p.ncta <= c) { cpg = c; break; }
   }
-  if (cpg == 0) {  // does not fit on chip: one option at a time through the single-option entry (split sweep)
+  if (cpg == 0 || (M_total && !p.spec)) {
+    if (M_total) {  // every rank takes this branch alike: eligibility depends on (M, dtype, semantics) only
+      set_error("path-sharded batch needs the speculative persistent sweep on every rank (sticky semantics, slice on chip): " + why);
+      return OPTMC_EUNSUPPORTED;
+    }
+    // does not fit on chip: one option at a time through the single-option entry (split sweep)
     for (int i = 0; i < n_options; ++i) {
       optmc_model_params m = *mp; m.S0 = opts[i].S0; m.T = opts[i].T;
       optmc_rng_params r = *rng; r.stream = rng->stream + opts[i].stream;
       optmc_lsm_params lp{opts[i].K, mp->r, opts[i].T, opts[i].is_put, basis, semantics, OPTMC_SWEEP_AUTO};
+      std::vector<double> hb, hbd;
+      std::vector<int64_t> hex, hni;
       optmc_lsm_result res{};
+      if (details) {
+        const int n1 = opts[i].N + 1;
+        hb.resize((size_t)n1 * (deg + 1)); hbd.resize(n1); hex.resize(n1); hni.resize(n1);
+        res.betas = hb.data(); res.boundary = hbd.data(); res.ex_count = hex.data(); res.n_itm = hni.data();
+      }
       int rc = optmc_price_american(ctx, &m, &r, M, opts[i].N, dtype, &lp, &res);
       if (rc) return rc;
       results[i].price = res.price; results[i].stderr_ = res.stderr_;
+      if (details) {
+        for (int t = 0; t <= opts[i].N; ++t) {
+          const size_t o = (size_t)i * ex->ld_dates + t;
+          if (ex->ex_count) ex->ex_count[o] = hex[t];
+          if (ex->boundary) ex->boundary[o] = hbd[t];
+          if (ex->n_itm) ex->n_itm[o] = hni[t];
+          if (ex->betas) for (int j = 0; j <= deg; ++j) ex->betas[o * 4 + j] = hb[(size_t)t * (deg + 1) + j];
+        }
+      }
+      if (want_eu) {  // the slab of this option is still in the context
+        optmc_european_result er{};
+        rc = launch_european_slab(ctx, static_cast<const char*>(ctx->slab) + (size_t)opts[i].N * ((M + 63) / 64 * 64) * es, M, dtype,
+                                  opts[i].K, mp->r, opts[i].T, opts[i].is_put, &er);
+        if (rc) return rc;
+        ex->european[2 * i] = er.mean; ex->european[2 * i + 1] = er.stderr_;
+      }
     }
     return OPTMC_OK;
   }
+  if (const char* e = getenv("OPTMC_BATCH_CPG")) {  // tuning aid: CTAs per option of a grouped launch
+    const int c = atoi(e);
+    ResPlan pe;
+    if (c >= cpg && c <= ctx->sm_count && plan_shape(ctx, M, dtype, sticky, c, &pe, &why)) { p = pe; cpg = c; }
+  }
   int G = ctx->sm_count / cpg;
   if (G > n_options) G = n_options;
+  if (M_total && G > kCommMaxGroups) G = kCommMaxGroups;
   {  // spread the SMs over the groups actually used
     const int c2 = ctx->sm_count / G;
     ResPlan p2;
@@ -205,17 +270,21 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
   }
   cpg = p.ncta;
   p.ngroups = G;
+  if (ex) { ex->shape[0] = p.nt; ex->shape[1] = p.ppt; ex->shape[2] = cpg; ex->shape[3] = G; }
 
   // workspaces: G slabs + per-wave descriptors / accumulators / results in one device block
   const size_t slab_stride = ((size_t)(n_max + 1) * ld * es + 255) / 256 * 256;
   int rc = ensure_bytes(&ctx->slab, &ctx->slab_bytes, slab_stride * G);
   if (rc) return rc;
+  const int n1 = n_max + 1;
   const size_t off_groups = 0;
   const size_t off_paths = off_groups + ((sizeof(ResGroup) * G + 255) / 256 * 256);
   const size_t off_words = off_paths + ((path_args_bytes() * G + 255) / 256 * 256);
   const size_t n_words = (size_t)G * 2 * kXchgWords * kXchgStride + (size_t)G * 2;  // accumulators + flags (as u64 pairs)
   const size_t off_final = off_words + ((n_words * 8 + 255) / 256 * 256);
-  const size_t total = off_final + (size_t)G * 4 * sizeof(double);
+  const size_t off_det = off_final + (((size_t)G * 8 * sizeof(double) + 255) / 256 * 256);
+  const size_t det_per_group = details ? (size_t)n1 * (kMaxBeta + 3) * 8 : 0;  // betas, bnd, exc, nitm
+  const size_t total = off_det + det_per_group * G;
   rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, total);
   if (rc) return rc;
   char* dev = static_cast<char*>(ctx->batch_dev);
@@ -223,12 +292,18 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
   unsigned long long* d_words = reinterpret_cast<unsigned long long*>(dev + off_words);
   int* d_flags = reinterpret_cast<int*>(d_words + (size_t)G * 2 * kXchgWords * kXchgStride);
   double* d_final = reinterpret_cast<double*>(dev + off_final);
+  double* d_betas = details ? reinterpret_cast<double*>(dev + off_det) : nullptr;
+  unsigned long long* d_bnd = details ? reinterpret_cast<unsigned long long*>(d_betas + (size_t)G * n1 * kMaxBeta) : nullptr;
+  unsigned long long* d_exc = details ? d_bnd + (size_t)G * n1 : nullptr;
+  long long* d_nitm = details ? reinterpret_cast<long long*>(d_exc + (size_t)G * n1) : nullptr;
 
   std::vector<ResGroup> hg(G);
   std::vector<char> hp(path_args_bytes() * G);
-  std::vector<double> hfin((size_t)G * 4);
+  std::vector<double> hfin((size_t)G * 8);
   std::vector<int> hflags((size_t)G * 4);
+  std::vector<double> hdet(details ? (size_t)G * n1 * (kMaxBeta + 3) : 0);
   ctx->last_paths_ms = 0.0; ctx->last_sweep_ms = 0.0;
+  double acc_paths_ms = 0.0, acc_sweep_ms = 0.0;
   for (int w0 = 0; w0 < n_options; w0 += G) {
     const int g_now = n_options - w0 < G ? n_options - w0 : G;
     for (int g = 0; g < g_now; ++g) {
@@ -236,48 +311,100 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
       const double disc = exp(-mp->r * (o.T / o.N));
       fill_group(&hg[g], static_cast<char*>(ctx->slab) + (size_t)g * slab_stride, ld, M, p.chunk, o.N, dtype, o.K, o.is_put,
                  disc, (semantics & OPTMC_SEM_REF_DISCOUNT) ? 1.0 : disc);
+      if (M_total) hg[g].M_total = M_total;
       hg[g].xw = d_words + (size_t)g * 2 * kXchgWords * kXchgStride;
       hg[g].flags = d_flags + (size_t)g * 4;
-      hg[g].betas = nullptr; hg[g].bnd = nullptr; hg[g].exc = nullptr; hg[g].nitm = nullptr;
-      hg[g].final_out = d_final + (size_t)g * 4;
+      hg[g].betas = details ? d_betas + (size_t)g * n1 * kMaxBeta : nullptr;
+      hg[g].bnd = details ? d_bnd + (size_t)g * n1 : nullptr;
+      hg[g].exc = details ? d_exc + (size_t)g * n1 : nullptr;
+      hg[g].nitm = details ? d_nitm + (size_t)g * n1 : nullptr;
+      hg[g].final_out = d_final + (size_t)g * 8;
     }
     OPTMC_CUDA(cudaMemcpyAsync(d_groups, hg.data(), sizeof(ResGroup) * g_now, cudaMemcpyHostToDevice, ctx->stream));
-    batch_reset_kernel<<<8, 256, 0, ctx->stream>>>(d_words, (int)n_words, d_final, G * 4);
+    rc = prepare_paths_batch(ctx, mp, rng, M, g_now, opts + w0, ctx->slab, slab_stride, ld, dev + off_paths, hp.data());
+    if (rc) return rc;
+    batch_reset_kernel<<<8, 256, 0, ctx->stream>>>(d_words, (int)n_words, d_final, G * 8, d_betas, d_bnd, d_exc, d_nitm,
+                                                   details ? g_now * n1 : 0, d_groups, n1);
     ctx->launches++;
     OPTMC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-    rc = launch_paths_batch(ctx, mp, rng, M, dtype, g_now, opts + w0, ctx->slab, slab_stride, ld, dev + off_paths, hp.data());
+    rc = launch_paths_batch(ctx, mp, dtype, g_now, ctx->slab, slab_stride, ld, dev + off_paths, hp.data());
     if (rc) return rc;
     OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
     ResPlan pw = p;
     pw.ngroups = g_now;
     ResArgs a{};
     a.groups = d_groups; a.cpg = cpg; a.nstage = p.nstage; a.stage_stride = p.stage_stride; a.sticky = sticky ? 1 : 0;
+    a.want_eu = (want_eu && p.spec) ? 1 : 0;
+    if (M_total) {  // in-kernel exchange with the peer ranks, one slot block per group
+      a.comm.nranks = ctx->comm.nranks; a.comm.rank = ctx->comm.rank; a.comm.g0 = ctx->comm.g;
+      a.comm.M_total = M_total;
+      for (int r = 0; r < ctx->comm.nranks; ++r) a.comm.slots[r] = ctx->comm.peers[r];
+      ctx->comm.g += (unsigned int)(n_max + a.want_eu);  // every rank advances alike
+    }
     rc = launch_resident(ctx, pw, a, dtype, deg);
     if (rc) return rc;
     OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-    OPTMC_CUDA(cudaMemcpyAsync(hfin.data(), d_final, sizeof(double) * 4 * g_now, cudaMemcpyDeviceToHost, ctx->stream));
+    OPTMC_CUDA(cudaMemcpyAsync(hfin.data(), d_final, sizeof(double) * 8 * g_now, cudaMemcpyDeviceToHost, ctx->stream));
     OPTMC_CUDA(cudaMemcpyAsync(hflags.data(), d_flags, sizeof(int) * 4 * g_now, cudaMemcpyDeviceToHost, ctx->stream));
+    if (details)
+      OPTMC_CUDA(cudaMemcpyAsync(hdet.data(), dev + off_det, det_per_group * G, cudaMemcpyDeviceToHost, ctx->stream));
     OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
     {
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->last_paths_ms += ms;
-      if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) ctx->last_sweep_ms += ms;
+      if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) acc_paths_ms += ms;
+      if (cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]) == cudaSuccess) acc_sweep_ms += ms;
     }
+    const double* hbetas = hdet.data();
+    const unsigned long long* hbnd = reinterpret_cast<const unsigned long long*>(hbetas + (size_t)G * n1 * kMaxBeta);
+    const unsigned long long* hexc = hbnd + (size_t)G * n1;
+    const long long* hnitm = reinterpret_cast<const long long*>(hexc + (size_t)G * n1);
     for (int g = 0; g < g_now; ++g) {
-      results[w0 + g].price = hfin[(size_t)g * 4];
-      results[w0 + g].stderr_ = hfin[(size_t)g * 4 + 1];
-      if (hflags[(size_t)g * 4]) {  // fixed-point exchange overflow: redo this option with the split kernels
-        const optmc_american_option& o = opts[w0 + g];
+      const int i = w0 + g;
+      const optmc_american_option& o = opts[i];
+      results[i].price = hfin[(size_t)g * 8];
+      results[i].stderr_ = hfin[(size_t)g * 8 + 1];
+      if (M_total) {
+        if (hflags[(size_t)g * 4 + 1]) { set_error("sharded batch: a peer rank did not answer (exchange timed out); re-run optmc_comm_export / optmc_comm_init on every rank"); return OPTMC_ECUDA; }
+        if (hflags[(size_t)g * 4]) { set_error("sharded batch: a Gram moment left the fixed-point exchange range (|m| < 2^43) or is not finite"); return OPTMC_EUNSUPPORTED; }
+      }
+      if (want_eu && a.want_eu) { ex->european[2 * i] = hfin[(size_t)g * 8 + 4]; ex->european[2 * i + 1] = hfin[(size_t)g * 8 + 5]; }
+      if (details) {
+        const unsigned long long none = o.is_put ? 0ull : ~0ull;
+        for (int t = 0; t <= o.N; ++t) {
+          const size_t src = (size_t)g * n1 + t, dst = (size_t)i * ex->ld_dates + t;
+          if (ex->ex_count) ex->ex_count[dst] = (int64_t)hexc[src];
+          if (ex->n_itm) ex->n_itm[dst] = (int64_t)hnitm[src];
+          if (ex->boundary) {
+            if (hbnd[src] == none) ex->boundary[dst] = nan("");
+            else memcpy(&ex->boundary[dst], &hbnd[src], 8);
+          }
+          if (ex->betas) for (int j = 0; j < 4; ++j) ex->betas[dst * 4 + j] = j <= deg ? hbetas[src * kMaxBeta + j] : nan("");
+        }
+      }
+      const bool redo = !M_total && hflags[(size_t)g * 4];  // fixed-point exchange overflow: redo with the split kernels
+      if (redo || (want_eu && !a.want_eu)) {
+        // NOTE: optmc_price_american reuses ctx->slab (safe: ensure_bytes never shrinks, and this wave's results are
+        // already on the host) and overwrites the context's event timings -- restored below from the accumulators.
         optmc_model_params m = *mp; m.S0 = o.S0; m.T = o.T;
         optmc_rng_params r = *rng; r.stream = rng->stream + o.stream;
-        optmc_lsm_params lp{o.K, mp->r, o.T, o.is_put, basis, semantics, OPTMC_SWEEP_SPLIT};
-        optmc_lsm_result res{};
-        rc = optmc_price_american(ctx, &m, &r, M, o.N, dtype, &lp, &res);
-        if (rc) return rc;
-        results[w0 + g].price = res.price; results[w0 + g].stderr_ = res.stderr_;
+        if (redo) {
+          optmc_lsm_params lp{o.K, mp->r, o.T, o.is_put, basis, semantics, OPTMC_SWEEP_SPLIT};
+          optmc_lsm_result res{};
+          rc = optmc_price_american(ctx, &m, &r, M, o.N, dtype, &lp, &res);
+          if (rc) return rc;
+          results[i].price = res.price; results[i].stderr_ = res.stderr_;
+        }
+        if (want_eu) {  // dense / split route: reduce the terminal row of the option's slab with the slab kernel
+          const char* slab_i = redo ? static_cast<const char*>(ctx->slab) : static_cast<const char*>(ctx->slab) + (size_t)g * slab_stride;
+          optmc_european_result er{};
+          rc = launch_european_slab(ctx, slab_i + (size_t)o.N * ld * es, M, dtype, o.K, mp->r, o.T, o.is_put, &er);
+          if (rc) return rc;
+          ex->european[2 * i] = er.mean; ex->european[2 * i + 1] = er.stderr_;
+        }
       }
     }
   }
+  ctx->last_paths_ms = acc_paths_ms; ctx->last_sweep_ms = acc_sweep_ms;
   return OPTMC_OK;
 }
 

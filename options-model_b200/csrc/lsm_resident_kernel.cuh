@@ -16,6 +16,7 @@ namespace optmc {
 struct ResGroup {
   const void* S;
   long long ld, M, chunk;
+  long long M_total;          // paths of the option over all ranks (= M unless the sweep is path-sharded)
   int N, is_put;
   double K, invK, disc, inv_disc, final_scale;
   double sgn, kk, c1, c2;     // storage-precision pass constants (see Store<>); exact in the storage type
@@ -25,7 +26,7 @@ struct ResGroup {
   unsigned long long* bnd;    // [(N+1)] or NULL
   unsigned long long* exc;    // [(N+1)] or NULL
   long long* nitm;            // [(N+1)] or NULL
-  double* final_out;          // [4]
+  double* final_out;          // [8]: price, stderr, sum, sum^2, European mean, European stderr (want_eu), -, -
 };
 
 // Path-sharded sweep over several GPUs: every rank runs this kernel on its block of paths and the
@@ -37,6 +38,7 @@ struct ResGroup {
 // CTAs of a rank then poll their own rank's slots until the nranks tags match and add the payloads as
 // integers, so every CTA of every rank obtains bit-identical totals.  A slot is rewritten two exchanges later,
 // which needs all ranks' pushes of exchange g + 1, which every CTA issues only after it read exchange g.
+constexpr int kCommSlotWords = 2 * kCommMaxRanks * kXchgWords;  // slot block of one option (group) on one rank
 constexpr unsigned int kCommSpinLimit = 1u << 22;  // ~seconds: a peer that never launched must not hang the GPU
 struct ResComm {
   int nranks = 1, rank = 0;
@@ -51,6 +53,7 @@ struct ResArgs {
   const ResGroup* groups;     // device array [G] for grouped launches
   int cpg;                    // CTAs per group
   int nstage, sticky;
+  int want_eu;                // speculative kernel: also reduce the European payoff of the terminal row (control variate)
   unsigned int stage_stride;  // bytes between stages in shared memory
   long long* trace;           // optional [2][(N+1)][8] phase clocks of the first and last CTA (OPTMC_TRACE)
 };
@@ -103,6 +106,9 @@ __device__ __forceinline__ double block_totals(double (&acc)[QP], double* s_red)
   return t;
 }
 
+constexpr unsigned long long kFxPoisonUnits = 1ull << 40;  // in units of 2^-4: 2^36 rows
+constexpr double kFxPoisonCount = 68719476736.0;            // 2^36
+
 // Warp 0 only.  `mine`: this CTA's total of quantity lane >> 1 (lanes < 2*QN), already in its final
 // units.  Adds it into the parity's accumulators, waits until all `ncta` CTAs have arrived and returns
 // the grid total of quantity `lane` in lanes < QN.  prev = this lane's accumulator value after the last
@@ -110,7 +116,8 @@ __device__ __forceinline__ double block_totals(double (&acc)[QP], double* s_red)
 template <int QN>
 __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long* xw, int par, int ncta,
                                                  unsigned long long& prev, int* flags, int* spins_out,
-                                                 const ResComm& cm, unsigned int seq, int cta, bool& dead) {
+                                                 const ResComm& cm, unsigned int seq, int cta, bool& dead,
+                                                 size_t slot_off = 0) {
   const int lane = threadIdx.x & 31;
   if (ncta == 1 && cm.nranks == 1) {  // the option fits one CTA: its totals are the grid totals
     if (spins_out) *spins_out = 0;
@@ -119,9 +126,18 @@ __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long
   unsigned long long sum = 0ull;
   int spins = 0;
   const bool single = cm.nranks == 1;
+  // A total that does not fit the fixed-point format (or is NaN) POISONS the exchange: 2^36 is added to the row
+  // count (quantity 0), which flows through the local and the cross-GPU sums like any other contribution, so every
+  // CTA of every rank sees a count >= kFxPoisonCount at this date and fails alike (no rank returns a price that
+  // silently misses another rank's moments).
+  unsigned long long hi, lo;
+  const bool enc_ok = fx_encode(mine, hi, lo) || lane >= 2 * QN;
+  const bool poison = !__all_sync(0xffffffffu, enc_ok);
+  if (poison && lane == 0) {
+    atomicExch(flags, 1);
+    hi += kFxPoisonUnits;
+  }
   if (lane < 2 * QN) {
-    unsigned long long hi, lo;
-    if (!fx_encode(mine, hi, lo)) atomicExch(flags, 1);
     unsigned long long* w = xw + ((size_t)par * kXchgWords + lane) * kXchgStride;
     red_relaxed_add_u64(w, (1ull << kFxCountShift) | ((lane & 1) ? lo : hi));
     if (single || cta == 0) {
@@ -142,10 +158,10 @@ __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long
         const unsigned long long pay =
             (lane & 1) ? sum : (sum - ((unsigned long long)ncta << 47) + (1ull << 55)) & kFxValueMask;
         for (int p = 0; p < cm.nranks; ++p)
-          st_relaxed_sys_u64(cm.slots[p] + (row + cm.rank) * kXchgWords + lane, tag | pay);
+          st_relaxed_sys_u64(cm.slots[p] + slot_off + (row + cm.rank) * kXchgWords + lane, tag | pay);
       }
       // all ranks' words are polled together (independent loads in flight: one L2 round trip per sweep of the slots)
-      const unsigned long long* mine_slots = cm.slots[cm.rank] + row * kXchgWords + lane;
+      const unsigned long long* mine_slots = cm.slots[cm.rank] + slot_off + row * kXchgWords + lane;
       unsigned long long v[kCommMaxRanks];
       unsigned int n = 0;
       for (;;) {
@@ -175,6 +191,14 @@ __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long
   return tot;
 }
 
+constexpr int kTraceCols = 12;
+// A stamp that cannot be issued before `dep` (a value loaded after a barrier) is available: BAR.SYNC defers its
+// blocking, so a bare clock read placed after it measures the issue of the barrier, not its completion.
+__device__ __forceinline__ long long clock_after(int dep) {
+  long long c;
+  asm volatile("{\n\t.reg .b32 t;\n\tmov.b32 t, %1;\n\tmov.u64 %0, %%clock64;\n\t}" : "=l"(c) : "r"(dep) : "memory");
+  return c;
+}
 #define OPTMC_TRACE_AT(ph)            \
   do {                                \
     if (tr) tr[(ph)] = clock64();     \
@@ -438,7 +462,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
   unsigned long long prev0 = 0ull, prev1 = 0ull;  // warp 0: accumulator baselines of the two parities
   bool comm_dead = false;                         // warp 0: a peer rank stopped answering (sharded sweeps)
   long long* const tr_base = (ga.trace && grp == 0 && tid == 0 && (cta == 0 || cta == ncta - 1))
-                                 ? ga.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * 8 : nullptr;
+                                 ? ga.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * kTraceCols : nullptr;
 
   // ---- date N: cash-flows = payoff(S[N]) (om3:616) ----
   R cf[PPT];
@@ -466,7 +490,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
   int seq = 0;
   double d_t = 1.0, dinv_t = 1.0;  // D_t and 1 / D_t of the iteration's decision date
   for (int t = N; t >= 1; --t) {
-    long long* tr = tr_base ? tr_base + (size_t)t * 8 : nullptr;
+    long long* tr = tr_base ? tr_base + (size_t)t * kTraceCols : nullptr;
     const bool gram = t >= 2;
     const bool decide = t <= N - 1 && s_valid != 0;
     const int slot_g = slot_t + 1 == nstage ? 0 : slot_t + 1;  // ring slot of the Gram date t-1
@@ -540,8 +564,10 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
       double tot[Q], beta[DEG + 1];
 #pragma unroll
       for (int q = 0; q < Q; ++q) tot[q] = __shfl_sync(0xffffffffu, tot_l, q);
-      const bool ok = solve_poly<DEG>(tot, beta);  // every lane, identical inputs: no divergence
+      const bool poisoned = !(tot[0] < kFxPoisonCount);  // see warp0_grid_sum
+      const bool ok = !poisoned && solve_poly<DEG>(tot, beta);  // every lane, identical inputs: no divergence
       if (lane == 0) {
+        if (poisoned) atomicExch(a.flags, 1);
         s_valid = ok ? 1 : 0;
         if (ok) {
           // payoff - continuation = (+-K - b0) + (-+1 - b1/K) S - (b2/K^2) S^2 ...  (x = S/K)
@@ -564,7 +590,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
         if (cta == 0 && a.betas) {
 #pragma unroll
           for (int i = 0; i <= DEG; ++i) a.betas[(size_t)(t - 1) * kMaxBeta + i] = ok ? beta[i] : nan("");
-          a.nitm[t - 1] = (long long)(tot[0] + 0.5);
+          a.nitm[t - 1] = poisoned ? 0ll : (long long)(tot[0] + 0.5);
         }
       }
       OPTMC_TRACE_AT(5);
@@ -608,12 +634,397 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
 }
 
 
+// ================================================================================================================
+// Speculative, warp-specialised form of the sparse (sticky-mask) sweep.
+//
+// Under the reference's sticky mask a path can change at date t only if it is still open AND in the money at t
+// (~0.5% of the paths): for every other path the contribution to the moments of date t-1 does not depend on
+// beta_t.  The CTA therefore runs NT compute threads plus ONE communication warp:
+//   compute warps, iteration t:   S(t)  speculative pass -- moments of date t-1 of the paths that are not
+//                                        candidates at t; candidates (open & in the money at t) go to a bit mask
+//                                 wait  beta_t                                   (named barrier BETA)
+//                                 C(t)  candidates only: decision of date t, their share of the moments of t-1
+//                                 warp reduce-scatter -> shared memory, arrive   (named barrier TOT)
+//   communication warp, iteration t:  arrive BETA (beta_t is in shared memory) ... wait TOT: CTA totals,
+//                                 exchange statistics, refill the stage ring (TMA), grid-wide sum (and the NVLink
+//                                 exchange of a path-sharded sweep), solve beta_(t-1) -> shared memory.
+// S(t-1) of the compute warps runs while the communication warp is in the exchange + solve of beta_(t-1): the
+// per-date critical path is  C + warp reduce + exchange + solve  instead of  pass + reduce + exchange + solve +
+// barrier (profiles/trace_summary_r2.txt).  Decisions, moments and prices are those of lsm_resident_kernel
+// (same arithmetic per path; the grid sum is order-independent), so the parity tests cover both.
+// ================================================================================================================
+// Barrier ids and thread counts are IMMEDIATES: ptxas sizes the CTA's barrier allocation from the ids it can see
+// (with register operands it reports "used 1 barriers" and barriers 1, 2 do not block).
+template <int ID, int NTHREADS> __device__ __forceinline__ void named_bar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory");
+}
+template <int ID, int NTHREADS> __device__ __forceinline__ void named_bar_arrive() {
+  asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory");
+}
+constexpr int kBarBeta = 1, kBarTot = 2;
+
+// S(t): no beta needed.  cand gets bit k for every path that is open and in the money at date t.
+template <typename R, int DEG, int PPT, int NT, bool DECIDE, bool GRAM>
+__device__ __forceinline__ void spec_pass(const R (&cf)[PPT], const R* __restrict__ st_t, const R* __restrict__ st_g,
+                                          const PassConsts<R>& pc, double (&mom)[Moments<DEG>::Q], unsigned int& rows,
+                                          typename MaskOf<(PPT > 32)>::type& cand) {
+  typedef typename MaskOf<(PPT > 32)>::type Mask;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const int j = tid + k * NT;
+    const R c = cf[k];
+    const bool open = !Store<R>::flagged(c, pc.flag);
+    const R st = DECIDE ? st_t[j] : (R)0;
+    const R sg = GRAM ? st_g[j] : (R)0;
+    const bool lt = DECIDE & open & (pc.sgn * st > pc.kk);
+    const bool lg = GRAM & open & (pc.sgn * sg > pc.kk);
+    if (__any_sync(0xffffffffu, lt | lg)) {
+      cand |= lt ? ((Mask)1 << k) : (Mask)0;
+      if (GRAM) {
+        const bool live = lg & !lt;  // not a candidate: its cash-flow cannot change at date t
+        const R y = c * pc.dg;       // live lanes are unflagged: c >= 0
+        rows += live ? 1u : 0u;
+        moments_accumulate_nocount<DEG>(mom, (double)(live ? sg : (R)0), (double)(live ? y : (R)0));
+      }
+    }
+  }
+}
+
+// C(t): the candidates, once beta_t is known (valid = the regression of date t succeeded).
+template <typename R, int DEG, int PPT, int NT, bool GRAM>
+__device__ __forceinline__ void cand_pass(R (&cf)[PPT], const R* __restrict__ st_t, const R* __restrict__ st_g,
+                                          const HitConsts<R, DEG>& dec, const PassConsts<R>& pc, bool valid,
+                                          double (&mom)[Moments<DEG>::Q], unsigned int& rows, unsigned int& cnt, R& em,
+                                          typename MaskOf<(PPT > 32)>::type cand) {
+  typedef typename MaskOf<(PPT > 32)>::type Mask;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const bool lt = (cand >> k) & (Mask)1;
+    if (__any_sync(0xffffffffu, lt)) {
+      const int j = tid + k * NT;
+      const R st = st_t[j];
+      bool sure;
+      bool pos = dec.fast(st, sure);
+      if (valid & lt & !sure) pos = dec.exact(st);  // rare: within fp32 rounding of the exercise boundary
+      const bool exer = valid & lt & pos;
+      const R pay = Store<R>::with_flag((fma(pc.sgn, st, pc.c1) + pc.c2) * pc.dinv, pc.flag);
+      R c = cf[k];
+      c = exer ? pay : c;
+      cf[k] = c;
+      cnt += exer ? 1u : 0u;
+      em = fmax(em, exer ? -(pc.sgn * st) : (R)-INFINITY);
+      if (GRAM) {
+        const R sg = st_g[j];
+        const bool live = lt & !exer & (pc.sgn * sg > pc.kk);
+        const R y = c * pc.dg;
+        rows += live ? 1u : 0u;
+        moments_accumulate_nocount<DEG>(mom, (double)(live ? sg : (R)0), (double)(live ? y : (R)0));
+      }
+    }
+  }
+}
+
+template <typename R, int DEG, int PPT, int NT>
+__global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const ResArgs ga) {
+  constexpr int Q = Moments<DEG>::Q;
+  constexpr int QP = Pow2<Q>::v;
+  constexpr int NW = NT / 32;
+  constexpr int NALL = NT + 32;
+  typedef typename MaskOf<(PPT > 32)>::type Mask;
+  static_assert(Q <= kXchgMaxQ, "Gram vector must fit the exchange buffer");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t mbar[3];
+  __shared__ double s_red[NW * 16];
+  __shared__ double s_dec[DEG + 1];     // exercise iff s_dec(s) > 0  (payoff - continuation as a polynomial in S)
+  __shared__ float s_hit[2 * DEG + 4];  // fp32 sweep: f[], b[] of s_dec (HitConsts); the discount slots are unused here
+  __shared__ int s_valid;
+  __shared__ unsigned long long s_bnd[2];
+  __shared__ unsigned int s_cnt[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_comm = warp == NW;
+  const int grp = blockIdx.x / ga.cpg;
+  const ResGroup a = ga.groups ? ga.groups[grp] : ga.one;
+  const int cta = blockIdx.x - grp * ga.cpg, ncta = ga.cpg;
+  const long long base = (long long)cta * a.chunk;
+  const long long rem = a.M - base;
+  const int n_local = (int)(rem < a.chunk ? rem : a.chunk);
+  const unsigned int bytes = (unsigned int)((size_t)n_local * sizeof(R));  // multiple of 16 (planner)
+  const bool is_put = a.is_put != 0;
+  const R sgn = (R)a.sgn, kk = (R)a.kk, c1 = (R)a.c1, c2 = (R)a.c2;
+  const unsigned int flag = 0x80000000u;  // sticky semantics only
+  const int N = a.N, nstage = ga.nstage;
+  const R* Sbase = static_cast<const R*>(a.S) + base;
+  const ResComm& cm = ga.comm;
+  // grouped + path-sharded: every group owns its own slot block on every rank
+  const size_t slot_off = ga.groups ? (size_t)grp * kCommSlotWords : 0;
+
+  auto slot_ptr = [&](int slot) -> R* { return reinterpret_cast<R*>(smem_raw + (size_t)slot * ga.stage_stride); };
+  auto issue_load = [&](int t, int slot) {  // one thread
+    uint64_t* bar = &mbar[slot];
+    mbar_arrive_expect_tx(bar, bytes);
+    bulk_load_1d(smem_raw + (size_t)slot * ga.stage_stride, Sbase + (size_t)t * a.ld, bytes, bar);
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
+    mbar_fence_init();
+    s_bnd[0] = s_bnd[1] = bnd_none(a.is_put);
+    s_cnt[0] = s_cnt[1] = 0u;
+    s_valid = 0;
+#pragma unroll
+    for (int i = 0; i < 2 * DEG + 4; ++i) s_hit[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i <= DEG; ++i) s_dec[i] = 0.0;
+  }
+  {  // out-of-the-money sentinel behind the slice in every stage (the bulk copies never touch it)
+    const R sentinel = is_put ? (R)INFINITY : (R)-INFINITY;
+    for (int s = 0; s < nstage; ++s)
+      for (int i = n_local + tid; i < PPT * NT; i += NALL) slot_ptr(s)[i] = sentinel;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < nstage; ++i)
+      if (N - i >= 1) issue_load(N - i, i);
+  }
+  long long* const tr_base = (ga.trace && grp == 0 && (cta == 0 || cta == ncta - 1))
+                                 ? ga.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * kTraceCols : nullptr;
+
+  if (is_comm) {
+    // ---------------------------------------------------------------------------------------------------------
+    // communication warp: CTA totals -> grid-wide sum -> solve; never touches a path
+    // ---------------------------------------------------------------------------------------------------------
+    double qscale = 1.0;  // lane l serves quantity l >> 1; raw-price moments are rescaled to x = S/K
+    {
+      const int pw = moment_power<DEG>(lane >> 1);
+      for (int i = 0; i < pw; ++i) qscale *= a.invK;
+    }
+    unsigned long long prev0 = 0ull, prev1 = 0ull;
+    bool comm_dead = false;
+    int seq = 0, slot_t = 0;
+    double d_t = 1.0, dinv_t = 1.0;
+    auto cta_totals = [&](int qp) -> double {  // lane -> quantity lane % qp; sums the warps' partials in a fixed order
+      const int G = 32 / qp;
+      const int q = lane % qp, g = lane / qp;
+      double v = 0.0;
+      for (int w = g; w < NW; w += G) v += s_red[w * qp + q];
+      for (int m = qp; m <= 16; m <<= 1) v += shfl_xor_f64(v, m);
+      return __shfl_sync(0xffffffffu, v, (lane >> 1) % qp);
+    };
+    auto flush_stats = [&](int t) {  // lane 0: exercise statistics of date t (collected by the compute warps)
+      if (s_cnt[0]) {
+        if (a.exc) atomicAdd(a.exc + t, (unsigned long long)s_cnt[0]);
+        if (a.bnd) {
+          if (is_put) atomicMax(a.bnd + t, s_bnd[0]); else atomicMin(a.bnd + t, s_bnd[0]);
+        }
+        s_cnt[0] = 0u;
+        s_bnd[0] = bnd_none(a.is_put);
+      }
+    };
+    if (ga.want_eu) {  // European leg on the option's own paths (om3:653-677): exp(-rT) payoff(S_N), summed like the price
+      named_bar_sync<kBarTot, NALL>();
+      const double mine = cta_totals(2);
+      unsigned long long pv = prev0;
+      const double tot_l = warp0_grid_sum<2>(mine, a.xw, 0, ncta, pv, a.flags, nullptr, cm, 0u, cta, comm_dead, slot_off);
+      prev0 = pv;
+      const double s1 = __shfl_sync(0xffffffffu, tot_l, 0), s2 = __shfl_sync(0xffffffffu, tot_l, 1);
+      if (cta == 0 && lane == 0) {
+        const double n = (double)a.M_total;
+        const double mean = s1 / n;
+        double var = n > 1.0 ? (s2 - n * mean * mean) / (n - 1.0) : 0.0;
+        if (var < 0.0) var = 0.0;
+        double df = 1.0;
+        for (int i = 0; i < N; ++i) df *= a.disc;
+        a.final_out[4] = mean * df;
+        a.final_out[5] = sqrt(var / n) * df;
+      }
+      seq = 1;
+    }
+    for (int t = N; t >= 1; --t) {
+      long long* tr = (tr_base && lane == 0) ? tr_base + (size_t)t * kTraceCols : nullptr;
+      if (tr) tr[10] = clock64();
+      named_bar_arrive<kBarBeta, NALL>();  // beta_t (or "none" at t = N) is in shared memory
+      d_t *= a.disc;
+      dinv_t *= a.inv_disc;
+      if (t == 1) break;
+      named_bar_sync<kBarTot, NALL>();     // every compute warp is done with date t; partials are in s_red
+      if (tr) tr[0] = clock_after(*(volatile int*)&s_cnt[1]);
+      const double mine = cta_totals(QP) * qscale;
+      if (tr) tr[9] = clock_after(__double2loint(mine));
+      if (lane == 0) {
+        flush_stats(t);
+        if (t - nstage >= 1) issue_load(t - nstage, slot_t);  // refill the slot date t vacated
+      }
+      int spins = 0;
+      unsigned long long pv = (seq & 1) ? prev1 : prev0;
+      const double tot_l = warp0_grid_sum<Q>(mine, a.xw, seq & 1, ncta, pv, a.flags, &spins, cm, (unsigned int)seq, cta, comm_dead, slot_off);
+      if (seq & 1) prev1 = pv; else prev0 = pv;
+      OPTMC_TRACE_AT(4);
+      if (tr) tr[7] = spins;
+      double tot[Q], beta[DEG + 1];
+#pragma unroll
+      for (int q = 0; q < Q; ++q) tot[q] = __shfl_sync(0xffffffffu, tot_l, q);
+      const bool poisoned = !(tot[0] < kFxPoisonCount);  // some CTA / rank could not encode its totals (or NaN)
+      const bool ok = !poisoned && solve_poly<DEG>(tot, beta);  // every lane, identical inputs: no divergence
+      if (lane == 0) {
+        if (poisoned) atomicExch(a.flags, 1);
+        s_valid = ok ? 1 : 0;
+        if (ok) {
+          // payoff - continuation = (+-K - b0) + (-+1 - b1/K) S - (b2/K^2) S^2 ...  (x = S/K)
+          double sc = 1.0;
+#pragma unroll
+          for (int i = 0; i <= DEG; ++i) {
+            double d = -beta[i] * sc;
+            if (i == 0) d += is_put ? a.K : -a.K;
+            if (i == 1) d += is_put ? -1.0 : 1.0;
+            s_dec[i] = d;
+            const float f = (float)d;
+            s_hit[i] = f;
+            s_hit[DEG + 1 + i] = fabsf(f) * 4.76837158203125e-7f;  // 8 * 2^-24, as Decider<float>::load
+            sc *= a.invK;
+          }
+        }
+        if (cta == 0 && a.betas) {
+#pragma unroll
+          for (int i = 0; i <= DEG; ++i) a.betas[(size_t)(t - 1) * kMaxBeta + i] = ok ? beta[i] : nan("");
+          a.nitm[t - 1] = poisoned ? 0ll : (long long)(tot[0] + 0.5);
+        }
+      }
+      OPTMC_TRACE_AT(5);
+      ++seq;
+      slot_t = slot_t + 1 == nstage ? 0 : slot_t + 1;
+    }
+    // ---- final reduction: mean and standard error of the cash-flows (om3:651) ----
+    named_bar_sync<kBarTot, NALL>();
+    const double mine = cta_totals(2);
+    if (lane == 0) flush_stats(1);
+    unsigned long long pv = (seq & 1) ? prev1 : prev0;
+    const double tot_l = warp0_grid_sum<2>(mine, a.xw, seq & 1, ncta, pv, a.flags, nullptr, cm, (unsigned int)seq, cta, comm_dead, slot_off);
+    const double s1 = __shfl_sync(0xffffffffu, tot_l, 0), s2 = __shfl_sync(0xffffffffu, tot_l, 1);
+    if (cta == 0 && lane == 0) {
+      const double n = (double)a.M_total;
+      const double mean = s1 / n;
+      double var = n > 1.0 ? (s2 - n * mean * mean) / (n - 1.0) : 0.0;
+      if (var < 0.0) var = 0.0;
+      const double scale = d_t * a.inv_disc * a.final_scale;  // D_1 (N - 1 discounts, om3:651), one more under TEXTBOOK
+      a.final_out[0] = mean * scale;
+      a.final_out[1] = sqrt(var / n) * scale;
+      a.final_out[2] = s1;
+      a.final_out[3] = s2;
+    }
+    return;
+  }
+
+  // -----------------------------------------------------------------------------------------------------------
+  // compute warps
+  // -----------------------------------------------------------------------------------------------------------
+  R cf[PPT];
+  int slot_t = 0;           // ring slot of the iteration's decision date
+  unsigned int phase = 0u;  // bit s: mbarrier phase parity the next wait on slot s expects
+  auto wait_slot = [&](int slot) {
+    mbar_wait(&mbar[slot], (phase >> slot) & 1u);
+    phase ^= 1u << slot;
+  };
+  wait_slot(0);
+  {  // date N: cash-flows = payoff(S[N]) (om3:616)
+    const R* st = slot_ptr(0);
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const R s = st[tid + k * NT];  // sentinel past the slice: out of the money -> 0
+      const R p = fma(sgn, s, c1) + c2;
+      cf[k] = (sgn * s > kk) ? p : (R)0;
+    }
+  }
+  if (ga.want_eu) {
+    double eu[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const double c = (double)cf[k];
+      eu[0] += c;
+      eu[1] += c * c;
+    }
+    warp_reduce_scatter<2>(eu, lane);
+    if (reduce_scatter_owner<2>(lane)) s_red[warp * 2 + reduce_scatter_index<2>(lane)] = eu[0];
+    named_bar_arrive<kBarTot, NALL>();
+  }
+  double d_t = 1.0, dinv_t = 1.0;  // D_t and 1 / D_t of the iteration's decision date
+  for (int t = N; t >= 1; --t) {
+    // stamps from a warp on the communication warp's scheduler (NW % 4 == 3): clock64 is read per scheduler partition
+    long long* tr = (tr_base && tid == 96) ? tr_base + (size_t)t * kTraceCols : nullptr;
+    const bool gram = t >= 2;
+    const int slot_g = slot_t + 1 == nstage ? 0 : slot_t + 1;  // ring slot of the Gram date t-1
+    if (gram) wait_slot(slot_g);
+    const R* st_t = slot_ptr(slot_t);
+    const R* st_g = slot_ptr(gram ? slot_g : slot_t);
+    double mom[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) mom[q] = 0.0;
+    unsigned int rows = 0, cnt = 0;
+    R em = (R)-INFINITY;  // max over exercised paths of -sgn * S: put -> max S, call -> -(min S)
+    const PassConsts<R> pc{sgn, kk, c1, c2, (R)dinv_t, (R)(d_t * a.disc), flag, n_local};
+    Mask cand = 0;
+    if (tr) tr[6] = clock64();  // stage ready: S(t) starts
+    if (t == N) spec_pass<R, DEG, PPT, NT, false, true>(cf, st_t, st_g, pc, mom, rows, cand);
+    else if (gram) spec_pass<R, DEG, PPT, NT, true, true>(cf, st_t, st_g, pc, mom, rows, cand);
+    else spec_pass<R, DEG, PPT, NT, true, false>(cf, st_t, st_g, pc, mom, rows, cand);
+    if (tr) tr[1] = clock_after((int)rows);
+    named_bar_sync<kBarBeta, NALL>();  // beta_t is in shared memory
+    if (tr) tr[2] = clock_after(*(volatile int*)&s_valid);
+    if (t < N) {
+      HitConsts<R, DEG> hc;
+      if constexpr (sizeof(R) == 4) { hc.d = s_dec; hc.c = s_hit; }
+      else { hc.dec.load(s_dec, true); hc.dinv_ = pc.dinv; hc.dg_ = pc.dg; }
+      const bool valid = s_valid != 0;
+      if (gram) cand_pass<R, DEG, PPT, NT, true>(cf, st_t, st_g, hc, pc, valid, mom, rows, cnt, em, cand);
+      else cand_pass<R, DEG, PPT, NT, false>(cf, st_t, st_g, hc, pc, valid, mom, rows, cnt, em, cand);
+      if (tr) tr[8] = clock_after((int)rows + (int)cnt);
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt) {  // warp-uniform
+        const double ext = -(double)sgn * (double)em;
+        unsigned long long b = (unsigned long long)__double_as_longlong(ext);
+        if (!isfinite(ext)) b = bnd_none(a.is_put);
+        b = is_put ? warp_max_u64(b) : warp_min_u64(b);
+        if (lane == 0) {
+          atomicAdd(&s_cnt[0], cnt);
+          if (is_put) atomicMax(&s_bnd[0], b); else atomicMin(&s_bnd[0], b);
+        }
+      }
+    }
+    d_t *= a.disc;
+    dinv_t *= a.inv_disc;
+    if (!gram) break;
+    double acc[QP];
+    mom[0] = (double)rows;
+#pragma unroll
+    for (int q = 0; q < QP; ++q) acc[q] = q < Q ? mom[q] : 0.0;
+    warp_reduce_scatter<QP>(acc, lane);
+    if (reduce_scatter_owner<QP>(lane)) s_red[warp * QP + reduce_scatter_index<QP>(lane)] = acc[0];
+    if (tr) tr[3] = clock_after(__double2loint(acc[0]));
+    named_bar_arrive<kBarTot, NALL>();
+    slot_t = slot_g;
+  }
+  // ---- final reduction ----
+  double fin[2] = {0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < PPT; ++k) {
+    const double c = fabs((double)cf[k]);  // slots past the slice hold 0
+    fin[0] += c;
+    fin[1] += c * c;
+  }
+  warp_reduce_scatter<2>(fin, lane);
+  if (reduce_scatter_owner<2>(lane)) s_red[warp * 2 + reduce_scatter_index<2>(lane)] = fin[0];
+  named_bar_arrive<kBarTot, NALL>();
+}
+
 // ---- launch table (one translation unit per storage precision) -------------------------------------------
 struct ResPlan {
   int ncta = 0;     // CTAs per option (group)
   int ngroups = 1;  // options swept by one launch
   int ppt = 0, nstage = 0, nt = 0;
   bool sparse = false;  // vote-skip passes (sticky semantics: few live paths per date)
+  bool spec = false;    // sparse only: speculative, warp-specialised kernel (NT compute threads + 1 communication warp)
   long long chunk = 0;
   unsigned int stage_stride = 0;
   size_t smem = 0;
@@ -637,7 +1048,32 @@ int launch_resident_t(optmc_ctx* ctx, const ResPlan& p, ResArgs& a) {
   X(512, 1) X(512, 2) X(512, 4) X(512, 8) X(512, 12) X(512, 14) X(512, 16) X(512, 20) X(512, 24) X(512, 28) \
   X(512, 32) X(512, 40) X(512, 48) X(768, 36) X(512, 54)
 
+template <typename R, int DEG, int PPT, int NT>
+int launch_resident_spec_t(optmc_ctx* ctx, const ResPlan& p, ResArgs& a) {
+  auto kern = lsm_resident_spec_kernel<R, DEG, PPT, NT>;
+  OPTMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  void* args[] = {(void*)&a};
+  OPTMC_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(p.ncta * p.ngroups), dim3(NT + 32), args, p.smem, ctx->stream));
+  ctx->launches++; ctx->sw.n_launches++;
+  return OPTMC_OK;
+}
+
+// Shapes of the speculative kernel: (compute threads, paths per thread); the CTA has 32 more threads (the
+// communication warp), so that the warp count stays a multiple of four -- registers are partitioned per scheduler,
+// and a 17th / 25th warp would cost every thread of the CTA a fifth of its registers.
+#define OPTMC_RES_SPEC_SHAPES(X) \
+  X(480, 1) X(480, 2) X(480, 4) X(480, 8) X(480, 12) X(480, 15) X(480, 16) X(480, 20) X(480, 24) X(480, 28) \
+  X(480, 32) X(480, 40) X(480, 48) X(736, 37) X(480, 56)
+
 template <typename R, int DEG> int launch_resident_shape(optmc_ctx* ctx, const ResPlan& p, ResArgs& a) {
+  if (p.spec) {
+#define X(NT_, PPT_) \
+    if (p.nt == NT_ && p.ppt == PPT_) return launch_resident_spec_t<R, DEG, PPT_, NT_>(ctx, p, a);
+    OPTMC_RES_SPEC_SHAPES(X)
+#undef X
+    set_error("no speculative resident instantiation for this slice size");
+    return OPTMC_EUNSUPPORTED;
+  }
 #define X(NT_, PPT_)                                                                       \
   if (p.nt == NT_ && p.ppt == PPT_)                                                        \
     return p.sparse ? launch_resident_t<R, DEG, PPT_, NT_, true>(ctx, p, a)                \

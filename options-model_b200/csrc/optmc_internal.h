@@ -19,6 +19,7 @@ constexpr int kMaxResidentCtas = 160; // CTAs of the persistent sweep (B200: 148
 // by L2 request count on the hot lines, not by atomic throughput.
 constexpr int kXchgWords = 2 * kXchgMaxQ;
 constexpr int kCommMaxRanks = 8;   // ranks of a path-sharded sweep (optmc_comm_*)
+constexpr int kCommMaxGroups = 16; // options of one path-sharded grouped launch (one slot block each)
 constexpr int kXchgStride = 1;
 inline size_t xchg_bytes() { return (size_t)2 * kXchgWords * kXchgStride * sizeof(unsigned long long); }
 constexpr int kMaxBeta = 4;
@@ -128,9 +129,11 @@ size_t path_args_bytes();
 int ivnet_sigma_batch(optmc_ctx* ctx, const optmc_ivnet* net, double tau, const double* S_dev, int64_t n, double* sigma_dev);
 int launch_paths_localvol(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, const optmc_ivnet* net,
                           int64_t M, int32_t N, int32_t dtype, void* S, int64_t ld);
-int launch_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
-                       int32_t dtype, int G, const optmc_american_option* opts, void* slab, size_t slab_stride_bytes,
-                       int64_t ld, void* d_args, void* h_args);
+int prepare_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M, int G,
+                        const optmc_american_option* opts, void* slab, size_t slab_stride_bytes, int64_t ld, void* d_args,
+                        void* h_args);
+int launch_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, int32_t dtype, int G, void* slab,
+                       size_t slab_stride_bytes, int64_t ld, void* d_args, void* h_args);
 int launch_philox_normals(optmc_ctx* ctx, const optmc_rng_params* rng, int32_t model, int64_t M, int32_t N,
                           int32_t which, int32_t dtype, void* Z);
 int launch_philox_kat(optmc_ctx* ctx, int n, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
@@ -151,7 +154,7 @@ int sweep_resident(optmc_ctx* ctx);                                 // one coope
 // grouped persistent sweep of a batch (lsm_resident.cu)
 int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                          int32_t dtype, int32_t basis, uint32_t semantics, int32_t n_options,
-                         const optmc_american_option* opts, optmc_price_result* results);
+                         const optmc_american_option* opts, optmc_price_result* results, optmc_batch_extras* ex);
 
 // lsm_global.cu
 int lsm_global(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype,

@@ -465,9 +465,11 @@ template <typename R, int VEC> static void launch_batch_scheme(int scheme, dim3 
 
 size_t path_args_bytes() { return sizeof(PathArgs); }
 
-int launch_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
-                       int32_t dtype, int G, const optmc_american_option* opts, void* slab, size_t slab_stride_bytes,
-                       int64_t ld, void* d_args, void* h_args) {
+// Two halves so that the caller can time the kernel alone: prepare = fill the per-option descriptors and copy them
+// to the device, launch = the batched generation kernel.
+int prepare_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M, int G,
+                        const optmc_american_option* opts, void* slab, size_t slab_stride_bytes, int64_t ld, void* d_args,
+                        void* h_args) {
   PathArgs* h = static_cast<PathArgs*>(h_args);
   for (int g = 0; g < G; ++g) {
     optmc_model_params m = *mp;
@@ -483,6 +485,12 @@ int launch_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc
     h[g].ld = ld;
   }
   OPTMC_CUDA(cudaMemcpyAsync(d_args, h, sizeof(PathArgs) * G, cudaMemcpyHostToDevice, ctx->stream));
+  return OPTMC_OK;
+}
+
+int launch_paths_batch(optmc_ctx* ctx, const optmc_model_params* mp, int32_t dtype, int G, void* slab,
+                       size_t slab_stride_bytes, int64_t ld, void* d_args, void* h_args) {
+  const PathArgs* h = static_cast<const PathArgs*>(h_args);
   const long long Mh = h[0].Mh;
   const bool vec4 = (Mh % 4 == 0) && (ld % 4 == 0) && ((uintptr_t)slab % 16 == 0) && (slab_stride_bytes % 16 == 0);
   const long long units = vec4 ? Mh / 4 : Mh;

@@ -1,4 +1,12 @@
-"""Dump per-date phase clocks of the resident sweep (OPTMC_TRACE) and print a per-phase summary (cycles)."""
+"""Dump per-date phase clocks of the resident sweep (OPTMC_TRACE) and print a per-phase summary (SM cycles).
+
+  python tools/trace_resident.py [out] [M] [N] [semantics] [max_ctas]
+
+Speculative kernel (sticky semantics, default): stamps of thread 96 (compute) 6 = S(t) starts, 1 = S(t) done, 2 = beta_t seen (BETA
+barrier passed), 3 = C(t) + warp reduce done; of the communication warp 0 = TOT barrier passed (all warps done with date
+t), 4 = grid-wide sum complete, 5 = beta_(t-1) solved.  Single-role kernel (OPTMC_RES_SPEC=0 or textbook semantics):
+0 pass start, 1 pass done, 2 CTA totals in warp 0, 4 grid sum complete, 5 solved.
+"""
 import os
 import sys
 
@@ -9,6 +17,8 @@ out = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/trace.txt"
 M = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 N = int(sys.argv[3]) if len(sys.argv) > 3 else 252
 SEM = sys.argv[4] if len(sys.argv) > 4 else "reference"
+if len(sys.argv) > 5:
+    os.environ["OPTMC_RES_MAXCTAS"] = sys.argv[5]
 from options_model_b200 import engine as E  # noqa: E402
 
 eng = E.Engine(0)
@@ -18,20 +28,43 @@ eng.lsm(S, 100.0, 0.05, 1.0, "put", semantics=SEM, impl="resident")  # warm
 os.environ["OPTMC_TRACE"] = out
 r = eng.lsm(S, 100.0, 0.05, 1.0, "put", semantics=SEM, impl="resident")
 del os.environ["OPTMC_TRACE"]
-print("price", r.price)
+print("price", r.price, open(out).readline().strip())
 rows = np.loadtxt(out, comments="#")
-# iteration t: stamps 0 pass start (beta visible, stage ready), 1 fused decide+Gram pass done, 2 CTA totals in
-# warp 0 (sync A), 4 grid sum complete, 5 solved; the next iteration's stamp 0 closes sync B + stage wait.
-cols = [0, 1, 2, 4, 5]
-names = ["fused decide+gram pass", "block reduce (sync A)", "publish + grid sum", "solve", "sync B + stage wait"]
+spec = SEM == "reference" and os.environ.get("OPTMC_RES_SPEC", "1") != "0"
+
+
+def med(x):
+    return f"median {np.median(x):8.0f}  p90 {np.percentile(x, 90):8.0f}"
+
+
 for c in (0, 1):
-    a = rows[rows[:, 0] == c][:, 2:]
-    a = a[(a[:, 0] > 0) & (a[:, 5] > 0)]
-    per_date = a[1:, 0] - a[:-1, 0]
-    print(f"cta {'first' if c == 0 else 'last'}: per-date total {np.median(per_date):.0f} cycles; spins median "
-          f"{np.median(a[:, 7]):.0f} p90 {np.percentile(a[:, 7], 90):.0f}")
-    d = np.diff(a[:, cols], axis=1)
-    for k in range(4):
-        print(f"   {names[k]:24s} median {np.median(d[:, k]):8.0f}  p90 {np.percentile(d[:, k], 90):8.0f}")
-    nxt = a[1:, 0] - a[:-1, 5]
-    print(f"   {names[4]:24s} median {np.median(nxt):8.0f}  p90 {np.percentile(nxt, 90):8.0f}")
+    a = rows[rows[:, 0] == c][:, 2:]  # rows ordered t = N .. 1
+    a = a[(a[:, 5] > 0)]
+    if spec:
+        a = a[(a[:, 1] > 0) & (a[:, 3] > 0)]
+        per_date = a[1:, 5] - a[:-1, 5]
+        print(f"cta {'first' if c == 0 else 'last'}: per-date total {med(per_date)} cycles; spins {med(a[:, 7])}")
+        print(f"   S(t) pass                  (1 - 6)        {med(a[:, 1] - a[:, 6])}")
+        print(f"   stage wait before S(t-1)   (6[t-1] - 3[t]) {med(a[1:, 6] - a[:-1, 3])}")
+        print(f"   BETA arrive -> beta seen   (2 - 10)       {med(a[:, 2] - a[:, 10])}")
+        print(f"   C(t) candidates            (8 - 2)        {med(a[1:, 8] - a[1:, 2])}")
+        print(f"   stats + warp reduce        (3 - 8)        {med(a[1:, 3] - a[1:, 8])}")
+        print(f"   CTA totals                 (9 - 0)        {med(a[:, 9] - a[:, 0])}")
+        print(f"   grid sum                   (4 - 9)        {med(a[:, 4] - a[:, 9])}")
+        print(f"   C(t) + warp reduce        (3 - 2)        {med(a[:, 3] - a[:, 2])}")
+        print(f"   TOT barrier (slowest warp) (0 - 3)        {med(a[:, 0] - a[:, 3])}")
+        print(f"   CTA totals + grid sum      (4 - 0)        {med(a[:, 4] - a[:, 0])}")
+        print(f"   solve                      (5 - 4)        {med(a[:, 5] - a[:, 4])}")
+        print(f"   beta_t seen after solved   (2[t-1] - 5[t]) {med(a[1:, 2] - a[:-1, 5])}")
+        print(f"   S(t-1) done after TOT(t)   (1[t-1] - 0[t]) {med(a[1:, 1] - a[:-1, 0])}   (negative: S finished before)")
+        print(f"   S(t-1) done vs beta solved (1[t-1] - 5[t]) {med(a[1:, 1] - a[:-1, 5])}   (positive: the pass, not the exchange, is critical)")
+    else:
+        a = a[(a[:, 0] > 0)]
+        per_date = a[1:, 0] - a[:-1, 0]
+        print(f"cta {'first' if c == 0 else 'last'}: per-date total {med(per_date)} cycles; spins {med(a[:, 7])}")
+        cols = [0, 1, 2, 4, 5]
+        names = ["fused decide+gram pass", "block reduce (sync A)", "publish + grid sum", "solve"]
+        d = np.diff(a[:, cols], axis=1)
+        for k in range(4):
+            print(f"   {names[k]:24s} {med(d[:, k])}")
+        print(f"   {'sync B + stage wait':24s} {med(a[1:, 0] - a[:-1, 5])}")
