@@ -234,7 +234,7 @@ int optmc_ctx_destroy(optmc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->slab); cudaFree(ctx->cf); cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->gram);
   cudaFree(ctx->d_betas); cudaFree(ctx->d_bnd); cudaFree(ctx->d_exc); cudaFree(ctx->d_nitm); cudaFree(ctx->d_valid);
-  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->gnet_rows); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
+  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->spill); cudaFree(ctx->gnet_rows); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
   for (int r = 0; r < 8; ++r) if (ctx->comm.opened[r]) cudaIpcCloseMemHandle(ctx->comm.peers[r]);
   cudaFree(ctx->comm.local);
   for (int i = 0; i < 3; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -286,7 +286,7 @@ int optmc_workspace_bytes(int64_t M, int32_t N, int32_t dtype, int32_t n_options
 
 int optmc_ctx_workspace_bytes(optmc_ctx* ctx, int64_t* bytes) {
   if (!ctx || !bytes) { set_error("null argument"); return OPTMC_EINVAL; }
-  *bytes = (int64_t)(ctx->slab_bytes + ctx->cf_bytes + ctx->partials_bytes + ctx->batch_dev_cap + ctx->gnet_rows_cap + ctx->eu_out_cap +
+  *bytes = (int64_t)(ctx->slab_bytes + ctx->cf_bytes + ctx->partials_bytes + ctx->batch_dev_cap + ctx->spill_bytes + ctx->gnet_rows_cap + ctx->eu_out_cap +
                      ctx->eu_par_cap + ctx->eu_tickets_cap +
                      ctx->per_date_cap * (kMaxBeta * sizeof(double) + 2 * sizeof(unsigned long long) + sizeof(long long) + sizeof(int)) +
                      xchg_bytes() + 1024 * sizeof(unsigned int) + 20 * sizeof(double) + 4 * sizeof(int));

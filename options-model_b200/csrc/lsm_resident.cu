@@ -44,8 +44,19 @@ static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int 
   // speculative, warp-specialised kernel.  Tuning aids: OPTMC_RES_SPARSE=0|1, OPTMC_RES_SPEC=0 (single-role kernel).
   p->sparse = sticky;
   if (const char* e = getenv("OPTMC_RES_SPARSE")) p->sparse = atoi(e) != 0;
-  p->spec = false;  // TEMP: off until the list-based candidate pass lands
+  p->spec = p->sparse;
   if (const char* e = getenv("OPTMC_RES_SPEC")) p->spec = p->sparse && atoi(e) != 0;
+  // Measured (profiles/sweep_bench_r2.txt): the speculative kernel wins where the per-date dependency chain, not the
+  // scan, bounds a date -- slices of up to ~7 k paths per CTA (one 1 M-path option on the whole machine: 0.80 vs
+  // 0.86 ms) -- and loses on larger slices, whose scan is issue-bound (13.5 k paths: 1.23 vs 1.15 ms; the 27 k-path
+  // slices of grouped launches: 2.57 vs 1.61 ms): those keep the single-role kernel.
+  if (p->spec && !getenv("OPTMC_RES_SPEC")) {
+    long long nc = (M + 479) / 480;
+    const int cap = ctx->sm_count < max_ctas ? ctx->sm_count : max_ctas;
+    if (nc > cap) nc = cap;
+    const long long ch = ((M + nc - 1) / nc + 3) / 4 * 4;
+    if (ch > 480 * 16) p->spec = false;
+  }
   const int wide = p->spec ? 736 : 768, narrow = p->spec ? 480 : 512;
   long long ncta = (M + narrow - 1) / narrow;  // at least one path per thread before adding CTAs
   if (ncta > ncta_cap) ncta = ncta_cap;
@@ -121,6 +132,7 @@ int sweep_resident(optmc_ctx* ctx) {
   if (ctx->sharded_M_total > 0) {  // optmc_lsm_poly_sharded: in-kernel exchange with the peer ranks
     a.comm.nranks = ctx->comm.nranks; a.comm.rank = ctx->comm.rank; a.comm.g0 = ctx->comm.g;
     a.comm.M_total = ctx->sharded_M_total;
+    a.one.M_total = ctx->sharded_M_total;
     for (int r = 0; r < ctx->comm.nranks; ++r) a.comm.slots[r] = ctx->comm.peers[r];
     ctx->comm.g += (unsigned int)sw.N;  // N - 1 Gram exchanges + the final one; every rank advances alike
   }
@@ -215,9 +227,9 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
   for (int c = 1; c <= ctx->sm_count; ++c) {
     if (plan_shape(ctx, M, dtype, sticky, c, &p, &why) && p.ncta <= c) { cpg = c; break; }
   }
-  if (cpg == 0 || (M_total && !p.spec)) {
+  if (cpg == 0) {
     if (M_total) {  // every rank takes this branch alike: eligibility depends on (M, dtype, semantics) only
-      set_error("path-sharded batch needs the speculative persistent sweep on every rank (sticky semantics, slice on chip): " + why);
+      set_error("path-sharded batch needs the persistent sweep on every rank (slice on chip): " + why);
       return OPTMC_EUNSUPPORTED;
     }
     // does not fit on chip: one option at a time through the single-option entry (split sweep)

@@ -55,7 +55,8 @@ struct ResArgs {
   int nstage, sticky;
   int want_eu;                // speculative kernel: also reduce the European payoff of the terminal row (control variate)
   unsigned int stage_stride;  // bytes between stages in shared memory
-  long long* trace;           // optional [2][(N+1)][8] phase clocks of the first and last CTA (OPTMC_TRACE)
+  long long* trace;           // optional [2][(N+1)][kTraceCols] phase clocks of the first and last CTA (OPTMC_TRACE)
+  void* spill;                // speculative kernel: candidate-list overflow, [CTAs][warps][PPT * 32] entries of 3 values
 };
 
 template <int QN> struct Pow2 { static constexpr int v = QN <= 2 ? 2 : QN <= 4 ? 4 : QN <= 8 ? 8 : 16; };
@@ -461,6 +462,8 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
   }
   unsigned long long prev0 = 0ull, prev1 = 0ull;  // warp 0: accumulator baselines of the two parities
   bool comm_dead = false;                         // warp 0: a peer rank stopped answering (sharded sweeps)
+  // grouped + path-sharded: every group owns its own slot block on every rank
+  const size_t slot_off = ga.groups ? (size_t)grp * kCommSlotWords : 0;
   long long* const tr_base = (ga.trace && grp == 0 && tid == 0 && (cta == 0 || cta == ncta - 1))
                                  ? ga.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * kTraceCols : nullptr;
 
@@ -557,7 +560,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
     if (warp == 0) {
       int spins = 0;
       unsigned long long pv = (seq & 1) ? prev1 : prev0;
-      const double tot_l = warp0_grid_sum<Q>(mine, a.xw, seq & 1, ncta, pv, a.flags, &spins, ga.comm, (unsigned int)seq, cta, comm_dead);
+      const double tot_l = warp0_grid_sum<Q>(mine, a.xw, seq & 1, ncta, pv, a.flags, &spins, ga.comm, (unsigned int)seq, cta, comm_dead, slot_off);
       if (seq & 1) prev1 = pv; else prev0 = pv;
       OPTMC_TRACE_AT(4);
       if (tr) tr[7] = spins;
@@ -617,10 +620,10 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
   }
   if (warp == 0) {
     unsigned long long pv = (seq & 1) ? prev1 : prev0;
-    const double tot_l = warp0_grid_sum<2>(mine, a.xw, seq & 1, ncta, pv, a.flags, nullptr, ga.comm, (unsigned int)seq, cta, comm_dead);
+    const double tot_l = warp0_grid_sum<2>(mine, a.xw, seq & 1, ncta, pv, a.flags, nullptr, ga.comm, (unsigned int)seq, cta, comm_dead, slot_off);
     const double s1 = __shfl_sync(0xffffffffu, tot_l, 0), s2 = __shfl_sync(0xffffffffu, tot_l, 1);
     if (cta == 0 && lane == 0) {
-      const double n = (double)(ga.comm.nranks > 1 ? ga.comm.M_total : a.M);
+      const double n = (double)a.M_total;
       const double mean = s1 / n;
       double var = n > 1.0 ? (s2 - n * mean * mean) / (n - 1.0) : 0.0;
       if (var < 0.0) var = 0.0;
@@ -663,64 +666,125 @@ template <int ID, int NTHREADS> __device__ __forceinline__ void named_bar_arrive
 }
 constexpr int kBarBeta = 1, kBarTot = 2;
 
-// S(t): no beta needed.  cand gets bit k for every path that is open and in the money at date t.
-template <typename R, int DEG, int PPT, int NT, bool DECIDE, bool GRAM>
-__device__ __forceinline__ void spec_pass(const R (&cf)[PPT], const R* __restrict__ st_t, const R* __restrict__ st_g,
-                                          const PassConsts<R>& pc, double (&mom)[Moments<DEG>::Q], unsigned int& rows,
-                                          typename MaskOf<(PPT > 32)>::type& cand) {
+// One listed path of a warp at the current date: what the decision and its row of the regression need (price at the
+// decision date, price at the Gram date, cash-flow), so that neither touches the price rows again.  The owning warp
+// fills its own segment in S(t) (order: step k, then lane -- fixed), processes it with one lane per entry once beta_t
+// is known, and the owners read the resulting cash-flow back.  Three planes (st, sg, c) of kCandCap entries per warp
+// in shared memory; the rest spill to the warp's block in global memory (dates close to maturity only).
+constexpr int kCandCap = 12;
+// the overflow path is rare and lives out of line: the unrolled scan must stay small (instruction cache)
+template <typename R> __device__ __noinline__ void cand_spill_store(R* p, int plane, R st, R sg, R c) {
+  p[0] = st; p[plane] = sg; p[2 * plane] = c;
+}
+template <typename R> struct CandList {
+  R* smem;         // this warp's segment: planes [3][kCandCap]
+  R* spill;        // this warp's block in global memory: planes [3][spill_cap]
+  int spill_cap;   // PPT * 32
+  __device__ __forceinline__ void store(int e, R st, R sg, R c) const {
+    if (e < kCandCap) { smem[e] = st; smem[kCandCap + e] = sg; smem[2 * kCandCap + e] = c; }
+    else cand_spill_store<R>(spill + (e - kCandCap), spill_cap, st, sg, c);
+  }
+  __device__ __forceinline__ void load(int e, R& st, R& sg, R& c) const {
+    if (e < kCandCap) { st = smem[e]; sg = smem[kCandCap + e]; c = smem[2 * kCandCap + e]; }
+    else { const R* p = spill + (e - kCandCap); st = p[0]; sg = p[spill_cap]; c = p[2 * spill_cap]; }
+  }
+  __device__ __forceinline__ void store_c(int e, R c) const {
+    if (e < kCandCap) smem[2 * kCandCap + e] = c; else spill[2 * spill_cap + (e - kCandCap)] = c;
+  }
+  __device__ __forceinline__ R load_c(int e) const {
+    return e < kCandCap ? smem[2 * kCandCap + e] : spill[2 * spill_cap + (e - kCandCap)];
+  }
+};
+
+// S(t), steps [K0, K1): no beta needed, no arithmetic beyond the in-the-money tests.  Every path that is open and in
+// the money at date t (a CANDIDATE: its cash-flow may change at t) or at date t-1 (a row of the regression of t-1)
+// goes to the warp's list -- the price of a date it is out of the money at is replaced by an out-of-the-money
+// sentinel -- and to the bit mask `listed`.  All floating-point work on these paths happens in cand_round, in one
+// rolled loop with one lane per entry: the unrolled scan stays small (instruction cache) and holds no fp64 state.
+template <typename R, int PPT, int NT, int K0, int K1>
+__device__ __forceinline__ void scan_pass(const R (&cf)[PPT], const R* __restrict__ st_t, const R* __restrict__ st_g,
+                                          const PassConsts<R>& pc, bool decide, bool gram,
+                                          typename MaskOf<(PPT > 32)>::type& listed, const CandList<R>& list, int& n_w) {
   typedef typename MaskOf<(PPT > 32)>::type Mask;
   const int tid = threadIdx.x;
+  const unsigned int lt_mask = (1u << (tid & 31)) - 1u;
+  const R otm = (R)(-pc.sgn * INFINITY);
+  // decide / gram are off at the first / last date only: an "in the money" threshold nothing passes switches the test off
+  const R kk_t = decide ? pc.kk : (R)INFINITY, kk_g = gram ? pc.kk : (R)INFINITY;
 #pragma unroll
-  for (int k = 0; k < PPT; ++k) {
+  for (int k = K0; k < K1; ++k) {
     const int j = tid + k * NT;
     const R c = cf[k];
+    const R st = st_t[j], sg = st_g[j];
     const bool open = !Store<R>::flagged(c, pc.flag);
-    const R st = DECIDE ? st_t[j] : (R)0;
-    const R sg = GRAM ? st_g[j] : (R)0;
-    const bool lt = DECIDE & open & (pc.sgn * st > pc.kk);
-    const bool lg = GRAM & open & (pc.sgn * sg > pc.kk);
-    if (__any_sync(0xffffffffu, lt | lg)) {
-      cand |= lt ? ((Mask)1 << k) : (Mask)0;
-      if (GRAM) {
-        const bool live = lg & !lt;  // not a candidate: its cash-flow cannot change at date t
-        const R y = c * pc.dg;       // live lanes are unflagged: c >= 0
-        rows += live ? 1u : 0u;
-        moments_accumulate_nocount<DEG>(mom, (double)(live ? sg : (R)0), (double)(live ? y : (R)0));
-      }
+    const bool lt = pc.sgn * st > kk_t;
+    const bool lg = pc.sgn * sg > kk_g;
+    const bool in = open & (lt | lg);
+    const unsigned int bal = __ballot_sync(0xffffffffu, in);
+    if (bal) {  // warp-uniform; ~15% of the steps
+      if (in) list.store(n_w + __popc(bal & lt_mask), lt ? st : otm, lg ? sg : otm, c);
+      n_w += __popc(bal);
+      listed |= in ? ((Mask)1 << k) : (Mask)0;
     }
   }
 }
 
-// C(t): the candidates, once beta_t is known (valid = the regression of date t succeeded).
-template <typename R, int DEG, int PPT, int NT, bool GRAM>
-__device__ __forceinline__ void cand_pass(R (&cf)[PPT], const R* __restrict__ st_t, const R* __restrict__ st_g,
-                                          const HitConsts<R, DEG>& dec, const PassConsts<R>& pc, bool valid,
-                                          double (&mom)[Moments<DEG>::Q], unsigned int& rows, unsigned int& cnt, R& em,
-                                          typename MaskOf<(PPT > 32)>::type cand) {
+// The listed paths of the warp, one lane per entry, once beta_t is known (valid = the regression of date t
+// succeeded): decision of date t for the candidates, the cash-flow after it (written back into the entry), and the
+// row of the regression of date t-1 if the path is in the money there and was not exercised just now (sticky mask).
+template <typename R, int DEG>
+__device__ __forceinline__ void cand_round(const CandList<R>& list, int n_w, const HitConsts<R, DEG>& dec,
+                                           const PassConsts<R>& pc, bool valid, double (&mom)[Moments<DEG>::Q],
+                                           unsigned int& rows, unsigned int& cnt, R& em) {
+  const int lane = threadIdx.x & 31;
+  for (int e0 = 0; e0 < n_w; e0 += 32) {  // warp-uniform trip count
+    const int e = e0 + lane;
+    const bool have = e < n_w;
+    R st, sg, c;
+    list.load(have ? e : 0, st, sg, c);
+    const bool lt = valid & have & (pc.sgn * st > pc.kk);
+    bool sure;
+    bool pos = dec.fast(lt ? st : (R)0, sure);
+    if (lt & !sure) pos = dec.exact(st);  // rare: within fp32 rounding of the exercise boundary
+    const bool exer = lt & pos;
+    const R pay = Store<R>::with_flag((fma(pc.sgn, st, pc.c1) + pc.c2) * pc.dinv, pc.flag);
+    c = exer ? pay : c;
+    if (exer) list.store_c(e, c);
+    cnt += exer ? 1u : 0u;
+    em = fmax(em, exer ? -(pc.sgn * st) : (R)-INFINITY);
+    const bool live = have & !exer & (pc.sgn * sg > pc.kk);
+    const R y = c * pc.dg;
+    rows += live ? 1u : 0u;
+    moments_accumulate_nocount<DEG>(mom, (double)(live ? sg : (R)0), (double)(live ? y : (R)0));
+  }
+}
+
+// The owners read their candidates' cash-flows back (same ballots, hence the same entry indices, as in S(t)).  The
+// steps with a candidate anywhere in the warp come from one warp-wide OR of the masks, so the walk over the PPT steps
+// is a chain of warp-uniform tests (four steps per test), not of votes.
+__device__ __forceinline__ unsigned int warp_or(unsigned int m) { return __reduce_or_sync(0xffffffffu, m); }
+__device__ __forceinline__ unsigned long long warp_or(unsigned long long m) {
+  return ((unsigned long long)__reduce_or_sync(0xffffffffu, (unsigned int)(m >> 32)) << 32) |
+         __reduce_or_sync(0xffffffffu, (unsigned int)m);
+}
+template <typename R, int PPT>
+__device__ __forceinline__ void cand_apply(R (&cf)[PPT], const CandList<R>& list,
+                                           typename MaskOf<(PPT > 32)>::type cand) {
   typedef typename MaskOf<(PPT > 32)>::type Mask;
-  const int tid = threadIdx.x;
+  const unsigned int lt_mask = (1u << (threadIdx.x & 31)) - 1u;
+  const Mask any = warp_or(cand);
+  int n = 0;
 #pragma unroll
-  for (int k = 0; k < PPT; ++k) {
-    const bool lt = (cand >> k) & (Mask)1;
-    if (__any_sync(0xffffffffu, lt)) {
-      const int j = tid + k * NT;
-      const R st = st_t[j];
-      bool sure;
-      bool pos = dec.fast(st, sure);
-      if (valid & lt & !sure) pos = dec.exact(st);  // rare: within fp32 rounding of the exercise boundary
-      const bool exer = valid & lt & pos;
-      const R pay = Store<R>::with_flag((fma(pc.sgn, st, pc.c1) + pc.c2) * pc.dinv, pc.flag);
-      R c = cf[k];
-      c = exer ? pay : c;
-      cf[k] = c;
-      cnt += exer ? 1u : 0u;
-      em = fmax(em, exer ? -(pc.sgn * st) : (R)-INFINITY);
-      if (GRAM) {
-        const R sg = st_g[j];
-        const bool live = lt & !exer & (pc.sgn * sg > pc.kk);
-        const R y = c * pc.dg;
-        rows += live ? 1u : 0u;
-        moments_accumulate_nocount<DEG>(mom, (double)(live ? sg : (R)0), (double)(live ? y : (R)0));
+  for (int k0 = 0; k0 < PPT; k0 += 4) {
+    if ((any >> k0) & (Mask)0xf) {
+#pragma unroll
+      for (int k = k0; k < k0 + 4 && k < PPT; ++k) {
+        if ((any >> k) & (Mask)1) {
+          const bool lt = (cand >> k) & (Mask)1;
+          const unsigned int bal = __ballot_sync(0xffffffffu, lt);
+          if (lt) cf[k] = list.load_c(n + __popc(bal & lt_mask));
+          n += __popc(bal);
+        }
       }
     }
   }
@@ -732,14 +796,17 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
   constexpr int QP = Pow2<Q>::v;
   constexpr int NW = NT / 32;
   constexpr int NALL = NT + 32;
+  constexpr int KH = (PPT + 1) / 2;  // steps [0, KH) = half A of a row, [KH, PPT) = half B
   typedef typename MaskOf<(PPT > 32)>::type Mask;
   static_assert(Q <= kXchgMaxQ, "Gram vector must fit the exchange buffer");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t mbar[3];
+  __shared__ __align__(8) uint64_t mbar[3][2];
   __shared__ double s_red[NW * 16];
   __shared__ double s_dec[DEG + 1];     // exercise iff s_dec(s) > 0  (payoff - continuation as a polynomial in S)
   __shared__ float s_hit[2 * DEG + 4];  // fp32 sweep: f[], b[] of s_dec (HitConsts); the discount slots are unused here
+  __shared__ R s_seg[NW][3 * kCandCap];
   __shared__ int s_valid;
+  __shared__ unsigned int s_done[2];    // compute warps that finished half A / half B of the current date's rows
   __shared__ unsigned long long s_bnd[2];
   __shared__ unsigned int s_cnt[2];
 
@@ -751,43 +818,52 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
   const long long base = (long long)cta * a.chunk;
   const long long rem = a.M - base;
   const int n_local = (int)(rem < a.chunk ? rem : a.chunk);
-  const unsigned int bytes = (unsigned int)((size_t)n_local * sizeof(R));  // multiple of 16 (planner)
+  const int n_a = n_local < KH * NT ? n_local : KH * NT;  // paths of the slice in half A (a multiple of 16 bytes)
+  const unsigned int bytes_a = (unsigned int)((size_t)n_a * sizeof(R));
+  const unsigned int bytes_b = (unsigned int)((size_t)(n_local - n_a) * sizeof(R));
   const bool is_put = a.is_put != 0;
   const R sgn = (R)a.sgn, kk = (R)a.kk, c1 = (R)a.c1, c2 = (R)a.c2;
   const unsigned int flag = 0x80000000u;  // sticky semantics only
-  const int N = a.N, nstage = ga.nstage;
+  const int N = a.N, nrow = ga.nstage;
   const R* Sbase = static_cast<const R*>(a.S) + base;
   const ResComm& cm = ga.comm;
   // grouped + path-sharded: every group owns its own slot block on every rank
   const size_t slot_off = ga.groups ? (size_t)grp * kCommSlotWords : 0;
 
-  auto slot_ptr = [&](int slot) -> R* { return reinterpret_cast<R*>(smem_raw + (size_t)slot * ga.stage_stride); };
-  auto issue_load = [&](int t, int slot) {  // one thread
-    uint64_t* bar = &mbar[slot];
-    mbar_arrive_expect_tx(bar, bytes);
-    bulk_load_1d(smem_raw + (size_t)slot * ga.stage_stride, Sbase + (size_t)t * a.ld, bytes, bar);
+  // Stage ring: date t lives in row (N - t) % nrow; every row is staged as two halves with their own mbarriers, so
+  // that half A of row t can be refilled (with date t - nrow) while the pass is still in half B: with two rows on
+  // chip (grouped launches: 27 k paths per CTA) the refill otherwise lands on the critical path of the next pass.
+  auto row_ptr = [&](int row) -> R* { return reinterpret_cast<R*>(smem_raw + (size_t)row * ga.stage_stride); };
+  auto issue_half = [&](int t, int row, int half) {  // one thread
+    const unsigned int nb = half ? bytes_b : bytes_a;
+    if (nb == 0) return;
+    uint64_t* bar = &mbar[row][half];
+    mbar_arrive_expect_tx(bar, nb);
+    bulk_load_1d(smem_raw + (size_t)row * ga.stage_stride + (half ? (size_t)KH * NT * sizeof(R) : 0),
+                 Sbase + (size_t)t * a.ld + (half ? KH * NT : 0), nb, bar);
   };
 
   if (tid == 0) {
-    for (int s = 0; s < nstage; ++s) mbar_init(&mbar[s], 1);
+    for (int s = 0; s < nrow; ++s) { mbar_init(&mbar[s][0], 1); mbar_init(&mbar[s][1], 1); }
     mbar_fence_init();
     s_bnd[0] = s_bnd[1] = bnd_none(a.is_put);
     s_cnt[0] = s_cnt[1] = 0u;
+    s_done[0] = s_done[1] = 0u;
     s_valid = 0;
 #pragma unroll
     for (int i = 0; i < 2 * DEG + 4; ++i) s_hit[i] = 0.f;
 #pragma unroll
     for (int i = 0; i <= DEG; ++i) s_dec[i] = 0.0;
   }
-  {  // out-of-the-money sentinel behind the slice in every stage (the bulk copies never touch it)
+  {  // out-of-the-money sentinel behind the slice in every row (the bulk copies never touch it)
     const R sentinel = is_put ? (R)INFINITY : (R)-INFINITY;
-    for (int s = 0; s < nstage; ++s)
-      for (int i = n_local + tid; i < PPT * NT; i += NALL) slot_ptr(s)[i] = sentinel;
+    for (int s = 0; s < nrow; ++s)
+      for (int i = n_local + tid; i < PPT * NT; i += NALL) row_ptr(s)[i] = sentinel;
   }
   __syncthreads();
   if (tid == 0) {
-    for (int i = 0; i < nstage; ++i)
-      if (N - i >= 1) issue_load(N - i, i);
+    for (int i = 0; i < nrow; ++i)
+      if (N - i >= 1) { issue_half(N - i, i, 0); issue_half(N - i, i, 1); }
   }
   long long* const tr_base = (ga.trace && grp == 0 && (cta == 0 || cta == ncta - 1))
                                  ? ga.trace + (size_t)(cta == 0 ? 0 : 1) * (N + 1) * kTraceCols : nullptr;
@@ -803,8 +879,8 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
     }
     unsigned long long prev0 = 0ull, prev1 = 0ull;
     bool comm_dead = false;
-    int seq = 0, slot_t = 0;
-    double d_t = 1.0, dinv_t = 1.0;
+    int seq = 0;
+    double d_t = 1.0;
     auto cta_totals = [&](int qp) -> double {  // lane -> quantity lane % qp; sums the warps' partials in a fixed order
       const int G = 32 / qp;
       const int q = lane % qp, g = lane / qp;
@@ -813,14 +889,17 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
       for (int m = qp; m <= 16; m <<= 1) v += shfl_xor_f64(v, m);
       return __shfl_sync(0xffffffffu, v, (lane >> 1) % qp);
     };
-    auto flush_stats = [&](int t) {  // lane 0: exercise statistics of date t (collected by the compute warps)
-      if (s_cnt[0]) {
-        if (a.exc) atomicAdd(a.exc + t, (unsigned long long)s_cnt[0]);
+    // lane 0: exercise statistics of date t.  The compute warps add them (slot t & 1) AFTER they arrived at TOT(t),
+    // off the critical path, so date t is flushed one iteration later: once every compute warp has passed BETA(t-1).
+    auto flush_stats = [&](int t) {
+      const int p = t & 1;
+      if (s_cnt[p]) {
+        if (a.exc) atomicAdd(a.exc + t, (unsigned long long)s_cnt[p]);
         if (a.bnd) {
-          if (is_put) atomicMax(a.bnd + t, s_bnd[0]); else atomicMin(a.bnd + t, s_bnd[0]);
+          if (is_put) atomicMax(a.bnd + t, s_bnd[p]); else atomicMin(a.bnd + t, s_bnd[p]);
         }
-        s_cnt[0] = 0u;
-        s_bnd[0] = bnd_none(a.is_put);
+        s_cnt[p] = 0u;
+        s_bnd[p] = bnd_none(a.is_put);
       }
     };
     if (ga.want_eu) {  // European leg on the option's own paths (om3:653-677): exp(-rT) payoff(S_N), summed like the price
@@ -847,16 +926,12 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
       if (tr) tr[10] = clock64();
       named_bar_arrive<kBarBeta, NALL>();  // beta_t (or "none" at t = N) is in shared memory
       d_t *= a.disc;
-      dinv_t *= a.inv_disc;
       if (t == 1) break;
       named_bar_sync<kBarTot, NALL>();     // every compute warp is done with date t; partials are in s_red
       if (tr) tr[0] = clock_after(*(volatile int*)&s_cnt[1]);
       const double mine = cta_totals(QP) * qscale;
       if (tr) tr[9] = clock_after(__double2loint(mine));
-      if (lane == 0) {
-        flush_stats(t);
-        if (t - nstage >= 1) issue_load(t - nstage, slot_t);  // refill the slot date t vacated
-      }
+      if (lane == 0 && t + 1 < N) flush_stats(t + 1);
       int spins = 0;
       unsigned long long pv = (seq & 1) ? prev1 : prev0;
       const double tot_l = warp0_grid_sum<Q>(mine, a.xw, seq & 1, ncta, pv, a.flags, &spins, cm, (unsigned int)seq, cta, comm_dead, slot_off);
@@ -894,12 +969,14 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
       }
       OPTMC_TRACE_AT(5);
       ++seq;
-      slot_t = slot_t + 1 == nstage ? 0 : slot_t + 1;
     }
     // ---- final reduction: mean and standard error of the cash-flows (om3:651) ----
     named_bar_sync<kBarTot, NALL>();
     const double mine = cta_totals(2);
-    if (lane == 0) flush_stats(1);
+    if (lane == 0) {
+      if (N >= 3) flush_stats(2);
+      if (N >= 2) flush_stats(1);
+    }
     unsigned long long pv = (seq & 1) ? prev1 : prev0;
     const double tot_l = warp0_grid_sum<2>(mine, a.xw, seq & 1, ncta, pv, a.flags, nullptr, cm, (unsigned int)seq, cta, comm_dead, slot_off);
     const double s1 = __shfl_sync(0xffffffffu, tot_l, 0), s2 = __shfl_sync(0xffffffffu, tot_l, 1);
@@ -921,15 +998,32 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
   // compute warps
   // -----------------------------------------------------------------------------------------------------------
   R cf[PPT];
-  int slot_t = 0;           // ring slot of the iteration's decision date
-  unsigned int phase = 0u;  // bit s: mbarrier phase parity the next wait on slot s expects
-  auto wait_slot = [&](int slot) {
-    mbar_wait(&mbar[slot], (phase >> slot) & 1u);
-    phase ^= 1u << slot;
+  unsigned int phase = 0u;  // bit (2 row + half): mbarrier phase parity the next wait on that half expects
+  auto wait_half = [&](int row, int half) {
+    if ((half ? bytes_b : bytes_a) == 0) return;
+    const int b = 2 * row + half;
+    mbar_wait(&mbar[row][half], (phase >> b) & 1u);
+    phase ^= 1u << b;
   };
-  wait_slot(0);
+  // the last compute warp to finish a half of row `row` (date t) refills it with date t - nrow
+  auto release_half = [&](int t, int row, int half) {
+    if (t - nrow < 1) return;
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      if (atomicAdd(&s_done[half], 1u) == (unsigned int)(NW - 1)) {
+        s_done[half] = 0u;
+        __threadfence_block();
+        issue_half(t - nrow, row, half);
+      }
+    }
+  };
+  const CandList<R> list{&s_seg[warp][0],
+                         static_cast<R*>(ga.spill) + ((size_t)blockIdx.x * NW + warp) * (size_t)(3 * PPT * 32), PPT * 32};
+  wait_half(0, 0);
+  wait_half(0, 1);
   {  // date N: cash-flows = payoff(S[N]) (om3:616)
-    const R* st = slot_ptr(0);
+    const R* st = row_ptr(0);
 #pragma unroll
     for (int k = 0; k < PPT; ++k) {
       const R s = st[tid + k * NT];  // sentinel past the slice: out of the money -> 0
@@ -949,37 +1043,55 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
     if (reduce_scatter_owner<2>(lane)) s_red[warp * 2 + reduce_scatter_index<2>(lane)] = eu[0];
     named_bar_arrive<kBarTot, NALL>();
   }
+  int row_t = 0;                   // ring row of the iteration's decision date
   double d_t = 1.0, dinv_t = 1.0;  // D_t and 1 / D_t of the iteration's decision date
   for (int t = N; t >= 1; --t) {
-    // stamps from a warp on the communication warp's scheduler (NW % 4 == 3): clock64 is read per scheduler partition
+    // stamps from a warp on the communication warp's scheduler (NW % 4 == 3)
     long long* tr = (tr_base && tid == 96) ? tr_base + (size_t)t * kTraceCols : nullptr;
     const bool gram = t >= 2;
-    const int slot_g = slot_t + 1 == nstage ? 0 : slot_t + 1;  // ring slot of the Gram date t-1
-    if (gram) wait_slot(slot_g);
-    const R* st_t = slot_ptr(slot_t);
-    const R* st_g = slot_ptr(gram ? slot_g : slot_t);
+    const int row_g = row_t + 1 == nrow ? 0 : row_t + 1;  // ring row of the Gram date t-1
+    const R* st_t = row_ptr(row_t);
+    const R* st_g = row_ptr(gram ? row_g : row_t);
     double mom[Q];
 #pragma unroll
     for (int q = 0; q < Q; ++q) mom[q] = 0.0;
     unsigned int rows = 0, cnt = 0;
     R em = (R)-INFINITY;  // max over exercised paths of -sgn * S: put -> max S, call -> -(min S)
     const PassConsts<R> pc{sgn, kk, c1, c2, (R)dinv_t, (R)(d_t * a.disc), flag, n_local};
-    Mask cand = 0;
-    if (tr) tr[6] = clock64();  // stage ready: S(t) starts
-    if (t == N) spec_pass<R, DEG, PPT, NT, false, true>(cf, st_t, st_g, pc, mom, rows, cand);
-    else if (gram) spec_pass<R, DEG, PPT, NT, true, true>(cf, st_t, st_g, pc, mom, rows, cand);
-    else spec_pass<R, DEG, PPT, NT, true, false>(cf, st_t, st_g, pc, mom, rows, cand);
-    if (tr) tr[1] = clock_after((int)rows);
+    Mask listed = 0;
+    int n_w = 0;  // listed paths of this warp at date t (warp-uniform)
+    if (gram) wait_half(row_g, 0);
+    if (tr) tr[6] = clock64();  // S(t) starts
+    scan_pass<R, PPT, NT, 0, KH>(cf, st_t, st_g, pc, t < N, gram, listed, list, n_w);
+    release_half(t, row_t, 0);
+    if (gram) wait_half(row_g, 1);
+    scan_pass<R, PPT, NT, KH, PPT>(cf, st_t, st_g, pc, t < N, gram, listed, list, n_w);
+    release_half(t, row_t, 1);
+    __syncwarp();  // the warp's entries are visible to all of its lanes
+    if (tr) tr[1] = clock_after(n_w);
     named_bar_sync<kBarBeta, NALL>();  // beta_t is in shared memory
     if (tr) tr[2] = clock_after(*(volatile int*)&s_valid);
-    if (t < N) {
+    {
       HitConsts<R, DEG> hc;
       if constexpr (sizeof(R) == 4) { hc.d = s_dec; hc.c = s_hit; }
       else { hc.dec.load(s_dec, true); hc.dinv_ = pc.dinv; hc.dg_ = pc.dg; }
-      const bool valid = s_valid != 0;
-      if (gram) cand_pass<R, DEG, PPT, NT, true>(cf, st_t, st_g, hc, pc, valid, mom, rows, cnt, em, cand);
-      else cand_pass<R, DEG, PPT, NT, false>(cf, st_t, st_g, hc, pc, valid, mom, rows, cnt, em, cand);
+      cand_round<R, DEG>(list, n_w, hc, pc, t < N && s_valid != 0, mom, rows, cnt, em);
       if (tr) tr[8] = clock_after((int)rows + (int)cnt);
+    }
+    d_t *= a.disc;
+    dinv_t *= a.inv_disc;
+    if (gram) {
+      double acc[QP];
+      mom[0] = (double)rows;
+#pragma unroll
+      for (int q = 0; q < QP; ++q) acc[q] = q < Q ? mom[q] : 0.0;
+      warp_reduce_scatter<QP>(acc, lane);
+      if (reduce_scatter_owner<QP>(lane)) s_red[warp * QP + reduce_scatter_index<QP>(lane)] = acc[0];
+      if (tr) tr[3] = clock_after(__double2loint(acc[0]));
+      named_bar_arrive<kBarTot, NALL>();
+    }
+    // off the critical path (the communication warp is in the exchange): statistics, cash-flows of the candidates
+    if (t < N) {
       cnt = __reduce_add_sync(0xffffffffu, cnt);
       if (cnt) {  // warp-uniform
         const double ext = -(double)sgn * (double)em;
@@ -987,23 +1099,16 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
         if (!isfinite(ext)) b = bnd_none(a.is_put);
         b = is_put ? warp_max_u64(b) : warp_min_u64(b);
         if (lane == 0) {
-          atomicAdd(&s_cnt[0], cnt);
-          if (is_put) atomicMax(&s_bnd[0], b); else atomicMin(&s_bnd[0], b);
+          atomicAdd(&s_cnt[t & 1], cnt);
+          if (is_put) atomicMax(&s_bnd[t & 1], b); else atomicMin(&s_bnd[t & 1], b);
         }
       }
+      __syncwarp();
+      cand_apply<R, PPT>(cf, list, listed);
+      __syncwarp();  // before the next pass overwrites the segment
     }
-    d_t *= a.disc;
-    dinv_t *= a.inv_disc;
     if (!gram) break;
-    double acc[QP];
-    mom[0] = (double)rows;
-#pragma unroll
-    for (int q = 0; q < QP; ++q) acc[q] = q < Q ? mom[q] : 0.0;
-    warp_reduce_scatter<QP>(acc, lane);
-    if (reduce_scatter_owner<QP>(lane)) s_red[warp * QP + reduce_scatter_index<QP>(lane)] = acc[0];
-    if (tr) tr[3] = clock_after(__double2loint(acc[0]));
-    named_bar_arrive<kBarTot, NALL>();
-    slot_t = slot_g;
+    row_t = row_g;
   }
   // ---- final reduction ----
   double fin[2] = {0.0, 0.0};
@@ -1052,6 +1157,12 @@ template <typename R, int DEG, int PPT, int NT>
 int launch_resident_spec_t(optmc_ctx* ctx, const ResPlan& p, ResArgs& a) {
   auto kern = lsm_resident_spec_kernel<R, DEG, PPT, NT>;
   OPTMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+  {  // candidate-list overflow (dates close to maturity, where a third of the paths are candidates)
+    const size_t need = (size_t)p.ncta * p.ngroups * (NT / 32) * (size_t)(3 * PPT * 32) * sizeof(R);
+    int rc = ensure_bytes(&ctx->spill, &ctx->spill_bytes, need);
+    if (rc) return rc;
+    a.spill = ctx->spill;
+  }
   void* args[] = {(void*)&a};
   OPTMC_CUDA(cudaLaunchCooperativeKernel((const void*)kern, dim3(p.ncta * p.ngroups), dim3(NT + 32), args, p.smem, ctx->stream));
   ctx->launches++; ctx->sw.n_launches++;

@@ -96,6 +96,7 @@ struct optmc_ctx {
   void* xchg = nullptr;                 // exchange accumulators of the persistent sweep, xchg_bytes()
   int* d_flags = nullptr;               // [4]: [0] = fixed-point exchange overflow
   void* batch_dev = nullptr; size_t batch_dev_cap = 0;  // per-wave descriptors / accumulators / results
+  void* spill = nullptr;     size_t spill_bytes = 0;     // speculative sweep: candidate-list overflow
   void* gnet_rows = nullptr; size_t gnet_rows_cap = 0;  // global network LSM: regression rows of all dates (x, t, y)
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};      // kernel timing of the fused calls (optmc_ctx_kernel_times)
   double last_paths_ms = 0.0, last_sweep_ms = 0.0;

@@ -42,7 +42,7 @@ def setenv(**kw):
 for M in (100_000, 1_000_000, 4_000_000):
     S = eng.paths(model, M, N, "f32", E.RngSpec(seed=1))
     ref = None
-    for label, env in (("spec", dict(OPTMC_RES_SPEC=None)), ("single-role", dict(OPTMC_RES_SPEC=0))):
+    for label, env in (("default", dict(OPTMC_RES_SPEC=None)), ("single-role", dict(OPTMC_RES_SPEC=0))):
         setenv(**env)
         for sem in ("reference",):
             ms, r = timed(lambda: eng.lsm(S, 100.0, 0.05, 1.0, "put", semantics=sem, impl="resident"))
@@ -58,7 +58,7 @@ for M in (100_000, 1_000_000, 4_000_000):
 
 for B in (1, 2, 4, 8):
     ref = None
-    for label, env in (("spec", dict(OPTMC_RES_SPEC=None)), ("single-role", dict(OPTMC_RES_SPEC=0))):
+    for label, env in (("default", dict(OPTMC_RES_SPEC=None)), ("single-role", dict(OPTMC_RES_SPEC=0))):
         setenv(**env)
         ms, (p, se) = timed(lambda: eng.price_american_batch(model, 1_000_000, 100.0, 100.0, 1.0, np.full(B, N), 1, "f32",
                                                                E.RngSpec(seed=3)), reps=5)
@@ -68,7 +68,7 @@ for B in (1, 2, 4, 8):
         ref = ref or key
         print(f"batch of {B} x 1M {label:12s} total {ms:7.3f} ms  paths {kp:.3f} sweep {ks:.3f} ms  "
               f"{B * 1e6 * N / ms / 1e6:7.1f} G path-steps/s  price[0] {p[0]:.6f} identical={same}", flush=True)
-setenv(OPTMC_RES_SPEC=None)
+setenv(OPTMC_RES_SPEC=1)
 for cap in (74, 49):
     setenv(OPTMC_BATCH_CPG=cap)
     ms, (p, se) = timed(lambda: eng.price_american_batch(model, 1_000_000, 100.0, 100.0, 1.0, np.full(4, N), 1, "f32",
