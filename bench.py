@@ -1,26 +1,35 @@
 #!/usr/bin/env python
 """bench.py -- path-steps/sec of the Heston American-put LSM hot path on N B200s (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--paths M] [--dates T]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--shard paths|options] [--paths M] [--dates T]
 
-Own arm (default): one process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A "step" is
-one pass of the hot path over one batch of --batch (4) independent options of BASELINE config 2 (Heston
-kappa=2 theta=0.04 xi=0.5 rho=-0.7, 252 steps, 1M paths each, quadratic-polynomial LSM): one batched K1 path
-launch (Philox in-register, step-major fp32 slabs) + one grouped persistent LSM sweep launch (each option on
-its own group of SMs) + the final payoff reductions, through optmc_price_american_batch.  With N GPUs every
-rank prices its own batches (option-sharding, no data-path collective: weak scaling).  Timing: CUDA events on
-the launching stream, barrier + synchronize on both sides, max over ranks; per-kernel times from CUDA events the
-library records around its two launches.  The 4 GB of slabs are 30x the L2, so no explicit L2 flush is needed.
+Own arm (default): one process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE for N > 1).  A "step" is one pass of
+the hot path over one batch of --batch (4) options of BASELINE config 2 (Heston kappa=2 theta=0.04 xi=0.5 rho=-0.7,
+252 steps, quadratic-polynomial LSM, reference semantics) through optmc_price_american_batch(_ex): one batched K1 path
+launch (Philox in-register, step-major fp32 slabs) + one grouped persistent LSM sweep launch + the final reductions.
+  N = 1: every option has --paths (1 M) paths.
+  N > 1, --shard paths (default; the north-star split): every option has N x 1 M paths, PATH-SHARDED -- each
+         rank generates and sweeps its own 1 M-path block of each of the 4 options, and the per-date Gram totals are
+         exchanged INSIDE the sweep kernel over NVLink peer memory (no host-launched collective on the data path).
+         Per-GPU work is that of the N = 1 step (weak scaling).  Before timing, a smaller sharded batch is checked
+         against the unsharded pricing of the same options on rank 0 (bit-identical prices, identical on all ranks);
+         a mismatch fails the run.
+  N > 1, --shard options: every rank prices its own batch of 1 M-path options (no collective at all).
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks; per-kernel times from
+CUDA events the library records around its two launches.  The 4 GB of slabs per step are 30x the L2, so no explicit L2
+flush is needed.
 
-Reference arm (--impl reference): the reference is pure Python and cannot travel to the GPU box, so this
-times its restatement (oracle/lsm_oracle.py, numpy) on the host cores, reference-style: a process pool
-with one independent option per worker (options_model_3.py:1053-1056), each step a bounded sample.
+Reference arm (--impl reference): the reference is pure Python and cannot travel to the GPU box, so this times its
+restatement (oracle/lsm_oracle.py, numpy) on the host cores, reference-style: a process pool with one independent
+pricing per worker (options_model_3.py:1053-1056).  Same config as the own arm at N = 1 (4 x 1 M paths x 252 steps of
+work per step), priced as a bounded sample: one slice of 4 M / cores paths per worker.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -34,18 +43,30 @@ METRIC = "path-steps/sec, Heston American put LSM"
 UNIT = "path-steps/s"
 
 
-def load_traffic(kernel_substr):
-    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/ncu_r1_summary.json)."""
-    p = os.path.join(ROOT, "profiles", "ncu_r1_summary.json")
-    try:
-        with open(p) as f:
-            d = json.load(f)
-        for name, ks in d.get("kernels", {}).items():
-            if kernel_substr in name:
-                return float(ks[0]["dram_bytes"])
-    except Exception:  # noqa: BLE001
-        pass
-    return None
+def workload_string(N, M, B):
+    return (f"BASELINE config 2: American put, Heston (kappa=2, theta=0.04, xi=0.5, rho=-0.7), {N} steps, {M} paths per "
+            f"option per GPU, poly2 LSM (reference semantics); a step prices a batch of {B} options of that size per GPU "
+            f"in one grouped launch")
+
+
+def load_traffic():
+    """DRAM bytes per launch of the two bench kernels from the committed ncu capture of THIS round's kernels
+    (profiles/ncu_r2_summary.json, written by tools/ncu_summary.py together with the git hash of the build)."""
+    for name in ("ncu_r2_summary.json", "ncu_r1_summary.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        try:
+            with open(p) as f:
+                d = json.load(f)
+        except Exception:  # noqa: BLE001
+            continue
+        out = {"source": f"profiles/{name}", "git": d.get("git"), "paths": None, "sweep": None}
+        for kname, ks in d.get("kernels", {}).items():
+            if "paths_x2_batch_kernel" in kname or (out["paths"] is None and "paths_batch_kernel" in kname):
+                out["paths"] = float(ks[0]["dram_bytes"])
+            if "lsm_resident_kernel" in kname and "36" in kname or (out["sweep"] is None and "lsm_resident_kernel" in kname):
+                out["sweep"] = float(ks[0]["dram_bytes"])
+        return out
+    return {"source": None, "git": None, "paths": None, "sweep": None}
 
 
 def load_peaks():
@@ -78,7 +99,7 @@ def cpu_baseline_single(M, N):
     price = _cpu_price_one((1, M, N))
     dt = time.perf_counter() - t0
     return {"value": M * N / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"numpy oracle (draws + Heston paths + poly2 LSM sweep), {M} paths x {N} steps, "
+            "sample": f"numpy oracle (draws + Heston paths + poly2 LSM sweep), one option of {M} paths x {N} steps, "
                       f"{dt:.1f} s, price {price:.4f}; host has {os.cpu_count()} cpus"}
 
 
@@ -89,7 +110,9 @@ def run_reference_arm(args):
     from concurrent.futures import ProcessPoolExecutor
 
     cores = os.cpu_count() or 1
-    M, N = args.ref_paths, args.dates
+    N, B = args.dates, args.batch
+    # the step's work (B x --paths path-steps x N) as one slice per worker
+    M = max(2, (B * args.paths // cores) // 2 * 2)
     with ProcessPoolExecutor(max_workers=cores) as ex:
         def step(i):
             return list(ex.map(_cpu_price_one, [(1000 * i + w, M, N) for w in range(cores)]))
@@ -100,15 +123,15 @@ def run_reference_arm(args):
             step(args.warmup + i)
         dt = time.perf_counter() - t0
     val = cores * M * N * args.steps / dt
+    sample = (f"oracle/lsm_oracle.py (numpy restatement of options_model_3.py:211-233,615-651 with the 8(c) polynomial "
+              f"regressor) in a reference-style process pool: per step {cores} workers x one pricing of {M} paths x {N} steps "
+              f"(= the step's {B} x {args.paths} paths, sliced one per core)")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"BASELINE config 2 (Heston American put, poly2 LSM, {N} steps), bounded sample: "
-                               f"{cores} independent options x {M} paths per step, one per worker process"},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"oracle/lsm_oracle.py (numpy restatement of options_model_3.py:211-233,615-651 with the "
-                                   f"8(c) polynomial regressor); {cores} worker processes x {M} paths x {N} steps per step"},
+        "config": {"workload": workload_string(N, args.paths, B), "batch": B, "reference_sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -164,10 +187,19 @@ class ClockSampler:
                 "samples": len(s)}
 
 
+def git_head():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True,
+                              timeout=5).stdout.strip() or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------------
 def run_own_arm(args):
+    import numpy as np
     import torch
 
     from options_model_b200 import _lib as L
@@ -191,17 +223,54 @@ def run_own_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     M, N, B = args.paths, args.dates, args.batch
+    shard = "none" if world == 1 else ("paths" if args.shard in ("auto", "paths") else "options")
     eng = E.Engine(local)
     stream = torch.cuda.Stream(device=local)
     model = E.heston(S0, R, T, **HP)
     b = 4  # fp32 storage
-    import numpy as np
-
     Ns = np.full(B, N, dtype=np.int64)
+    parity = None
+    if shard == "paths":
+        from options_model_b200 import sharded as SH
+
+        SH.init_peer_exchange(eng, dist)
+        # ---- correctness of the fused exchange before anything is timed: a smaller sharded batch against the unsharded
+        # pricing of the SAME options (same Philox counters: pair_offset) on rank 0, and agreement across the ranks
+        Ms, Nsm, Bs = 65536, 60, 2
+        with torch.cuda.stream(stream):
+            ps, _, _ = eng.price_american_batch(model, Ms, S0, K, T, np.full(Bs, Nsm), 1, "f32",
+                                                E.RngSpec(seed=77, pair_offset=rank * (Ms // 2)), streams=np.arange(Bs) + 5,
+                                                M_total=Ms * world)
+            stream.synchronize()
+            everyone = [None] * world
+            dist.all_gather_object(everyone, [float(x) for x in ps])
+            single = None
+            if rank == 0:
+                p1, _ = eng.price_american_batch(model, Ms * world, S0, K, T, np.full(Bs, Nsm), 1, "f32", E.RngSpec(seed=77),
+                                                 streams=np.arange(Bs) + 5)
+                single = [float(x) for x in p1]
+            holder = [single]
+            dist.broadcast_object_list(holder, src=0)
+            single = holder[0]
+        rel = max(abs(a - c) / abs(c) for a, c in zip(everyone[0], single))
+        parity = {"rel_vs_single": rel, "identical_on_all_ranks": all(e == everyone[0] for e in everyone),
+                  "checked": f"{Bs} options x {Ms * world} paths x {Nsm} dates, sharded over {world} ranks vs one GPU",
+                  "sharded_prices": everyone[0], "single_gpu_prices": single}
     with torch.cuda.stream(stream):
         def step(i):
-            # B fresh options (Philox streams) per step and rank; host scalars in, host prices out
+            # B fresh options (Philox streams) per step; host scalars in, host prices out
+            if shard == "paths":  # the same options on every rank, each rank its own block of paths
+                out = eng.price_american_batch(model, M, S0, K, T, Ns, 1, "f32", E.RngSpec(seed=42, pair_offset=rank * (M // 2)),
+                                               "poly2", "reference", streams=i * B + np.arange(B), M_total=M * world)
+                return out[0], out[1]
             streams = (rank * 1_000_003 + i) * B + np.arange(B)
             return eng.price_american_batch(model, M, S0, K, T, Ns, 1, "f32", E.RngSpec(seed=42), "poly2", "reference",
                                             streams=streams)
@@ -223,20 +292,15 @@ def run_own_arm(args):
             t_end.record()
             barrier()
         launches = eng.launch_count() - l0
-        ms_total = t_start.elapsed_time(t_end)
+        ms_total = max_over_ranks(t_start.elapsed_time(t_end))
         ms_paths /= args.steps
         ms_sweep /= args.steps
-
-        class _Res:
-            pass
-
-        res = _Res()
-        res.price, res.stderr = float(price[0]), float(se[0])
+        price0, se0 = float(price[0]), float(se[0])
 
         # end-to-end through the reference-facing call: host scalars in, host floats out, every step
         pricer = compat.AdvancedOptionPricer(K=K, r=R, sigma=None, option_type="put", rng_manager=compat.RNGManager(42),
-                                             use_heston=True, heston_params=HP, use_control_variate=False,
-                                             device=local)
+                                             use_heston=True, heston_params=HP, use_control_variate=False, device=local,
+                                             path_shard=(rank, world) if shard == "paths" else None)
         grid_S0, grid_T, grid_N = np.full(B, S0), np.full(B, T), Ns
         for _ in range(max(1, args.warmup // 2)):
             pricer.price_american_grid(grid_S0, grid_T, grid_N, M)
@@ -245,76 +309,81 @@ def run_own_arm(args):
         for _ in range(args.steps):
             price_e2e = float(pricer.price_american_grid(grid_S0, grid_T, grid_N, M)[0][0])
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
+        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         barrier()
 
-    # path-sharding (second mode): ONE option of world x M paths, paths generated shard-local, the sweep
-    # exchanging its per-date totals inside the kernel over NVLink peer memory.  Reported as context.
-    sharded_info = None
-    if world > 1 and not args.no_other_configs:
-        from options_model_b200 import sharded as SH
-        try:
-            SH.init_peer_exchange(eng, dist)
-            Mt = M * world
-            off, m_loc = SH.shard_pairs(Mt, rank, world)
+    others = {}
+    peak, peak_src = load_peaks()
 
-            def one():
-                Sl = eng.paths(model, m_loc, N, "f32", E.RngSpec(seed=21, pair_offset=off))
-                return SH.sweep_sharded_fused(eng, dist, Sl, Mt, K, R, T)
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / reps, out
 
-            with torch.cuda.stream(stream):
-                for _ in range(3):
-                    rs = one()
-                stream.synchronize()
-                barrier()
-                e0s, e1s = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0s.record(stream)
-                reps = 10
-                for _ in range(reps):
-                    rs = one()
-                e1s.record(stream)
-                stream.synchronize()
-            tt = torch.tensor([e0s.elapsed_time(e1s) / reps], device="cuda")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            ms_sh = float(tt.item())
-            sharded_info = {"workload": f"one Heston put of {Mt} paths x {N} dates path-sharded over {world} GPUs; per-date "
-                                        "totals exchanged inside the persistent sweep kernel through NVLink peer memory",
-                            "ms": ms_sh, "path_steps_per_s": Mt * N / ms_sh * 1e3, "price": rs.price, "collective_launches": 0}
-            eng.comm_finalize()
-        except Exception as e:  # noqa: BLE001 -- context only; the headline does not depend on it
-            sharded_info = {"error": str(e)[:200]}
+    if not args.no_other_configs:
+        # ---- BASELINE configs 4 and 5 as stated: sharded over the ranks by OPTION, no data-path collective; every rank
+        # participates, the time is the slowest rank's ----
+        with torch.cuda.stream(stream):
+            Kg, Tg = np.meshgrid(np.linspace(70, 130, 32), np.linspace(1 / 12, 2, 32))
+            Kg, Tg = Kg.ravel(), Tg.ravel()
+            mine = np.arange(rank, 1024, world)
+            barrier()
+            dt4, _ = timed(lambda: eng.price_american_batch(model, 262_144, S0, Kg[mine], Tg[mine], np.full(mine.size, 252), 1,
+                                                            "f32", E.RngSpec(seed=9), streams=mine), 1)
+            dt4 = max_over_ranks(dt4)
+            others["config4_1024_options_x_256k_x252"] = {
+                "ms": dt4 * 1e3, "path_steps_per_s": 1024 * 262_144 * 252 / dt4, "us_per_option": dt4 / 1024 * 1e6 * world,
+                "options_per_rank": int(mine.size), "sharding": f"options rank::{world}, no collective"}
+            Kc, Tc = np.meshgrid(np.linspace(80, 120, 20), np.linspace(0.1, 1.0, 10))
+            cfg = compat.CalibrationConfig(n_mc_paths=50_000, n_time_steps=100, seed=13, verbose=False, plot_results=False)
+            gather = None
+            if dist is not None:
+                def gather(x):
+                    parts = [None] * world
+                    dist.all_gather_object(parts, x)
+                    return parts
+            obj = compat.HestonObjective(compat.HestonPricer(cfg, dtype="f32", device=local), S0, R, Kc.ravel(), Tc.ravel(),
+                                         np.full(200, 0.2), common_random_numbers=True, rank=rank, world=world,
+                                         all_gather=gather)
+            x0 = np.array([HP["kappa"], HP["theta"], HP["xi"], HP["rho"], HP["v0"]])
+            barrier()
+            dt5, f5 = timed(lambda: obj(x0), 3)
+            dt5 = max_over_ranks(dt5)
+            others["config5_calibration_objective_200x50k_x100"] = {
+                "ms": dt5 * 1e3, "path_steps_per_s": 1e9 / dt5, "objective": float(f5),
+                "call": "compat.HestonObjective (heston_calibration.py:404-472), rows rank::world, one fused launch per rank + "
+                        "one all_gather of the prices"}
     barrier()
 
-    # the other BASELINE configs, one short measurement each (rank 0 only; reported as context, not as `value`)
-    others = {}
-    if rank == 0 and not args.no_other_configs:
-        def timed(fn, reps):
-            fn()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(reps):
-                out = fn()
-            torch.cuda.synchronize()
-            return (time.perf_counter() - t0) / reps, out
-
+    # the other BASELINE configs on one GPU (rank 0 of a single-GPU run; reported as context, not as `value`)
+    if rank == 0 and world == 1 and not args.no_other_configs:
         with torch.cuda.stream(stream):
             gbm = E.gbm(S0, R, T, 0.2)
             dt1, r1 = timed(lambda: eng.price_american(gbm, 100_000, 50, K, "put", "f32", E.RngSpec(seed=7)), 20)
             others["config1_gbm_100k_x50"] = {"ms": dt1 * 1e3, "path_steps_per_s": 100_000 * 50 / dt1, "price": r1.price}
-            # config 2 as ONE option at growing path counts (the latency -> bandwidth transition): 1 M and 4 M run the
-            # persistent sweep (cash-flows in registers), 16 M exceeds its on-chip capacity and runs the split kernels
-            for Mx in (1_000_000, 4_000_000, 16_000_000):
-                dtx, rx = timed(lambda: eng.price_american(model, Mx, N, K, "put", "f32", E.RngSpec(seed=17)), 2)
-                pk, sk = eng.kernel_times()
-                others[f"config2_single_option_{Mx // 1_000_000}M_x252"] = {
-                    "ms": dtx * 1e3, "path_steps_per_s": Mx * N / dtx, "paths_kernel_ms": pk, "sweep_ms": sk,
-                    "sweep": "persistent" if rx.impl_used == L.SWEEP_RESIDENT else "split", "price": rx.price}
-            Kg, Tg = np.meshgrid(np.linspace(70, 130, 32), np.linspace(1 / 12, 2, 32))
-            n4 = 128  # one GPU's share of the 1024-option grid at 8 GPUs
-            dt4, r4 = timed(lambda: eng.price_american_batch(model, 262_144, S0, Kg.ravel()[:n4], Tg.ravel()[:n4],
-                                                             np.full(n4, 252), 1, "f32", E.RngSpec(seed=9)), 1)
-            others["config4_128_options_x_256k_x252"] = {"ms": dt4 * 1e3, "path_steps_per_s": n4 * 262_144 * 252 / dt4,
-                                                         "us_per_option": dt4 / n4 * 1e6}
+            # config 2 AS STATED: one option of 1 M paths (the per-date dependency chain, not bandwidth, bounds it), both semantics;
+            # then growing path counts (latency -> bandwidth): 4 M persistent, 16 M split sweep
+            for Mx, sems in ((1_000_000, ("reference", "textbook")), (4_000_000, ("reference",)), (16_000_000, ("reference",))):
+                for sem in sems:
+                    dtx, rx = timed(lambda: eng.price_american(model, Mx, N, K, "put", "f32", E.RngSpec(seed=17), semantics=sem), 3)
+                    pk, sk = eng.kernel_times()
+                    others[f"config2_single_option_{Mx // 1_000_000}M_x252" + ("" if sem == "reference" else "_textbook")] = {
+                        "ms": dtx * 1e3, "path_steps_per_s": Mx * N / dtx, "paths_kernel_ms": pk, "sweep_ms": sk,
+                        "pipeline_frac": 4 * b * Mx * N / (dtx * 1e9) / peak,
+                        "paths_frac": b * Mx * (N + 1) / (pk * 1e6) / peak if pk else None,
+                        "sweep_frac": (3 * b * Mx * (N - 1) + b * Mx) / (sk * 1e6) / peak if sk else None,
+                        "sweep": "persistent" if rx.impl_used == L.SWEEP_RESIDENT else "split", "price": rx.price}
+            dtt, (pt, _) = timed(lambda: eng.price_american_batch(model, M, S0, K, T, Ns, 1, "f32", E.RngSpec(seed=42),
+                                                                 "poly2", "textbook"), 3)
+            pk, sk = eng.kernel_times()
+            others["config2_batch4_textbook"] = {"ms": dtt * 1e3, "path_steps_per_s": B * M * N / dtt, "paths_kernel_ms": pk,
+                                                 "sweep_ms": sk, "pipeline_frac": 4 * b * B * M * N / (dtt * 1e9) / peak,
+                                                 "price": float(pt[0]),
+                                                 "note": "textbook semantics (no sticky mask: ~40% of the paths in every regression, dense passes)"}
             # local volatility: ImprovedIVNetwork(2 -> 64, 4 residual LayerNorm/GELU blocks) inside every step
             rs = np.random.default_rng(0)
             Hn, Ln = 64, 4
@@ -342,11 +411,6 @@ def run_own_arm(args):
             others["config3_nn_lsm_4M_x252_hidden128_tcgen05"] = {"ms": dt3 * 1e3, "path_steps_per_s": 4_000_000 * 252 / dt3,
                                                                    "price": r3.price, "note": "sweep only (paths resident)"}
             del S4
-            Kc, Tc = np.meshgrid(np.linspace(80, 120, 20), np.linspace(0.1, 1.0, 10))
-            calib = E.heston(S0, R, T, scheme=L.SCHEME_HESTON_REF_CALIB, **HP)
-            dt5, r5 = timed(lambda: eng.price_european_batch(calib, 50_000, 100, Kc.ravel(), Tc.ravel(),
-                                                             np.zeros(200, dtype=np.int32), "f32", E.RngSpec(seed=13)), 3)
-            others["config5_calibration_objective_200x50k_x100"] = {"ms": dt5 * 1e3, "path_steps_per_s": 1e9 / dt5}
             Sg = eng.paths(model, M, N, "f32", E.RngSpec(seed=15))
             dtg, rg = timed(lambda: eng.lsm_global(Sg, K, R, T, "put", arrays=False), 3)
             others["global_regression_lsm_1M_x252"] = {"ms": dtg * 1e3, "slab_GBps": 2 * b * M * (N + 1) / dtg / 1e9,
@@ -354,17 +418,11 @@ def run_own_arm(args):
             del Sg
     barrier()
 
-    if dist is not None:
-        t = torch.tensor([ms_total, e2e_s * 1e3], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_ms = float(t[0]), float(t[1])
-    else:
-        e2e_ms = e2e_s * 1e3
-
+    rc = 0
     if rank == 0:
         import ctypes
 
-        peak, peak_src = load_peaks()
+        traffic = load_traffic()
         path_steps = world * B * M * N * args.steps
         value = path_steps / (ms_total * 1e-3)
         # algorithmic bytes: generation b per path-step (rows 0..N stored); sweep 3b per path
@@ -372,60 +430,75 @@ def run_own_arm(args):
         bytes_paths = B * b * M * (N + 1)                     # one batched launch generates B slabs
         bytes_sweep = B * (3 * b * M * (N - 1) + b * M)       # one grouped launch sweeps B options
         kern = {
-            "paths_batch_kernel<f32,heston_ref_absorb,vec4>": {
+            "paths_x2_batch_kernel<heston_ref_absorb> (f32x2 packed step, 3 steps per Philox block)": {
                 "ms": ms_paths, "alg_bytes": bytes_paths, "GBps": bytes_paths / (ms_paths * 1e-3) / 1e9,
-                "dram_bytes_ncu": load_traffic("paths_batch_kernel")},
-            "lsm_resident_kernel<f32,poly2,sparse>": {
+                "frac": bytes_paths / (ms_paths * 1e-3) / 1e9 / peak, "dram_bytes_ncu": traffic["paths"]},
+            "lsm_resident_kernel<f32,poly2,sparse> (grouped, 4 x 37 CTAs)": {
                 "ms": ms_sweep, "alg_bytes": bytes_sweep, "GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9,
-                "dram_bytes_ncu": load_traffic("lsm_resident_kernel")},
+                "frac": bytes_sweep / (ms_sweep * 1e-3) / 1e9 / peak, "dram_bytes_ncu": traffic["sweep"]},
         }
         dom = max(kern, key=lambda k: kern[k]["ms"])
         ach = kern[dom]["GBps"]
         cpu = cpu_baseline_single(args.cpu_paths, N) if world == 1 and not args.no_cpu else None
         h2d = ctypes.sizeof(L.ModelParams) + ctypes.sizeof(L.RngParams) + B * ctypes.sizeof(L.AmericanOption)
+        sharding = {"none": "single GPU",
+                    "paths": f"PATHS of every option across the {world} ranks (each option {world * M} paths); per-date Gram "
+                             "totals exchanged inside the sweep kernel over NVLink peer memory, no collective launch",
+                    "options": "options across ranks (no data-path collective)"}[shard]
+        single = others.get("config2_single_option_1M_x252")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE config 2: American put, Heston (kappa=2, theta=0.04, xi=0.5, rho=-0.7), "
-                                   f"{N} steps, {M} paths per option, poly2 LSM (reference semantics); a step prices a batch "
-                                   f"of {B} independent options of that size per GPU in one grouped launch",
-                       "batch": B,
+            "config": {"workload": workload_string(N, M, B), "batch": B,
                        "storage": "fp32 step-major slab, fp64 Gram/solve/decision", "rng": "Philox4x32-10 in-register",
-                       "sharding": "options across ranks (no data-path collective)",
+                       "sharding": sharding, "shard_mode": shard,
                        "l2": f"slabs {B * b * M * (N + 1) / 1e6:.0f} MB per step > L2 ({eng.l2_bytes / 1e6:.0f} MB): no flush needed",
-                       "price": res.price, "stderr": res.stderr},
+                       "price": price0, "stderr": se0, "git": git_head()},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": kern[dom]["dram_bytes_ncu"], "kernel": dom, "peak_source": peak_src,
+                         "traffic_source": f"{traffic['source']} (ncu dram__bytes_read+write per launch, build {traffic['git']})",
                          "note": "achieved = algorithmic bytes (SURVEY 8d: 3b per path per exercise date for the sweep, "
-                                 "b per path-step for generation) / CUDA-event time of that kernel; traffic = DRAM bytes "
-                                 "per launch from the committed ncu capture (profiles/)",
+                                 "b per path-step for generation) / CUDA-event time of that kernel, measured in this run",
                          "dram_frac": (kern[dom]["dram_bytes_ncu"] / (kern[dom]["ms"] * 1e-3) / 1e9 / peak
                                        if kern[dom]["dram_bytes_ncu"] else None),
-                         "dram_note": "dram_frac = measured DRAM traffic of the kernel / its time / peak: the sweep keeps the "
+                         "dram_note": "dram_frac = ncu DRAM traffic of the kernel / its time / peak: the sweep keeps the "
                                       "cash-flows in registers, so 2b of the 3b algorithmic bytes per path-date never reach HBM "
-                                      "and frac (algorithmic) exceeds 1",
+                                      "and frac (algorithmic) exceeds 1; the path kernel is bound by the FMA (Philox IMAD.WIDE) "
+                                      "and MUFU pipes, not by HBM (profiles/paths_bench_r2.txt)",
                          "pipeline_frac": (4 * b * B * M * N * world * args.steps) / (ms_total * 1e-3) / 1e9 / (peak * world),
+                         "pipeline_frac_single_option": single["pipeline_frac"] if single else None,
                          "kernels": kern},
             "e2e": {"value": world * B * M * N * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 48 * B, "ms_per_step": e2e_ms / args.steps, "price": price_e2e,
-                    "call": "compat.AdvancedOptionPricer.price_american_grid -> optmc_price_american_batch (host option "
+                    "call": "compat.AdvancedOptionPricer.price_american_grid -> optmc_price_american_batch(_ex) (host option "
                             "scalars in, host prices out; the path's inputs are option/model scalars, normals are "
                             "generated in-kernel)"},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
         }
-        if sharded_info:
-            others["path_sharded_single_option"] = sharded_info
+        if parity:
+            line["path_sharded_parity"] = parity
+            if not (parity["rel_vs_single"] == 0.0 and parity["identical_on_all_ranks"]):
+                rc = 1
         if others:
             line["other_configs"] = others
         if cpu:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
+        if rc:
+            print("bench.py: path-sharded prices differ from the single-GPU prices", file=sys.stderr, flush=True)
     if dist is not None:
+        flag = torch.tensor([rc], device="cuda")
+        dist.broadcast(flag, src=0)
+        rc = int(flag[0])
+        if shard == "paths":
+            eng.comm_finalize()
         dist.barrier()
         dist.destroy_process_group()
     eng.close()
+    if rc:
+        sys.exit(rc)
 
 
 def main():
@@ -434,13 +507,14 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--paths", type=int, default=1_000_000)
+    ap.add_argument("--shard", default="auto", choices=["auto", "paths", "options"],
+                    help="N > 1: split every option's paths over the ranks (default) or give every rank its own options")
+    ap.add_argument("--paths", type=int, default=1_000_000, help="paths per option per GPU")
     ap.add_argument("--dates", type=int, default=252)
-    ap.add_argument("--batch", type=int, default=4, help="independent options priced per step (one grouped launch)")
+    ap.add_argument("--batch", type=int, default=4, help="options priced per step (one grouped launch)")
     ap.add_argument("--cpu-paths", type=int, default=1_000_000, help="CPU-baseline sample size (paths)")
-    ap.add_argument("--ref-paths", type=int, default=50_000, help="reference arm: paths per worker per step")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of BASELINE configs 1/3/4/5")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of the other BASELINE configs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "own":
         args.warmup = 3

@@ -388,6 +388,14 @@ int optmc_price_american_batch_ex(optmc_ctx* ctx, const optmc_model_params* mp, 
                                   const optmc_american_option* opts, optmc_price_result* results,
                                   optmc_batch_extras* extras);
 
+/* The same fused kernel with per-option spot and step count: the INDEPENDENT European leg of a whole S0 x maturity
+ * curve with the control variate on (om3:653-677 inside om3:697-713: one price_european_streaming per grid point,
+ * steps = max(10, min(130, ceil(days)))) as one launch.  S0 may be NULL (mp->S0 for every option). */
+int optmc_price_european_grid(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                              int32_t dtype, int32_t n_options, const double* S0, const double* K, const double* T,
+                              const int32_t* N, const int32_t* is_put, const int32_t* stream_id,
+                              optmc_european_result* results);
+
 /* price_european_streaming / price_european_gpu / HestonPricer.price_european_option
  * (om3:382-437, om3gpu:605-653, hc:259-281): paths are generated and reduced in registers, nothing is
  * stored.  n_options options share mp/rng except K[i], T[i], is_put[i]; option i uses Philox stream

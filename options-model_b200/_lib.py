@@ -55,6 +55,12 @@ class PriceResult(C.Structure):
     _fields_ = [("price", C.c_double), ("stderr_", C.c_double)]
 
 
+class BatchExtras(C.Structure):  # optmc_batch_extras
+    _fields_ = [("ex_count", C.POINTER(C.c_int64)), ("boundary", C.POINTER(C.c_double)), ("betas", C.POINTER(C.c_double)),
+                ("n_itm", C.POINTER(C.c_int64)), ("ld_dates", C.c_int32), ("reserved", C.c_int32),
+                ("european", C.POINTER(C.c_double)), ("shape", C.c_int32 * 4), ("M_total", C.c_int64)]
+
+
 class MlpParams(C.Structure):
     _fields_ = [("hidden", C.c_int32), ("epochs", C.c_int32), ("lr", C.c_double), ("seed", C.c_uint64)]
 
@@ -143,9 +149,15 @@ PROTOTYPES = {
                                        _P(LsmParams), _P(LsmResult)]),
     "optmc_price_american_batch": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
                                              C.c_uint32, C.c_int32, _P(AmericanOption), _P(PriceResult)]),
+    "optmc_price_american_batch_ex": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32,
+                                                C.c_int32, C.c_uint32, C.c_int32, _P(AmericanOption), _P(PriceResult),
+                                                _P(BatchExtras)]),
     "optmc_price_european_batch": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32,
                                              C.c_int32, C.c_int32, _P(C.c_double), _P(C.c_double), _P(C.c_int32),
                                              _P(C.c_int32), _P(EuropeanResult)]),
+    "optmc_price_european_grid": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
+                                            _P(C.c_double), _P(C.c_double), _P(C.c_double), _P(C.c_int32), _P(C.c_int32),
+                                            _P(C.c_int32), _P(EuropeanResult)]),
     "optmc_european_from_slab": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double,
                                            C.c_double, C.c_int32, _P(EuropeanResult)]),
     "optmc_features_ref7": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_double,

@@ -292,7 +292,7 @@ class AdvancedOptionPricer:
                  # engine extensions (not in the reference)
                  lsm_regressor: str = "poly2", semantics: str = "reference", dtype: str = "f32", device: int = 0,
                  gpu_reference_quirks: bool = False, batched: bool = True, out_of_sample: bool = False,
-                 control_variate_same_paths: bool = False):
+                 control_variate_same_paths: bool = False, path_shard: Optional[Tuple[int, int]] = None):
         self.K = K
         self.r = r
         self.sigma = sigma
@@ -316,6 +316,9 @@ class AdvancedOptionPricer:
         self.batched = batched
         self.out_of_sample = out_of_sample  # fit the polynomial on one path set, exercise on an independent one
         self.control_variate_same_paths = control_variate_same_paths  # European leg on the American paths
+        # (rank, world) of a path-sharded pricer: price_american_grid prices num_simulations paths PER RANK
+        # of every option, the sweep exchanges its totals over NVLink (sharded.init_peer_exchange first)
+        self.path_shard = path_shard
         self.last_result: Optional[E.SweepResult] = None
         self._lsm_net = None      # om3gpu:596: the torch-GPU file caches its network across pricing calls
         self._nn_variant = "cpu"  # training defaults of om3:565-613; the *_gpu entry point switches to om3gpu:740-798
@@ -373,11 +376,14 @@ class AdvancedOptionPricer:
             self.last_result = out
             return float(out["price"])
         eng = _engine(self.device)
+        # Philox key = the master seed, stream = this pricing's child seed: the convention of price_american_grid, so
+        # the batched curve and the per-point loop return identical prices point by point
         res = eng.price_american(model, M, int(num_time_steps), self.K, self.option_type, self.dtype,
-                                 E.RngSpec(seed=seed), basis=self.lsm_regressor,
+                                 E.RngSpec(seed=self.rng_manager.master_seed, stream=seed), basis=self.lsm_regressor,
                                  semantics=self.semantics, arrays=self.verbose or self.out_of_sample)
-        if self.out_of_sample:  # the fitted policy priced on fresh paths (Philox stream 1 of the same seed)
-            S_new = eng.paths(model, M, int(num_time_steps), self.dtype, E.RngSpec(seed=seed, stream=1))
+        if self.out_of_sample:  # the fitted policy priced on fresh paths (the next Philox key, same stream)
+            S_new = eng.paths(model, M, int(num_time_steps), self.dtype,
+                              E.RngSpec(seed=self.rng_manager.master_seed + 1, stream=seed))
             res = eng.lsm_apply_policy(S_new, res.betas, self.K, self.r, T, self.option_type, self.lsm_regressor,
                                        self.semantics, arrays=self.verbose)
         self.last_result = res
@@ -405,12 +411,22 @@ class AdvancedOptionPricer:
         advances once per reference chunk (om3:392) so later calls see the same seed tree."""
         n_chunks = max(1, -(-int(num_simulations) // int(self.chunk_size)))
         seeds = [int(self.rng_manager.get_child_seed()) for _ in range(n_chunks)]
-        model = self._model(S0, T)
         n = int(num_simulations)
         anti = n % 2 == 0
+        if self.iv_model is not None:  # om3:394-395: local-volatility paths, then the payoff of the terminal row
+            eng = _engine(self.device)
+            M = n // 2 * 2
+            S = eng.paths_localvol(S0, self.r, T, self.iv_model.net, self.K, M, int(num_time_steps), self.dtype,
+                                   E.RngSpec(seed=seeds[0], stream=0x45))
+            mean, se = eng.european_from_slab(S[int(num_time_steps)].contiguous(), self.K, self.r, T, self.option_type)
+            if self.verbose:
+                print(f"European streaming MC: {mean:.4f} ± {se:.4f} (n={M})")
+            return float(mean)
+        model = self._model(S0, T)
         mean, se = _engine(self.device).price_european_batch(model, n, int(num_time_steps), [self.K], [T],
                                                              [1 if self.option_type == "put" else 0], self.dtype,
-                                                             E.RngSpec(seed=seeds[0], stream=0x45, antithetic=anti))
+                                                             E.RngSpec(seed=self.rng_manager.master_seed,
+                                                                       stream=0x45 + (seeds[0] & 0x7FFFFFFF), antithetic=anti))
         if self.verbose:
             print(f"European streaming MC: {mean[0]:.4f} ± {se[0]:.4f} (n={n})")
         return float(mean[0])
@@ -431,7 +447,7 @@ class AdvancedOptionPricer:
             self.rng_manager.get_child_seed()
             M, N = num_simulations // 2 * 2, int(num_time_steps)
             eng = _engine(self.device)
-            S = eng.paths(self._model(S0, T), M, N, self.dtype, E.RngSpec(seed=seed))
+            S = eng.paths(self._model(S0, T), M, N, self.dtype, E.RngSpec(seed=self.rng_manager.master_seed, stream=seed))
             res = eng.lsm(S, self.K, self.r, T, self.option_type, self.lsm_regressor, self.semantics, arrays=False)
             eu_mc, _ = eng.european_from_slab(S[N].contiguous(), self.K, self.r, T, self.option_type)
             eu_exact = BlackScholesGreeks.black_scholes_price(S0, self.K, T, self.r, self.sigma, self.option_type)
@@ -459,7 +475,8 @@ class AdvancedOptionPricer:
             return self.price_american_with_control_variate(S0, T, num_simulations, num_time_steps)
         return self.price_american_enhanced_lsm(S0, T, num_simulations, num_time_steps)
 
-    def price_american_grid(self, S0, T, num_time_steps, num_simulations: int = 10000, K=None):
+    def price_american_grid(self, S0, T, num_time_steps, num_simulations: int = 10000, K=None, european: bool = False,
+                            seeds=None):
         """Engine extension: price a whole grid (arrays S0 / T / steps / K broadcast against each other) with
         optmc_price_american_batch -- what the reference does with one price_american_enhanced_lsm call per
         grid point (om3:706-712).  The master generator advances exactly as in the per-point loop (om3:454-455);
@@ -475,27 +492,67 @@ class AdvancedOptionPricer:
             raise ValueError("r must be non-negative.")
         if num_simulations <= 0 or np.any(Na <= 0):
             raise ValueError("num_simulations and num_time_steps must be positive integers.")
-        seeds = []
-        for _ in range(S0a.size):
-            seeds.append(int(self.rng_manager.master_rng.integers(0, 2**31 - 1)))  # om3:454
-            self.rng_manager.get_child_seed()                                      # om3:455
+        if seeds is None:
+            seeds = []
+            for _ in range(S0a.size):
+                seeds.append(int(self.rng_manager.master_rng.integers(0, 2**31 - 1)))  # om3:454
+                self.rng_manager.get_child_seed()                                      # om3:455
         M = num_simulations // 2 * 2
         model = self._model(float(S0a[0]), float(Ta[0]))
-        price, se = _engine(self.device).price_american_batch(
-            model, M, S0a, Ka, Ta, Na, 1 if self.option_type == "put" else 0, self.dtype,
-            E.RngSpec(seed=self.rng_manager.master_seed), basis=self.lsm_regressor, semantics=self.semantics,
-            streams=seeds)
+        rng = E.RngSpec(seed=self.rng_manager.master_seed)
+        M_total = 0
+        if self.path_shard is not None:
+            rank, world = self.path_shard
+            M_total = M * world
+            rng = E.RngSpec(seed=self.rng_manager.master_seed, pair_offset=rank * (M // 2))
+        out = _engine(self.device).price_american_batch(
+            model, M, S0a, Ka, Ta, Na, 1 if self.option_type == "put" else 0, self.dtype, rng,
+            basis=self.lsm_regressor, semantics=self.semantics, streams=seeds, european=european, M_total=M_total)
+        if european or M_total:
+            price, se, extras = out
+            if european:
+                return price.reshape(shape), se.reshape(shape), extras["european"][:, 0].reshape(shape)
+        else:
+            price, se = out
         return price.reshape(shape), se.reshape(shape)
 
     def compute_curve_for_S0(self, S0: float, intervals_per_day: int, total_points: int, num_simulations: int,
                              plot_paths: bool) -> List[Dict[str, Any]]:
-        """om3:697-713.  Without the control variate the whole curve is one batched engine call."""
+        """om3:697-713.  The whole curve is one batched engine call (two with the independent control-variate leg):
+        price_american_option's default route (om3:692-693) is american + (BS - european_MC); the European leg is either
+        reduced from each option's OWN terminal row inside the grouped sweep launch (control_variate_same_paths) or
+        priced on independent paths by one fused optmc_price_european_grid launch, as the reference's
+        price_european_streaming call per grid point does.  The generators advance exactly as in the per-point loop."""
         cv = self.use_control_variate and self.sigma is not None
         eu = self.use_streaming and self.european_approximation
-        if self.batched and not cv and not eu and total_points > 0:
+        grid_ok = self.batched and not eu and total_points > 0 and self.iv_model is None and self.lsm_regressor != "nn"
+        if grid_ok:
             days = np.array([i / intervals_per_day for i in range(total_points, 0, -1)])
             steps = np.maximum(10, np.minimum(130, np.ceil(days))).astype(np.int64)
-            prices, _ = self.price_american_grid(S0, days / 365, steps, num_simulations)
+            T = days / 365
+            if not cv:
+                prices, _ = self.price_american_grid(S0, T, steps, num_simulations)
+            else:
+                n_chunks = max(1, -(-int(num_simulations) // int(self.chunk_size)))
+                am_seeds, eu_seeds = [], []
+                for _ in range(total_points):  # per point: the American draws (om3:454-455), then the European chunks (om3:392)
+                    am_seeds.append(int(self.rng_manager.master_rng.integers(0, 2**31 - 1)))
+                    self.rng_manager.get_child_seed()
+                    if not self.control_variate_same_paths:
+                        eu_seeds.append([int(self.rng_manager.get_child_seed()) for _ in range(n_chunks)][0] & 0x7FFFFFFF)
+                put = 1 if self.option_type == "put" else 0
+                if self.control_variate_same_paths:
+                    am, _, eu_mc = self.price_american_grid(S0, T, steps, num_simulations, european=True, seeds=am_seeds)
+                else:
+                    am, _ = self.price_american_grid(S0, T, steps, num_simulations, seeds=am_seeds)
+                    n = int(num_simulations)
+                    eu_mc, _ = _engine(self.device).price_european_grid(
+                        self._model(S0, float(T[0])), n, S0, self.K, T, steps, put, self.dtype,
+                        E.RngSpec(seed=self.rng_manager.master_seed, stream=0x45, antithetic=n % 2 == 0),
+                        stream_id=np.asarray(eu_seeds, dtype=np.int64).astype(np.int32))
+                exact = np.array([BlackScholesGreeks.black_scholes_price(S0, self.K, float(t), self.r, self.sigma,
+                                                                         self.option_type) for t in T])
+                prices = am + 1.0 * (exact - eu_mc)
             return [{"S0": S0, "Days to Expiry": float(d), "Option Value": float(p)} for d, p in zip(days, prices)]
         records = []
         for i in range(total_points, 0, -1):
@@ -845,7 +902,15 @@ class HestonObjective:
     common_random_numbers=True keeps the Philox key fixed across evaluations: a smooth objective for
     gradient-based optimisers instead of the reference's re-seeded noise."""
 
-    def __init__(self, pricer: "HestonPricer", S0: float, r: float, K, T, sigma_iv, common_random_numbers: bool = False):
+    def __init__(self, pricer: "HestonPricer", S0: float, r: float, K, T, sigma_iv, common_random_numbers: bool = False,
+                 rank: int = 0, world: int = 1, all_gather=None):
+        """rank / world / all_gather: option-sharded evaluation over several GPUs (the reference loops over
+        the rows, hc:424-433): every rank prices rows rank::world in one launch, ``all_gather(local_prices) ->
+        [prices of rank 0, rank 1, ...]`` (host plumbing, e.g. torch.distributed.all_gather_object) is the only exchange,
+        and every rank returns the same objective.  All ranks must construct the pricer with the same seed."""
+        self.rank, self.world, self.all_gather = int(rank), int(world), all_gather
+        if self.world > 1 and all_gather is None:
+            raise ValueError("world > 1 needs an all_gather callable")
         self.pricer, self.S0, self.r = pricer, float(S0), float(r)
         self.K = np.asarray(K, dtype=np.float64).ravel()
         self.T = np.asarray(T, dtype=np.float64).ravel()
@@ -859,11 +924,20 @@ class HestonObjective:
         seed = self._seed if self.crn else int(self.pricer.rng.integers(0, 2**63 - 1))
         M = cfg.n_mc_paths // 2 * 2 if cfg.use_antithetic else cfg.n_mc_paths
         n = len(self.K)
-        mean, _ = _engine(self.pricer.device).price_european_batch(
-            self.pricer._model(params, self.S0, float(self.T[0]), self.r), M, cfg.n_time_steps, self.K, self.T,
-            np.zeros(n, dtype=np.int32), self.pricer.dtype, E.RngSpec(seed=seed, antithetic=bool(cfg.use_antithetic)),
-            stream_id=np.arange(n, dtype=np.int32))
-        return np.asarray(mean)
+        rows = np.arange(self.rank, n, self.world)  # this rank's rows; row i keeps Philox stream i on any rank count
+        mean = np.zeros(0)
+        if rows.size:
+            mean, _ = _engine(self.pricer.device).price_european_batch(
+                self.pricer._model(params, self.S0, float(self.T[0]), self.r), M, cfg.n_time_steps, self.K[rows],
+                self.T[rows], np.zeros(rows.size, dtype=np.int32), self.pricer.dtype,
+                E.RngSpec(seed=seed, antithetic=bool(cfg.use_antithetic)), stream_id=rows.astype(np.int32))
+        if self.world == 1:
+            return np.asarray(mean)
+        parts = self.all_gather(np.asarray(mean))
+        out = np.empty(n)
+        for rk, part in enumerate(parts):
+            out[rk::self.world] = np.asarray(part)
+        return out
 
     def __call__(self, x) -> float:
         try:

@@ -630,6 +630,17 @@ int optmc_price_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, con
   OPTMC_TRY_END
 }
 
+int optmc_price_european_grid(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
+                              int32_t dtype, int32_t n_options, const double* S0, const double* K, const double* T,
+                              const int32_t* N, const int32_t* is_put, const int32_t* stream_id,
+                              optmc_european_result* results) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  if (!N) { set_error("null argument"); return OPTMC_EINVAL; }
+  return launch_european_batch(ctx, mp, rng, M, N[0], dtype, n_options, K, T, is_put, stream_id, results, N, S0);
+  OPTMC_TRY_END
+}
+
 int optmc_european_from_slab(optmc_ctx* ctx, const void* ST_dev, int64_t M, int32_t dtype, double K, double r,
                              double T, int32_t is_put, optmc_european_result* out) {
   OPTMC_TRY_BEGIN

@@ -22,7 +22,7 @@ struct EuArgs {
   unsigned int stream;
   long long pair_offset;
   double S0, v0, r, sigma, kappa, theta, xi, rho, rho_c;
-  const double* par;  // [n_options][4]: K, T, is_put, stream id
+  const double* par;  // [n_options][6]: K, T, is_put, stream id, N (0: a.N), S0 (0: a.S0)
   double* partials;   // [n_options][gridDim.x][2]
   unsigned int* tickets;  // [n_options]
   double* out;        // [n_options][3]: mean, stderr, n
@@ -36,9 +36,11 @@ __global__ void __launch_bounds__(kEuThreads) european_fused_kernel(const EuArgs
   __shared__ double red[kEuWarps * 2];
   __shared__ bool is_last;
   const int opt = blockIdx.y;
-  const double K = a.par[opt * 4 + 0], T = a.par[opt * 4 + 1];
-  const bool is_put = a.par[opt * 4 + 2] != 0.0;
-  const double dt = T / a.N;
+  const double K = a.par[opt * 6 + 0], T = a.par[opt * 6 + 1];
+  const bool is_put = a.par[opt * 6 + 2] != 0.0;
+  const int N = a.par[opt * 6 + 4] > 0.0 ? (int)a.par[opt * 6 + 4] : a.N;  // per-option steps (curve drivers, om3:709)
+  const double S0 = a.par[opt * 6 + 5] > 0.0 ? a.par[opt * 6 + 5] : a.S0;
+  const double dt = T / N;
   GbmConsts<R> gc;
   gc.drift = (R)((a.r - 0.5 * a.sigma * a.sigma) * dt);
   gc.diffusion = (R)(a.sigma * sqrt(dt));
@@ -48,14 +50,14 @@ __global__ void __launch_bounds__(kEuThreads) european_fused_kernel(const EuArgs
   QeConsts<R> qe{};
   if (SCHEME == OPTMC_SCHEME_HESTON_QE) qe = qe_consts(hc);
   const double df = exp(-a.r * T);
-  const unsigned int stream = a.stream + (unsigned int)a.par[opt * 4 + 3];
+  const unsigned int stream = a.stream + (unsigned int)a.par[opt * 6 + 3];
   const bool anti = a.anti != 0;
 
   double acc[2] = {0.0, 0.0};
   for (long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x; col < a.Mh;
        col += (long long)gridDim.x * blockDim.x) {
-    R sp = (R)a.S0, sm = (R)a.S0, vp = (R)a.v0, vm = (R)a.v0;
-    for (int t0 = 0; t0 < a.N; t0 += SPB) {
+    R sp = (R)S0, sm = (R)S0, vp = (R)a.v0, vm = (R)a.v0;
+    for (int t0 = 0; t0 < N; t0 += SPB) {
       R n[6];
       Philox4 p = philox_for((unsigned long long)(a.pair_offset + col), (unsigned int)(t0 / SPB), stream, a.seed);
       if constexpr (F32H) {
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(kEuThreads) european_fused_kernel(const EuArgs
       }
 #pragma unroll
       for (int s = 0; s < SPB; ++s) {
-        if (t0 + s + 1 > a.N) break;
+        if (t0 + s + 1 > N) break;
         const R z1 = HES ? n[2 * s] : n[s];
         const R z2 = HES ? n[2 * s + 1] : (R)0;
         if (HES) {
@@ -134,7 +136,8 @@ template <typename R> static void launch_eu_scheme(int scheme, dim3 grid, cudaSt
 
 int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                           int32_t N, int32_t dtype, int32_t n_options, const double* K, const double* T,
-                          const int32_t* is_put, const int32_t* stream_id, optmc_european_result* results) {
+                          const int32_t* is_put, const int32_t* stream_id, optmc_european_result* results,
+                          const int32_t* N_opt, const double* S0_opt) {
   if (!mp || !rng || !K || !T || !is_put || !results) { set_error("null argument"); return OPTMC_EINVAL; }
   if (n_options <= 0 || n_options > 65535) { set_error("n_options must be in [1, 65535]"); return OPTMC_EINVAL; }
   if (M <= 0 || N <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
@@ -157,7 +160,7 @@ int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const op
   long long cap = ((long long)ctx->sm_count * 8 * 4 + n_options - 1) / n_options;
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
-  int rc = ensure_bytes((void**)&ctx->eu_par, &ctx->eu_par_cap, (size_t)n_options * 4 * sizeof(double));
+  int rc = ensure_bytes((void**)&ctx->eu_par, &ctx->eu_par_cap, (size_t)n_options * 6 * sizeof(double));
   if (rc) return rc;
   rc = ensure_bytes((void**)&ctx->eu_out, &ctx->eu_out_cap, (size_t)n_options * 3 * sizeof(double));
   if (rc) return rc;
@@ -169,9 +172,16 @@ int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const op
     OPTMC_CUDA(cudaMemsetAsync(ctx->eu_tickets, 0, ctx->eu_tickets_cap, ctx->stream));
   }
   unsigned int* tickets = ctx->eu_tickets;
-  std::string par(sizeof(double) * 4 * n_options, '\0');
+  std::string par(sizeof(double) * 6 * n_options, '\0');
   double* hp = reinterpret_cast<double*>(&par[0]);
-  for (int i = 0; i < n_options; ++i) { hp[4 * i] = K[i]; hp[4 * i + 1] = T[i]; hp[4 * i + 2] = is_put[i] ? 1.0 : 0.0; hp[4 * i + 3] = (double)(stream_id ? stream_id[i] : i); }
+  for (int i = 0; i < n_options; ++i) {
+    if (N_opt && N_opt[i] <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
+    if (S0_opt && !(S0_opt[i] > 0)) { set_error("S0, K, T must be positive."); return OPTMC_EINVAL; }
+    hp[6 * i] = K[i]; hp[6 * i + 1] = T[i]; hp[6 * i + 2] = is_put[i] ? 1.0 : 0.0;
+    hp[6 * i + 3] = (double)(stream_id ? stream_id[i] : i);
+    hp[6 * i + 4] = N_opt ? (double)N_opt[i] : 0.0;
+    hp[6 * i + 5] = S0_opt ? S0_opt[i] : 0.0;
+  }
   OPTMC_CUDA(cudaMemcpyAsync(ctx->eu_par, hp, par.size(), cudaMemcpyHostToDevice, ctx->stream));
   a.par = ctx->eu_par; a.partials = ctx->partials; a.tickets = tickets; a.out = ctx->eu_out;
   dim3 grid((unsigned)gx, (unsigned)n_options);

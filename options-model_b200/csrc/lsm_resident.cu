@@ -346,7 +346,7 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
     pw.ngroups = g_now;
     ResArgs a{};
     a.groups = d_groups; a.cpg = cpg; a.nstage = p.nstage; a.stage_stride = p.stage_stride; a.sticky = sticky ? 1 : 0;
-    a.want_eu = (want_eu && p.spec) ? 1 : 0;
+    a.want_eu = want_eu ? 1 : 0;
     if (M_total) {  // in-kernel exchange with the peer ranks, one slot block per group
       a.comm.nranks = ctx->comm.nranks; a.comm.rank = ctx->comm.rank; a.comm.g0 = ctx->comm.g;
       a.comm.M_total = M_total;

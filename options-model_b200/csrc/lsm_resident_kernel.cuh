@@ -486,11 +486,39 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
     }
   }
 
+  int seq = 0;
+  if (ga.want_eu) {  // European leg on the option's own paths (om3:653-677): exp(-rT) payoff(S_N), summed like the price
+    double eu[2] = {0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < PPT; ++k) {
+      const double c = (double)cf[k];
+      eu[0] += c;
+      eu[1] += c * c;
+    }
+    const double mine_eu = block_totals<2, NW>(eu, s_red);
+    if (warp == 0) {
+      unsigned long long pv = prev0;
+      const double tot_l = warp0_grid_sum<2>(mine_eu, a.xw, 0, ncta, pv, a.flags, nullptr, ga.comm, 0u, cta, comm_dead, slot_off);
+      prev0 = pv;
+      const double s1 = __shfl_sync(0xffffffffu, tot_l, 0), s2 = __shfl_sync(0xffffffffu, tot_l, 1);
+      if (cta == 0 && lane == 0) {
+        const double n = (double)a.M_total;
+        const double mean = s1 / n;
+        double var = n > 1.0 ? (s2 - n * mean * mean) / (n - 1.0) : 0.0;
+        if (var < 0.0) var = 0.0;
+        double df = 1.0;
+        for (int i = 0; i < N; ++i) df *= a.disc;
+        a.final_out[4] = mean * df;
+        a.final_out[5] = sqrt(var / n) * df;
+      }
+    }
+    seq = 1;
+  }
+
   // Iteration t (t = N .. 1) makes ONE branch-free pass over the CTA's paths:
   //   (1) exercise decision of date t with the polynomial solved at the end of iteration t+1 (none at t = N),
   //   (2) discount (om3:620) and the ITM-masked raw-price moments of date t-1 (om3:621 mask) -- skipped at t = 1,
   // followed by the block reduction, the grid sum and the solve for date t-1.
-  int seq = 0;
   double d_t = 1.0, dinv_t = 1.0;  // D_t and 1 / D_t of the iteration's decision date
   for (int t = N; t >= 1; --t) {
     long long* tr = tr_base ? tr_base + (size_t)t * kTraceCols : nullptr;

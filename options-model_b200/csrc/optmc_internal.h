@@ -176,7 +176,8 @@ int mlp_grad_debug(optmc_ctx* ctx, int H, long long n, const float* xs, const fl
 // european.cu
 int launch_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                           int32_t N, int32_t dtype, int32_t n_options, const double* K, const double* T,
-                          const int32_t* is_put, const int32_t* stream_id, optmc_european_result* results);
+                          const int32_t* is_put, const int32_t* stream_id, optmc_european_result* results,
+                          const int32_t* N_opt = nullptr, const double* S0_opt = nullptr);
 int launch_european_slab(optmc_ctx* ctx, const void* ST, int64_t M, int32_t dtype, double K, double r, double T,
                          int32_t is_put, optmc_european_result* out);
 

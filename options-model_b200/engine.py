@@ -505,9 +505,16 @@ class Engine:
         return self._to_result(res, keep)
 
     def price_american_batch(self, model: ModelSpec, M: int, S0, K, T, N, is_put, dtype="f32",
-                             rng: Optional[RngSpec] = None, basis="poly2", semantics="reference", streams=None):
+                             rng: Optional[RngSpec] = None, basis="poly2", semantics="reference", streams=None,
+                             details=False, european=False, M_total: int = 0):
         """Grid of American options in a few grouped launches (om3:697-713 / om3gpu:934-956 curve drivers,
-        BASELINE config 4).  S0, K, T, N, is_put: scalars or arrays of length n.  -> (price[n], stderr[n])."""
+        BASELINE config 4).  S0, K, T, N, is_put: scalars or arrays of length n.  -> (price[n], stderr[n]).
+
+        details / european / M_total select optmc_price_american_batch_ex and return (price, stderr, extras) with
+        extras = dict(ex_count, boundary, betas, n_itm [n, max N + 1 (, 4)], european [n, 2], shape [4]):
+        per-date outputs of every option, the European leg on each option's own paths (control variate,
+        om3:653-677), the launched sweep shape.  M_total > 0: path-sharded batch -- this rank holds M paths of EVERY
+        option starting at pair rng.pair_offset, totals are exchanged inside the sweep kernel (comm_init first)."""
         rng = rng or RngSpec()
         arrs = np.broadcast_arrays(np.asarray(S0, dtype=np.float64), np.asarray(K, dtype=np.float64),
                                    np.asarray(T, dtype=np.float64), np.asarray(N, dtype=np.int64),
@@ -523,9 +530,55 @@ class Engine:
         lp = self._lsm_params(1.0, model.r, 1.0, "put", basis, semantics, "auto")
         mp, rp = model.c(), rng.c()
         self._sync_stream()
-        L.check(self.lib.optmc_price_american_batch(self._h, C.byref(mp), C.byref(rp), int(M), _dtype_code(dtype),
-                                                    int(lp.basis), int(lp.semantics), n, opts, out))
-        return np.array([o.price for o in out]), np.array([o.stderr_ for o in out])
+        if not (details or european or M_total):
+            L.check(self.lib.optmc_price_american_batch(self._h, C.byref(mp), C.byref(rp), int(M), _dtype_code(dtype),
+                                                        int(lp.basis), int(lp.semantics), n, opts, out))
+            return np.array([o.price for o in out]), np.array([o.stderr_ for o in out])
+        ex = L.BatchExtras()
+        n1 = int(Na.max()) + 1
+        extras = {}
+        if details:
+            extras["ex_count"] = np.zeros((n, n1), dtype=np.int64)
+            extras["n_itm"] = np.zeros((n, n1), dtype=np.int64)
+            extras["boundary"] = np.full((n, n1), np.nan)
+            extras["betas"] = np.full((n, n1, 4), np.nan)
+            ex.ex_count = extras["ex_count"].ctypes.data_as(C.POINTER(C.c_int64))
+            ex.n_itm = extras["n_itm"].ctypes.data_as(C.POINTER(C.c_int64))
+            ex.boundary = extras["boundary"].ctypes.data_as(C.POINTER(C.c_double))
+            ex.betas = extras["betas"].ctypes.data_as(C.POINTER(C.c_double))
+            ex.ld_dates = n1
+        if european:
+            extras["european"] = np.zeros((n, 2))
+            ex.european = extras["european"].ctypes.data_as(C.POINTER(C.c_double))
+        ex.M_total = int(M_total)
+        L.check(self.lib.optmc_price_american_batch_ex(self._h, C.byref(mp), C.byref(rp), int(M), _dtype_code(dtype),
+                                                       int(lp.basis), int(lp.semantics), n, opts, out, C.byref(ex)))
+        extras["shape"] = [int(v) for v in ex.shape]
+        return np.array([o.price for o in out]), np.array([o.stderr_ for o in out]), extras
+
+    def price_european_grid(self, model: ModelSpec, M: int, S0, K, T, N, is_put, dtype="f32",
+                            rng: Optional[RngSpec] = None, stream_id=None):
+        """Fused no-store European pricing with per-option spot / strike / maturity / step count (the independent
+        control-variate leg of a whole curve, om3:653-713, as ONE launch).  -> (mean[n], stderr[n])."""
+        rng = rng or RngSpec()
+        arrs = np.broadcast_arrays(np.asarray(S0, dtype=np.float64), np.asarray(K, dtype=np.float64),
+                                   np.asarray(T, dtype=np.float64), np.asarray(N, dtype=np.int32),
+                                   np.asarray(is_put, dtype=np.int32))
+        S0a, Ka, Ta, Na, Pa = (np.ascontiguousarray(np.atleast_1d(a).ravel()) for a in arrs)
+        n = Ka.size
+        out = (L.EuropeanResult * n)()
+        mp, rp = model.c(), rng.c()
+        self._sync_stream()
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+        sid = None
+        if stream_id is not None:
+            sid_arr = np.ascontiguousarray(np.asarray(stream_id, dtype=np.int32))
+            assert sid_arr.size == n
+            sid = sid_arr.ctypes.data_as(ip)
+        L.check(self.lib.optmc_price_european_grid(self._h, C.byref(mp), C.byref(rp), int(M), _dtype_code(dtype), n,
+                                                   S0a.ctypes.data_as(dp), Ka.ctypes.data_as(dp), Ta.ctypes.data_as(dp),
+                                                   Na.ctypes.data_as(ip), Pa.ctypes.data_as(ip), sid, out))
+        return (np.array([o.mean for o in out]), np.array([o.stderr_ for o in out]))
 
     def price_european_batch(self, model: ModelSpec, M: int, N: int, K, T, is_put, dtype="f32",
                              rng: Optional[RngSpec] = None, stream_id=None):

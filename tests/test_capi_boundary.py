@@ -91,7 +91,7 @@ def test_ctypes_mirrors_match_the_compiled_header(lib, tmp_path):
              "optmc_lsm_result": lib.LsmResult, "optmc_european_result": lib.EuropeanResult,
              "optmc_global_result": lib.GlobalResult, "optmc_mlp_params": lib.MlpParams, "optmc_gnet_params": lib.GnetParams,
              "optmc_gnet_result": lib.GnetResult, "optmc_american_option": lib.AmericanOption,
-             "optmc_price_result": lib.PriceResult, "optmc_ivnet": lib.IvNet}
+             "optmc_price_result": lib.PriceResult, "optmc_ivnet": lib.IvNet, "optmc_batch_extras": lib.BatchExtras}
     src = open(os.path.join(ROOT, "include", "optmc.h")).read()
     declared = set(re.findall(r"typedef struct (optmc_[a-z_]+) \{", src))
     assert declared == set(pairs), declared ^ set(pairs)

@@ -218,3 +218,68 @@ def test_compat_om1_api_mean_std_zero_prob(mods):
     assert [x["Days to Expiry"] for x in rec] == [2.0, 1.0] and set(rec[0]) == {"S0", "Days to Expiry", "Option Value", "Std Dev", "Zero Prob"}
     with pytest.raises(ValueError):
         compat.om1.price_american_option(S0, K, T, r, -1.0)
+
+
+def test_compat_batched_curve_equals_per_point_loop(mods):
+    """compute_curve_for_S0(batched=True) and the per-point loop draw the same Philox streams (key = master seed,
+    stream = child seed): identical prices point by point, without and with the control variate."""
+    from options_model_b200 import compat
+
+    for cv, same in ((False, False), (True, False), (True, True)):
+        out = []
+        for batched in (True, False):
+            p = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, option_type="put", rng_manager=compat.RNGManager(7),
+                                            use_control_variate=cv, control_variate_same_paths=same, batched=batched)
+            rec = p.compute_curve_for_S0(100.0, 1, 12, 4000, False)
+            out.append(np.array([r["Option Value"] for r in rec]))
+            state = p.rng_manager.master_rng.integers(0, 2**31 - 1)  # both routes advance the generators alike
+            out.append(state)
+        np.testing.assert_allclose(out[0], out[2], rtol=1e-6, atol=1e-9)  # fp32 slabs: grouped vs single launch geometry
+        assert out[1] == out[3]
+
+
+def test_compat_curve_control_variate_is_batched_and_reduces_variance(mods):
+    """The reference's default route (om3:692-693) for a whole curve: <= 3 launches per grid wave, and the same-path
+    European leg removes variance the independent leg adds (spread of the CV-adjusted price over seeds)."""
+    from options_model_b200 import compat
+
+    eng = compat._engine(0)
+    spread = {}
+    for same in (False, True):
+        vals = []
+        for seed in range(12):
+            p = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, option_type="put", rng_manager=compat.RNGManager(seed),
+                                            use_control_variate=True, control_variate_same_paths=same, semantics="textbook")
+            l0 = eng.launch_count()
+            rec = p.compute_curve_for_S0(100.0, 1, 30, 6000, False)
+            launches = eng.launch_count() - l0
+            assert launches <= 3 * 2, launches  # reset + paths + grouped sweep (+ one fused European launch), per wave
+            vals.append([r["Option Value"] for r in rec])
+        spread[same] = np.std(np.array(vals), axis=0).mean()  # spread over seeds, averaged over the 30 curve points
+    assert spread[True] < 0.8 * spread[False], spread
+
+
+def test_compat_iv_model_with_control_variate(mods, golden_dir):
+    """an iv_model pricer with the constructor defaults (use_control_variate=True, sigma given) prices the
+    American leg on local-volatility paths and the European control leg through the same network; the curve driver
+    falls back to the per-point loop."""
+    import os
+
+    from options_model_b200 import compat
+
+    g = np.load(os.path.join(golden_dir, "ref_localvol.npz"))
+
+    # the flattened ImprovedIVNetwork of the fixture, as compat.IVModel stores it
+    H, Lh, ms, ts, eps = g["h32_meta"]
+    ivm = compat.IVModel.__new__(compat.IVModel)
+    ivm.net = dict(hidden=int(H), layers=int(Lh), weights=g["h32_weights"].astype(np.float32), m_scale=float(ms),
+                   tau_scale=float(ts), epsilon=float(eps))
+    ivm.m_scale, ivm.tau_scale = float(ms), float(ts)
+    p = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, option_type="put", rng_manager=compat.RNGManager(3),
+                                    iv_model=ivm)
+    v = p.price_american_option(100.0, 0.5, 4000, 20)
+    assert np.isfinite(v) and v > 0
+    e = p.price_european_streaming(100.0, 0.5, 4000, 20)
+    assert np.isfinite(e) and e > 0
+    rec = p.compute_curve_for_S0(100.0, 1, 3, 2000, False)
+    assert len(rec) == 3 and all(np.isfinite(r["Option Value"]) for r in rec)

@@ -335,3 +335,96 @@ def test_error_paths_of_the_newer_entry_points(eng, mods):
     assert 0 <= eng.lsm_zero_cashflows() <= 4096
     with pytest.raises(AssertionError):
         eng.lsm_apply_policy(S, np.zeros((3, 3)), 100.0, 0.05, 1.0)  # betas must be [(N+1), p]
+
+
+def test_bench_shape_4x1M_fp32_vs_oracle_same_draws(eng, mods):
+    """The launch bench.py times -- optmc_price_american_batch, 4 options x 1 M paths x 252 dates, fp32 slabs, one
+    grouped persistent sweep (4 groups of 37 CTAs, 768 threads x 36 paths) -- against the oracle fed the kernel's own
+    Philox normals, both semantics: prices within 1e-4 (north star, fp32), exercise counts within 2e-4 of the paths
+    (fp32 paths vs fp64 oracle paths: a handful of borderline decisions may flip), regression-row counts of the
+    first regression equal up to the same flips."""
+    L, E, orc = mods
+    M, N, K, B = 1_000_000, 252, 100.0, 4
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    streams = np.array([11, 12, 13, 14])
+    out = {}
+    for sem in ("reference", "textbook"):
+        price, se, ex = eng.price_american_batch(model, M, 100.0, K, 1.0, np.full(B, N), 1, "f32", E.RngSpec(seed=42),
+                                                 semantics=sem, streams=streams, details=True, european=True)
+        out[sem] = (price, se, ex)
+        nt, ppt, cpg, G = ex["shape"]
+        assert (cpg, G) == (eng.sm_count // B, B) and nt * ppt * cpg >= M, ex["shape"]
+        if sem == "reference" and eng.sm_count == 148:
+            assert (nt, ppt) == (768, 36), ex["shape"]  # the sparse wide shape of the headline bench
+    for i in range(B):
+        rng = E.RngSpec(seed=42, stream=int(streams[i]))
+        z1 = eng.philox_normals(L.MODEL_HESTON, M, N, 0, "f32", rng).double().cpu().numpy()
+        z2 = eng.philox_normals(L.MODEL_HESTON, M, N, 1, "f32", rng).double().cpu().numpy()
+        S = orc.heston_paths_antithetic(100.0, 0.05, 1.0, HP["v0"], HP["kappa"], HP["theta"], HP["xi"], HP["rho"], M, N, z1, z2)
+        del z1, z2
+        eu_ref = orc.european_from_paths(S[N], K, 0.05, 1.0, "put")
+        for sem in ("reference", "textbook"):
+            ref = orc.lsm_sweep(S, K, 0.05, 1.0, "put", semantics=sem)
+            price, se, ex = out[sem]
+            assert price[i] == pytest.approx(ref.price, rel=1e-4), (sem, i)
+            assert se[i] == pytest.approx(ref.stderr, rel=1e-3), (sem, i)
+            assert np.abs(ex["ex_count"][i] - ref.ex_count).sum() <= 2e-4 * M, (sem, i)  # measured: ~1e-4 M borderline flips
+            assert abs(int(ex["n_itm"][i, N - 1]) - int(ref.n_itm[N - 1])) <= 1e-5 * M
+            assert ex["european"][i, 0] == pytest.approx(eu_ref[0], rel=1e-5)
+            assert ex["european"][i, 1] == pytest.approx(eu_ref[1], rel=1e-4)
+        del S
+
+
+def test_batch_extras_equal_single_option_outputs(eng, mods):
+    """optmc_price_american_batch_ex: per-date outputs and the European leg of every option equal the single-option
+    calls on the same Philox stream (fp64, bit-level agreement of integers, 1e-12 of floats)."""
+    L, E, orc = mods
+    M = 20_000
+    S0 = np.array([100.0, 96.0, 104.0]); K = np.array([100.0, 100.0, 98.0]); T = np.array([1.0, 0.5, 0.75])
+    N = np.array([30, 17, 24]); put = np.array([1, 1, 0]); streams = np.array([2, 4, 6])
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    for sem in ("reference", "textbook"):
+        price, se, ex = eng.price_american_batch(model, M, S0, K, T, N, put, "f64", E.RngSpec(seed=31), semantics=sem,
+                                                 streams=streams, details=True, european=True)
+        for i in range(3):
+            ot = "put" if put[i] else "call"
+            m = E.heston(S0[i], 0.05, T[i], **HP)
+            rs = E.RngSpec(seed=31, stream=int(streams[i]))
+            single = eng.price_american(m, M, int(N[i]), K[i], ot, "f64", rs, semantics=sem, arrays=True)
+            n1 = int(N[i]) + 1
+            assert price[i] == pytest.approx(single.price, rel=1e-12)
+            np.testing.assert_array_equal(ex["ex_count"][i, :n1], single.ex_count)
+            np.testing.assert_array_equal(ex["n_itm"][i, :n1], single.n_itm)
+            np.testing.assert_array_equal(np.isnan(ex["boundary"][i, :n1]), np.isnan(single.boundary))
+            np.testing.assert_allclose(np.nan_to_num(ex["boundary"][i, :n1]), np.nan_to_num(single.boundary), rtol=0)
+            np.testing.assert_allclose(np.nan_to_num(ex["betas"][i, :n1, :3]), np.nan_to_num(single.betas), rtol=1e-9, atol=1e-12)
+            Ssl = eng.paths(m, M, int(N[i]), "f64", rs)
+            eu, eu_se = eng.european_from_slab(Ssl[int(N[i])].contiguous(), K[i], 0.05, T[i], ot)
+            assert ex["european"][i, 0] == pytest.approx(eu, rel=1e-12)
+            assert ex["european"][i, 1] == pytest.approx(eu_se, rel=1e-9)
+
+
+def test_path_sharded_batch_single_rank_group(eng, mods):
+    """optmc_price_american_batch_ex with M_total on a one-rank group (comm_export / comm_init with itself): the
+    in-kernel cross-rank exchange path runs (tagged slot words, re-centred payloads, one slot block per option) and
+    must reproduce the plain batch bit for bit; with two emulated halves of the paths priced separately the Philox
+    counters line up through pair_offset.  (Two real GPUs: tests/test_multi_gpu.py.)"""
+    L, E, orc = mods
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    e = E.Engine(0)
+    try:
+        e.comm_init(0, 1, [e.comm_export()])
+        for M, N, B in ((40_000, 30, 3), (600_000, 25, 4)):
+            streams = np.arange(B) + 3
+            plain, se = eng.price_american_batch(model, M, 100.0, 100.0, 1.0, np.full(B, N), 1, "f32", E.RngSpec(seed=8),
+                                                 streams=streams)
+            for _ in range(2):  # twice: the exchange counter keeps running across launches
+                sh, se2, ex = e.price_american_batch(model, M, 100.0, 100.0, 1.0, np.full(B, N), 1, "f32", E.RngSpec(seed=8),
+                                                     streams=streams, M_total=M)
+                np.testing.assert_array_equal(sh, plain)
+                np.testing.assert_array_equal(se2, se)
+        with pytest.raises(Exception):  # one N per sharded batch
+            e.price_american_batch(model, 40_000, 100.0, 100.0, 1.0, np.array([20, 30]), 1, "f32", E.RngSpec(seed=8), M_total=40_000)
+        e.comm_finalize()
+    finally:
+        e.close()

@@ -28,3 +28,18 @@ def test_fused_sharded_sweep_two_gpus():
     for k, v in out.items():
         if k.startswith("check_"):
             assert v["ok"] and v["identical_on_all_ranks"], (k, v)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_bench_path_sharded_batch_two_gpus():
+    """bench.py's multi-GPU mode (every option's paths split over the ranks, totals exchanged inside the grouped sweep
+    kernel): the built-in parity check against the single-GPU pricing must report bit-identical prices."""
+    port = 29900 + os.getpid() % 90
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "2", "--warmup", "3",
+           "--paths", "200000", "--dates", "40", "--no-cpu", "--no-other-configs"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    out = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["n_gpus"] == 2 and out["config"]["shard_mode"] == "paths"
+    assert out["path_sharded_parity"]["rel_vs_single"] == 0.0 and out["path_sharded_parity"]["identical_on_all_ranks"]
