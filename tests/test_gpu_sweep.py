@@ -368,7 +368,10 @@ def test_bench_shape_4x1M_fp32_vs_oracle_same_draws(eng, mods):
             price, se, ex = out[sem]
             assert price[i] == pytest.approx(ref.price, rel=1e-4), (sem, i)
             assert se[i] == pytest.approx(ref.stderr, rel=1e-3), (sem, i)
-            assert np.abs(ex["ex_count"][i] - ref.ex_count).sum() <= 2e-4 * M, (sem, i)  # measured: ~1e-4 M borderline flips
+            # borderline decisions flip between the fp32 paths and the oracle's fp64 paths: ~1e-4 M under the sticky mask
+            # (every path decides once); textbook semantics count every date's decisions (~1.4e5 per date)
+            flips = np.abs(ex["ex_count"][i] - ref.ex_count).sum()
+            assert flips <= (2e-4 * M if sem == "reference" else 1e-3 * ref.ex_count.sum()), (sem, i, flips)
             assert abs(int(ex["n_itm"][i, N - 1]) - int(ref.n_itm[N - 1])) <= 1e-5 * M
             assert ex["european"][i, 0] == pytest.approx(eu_ref[0], rel=1e-5)
             assert ex["european"][i, 1] == pytest.approx(eu_ref[1], rel=1e-4)
