@@ -232,7 +232,7 @@ def run_own_arm(args):
 
     M, N, B = args.paths, args.dates, args.batch
     shard = "none" if world == 1 else ("paths" if args.shard in ("auto", "paths") else "options")
-    eng = E.Engine(local)
+    eng = E.default_engine(local)  # the engine compat's pricers use as well (one context, one set of peer mappings)
     stream = torch.cuda.Stream(device=local)
     model = E.heston(S0, R, T, **HP)
     b = 4  # fp32 storage
@@ -496,7 +496,6 @@ def run_own_arm(args):
             eng.comm_finalize()
         dist.barrier()
         dist.destroy_process_group()
-    eng.close()
     if rc:
         sys.exit(rc)
 

@@ -77,7 +77,7 @@ static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int 
   if (!shape) { *why = "slice exceeds the register-resident capacity"; return false; }
   // every stage holds the full NT x PPT slot grid: the tail behind the slice is an out-of-the-money sentinel
   const size_t stride = ((size_t)shape->nt * shape->ppt * es + 127) / 128 * 128;
-  const size_t avail = (size_t)ctx->max_smem_optin - 8192;  // static shared + slack
+  const size_t avail = (size_t)ctx->max_smem_optin - (p->spec ? 14336 : 8192);  // static shared (candidate lists) + slack
   int nstage = 3;
   if (stride * 3 > avail) nstage = 2;
   if (stride * 2 > avail) { *why = "slice exceeds shared memory"; return false; }

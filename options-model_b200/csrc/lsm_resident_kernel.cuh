@@ -192,7 +192,7 @@ __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long
   return tot;
 }
 
-constexpr int kTraceCols = 12;
+constexpr int kTraceCols = 16;
 // A stamp that cannot be issued before `dep` (a value loaded after a barrier) is available: BAR.SYNC defers its
 // blocking, so a bare clock read placed after it measures the issue of the barrier, not its completion.
 __device__ __forceinline__ long long clock_after(int dep) {
@@ -699,18 +699,16 @@ constexpr int kBarBeta = 1, kBarTot = 2;
 // fills its own segment in S(t) (order: step k, then lane -- fixed), processes it with one lane per entry once beta_t
 // is known, and the owners read the resulting cash-flow back.  Three planes (st, sg, c) of kCandCap entries per warp
 // in shared memory; the rest spill to the warp's block in global memory (dates close to maturity only).
-constexpr int kCandCap = 12;
-// the overflow path is rare and lives out of line: the unrolled scan must stay small (instruction cache)
-template <typename R> __device__ __noinline__ void cand_spill_store(R* p, int plane, R st, R sg, R c) {
-  p[0] = st; p[plane] = sg; p[2 * plane] = c;
-}
+constexpr int kCandCap = 32;  // one full round of the warp; steady-state lists (2-18 entries) stay on chip
 template <typename R> struct CandList {
   R* smem;         // this warp's segment: planes [3][kCandCap]
   R* spill;        // this warp's block in global memory: planes [3][spill_cap]
   int spill_cap;   // PPT * 32
+  unsigned char* step_of;   // shared [kCandCap]: scan step k of entry e (entries in shared memory only)
+  unsigned char* n_before;  // shared [PPT]: entries listed before step k (written at the steps that listed something)
   __device__ __forceinline__ void store(int e, R st, R sg, R c) const {
     if (e < kCandCap) { smem[e] = st; smem[kCandCap + e] = sg; smem[2 * kCandCap + e] = c; }
-    else cand_spill_store<R>(spill + (e - kCandCap), spill_cap, st, sg, c);
+    else { R* p = spill + (e - kCandCap); p[0] = st; p[spill_cap] = sg; p[2 * spill_cap] = c; }
   }
   __device__ __forceinline__ void load(int e, R& st, R& sg, R& c) const {
     if (e < kCandCap) { st = smem[e]; sg = smem[kCandCap + e]; c = smem[2 * kCandCap + e]; }
@@ -729,32 +727,63 @@ template <typename R> struct CandList {
 // goes to the warp's list -- the price of a date it is out of the money at is replaced by an out-of-the-money
 // sentinel -- and to the bit mask `listed`.  All floating-point work on these paths happens in cand_round, in one
 // rolled loop with one lane per entry: the unrolled scan stays small (instruction cache) and holds no fp64 state.
+// shared-memory accesses of the scan by 32-bit shared address + immediate offset: one instruction per access and two
+// live address registers for the whole pass (generic pointers cost 64-bit address arithmetic per step, which at the
+// 80-register budget of the wide shape the compiler re-materialises instead of keeping live)
+template <int OFF> __device__ __forceinline__ float lds_imm(uint32_t addr, float) {
+  float v; asm("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF)); return v;
+}
+template <int OFF> __device__ __forceinline__ double lds_imm(uint32_t addr, double) {
+  double v; asm("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF)); return v;
+}
+__device__ __forceinline__ void sts_at(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_at(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+
+template <typename R, int PPT, int NT, int K, int K1> struct ScanSteps {
+  typedef typename MaskOf<(PPT > 32)>::type Mask;
+  static __device__ __forceinline__ void run(const R (&cf)[PPT], uint32_t at, uint32_t ag, R sgn, R kk_t, R kk_g, Mask& listed,
+                                             const CandList<R>& list, uint32_t seg, int& n_w) {
+    const R c = cf[K];
+    const R st = lds_imm<K * NT * (int)sizeof(R)>(at, R());
+    const R sg = lds_imm<K * NT * (int)sizeof(R)>(ag, R());
+    const bool in = !(c < (R)0) & ((sgn * st > kk_t) | (sgn * sg > kk_g));  // open (sign bit clear) and in the money
+    const unsigned int bal = __ballot_sync(0xffffffffu, in);
+    if (bal) {  // warp-uniform; ~15% of the steps
+      if (in) {
+        const R otm = (R)(-sgn * INFINITY);
+        const int e = n_w + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+        const R vt = (sgn * st > kk_t) ? st : otm, vg = (sgn * sg > kk_g) ? sg : otm;
+        if (e < kCandCap) {
+          const uint32_t q = seg + (uint32_t)e * (uint32_t)sizeof(R);
+          sts_at(q, vt);
+          sts_at(q + kCandCap * (uint32_t)sizeof(R), vg);
+          sts_at(q + 2 * kCandCap * (uint32_t)sizeof(R), c);
+          list.step_of[e] = (unsigned char)K;
+        } else {
+          R* p = list.spill + (e - kCandCap);
+          p[0] = vt; p[list.spill_cap] = vg; p[2 * list.spill_cap] = c;
+        }
+        listed |= (Mask)1 << K;
+      }
+      list.n_before[K] = (unsigned char)(n_w < 255 ? n_w : 255);
+      n_w += __popc(bal);
+    }
+    ScanSteps<R, PPT, NT, K + 1, K1>::run(cf, at, ag, sgn, kk_t, kk_g, listed, list, seg, n_w);
+  }
+};
+template <typename R, int PPT, int NT, int K1> struct ScanSteps<R, PPT, NT, K1, K1> {
+  typedef typename MaskOf<(PPT > 32)>::type Mask;
+  static __device__ __forceinline__ void run(const R (&)[PPT], uint32_t, uint32_t, R, R, R, Mask&, const CandList<R>&, uint32_t, int&) {}
+};
+
 template <typename R, int PPT, int NT, int K0, int K1>
 __device__ __forceinline__ void scan_pass(const R (&cf)[PPT], const R* __restrict__ st_t, const R* __restrict__ st_g,
                                           const PassConsts<R>& pc, bool decide, bool gram,
                                           typename MaskOf<(PPT > 32)>::type& listed, const CandList<R>& list, int& n_w) {
-  typedef typename MaskOf<(PPT > 32)>::type Mask;
-  const int tid = threadIdx.x;
-  const unsigned int lt_mask = (1u << (tid & 31)) - 1u;
-  const R otm = (R)(-pc.sgn * INFINITY);
   // decide / gram are off at the first / last date only: an "in the money" threshold nothing passes switches the test off
   const R kk_t = decide ? pc.kk : (R)INFINITY, kk_g = gram ? pc.kk : (R)INFINITY;
-#pragma unroll
-  for (int k = K0; k < K1; ++k) {
-    const int j = tid + k * NT;
-    const R c = cf[k];
-    const R st = st_t[j], sg = st_g[j];
-    const bool open = !Store<R>::flagged(c, pc.flag);
-    const bool lt = pc.sgn * st > kk_t;
-    const bool lg = pc.sgn * sg > kk_g;
-    const bool in = open & (lt | lg);
-    const unsigned int bal = __ballot_sync(0xffffffffu, in);
-    if (bal) {  // warp-uniform; ~15% of the steps
-      if (in) list.store(n_w + __popc(bal & lt_mask), lt ? st : otm, lg ? sg : otm, c);
-      n_w += __popc(bal);
-      listed |= in ? ((Mask)1 << k) : (Mask)0;
-    }
-  }
+  const uint32_t at = smem_u32(st_t) + threadIdx.x * (uint32_t)sizeof(R), ag = smem_u32(st_g) + threadIdx.x * (uint32_t)sizeof(R);
+  ScanSteps<R, PPT, NT, K0, K1>::run(cf, at, ag, pc.sgn, kk_t, kk_g, listed, list, smem_u32(list.smem), n_w);
 }
 
 // The listed paths of the warp, one lane per entry, once beta_t is known (valid = the regression of date t
@@ -763,7 +792,7 @@ __device__ __forceinline__ void scan_pass(const R (&cf)[PPT], const R* __restric
 template <typename R, int DEG>
 __device__ __forceinline__ void cand_round(const CandList<R>& list, int n_w, const HitConsts<R, DEG>& dec,
                                            const PassConsts<R>& pc, bool valid, double (&mom)[Moments<DEG>::Q],
-                                           unsigned int& rows, unsigned int& cnt, R& em) {
+                                           unsigned int& rows, unsigned int& cnt, R& em, unsigned long long& exer_steps) {
   const int lane = threadIdx.x & 31;
   for (int e0 = 0; e0 < n_w; e0 += 32) {  // warp-uniform trip count
     const int e = e0 + lane;
@@ -777,7 +806,10 @@ __device__ __forceinline__ void cand_round(const CandList<R>& list, int n_w, con
     const bool exer = lt & pos;
     const R pay = Store<R>::with_flag((fma(pc.sgn, st, pc.c1) + pc.c2) * pc.dinv, pc.flag);
     c = exer ? pay : c;
-    if (exer) list.store_c(e, c);
+    if (exer) {
+      list.store_c(e, c);
+      exer_steps |= 1ull << (e < kCandCap ? list.step_of[e] : 63);  // bit 63: an exercised entry lives in the spill block
+    }
     cnt += exer ? 1u : 0u;
     em = fmax(em, exer ? -(pc.sgn * st) : (R)-INFINITY);
     const bool live = have & !exer & (pc.sgn * sg > pc.kk);
@@ -796,11 +828,34 @@ __device__ __forceinline__ unsigned long long warp_or(unsigned long long m) {
          __reduce_or_sync(0xffffffffu, (unsigned int)m);
 }
 template <typename R, int PPT>
-__device__ __forceinline__ void cand_apply(R (&cf)[PPT], const CandList<R>& list,
-                                           typename MaskOf<(PPT > 32)>::type cand) {
+__device__ __forceinline__ void cand_apply(R (&cf)[PPT], const CandList<R>& list, int n_w,
+                                           typename MaskOf<(PPT > 32)>::type cand, unsigned long long exer_steps) {
   typedef typename MaskOf<(PPT > 32)>::type Mask;
   const unsigned int lt_mask = (1u << (threadIdx.x & 31)) - 1u;
-  const Mask any = warp_or(cand);
+  // Only an EXERCISED entry changes its path's cash-flow, and few do (none at most dates): the steps that need the
+  // read-back come from the warp-wide OR of the lanes' exercised-step masks, the entry index of (step, lane) from the
+  // count the scan recorded at that step.  The walk over the PPT steps is a chain of warp-uniform tests.
+  const unsigned long long ex = warp_or(exer_steps);
+  if (ex == 0ull) return;
+  if (!(ex >> 63)) {
+    const R* cplane = list.smem + 2 * kCandCap;
+#pragma unroll
+    for (int k0 = 0; k0 < PPT; k0 += 4) {
+      if ((ex >> k0) & 0xfull) {
+#pragma unroll
+        for (int k = k0; k < k0 + 4 && k < PPT; ++k) {
+          if ((ex >> k) & 1ull) {
+            const bool lt = (cand >> k) & (Mask)1;
+            const unsigned int bal = __ballot_sync(0xffffffffu, lt);
+            const int e = (int)list.n_before[k] + __popc(bal & lt_mask);
+            if (lt && e < kCandCap) cf[k] = cplane[e];
+          }
+        }
+      }
+    }
+    return;
+  }
+  const Mask any = warp_or(cand);  // dates close to maturity: entries spilled to global memory -- read everything back
   int n = 0;
 #pragma unroll
   for (int k0 = 0; k0 < PPT; k0 += 4) {
@@ -833,6 +888,8 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
   __shared__ double s_dec[DEG + 1];     // exercise iff s_dec(s) > 0  (payoff - continuation as a polynomial in S)
   __shared__ float s_hit[2 * DEG + 4];  // fp32 sweep: f[], b[] of s_dec (HitConsts); the discount slots are unused here
   __shared__ R s_seg[NW][3 * kCandCap];
+  __shared__ unsigned char s_step[NW][kCandCap];
+  __shared__ unsigned char s_nbefore[NW][(PPT + 3) / 4 * 4];
   __shared__ int s_valid;
   __shared__ unsigned int s_done[2];    // compute warps that finished half A / half B of the current date's rows
   __shared__ unsigned long long s_bnd[2];
@@ -1047,7 +1104,8 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
     }
   };
   const CandList<R> list{&s_seg[warp][0],
-                         static_cast<R*>(ga.spill) + ((size_t)blockIdx.x * NW + warp) * (size_t)(3 * PPT * 32), PPT * 32};
+                         static_cast<R*>(ga.spill) + ((size_t)blockIdx.x * NW + (warp < NW ? warp : 0)) * (size_t)(3 * PPT * 32), PPT * 32,
+                         &s_step[warp < NW ? warp : 0][0], &s_nbefore[warp < NW ? warp : 0][0]};
   wait_half(0, 0);
   wait_half(0, 1);
   {  // date N: cash-flows = payoff(S[N]) (om3:616)
@@ -1087,6 +1145,7 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
     R em = (R)-INFINITY;  // max over exercised paths of -sgn * S: put -> max S, call -> -(min S)
     const PassConsts<R> pc{sgn, kk, c1, c2, (R)dinv_t, (R)(d_t * a.disc), flag, n_local};
     Mask listed = 0;
+    unsigned long long exer_steps = 0ull;  // steps k whose entry of this lane was exercised at date t
     int n_w = 0;  // listed paths of this warp at date t (warp-uniform)
     if (gram) wait_half(row_g, 0);
     if (tr) tr[6] = clock64();  // S(t) starts
@@ -1103,7 +1162,7 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
       HitConsts<R, DEG> hc;
       if constexpr (sizeof(R) == 4) { hc.d = s_dec; hc.c = s_hit; }
       else { hc.dec.load(s_dec, true); hc.dinv_ = pc.dinv; hc.dg_ = pc.dg; }
-      cand_round<R, DEG>(list, n_w, hc, pc, t < N && s_valid != 0, mom, rows, cnt, em);
+      cand_round<R, DEG>(list, n_w, hc, pc, t < N && s_valid != 0, mom, rows, cnt, em, exer_steps);
       if (tr) tr[8] = clock_after((int)rows + (int)cnt);
     }
     d_t *= a.disc;
@@ -1120,20 +1179,24 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
     }
     // off the critical path (the communication warp is in the exchange): statistics, cash-flows of the candidates
     if (t < N) {
-      cnt = __reduce_add_sync(0xffffffffu, cnt);
-      if (cnt) {  // warp-uniform
-        const double ext = -(double)sgn * (double)em;
-        unsigned long long b = (unsigned long long)__double_as_longlong(ext);
-        if (!isfinite(ext)) b = bnd_none(a.is_put);
-        b = is_put ? warp_max_u64(b) : warp_min_u64(b);
-        if (lane == 0) {
-          atomicAdd(&s_cnt[t & 1], cnt);
-          if (is_put) atomicMax(&s_bnd[t & 1], b); else atomicMin(&s_bnd[t & 1], b);
+      if (a.exc != nullptr || a.bnd != nullptr) {  // per-date exercise statistics were asked for
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt) {  // warp-uniform
+          const double ext = -(double)sgn * (double)em;
+          unsigned long long b = (unsigned long long)__double_as_longlong(ext);
+          if (!isfinite(ext)) b = bnd_none(a.is_put);
+          b = is_put ? warp_max_u64(b) : warp_min_u64(b);
+          if (lane == 0) {
+            atomicAdd(&s_cnt[t & 1], cnt);
+            if (is_put) atomicMax(&s_bnd[t & 1], b); else atomicMin(&s_bnd[t & 1], b);
+          }
         }
       }
       __syncwarp();
-      cand_apply<R, PPT>(cf, list, listed);
+      if (tr) tr[12] = clock64();
+      cand_apply<R, PPT>(cf, list, n_w, listed, exer_steps);
       __syncwarp();  // before the next pass overwrites the segment
+      if (tr) tr[11] = clock_after(__float_as_int((float)cf[0]));
     }
     if (!gram) break;
     row_t = row_g;

@@ -45,7 +45,9 @@ for c in (0, 1):
         per_date = a[1:, 5] - a[:-1, 5]
         print(f"cta {'first' if c == 0 else 'last'}: per-date total {med(per_date)} cycles; spins {med(a[:, 7])}")
         print(f"   S(t) pass                  (1 - 6)        {med(a[:, 1] - a[:, 6])}")
-        print(f"   stage wait before S(t-1)   (6[t-1] - 3[t]) {med(a[1:, 6] - a[:-1, 3])}")
+        print(f"   arrive TOT + stats         (12 - 3)       {med(a[1:, 12] - a[1:, 3])}")
+        print(f"   cand_apply                 (11 - 12)      {med(a[1:, 11] - a[1:, 12])}")
+        print(f"   loop top + stage wait      (6[t-1] - 11[t]) {med(a[2:, 6] - a[1:-1, 11])}")
         print(f"   BETA arrive -> beta seen   (2 - 10)       {med(a[:, 2] - a[:, 10])}")
         print(f"   C(t) candidates            (8 - 2)        {med(a[1:, 8] - a[1:, 2])}")
         print(f"   stats + warp reduce        (3 - 8)        {med(a[1:, 3] - a[1:, 8])}")
