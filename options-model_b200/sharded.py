@@ -17,14 +17,18 @@ from typing import Optional
 import numpy as np
 
 
-def shard_pairs(M: int, rank: int, world: int):
+def shard_pairs(M: int, rank: int, world: int, granule: int = 8):
     """Contiguous block of antithetic pairs for ``rank``: returns (pair_offset, local_M).  Both members of a
-    pair live on the same rank (local columns j and j + local_M/2)."""
+    pair live on the same rank (local columns j and j + local_M/2).  Blocks are multiples of ``granule`` pairs (the
+    persistent sweep stages whole 16-byte units: 4 fp32 / 2 fp64 paths) except the last rank's, which takes the
+    remainder -- so every rank but possibly the last is eligible for the fused sweep, and eligibility can be agreed on
+    before anything is launched (``sweep_sharded_fused``)."""
     pairs = M // 2
-    base, extra = divmod(pairs, world)
-    lo = rank * base + min(rank, extra)
-    n = base + (1 if rank < extra else 0)
-    return lo, 2 * n
+    per = -(-pairs // world)                   # ceil
+    per = -(-per // granule) * granule         # round up to the granule
+    lo = min(rank * per, pairs)
+    hi = min(lo + per, pairs)
+    return lo, 2 * (hi - lo)
 
 
 @dataclass
@@ -98,7 +102,34 @@ def sweep_sharded_fused(engine, dist, S_local, M_total, K, r, T, option_type="pu
     NCCL variant disappear from the data path.  Requires ``init_peer_exchange`` once per process group.
     Every rank returns the global price; with ``arrays`` the per-rank exercise counts / boundaries are combined
     over the group (that combine is host plumbing after the sweep, not part of it)."""
-    res = engine.lsm_sharded(S_local, M_total, K, r, T, option_type, basis, semantics, arrays=arrays)
+    # Every rank must launch or none (a rank that fails validation would leave its peers spinning on the exchange, and
+    # the running exchange counter would diverge): agree on the outcome of the call collectively, and re-wire the
+    # exchange (fresh slots, counter reset on every rank) after any failure before raising on every rank alike.
+    err = None
+    res = None
+    if S_local.shape[1] == 0 or (S_local.shape[1] * S_local.element_size()) % 16 != 0:
+        err = ValueError(f"rank block of {S_local.shape[1]} paths is not a multiple of 16 bytes (use shard_pairs)")
+    world = dist.get_world_size(group)
+    if world > 1:
+        pre = [None] * world
+        dist.all_gather_object(pre, err is None, group=group)
+        if not all(pre):
+            raise RuntimeError(f"fused sharded sweep not launched: ineligible block on ranks {[i for i, ok in enumerate(pre) if not ok]}: {err}")
+    elif err is not None:
+        raise err
+    try:
+        res = engine.lsm_sharded(S_local, M_total, K, r, T, option_type, basis, semantics, arrays=arrays)
+    except Exception as e:  # noqa: BLE001 -- reported collectively below
+        err = e
+    if world > 1:
+        post = [None] * world
+        dist.all_gather_object(post, None if err is None else str(err), group=group)
+        if any(p is not None for p in post):
+            init_peer_exchange(engine, dist, group)
+            raise RuntimeError(f"fused sharded sweep failed on ranks {[i for i, p in enumerate(post) if p is not None]}: "
+                               f"{[p for p in post if p is not None][0]}")
+    elif err is not None:
+        raise err
     if arrays and dist.get_world_size(group) > 1:
         import torch
 

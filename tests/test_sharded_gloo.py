@@ -199,3 +199,21 @@ def test_peer_exchange_wiring_two_ranks_gloo(fail_on):
             assert info[2] == [bytes([0]) * 64, bytes([1]) * 64]
     else:
         assert [g[1] for g in got] == ["raised", "raised"]
+
+
+def test_shard_pairs_blocks_are_contiguous_and_aligned():
+    """Per-rank blocks tile the pairs exactly, in rank order; every block but the last non-empty one is a multiple of
+    8 pairs (16-byte units of the persistent sweep)."""
+    from options_model_b200 import sharded
+
+    for M in (2, 100, 4096, 100_000, 1_000_002, 8_000_000):
+        for world in (1, 2, 3, 4, 8):
+            nxt, sizes = 0, []
+            for r in range(world):
+                off, m = sharded.shard_pairs(M, r, world)
+                assert off == nxt and m % 2 == 0 and m >= 0
+                nxt += m // 2
+                sizes.append(m // 2)
+            assert nxt == M // 2
+            nonempty = [s for s in sizes if s]
+            assert all(s % 8 == 0 for s in nonempty[:-1])

@@ -72,6 +72,10 @@ WANT = {
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio": "stall_short_scoreboard",
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio": "stall_not_selected",
+    "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio": "stall_dispatch",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio": "stall_branch_resolving",
+    "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active": "pipe_fma_cycles_pct",
+    "sm__icc_request_hit_rate.pct": "icache_hit_pct",
 }
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}
 def ingest(raw_text):
@@ -98,6 +102,10 @@ if os.path.exists(rep) and use_rep:
 for path in extra_csv:
     ingest(open(path).read())
 
+try:  # the build the capture was taken from (bench.py reports it next to roofline.traffic)
+    summary["git"] = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+except Exception:  # noqa: BLE001
+    pass
 with open(os.path.join(out_dir, f"ncu_{tag}_summary.json"), "w") as f:
     json.dump(summary, f, indent=1)
 
@@ -115,7 +123,8 @@ for name, ks in summary["kernels"].items():
                 "warps_active_pct", "pipe_alu_pct", "pipe_fma_pct", "pipe_fp64_pct", "pipe_xu_pct", "pipe_lsu_pct",
                 "pipe_tensor_pct", "pipe_tc_pct", "pipe_tc_cycles_pct", "pipe_tensor_hmma_pct", "pipe_tmem_pct",
                 "stall_barrier", "stall_wait", "stall_math_pipe", "stall_no_instruction", "stall_long_scoreboard",
-                "stall_short_scoreboard", "stall_not_selected"):
+                "stall_short_scoreboard", "stall_not_selected", "stall_dispatch", "stall_branch_resolving", "pipe_fma_cycles_pct",
+                "icache_hit_pct"):
         if key in k:
             lines.append(f"* {key}: {k[key]:.6g}")
     lines.append("")
