@@ -388,6 +388,19 @@ int optmc_price_american_batch_ex(optmc_ctx* ctx, const optmc_model_params* mp, 
                                   const optmc_american_option* opts, optmc_price_result* results,
                                   optmc_batch_extras* extras);
 
+/* ---- quasi-Monte-Carlo draws (no counterpart in the reference, which draws PCG64 pseudo-random normals,
+ * om3:223-224,475) ----
+ * Sobol' points (Joe-Kuo 2008 direction numbers, first 512 dimensions = factors x N) with an optional random digital
+ * shift (digital_shift: host [factors * N] 32-bit words, NULL = the plain sequence) and an optional Brownian-bridge
+ * ordering of the dimensions.  Writes step-major normals Z1 (and Z2 for factors = 2) [N][M/2] of `dtype` that the path
+ * entry points accept as external draws (optmc_rng_params.z1_dev / z2_dev, antithetic layout); point index = antithetic
+ * pair index + pair_offset + 1, so shards of a path set generate their own blocks. */
+int optmc_qmc_normals(optmc_ctx* ctx, int64_t M, int32_t N, int32_t factors, int32_t brownian_bridge, int64_t pair_offset,
+                      const uint32_t* digital_shift, int32_t dtype, void* Z1_dev, void* Z2_dev);
+/* The bridge construction order the kernel uses (test aid): step s sets row idx[s] (holding W(idx+1)) to
+ * wl W(left) + wr W(right+1) + sd z_s, W(0) = 0.  Host arrays of length N. */
+int optmc_qmc_bridge_schedule(int32_t N, int32_t* idx, int32_t* left, int32_t* right, double* wl, double* wr, double* sd);
+
 /* The same fused kernel with per-option spot and step count: the INDEPENDENT European leg of a whole S0 x maturity
  * curve with the control variate on (om3:653-677 inside om3:697-713: one price_european_streaming per grid point,
  * steps = max(10, min(130, ceil(days)))) as one launch.  S0 may be NULL (mp->S0 for every option). */

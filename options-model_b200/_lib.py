@@ -155,6 +155,10 @@ PROTOTYPES = {
     "optmc_price_european_batch": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32,
                                              C.c_int32, C.c_int32, _P(C.c_double), _P(C.c_double), _P(C.c_int32),
                                              _P(C.c_int32), _P(EuropeanResult)]),
+    "optmc_qmc_normals": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int64, _P(C.c_uint32), C.c_int32,
+                                    C.c_void_p, C.c_void_p]),
+    "optmc_qmc_bridge_schedule": (C.c_int, [C.c_int32, _P(C.c_int32), _P(C.c_int32), _P(C.c_int32), _P(C.c_double),
+                                            _P(C.c_double), _P(C.c_double)]),
     "optmc_price_european_grid": (C.c_int, [C.c_void_p, _P(ModelParams), _P(RngParams), C.c_int64, C.c_int32, C.c_int32,
                                             _P(C.c_double), _P(C.c_double), _P(C.c_double), _P(C.c_int32), _P(C.c_int32),
                                             _P(C.c_int32), _P(EuropeanResult)]),

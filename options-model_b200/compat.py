@@ -292,7 +292,8 @@ class AdvancedOptionPricer:
                  # engine extensions (not in the reference)
                  lsm_regressor: str = "poly2", semantics: str = "reference", dtype: str = "f32", device: int = 0,
                  gpu_reference_quirks: bool = False, batched: bool = True, out_of_sample: bool = False,
-                 control_variate_same_paths: bool = False, path_shard: Optional[Tuple[int, int]] = None):
+                 control_variate_same_paths: bool = False, path_shard: Optional[Tuple[int, int]] = None,
+                 qmc: bool = False):
         self.K = K
         self.r = r
         self.sigma = sigma
@@ -319,6 +320,9 @@ class AdvancedOptionPricer:
         # (rank, world) of a path-sharded pricer: price_american_grid prices num_simulations paths PER RANK
         # of every option, the sweep exchanges its totals over NVLink (sharded.init_peer_exchange first)
         self.path_shard = path_shard
+        # Sobol' + Brownian-bridge draws with a random digital shift keyed by the pricing's child seed
+        # instead of pseudo-random normals (per-point pricing with the polynomial regressor; steps x factors <= 512)
+        self.qmc = qmc
         self.last_result: Optional[E.SweepResult] = None
         self._lsm_net = None      # om3gpu:596: the torch-GPU file caches its network across pricing calls
         self._nn_variant = "cpu"  # training defaults of om3:565-613; the *_gpu entry point switches to om3gpu:740-798
@@ -376,6 +380,14 @@ class AdvancedOptionPricer:
             self.last_result = out
             return float(out["price"])
         eng = _engine(self.device)
+        if self.qmc:
+            heston = self.use_heston and self.heston_params is not None
+            Z = eng.qmc_normals(M, int(num_time_steps), factors=2 if heston else 1, bridge=True, dtype=self.dtype, shift_seed=seed)
+            rs = E.RngSpec(z1=Z[0], z2=Z[1]) if heston else E.RngSpec(z1=Z)
+            S = eng.paths(model, M, int(num_time_steps), self.dtype, rs)
+            res = eng.lsm(S, self.K, self.r, T, self.option_type, self.lsm_regressor, self.semantics, arrays=self.verbose)
+            self.last_result = res
+            return float(res.price)
         # Philox key = the master seed, stream = this pricing's child seed: the convention of price_american_grid, so
         # the batched curve and the per-point loop return identical prices point by point
         res = eng.price_american(model, M, int(num_time_steps), self.K, self.option_type, self.dtype,
@@ -525,7 +537,8 @@ class AdvancedOptionPricer:
         price_european_streaming call per grid point does.  The generators advance exactly as in the per-point loop."""
         cv = self.use_control_variate and self.sigma is not None
         eu = self.use_streaming and self.european_approximation
-        grid_ok = self.batched and not eu and total_points > 0 and self.iv_model is None and self.lsm_regressor != "nn"
+        grid_ok = (self.batched and not eu and total_points > 0 and self.iv_model is None and self.lsm_regressor != "nn"
+                   and not self.qmc)
         if grid_ok:
             days = np.array([i / intervals_per_day for i in range(total_points, 0, -1)])
             steps = np.maximum(10, np.minimum(130, np.ceil(days))).astype(np.int64)

@@ -234,7 +234,7 @@ int optmc_ctx_destroy(optmc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->slab); cudaFree(ctx->cf); cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->gram);
   cudaFree(ctx->d_betas); cudaFree(ctx->d_bnd); cudaFree(ctx->d_exc); cudaFree(ctx->d_nitm); cudaFree(ctx->d_valid);
-  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->spill); cudaFree(ctx->gnet_rows); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
+  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->spill); cudaFree(ctx->qmc_dev); cudaFree(ctx->gnet_rows); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
   for (int r = 0; r < 8; ++r) if (ctx->comm.opened[r]) cudaIpcCloseMemHandle(ctx->comm.peers[r]);
   cudaFree(ctx->comm.local);
   for (int i = 0; i < 3; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -627,6 +627,21 @@ int optmc_price_european_batch(optmc_ctx* ctx, const optmc_model_params* mp, con
   OPTMC_TRY_BEGIN
   OPTMC_ENTER(ctx);
   return launch_european_batch(ctx, mp, rng, M, N, dtype, n_options, K, T, is_put, stream_id, results);
+  OPTMC_TRY_END
+}
+
+int optmc_qmc_normals(optmc_ctx* ctx, int64_t M, int32_t N, int32_t factors, int32_t brownian_bridge, int64_t pair_offset,
+                      const uint32_t* digital_shift, int32_t dtype, void* Z1_dev, void* Z2_dev) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return launch_qmc_normals(ctx, M, N, factors, brownian_bridge, pair_offset, digital_shift, dtype, Z1_dev, Z2_dev);
+  OPTMC_TRY_END
+}
+
+int optmc_qmc_bridge_schedule(int32_t N, int32_t* idx, int32_t* left, int32_t* right, double* wl, double* wr, double* sd) {
+  OPTMC_TRY_BEGIN
+  if (!idx || !left || !right || !wl || !wr || !sd) { set_error("null argument"); return OPTMC_EINVAL; }
+  return bridge_schedule_host(N, idx, left, right, wl, wr, sd);
   OPTMC_TRY_END
 }
 

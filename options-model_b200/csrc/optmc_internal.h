@@ -97,6 +97,8 @@ struct optmc_ctx {
   int* d_flags = nullptr;               // [4]: [0] = fixed-point exchange overflow
   void* batch_dev = nullptr; size_t batch_dev_cap = 0;  // per-wave descriptors / accumulators / results
   void* spill = nullptr;     size_t spill_bytes = 0;     // speculative sweep: candidate-list overflow
+  void* qmc_dev = nullptr;   size_t qmc_dev_cap = 0;     // Sobol direction numbers, digital shifts, bridge schedule
+  bool qmc_table_ready = false;
   void* gnet_rows = nullptr; size_t gnet_rows_cap = 0;  // global network LSM: regression rows of all dates (x, t, y)
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};      // kernel timing of the fused calls (optmc_ctx_kernel_times)
   double last_paths_ms = 0.0, last_sweep_ms = 0.0;
@@ -140,6 +142,11 @@ int launch_philox_normals(optmc_ctx* ctx, const optmc_rng_params* rng, int32_t m
 int launch_philox_kat(optmc_ctx* ctx, int n, const uint32_t* ctr, const uint32_t* key, uint32_t* out);
 int launch_features(optmc_ctx* ctx, const void* S, int64_t n, int32_t dtype, double K, double T, double t_current,
                     void* F);
+
+// qmc.cu
+int launch_qmc_normals(optmc_ctx* ctx, int64_t M, int32_t N, int32_t factors, int32_t bridge, int64_t pair_offset,
+                       const uint32_t* shift_host, int32_t dtype, void* Z1, void* Z2);
+int bridge_schedule_host(int32_t N, int32_t* idx, int32_t* left, int32_t* right, double* wl, double* wr, double* sd);
 
 // lsm.cu
 int sweep_begin(optmc_ctx* ctx);

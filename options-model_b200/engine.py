@@ -556,6 +556,31 @@ class Engine:
         extras["shape"] = [int(v) for v in ex.shape]
         return np.array([o.price for o in out]), np.array([o.stderr_ for o in out]), extras
 
+    def qmc_normals(self, M: int, N: int, factors: int = 1, bridge: bool = True, dtype="f64", shift_seed: Optional[int] = None,
+                    pair_offset: int = 0):
+        """Sobol' (Joe-Kuo) + Brownian-bridge normals as step-major device tensors [N, M/2] for
+        RngSpec(z1=..., z2=...).  shift_seed: random digital shift (randomised QMC; None = the plain sequence)."""
+        t = self.torch
+        td = t.float64 if dtype == "f64" else t.float32
+        Z1 = t.empty((N, M // 2), dtype=td, device=self.tdev)
+        Z2 = t.empty((N, M // 2), dtype=td, device=self.tdev) if factors == 2 else None
+        shift = None
+        if shift_seed is not None:
+            sh = np.random.default_rng(shift_seed).integers(0, 2**32, size=factors * N, dtype=np.uint64).astype(np.uint32)
+            shift = sh.ctypes.data_as(C.POINTER(C.c_uint32))
+        self._sync_stream()
+        L.check(self.lib.optmc_qmc_normals(self._h, int(M), int(N), int(factors), 1 if bridge else 0, int(pair_offset), shift,
+                                           _dtype_code(dtype), Z1.data_ptr(), Z2.data_ptr() if Z2 is not None else None))
+        return (Z1, Z2) if factors == 2 else Z1
+
+    def qmc_bridge_schedule(self, N: int):
+        ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        idx, left, right = (np.zeros(N, dtype=np.int32) for _ in range(3))
+        wl, wr, sd = (np.zeros(N) for _ in range(3))
+        L.check(self.lib.optmc_qmc_bridge_schedule(int(N), idx.ctypes.data_as(ip), left.ctypes.data_as(ip), right.ctypes.data_as(ip),
+                                                   wl.ctypes.data_as(dp), wr.ctypes.data_as(dp), sd.ctypes.data_as(dp)))
+        return idx, left, right, wl, wr, sd
+
     def price_european_grid(self, model: ModelSpec, M: int, S0, K, T, N, is_put, dtype="f32",
                             rng: Optional[RngSpec] = None, stream_id=None):
         """Fused no-store European pricing with per-option spot / strike / maturity / step count (the independent

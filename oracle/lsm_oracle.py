@@ -950,3 +950,67 @@ def price_american_lsm(S0, K, r, T, option_type, num_simulations, num_time_steps
     if return_paths:
         return res, S, normals
     return res
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Quasi-Monte-Carlo draws: no counterpart in the reference (PCG64 normals, om3:223-224,475).  Restated
+# from the published constructions: Sobol' points with Joe-Kuo (2008) direction numbers -- scipy.stats.qmc.Sobol ships
+# the same table and serves as the independent implementation of the point set -- and the Brownian-bridge ordering of
+# Jaeckel, "Monte Carlo Methods in Finance" (2002), sec. 10.8.3.
+# ----------------------------------------------------------------------------------------------------------------
+def brownian_bridge_schedule(N):
+    """Construction order on the unit grid t = 1..N: step s sets W(idx+1) = wl W(left) + wr W(right+1) + sd z_s (W(0) = 0)."""
+    idx, left, right = (np.zeros(N, dtype=np.int64) for _ in range(3))
+    wl, wr, sd = (np.zeros(N) for _ in range(3))
+    done = np.zeros(N, dtype=bool)
+    done[N - 1] = True
+    idx[0], right[0], sd[0] = N - 1, N - 1, np.sqrt(N)
+    j = 0
+    for i in range(1, N):
+        while done[j]:
+            j += 1
+        k = j
+        while not done[k]:
+            k += 1
+        l = j + ((k - 1 - j) >> 1)
+        done[l] = True
+        idx[i], left[i], right[i] = l, j, k
+        wl[i], wr[i] = (k - l) / (k + 1 - j), (l + 1 - j) / (k + 1 - j)
+        sd[i] = np.sqrt((l + 1 - j) * (k - l) / (k + 1 - j))
+        j = k + 1
+        if j >= N:
+            j = 0
+    return idx, left, right, wl, wr, sd
+
+
+def sobol_bridge_normals(M, N, factors=1, bridge=True, shift=None, pair_offset=0):
+    """Step-major normals [factors][N][M/2] of antithetic pairs pair_offset .. pair_offset + M/2 - 1: Sobol' point
+    (pair index + 1) in factors * N dimensions, optional digital shift (uint32 per dimension), u = (x + 1/2) 2^-32,
+    z = Phi^-1(u); with ``bridge`` the dimensions of a factor drive the Brownian-bridge construction and the normals
+    are the increments of the constructed path."""
+    from scipy.special import ndtri
+    from scipy.stats import qmc
+
+    D, Mh = factors * N, M // 2
+    eng = qmc.Sobol(d=D, scramble=False, bits=32)
+    eng.fast_forward(1 + int(pair_offset))
+    x = np.rint(eng.random(Mh) * 4294967296.0).astype(np.uint64).astype(np.uint32)  # [Mh, D], exact multiples of 2^-32
+    if shift is not None:
+        x = x ^ np.asarray(shift, dtype=np.uint32)[None, :]
+    z = ndtri((x.astype(np.float64) + 0.5) * 2.3283064365386963e-10)          # [Mh, D]
+    out = np.empty((factors, N, Mh))
+    sched = brownian_bridge_schedule(N) if bridge else None
+    for f in range(factors):
+        zf = z[:, f * N:(f + 1) * N]
+        if not bridge:
+            out[f] = zf.T
+            continue
+        idx, left, right, wl, wr, sd = sched
+        W = np.zeros((N, Mh))
+        W[idx[0]] = sd[0] * zf[:, 0]
+        for s in range(1, N):
+            lo = W[left[s] - 1] if left[s] > 0 else 0.0
+            W[idx[s]] = wl[s] * lo + wr[s] * W[right[s]] + sd[s] * zf[:, s]
+        out[f, 0] = W[0]
+        out[f, 1:] = W[1:] - W[:-1]
+    return out

@@ -283,3 +283,21 @@ def test_compat_iv_model_with_control_variate(mods, golden_dir):
     assert np.isfinite(e) and e > 0
     rec = p.compute_curve_for_S0(100.0, 1, 3, 2000, False)
     assert len(rec) == 3 and all(np.isfinite(r["Option Value"]) for r in rec)
+
+
+def test_compat_qmc_flag(mods):
+    """AdvancedOptionPricer(qmc=True): Sobol' + Brownian-bridge draws behind the reference's call signature (GBM and
+    Heston); same estimator, tighter: the spread over seeds is smaller than with pseudo-random draws."""
+    from options_model_b200 import compat
+
+    vals = {False: [], True: []}
+    for q in (False, True):
+        for sd in range(8):
+            p = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, option_type="put", rng_manager=compat.RNGManager(sd),
+                                            use_control_variate=False, semantics="textbook", qmc=q)
+            vals[q].append(p.price_american_option(100.0, 1.0, 50_000, 50))
+    assert abs(np.mean(vals[True]) - np.mean(vals[False])) < 0.05 and np.std(vals[True]) < np.std(vals[False])
+    ph = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=None, option_type="put", rng_manager=compat.RNGManager(1),
+                                     use_heston=True, heston_params=HP, use_control_variate=False, qmc=True)
+    v = ph.price_american_option(100.0, 1.0, 50_000, 50)
+    assert 5.0 < v < 7.0

@@ -231,3 +231,53 @@ def test_localvol_philox_counters_and_throughput(eng, mods, golden_dir):
     Z = eng.philox_normals(L.MODEL_GBM, M, N, 0, "f64", rng)  # the GBM counter layout: 4 steps per Philox block
     ref = orc.localvol_paths_antithetic(100.0, 0.05, 1.0, M, N, net, 105.0, Z.cpu().numpy())
     np.testing.assert_allclose(S.cpu().numpy(), ref, rtol=5e-5)
+
+
+@pytest.mark.parametrize("bridge", [False, True])
+def test_qmc_normals_vs_oracle(eng, mods, bridge):
+    """Sobol' (Joe-Kuo) + Brownian-bridge normals against the oracle's restatement (scipy's Sobol' engine as
+    the independent point set, Jaeckel's bridge): plain and digitally shifted, one and two factors, and sharded blocks
+    (pair_offset) equal to the corresponding columns of the whole set."""
+    L, E, orc = mods
+    M, N = 4096, 50
+    for factors, seed in ((1, None), (2, 5)):
+        got = eng.qmc_normals(M, N, factors=factors, bridge=bridge, dtype="f64", shift_seed=seed)
+        got = [got] if factors == 1 else list(got)
+        shift = None
+        if seed is not None:
+            shift = np.random.default_rng(seed).integers(0, 2**32, size=factors * N, dtype=np.uint64).astype(np.uint32)
+        ref = orc.sobol_bridge_normals(M, N, factors, bridge, shift)
+        for f in range(factors):
+            np.testing.assert_allclose(got[f].cpu().numpy(), ref[f], rtol=1e-9, atol=1e-9)
+    whole = eng.qmc_normals(M, N, factors=1, bridge=bridge, dtype="f64", shift_seed=9).cpu().numpy()
+    part = eng.qmc_normals(M // 2, N, factors=1, bridge=bridge, dtype="f64", shift_seed=9, pair_offset=M // 4).cpu().numpy()
+    np.testing.assert_array_equal(part, whole[:, M // 4:])
+    z = eng.qmc_normals(1 << 16, N, factors=1, bridge=bridge, dtype="f32", shift_seed=1).double().cpu().numpy()
+    assert abs(z.mean()) < 1e-3 and abs(z.var() - 1) < 2e-3  # far tighter than 65536 x 50 pseudo-random draws would be
+
+
+def test_qmc_brownian_bridge_reduces_the_error_of_config1(eng, mods):
+    """Randomised QMC (16 digital shifts) vs Philox (16 seeds) on BASELINE config 1 (GBM put 100 k x 50, textbook
+    semantics, judged against the textbook value, not the reference): European leg and American price agree within
+    the spreads, and the spread over shifts is several times smaller than over pseudo-random seeds."""
+    L, E, orc = mods
+    M, N, K = 100_000, 50, 100.0
+    gbm = E.gbm(100.0, 0.05, 1.0, 0.2)
+    from options_model_b200 import compat
+
+    bs = compat.BlackScholesGreeks.black_scholes_price(100.0, K, 1.0, 0.05, 0.2, "put")
+    res = {"qmc": [], "philox": []}
+    for s in range(16):
+        z = eng.qmc_normals(M, N, factors=1, bridge=True, dtype="f32", shift_seed=100 + s)
+        Sq = eng.paths(gbm, M, N, "f32", E.RngSpec(z1=z))
+        Sp = eng.paths(gbm, M, N, "f32", E.RngSpec(seed=100 + s))
+        for name, S in (("qmc", Sq), ("philox", Sp)):
+            eu, _ = eng.european_from_slab(S[N].contiguous(), K, 0.05, 1.0, "put")
+            am = eng.lsm(S, K, 0.05, 1.0, "put", semantics="textbook", arrays=False).price
+            res[name].append((eu, am))
+    q, p = np.array(res["qmc"]), np.array(res["philox"])
+    assert abs(q[:, 0].mean() - bs) < 4 * q[:, 0].std() / 4 + 1e-4      # unbiased: mean over shifts vs Black-Scholes
+    assert q[:, 0].std() < 0.25 * p[:, 0].std()                            # European leg: > 4x smaller spread
+    assert q[:, 1].std() < 0.6 * p[:, 1].std()                             # American price: the regression noise remains
+    assert abs(q[:, 1].mean() - p[:, 1].mean()) < 3 * np.hypot(q[:, 1].std(), p[:, 1].std()) / 4 + 5e-3
+    assert 6.0 < q[:, 1].mean() < 6.15                                     # textbook value of config 1 (binomial 6.09)

@@ -157,3 +157,32 @@ def test_fixed_point_exchange_is_exact_and_order_independent(hs):
     for bad in (1e13, -1e13, np.inf, np.nan):
         v = np.array([1.0, bad])
         assert hs.hs_fx_sum(2, _p(v), C.byref(out), words) == 0
+
+
+def test_brownian_bridge_schedule_matches_oracle_and_reproduces_brownian_covariance():
+    """optmc_qmc_bridge_schedule (host code of csrc/qmc.cu, no GPU needed) == the oracle's restatement of Jaeckel's
+    construction; as a linear map W = A z it must reproduce Cov(W_s, W_t) = min(s, t) exactly, for any N."""
+    import ctypes as C
+
+    from options_model_b200 import _lib as L
+    from oracle import lsm_oracle as orc
+
+    lib = L.load_library()
+    ip, dp = C.POINTER(C.c_int32), C.POINTER(C.c_double)
+    for N in (1, 2, 3, 7, 50, 64, 252):
+        idx, left, right = (np.zeros(N, dtype=np.int32) for _ in range(3))
+        wl, wr, sd = (np.zeros(N) for _ in range(3))
+        assert lib.optmc_qmc_bridge_schedule(N, idx.ctypes.data_as(ip), left.ctypes.data_as(ip), right.ctypes.data_as(ip),
+                                             wl.ctypes.data_as(dp), wr.ctypes.data_as(dp), sd.ctypes.data_as(dp)) == 0
+        o = orc.brownian_bridge_schedule(N)
+        for got, want in zip((idx, left, right, wl, wr, sd), o):
+            np.testing.assert_allclose(got, want, rtol=1e-15)
+        assert sorted(idx.tolist()) == list(range(N))
+        A = np.zeros((N, N))  # W = A z
+        A[idx[0], 0] = sd[0]
+        for s in range(1, N):
+            lo = A[left[s] - 1] if left[s] > 0 else 0.0
+            A[idx[s]] = wl[s] * lo + wr[s] * A[right[s]]
+            A[idx[s], s] += sd[s]
+        t = np.arange(1, N + 1)
+        np.testing.assert_allclose(A @ A.T, np.minimum.outer(t, t), rtol=1e-12, atol=1e-12)
