@@ -277,6 +277,10 @@ def run_own_arm(args):
 
         for i in range(args.warmup):
             step(i)
+        # which sweep kernel the batch entry point kept for this box (it times both on the first wave of a new shape)
+        shape = eng.price_american_batch(model, M, S0, K, T, Ns, 1, "f32", E.RngSpec(seed=42, pair_offset=rank * (M // 2)),
+                                         "poly2", "reference", streams=np.arange(B), details=True,
+                                         M_total=M * world if shard == "paths" else 0)[2]["shape"]
         barrier()
         l0 = eng.launch_count()
         ms_paths = ms_sweep = 0.0
@@ -433,7 +437,9 @@ def run_own_arm(args):
             "paths_x2_batch_kernel<heston_ref_absorb> (f32x2 packed step, 3 steps per Philox block)": {
                 "ms": ms_paths, "alg_bytes": bytes_paths, "GBps": bytes_paths / (ms_paths * 1e-3) / 1e9,
                 "frac": bytes_paths / (ms_paths * 1e-3) / 1e9 / peak, "dram_bytes_ncu": traffic["paths"]},
-            "lsm_resident_kernel<f32,poly2,sparse> (grouped, 4 x 37 CTAs)": {
+            (f"lsm_resident_spec_kernel<f32,poly2,{shape[1]},{shape[0]}> (grouped, {shape[3]} x {shape[2]} CTAs, speculative)"
+             if shape[0] in (480, 736) else
+             f"lsm_resident_kernel<f32,poly2,{shape[1]},{shape[0]},sparse> (grouped, {shape[3]} x {shape[2]} CTAs)"): {
                 "ms": ms_sweep, "alg_bytes": bytes_sweep, "GBps": bytes_sweep / (ms_sweep * 1e-3) / 1e9,
                 "frac": bytes_sweep / (ms_sweep * 1e-3) / 1e9 / peak, "dram_bytes_ncu": traffic["sweep"]},
         }
@@ -454,7 +460,9 @@ def run_own_arm(args):
                        "storage": "fp32 step-major slab, fp64 Gram/solve/decision", "rng": "Philox4x32-10 in-register",
                        "sharding": sharding, "shard_mode": shard,
                        "l2": f"slabs {B * b * M * (N + 1) / 1e6:.0f} MB per step > L2 ({eng.l2_bytes / 1e6:.0f} MB): no flush needed",
-                       "price": price0, "stderr": se0, "git": git_head()},
+                       "price": price0, "stderr": se0, "git": git_head(),
+                       "sweep_shape": {"threads": shape[0], "paths_per_thread": shape[1], "ctas_per_option": shape[2],
+                                       "options_per_launch": shape[3]}},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "traffic": kern[dom]["dram_bytes_ncu"], "kernel": dom, "peak_source": peak_src,
                          "traffic_source": f"{traffic['source']} (ncu dram__bytes_read+write per launch, build {traffic['git']})",

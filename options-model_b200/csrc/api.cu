@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <stdlib.h>
+
 #include "optmc_internal.h"
 
 namespace optmc {

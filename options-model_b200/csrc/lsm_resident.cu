@@ -34,7 +34,9 @@ static const ResShape kSpecShapes[] = {OPTMC_RES_SPEC_SHAPES(X)};  // nt = compu
 
 // Slice the M paths of ONE option over at most `max_ctas` CTAs and pick the smallest compiled (threads,
 // paths-per-thread) shape that holds a slice.
-static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int max_ctas, ResPlan* p, std::string* why) {
+// force_spec: -1 = the planner's rule, 0 / 1 = single-role / speculative kernel (the batch entry point's autotuner)
+static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int max_ctas, ResPlan* p, std::string* why,
+                       int force_spec = -1) {
   const size_t es = dtype == OPTMC_F64 ? 8 : 4;
   if ((M * es) % 16 != 0) { *why = "path count is not a multiple of 16 bytes (bulk copies move whole 16-byte units)"; return false; }
   if (ctx->cc < 90) { *why = "bulk async copy needs sm_90+"; return false; }
@@ -49,8 +51,12 @@ static bool plan_shape(optmc_ctx* ctx, long long M, int dtype, bool sticky, int 
   // Measured (profiles/sweep_bench_r2.txt): the speculative kernel wins where the per-date dependency chain, not the
   // scan, bounds a date -- slices of up to ~7 k paths per CTA (one 1 M-path option on the whole machine: 0.80 vs
   // 0.86 ms) -- and loses on larger slices, whose scan is issue-bound (13.5 k paths: 1.23 vs 1.15 ms; the 27 k-path
-  // slices of grouped launches: 2.57 vs 1.61 ms): those keep the single-role kernel.
-  if (p->spec && !getenv("OPTMC_RES_SPEC")) {
+  // slices of grouped launches: 2.57 vs 1.61 ms): those keep the single-role kernel.  The pool's boxes differ (on
+  // some the single-role kernel's solve section takes 4 500 instead of 700 cycles and the speculative kernel wins at
+  // every size: DESIGN.md 4, "box variance"), so the batch entry point does not trust this rule blindly: it times both
+  // kernels on the first wave of a new batch shape and keeps the faster (price_american_batch).
+  if (force_spec >= 0) p->spec = p->sparse && force_spec != 0;
+  else if (p->spec && !getenv("OPTMC_RES_SPEC")) {
     long long nc = (M + 479) / 480;
     const int cap = ctx->sm_count < max_ctas ? ctx->sm_count : max_ctas;
     if (nc > cap) nc = cap;
@@ -309,6 +315,22 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
   unsigned long long* d_exc = details ? d_bnd + (size_t)G * n1 : nullptr;
   long long* d_nitm = details ? reinterpret_cast<long long*>(d_exc + (size_t)G * n1) : nullptr;
 
+  // Autotuned kernel choice (sticky semantics, not sharded, no OPTMC_RES_SPEC override): the first wave of a batch shape
+  // this context has not seen is swept by BOTH kernels (same slabs, bit-identical results), timed by CUDA events, and
+  // the faster one is remembered for the shape.
+  const unsigned long long tune_key = ((unsigned long long)M << 20) ^ ((unsigned long long)G << 8) ^ (unsigned)(dtype * 4 + deg);
+  bool do_tune = false;
+  if (sticky && !M_total && !getenv("OPTMC_RES_SPEC") && !getenv("OPTMC_BATCH_CPG")) {
+    int known = -1;
+    for (const auto& kv : ctx->sweep_choice) if (kv.first == tune_key) known = kv.second;
+    if (known < 0) do_tune = true;
+    else if ((known != 0) != p.spec) {
+      ResPlan pk;
+      if (plan_shape(ctx, M, dtype, sticky, ctx->sm_count / G, &pk, &why, known)) { p = pk; cpg = p.ncta; p.ngroups = G; }
+    }
+  }
+  if (ex) { ex->shape[0] = p.nt; ex->shape[1] = p.ppt; ex->shape[2] = cpg; ex->shape[3] = G; }
+
   std::vector<ResGroup> hg(G);
   std::vector<char> hp(path_args_bytes() * G);
   std::vector<double> hfin((size_t)G * 8);
@@ -356,6 +378,36 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
     rc = launch_resident(ctx, pw, a, dtype, deg);
     if (rc) return rc;
     OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (do_tune && w0 == 0) {
+      do_tune = false;
+      ResPlan alt;
+      int choice = p.spec ? 1 : 0;
+      if (plan_shape(ctx, M, dtype, sticky, ctx->sm_count / G, &alt, &why, p.spec ? 0 : 1) && alt.ncta * G <= ctx->sm_count &&
+          alt.spec != p.spec) {
+        float ms_a = 0.f, ms_b = 0.f;
+        OPTMC_CUDA(cudaEventSynchronize(ctx->ev[2]));
+        cudaEventElapsedTime(&ms_a, ctx->ev[1], ctx->ev[2]);
+        for (int g = 0; g < g_now; ++g) hg[g].chunk = alt.chunk;
+        OPTMC_CUDA(cudaMemcpyAsync(d_groups, hg.data(), sizeof(ResGroup) * g_now, cudaMemcpyHostToDevice, ctx->stream));
+        batch_reset_kernel<<<8, 256, 0, ctx->stream>>>(d_words, (int)n_words, d_final, G * 8, d_betas, d_bnd, d_exc, d_nitm,
+                                                       details ? g_now * n1 : 0, d_groups, n1);
+        ctx->launches++;
+        OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+        ResPlan pa = alt;
+        pa.ngroups = g_now;
+        ResArgs b{};
+        b.groups = d_groups; b.cpg = alt.ncta; b.nstage = alt.nstage; b.stage_stride = alt.stage_stride; b.sticky = 1;
+        b.want_eu = a.want_eu;
+        rc = launch_resident(ctx, pa, b, dtype, deg);
+        if (rc) return rc;
+        OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+        OPTMC_CUDA(cudaEventSynchronize(ctx->ev[2]));
+        cudaEventElapsedTime(&ms_b, ctx->ev[1], ctx->ev[2]);
+        if (ms_b < ms_a) { p = alt; cpg = alt.ncta; p.ngroups = G; choice = alt.spec ? 1 : 0; }
+        if (ex) { ex->shape[0] = p.nt; ex->shape[1] = p.ppt; ex->shape[2] = cpg; ex->shape[3] = G; }
+      }
+      ctx->sweep_choice.push_back({tune_key, choice});
+    }
     OPTMC_CUDA(cudaMemcpyAsync(hfin.data(), d_final, sizeof(double) * 8 * g_now, cudaMemcpyDeviceToHost, ctx->stream));
     OPTMC_CUDA(cudaMemcpyAsync(hflags.data(), d_flags, sizeof(int) * 4 * g_now, cudaMemcpyDeviceToHost, ctx->stream));
     if (details)

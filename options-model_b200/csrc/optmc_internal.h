@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/optmc.h"
@@ -79,6 +80,7 @@ struct optmc_ctx {
   int max_smem_optin = 0;
   int cc = 0;
   int64_t launches = 0;
+  std::vector<std::pair<unsigned long long, int>> sweep_choice;  // batch shape -> timed kernel choice (lsm_resident.cu)
 
   // grow-only device workspaces
   void* slab = nullptr;      size_t slab_bytes = 0;      // price_american path slab

@@ -355,7 +355,9 @@ def test_bench_shape_4x1M_fp32_vs_oracle_same_draws(eng, mods):
         nt, ppt, cpg, G = ex["shape"]
         assert (cpg, G) == (eng.sm_count // B, B) and nt * ppt * cpg >= M, ex["shape"]
         if sem == "reference" and eng.sm_count == 148:
-            assert (nt, ppt) == (768, 36), ex["shape"]  # the sparse wide shape of the headline bench
+            # the wide shape of the headline bench: single-role 768 x 36 or speculative (736 + 32) x 37, whichever the
+            # batch entry point timed faster on this box (both kernels give bit-identical results)
+            assert (nt, ppt) in ((768, 36), (736, 37)), ex["shape"]
     for i in range(B):
         rng = E.RngSpec(seed=42, stream=int(streams[i]))
         z1 = eng.philox_normals(L.MODEL_HESTON, M, N, 0, "f32", rng).double().cpu().numpy()
@@ -400,7 +402,9 @@ def test_batch_extras_equal_single_option_outputs(eng, mods):
             np.testing.assert_array_equal(ex["n_itm"][i, :n1], single.n_itm)
             np.testing.assert_array_equal(np.isnan(ex["boundary"][i, :n1]), np.isnan(single.boundary))
             np.testing.assert_allclose(np.nan_to_num(ex["boundary"][i, :n1]), np.nan_to_num(single.boundary), rtol=0)
-            np.testing.assert_allclose(np.nan_to_num(ex["betas"][i, :n1, :3]), np.nan_to_num(single.betas), rtol=1e-9, atol=1e-12)
+            # different launch geometry (the batch entry point times both sweep kernels): the fixed-point grid sums truncate per
+            # CTA, which moves the ill-conditioned individual betas in the 9th digit
+            np.testing.assert_allclose(np.nan_to_num(ex["betas"][i, :n1, :3]), np.nan_to_num(single.betas), rtol=1e-7, atol=1e-10)
             Ssl = eng.paths(m, M, int(N[i]), "f64", rs)
             eu, eu_se = eng.european_from_slab(Ssl[int(N[i])].contiguous(), K[i], 0.05, T[i], ot)
             assert ex["european"][i, 0] == pytest.approx(eu, rel=1e-12)
