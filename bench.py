@@ -275,6 +275,23 @@ def run_own_arm(args):
             return eng.price_american_batch(model, M, S0, K, T, Ns, 1, "f32", E.RngSpec(seed=42), "poly2", "reference",
                                             streams=streams)
 
+        tuned = None
+        if shard == "paths" and "OPTMC_RES_SPEC" not in os.environ:
+            # the sharded batch cannot time its two sweep kernels inside one call (every rank must launch the same one):
+            # time both here, max over ranks, and keep the faster for the rest of the run (OPTMC_RES_SPEC is the
+            # library's kernel override; the results are bit-identical either way)
+            tuned = {}
+            for spec in ("0", "1"):
+                os.environ["OPTMC_RES_SPEC"] = spec
+                step(0)
+                barrier()
+                t0 = time.perf_counter()
+                for i in range(3):
+                    step(i)
+                torch.cuda.synchronize()
+                tuned["speculative" if spec == "1" else "single_role"] = max_over_ranks((time.perf_counter() - t0) / 3 * 1e3)
+            os.environ["OPTMC_RES_SPEC"] = "1" if tuned["speculative"] < tuned["single_role"] else "0"
+            tuned["kept"] = "speculative" if os.environ["OPTMC_RES_SPEC"] == "1" else "single_role"
         for i in range(args.warmup):
             step(i)
         # which sweep kernel the batch entry point kept for this box (it times both on the first wave of a new shape)
@@ -461,6 +478,7 @@ def run_own_arm(args):
                        "sharding": sharding, "shard_mode": shard,
                        "l2": f"slabs {B * b * M * (N + 1) / 1e6:.0f} MB per step > L2 ({eng.l2_bytes / 1e6:.0f} MB): no flush needed",
                        "price": price0, "stderr": se0, "git": git_head(),
+                       "sharded_sweep_kernel_ms_per_step": tuned,
                        "sweep_shape": {"threads": shape[0], "paths_per_thread": shape[1], "ctas_per_option": shape[2],
                                        "options_per_launch": shape[3]}},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
