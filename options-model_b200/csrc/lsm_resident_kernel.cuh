@@ -741,11 +741,14 @@ __device__ __forceinline__ void sts_at(uint32_t addr, double v) { asm volatile("
 
 template <typename R, int PPT, int NT, int K, int K1> struct ScanSteps {
   typedef typename MaskOf<(PPT > 32)>::type Mask;
+  // (st, sg) of step K arrive preloaded: the loads of step K + 1 are issued before the vote of step K, so their
+  // latency overlaps it (the per-step chain load -> compare -> vote -> branch bounds the scan of a warp)
   static __device__ __forceinline__ void run(const R (&cf)[PPT], uint32_t at, uint32_t ag, R sgn, R kk_t, R kk_g, Mask& listed,
-                                             const CandList<R>& list, uint32_t seg, int& n_w) {
+                                             const CandList<R>& list, uint32_t seg, int& n_w, R st, R sg) {
     const R c = cf[K];
-    const R st = lds_imm<K * NT * (int)sizeof(R)>(at, R());
-    const R sg = lds_imm<K * NT * (int)sizeof(R)>(ag, R());
+    constexpr int KN = K + 1 < K1 ? K + 1 : K;
+    const R st_n = lds_imm<KN * NT * (int)sizeof(R)>(at, R());
+    const R sg_n = lds_imm<KN * NT * (int)sizeof(R)>(ag, R());
     const bool in = !(c < (R)0) & ((sgn * st > kk_t) | (sgn * sg > kk_g));  // open (sign bit clear) and in the money
     const unsigned int bal = __ballot_sync(0xffffffffu, in);
     if (bal) {  // warp-uniform; ~15% of the steps
@@ -768,12 +771,12 @@ template <typename R, int PPT, int NT, int K, int K1> struct ScanSteps {
       list.n_before[K] = (unsigned char)(n_w < 255 ? n_w : 255);
       n_w += __popc(bal);
     }
-    ScanSteps<R, PPT, NT, K + 1, K1>::run(cf, at, ag, sgn, kk_t, kk_g, listed, list, seg, n_w);
+    ScanSteps<R, PPT, NT, K + 1, K1>::run(cf, at, ag, sgn, kk_t, kk_g, listed, list, seg, n_w, st_n, sg_n);
   }
 };
 template <typename R, int PPT, int NT, int K1> struct ScanSteps<R, PPT, NT, K1, K1> {
   typedef typename MaskOf<(PPT > 32)>::type Mask;
-  static __device__ __forceinline__ void run(const R (&)[PPT], uint32_t, uint32_t, R, R, R, Mask&, const CandList<R>&, uint32_t, int&) {}
+  static __device__ __forceinline__ void run(const R (&)[PPT], uint32_t, uint32_t, R, R, R, Mask&, const CandList<R>&, uint32_t, int&, R, R) {}
 };
 
 template <typename R, int PPT, int NT, int K0, int K1>
@@ -783,7 +786,9 @@ __device__ __forceinline__ void scan_pass(const R (&cf)[PPT], const R* __restric
   // decide / gram are off at the first / last date only: an "in the money" threshold nothing passes switches the test off
   const R kk_t = decide ? pc.kk : (R)INFINITY, kk_g = gram ? pc.kk : (R)INFINITY;
   const uint32_t at = smem_u32(st_t) + threadIdx.x * (uint32_t)sizeof(R), ag = smem_u32(st_g) + threadIdx.x * (uint32_t)sizeof(R);
-  ScanSteps<R, PPT, NT, K0, K1>::run(cf, at, ag, pc.sgn, kk_t, kk_g, listed, list, smem_u32(list.smem), n_w);
+  if (K0 >= K1) return;
+  ScanSteps<R, PPT, NT, K0, K1>::run(cf, at, ag, pc.sgn, kk_t, kk_g, listed, list, smem_u32(list.smem), n_w,
+                                     lds_imm<K0 * NT * (int)sizeof(R)>(at, R()), lds_imm<K0 * NT * (int)sizeof(R)>(ag, R()));
 }
 
 // The listed paths of the warp, one lane per entry, once beta_t is known (valid = the regression of date t
