@@ -320,6 +320,14 @@ int optmc_lsm_gnet(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int
  * W3[128][128] b3 w4[128] b4 (torch state_dict order), without dropout. */
 int optmc_gnet_grad_debug(optmc_ctx* ctx, int64_t n, const float* feat, const float* ys, const float* params, float* grads,
                           float* loss);
+/* Test aid: the counter-based shuffle and dropout streams of optmc_lsm_gnet, evaluated by the device code the training
+ * and decision kernels use (the reference draws both from torch's global generator, om3:577 / om3:96-101; a paired
+ * check against the torch restatement needs the engine's).  perm_out[i], i < n_rows: the row that position i of epoch
+ * `epoch` (0-based) reads.  keep_out[(i * 3 + layer) * 4 + w]: bit b set = hidden unit 32 w + b of `layer` is kept for
+ * row id row_ids[i], under optimiser step `step` (1-based, counted across epochs; the row id is the position in the
+ * epoch's order) or, with step == 0, under the decision pass (row id = (uint32) path * 0x01000193 + date).  Host pointers. */
+int optmc_gnet_streams_debug(optmc_ctx* ctx, uint64_t seed, int32_t epoch, int32_t step, double dropout, int64_t n_rows,
+                             int64_t* perm_out, const uint32_t* row_ids, int64_t n_ids, uint32_t* keep_out);
 
 /* Per-date building blocks for path-sharded multi-GPU sweeps: the host all-reduces `gram_dev`
  * (optmc_lsm_gram_len doubles) between the two calls. */

@@ -140,6 +140,8 @@ PROTOTYPES = {
                                  _P(GnetParams), _P(GnetResult)]),
     "optmc_gnet_grad_debug": (C.c_int, [C.c_void_p, C.c_int64, _P(C.c_float), _P(C.c_float), _P(C.c_float), _P(C.c_float),
                                         _P(C.c_float)]),
+    "optmc_gnet_streams_debug": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_double, C.c_int64, _P(C.c_int64),
+                                           _P(C.c_uint32), C.c_int64, _P(C.c_uint32)]),
     "optmc_lsm_gram_len": (C.c_int, [C.c_int32]),
     "optmc_lsm_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams)]),
     "optmc_lsm_gram_date": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),

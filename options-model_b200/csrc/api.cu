@@ -496,6 +496,14 @@ int optmc_gnet_grad_debug(optmc_ctx* ctx, int64_t n, const float* feat, const fl
   OPTMC_TRY_END
 }
 
+int optmc_gnet_streams_debug(optmc_ctx* ctx, uint64_t seed, int32_t epoch, int32_t step, double dropout, int64_t n_rows,
+                             int64_t* perm_out, const uint32_t* row_ids, int64_t n_ids, uint32_t* keep_out) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  return gnet_streams_debug(ctx, seed, epoch, step, dropout, n_rows, reinterpret_cast<long long*>(perm_out), row_ids, n_ids, keep_out);
+  OPTMC_TRY_END
+}
+
 int optmc_lsm_mlp(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
                   const optmc_lsm_params* lp, const optmc_mlp_params* np, optmc_lsm_result* out) {
   OPTMC_TRY_BEGIN

@@ -972,4 +972,49 @@ int gnet_grad_debug(optmc_ctx* ctx, long long n, const float* feat, const float*
   return OPTMC_OK;
 }
 
+// Test aid: the engine's shuffle and dropout streams as the training / decision kernels evaluate them.  perm_out[i] = the
+// row position i of epoch `epoch` reads (n_rows rows); keep_out[(i * 3 + layer) * 4 + w] = 32 keep bits (units 32 w ..)
+// of row id row_ids[i] under the stream of optimiser step `step` (step > 0) or of the decision pass (step == 0).
+__global__ void gnet_streams_kernel(Perm perm, Drop drop, long long n_perm, const unsigned int* __restrict__ row_ids, long long n_ids,
+                                    long long* __restrict__ perm_out, unsigned int* __restrict__ keep_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_perm) perm_out[i] = (long long)perm_apply(perm, (unsigned long long)i);
+  if (i < n_ids) {
+    const unsigned int r = row_ids[i];
+    for (int layer = 0; layer < 3; ++layer)
+      for (int w = 0; w < 4; ++w) {
+        unsigned int word = 0u;
+        for (int q = 0; q < 4; ++q) word |= drop_keep8(drop, r, layer, w * 4 + q) << (q * 8);
+        keep_out[(i * 3 + layer) * 4 + w] = word;
+      }
+  }
+}
+
+int gnet_streams_debug(optmc_ctx* ctx, unsigned long long seed, int epoch, int step, double dropout, long long n_rows,
+                       long long* perm_out, const unsigned int* row_ids, long long n_ids, unsigned int* keep_out) {
+  if (n_rows < 0 || n_ids < 0 || epoch < 0 || step < 0 || (n_rows > 0 && !perm_out) || (n_ids > 0 && (!row_ids || !keep_out))) {
+    set_error("bad argument"); return OPTMC_EINVAL;
+  }
+  const long long n = n_rows > n_ids ? n_rows : n_ids;
+  if (n == 0) return OPTMC_OK;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_perm = take((size_t)n_rows * 8), o_ids = take((size_t)n_ids * 4), o_keep = take((size_t)n_ids * 48);
+  int rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
+  if (rc) return rc;
+  char* dev = static_cast<char*>(ctx->batch_dev);
+  if (n_ids) OPTMC_CUDA(cudaMemcpyAsync(dev + o_ids, row_ids, (size_t)n_ids * 4, cudaMemcpyHostToDevice, ctx->stream));
+  const Perm perm = make_perm((unsigned long long)n_rows, (unsigned int)(seed * 0x9e3779b97f4a7c15ull >> 32) + 0x632be5abu * (unsigned int)(epoch + 1));
+  const Drop drop = make_drop(dropout, (unsigned int)seed * 0x2545f491u + (step > 0 ? (unsigned int)step * 0x9e3779b1u : 0x51ed270bu));
+  gnet_streams_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(perm, drop, n_rows, reinterpret_cast<unsigned int*>(dev + o_ids), n_ids,
+                                                                           reinterpret_cast<long long*>(dev + o_perm),
+                                                                           reinterpret_cast<unsigned int*>(dev + o_keep));
+  ctx->launches += 1;
+  OPTMC_CUDA(cudaGetLastError());
+  if (n_rows) OPTMC_CUDA(cudaMemcpyAsync(perm_out, dev + o_perm, (size_t)n_rows * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (n_ids) OPTMC_CUDA(cudaMemcpyAsync(keep_out, dev + o_keep, (size_t)n_ids * 48, cudaMemcpyDeviceToHost, ctx->stream));
+  OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return OPTMC_OK;
+}
+
 }  // namespace optmc

@@ -178,6 +178,8 @@ int lsm_apply_policy(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32
 int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
              const optmc_gnet_params* gp, optmc_gnet_result* out);
 int gnet_grad_debug(optmc_ctx* ctx, long long n, const float* feat, const float* ys, const float* params, float* grads, float* loss);
+int gnet_streams_debug(optmc_ctx* ctx, unsigned long long seed, int epoch, int step, double dropout, long long n_rows,
+                       long long* perm_out, const unsigned int* row_ids, long long n_ids, unsigned int* keep_out);
 int mlp_init_params_host(int H, unsigned long long seed, int date, float* out);
 int mlp_grad_debug(optmc_ctx* ctx, int H, long long n, const float* xs, const float* ys, const float* params, float* grads,
                    float* cont);

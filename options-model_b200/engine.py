@@ -439,6 +439,20 @@ class Engine:
                                                params.ctypes.data_as(fp), grads.ctypes.data_as(fp), C.byref(loss)))
         return grads, float(loss.value)
 
+    def gnet_streams_debug(self, seed: int, epoch: int = 0, step: int = 1, dropout: float = 0.1, n_rows: int = 0, row_ids=None):
+        """The shuffle of `epoch` over n_rows rows and the keep masks [len(row_ids), 3, 128] of optimiser step `step`
+        (0 = the decision pass) as the device code evaluates them -- test aid for the paired training check."""
+        perm = np.zeros(int(n_rows), dtype=np.int64)
+        ids = np.ascontiguousarray(row_ids if row_ids is not None else np.zeros(0), dtype=np.uint32)
+        words = np.zeros((ids.size, 3, 4), dtype=np.uint32)
+        self._sync_stream()
+        L.check(self.lib.optmc_gnet_streams_debug(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(epoch), int(step), float(dropout),
+                                                  perm.size, perm.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                  ids.ctypes.data_as(C.POINTER(C.c_uint32)), ids.size,
+                                                  words.ctypes.data_as(C.POINTER(C.c_uint32))))
+        keep = ((words[:, :, :, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(ids.size, 3, 128)
+        return perm, keep
+
     def mlp_init_params(self, seed: int, date: int, hidden: int = 32) -> np.ndarray:
         n = 3 * hidden + hidden * hidden + hidden + 1
         out = np.zeros(n, dtype=np.float32)

@@ -223,6 +223,49 @@ def test_gnet_training_and_prices_vs_torch_restatement(eng, mods):
     assert got[0]["ex_count"][1:25].sum() > 0 and np.isnan(got[0]["boundary"][0])
 
 
+def test_gnet_streams_device_equals_numpy_restatement(eng, mods):
+    """The shuffle and the dropout masks the training / decision kernels evaluate (optmc_gnet_streams_debug runs the same
+    device functions) against oracle/engine_streams.py, bit for bit -- what makes the paired test below a paired one."""
+    from oracle import engine_streams as es
+
+    rows = np.concatenate([np.arange(300, dtype=np.uint32), es.walk_row_id(np.arange(39_000, 39_300), 17)])
+    for seed, ep, step, n in ((3, 0, 1, 1), (3, 1, 77, 1000), (2**40 + 5, 4, 301, 481_233), (42, 0, 0, 4097)):
+        perm, keep = eng.gnet_streams_debug(seed, ep, step, 0.1, n, rows)
+        assert np.array_equal(perm, es.feistel_perm(n, es.perm_key(seed, ep)))
+        key = es.train_drop_key(seed, step) if step else es.walk_drop_key(seed)
+        for layer in range(3):
+            assert np.array_equal(keep[:, layer], es.keep_mask(key, rows, layer, 0.1))
+    _, keep = eng.gnet_streams_debug(3, 0, 5, 0.0, 0, rows)
+    assert keep.all()
+
+
+def test_gnet_paired_training_vs_torch_same_init_shuffle_and_masks(eng, mods):
+    """the engine and the torch fp32 restatement of om3gpu:700-830 trained from the SAME initial weights
+    on the SAME mini-batches with the SAME dropout masks (oracle/engine_streams.py).  What differs is arithmetic: bf16
+    tensor-core operands in the two hidden layers.  Tolerances: per-epoch loss 0.2 %, price 1 %, exercise counts
+    within 2 % of the paths in total (replaces the 0.35-absolute statistical bound of the unpaired test above)."""
+    from oracle import engine_streams as es
+
+    L, E, orc = mods
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    M, N, epochs, seed = 40_000, 25, 12, 11
+    S = eng.paths(model, M, N, "f64", E.RngSpec(seed=8))
+    init = es.torch_default_init(5)
+    got = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "reference", variant="gpu", epochs=epochs, seed=seed, stop_patience=0,
+                       init_params=init, return_params=True)
+    log = []
+    price, st = es.paired_gnet(S.cpu().numpy(), 100.0, 0.05, 1.0, "put", init, seed, epochs=epochs, log=log)
+    assert got["n_rows"] == st["n_rows"] and got["epochs_run"] == epochs
+    assert got["best_loss"] == pytest.approx(st["best_loss"], rel=2e-3)
+    assert got["price"] == pytest.approx(price, rel=1e-2)
+    assert np.abs(got["ex_count"] - st["ex_count"]).sum() <= 0.02 * M
+    # the trained weights themselves stay close (300 optimiser steps of bf16-vs-fp32 drift): relative L2 distance
+    d = np.linalg.norm(got["params"] - st["params"]) / np.linalg.norm(st["params"])
+    print(f"paired gnet: price {got['price']:.5f} vs {price:.5f}, best loss {got['best_loss']:.6f} vs {st['best_loss']:.6f}, "
+          f"|d ex_count| {np.abs(got['ex_count'] - st['ex_count']).sum()} of {M}, param distance {d:.4f}")
+    assert d < 0.15, d
+
+
 def test_gnet_textbook_policy_is_sane_and_edge_cases(eng, mods):
     L, E, orc = mods
     gbm = E.gbm(100.0, 0.05, 1.0, 0.2)

@@ -186,3 +186,23 @@ def test_brownian_bridge_schedule_matches_oracle_and_reproduces_brownian_covaria
             A[idx[s], s] += sd[s]
         t = np.arange(1, N + 1)
         np.testing.assert_allclose(A @ A.T, np.minimum.outer(t, t), rtol=1e-12, atol=1e-12)
+
+
+def test_engine_stream_restatements_are_well_formed():
+    """oracle/engine_streams.py (paired network check): the Feistel shuffle is a bijection of [0, n) that depends on the
+    key, the dropout mask keeps (256 - round(256 p)) / 256 of the units and differs between layers / steps."""
+    from oracle import engine_streams as es
+
+    for n in (1, 2, 3, 1000, 65_537):
+        p = es.feistel_perm(n, es.perm_key(42, 0))
+        assert np.array_equal(np.sort(p), np.arange(n))
+    a, b = es.feistel_perm(5000, es.perm_key(42, 0)), es.feistel_perm(5000, es.perm_key(42, 1))
+    assert (a != b).mean() > 0.99 and (a != np.arange(5000)).mean() > 0.99
+    rows = np.arange(4096, dtype=np.uint32)
+    k0 = es.keep_mask(es.train_drop_key(42, 1), rows, 0, 0.1)
+    k1 = es.keep_mask(es.train_drop_key(42, 1), rows, 1, 0.1)
+    k2 = es.keep_mask(es.train_drop_key(42, 2), rows, 0, 0.1)
+    assert k0.shape == (4096, 128)
+    assert abs(k0.mean() - 230 / 256) < 2e-3 and es.keep_scale(0.1) == 256 / 230
+    assert 0.1 < (k0 != k1).mean() < 0.25 and 0.1 < (k0 != k2).mean() < 0.25
+    assert es.keep_mask(7, rows, 0, 0.0).all()
