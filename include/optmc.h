@@ -315,6 +315,29 @@ typedef struct optmc_gnet_result {
 
 int optmc_lsm_gnet(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int32_t N, int32_t dtype,
                    const optmc_lsm_params* lp /* basis ignored */, const optmc_gnet_params* gp, optmc_gnet_result* out);
+/* PATH-SHARDED global network LSM ("all-reduce of the 34 177 fp32 gradients per optimiser step"; the loop
+ * being sharded is om3:565-613).  Every rank of an optmc_comm_init group calls this with its own block of paths
+ * (M_local columns of S_dev) and the same parameters:
+ *   - pass 1 runs on the rank's paths; the row counts and the fixed-point feature / target moments are gathered through
+ *     peer memory, so every rank z-scores with the moments of ALL rows;
+ *   - optimiser step b of an epoch covers positions [b batch, (b+1) batch) of the global order; rank r contributes the
+ *     proportional slice of its own (shuffled) rows (optmc_gnet_shard_plan).  Each rank sums its tiles' partial
+ *     gradients in a fixed order and PUSHES the 34 178 words (gradient + batch loss, {tag, fp32} pairs) into every
+ *     peer's memory over NVLink; the optimiser kernel polls its own memory and adds the ranks' vectors in rank order:
+ *     weights, losses, scheduler and early-stopping decisions are bit-identical on every rank, with no host-launched
+ *     collective on the data path;
+ *   - pass 2 runs on the rank's paths; the fixed-point (sum, sum^2) of the values is gathered the same way.
+ * Every rank returns the same price / stderr / best_loss; n_rows = rows of all ranks; n_paths = M_total; ex_count and
+ * boundary cover the rank's own paths.  With a one-rank group the result is bit-identical to optmc_lsm_gnet.  A peer
+ * that never launches makes the others give up after a few seconds with OPTMC_ECUDA. */
+int optmc_lsm_gnet_sharded(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M_local, int64_t M_total, int32_t N,
+                           int32_t dtype, const optmc_lsm_params* lp, const optmc_gnet_params* gp, optmc_gnet_result* out);
+/* Host arithmetic of that split (no device needed): given every rank's row count, [*lo, *hi) = the positions of rank
+ * `rank`'s own shuffled order that belong to optimiser step b (0-based) of an epoch, *global_rows = rows of all ranks in
+ * that step (the gradient's normaliser).  Steps per epoch = ceil(sum(n_rows) / batch); over them every row of every rank
+ * is used exactly once; with nranks == 1 the steps are optmc_lsm_gnet's batches. */
+int optmc_gnet_shard_plan(const int64_t* n_rows, int32_t nranks, int32_t batch, int64_t b, int32_t rank, int64_t* lo,
+                          int64_t* hi, int64_t* global_rows);
 /* Test aid: mean-squared-error loss and its gradient for one batch of n <= 16384 host rows given as NORMALISED
  * features feat[n][7] and targets ys[n], at host params[34177] in the order W1[128][7] b1 W2[128][128] b2
  * W3[128][128] b3 w4[128] b4 (torch state_dict order), without dropout. */

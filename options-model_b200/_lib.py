@@ -138,6 +138,10 @@ PROTOTYPES = {
                                          _P(C.c_double), _P(LsmResult)]),
     "optmc_lsm_gnet": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P(LsmParams),
                                  _P(GnetParams), _P(GnetResult)]),
+    "optmc_lsm_gnet_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                         _P(LsmParams), _P(GnetParams), _P(GnetResult)]),
+    "optmc_gnet_shard_plan": (C.c_int, [_P(C.c_int64), C.c_int32, C.c_int32, C.c_int64, C.c_int32, _P(C.c_int64), _P(C.c_int64),
+                                        _P(C.c_int64)]),
     "optmc_gnet_grad_debug": (C.c_int, [C.c_void_p, C.c_int64, _P(C.c_float), _P(C.c_float), _P(C.c_float), _P(C.c_float),
                                         _P(C.c_float)]),
     "optmc_gnet_streams_debug": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_double, C.c_int64, _P(C.c_int64),

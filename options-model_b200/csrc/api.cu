@@ -357,7 +357,7 @@ int optmc_lsm_poly(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int
 
 // ---- path-sharded sweep over several GPUs: exchange slots in peer-mapped memory ----------------
 static size_t comm_slot_bytes() {  // one slot block [2 parities][ranks][words] per option of a grouped launch
-  return (size_t)optmc::kCommMaxGroups * 2 * optmc::kCommMaxRanks * kXchgWords * sizeof(unsigned long long);
+  return (optmc::kCommSweepWords + optmc::kCommGnetWords) * sizeof(unsigned long long);  // + the network LSM's region
 }
 
 int optmc_comm_export(optmc_ctx* ctx, void* handle_out) {
@@ -371,6 +371,7 @@ int optmc_comm_export(optmc_ctx* ctx, void* handle_out) {
   OPTMC_CUDA(cudaMemset(ctx->comm.local, 0, comm_slot_bytes()));
   OPTMC_CUDA(cudaDeviceSynchronize());
   ctx->comm.g = 2;
+  ctx->comm.gn_step = 1; ctx->comm.gn_meta = 1;
   cudaIpcMemHandle_t h;
   OPTMC_CUDA(cudaIpcGetMemHandle(&h, ctx->comm.local));
   memcpy(handle_out, &h, sizeof(h));
@@ -484,7 +485,24 @@ int optmc_lsm_gnet(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int
                    const optmc_lsm_params* lp, const optmc_gnet_params* gp, optmc_gnet_result* out) {
   OPTMC_TRY_BEGIN
   OPTMC_ENTER(ctx);
-  return lsm_gnet(ctx, S_dev, ld, M, N, dtype, lp, gp, out);
+  return lsm_gnet(ctx, S_dev, ld, M, 0, N, dtype, lp, gp, out);
+  OPTMC_TRY_END
+}
+
+int optmc_lsm_gnet_sharded(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M_local, int64_t M_total, int32_t N,
+                           int32_t dtype, const optmc_lsm_params* lp, const optmc_gnet_params* gp, optmc_gnet_result* out) {
+  OPTMC_TRY_BEGIN
+  OPTMC_ENTER(ctx);
+  if (ctx->comm.nranks < 1) { set_error("optmc_comm_init must be called first"); return OPTMC_EINVAL; }
+  if (M_total < M_local || M_total <= 0) { set_error("M_total must be >= M_local"); return OPTMC_EINVAL; }
+  return lsm_gnet(ctx, S_dev, ld, M_local, M_total, N, dtype, lp, gp, out);
+  OPTMC_TRY_END
+}
+
+int optmc_gnet_shard_plan(const int64_t* n_rows, int32_t nranks, int32_t batch, int64_t b, int32_t rank, int64_t* lo,
+                          int64_t* hi, int64_t* global_rows) {
+  OPTMC_TRY_BEGIN
+  return gnet_shard_plan(n_rows, nranks, batch, b, rank, lo, hi, global_rows);
   OPTMC_TRY_END
 }
 

@@ -430,6 +430,7 @@ struct GradArgs {
   const double* sqrt_tau;
   const GnetNorm* nm;
   long long start, end;                               // rows [start, end) of the (permuted) order form this batch
+  float inv_b2;                                       // 2 / rows of the optimiser step (all ranks' rows when path-sharded)
   Perm perm;
   Drop drop;
   float* gpart;                                       // [tiles][kGP + 1]
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
   const unsigned int cA = 0, cB = 128, cC = 256, cV1 = 384, cV2 = 400, cV3 = 416, cV4 = 432;
   const long long r = a.start + (long long)blockIdx.x * 128 + row;
   const bool act = r < a.end;
-  const float inv_b2 = 2.0f / (float)(a.end - a.start);
+  const float inv_b2 = a.inv_b2;
   unsigned int phase = 0;
   float fn[kGIn], y = 0.f;
 #pragma unroll
@@ -570,31 +571,115 @@ __global__ void __launch_bounds__(kGThreads, 1) gnet_grad_kernel(const GradArgs 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }
 
+// ---- path-sharded training: gradients and small vectors travel through peer-mapped memory (optmc_comm_*) -----------
+// Every 64-bit word is {tag32, payload32} (single-copy atomic, self-validating: no flag, no fence).  A rank PUSHES its
+// words into slot [tag & 1][rank] of every rank's region with st.relaxed.sys; readers poll their OWN memory until the
+// tags match.  A slot is rewritten two exchanges later, which stream order puts behind every reader: rank r pushes
+// exchange s + 2 after its kernel of exchange s + 1 has seen rank q's words of s + 1, which q pushed after its reader of
+// exchange s had finished.
+struct GnetPeers {
+  unsigned long long* base[kCommMaxRanks];  // each rank's region (behind the sweep's exchange slots)
+  int rank, nranks;
+};
+constexpr unsigned int kGnetSpinLimit = 1u << 23;  // ~seconds: a peer that never launched must not hang the GPU
+__device__ __forceinline__ unsigned long long* gpeer_grad(unsigned long long* base, unsigned int par, int src) {
+  return base + ((size_t)par * kCommMaxRanks + src) * kGnetPad;
+}
+__device__ __forceinline__ unsigned long long* gpeer_meta(unsigned long long* base, unsigned int par, int src) {
+  return base + (size_t)2 * kCommMaxRanks * kGnetPad + ((size_t)par * kCommMaxRanks + src) * kGnetMetaWords;
+}
+// polls slot [par][r][i] of this rank's region for every rank r; returns false after a time-out (flags[1] set: every
+// later poll of this and the following kernels gives up at once, the host reports OPTMC_ECUDA)
+__device__ __forceinline__ bool gpeer_poll(const unsigned long long* mine, size_t stride, int nranks, unsigned int tag,
+                                           unsigned int (&pay)[kCommMaxRanks], int* flags) {
+  bool dead = *reinterpret_cast<volatile int*>(flags + 1) != 0;
+  unsigned long long v[kCommMaxRanks];
+  unsigned int n = 0;
+  for (;;) {
+#pragma unroll
+    for (int r = 0; r < kCommMaxRanks; ++r) v[r] = r < nranks ? ld_relaxed_sys_u64(mine + (size_t)r * stride) : (unsigned long long)tag << 32;
+    bool all = true;
+#pragma unroll
+    for (int r = 0; r < kCommMaxRanks; ++r) all &= (unsigned int)(v[r] >> 32) == tag;
+    if (all || dead) break;
+    if (++n >= kGnetSpinLimit) { dead = true; atomicExch(flags + 1, 1); }
+  }
+#pragma unroll
+  for (int r = 0; r < kCommMaxRanks; ++r) pay[r] = (unsigned int)v[r];
+  return !dead;
+}
+
+// fixed-order sum of this rank's per-tile partial gradients (+ the tiles' squared errors), pushed to every rank
+__global__ void __launch_bounds__(256) gnet_reduce_push_kernel(const float* __restrict__ gpart, int ntiles, GnetPeers pe, unsigned int tag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > kGP) return;
+  float g = 0.f;
+  for (int b = 0; b < ntiles; ++b) g += gpart[(size_t)b * (kGP + 1) + i];
+  const unsigned long long w = ((unsigned long long)tag << 32) | __float_as_uint(g);
+  for (int p = 0; p < pe.nranks; ++p) st_relaxed_sys_u64(gpeer_grad(pe.base[p], tag & 1u, pe.rank) + i, w);
+}
+
+// all-gather + integer sum of n64 <= 64 64-bit words (row counts, fixed-point moments, the final value sums):
+// gath[r][j] = rank r's word j, tot[j] = their wrap-around sum.  One CTA.
+__global__ void __launch_bounds__(128) gnet_gather_kernel(const unsigned long long* __restrict__ src, int n64, GnetPeers pe, unsigned int tag,
+                                                          unsigned long long* __restrict__ gath, unsigned long long* __restrict__ tot, int* flags) {
+  __shared__ unsigned int half[kCommMaxRanks][128];
+  const int i = threadIdx.x;
+  if (i < 2 * n64) {
+    const unsigned int mine = (unsigned int)(src[i >> 1] >> ((i & 1) * 32));
+    const unsigned long long w = ((unsigned long long)tag << 32) | mine;
+    for (int p = 0; p < pe.nranks; ++p) st_relaxed_sys_u64(gpeer_meta(pe.base[p], tag & 1u, pe.rank) + i, w);
+    unsigned int pay[kCommMaxRanks];
+    gpeer_poll(gpeer_meta(pe.base[pe.rank], tag & 1u, 0) + i, kGnetMetaWords, pe.nranks, tag, pay, flags);
+#pragma unroll
+    for (int r = 0; r < kCommMaxRanks; ++r) half[r][i] = pay[r];
+  }
+  __syncthreads();
+  if (i < n64) {
+    unsigned long long t = 0ull;
+    for (int r = 0; r < pe.nranks; ++r) {
+      const unsigned long long v = (unsigned long long)half[r][2 * i] | ((unsigned long long)half[r][2 * i + 1] << 32);
+      gath[(size_t)r * n64 + i] = v;
+      t += v;
+    }
+    tot[i] = t;
+  }
+}
+
 // Adam (torch.optim.Adam with L2 weight decay, om3:579) or AdamW (decoupled, om3gpu:753): fixed-order sum of the
-// per-tile partial gradients; block 0 also adds the batch's mean squared error to the epoch accumulator.
+// per-tile partial gradients (PEER: of the ranks' pushed vectors, in rank order -- identical on every rank); block 0 also
+// adds the batch's mean squared error to the epoch accumulator.
+template <bool PEER>
 __global__ void __launch_bounds__(256) gnet_adam_kernel(float* params, __nv_bfloat16* wpack, float* adam_m, float* adam_v, const float* __restrict__ gpart,
                                                         int ntiles, float lr, float wd, int decoupled, int step, float inv_batch,
-                                                        double* epoch_loss) {
+                                                        double* epoch_loss, GnetPeers pe, unsigned int tag, int* flags) {
   const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
   const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < kGP) {
+  if (i <= kGP) {
     float g = 0.f;
-    for (int b = 0; b < ntiles; ++b) g += gpart[(size_t)b * (kGP + 1) + i];
-    float p = params[i];
-    if (decoupled) p -= lr * wd * p; else g = fmaf(wd, p, g);
-    const float m = b1 * adam_m[i] + (1.0f - b1) * g;
-    const float v = b2 * adam_v[i] + (1.0f - b2) * g * g;
-    adam_m[i] = m; adam_v[i] = v;
-    p -= (lr / bc1) * (m / (sqrtf(v) / sqrtf(bc2) + eps));
-    params[i] = p;
-    const int k = gnet_pack_index(i);
-    if (k >= 0) wpack[k] = __float2bfloat16_rn(p);
-  }
-  if (i == 0 && epoch_loss) {
-    float l = 0.f;
-    for (int b = 0; b < ntiles; ++b) l += gpart[(size_t)b * (kGP + 1) + kGP];
-    *epoch_loss += (double)(l * inv_batch);
+    if (PEER) {
+      unsigned int pay[kCommMaxRanks];
+      gpeer_poll(gpeer_grad(pe.base[pe.rank], tag & 1u, 0) + i, kGnetPad, pe.nranks, tag, pay, flags);
+      g = __uint_as_float(pay[0]);
+#pragma unroll
+      for (int r = 1; r < kCommMaxRanks; ++r) if (r < pe.nranks) g += __uint_as_float(pay[r]);
+    } else if (i < kGP || epoch_loss) {
+      for (int b = 0; b < ntiles; ++b) g += gpart[(size_t)b * (kGP + 1) + i];
+    }
+    if (i < kGP) {
+      float p = params[i];
+      if (decoupled) p -= lr * wd * p; else g = fmaf(wd, p, g);
+      const float m = b1 * adam_m[i] + (1.0f - b1) * g;
+      const float v = b2 * adam_v[i] + (1.0f - b2) * g * g;
+      adam_m[i] = m; adam_v[i] = v;
+      p -= (lr / bc1) * (m / (sqrtf(v) / sqrtf(bc2) + eps));
+      params[i] = p;
+      const int k = gnet_pack_index(i);
+      if (k >= 0) wpack[k] = __float2bfloat16_rn(p);
+    } else if (epoch_loss) {
+      *epoch_loss += (double)(g * inv_batch);  // element kGP: the step's sum of squared errors
+    }
   }
 }
 
@@ -724,9 +809,37 @@ static Perm make_perm(unsigned long long n, unsigned int key) {
 
 static size_t gnet_smem_bytes() { return sizeof(GnetSmem) + 1024; }
 
+// Step b of an epoch covers positions [b batch, (b+1) batch) of the global order of all ranks' rows; a rank's share is the
+// proportional slice of its own order (floor arithmetic: the slices of consecutive steps tile [0, n_rank) exactly).
+static long long shard_pos(long long pos, long long n_rank, long long n_total) {
+  return n_total > 0 ? (long long)(((unsigned __int128)pos * (unsigned __int128)n_rank) / (unsigned __int128)n_total) : 0;
+}
+int gnet_shard_plan(const int64_t* n_rows, int32_t nranks, int32_t batch, int64_t b, int32_t rank, int64_t* lo, int64_t* hi,
+                    int64_t* global_rows) {
+  if (!n_rows || nranks < 1 || nranks > kCommMaxRanks || batch < 1 || b < 0 || rank < 0 || rank >= nranks) { set_error("bad argument"); return OPTMC_EINVAL; }
+  long long n_total = 0;
+  for (int r = 0; r < nranks; ++r) { if (n_rows[r] < 0) { set_error("bad argument"); return OPTMC_EINVAL; } n_total += n_rows[r]; }
+  const long long p0 = b * (long long)batch < n_total ? b * (long long)batch : n_total;
+  const long long p1 = p0 + batch < n_total ? p0 + batch : n_total;
+  long long g = 0;
+  for (int r = 0; r < nranks; ++r) {
+    const long long l = shard_pos(p0, n_rows[r], n_total), h = shard_pos(p1, n_rows[r], n_total);
+    g += h - l;
+    if (r == rank) { if (lo) *lo = l; if (hi) *hi = h; }
+  }
+  if (global_rows) *global_rows = g;
+  return OPTMC_OK;
+}
+
 template <typename R>
-static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, const optmc_lsm_params* lp,
+static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int64_t M_total, int32_t N, const optmc_lsm_params* lp,
                       const optmc_gnet_params* gp, optmc_gnet_result* out) {
+  const bool sharded = M_total > 0;
+  GnetPeers pe{};
+  if (sharded) {
+    pe.rank = ctx->comm.rank; pe.nranks = ctx->comm.nranks;
+    for (int r = 0; r < pe.nranks; ++r) pe.base[r] = ctx->comm.peers[r] + kCommSweepWords;
+  }
   const bool sticky = (lp->semantics & OPTMC_SEM_STICKY_MASK) != 0;
   const bool refdisc = (lp->semantics & OPTMC_SEM_REF_DISCOUNT) != 0;
   const double dt = lp->T / N, disc = exp(-lp->r * dt);
@@ -755,8 +868,11 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   // device workspace (everything but the row table)
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-  const size_t o_tab = take(tab.size() * 8), o_counts = take((size_t)(ncounts > 0 ? ncounts : 1) * 8), o_sums = take(2 * kGQ * 8 + 4 * 8),
-               o_nrows = take(8), o_norm = take(sizeof(GnetNorm)), o_params = take((size_t)kGP * 4), o_best = take((size_t)kGP * 4),
+  // meta block: [0] row count, [1, 33) fixed-point moments, [33, 37) fixed-point value sums -- contiguous, so that a
+  // path-sharded run gathers them as one vector; tot / gath: the ranks' sums and the ranks' own words
+  constexpr int kMetaN = 1 + 2 * kGQ + 4;
+  const size_t o_tab = take(tab.size() * 8), o_counts = take((size_t)(ncounts > 0 ? ncounts : 1) * 8), o_meta = take(kMetaN * 8),
+               o_tot = take(kMetaN * 8), o_gath = take((size_t)kCommMaxRanks * kMetaN * 8), o_norm = take(sizeof(GnetNorm)), o_params = take((size_t)kGP * 4), o_best = take((size_t)kGP * 4),
                o_m = take((size_t)kGP * 4), o_v = take((size_t)kGP * 4), o_gpart = take((size_t)max_tiles * (kGP + 1) * 4),
                o_loss = take(8), o_pack = take(2 * kTcTileBytes);
   rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
@@ -764,9 +880,12 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   char* dev = static_cast<char*>(ctx->batch_dev);
   double* d_tab = reinterpret_cast<double*>(dev + o_tab);
   unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(dev + o_counts);
-  unsigned long long* d_sums = reinterpret_cast<unsigned long long*>(dev + o_sums);
+  unsigned long long* d_meta = reinterpret_cast<unsigned long long*>(dev + o_meta);
+  unsigned long long* d_tot = reinterpret_cast<unsigned long long*>(dev + o_tot);
+  unsigned long long* d_gath = reinterpret_cast<unsigned long long*>(dev + o_gath);
+  long long* d_nrows = reinterpret_cast<long long*>(d_meta);
+  unsigned long long* d_sums = d_meta + 1;
   unsigned long long* d_fin = d_sums + 2 * kGQ;
-  long long* d_nrows = reinterpret_cast<long long*>(dev + o_nrows);
   GnetNorm* d_norm = reinterpret_cast<GnetNorm*>(dev + o_norm);
   float* d_params = reinterpret_cast<float*>(dev + o_params);
   float* d_best = reinterpret_cast<float*>(dev + o_best);
@@ -776,8 +895,7 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   double* d_loss = reinterpret_cast<double*>(dev + o_loss);
   __nv_bfloat16* d_pack = reinterpret_cast<__nv_bfloat16*>(dev + o_pack);
   OPTMC_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  OPTMC_CUDA(cudaMemsetAsync(d_sums, 0, 2 * kGQ * 8 + 4 * 8, ctx->stream));
-  OPTMC_CUDA(cudaMemsetAsync(d_nrows, 0, 8, ctx->stream));
+  OPTMC_CUDA(cudaMemsetAsync(d_meta, 0, kMetaN * 8, ctx->stream));
   const R* Sr = static_cast<const R*>(S);
   OPTMC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
 
@@ -792,9 +910,8 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   }
   out->n_rows = n_rows; out->epochs_run = 0; out->best_loss = nan(""); out->final_lr = gp->lr;
   const double final_scale = refdisc ? 1.0 : disc;
-  if (n_rows == 0) {  // om3:517-518: no regression rows -> mean of the discounted terminal payoffs
-    // fall through to pass 2 with a network that is never consulted
-  }
+  // n_rows == 0 (om3:517-518: no regression rows -> mean of the discounted terminal payoffs): pass 2 runs with a
+  // network that is never consulted
   float *d_xs = nullptr, *d_ys = nullptr;
   int* d_ts = nullptr;
   if (n_rows > 0) {
@@ -805,8 +922,32 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
     d_xs = reinterpret_cast<float*>(rows); d_ts = reinterpret_cast<int*>(rows + seg); d_ys = reinterpret_cast<float*>(rows + 2 * seg);
     gnet_compact_kernel<R><<<dim3(nchunks, N - 1), 256, 0, ctx->stream>>>(Sr, ld, M, N, lp->K, lp->is_put, d_counts, nchunks, d_tab,
                                                                          d_tab + (N + 1), d_xs, d_ts, d_ys, d_sums, ctx->d_flags);
-    gnet_norm_kernel<<<1, 32, 0, ctx->stream>>>(d_sums, d_nrows, gp->target_ddof ? 1 : 0, d_norm);
-    n_launches += 2; ctx->launches += 2;
+    ++n_launches; ctx->launches++;
+    OPTMC_CUDA(cudaGetLastError());
+  }
+  // rows of every rank (sharded: gathered with the moments through peer memory; every rank launches this, rows or not)
+  long long n_rank[kCommMaxRanks] = {n_rows};
+  long long n_total = n_rows;
+  const unsigned long long* d_sums_all = d_sums;
+  const long long* d_nrows_all = d_nrows;
+  if (sharded) {
+    gnet_gather_kernel<<<1, 128, 0, ctx->stream>>>(d_meta, 1 + 2 * kGQ, pe, ctx->comm.gn_meta++, d_gath, d_tot, ctx->d_flags);
+    ++n_launches; ctx->launches++;
+    OPTMC_CUDA(cudaGetLastError());
+    unsigned long long hg[kCommMaxRanks * (1 + 2 * kGQ)];
+    int hf[4];
+    OPTMC_CUDA(cudaMemcpyAsync(hg, d_gath, sizeof(hg), cudaMemcpyDeviceToHost, ctx->stream));
+    OPTMC_CUDA(cudaMemcpyAsync(hf, ctx->d_flags, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream));
+    OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (hf[1]) { set_error("sharded network LSM: a peer rank did not answer (exchange timed out); re-run optmc_comm_export / optmc_comm_init on every rank"); return OPTMC_ECUDA; }
+    n_total = 0;
+    for (int r = 0; r < pe.nranks; ++r) { n_rank[r] = (long long)hg[(size_t)r * (1 + 2 * kGQ)]; n_total += n_rank[r]; }
+    d_sums_all = d_tot + 1; d_nrows_all = reinterpret_cast<const long long*>(d_tot);
+    out->n_rows = n_total;
+  }
+  if (n_total > 0) {
+    gnet_norm_kernel<<<1, 32, 0, ctx->stream>>>(d_sums_all, d_nrows_all, gp->target_ddof ? 1 : 0, d_norm);
+    ++n_launches; ctx->launches++;
     OPTMC_CUDA(cudaGetLastError());
   } else {
     GnetNorm z{};
@@ -828,29 +969,51 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   int step = 0, since_best = 0, sched_bad = 0, epochs_run = 0;
   double sched_best = INFINITY;
   bool have_best = false;
-  if (n_rows > 0) {
-    const long long nb = (n_rows + batch - 1) / batch;
+  if (n_total > 0) {
+    const long long nb = (n_total + batch - 1) / batch;
+    const unsigned int rank_key = sharded ? (unsigned int)pe.rank * 0x3c6ef372u : 0u;  // the ranks shuffle / mask independently
     for (int ep = 0; ep < gp->epochs; ++ep) {
       OPTMC_CUDA(cudaMemsetAsync(d_loss, 0, 8, ctx->stream));
       GradArgs ga{};
       ga.params = d_params; ga.wpack = d_pack; ga.xs = d_xs; ga.ts = d_ts; ga.ys = d_ys; ga.feat = nullptr; ga.sqrt_tau = d_tab + (N + 1); ga.nm = d_norm;
-      ga.perm = make_perm((unsigned long long)n_rows, (unsigned int)(gp->seed * 0x9e3779b97f4a7c15ull >> 32) + 0x632be5abu * (unsigned int)(ep + 1));
+      ga.perm = make_perm((unsigned long long)n_rows, (unsigned int)(gp->seed * 0x9e3779b97f4a7c15ull >> 32) + 0x632be5abu * (unsigned int)(ep + 1) + rank_key);
       ga.gpart = d_gpart;
       for (long long b = 0; b < nb; ++b) {
-        ga.start = b * batch;
-        ga.end = ga.start + batch < n_rows ? ga.start + batch : n_rows;
+        long long step_rows;  // rows of all ranks in this step: the gradient's normaliser
+        if (sharded) {
+          const long long p0 = b * batch, p1 = p0 + batch < n_total ? p0 + batch : n_total;
+          ga.start = shard_pos(p0, n_rows, n_total); ga.end = shard_pos(p1, n_rows, n_total);
+          step_rows = 0;
+          for (int r = 0; r < pe.nranks; ++r) step_rows += shard_pos(p1, n_rank[r], n_total) - shard_pos(p0, n_rank[r], n_total);
+        } else {
+          ga.start = b * batch;
+          ga.end = ga.start + batch < n_rows ? ga.start + batch : n_rows;
+          step_rows = ga.end - ga.start;
+        }
+        ga.inv_b2 = 2.0f / (float)step_rows;
         ++step;
-        ga.drop = make_drop(gp->dropout, (unsigned int)gp->seed * 0x2545f491u + (unsigned int)step * 0x9e3779b1u);
+        ga.drop = make_drop(gp->dropout, (unsigned int)gp->seed * 0x2545f491u + (unsigned int)step * 0x9e3779b1u + rank_key);
         const int tiles = (int)((ga.end - ga.start + 127) / 128);
-        gnet_grad_kernel<<<tiles, kGThreads, gnet_smem_bytes(), ctx->stream>>>(ga);
-        gnet_adam_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(d_params, d_pack, d_m, d_v, d_gpart, tiles, (float)lr, (float)gp->weight_decay,
-                                                                     gp->decoupled_wd, step, 1.0f / (float)(ga.end - ga.start), d_loss);
-        n_launches += 2; ctx->launches += 2;
+        if (tiles > 0) { gnet_grad_kernel<<<tiles, kGThreads, gnet_smem_bytes(), ctx->stream>>>(ga); ++n_launches; ctx->launches++; }
+        if (sharded) {
+          const unsigned int tag = ctx->comm.gn_step++;
+          gnet_reduce_push_kernel<<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(d_gpart, tiles, pe, tag);
+          gnet_adam_kernel<true><<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(d_params, d_pack, d_m, d_v, d_gpart, 0, (float)lr, (float)gp->weight_decay,
+                                                                             gp->decoupled_wd, step, 1.0f / (float)step_rows, d_loss, pe, tag, ctx->d_flags);
+          n_launches += 2; ctx->launches += 2;
+        } else {
+          gnet_adam_kernel<false><<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(d_params, d_pack, d_m, d_v, d_gpart, tiles, (float)lr, (float)gp->weight_decay,
+                                                                              gp->decoupled_wd, step, 1.0f / (float)step_rows, d_loss, pe, 0u, ctx->d_flags);
+          ++n_launches; ctx->launches++;
+        }
       }
       OPTMC_CUDA(cudaGetLastError());
       double sum_loss = 0.0;
+      int hf[4] = {0, 0, 0, 0};
       OPTMC_CUDA(cudaMemcpyAsync(&sum_loss, d_loss, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      if (sharded) OPTMC_CUDA(cudaMemcpyAsync(hf, ctx->d_flags, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream));
       OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (hf[1]) { set_error("sharded network LSM: a peer rank did not answer (gradient exchange timed out); re-run optmc_comm_export / optmc_comm_init on every rank"); return OPTMC_ECUDA; }
       const double avg = sum_loss / (double)nb;
       ++epochs_run;
       if (!(avg == avg)) { set_error("network LSM: the training loss is not finite"); return OPTMC_ECUDA; }
@@ -884,13 +1047,17 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   wa.K = lp->K; wa.invK = 1.0 / lp->K; wa.params = d_params; wa.wpack = d_pack; wa.nm = d_norm;
   wa.sqrt_tau = d_tab + (N + 1); wa.Dm = d_tab + 2 * (N + 1);
   const int inf_drop = gp->inference_dropout < 0 ? (refdisc && sticky ? 1 : 0) : gp->inference_dropout;
-  wa.drop = make_drop(inf_drop ? gp->dropout : 0.0, (unsigned int)gp->seed * 0x2545f491u + 0x51ed270bu);
+  wa.drop = make_drop(inf_drop ? gp->dropout : 0.0, (unsigned int)gp->seed * 0x2545f491u + 0x51ed270bu + (sharded ? (unsigned int)pe.rank * 0x3c6ef372u : 0u));
   wa.fin = d_fin; wa.flags = ctx->d_flags;
   const bool stats = out->ex_count != nullptr || out->boundary != nullptr;
   wa.exc = stats ? ctx->d_exc : nullptr; wa.bnd = stats ? ctx->d_bnd : nullptr;
   const unsigned wg = (unsigned)((M + 127) / 128);
   gnet_walk_kernel<R><<<wg, kGThreads, gnet_smem_bytes(), ctx->stream>>>(wa);
-  gnet_final_kernel<<<1, 1, 0, ctx->stream>>>(d_fin, M, final_scale, ctx->d_final);
+  if (sharded) {  // the ranks' fixed-point value sums: integer addition, the same price on every rank
+    gnet_gather_kernel<<<1, 128, 0, ctx->stream>>>(d_fin, 4, pe, ctx->comm.gn_meta++, d_gath, d_tot, ctx->d_flags);
+    ++n_launches; ctx->launches++;
+  }
+  gnet_final_kernel<<<1, 1, 0, ctx->stream>>>(sharded ? d_tot : d_fin, sharded ? M_total : M, final_scale, ctx->d_final);
   n_launches += 2; ctx->launches += 2;
   OPTMC_CUDA(cudaGetLastError());
   OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -904,12 +1071,13 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   if (out->boundary) { hb.resize(N + 1); OPTMC_CUDA(cudaMemcpyAsync(hb.data(), ctx->d_bnd, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
   if (out->ex_count) { he.resize(N + 1); OPTMC_CUDA(cudaMemcpyAsync(he.data(), ctx->d_exc, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
   OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (sharded && flags[1]) { set_error("sharded network LSM: a peer rank did not answer (exchange timed out); re-run optmc_comm_export / optmc_comm_init on every rank"); return OPTMC_ECUDA; }
   if (flags[0]) { set_error("network LSM: a sum left the fixed-point range or is not finite"); return OPTMC_EUNSUPPORTED; }
   float t01 = 0.f, t12 = 0.f;
   cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
   cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
   ctx->last_paths_ms = t01; ctx->last_sweep_ms = t12;  // here: fit (pass 1 + training) and pass 2
-  out->price = fin[0]; out->stderr_ = fin[1]; out->n_paths = M; out->n_launches = n_launches;
+  out->price = fin[0]; out->stderr_ = fin[1]; out->n_paths = sharded ? M_total : M; out->n_launches = n_launches;
   if (out->boundary) {
     const unsigned long long none = lp->is_put ? 0ull : ~0ull;
     for (int t = 0; t <= N; ++t) {
@@ -921,7 +1089,7 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int3
   return OPTMC_OK;
 }
 
-int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
+int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int64_t M_total, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
              const optmc_gnet_params* gp, optmc_gnet_result* out) {
   if (!S || !lp || !gp || !out) { set_error("null argument"); return OPTMC_EINVAL; }
   if (!(lp->K > 0) || !(lp->T > 0)) { set_error("S0, K, T must be positive."); return OPTMC_EINVAL; }
@@ -934,7 +1102,8 @@ int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, in
     set_error("network LSM: bad training parameters"); return OPTMC_EINVAL;
   }
   if (ctx->cc < 100) { set_error("network LSM needs tcgen05 (sm_100)"); return OPTMC_EUNSUPPORTED; }
-  return dtype == OPTMC_F64 ? lsm_gnet_t<double>(ctx, S, ld, M, N, lp, gp, out) : lsm_gnet_t<float>(ctx, S, ld, M, N, lp, gp, out);
+  return dtype == OPTMC_F64 ? lsm_gnet_t<double>(ctx, S, ld, M, M_total, N, lp, gp, out)
+                            : lsm_gnet_t<float>(ctx, S, ld, M, M_total, N, lp, gp, out);
 }
 
 // Test aid: loss and parameter gradients of one batch of n <= 16384 rows given as normalised features [n][7] and
@@ -958,7 +1127,7 @@ int gnet_grad_debug(optmc_ctx* ctx, long long n, const float* feat, const float*
   ga.params = reinterpret_cast<float*>(dev + o_par); ga.feat = reinterpret_cast<float*>(dev + o_feat);
   ga.wpack = reinterpret_cast<__nv_bfloat16*>(dev + o_pack);
   gnet_pack_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(ga.params, reinterpret_cast<__nv_bfloat16*>(dev + o_pack));
-  ga.ys = reinterpret_cast<float*>(dev + o_ys); ga.start = 0; ga.end = n; ga.perm = make_perm(1, 0); ga.drop = make_drop(0.0, 0);
+  ga.ys = reinterpret_cast<float*>(dev + o_ys); ga.start = 0; ga.end = n; ga.inv_b2 = 2.0f / (float)n; ga.perm = make_perm(1, 0); ga.drop = make_drop(0.0, 0);
   ga.gpart = reinterpret_cast<float*>(dev + o_gpart);
   gnet_grad_kernel<<<tiles, kGThreads, gnet_smem_bytes(), ctx->stream>>>(ga);
   gnet_sum_partials_kernel<<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(ga.gpart, tiles, reinterpret_cast<float*>(dev + o_out), 1.0f / (float)n);

@@ -22,6 +22,12 @@ constexpr int kXchgWords = 2 * kXchgMaxQ;
 constexpr int kCommMaxRanks = 8;   // ranks of a path-sharded sweep (optmc_comm_*)
 constexpr int kCommMaxGroups = 16; // options of one path-sharded grouped launch (one slot block each)
 constexpr int kXchgStride = 1;
+// Peer-mapped region of the path-sharded network LSM (lsm_gnet.cu), behind the sweep's exchange slots in the same
+// allocation: grad[2 parities][ranks][kGnetPad] and meta[2][ranks][kGnetMetaWords] 64-bit words {tag32, payload32}.
+constexpr int kGnetPad = 34304;        // 34177 parameters + the batch loss, rounded up to 128 words
+constexpr int kGnetMetaWords = 256;
+constexpr size_t kCommSweepWords = (size_t)kCommMaxGroups * 2 * kCommMaxRanks * kXchgWords;
+constexpr size_t kCommGnetWords = (size_t)2 * kCommMaxRanks * (kGnetPad + kGnetMetaWords);
 inline size_t xchg_bytes() { return (size_t)2 * kXchgWords * kXchgStride * sizeof(unsigned long long); }
 constexpr int kMaxBeta = 4;
 
@@ -112,6 +118,7 @@ struct optmc_ctx {
   struct Comm {
     int nranks = 0, rank = 0;
     unsigned int g = 2;                      // running exchange counter (tags 2, 3 differ from the zeroed slots)
+    unsigned int gn_step = 1, gn_meta = 1;   // network LSM: running tags of the gradient / small-vector exchanges (0 = empty)
     unsigned long long* local = nullptr;     // this rank's slot array
     unsigned long long* peers[optmc::kCommMaxRanks] = {};       // peers[rank] == local; the others are cudaIpcOpenMemHandle mappings
     bool opened[optmc::kCommMaxRanks] = {};
@@ -175,8 +182,10 @@ int lsm_mlp(optmc_ctx* ctx, const optmc_mlp_params* np, optmc_lsm_result* out);
 int lsm_apply_policy(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
                      const double* betas, optmc_lsm_result* out);
 // lsm_gnet.cu
-int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
-             const optmc_gnet_params* gp, optmc_gnet_result* out);
+int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int64_t M_total /* > 0: path-sharded */, int32_t N, int32_t dtype,
+             const optmc_lsm_params* lp, const optmc_gnet_params* gp, optmc_gnet_result* out);
+int gnet_shard_plan(const int64_t* n_rows, int32_t nranks, int32_t batch, int64_t b, int32_t rank, int64_t* lo, int64_t* hi,
+                    int64_t* global_rows);
 int gnet_grad_debug(optmc_ctx* ctx, long long n, const float* feat, const float* ys, const float* params, float* grads, float* loss);
 int gnet_streams_debug(optmc_ctx* ctx, unsigned long long seed, int epoch, int step, double dropout, long long n_rows,
                        long long* perm_out, const unsigned int* row_ids, long long n_ids, unsigned int* keep_out);

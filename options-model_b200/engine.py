@@ -386,11 +386,14 @@ class Engine:
 
     def lsm_gnet(self, S, K, r, T, option_type="put", semantics="reference", variant="cpu", epochs=25, batch=None, lr=1e-3,
                  weight_decay=None, dropout=0.1, seed=42, inference_dropout=-1, arrays=True, M: Optional[int] = None,
-                 init_params=None, return_params=False, **over):
+                 init_params=None, return_params=False, M_total: Optional[int] = None, **over):
         """The reference's v3 algorithm with its own regressor (om3:482-651): one SingleLSMNet(7,128,3) trained on the
         rows of all dates (tcgen05), then the decision pass.  ``variant`` picks the defaults of the CPU file
         (om3:565-613: batch 256, Adam + L2 1e-5, ReduceLROnPlateau, patience 8, population std) or of the torch-GPU
-        file (om3gpu:740-798: batch 8192, AdamW 1e-4, no scheduler, patience 3, sample std).  Returns a dict."""
+        file (om3gpu:740-798: batch 8192, AdamW 1e-4, no scheduler, patience 3, sample std).  Returns a dict.
+        ``M_total``: this rank's part of a PATH-SHARDED fit (optmc_lsm_gnet_sharded; every rank of the comm_init group
+        calls with its block of paths): price / stderr / best_loss / params are the global ones, identical on every
+        rank; ex_count / boundary cover this rank's paths (sharded.gnet_sharded combines them)."""
         assert S.is_cuda and S.dim() == 2 and S.stride(1) == 1
         N = S.shape[0] - 1
         M = int(M if M is not None else S.shape[1])
@@ -420,10 +423,19 @@ class Engine:
             res.boundary = bnd.ctypes.data_as(C.POINTER(C.c_double))
             res.ex_count = exc.ctypes.data_as(C.POINTER(C.c_int64))
         self._sync_stream()
-        L.check(self.lib.optmc_lsm_gnet(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), C.byref(gp), C.byref(res)))
+        if M_total is not None:
+            L.check(self.lib.optmc_lsm_gnet_sharded(self._h, S.data_ptr(), S.stride(0), M, int(M_total), N, code, C.byref(lp),
+                                                    C.byref(gp), C.byref(res)))
+        else:
+            L.check(self.lib.optmc_lsm_gnet(self._h, S.data_ptr(), S.stride(0), M, N, code, C.byref(lp), C.byref(gp), C.byref(res)))
         return dict(price=res.price, stderr=res.stderr_, n_paths=int(res.n_paths), n_rows=int(res.n_rows),
                     epochs_run=int(res.epochs_run), n_launches=int(res.n_launches), best_loss=res.best_loss,
                     final_lr=res.final_lr, boundary=bnd, ex_count=exc, params=p_out)
+
+    def gnet_shard_plan(self, n_rows, batch: int, b: int, rank: int):
+        """(lo, hi, global_rows): rank's slice of its own shuffled rows in optimiser step b of a path-sharded fit, and
+        the rows of all ranks in that step.  Host arithmetic only (optmc_gnet_shard_plan)."""
+        return gnet_shard_plan(self.lib, n_rows, batch, b, rank)
 
     def gnet_grad_debug(self, feat: np.ndarray, ys: np.ndarray, params: np.ndarray):
         """MSE loss and gradient of SingleLSMNet(7,128,3) on host rows (normalised features [n,7]) -- test aid."""
@@ -670,3 +682,11 @@ def default_engine(device: int = 0) -> Engine:
     if device not in _DEFAULT:
         _DEFAULT[device] = Engine(device)
     return _DEFAULT[device]
+
+
+def gnet_shard_plan(lib, n_rows, batch: int, b: int, rank: int):
+    """optmc_gnet_shard_plan without a context (no device needed)."""
+    arr = (C.c_int64 * len(n_rows))(*[int(x) for x in n_rows])
+    lo, hi, g = C.c_int64(), C.c_int64(), C.c_int64()
+    L.check(lib.optmc_gnet_shard_plan(arr, len(n_rows), int(batch), int(b), int(rank), C.byref(lo), C.byref(hi), C.byref(g)))
+    return int(lo.value), int(hi.value), int(g.value)

@@ -144,3 +144,43 @@ def sweep_sharded_fused(engine, dist, S_local, M_total, K, r, T, option_type="pu
         b[~np.isfinite(b)] = np.nan
         res.boundary = b
     return res
+
+
+def gnet_sharded(engine, dist, S_local, M_total, K, r, T, option_type="put", semantics="reference", group=None, arrays=False,
+                 **kw):
+    """The reference's global network regression (om3:482-651, ``SingleLSMNet``) with the PATHS sharded over the ranks:
+    every rank collects the rows of its own paths, the per-step gradient vectors (34 177 fp32 + the batch loss) travel
+    between the GPUs through peer-mapped memory inside the reduce / optimiser kernels (optmc_lsm_gnet_sharded; no
+    host-launched collective on the data path), every rank ends with the same weights, loss and price.  Requires
+    ``init_peer_exchange`` once per process group.  Same collective error handling as ``sweep_sharded_fused``: all ranks
+    raise or none does, and the exchange is re-wired after a failure."""
+    world = dist.get_world_size(group)
+    err = None
+    res = None
+    try:
+        res = engine.lsm_gnet(S_local, K, r, T, option_type, semantics, arrays=arrays, M_total=int(M_total), **kw)
+    except Exception as e:  # noqa: BLE001 -- reported collectively below
+        err = e
+    if world > 1:
+        post = [None] * world
+        dist.all_gather_object(post, None if err is None else str(err), group=group)
+        if any(p is not None for p in post):
+            init_peer_exchange(engine, dist, group)
+            raise RuntimeError(f"sharded network LSM failed on ranks {[i for i, p in enumerate(post) if p is not None]}: "
+                               f"{[p for p in post if p is not None][0]}")
+    elif err is not None:
+        raise err
+    if arrays and world > 1:
+        import torch
+
+        dev = S_local.device
+        exc = torch.as_tensor(res["ex_count"], device=dev)
+        dist.all_reduce(exc, op=dist.ReduceOp.SUM, group=group)
+        res["ex_count"] = exc.cpu().numpy()
+        put = option_type == "put"
+        bnd = torch.as_tensor(np.nan_to_num(res["boundary"], nan=-np.inf if put else np.inf), device=dev)
+        dist.all_reduce(bnd, op=dist.ReduceOp.MAX if put else dist.ReduceOp.MIN, group=group)
+        b = bnd.cpu().numpy()
+        b[~np.isfinite(b)] = np.nan
+        res["boundary"] = b
+    return res

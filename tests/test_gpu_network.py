@@ -295,3 +295,37 @@ def test_gnet_warm_start_roundtrip(eng, mods):
     assert b["price"] == a["price"] and b["epochs_run"] == 0
     c = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "textbook", variant="gpu", epochs=2, seed=5, init_params=a["params"], stop_patience=0)
     assert c["best_loss"] < a["best_loss"] + 5e-3
+
+
+def test_gnet_sharded_single_rank_group_is_bit_identical(eng, mods):
+    """optmc_lsm_gnet_sharded on a one-rank group (comm_export / comm_init with itself): the peer-memory path runs --
+    row counts and moments gathered through tagged words, per-step gradients pushed as {tag, fp32} words and summed by
+    the optimiser kernel from the slots, the final value sums gathered -- and must reproduce optmc_lsm_gnet bit for bit
+    (same batches by construction of optmc_gnet_shard_plan, rank 0 keys unchanged).  Two real GPUs: tests/test_multi_gpu.py."""
+    L, E, orc = mods
+    e = E.Engine(0)
+    try:
+        e.comm_init(0, 1, [e.comm_export()])
+        for mdl, M, N, batch in ((E.gbm(100.0, 0.05, 1.0, 0.2), 20_000, 20, 256), (E.heston(100.0, 0.05, 1.0, **HP), 60_000, 30, 8192)):
+            S = eng.paths(mdl, M, N, "f32", E.RngSpec(seed=21))
+            kw = dict(variant="cpu" if batch == 256 else "gpu", epochs=3, batch=batch, seed=9, return_params=True)
+            plain = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "reference", **kw)
+            for _ in range(2):  # twice: the exchange tags keep running across calls
+                S2 = e.paths(mdl, M, N, "f32", E.RngSpec(seed=21))
+                sh = e.lsm_gnet(S2, 100.0, 0.05, 1.0, "put", "reference", M_total=M, **kw)
+                assert sh["price"] == plain["price"] and sh["stderr"] == plain["stderr"]
+                assert sh["best_loss"] == plain["best_loss"] and sh["n_rows"] == plain["n_rows"] and sh["epochs_run"] == plain["epochs_run"]
+                np.testing.assert_array_equal(sh["params"], plain["params"])
+                np.testing.assert_array_equal(sh["ex_count"], plain["ex_count"])
+        # a slab without in-the-money rows: nothing to fit, the gathers still run
+        S = eng.paths(E.gbm(100.0, 0.05, 0.01, 0.01), 4096, 4, "f32", E.RngSpec(seed=3))
+        a = eng.lsm_gnet(S, 50.0, 0.05, 0.01, "put", "reference", epochs=2)
+        b = e.lsm_gnet(e.paths(E.gbm(100.0, 0.05, 0.01, 0.01), 4096, 4, "f32", E.RngSpec(seed=3)), 50.0, 0.05, 0.01, "put", "reference",
+                       epochs=2, M_total=4096)
+        assert a["n_rows"] == b["n_rows"] == 0 and a["price"] == b["price"] == 0.0
+        e.comm_finalize()
+    finally:
+        e.close()
+    with pytest.raises(Exception):  # no group wired
+        eng.lsm_gnet(eng.paths(E.gbm(100.0, 0.05, 1.0, 0.2), 4096, 4, "f32", E.RngSpec(seed=3)), 100.0, 0.05, 1.0, "put", "reference",
+                     epochs=1, M_total=4096)
