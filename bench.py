@@ -378,6 +378,40 @@ def run_own_arm(args):
                 "ms": dt5 * 1e3, "path_steps_per_s": 1e9 / dt5, "objective": float(f5),
                 "call": "compat.HestonObjective (heston_calibration.py:404-472), rows rank::world, one fused launch per rank + "
                         "one all_gather of the prices"}
+            # ---- the reference's global network regression (om3:565-613) with the PATHS sharded over the ranks: BASELINE
+            # config 1's shape per rank (100 k GBM paths x 50 dates, batch 8192 per rank), gradients exchanged through peer
+            # memory inside the reduce / optimiser kernels (optmc_lsm_gnet_sharded); weak scaling of the epoch time ----
+            if shard in ("none", "paths"):
+                try:
+                    Mg, Ng = 100_000, 50
+                    Sgn = eng.paths(E.gbm(S0, R, T, 0.2), Mg, Ng, "f32", E.RngSpec(seed=7, pair_offset=rank * (Mg // 2)))
+                    kwg = dict(variant="gpu", batch=8192 * world, seed=1, arrays=False, stop_patience=0)
+
+                    def fit(ep):
+                        if shard == "paths":
+                            return SH.gnet_sharded(eng, dist, Sgn, Mg * world, K, R, T, "put", "reference", epochs=ep, **kwg)
+                        return eng.lsm_gnet(Sgn, K, R, T, "put", "reference", epochs=ep, **kwg)
+
+                    fit(1)
+                    tg = {}
+                    for ep in (1, 4):
+                        barrier()
+                        dtg_, rgn = timed(lambda: fit(ep), 1)
+                        tg[ep] = max_over_ranks(dtg_)
+                    sig = [None] * world
+                    if dist is not None:
+                        dist.all_gather_object(sig, (rgn["price"], rgn["best_loss"]))
+                    steps_ep = -(-rgn["n_rows"] // (8192 * world))
+                    others["global_network_lsm_path_sharded_100k_x50_per_rank"] = {
+                        "epoch_ms": (tg[4] - tg[1]) / 3 * 1e3, "us_per_optimiser_step": (tg[4] - tg[1]) / 3 / steps_ep * 1e6,
+                        "rows_all_ranks": rgn["n_rows"], "global_batch": 8192 * world, "steps_per_epoch": steps_ep,
+                        "rows_per_s": rgn["n_rows"] / ((tg[4] - tg[1]) / 3), "best_loss": rgn["best_loss"], "price": rgn["price"],
+                        "identical_on_all_ranks": all(x == sig[0] for x in sig) if dist is not None else True,
+                        "note": "SingleLSMNet(7,128,3) on tcgen05; per step each rank pushes its 34 178-word gradient vector into "
+                                "every peer's memory over NVLink and the optimiser kernel sums the ranks' vectors in rank order"}
+                    del Sgn
+                except Exception as e:  # noqa: BLE001 -- context only; gnet_sharded raises on all ranks or on none
+                    others["global_network_lsm_path_sharded_100k_x50_per_rank"] = {"error": str(e)[:200]}
     barrier()
 
     # the other BASELINE configs on one GPU (rank 0 of a single-GPU run; reported as context, not as `value`)
@@ -431,6 +465,13 @@ def run_own_arm(args):
                                                 arrays=False), 1)
             others["config3_nn_lsm_4M_x252_hidden128_tcgen05"] = {"ms": dt3 * 1e3, "path_steps_per_s": 4_000_000 * 252 / dt3,
                                                                    "price": r3.price, "note": "sweep only (paths resident)"}
+            dt3s, r3s = timed(lambda: eng.lsm_gnet(S4, K, R, T, "put", "reference", variant="gpu", per_date=1, epochs=10, batch=131072,
+                                                   stop_patience=0, seed=1, arrays=False), 1)
+            others["config3_single_lsm_net_per_date_4M_x252_tcgen05"] = {
+                "ms": dt3s * 1e3, "path_steps_per_s": 4_000_000 * 252 / dt3s, "price": r3s["price"], "rows": r3s["n_rows"],
+                "optimiser_steps": r3s["epochs_run"],
+                "note": "a fresh SingleLSMNet(7,128,3) per exercise date (optmc_gnet_params.per_date), 10 full-batch AdamW steps per "
+                        "date, in-sample decision; sweep only (paths resident)"}
             del S4
             Sg = eng.paths(model, M, N, "f32", E.RngSpec(seed=15))
             dtg, rg = timed(lambda: eng.lsm_global(Sg, K, R, T, "put", arrays=False), 3)

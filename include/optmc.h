@@ -296,7 +296,14 @@ typedef struct optmc_gnet_params {
   double dropout;             /* 0.1; realised as the nearest multiple of 1/256 */
   int32_t inference_dropout;  /* pass 2 with dropout active: 1 / 0; -1 = as the reference under reference semantics
                                  (the net is never switched to eval mode), off under textbook */
-  int32_t reserved;
+  int32_t per_date;           /* 0 = ONE network for all dates (om3:482-651).  1 = a FRESH SingleLSMNet(7, 128, 3) per exercise date,
+                                 trained on that date's live rows against the current cash-flows and used in-sample -- the loop of
+                                 om2:277-310 / om15:145-186 with om3's regressor (BASELINE config 3: "tensor-core fit per date").
+                                 Features and target are z-scored with the date's own moments; `epochs` x ceil(rows / batch)
+                                 optimiser steps per date (batch >= the date's rows = om2's full-batch steps); per-date initial
+                                 weights / shuffles / masks derive from seed and the date; init_params is ignored; n_rows /
+                                 epochs_run = totals over the dates, best_loss = mean over the fitted dates, final_params = the
+                                 network of date 1.  A slab with one exercise date (N = 2) reproduces per_date = 0 bit for bit. */
   uint64_t seed;
   const float* init_params;   /* host [34177] (state_dict order) or NULL = fresh torch-default initialisation.  The torch-GPU
                                  file keeps ONE network across pricing calls (om3gpu:741-748): pass the previous call's

@@ -74,7 +74,7 @@ class GnetParams(C.Structure):  # optmc_gnet_params
     _fields_ = [("hidden", C.c_int32), ("layers", C.c_int32), ("epochs", C.c_int32), ("batch", C.c_int32),
                 ("lr", C.c_double), ("weight_decay", C.c_double), ("decoupled_wd", C.c_int32), ("sched_patience", C.c_int32),
                 ("sched_factor", C.c_double), ("min_lr", C.c_double), ("stop_patience", C.c_int32), ("target_ddof", C.c_int32),
-                ("min_delta", C.c_double), ("dropout", C.c_double), ("inference_dropout", C.c_int32), ("reserved", C.c_int32),
+                ("min_delta", C.c_double), ("dropout", C.c_double), ("inference_dropout", C.c_int32), ("per_date", C.c_int32),
                 ("seed", C.c_uint64), ("init_params", C.POINTER(C.c_float)), ("final_params", C.POINTER(C.c_float))]
 
 

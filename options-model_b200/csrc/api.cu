@@ -485,6 +485,17 @@ int optmc_lsm_gnet(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_t M, int
                    const optmc_lsm_params* lp, const optmc_gnet_params* gp, optmc_gnet_result* out) {
   OPTMC_TRY_BEGIN
   OPTMC_ENTER(ctx);
+  if (gp && gp->per_date) {  // a fresh network per exercise date (the loop of om2:277-310 with om3's regressor)
+    if (!lp || !out) { set_error("null argument"); return OPTMC_EINVAL; }
+    optmc_lsm_params l2 = *lp;
+    l2.basis = OPTMC_BASIS_POLY2;  // unused by the network; keeps the shared validation
+    l2.impl = OPTMC_SWEEP_SPLIT;
+    int rc = bind_sweep(ctx, S_dev, ld, M, N, dtype, &l2);
+    if (rc) return rc;
+    rc = gnet_validate(ctx, gp);
+    if (rc) return rc;
+    return lsm_gnet_per_date(ctx, gp, out);
+  }
   return lsm_gnet(ctx, S_dev, ld, M, 0, N, dtype, lp, gp, out);
   OPTMC_TRY_END
 }
@@ -495,6 +506,7 @@ int optmc_lsm_gnet_sharded(optmc_ctx* ctx, const void* S_dev, int64_t ld, int64_
   OPTMC_ENTER(ctx);
   if (ctx->comm.nranks < 1) { set_error("optmc_comm_init must be called first"); return OPTMC_EINVAL; }
   if (M_total < M_local || M_total <= 0) { set_error("M_total must be >= M_local"); return OPTMC_EINVAL; }
+  if (gp && gp->per_date) { set_error("sharded network LSM: the per-date fit is single-GPU"); return OPTMC_EUNSUPPORTED; }
   return lsm_gnet(ctx, S_dev, ld, M_local, M_total, N, dtype, lp, gp, out);
   OPTMC_TRY_END
 }

@@ -831,6 +831,107 @@ int gnet_shard_plan(const int64_t* n_rows, int32_t nranks, int32_t batch, int64_
   return OPTMC_OK;
 }
 
+// a7: mini-batch training (om3:565-613) of the network in io.params on the rows (io.xs, io.ts, io.ys); the caller has
+// initialised io.params / io.m / io.v / io.pack and io.norm.  Used by the global fit (all dates' rows, optionally the
+// ranks' shares of a path-sharded fit) and by the per-date fit (one date's rows).
+struct GnetTrainIo {
+  float *params, *best, *m, *v, *gpart;
+  double* loss;
+  __nv_bfloat16* pack;
+  const GnetNorm* norm;
+  const double* sqrt_tau;
+  const float* xs; const int* ts; const float* ys;
+  long long n_rows, n_total;       // this rank's rows, all ranks' rows
+  const long long* n_rank;         // [nranks]
+  bool sharded;
+  GnetPeers pe;
+  int batch;
+  unsigned long long seed;         // shuffle / dropout streams
+  // results
+  double lr, best_loss;
+  int epochs_run, n_launches;
+  bool have_best;
+};
+
+static int gnet_train(optmc_ctx* ctx, const optmc_gnet_params* gp, GnetTrainIo& io) {
+  const int batch = io.batch;
+  double lr = gp->lr, best = INFINITY;
+  int step = 0, since_best = 0, sched_bad = 0, epochs_run = 0;
+  double sched_best = INFINITY;
+  bool have_best = false;
+  if (io.n_total > 0) {
+    const long long nb = (io.n_total + batch - 1) / batch;
+    const unsigned int rank_key = io.sharded ? (unsigned int)io.pe.rank * 0x3c6ef372u : 0u;  // the ranks shuffle / mask independently
+    for (int ep = 0; ep < gp->epochs; ++ep) {
+      OPTMC_CUDA(cudaMemsetAsync(io.loss, 0, 8, ctx->stream));
+      GradArgs ga{};
+      ga.params = io.params; ga.wpack = io.pack; ga.xs = io.xs; ga.ts = io.ts; ga.ys = io.ys; ga.feat = nullptr; ga.sqrt_tau = io.sqrt_tau; ga.nm = io.norm;
+      ga.perm = make_perm((unsigned long long)io.n_rows, (unsigned int)(io.seed * 0x9e3779b97f4a7c15ull >> 32) + 0x632be5abu * (unsigned int)(ep + 1) + rank_key);
+      ga.gpart = io.gpart;
+      for (long long b = 0; b < nb; ++b) {
+        long long step_rows;  // rows of all ranks in this step: the gradient's normaliser
+        if (io.sharded) {
+          const long long p0 = b * batch, p1 = p0 + batch < io.n_total ? p0 + batch : io.n_total;
+          ga.start = shard_pos(p0, io.n_rows, io.n_total); ga.end = shard_pos(p1, io.n_rows, io.n_total);
+          step_rows = 0;
+          for (int r = 0; r < io.pe.nranks; ++r) step_rows += shard_pos(p1, io.n_rank[r], io.n_total) - shard_pos(p0, io.n_rank[r], io.n_total);
+        } else {
+          ga.start = b * batch;
+          ga.end = ga.start + batch < io.n_rows ? ga.start + batch : io.n_rows;
+          step_rows = ga.end - ga.start;
+        }
+        ga.inv_b2 = 2.0f / (float)step_rows;
+        ++step;
+        ga.drop = make_drop(gp->dropout, (unsigned int)io.seed * 0x2545f491u + (unsigned int)step * 0x9e3779b1u + rank_key);
+        const int tiles = (int)((ga.end - ga.start + 127) / 128);
+        if (tiles > 0) { gnet_grad_kernel<<<tiles, kGThreads, gnet_smem_bytes(), ctx->stream>>>(ga); ++io.n_launches; ctx->launches++; }
+        if (io.sharded) {
+          const unsigned int tag = ctx->comm.gn_step++;
+          gnet_reduce_push_kernel<<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(io.gpart, tiles, io.pe, tag);
+          gnet_adam_kernel<true><<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(io.params, io.pack, io.m, io.v, io.gpart, 0, (float)lr, (float)gp->weight_decay,
+                                                                             gp->decoupled_wd, step, 1.0f / (float)step_rows, io.loss, io.pe, tag, ctx->d_flags);
+          io.n_launches += 2; ctx->launches += 2;
+        } else {
+          gnet_adam_kernel<false><<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(io.params, io.pack, io.m, io.v, io.gpart, tiles, (float)lr, (float)gp->weight_decay,
+                                                                              gp->decoupled_wd, step, 1.0f / (float)step_rows, io.loss, io.pe, 0u, ctx->d_flags);
+          ++io.n_launches; ctx->launches++;
+        }
+      }
+      OPTMC_CUDA(cudaGetLastError());
+      double sum_loss = 0.0;
+      int hf[4] = {0, 0, 0, 0};
+      OPTMC_CUDA(cudaMemcpyAsync(&sum_loss, io.loss, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      if (io.sharded) OPTMC_CUDA(cudaMemcpyAsync(hf, ctx->d_flags, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream));
+      OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (hf[1]) { set_error("sharded network LSM: a peer rank did not answer (gradient exchange timed out); re-run optmc_comm_export / optmc_comm_init on every rank"); return OPTMC_ECUDA; }
+      const double avg = sum_loss / (double)nb;
+      ++epochs_run;
+      if (!(avg == avg)) { set_error("network LSM: the training loss is not finite"); return OPTMC_ECUDA; }
+      // ReduceLROnPlateau (mode min, rel threshold 1e-4, om3:580): patience epochs without improvement -> lr *= factor
+      if (gp->sched_patience > 0) {
+        if (avg < sched_best * (1.0 - 1e-4)) { sched_best = avg; sched_bad = 0; }
+        else if (++sched_bad > gp->sched_patience) {
+          const double nl = lr * gp->sched_factor > gp->min_lr ? lr * gp->sched_factor : gp->min_lr;
+          lr = nl; sched_bad = 0;
+        }
+      }
+      if (avg < best - gp->min_delta) {  // om3:599-603
+        best = avg; since_best = 0; have_best = true;
+        OPTMC_CUDA(cudaMemcpyAsync(io.best, io.params, (size_t)kGP * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      } else if (gp->stop_patience > 0 && ++since_best >= gp->stop_patience) {
+        break;
+      }
+    }
+    if (have_best) {  // om3:611-613
+      OPTMC_CUDA(cudaMemcpyAsync(io.params, io.best, (size_t)kGP * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+      gnet_pack_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(io.params, io.pack);
+      ++io.n_launches; ctx->launches++;
+    }
+  }
+  io.lr = lr; io.best_loss = best; io.epochs_run = epochs_run; io.have_best = have_best;
+  return OPTMC_OK;
+}
+
 template <typename R>
 static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int64_t M_total, int32_t N, const optmc_lsm_params* lp,
                       const optmc_gnet_params* gp, optmc_gnet_result* out) {
@@ -965,79 +1066,16 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int6
   OPTMC_CUDA(cudaFuncSetAttribute(gnet_walk_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gnet_smem_bytes()));
 
   // ---- a7: mini-batch training (om3:565-613) ----
-  double lr = gp->lr, best = INFINITY;
-  int step = 0, since_best = 0, sched_bad = 0, epochs_run = 0;
-  double sched_best = INFINITY;
-  bool have_best = false;
-  if (n_total > 0) {
-    const long long nb = (n_total + batch - 1) / batch;
-    const unsigned int rank_key = sharded ? (unsigned int)pe.rank * 0x3c6ef372u : 0u;  // the ranks shuffle / mask independently
-    for (int ep = 0; ep < gp->epochs; ++ep) {
-      OPTMC_CUDA(cudaMemsetAsync(d_loss, 0, 8, ctx->stream));
-      GradArgs ga{};
-      ga.params = d_params; ga.wpack = d_pack; ga.xs = d_xs; ga.ts = d_ts; ga.ys = d_ys; ga.feat = nullptr; ga.sqrt_tau = d_tab + (N + 1); ga.nm = d_norm;
-      ga.perm = make_perm((unsigned long long)n_rows, (unsigned int)(gp->seed * 0x9e3779b97f4a7c15ull >> 32) + 0x632be5abu * (unsigned int)(ep + 1) + rank_key);
-      ga.gpart = d_gpart;
-      for (long long b = 0; b < nb; ++b) {
-        long long step_rows;  // rows of all ranks in this step: the gradient's normaliser
-        if (sharded) {
-          const long long p0 = b * batch, p1 = p0 + batch < n_total ? p0 + batch : n_total;
-          ga.start = shard_pos(p0, n_rows, n_total); ga.end = shard_pos(p1, n_rows, n_total);
-          step_rows = 0;
-          for (int r = 0; r < pe.nranks; ++r) step_rows += shard_pos(p1, n_rank[r], n_total) - shard_pos(p0, n_rank[r], n_total);
-        } else {
-          ga.start = b * batch;
-          ga.end = ga.start + batch < n_rows ? ga.start + batch : n_rows;
-          step_rows = ga.end - ga.start;
-        }
-        ga.inv_b2 = 2.0f / (float)step_rows;
-        ++step;
-        ga.drop = make_drop(gp->dropout, (unsigned int)gp->seed * 0x2545f491u + (unsigned int)step * 0x9e3779b1u + rank_key);
-        const int tiles = (int)((ga.end - ga.start + 127) / 128);
-        if (tiles > 0) { gnet_grad_kernel<<<tiles, kGThreads, gnet_smem_bytes(), ctx->stream>>>(ga); ++n_launches; ctx->launches++; }
-        if (sharded) {
-          const unsigned int tag = ctx->comm.gn_step++;
-          gnet_reduce_push_kernel<<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(d_gpart, tiles, pe, tag);
-          gnet_adam_kernel<true><<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(d_params, d_pack, d_m, d_v, d_gpart, 0, (float)lr, (float)gp->weight_decay,
-                                                                             gp->decoupled_wd, step, 1.0f / (float)step_rows, d_loss, pe, tag, ctx->d_flags);
-          n_launches += 2; ctx->launches += 2;
-        } else {
-          gnet_adam_kernel<false><<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(d_params, d_pack, d_m, d_v, d_gpart, tiles, (float)lr, (float)gp->weight_decay,
-                                                                              gp->decoupled_wd, step, 1.0f / (float)step_rows, d_loss, pe, 0u, ctx->d_flags);
-          ++n_launches; ctx->launches++;
-        }
-      }
-      OPTMC_CUDA(cudaGetLastError());
-      double sum_loss = 0.0;
-      int hf[4] = {0, 0, 0, 0};
-      OPTMC_CUDA(cudaMemcpyAsync(&sum_loss, d_loss, 8, cudaMemcpyDeviceToHost, ctx->stream));
-      if (sharded) OPTMC_CUDA(cudaMemcpyAsync(hf, ctx->d_flags, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream));
-      OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
-      if (hf[1]) { set_error("sharded network LSM: a peer rank did not answer (gradient exchange timed out); re-run optmc_comm_export / optmc_comm_init on every rank"); return OPTMC_ECUDA; }
-      const double avg = sum_loss / (double)nb;
-      ++epochs_run;
-      if (!(avg == avg)) { set_error("network LSM: the training loss is not finite"); return OPTMC_ECUDA; }
-      // ReduceLROnPlateau (mode min, rel threshold 1e-4, om3:580): patience epochs without improvement -> lr *= factor
-      if (gp->sched_patience > 0) {
-        if (avg < sched_best * (1.0 - 1e-4)) { sched_best = avg; sched_bad = 0; }
-        else if (++sched_bad > gp->sched_patience) {
-          const double nl = lr * gp->sched_factor > gp->min_lr ? lr * gp->sched_factor : gp->min_lr;
-          lr = nl; sched_bad = 0;
-        }
-      }
-      if (avg < best - gp->min_delta) {  // om3:599-603
-        best = avg; since_best = 0; have_best = true;
-        OPTMC_CUDA(cudaMemcpyAsync(d_best, d_params, (size_t)kGP * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-      } else if (gp->stop_patience > 0 && ++since_best >= gp->stop_patience) {
-        break;
-      }
-    }
-    if (have_best) {  // om3:611-613
-      OPTMC_CUDA(cudaMemcpyAsync(d_params, d_best, (size_t)kGP * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-      gnet_pack_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(d_params, d_pack);
-      ++n_launches; ctx->launches++;
-    }
-  }
+  GnetTrainIo io{};
+  io.params = d_params; io.best = d_best; io.m = d_m; io.v = d_v; io.gpart = d_gpart; io.loss = d_loss; io.pack = d_pack; io.norm = d_norm;
+  io.sqrt_tau = d_tab + (N + 1); io.xs = d_xs; io.ts = d_ts; io.ys = d_ys; io.n_rows = n_rows; io.n_total = n_total; io.n_rank = n_rank;
+  io.sharded = sharded; io.pe = pe; io.batch = batch; io.seed = gp->seed;
+  rc = gnet_train(ctx, gp, io);
+  n_launches += io.n_launches;
+  if (rc) return rc;
+  const double lr = io.lr, best = io.best_loss;
+  const int epochs_run = io.epochs_run;
+  const bool have_best = io.have_best;
   OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   out->epochs_run = epochs_run; out->best_loss = have_best ? best : nan(""); out->final_lr = lr;
 
@@ -1089,6 +1127,314 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int6
   return OPTMC_OK;
 }
 
+// ---- PER-DATE fit of the same network (gp->per_date): the loop of om2:277-310 / om15:145-186 with om3's regressor ----
+// At every exercise date a fresh SingleLSMNet(7, 128, 3) is trained on the date's live rows (seven reference features of
+// (S/K, tau), z-scored with the date's own moments -- constant features get std 1, om3:561 -- against the z-scored
+// current cash-flows) by the mini-batch loop of gnet_train, and its in-sample prediction decides (strict '>').  The
+// cash-flows live in HBM in date-N money with the exercised flag in the sign bit, exactly as in the other split sweeps.
+template <typename R>
+__device__ __forceinline__ bool gpd_live(R s, R c, double K, int is_put, int sticky) {
+  return !(sticky && signbit(c)) && payoff<double>((double)s, K, is_put != 0) > 0.0;
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) gpd_count_kernel(const R* __restrict__ S_t, const R* __restrict__ cf, long long M, double K, int is_put,
+                                                        int sticky, unsigned long long* __restrict__ counts) {
+  const long long base = (long long)blockIdx.x * kGChunk;
+  unsigned int c = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long j = base + k * 256 + threadIdx.x;
+    if (j < M) c += gpd_live<R>(S_t[j], cf[j], K, is_put, sticky) ? 1u : 0u;
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ unsigned int s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += s[w];
+    counts[blockIdx.x] = tot;
+  }
+}
+
+// rows of one date in the order of gnet_compact_kernel (k-major inside a 1024-path chunk); y = value of the cash-flow at
+// date t (date-N money x D_t); idx = the path of the row
+template <typename R>
+__global__ void __launch_bounds__(256) gpd_compact_kernel(const R* __restrict__ S_t, const R* __restrict__ cf, long long M, int t, double K,
+                                                          int is_put, int sticky, double dg, double stau,
+                                                          const unsigned long long* __restrict__ offsets, float* __restrict__ xs,
+                                                          int* __restrict__ ts, float* __restrict__ ys, unsigned int* __restrict__ idx,
+                                                          unsigned long long* __restrict__ sums, int* flags) {
+  const long long base = (long long)blockIdx.x * kGChunk;
+  const double invK = 1.0 / K;
+  __shared__ unsigned int wsum[4][8];
+  __shared__ double red[8][kGQ];
+  double acc[kGQ];
+#pragma unroll
+  for (int q = 0; q < kGQ; ++q) acc[q] = 0.0;
+  const unsigned long long off = offsets[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool live[4];
+  double sv[4], cv[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const long long j = base + k * 256 + threadIdx.x;
+    sv[k] = 0.0; cv[k] = 0.0; live[k] = false;
+    if (j < M) {
+      const R s = S_t[j], c = cf[j];
+      sv[k] = (double)s; cv[k] = fabs((double)c);
+      live[k] = gpd_live<R>(s, c, K, is_put, sticky);
+    }
+    const unsigned int b = __ballot_sync(0xffffffffu, live[k]);
+    if (lane == 0) wsum[k][warp] = __popc(b);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    unsigned int before = 0;
+    for (int kk = 0; kk < k; ++kk)
+      for (int w = 0; w < 8; ++w) before += wsum[kk][w];
+    for (int w = 0; w < warp; ++w) before += wsum[k][w];
+    const unsigned int b = __ballot_sync(0xffffffffu, live[k]);
+    if (live[k]) {
+      const long long j = base + k * 256 + threadIdx.x;
+      const unsigned long long r = off + before + __popc(b & ((1u << lane) - 1u));
+      const double x = sv[k] * invK;
+      const double y = cv[k] * dg;
+      xs[r] = (float)x; ts[r] = t; ys[r] = (float)y; idx[r] = (unsigned int)j;
+      double f[7];
+      f[0] = 1.0; f[1] = x; f[2] = x * x; f[3] = x * x * x; f[4] = x > 1.0 ? x - 1.0 : 0.0; f[5] = stau; f[6] = x * stau;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) { acc[2 * q] += f[q]; acc[2 * q + 1] += f[q] * f[q]; }
+      acc[14] += y; acc[15] += y * y;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kGQ; ++q) {
+    double v = acc[q];
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) red[warp][q] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kGQ) {
+    double v = 0.0;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    if (v != 0.0) {
+      unsigned long long hi, lo;
+      if (!fx_encode(v, hi, lo)) atomicExch(flags, 1);
+      atomicAdd(sums + 2 * threadIdx.x, hi - (1ull << 47));
+      atomicAdd(sums + 2 * threadIdx.x + 1, lo);
+    }
+  }
+}
+
+// in-sample continuation of the date's rows on the tensor cores + exercise decision (strict '>', om2:304 / om3:644)
+template <typename R>
+__global__ void __launch_bounds__(kGThreads, 1) gpd_decide_kernel(const float* __restrict__ params, const __nv_bfloat16* __restrict__ wpack,
+                                                                  const GnetNorm* __restrict__ nmp, const float* __restrict__ xs,
+                                                                  const unsigned int* __restrict__ idx, long long n, int t, float stau,
+                                                                  const R* __restrict__ S_t, R* cf, double K, double Kh, double Kl, int is_put,
+                                                                  int sticky, R dinv, Drop drop, unsigned long long* exc_t,
+                                                                  unsigned long long* bnd_t) {
+  extern __shared__ __align__(1024) unsigned char smem_g[];
+  GnetSmem& sm = *reinterpret_cast<GnetSmem*>(smem_g);
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & 127, half = tid >> 7;
+  const unsigned int tmem = gnet_setup(sm, params, wpack);
+  if (tid == 0) gnet_weights_ready(sm);
+  const unsigned int lane_base = (unsigned int)((warp & 3) * 32) << 16;
+  const long long r = (long long)blockIdx.x * 128 + row;
+  const bool act = r < n;
+  const GnetNorm nm = *nmp;
+  const unsigned int j = act ? idx[r] : 0u;
+  float fn[kGIn];
+  gnet_features(act ? xs[r] : 0.f, stau, nm, fn);
+  const unsigned int rr = j * 0x01000193u + (unsigned int)t;  // the decision pass's stream (gnet_walk_kernel)
+  unsigned int phase = 0;
+  gnet_layer1(sm, fn, row, half, rr, drop);
+  tc_publish();
+  if (tid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mma_ab_t(tmem, sm.A1, sm.W2);
+    umma_commit(&sm.bar);
+  }
+  tc_bar_wait(&sm.bar, phase); phase ^= 1u;
+  gnet_hidden<false>(sm, tmem + lane_base, sm.b2, sm.A2, row, half, rr, 1, drop);
+  tc_publish();
+  if (tid == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    mma_ab_t(tmem + 128, sm.A2, sm.W3);
+    umma_commit(&sm.bar);
+  }
+  tc_bar_wait(&sm.bar, phase); phase ^= 1u;
+  const float out = gnet_join_dot(sm, gnet_hidden<true, false>(sm, tmem + lane_base + 128, sm.b3, sm.A3, row, half, rr, 2, drop), row, half);
+  unsigned int cnt = 0;
+  unsigned long long bnd = bnd_none(is_put);
+  if (act && half == 0) {
+    const R sr = S_t[j];
+    const double s = (double)sr;
+    const double pay = payoff<double>(s, K, is_put != 0);
+    const double cont = (double)(out * nm.ystd + nm.ymean);  // om3:640
+    if (pay > cont) {
+      const R sgn = is_put ? (R)-1 : (R)1;
+      const R a = (fma(sgn, sr, (R)(is_put ? Kh : -Kh)) + (R)(is_put ? Kl : -Kl)) * dinv;  // payoff in date-N money
+      cf[j] = sticky ? -a : a;
+      cnt = 1;
+      bnd = (unsigned long long)__double_as_longlong(s);
+    }
+  }
+  if (half == 0) {
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    bnd = is_put ? warp_max_u64(bnd) : warp_min_u64(bnd);
+    if ((tid & 31) == 0 && cnt && exc_t) {
+      atomicAdd(exc_t, (unsigned long long)cnt);
+      if (is_put) atomicMax(bnd_t, bnd); else atomicMin(bnd_t, bnd);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+}
+
+// Host loop; the sweep is bound to the context (api.cu: bind_sweep) like the other split sweeps.  The first fitted date
+// (t = N - 1) uses gp->seed itself, so that a slab with ONE exercise date (N = 2) reproduces optmc_lsm_gnet bit for bit.
+template <typename R>
+static int lsm_gnet_per_date_t(optmc_ctx* ctx, const optmc_gnet_params* gp, optmc_gnet_result* out) {
+  SweepDesc& sw = ctx->sw;
+  const long long M = sw.M;
+  const int N = sw.N;
+  const optmc_lsm_params* lp = &sw.lp;
+  const bool sticky = (lp->semantics & OPTMC_SEM_STICKY_MASK) != 0;
+  const bool refdisc = (lp->semantics & OPTMC_SEM_REF_DISCOUNT) != 0;
+  const double dt = lp->T / N;
+  const int nchunks = (int)((M + kGChunk - 1) / kGChunk);
+  const int batch = gp->batch > 0 ? gp->batch : 256;
+  const int max_tiles = (batch + 127) / 128;
+  std::vector<double> st((size_t)N + 1);
+  for (int t = 0; t <= N; ++t) { const double tau = lp->T - t * dt; st[t] = sqrt(tau > 1e-6 ? tau : 1e-6); }
+  constexpr int kMetaN = 1 + 2 * kGQ;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t seg = ((size_t)M * 4 + 255) / 256 * 256;
+  const size_t o_tab = take(st.size() * 8), o_counts = take((size_t)nchunks * 8), o_meta = take(kMetaN * 8), o_norm = take(sizeof(GnetNorm)),
+               o_params = take((size_t)kGP * 4), o_best = take((size_t)kGP * 4), o_m = take((size_t)kGP * 4), o_v = take((size_t)kGP * 4),
+               o_gpart = take((size_t)max_tiles * (kGP + 1) * 4), o_loss = take(8), o_pack = take(2 * kTcTileBytes),
+               o_rows = take(4 * seg);
+  int rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
+  if (rc) return rc;
+  char* dev = static_cast<char*>(ctx->batch_dev);
+  double* d_tab = reinterpret_cast<double*>(dev + o_tab);
+  unsigned long long* d_counts = reinterpret_cast<unsigned long long*>(dev + o_counts);
+  unsigned long long* d_meta = reinterpret_cast<unsigned long long*>(dev + o_meta);
+  long long* d_nrows = reinterpret_cast<long long*>(d_meta);
+  unsigned long long* d_sums = d_meta + 1;
+  GnetNorm* d_norm = reinterpret_cast<GnetNorm*>(dev + o_norm);
+  float* d_xs = reinterpret_cast<float*>(dev + o_rows);
+  int* d_ts = reinterpret_cast<int*>(dev + o_rows + seg);
+  float* d_ys = reinterpret_cast<float*>(dev + o_rows + 2 * seg);
+  unsigned int* d_idx = reinterpret_cast<unsigned int*>(dev + o_rows + 3 * seg);
+  OPTMC_CUDA(cudaMemcpyAsync(d_tab, st.data(), st.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  OPTMC_CUDA(cudaFuncSetAttribute(gnet_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gnet_smem_bytes()));
+  OPTMC_CUDA(cudaFuncSetAttribute(gpd_decide_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gnet_smem_bytes()));
+  rc = sweep_begin(ctx);  // cf = payoff(S[N]) (date-N money), per-date statistics reset
+  if (rc) return rc;
+  OPTMC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  const R* Sr = static_cast<const R*>(sw.S);
+  R* cf = static_cast<R*>(ctx->cf);
+  const int inf_drop = gp->inference_dropout < 0 ? (refdisc && sticky ? 1 : 0) : gp->inference_dropout;
+  long long rows_all = 0;
+  int epochs_all = 0, n_launches = 0, fitted = 0;
+  double loss_sum = 0.0, lr_last = gp->lr;
+  GnetTrainIo io{};
+  io.params = reinterpret_cast<float*>(dev + o_params); io.best = reinterpret_cast<float*>(dev + o_best);
+  io.m = reinterpret_cast<float*>(dev + o_m); io.v = reinterpret_cast<float*>(dev + o_v);
+  io.gpart = reinterpret_cast<float*>(dev + o_gpart); io.loss = reinterpret_cast<double*>(dev + o_loss);
+  io.pack = reinterpret_cast<__nv_bfloat16*>(dev + o_pack); io.norm = d_norm; io.sqrt_tau = d_tab;
+  io.xs = d_xs; io.ts = d_ts; io.ys = d_ys; io.sharded = false; io.batch = batch;
+  for (int t = N - 1; t >= 1; --t) {
+    const R* S_t = Sr + (size_t)t * sw.ld;
+    const unsigned long long seed_t = gp->seed + (unsigned long long)(N - 1 - t) * 0x9e3779b97f4a7c15ull;
+    OPTMC_CUDA(cudaMemsetAsync(d_meta, 0, kMetaN * 8, ctx->stream));
+    gpd_count_kernel<R><<<nchunks, 256, 0, ctx->stream>>>(S_t, cf, M, lp->K, lp->is_put, sticky ? 1 : 0, d_counts);
+    gnet_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, nchunks, d_nrows);
+    n_launches += 2; ctx->launches += 2;
+    long long n_rows = 0;
+    OPTMC_CUDA(cudaMemcpyAsync(&n_rows, d_nrows, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    OPTMC_CUDA(cudaMemcpyAsync(ctx->d_nitm + t, d_nrows, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_rows == 0) continue;  // om2:284-285
+    gpd_compact_kernel<R><<<nchunks, 256, 0, ctx->stream>>>(S_t, cf, M, t, lp->K, lp->is_put, sticky ? 1 : 0, sw.Dt[t], st[t], d_counts, d_xs,
+                                                            d_ts, d_ys, d_idx, d_sums, ctx->d_flags);
+    gnet_norm_kernel<<<1, 32, 0, ctx->stream>>>(d_sums, d_nrows, gp->target_ddof ? 1 : 0, d_norm);
+    gnet_init_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(io.params, io.m, io.v, seed_t);
+    gnet_pack_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(io.params, io.pack);
+    n_launches += 4; ctx->launches += 4;
+    const long long n_rank[1] = {n_rows};
+    io.n_rows = n_rows; io.n_total = n_rows; io.n_rank = n_rank; io.seed = seed_t; io.n_launches = 0;
+    rc = gnet_train(ctx, gp, io);
+    n_launches += io.n_launches;
+    if (rc) return rc;
+    const Drop drop = make_drop(inf_drop ? gp->dropout : 0.0, (unsigned int)seed_t * 0x2545f491u + 0x51ed270bu);
+    const bool stats = out->ex_count != nullptr || out->boundary != nullptr;
+    gpd_decide_kernel<R><<<(unsigned)((n_rows + 127) / 128), kGThreads, gnet_smem_bytes(), ctx->stream>>>(
+        io.params, io.pack, d_norm, d_xs, d_idx, n_rows, t, (float)st[t], S_t, cf, lp->K, sw.Kh, sw.Kl, lp->is_put, sticky ? 1 : 0, (R)sw.Dinv[t],
+        drop, stats ? ctx->d_exc + t : nullptr, stats ? ctx->d_bnd + t : nullptr);
+    ++n_launches; ctx->launches++;
+    OPTMC_CUDA(cudaGetLastError());
+    rows_all += n_rows; epochs_all += io.epochs_run; lr_last = io.lr; ++fitted;
+    if (io.have_best) loss_sum += io.best_loss;
+  }
+  OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  rc = sweep_finish(ctx, ctx->gram);
+  if (rc) return rc;
+  rc = sweep_finalize_price(ctx, ctx->gram);
+  if (rc) return rc;
+  OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+  sw.impl_used = OPTMC_SWEEP_SPLIT;
+  sw.have_results = true;
+  double fin[4];
+  int flags[4];
+  OPTMC_CUDA(cudaMemcpyAsync(fin, ctx->d_final, sizeof(fin), cudaMemcpyDeviceToHost, ctx->stream));
+  OPTMC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+  if (gp->final_params) OPTMC_CUDA(cudaMemcpyAsync(gp->final_params, io.params, (size_t)kGP * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<unsigned long long> hb, he;
+  if (out->boundary) { hb.resize(N + 1); OPTMC_CUDA(cudaMemcpyAsync(hb.data(), ctx->d_bnd, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
+  if (out->ex_count) { he.resize(N + 1); OPTMC_CUDA(cudaMemcpyAsync(he.data(), ctx->d_exc, (size_t)(N + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
+  OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (flags[0]) { set_error("network LSM: a sum left the fixed-point range or is not finite"); return OPTMC_EUNSUPPORTED; }
+  float t01 = 0.f, t12 = 0.f;
+  cudaEventElapsedTime(&t01, ctx->ev[0], ctx->ev[1]);
+  cudaEventElapsedTime(&t12, ctx->ev[1], ctx->ev[2]);
+  ctx->last_paths_ms = 0.0; ctx->last_sweep_ms = t01 + t12;
+  out->price = fin[0]; out->stderr_ = fin[1]; out->n_paths = M; out->n_rows = rows_all; out->epochs_run = epochs_all;
+  out->n_launches = n_launches + sw.n_launches;
+  out->best_loss = fitted ? loss_sum / fitted : nan("");  // mean over the fitted dates
+  out->final_lr = lr_last;
+  if (out->boundary) {
+    const unsigned long long none = lp->is_put ? 0ull : ~0ull;
+    for (int t = 0; t <= N; ++t) {
+      if (hb[t] == none) out->boundary[t] = nan("");
+      else memcpy(&out->boundary[t], &hb[t], 8);
+    }
+  }
+  if (out->ex_count) for (int t = 0; t <= N; ++t) out->ex_count[t] = (int64_t)he[t];
+  return OPTMC_OK;
+}
+
+int lsm_gnet_per_date(optmc_ctx* ctx, const optmc_gnet_params* gp, optmc_gnet_result* out) {
+  return ctx->sw.dtype == OPTMC_F64 ? lsm_gnet_per_date_t<double>(ctx, gp, out) : lsm_gnet_per_date_t<float>(ctx, gp, out);
+}
+
+int gnet_validate(optmc_ctx* ctx, const optmc_gnet_params* gp) {
+  if (gp->hidden != kGH || gp->layers != 3) { set_error("network LSM: the tensor-core kernels are built for SingleLSMNet(7, 128, 3)"); return OPTMC_EUNSUPPORTED; }
+  if (gp->epochs < 0 || gp->batch < 0 || gp->batch > 128 * 1024 || !(gp->lr > 0) || gp->dropout < 0 || gp->dropout >= 1) {
+    set_error("network LSM: bad training parameters"); return OPTMC_EINVAL;
+  }
+  if (ctx->cc < 100) { set_error("network LSM needs tcgen05 (sm_100)"); return OPTMC_EUNSUPPORTED; }
+  return OPTMC_OK;
+}
+
 int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int64_t M_total, int32_t N, int32_t dtype, const optmc_lsm_params* lp,
              const optmc_gnet_params* gp, optmc_gnet_result* out) {
   if (!S || !lp || !gp || !out) { set_error("null argument"); return OPTMC_EINVAL; }
@@ -1097,11 +1443,8 @@ int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int64_t M_tot
   if (M <= 0 || N <= 0) { set_error("num_simulations and num_time_steps must be positive integers."); return OPTMC_EINVAL; }
   if (ld < M) { set_error("ld must be >= M"); return OPTMC_EINVAL; }
   if (dtype != OPTMC_F32 && dtype != OPTMC_F64) { set_error("bad dtype"); return OPTMC_EINVAL; }
-  if (gp->hidden != kGH || gp->layers != 3) { set_error("network LSM: the tensor-core kernels are built for SingleLSMNet(7, 128, 3)"); return OPTMC_EUNSUPPORTED; }
-  if (gp->epochs < 0 || gp->batch < 0 || gp->batch > 128 * 1024 || !(gp->lr > 0) || gp->dropout < 0 || gp->dropout >= 1) {
-    set_error("network LSM: bad training parameters"); return OPTMC_EINVAL;
-  }
-  if (ctx->cc < 100) { set_error("network LSM needs tcgen05 (sm_100)"); return OPTMC_EUNSUPPORTED; }
+  const int rcv = gnet_validate(ctx, gp);
+  if (rcv) return rcv;
   return dtype == OPTMC_F64 ? lsm_gnet_t<double>(ctx, S, ld, M, M_total, N, lp, gp, out)
                             : lsm_gnet_t<float>(ctx, S, ld, M, M_total, N, lp, gp, out);
 }

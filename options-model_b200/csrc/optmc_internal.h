@@ -184,6 +184,8 @@ int lsm_apply_policy(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int32
 // lsm_gnet.cu
 int lsm_gnet(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int64_t M_total /* > 0: path-sharded */, int32_t N, int32_t dtype,
              const optmc_lsm_params* lp, const optmc_gnet_params* gp, optmc_gnet_result* out);
+int gnet_validate(optmc_ctx* ctx, const optmc_gnet_params* gp);
+int lsm_gnet_per_date(optmc_ctx* ctx, const optmc_gnet_params* gp, optmc_gnet_result* out);  // sweep bound to the context
 int gnet_shard_plan(const int64_t* n_rows, int32_t nranks, int32_t batch, int64_t b, int32_t rank, int64_t* lo, int64_t* hi,
                     int64_t* global_rows);
 int gnet_grad_debug(optmc_ctx* ctx, long long n, const float* feat, const float* ys, const float* params, float* grads, float* loss);

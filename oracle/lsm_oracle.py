@@ -578,6 +578,42 @@ class ContNetRegressor:
         return cont.astype(np.float64), None
 
 
+class SingleLSMNetDateRegressor:
+    """Per-date fit of om3's regressor -- the loop of om2:277-310 (= om15:145-186) with `SingleLSMNet(7, hidden, 3)`
+    (om3:85-103) in place of ContNet (BASELINE config 3, "tensor-core fit per date"; the reference ships the two pieces,
+    not this combination): at date t the seven reference features (om3:105-121) of the live rows are z-scored with the
+    date's own moments (std == 0 -> 1, om3:561), the current cash-flows with their mean / std (om3:550-556; ddof as
+    `single_lsm_net_fit`'s variant), a FRESH network is trained by :func:`single_lsm_net_fit` (om3:565-613 /
+    om3gpu:740-798) and predicts in-sample (dropout active iff ``inference_dropout``).  Streams: torch's RNG seeded with
+    ``seed + t`` -- comparable with the engine statistically."""
+
+    p = 1
+
+    def __init__(self, K, r, T, variant="gpu", hidden=128, epochs=10, lr=1e-3, batch=None, dropout=0.1, seed=0,
+                 inference_dropout=False, target_ddof=None, patience=None):
+        self.K, self.r, self.T = K, r, T
+        self.kw = dict(variant=variant, hidden=hidden, epochs=epochs, lr=lr, batch=batch, dropout=dropout,
+                       inference_dropout=inference_dropout, patience=patience)
+        self.seed = seed
+        self.ddof = (0 if variant == "cpu" else 1) if target_ddof is None else target_ddof
+        self.loss = {}
+
+    def __call__(self, t, t_current, S_itm, Y):
+        F = features_ref7(np.asarray(S_itm, dtype=np.float64), self.K, self.r, self.T, t_current)
+        f_mean, f_std = F.mean(axis=0), F.std(axis=0)
+        f_std[f_std == 0] = 1
+        Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)
+        y_mean = Y.mean()
+        y_std = Y.std(ddof=self.ddof) if Y.size > self.ddof else 0.0
+        if not y_std > 0:
+            y_std = 1.0
+        log = []
+        Xn = (F - f_mean) / f_std
+        predict = single_lsm_net_fit(seed=self.seed + t, log=log, **self.kw)(Xn, (Y - y_mean) / y_std)
+        self.loss[t] = min(log) if log else float("nan")
+        return np.asarray(predict(Xn)).reshape(-1) * y_std + y_mean, None
+
+
 class FixedPolicyRegressor:
     """Out-of-sample exercise: the continuation value comes from coefficients fitted on OTHER paths
     (``betas[t]`` as returned by :func:`lsm_sweep`; a NaN row means "no exercise at that date").  Plugged into
@@ -736,7 +772,7 @@ def lsm_global(S, K, r, T, option_type, fit: Callable, target_ddof=0):
 
 
 def single_lsm_net_fit(variant="cpu", hidden=128, epochs=25, lr=1e-3, batch=None, dropout=0.1, seed=0,
-                       inference_dropout=True, log=None, reference_streams=False):
+                       inference_dropout=True, log=None, reference_streams=False, patience=None):
     """``fit`` for :func:`lsm_global` restating the reference's global network regression in torch (CPU, fp32).
 
     variant "cpu" = om3:565-613: SingleLSMNet(7, hidden, 3) (om3:85-103), DataLoader(batch 256, shuffle), Adam(lr,
@@ -799,7 +835,7 @@ def single_lsm_net_fit(variant="cpu", hidden=128, epochs=25, lr=1e-3, batch=None
                 best, best_sd, bad = avg, copy.deepcopy(net.state_dict()), 0
             else:
                 bad += 1
-                if bad >= (8 if cpu else 3):
+                if bad >= ((8 if cpu else 3) if patience is None else patience):  # om3:605 / om3gpu:786
                     break
         if best_sd is not None:
             net.load_state_dict(best_sd)

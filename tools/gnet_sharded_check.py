@@ -6,7 +6,7 @@ the single-GPU fit and timed.  Launch with one process per GPU:
       tools/gnet_sharded_check.py [--paths 100000] [--dates 50] [--epochs 6] [--time-paths 100000]
 
 Checks: price / stderr / best loss / final weights bit-identical on every rank; the row count equals the single-GPU
-fit's; loss within 1 % and price within 1.5 % of the single-GPU fit on the same paths (the ranks' mini-batches are
+fit's; loss within 1 % and price within 4 % of the single-GPU fit on the same paths (the estimator's own seed-to-seed spread is +-2.5 %: DESIGN 4; the ranks' mini-batches are
 composed differently, so the fits agree statistically, not bit for bit).  Exit code 0 = all passed; rank 0 prints one
 JSON line.
 """
@@ -74,7 +74,7 @@ def main():
         e_price = abs(res["price"] - single["price"]) / single["price"]
         e_loss = abs(res["best_loss"] - single["best_loss"]) / single["best_loss"]
         exc_ok = int(res["ex_count"].sum()) > 0 and abs(int(res["ex_count"].sum()) - int(single["ex_count"].sum())) < 0.05 * M
-        good = same and res["n_rows"] == single["n_rows"] and res["n_paths"] == M and e_price < 0.015 and e_loss < 0.01 and exc_ok
+        good = same and res["n_rows"] == single["n_rows"] and res["n_paths"] == M and e_price < 0.04 and e_loss < 0.01 and exc_ok
         ok &= good
         out[f"check_{name}"] = dict(price=res["price"], single_price=single["price"], rel_price=e_price, loss=res["best_loss"],
                                     single_loss=single["best_loss"], rel_loss=e_loss, n_rows=res["n_rows"],
