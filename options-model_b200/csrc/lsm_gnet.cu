@@ -831,12 +831,30 @@ int gnet_shard_plan(const int64_t* n_rows, int32_t nranks, int32_t batch, int64_
   return OPTMC_OK;
 }
 
+// End of an epoch without a host round trip (no scheduler, no early stopping: nothing the host must decide): the
+// best-weights snapshot of om3:599-603 on the device.  st[2][4] = {best, have_best, bad (non-finite loss seen), -},
+// double-buffered by epoch parity so that every thread tests the same `best`.
+__global__ void __launch_bounds__(256) gnet_epoch_end_kernel(const double* __restrict__ loss, double nb, double min_delta, double* st, int ep,
+                                                             const float* __restrict__ params, float* __restrict__ best) {
+  const double* cur = st + (ep & 1) * 4;
+  double* nxt = st + ((ep + 1) & 1) * 4;
+  const double avg = *loss / nb;
+  const bool better = avg < cur[0] - min_delta;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (better && i < kGP) best[i] = params[i];
+  if (i == 0) {
+    nxt[0] = better ? avg : cur[0];
+    nxt[1] = better ? 1.0 : cur[1];
+    nxt[2] = (avg == avg) ? cur[2] : 1.0;
+  }
+}
+
 // a7: mini-batch training (om3:565-613) of the network in io.params on the rows (io.xs, io.ts, io.ys); the caller has
 // initialised io.params / io.m / io.v / io.pack and io.norm.  Used by the global fit (all dates' rows, optionally the
 // ranks' shares of a path-sharded fit) and by the per-date fit (one date's rows).
 struct GnetTrainIo {
   float *params, *best, *m, *v, *gpart;
-  double* loss;
+  double* loss;                    // [1] epoch accumulator + [8] device epoch state (gnet_epoch_end_kernel)
   __nv_bfloat16* pack;
   const GnetNorm* norm;
   const double* sqrt_tau;
@@ -862,6 +880,13 @@ static int gnet_train(optmc_ctx* ctx, const optmc_gnet_params* gp, GnetTrainIo& 
   if (io.n_total > 0) {
     const long long nb = (io.n_total + batch - 1) / batch;
     const unsigned int rank_key = io.sharded ? (unsigned int)io.pe.rank * 0x3c6ef372u : 0u;  // the ranks shuffle / mask independently
+    // the host looks at every epoch's loss only when it has something to decide (scheduler, early stopping)
+    const bool host_epochs = gp->sched_patience > 0 || gp->stop_patience > 0;
+    double* d_state = io.loss + 1;
+    if (!host_epochs) {
+      const double st0[8] = {INFINITY, 0.0, 0.0, 0.0, INFINITY, 0.0, 0.0, 0.0};
+      OPTMC_CUDA(cudaMemcpyAsync(d_state, st0, sizeof(st0), cudaMemcpyHostToDevice, ctx->stream));
+    }
     for (int ep = 0; ep < gp->epochs; ++ep) {
       OPTMC_CUDA(cudaMemsetAsync(io.loss, 0, 8, ctx->stream));
       GradArgs ga{};
@@ -898,6 +923,12 @@ static int gnet_train(optmc_ctx* ctx, const optmc_gnet_params* gp, GnetTrainIo& 
         }
       }
       OPTMC_CUDA(cudaGetLastError());
+      if (!host_epochs) {
+        gnet_epoch_end_kernel<<<(kGP + 255) / 256, 256, 0, ctx->stream>>>(io.loss, (double)nb, gp->min_delta, d_state, ep, io.params, io.best);
+        ++io.n_launches; ctx->launches++;
+        ++epochs_run;
+        continue;
+      }
       double sum_loss = 0.0;
       int hf[4] = {0, 0, 0, 0};
       OPTMC_CUDA(cudaMemcpyAsync(&sum_loss, io.loss, 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -921,6 +952,16 @@ static int gnet_train(optmc_ctx* ctx, const optmc_gnet_params* gp, GnetTrainIo& 
       } else if (gp->stop_patience > 0 && ++since_best >= gp->stop_patience) {
         break;
       }
+    }
+    if (!host_epochs && gp->epochs > 0) {
+      double hs[4];
+      int hf[4] = {0, 0, 0, 0};
+      OPTMC_CUDA(cudaMemcpyAsync(hs, d_state + (gp->epochs & 1) * 4, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+      if (io.sharded) OPTMC_CUDA(cudaMemcpyAsync(hf, ctx->d_flags, sizeof(hf), cudaMemcpyDeviceToHost, ctx->stream));
+      OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (hf[1]) { set_error("sharded network LSM: a peer rank did not answer (gradient exchange timed out); re-run optmc_comm_export / optmc_comm_init on every rank"); return OPTMC_ECUDA; }
+      if (hs[2] != 0.0) { set_error("network LSM: the training loss is not finite"); return OPTMC_ECUDA; }
+      best = hs[0]; have_best = hs[1] != 0.0;
     }
     if (have_best) {  // om3:611-613
       OPTMC_CUDA(cudaMemcpyAsync(io.params, io.best, (size_t)kGP * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -975,7 +1016,7 @@ static int lsm_gnet_t(optmc_ctx* ctx, const void* S, int64_t ld, int64_t M, int6
   const size_t o_tab = take(tab.size() * 8), o_counts = take((size_t)(ncounts > 0 ? ncounts : 1) * 8), o_meta = take(kMetaN * 8),
                o_tot = take(kMetaN * 8), o_gath = take((size_t)kCommMaxRanks * kMetaN * 8), o_norm = take(sizeof(GnetNorm)), o_params = take((size_t)kGP * 4), o_best = take((size_t)kGP * 4),
                o_m = take((size_t)kGP * 4), o_v = take((size_t)kGP * 4), o_gpart = take((size_t)max_tiles * (kGP + 1) * 4),
-               o_loss = take(8), o_pack = take(2 * kTcTileBytes);
+               o_loss = take(9 * 8), o_pack = take(2 * kTcTileBytes);
   rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
   if (rc) return rc;
   char* dev = static_cast<char*>(ctx->batch_dev);
@@ -1319,7 +1360,7 @@ static int lsm_gnet_per_date_t(optmc_ctx* ctx, const optmc_gnet_params* gp, optm
   const size_t seg = ((size_t)M * 4 + 255) / 256 * 256;
   const size_t o_tab = take(st.size() * 8), o_counts = take((size_t)nchunks * 8), o_meta = take(kMetaN * 8), o_norm = take(sizeof(GnetNorm)),
                o_params = take((size_t)kGP * 4), o_best = take((size_t)kGP * 4), o_m = take((size_t)kGP * 4), o_v = take((size_t)kGP * 4),
-               o_gpart = take((size_t)max_tiles * (kGP + 1) * 4), o_loss = take(8), o_pack = take(2 * kTcTileBytes),
+               o_gpart = take((size_t)max_tiles * (kGP + 1) * 4), o_loss = take(9 * 8), o_pack = take(2 * kTcTileBytes),
                o_rows = take(4 * seg);
   int rc = ensure_bytes(&ctx->batch_dev, &ctx->batch_dev_cap, off);
   if (rc) return rc;

@@ -381,3 +381,16 @@ def test_gnet_per_date_vs_torch_restatement(eng, mods):
     assert again["price"] == got[0]["price"]
     r = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "reference", per_date=1, seed=1, variant="gpu", epochs=10, batch=4096)
     assert r["price"] > poly.price * 0.95 and r["ex_count"][1:N].sum() > 0
+
+
+def test_gnet_device_side_epoch_end_equals_host_loop(eng, mods):
+    """Without a scheduler and without early stopping the best-weights snapshot (om3:599-603) is taken on the device and
+    the host never waits for an epoch; a patience that cannot trigger forces the host loop -- same weights, loss, price."""
+    L, E, orc = mods
+    S = eng.paths(E.gbm(100.0, 0.05, 1.0, 0.2), 30_000, 12, "f32", E.RngSpec(seed=2))
+    kw = dict(variant="gpu", epochs=7, batch=4096, seed=3, return_params=True)
+    dev = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "reference", stop_patience=0, **kw)
+    host = eng.lsm_gnet(S, 100.0, 0.05, 1.0, "put", "reference", stop_patience=1_000_000, **kw)
+    assert dev["epochs_run"] == host["epochs_run"] == 7 and dev["n_launches"] != host["n_launches"]
+    assert dev["best_loss"] == host["best_loss"] and dev["price"] == host["price"]
+    np.testing.assert_array_equal(dev["params"], host["params"])
