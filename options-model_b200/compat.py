@@ -366,15 +366,19 @@ class AdvancedOptionPricer:
             self.last_result = res
             return float(res.price)
         model = self._model(S0, T)
-        if self.lsm_regressor == "nn":  # the reference's own regressor: one SingleLSMNet for all dates (om3:482-651)
+        if self.lsm_regressor in ("nn", "nn_per_date"):
+            # "nn": the reference's own regressor, one SingleLSMNet for all dates (om3:482-651); "nn_per_date": a fresh
+            # SingleLSMNet per exercise date (the om2:277-310 loop with om3's network; BASELINE config 3)
             if self.nn_hidden != 128 or self.nn_layers != 3:
                 raise ValueError("lsm_regressor='nn' is built for SingleLSMNet(7, 128, 3) (nn_hidden=128, nn_layers=3)")
             eng = _engine(self.device)
             S = eng.paths(model, M, int(num_time_steps), self.dtype, E.RngSpec(seed=seed))
-            warm = self.gpu_reference_quirks and self._nn_variant == "gpu"  # om3gpu:741-748: one cached network per pricer
+            per_date = self.lsm_regressor == "nn_per_date"
+            warm = self.gpu_reference_quirks and self._nn_variant == "gpu" and not per_date  # om3gpu:741-748: one cached network per pricer
             out = eng.lsm_gnet(S, self.K, self.r, T, self.option_type, self.semantics, variant=self._nn_variant,
                                epochs=self.nn_epochs, lr=self.nn_lr, dropout=self.nn_dropout, seed=int(torch_seed or 0),
-                               arrays=self.verbose, init_params=self._lsm_net if warm else None, return_params=warm)
+                               arrays=self.verbose, init_params=self._lsm_net if warm else None, return_params=warm,
+                               per_date=1 if per_date else 0)
             if warm:
                 self._lsm_net = out["params"]
             self.last_result = out
@@ -450,7 +454,7 @@ class AdvancedOptionPricer:
         """om3:653-677: american + 1.0 * (BS_analytic - european_MC), European leg on independent paths."""
         if self.control_variate_same_paths and self.use_control_variate and self.sigma is not None \
                 and self.iv_model is None and not (self.use_heston and self.heston_params is not None) \
-                and self.lsm_regressor != "nn":
+                and not self.lsm_regressor.startswith("nn"):
             # SURVEY 8f n1: the European payoff of the SAME paths as the control -- one slab, one sweep, one reduction of
             # its terminal row (the reference simulates the European leg independently, which adds its variance)
             if S0 <= 0 or self.K <= 0 or T <= 0:
@@ -537,7 +541,7 @@ class AdvancedOptionPricer:
         price_european_streaming call per grid point does.  The generators advance exactly as in the per-point loop."""
         cv = self.use_control_variate and self.sigma is not None
         eu = self.use_streaming and self.european_approximation
-        grid_ok = (self.batched and not eu and total_points > 0 and self.iv_model is None and self.lsm_regressor != "nn"
+        grid_ok = (self.batched and not eu and total_points > 0 and self.iv_model is None and not self.lsm_regressor.startswith("nn")
                    and not self.qmc)
         if grid_ok:
             days = np.array([i / intervals_per_day for i in range(total_points, 0, -1)])

@@ -419,7 +419,11 @@ __global__ void mlp_nitm_kernel(const MlpState* st, long long* nitm_t, double* l
 constexpr int kTH = 128;
 constexpr int kTP = 3 * kTH + kTH * kTH + kTH + 1;  // 16897
 constexpr int tW1 = 0, tB1 = kTH, tW2 = 2 * kTH, tB2 = 2 * kTH + kTH * kTH, tW3 = tB2 + kTH, tB3 = tW3 + kTH;
-constexpr int kTcThreads = 256;            // thread = (row = tid & 127, column half = tid >> 7)
+constexpr int kTcThreads = 512;            // thread = (row = tid & 127, column part = tid >> 7): 16 warps hide the TMEM / shared
+                                           // latencies of the epilogues (8 warps: issue slots 30 % busy, profiles/ncu_r1_summary)
+constexpr int kTcParts = kTcThreads / 128; // column parts per row (2 or 4)
+constexpr int kTcG8 = 16 / kTcParts;       // 8-column groups per part
+constexpr int kTcG32 = 4 / kTcParts;       // 32-column TMEM chunks per part
 constexpr int kTileBytes = kTcTileBytes;   // 32 KB
 constexpr int kAuxBytes = kTcPanelBytes;   // 4 KB panel [row][16]
 
@@ -427,7 +431,7 @@ struct TcSmem {
   unsigned char T1[kTileBytes], T2[kTileBytes], T3[kTileBytes], T4[kTileBytes], W2[kTileBytes];
   unsigned char aux[2][kAuxBytes];
   float w1[kTH], b1[kTH], b2[kTH], w3[kTH];
-  float dot[2][128];              // partial output-layer dot products of the two column halves
+  float dot[kTcParts][128];       // partial output-layer dot products of the column parts
   unsigned int mask[2][4][128];   // per layer: 128 "unit is active" bits of each row (word-major: conflict-free)
   float b3;
   float red[8];
@@ -451,9 +455,9 @@ __device__ __forceinline__ unsigned int tc_setup(TcSmem& sm, const float* __rest
     bulk_load_1d(sm.W2, wpack, kTileBytes, reinterpret_cast<uint64_t*>(&sm.wbar));
   }
   if (tid < 128) { sm.w1[row] = params[tW1 + row]; sm.b1[row] = params[tB1 + row]; }
-  else { sm.b2[row] = params[tB2 + row]; sm.w3[row] = params[tW3 + row]; }
+  else if (tid < 256) { sm.b2[row] = params[tB2 + row]; sm.w3[row] = params[tW3 + row]; }
   if (tid == 0) sm.b3 = params[tB3];
-  {  // panels: [1, x, dout, 0 ...]; the constant and zero columns are written once (thread halves take one panel each)
+  if (tid < 256) {  // panels: [1, x, dout, 0 ...]; the constant and zero columns are written once (one panel per 128 threads)
     unsigned char* ax = sm.aux[tid >> 7];
     *reinterpret_cast<uint4*>(ax + aux_off(row, 0)) = make_uint4(0x00003f80u, 0u, 0u, 0u);  // bf16 1.0 in column 0
     *reinterpret_cast<uint4*>(ax + aux_off(row, 8)) = make_uint4(0u, 0u, 0u, 0u);
@@ -475,7 +479,7 @@ __device__ __forceinline__ unsigned int tc_setup(TcSmem& sm, const float* __rest
 __device__ __forceinline__ void tc_layer1(TcSmem& sm, float x, int row, int half) {
   unsigned int word = 0u;
 #pragma unroll 1
-  for (int c = half * 8; c < half * 8 + 8; ++c) {
+  for (int c = half * kTcG8; c < half * kTcG8 + kTcG8; ++c) {
     float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -493,7 +497,7 @@ template <bool STORE>
 __device__ __forceinline__ float tc_layer2(TcSmem& sm, unsigned int taddr, int row, int half) {
   float out = 0.f;
 #pragma unroll 1
-  for (int c0 = half * 2; c0 < half * 2 + 2; ++c0) {
+  for (int c0 = half * kTcG32; c0 < half * kTcG32 + kTcG32; ++c0) {
     float z[32];
     tmem_ld32(taddr + c0 * 32, z);
     unsigned int word = 0u;
@@ -518,6 +522,7 @@ __device__ __forceinline__ float tc_layer2(TcSmem& sm, unsigned int taddr, int r
 __device__ __forceinline__ float tc_join_dot(TcSmem& sm, float part, int row, int half) {
   sm.dot[half][row] = part;
   __syncthreads();
+  if (kTcParts == 4) return ((sm.dot[0][row] + sm.dot[1][row]) + (sm.dot[2 % kTcParts][row] + sm.dot[3 % kTcParts][row])) + sm.b3;
   return (sm.dot[0][row] + sm.dot[1][row]) + sm.b3;
 }
 
@@ -573,7 +578,7 @@ mlp_tc_grad_kernel(const float* __restrict__ params, const __nv_bfloat16* __rest
     if (half == 0) { loss = fmaf(err, err, loss); gb3 += dout; }
     // S2b: dZ2 tile (this thread's 64 columns) and the dout column of the panel
 #pragma unroll 1
-    for (int c = half * 8; c < half * 8 + 8; ++c) {
+    for (int c = half * kTcG8; c < half * kTcG8 + kTcG8; ++c) {
       const unsigned int word = sm.mask[1][c >> 2][row] >> ((c & 3) * 8);
       float v[8];
 #pragma unroll
@@ -604,7 +609,7 @@ mlp_tc_grad_kernel(const float* __restrict__ params, const __nv_bfloat16* __rest
     tc_bar_wait(&sm.bar, phase); phase ^= 1u;
     // S3: dH1' = dH1 (h1 > 0) tile
 #pragma unroll 1
-    for (int c0 = half * 2; c0 < half * 2 + 2; ++c0) {
+    for (int c0 = half * kTcG32; c0 < half * kTcG32 + kTcG32; ++c0) {
       float d[32];
       tmem_ld32(tmem + lane_base + cZ + c0 * 32, d);
       const unsigned int word = sm.mask[0][c0][row];
@@ -633,7 +638,7 @@ mlp_tc_grad_kernel(const float* __restrict__ params, const __nv_bfloat16* __rest
   // warp write consecutive addresses of row j of W2's gradient.  The vector gradients have lane = unit.
   float* gp = gpart + (size_t)blockIdx.x * (kTP + 1);
 #pragma unroll 1
-  for (int c0 = half * 2; c0 < half * 2 + 2; ++c0) {
+  for (int c0 = half * kTcG32; c0 < half * kTcG32 + kTcG32; ++c0) {
     float w[32];
     tmem_ld32(tmem + lane_base + cW + c0 * 32, w);
 #pragma unroll
@@ -643,7 +648,7 @@ mlp_tc_grad_kernel(const float* __restrict__ params, const __nv_bfloat16* __rest
     float v1[16];
     tmem_ld16(tmem + lane_base + cV1, v1);
     gp[tB1 + row] = v1[0]; gp[tW1 + row] = v1[1];
-  } else {
+  } else if (half == 1) {
     float v2[16], v3[16];
     tmem_ld16(tmem + lane_base + cV2, v2);
     tmem_ld16(tmem + lane_base + cV3, v3);
