@@ -609,16 +609,6 @@ __device__ __forceinline__ bool gpeer_poll(const unsigned long long* mine, size_
   return !dead;
 }
 
-// fixed-order sum of this rank's per-tile partial gradients (+ the tiles' squared errors), pushed to every rank
-__global__ void __launch_bounds__(256) gnet_reduce_push_kernel(const float* __restrict__ gpart, int ntiles, GnetPeers pe, unsigned int tag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > kGP) return;
-  float g = 0.f;
-  for (int b = 0; b < ntiles; ++b) g += gpart[(size_t)b * (kGP + 1) + i];
-  const unsigned long long w = ((unsigned long long)tag << 32) | __float_as_uint(g);
-  for (int p = 0; p < pe.nranks; ++p) st_relaxed_sys_u64(gpeer_grad(pe.base[p], tag & 1u, pe.rank) + i, w);
-}
-
 // all-gather + integer sum of n64 <= 64 64-bit words (row counts, fixed-point moments, the final value sums):
 // gath[r][j] = rank r's word j, tot[j] = their wrap-around sum.  One CTA.
 __global__ void __launch_bounds__(128) gnet_gather_kernel(const unsigned long long* __restrict__ src, int n64, GnetPeers pe, unsigned int tag,
@@ -647,8 +637,8 @@ __global__ void __launch_bounds__(128) gnet_gather_kernel(const unsigned long lo
 }
 
 // Adam (torch.optim.Adam with L2 weight decay, om3:579) or AdamW (decoupled, om3gpu:753): fixed-order sum of the
-// per-tile partial gradients (PEER: of the ranks' pushed vectors, in rank order -- identical on every rank); block 0 also
-// adds the batch's mean squared error to the epoch accumulator.
+// per-tile partial gradients (PEER: this rank's sum is pushed to every rank, then the ranks' vectors are added in rank
+// order -- identical on every rank); element kGP carries the step's squared error into the epoch accumulator.
 template <bool PEER>
 __global__ void __launch_bounds__(256) gnet_adam_kernel(float* params, __nv_bfloat16* wpack, float* adam_m, float* adam_v, const float* __restrict__ gpart,
                                                         int ntiles, float lr, float wd, int decoupled, int step, float inv_batch,
@@ -659,6 +649,11 @@ __global__ void __launch_bounds__(256) gnet_adam_kernel(float* params, __nv_bflo
   if (i <= kGP) {
     float g = 0.f;
     if (PEER) {
+      // this rank's vector: fixed-order sum of its tiles, pushed into slot [tag & 1][rank] of EVERY rank (its own
+      // included) before anything is polled -- the peers' optimiser kernels do the same concurrently
+      for (int b = 0; b < ntiles; ++b) g += gpart[(size_t)b * (kGP + 1) + i];
+      const unsigned long long w = ((unsigned long long)tag << 32) | __float_as_uint(g);
+      for (int p = 0; p < pe.nranks; ++p) st_relaxed_sys_u64(gpeer_grad(pe.base[p], tag & 1u, pe.rank) + i, w);
       unsigned int pay[kCommMaxRanks];
       gpeer_poll(gpeer_grad(pe.base[pe.rank], tag & 1u, 0) + i, kGnetPad, pe.nranks, tag, pay, flags);
       g = __uint_as_float(pay[0]);
@@ -912,10 +907,9 @@ static int gnet_train(optmc_ctx* ctx, const optmc_gnet_params* gp, GnetTrainIo& 
         if (tiles > 0) { gnet_grad_kernel<<<tiles, kGThreads, gnet_smem_bytes(), ctx->stream>>>(ga); ++io.n_launches; ctx->launches++; }
         if (io.sharded) {
           const unsigned int tag = ctx->comm.gn_step++;
-          gnet_reduce_push_kernel<<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(io.gpart, tiles, io.pe, tag);
-          gnet_adam_kernel<true><<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(io.params, io.pack, io.m, io.v, io.gpart, 0, (float)lr, (float)gp->weight_decay,
+          gnet_adam_kernel<true><<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(io.params, io.pack, io.m, io.v, io.gpart, tiles, (float)lr, (float)gp->weight_decay,
                                                                              gp->decoupled_wd, step, 1.0f / (float)step_rows, io.loss, io.pe, tag, ctx->d_flags);
-          io.n_launches += 2; ctx->launches += 2;
+          ++io.n_launches; ctx->launches++;
         } else {
           gnet_adam_kernel<false><<<(kGP + 256) / 256, 256, 0, ctx->stream>>>(io.params, io.pack, io.m, io.v, io.gpart, tiles, (float)lr, (float)gp->weight_decay,
                                                                               gp->decoupled_wd, step, 1.0f / (float)step_rows, io.loss, io.pe, 0u, ctx->d_flags);

@@ -136,7 +136,7 @@ def test_compat_pricer_nn_regressor(mods):
     q = compat.AdvancedOptionPricer(K=100.0, r=0.05, sigma=0.2, option_type="put", rng_manager=compat.RNGManager(42),
                                     lsm_regressor="nn_per_date", nn_epochs=3)
     w = q.price_american_enhanced_lsm_gpu(100.0, 1.0, num_simulations=50_000, num_time_steps=10)
-    assert 5.5 < w < 8.5 and q.last_result["n_rows"] > 100_000 and q.last_result["epochs_run"] >= 9
+    assert 5.5 < w < 8.5 and q.last_result["n_rows"] > 20_000 and q.last_result["epochs_run"] >= 9
 
 
 def test_compat_out_of_sample_flag(mods):
