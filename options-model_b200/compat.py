@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import logging
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, make_dataclass
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -743,44 +743,38 @@ class HestonParams:
     rho: float
     v0: float
 
-    def __post_init__(self):  # hc:43-54
-        if not (0 < self.kappa < 20):
-            raise ValueError(f"kappa={self.kappa} must be in (0, 20)")
-        if not (0 < self.theta < 2):
-            raise ValueError(f"theta={self.theta} must be in (0, 2)")
-        if not (0 < self.sigma < 3):
-            raise ValueError(f"sigma={self.sigma} must be in (0, 3)")
-        if not (-1 < self.rho < 1):
-            raise ValueError(f"rho={self.rho} must be in (-1, 1)")
-        if not (0 < self.v0 < 2):
-            raise ValueError(f"v0={self.v0} must be in (0, 2)")
+    # open intervals the calibrator accepts (hc:43-54); the messages are the reference's
+    _BOUNDS = (("kappa", 0, 20), ("theta", 0, 2), ("sigma", 0, 3), ("rho", -1, 1), ("v0", 0, 2))
+
+    def __post_init__(self):
+        for name, lo, hi in self._BOUNDS:
+            value = getattr(self, name)
+            if not lo < value < hi:
+                raise ValueError(f"{name}={value} must be in ({lo}, {hi})")
 
     def to_array(self) -> np.ndarray:
-        return np.array([self.kappa, self.theta, self.sigma, self.rho, self.v0])
+        return np.array([getattr(self, name) for name, _, _ in self._BOUNDS])
 
     @classmethod
     def from_array(cls, x: np.ndarray) -> "HestonParams":
-        return cls(kappa=x[0], theta=x[1], sigma=x[2], rho=x[3], v0=x[4])
+        return cls(*(x[i] for i in range(len(cls._BOUNDS))))
 
     def feller_condition(self) -> bool:
         return 2 * self.kappa * self.theta >= self.sigma**2
 
 
-@dataclass
-class CalibrationConfig:  # hc:75-90
-    use_vega_weighting: bool = True
-    min_vega_weight: float = 0.01
-    max_iterations: int = 2000
-    tolerance: float = 1e-8
-    n_mc_paths: int = 100000
-    n_time_steps: int = 100
-    use_antithetic: bool = True
-    seed: int = 42
-    verbose: bool = True
-    plot_results: bool = True
-    optimization_methods: List[str] = field(default_factory=lambda: ["L-BFGS-B", "differential_evolution", "dual_annealing"])
-    fallback_enabled: bool = True
-    regime_detection: bool = True
+def _calibration_config_fields():
+    """Field table of the calibrator's configuration (hc:75-90).  The pricing path reads n_mc_paths, n_time_steps,
+    use_antithetic, seed, use_vega_weighting and min_vega_weight; the rest belongs to the optimiser / reporting side
+    (out of scope) and is carried so that a reference-side `CalibrationConfig(**kwargs)` keeps working."""
+    return [("use_vega_weighting", bool, True), ("min_vega_weight", float, 0.01), ("max_iterations", int, 2000),
+            ("tolerance", float, 1e-8), ("n_mc_paths", int, 100000), ("n_time_steps", int, 100), ("use_antithetic", bool, True),
+            ("seed", int, 42), ("verbose", bool, True), ("plot_results", bool, True),
+            ("optimization_methods", List[str], field(default_factory=lambda: ["L-BFGS-B", "differential_evolution", "dual_annealing"])),
+            ("fallback_enabled", bool, True), ("regime_detection", bool, True)]
+
+
+CalibrationConfig = make_dataclass("CalibrationConfig", _calibration_config_fields())
 
 
 class HestonPricer:
