@@ -384,26 +384,47 @@ int price_american_batch(optmc_ctx* ctx, const optmc_model_params* mp, const opt
       int choice = p.spec ? 1 : 0;
       if (plan_shape(ctx, M, dtype, sticky, ctx->sm_count / G, &alt, &why, p.spec ? 0 : 1) && alt.ncta * G <= ctx->sm_count &&
           alt.spec != p.spec) {
+        // Each candidate sweeps the wave's slabs three times; the first run is a warm-up (module load, instruction
+        // cache, attribute calls of a kernel this context has not launched) and the faster of the other two counts.
+        // Both kernels produce the same bits, so whichever ran last leaves the wave's results in place.
+        auto time_plan = [&](const ResPlan& pl, float* best) -> int {
+          for (int g = 0; g < g_now; ++g) hg[g].chunk = pl.chunk;
+          OPTMC_CUDA(cudaMemcpyAsync(d_groups, hg.data(), sizeof(ResGroup) * g_now, cudaMemcpyHostToDevice, ctx->stream));
+          ResPlan pa = pl;
+          pa.ngroups = g_now;
+          ResArgs b{};
+          b.groups = d_groups; b.cpg = pl.ncta; b.nstage = pl.nstage; b.stage_stride = pl.stage_stride; b.sticky = 1;
+          b.want_eu = a.want_eu;
+          *best = 1e30f;
+          for (int rep = 0; rep < 3; ++rep) {
+            batch_reset_kernel<<<8, 256, 0, ctx->stream>>>(d_words, (int)n_words, d_final, G * 8, d_betas, d_bnd, d_exc, d_nitm,
+                                                           details ? g_now * n1 : 0, d_groups, n1);
+            ctx->launches++;
+            OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+            const int rcl = launch_resident(ctx, pa, b, dtype, deg);
+            if (rcl) return rcl;
+            OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+            OPTMC_CUDA(cudaEventSynchronize(ctx->ev[2]));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+            if (rep > 0 && ms < *best) *best = ms;
+          }
+          return OPTMC_OK;
+        };
         float ms_a = 0.f, ms_b = 0.f;
         OPTMC_CUDA(cudaEventSynchronize(ctx->ev[2]));
-        cudaEventElapsedTime(&ms_a, ctx->ev[1], ctx->ev[2]);
-        for (int g = 0; g < g_now; ++g) hg[g].chunk = alt.chunk;
-        OPTMC_CUDA(cudaMemcpyAsync(d_groups, hg.data(), sizeof(ResGroup) * g_now, cudaMemcpyHostToDevice, ctx->stream));
-        batch_reset_kernel<<<8, 256, 0, ctx->stream>>>(d_words, (int)n_words, d_final, G * 8, d_betas, d_bnd, d_exc, d_nitm,
-                                                       details ? g_now * n1 : 0, d_groups, n1);
-        ctx->launches++;
-        OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
-        ResPlan pa = alt;
-        pa.ngroups = g_now;
-        ResArgs b{};
-        b.groups = d_groups; b.cpg = alt.ncta; b.nstage = alt.nstage; b.stage_stride = alt.stage_stride; b.sticky = 1;
-        b.want_eu = a.want_eu;
-        rc = launch_resident(ctx, pa, b, dtype, deg);
+        ResPlan cur = p;
+        cur.ncta = cpg;
+        rc = time_plan(alt, &ms_b);
         if (rc) return rc;
-        OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-        OPTMC_CUDA(cudaEventSynchronize(ctx->ev[2]));
-        cudaEventElapsedTime(&ms_b, ctx->ev[1], ctx->ev[2]);
-        if (ms_b < ms_a) { p = alt; cpg = alt.ncta; p.ngroups = G; choice = alt.spec ? 1 : 0; }
+        rc = time_plan(cur, &ms_a);
+        if (rc) return rc;
+        if (ms_b < ms_a) {
+          p = alt; cpg = alt.ncta; p.ngroups = G; choice = alt.spec ? 1 : 0;
+          float again = 0.f;
+          rc = time_plan(alt, &again);  // leave the buffers (and the recorded events) in the state of the kept kernel
+          if (rc) return rc;
+        }
         if (ex) { ex->shape[0] = p.nt; ex->shape[1] = p.ppt; ex->shape[2] = cpg; ex->shape[3] = G; }
       }
       ctx->sweep_choice.push_back({tune_key, choice});

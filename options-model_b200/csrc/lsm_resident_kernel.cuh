@@ -138,49 +138,60 @@ __device__ __forceinline__ double warp0_grid_sum(double mine, unsigned long long
     atomicExch(flags, 1);
     hi += kFxPoisonUnits;
   }
-  if (lane < 2 * QN) {
-    unsigned long long* w = xw + ((size_t)par * kXchgWords + lane) * kXchgStride;
-    red_relaxed_add_u64(w, (1ull << kFxCountShift) | ((lane & 1) ? lo : hi));
-    if (single || cta == 0) {
-      unsigned long long d;
-      do {
-        d = ld_relaxed_u64(w) - prev;
-        ++spins;
-      } while ((d >> kFxCountShift) != (unsigned long long)ncta);
+  // Every lane runs the polling loops and leaves them on a warp-wide vote: with per-lane exits (lanes see their words
+  // complete in different iterations) the warp stayed split into convergence groups after the loop, and every later
+  // __shfl_sync / vote of the solve took the compiler's divergent-warp path (WARPSYNC.COLLECTIVE per instruction):
+  // ~4 000 extra cycles per date whenever the poll needed more than one or two rounds ("box variance").
+  const bool act = lane < 2 * QN;
+  const int wl = act ? lane : 0;  // idle lanes re-read word 0 and ignore it
+  unsigned long long* w = xw + ((size_t)par * kXchgWords + wl) * kXchgStride;
+  if (act) red_relaxed_add_u64(w, (1ull << kFxCountShift) | ((lane & 1) ? lo : hi));
+  if (single || cta == 0) {  // warp-uniform
+    unsigned long long d;
+    bool done;
+    do {
+      d = ld_relaxed_u64(w) - prev;
+      ++spins;
+      done = !act || (d >> kFxCountShift) == (unsigned long long)ncta;
+    } while (!__all_sync(0xffffffffu, done));
+    // a word that is complete cannot change before this CTA has contributed to the next exchange of the same parity
+    if (act) {
       prev += d;
       sum = d & kFxValueMask;
     }
-    if (!single) {
-      const unsigned int g = cm.g0 + seq;
-      const unsigned long long tag = (unsigned long long)(g & 0xffu) << kFxCountShift;
-      const size_t row = (size_t)(g & 1u) * kCommMaxRanks;
-      if (cta == 0) {
-        // re-centre the biased high chunk so that the reader needs no CTA counts: |sum_hi - ncta 2^47| < 2^55
-        const unsigned long long pay =
-            (lane & 1) ? sum : (sum - ((unsigned long long)ncta << 47) + (1ull << 55)) & kFxValueMask;
-        for (int p = 0; p < cm.nranks; ++p)
-          st_relaxed_sys_u64(cm.slots[p] + slot_off + (row + cm.rank) * kXchgWords + lane, tag | pay);
-      }
-      // all ranks' words are polled together (independent loads in flight: one L2 round trip per sweep of the slots)
-      const unsigned long long* mine_slots = cm.slots[cm.rank] + slot_off + row * kXchgWords + lane;
-      unsigned long long v[kCommMaxRanks];
-      unsigned int n = 0;
-      for (;;) {
+  }
+  if (!single) {
+    const unsigned int g = cm.g0 + seq;
+    const unsigned long long tag = (unsigned long long)(g & 0xffu) << kFxCountShift;
+    const size_t row = (size_t)(g & 1u) * kCommMaxRanks;
+    if (cta == 0 && act) {
+      // re-centre the biased high chunk so that the reader needs no CTA counts: |sum_hi - ncta 2^47| < 2^55
+      const unsigned long long pay =
+          (lane & 1) ? sum : (sum - ((unsigned long long)ncta << 47) + (1ull << 55)) & kFxValueMask;
+      for (int p = 0; p < cm.nranks; ++p)
+        st_relaxed_sys_u64(cm.slots[p] + slot_off + (row + cm.rank) * kXchgWords + lane, tag | pay);
+    }
+    // all ranks' words are polled together (independent loads in flight: one L2 round trip per sweep of the slots)
+    const unsigned long long* mine_slots = cm.slots[cm.rank] + slot_off + row * kXchgWords + wl;
+    unsigned long long v[kCommMaxRanks];
+    unsigned int n = 0;
+    for (;;) {
 #pragma unroll
-        for (int r = 0; r < kCommMaxRanks; ++r)
-          v[r] = r < cm.nranks ? ld_relaxed_sys_u64(mine_slots + (size_t)r * kXchgWords) : tag;
-        bool all = true;
+      for (int r = 0; r < kCommMaxRanks; ++r)
+        v[r] = r < cm.nranks ? ld_relaxed_sys_u64(mine_slots + (size_t)r * kXchgWords) : tag;
+      bool all = true;
 #pragma unroll
-        for (int r = 0; r < kCommMaxRanks; ++r) all &= (v[r] & ~kFxValueMask) == tag;
-        if (all || dead) break;
-        if (++n >= kCommSpinLimit) dead = true;
-      }
+      for (int r = 0; r < kCommMaxRanks; ++r) all &= (v[r] & ~kFxValueMask) == tag;
+      if (__all_sync(0xffffffffu, all || !act) || dead) break;  // `dead` and n are warp-uniform
+      if (++n >= kCommSpinLimit) dead = true;
+    }
+    if (act) {
       sum = 0ull;
 #pragma unroll
       for (int r = 0; r < kCommMaxRanks; ++r) sum += v[r] & kFxValueMask;
-      if (dead) atomicExch(flags + 1, 1);
       if (!(lane & 1)) sum -= (unsigned long long)cm.nranks << 55;  // two's complement: signed total of the high chunks
     }
+    if (dead && lane == 0) atomicExch(flags + 1, 1);
   }
   __syncwarp();
   dead = __any_sync(0xffffffffu, dead);
