@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(NT, 1) lsm_resident_kernel(const ResArgs ga) {
   int slot_t = 0;           // ring slot of the iteration's decision date
   unsigned int phase = 0u;  // bit s: mbarrier phase parity the next wait on slot s expects
   auto wait_slot = [&](int slot) {
-    mbar_wait(&mbar[slot], (phase >> slot) & 1u);
+    mbar_wait_warp(&mbar[slot], (phase >> slot) & 1u);  // every thread of the CTA waits: whole warps
     phase ^= 1u << slot;
   };
   wait_slot(0);
@@ -1103,7 +1103,7 @@ __global__ void __launch_bounds__(NT + 32, 1) lsm_resident_spec_kernel(const Res
   auto wait_half = [&](int row, int half) {
     if ((half ? bytes_b : bytes_a) == 0) return;
     const int b = 2 * row + half;
-    mbar_wait(&mbar[row][half], (phase >> b) & 1u);
+    mbar_wait_warp(&mbar[row][half], (phase >> b) & 1u);  // whole compute warps wait
     phase ^= 1u << b;
   };
   // the last compute warp to finish a half of row `row` (date t) refills it with date t - nrow

@@ -141,6 +141,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// The same wait for a WHOLE warp (all 32 lanes call it): the loop is left on a warp-wide vote, so the warp is converged
+// afterwards.  With per-lane exits (a lane whose try_wait timed out goes round again) the warp can stay split, and the
+// compiler's divergent-warp path then runs every later vote / shuffle through WARPSYNC.COLLECTIVE.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!__all_sync(0xffffffffu, ok != 0u));
+}
 // global -> shared bulk copy, completion signalled on the mbarrier (bytes % 16 == 0, 16-byte aligned).
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
