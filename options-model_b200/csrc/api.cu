@@ -32,18 +32,24 @@ int ensure_bytes(void** p, size_t* cap, size_t need) {
   return OPTMC_OK;
 }
 
+static size_t per_date_row_bytes() { return kMaxBeta * 8 + 8 + 8 + 8 + 4; }
+
 int ensure_per_date(optmc_ctx* ctx, int N) {
   const size_t need = (size_t)N + 1;
   if (need <= ctx->per_date_cap) return OPTMC_OK;
-  cudaFree(ctx->d_betas); cudaFree(ctx->d_bnd); cudaFree(ctx->d_exc); cudaFree(ctx->d_nitm); cudaFree(ctx->d_valid);
+  // ONE block [betas | boundary | exercise counts | ITM counts | valid]: fetch_results brings the per-date outputs back
+  // with a single copy (five pageable copies + two stream synchronisations were ~10 % of a 1 ms pricing call)
+  cudaFree(ctx->d_betas);
   ctx->d_betas = nullptr; ctx->d_bnd = nullptr; ctx->d_exc = nullptr; ctx->d_nitm = nullptr; ctx->d_valid = nullptr;
   ctx->per_date_cap = 0;
   const size_t cap = need < 512 ? 512 : need;
-  OPTMC_CUDA(cudaMalloc((void**)&ctx->d_betas, cap * kMaxBeta * sizeof(double)));
-  OPTMC_CUDA(cudaMalloc((void**)&ctx->d_bnd, cap * sizeof(unsigned long long)));
-  OPTMC_CUDA(cudaMalloc((void**)&ctx->d_exc, cap * sizeof(unsigned long long)));
-  OPTMC_CUDA(cudaMalloc((void**)&ctx->d_nitm, cap * sizeof(long long)));
-  OPTMC_CUDA(cudaMalloc((void**)&ctx->d_valid, cap * sizeof(int)));
+  char* block = nullptr;
+  OPTMC_CUDA(cudaMalloc((void**)&block, cap * per_date_row_bytes()));
+  ctx->d_betas = reinterpret_cast<double*>(block);
+  ctx->d_bnd = reinterpret_cast<unsigned long long*>(block + cap * kMaxBeta * 8);
+  ctx->d_exc = ctx->d_bnd + cap;
+  ctx->d_nitm = reinterpret_cast<long long*>(ctx->d_exc + cap);
+  ctx->d_valid = reinterpret_cast<int*>(ctx->d_nitm + cap);
   ctx->per_date_cap = cap;
   return OPTMC_OK;
 }
@@ -116,16 +122,30 @@ static int fetch_results(optmc_ctx* ctx, optmc_lsm_result* out) {
   if (!sw.have_results) { set_error("no sweep results to fetch"); return OPTMC_EINVAL; }
   const int n1 = sw.N + 1;
   const int p = sw.deg + 1;
-  double fin[4];
-  std::vector<double> hb;
-  std::vector<unsigned long long> hbnd, hexc;
-  std::vector<long long> hn;
+  // one pinned staging buffer: [final (4 doubles) | flags (4 ints) | per-date block up to the requested arrays]
+  const bool want_arrays = out->betas || out->boundary || out->ex_count || out->n_itm;
+  const size_t cap = ctx->per_date_cap;
+  const size_t arr_bytes = want_arrays ? cap * (kMaxBeta * 8 + 3 * 8) : 0;  // betas, boundary, exercise counts, ITM counts
+  const size_t need = 64 + arr_bytes;
+  if (need > ctx->h_fetch_cap) {
+    cudaFreeHost(ctx->h_fetch);
+    ctx->h_fetch = nullptr; ctx->h_fetch_cap = 0;
+    OPTMC_CUDA(cudaMallocHost(&ctx->h_fetch, need));
+    ctx->h_fetch_cap = need;
+  }
+  char* hbuf = static_cast<char*>(ctx->h_fetch);
+  auto fetch = [&]() -> int {
+    OPTMC_CUDA(cudaMemcpyAsync(hbuf, ctx->d_final, 4 * sizeof(double) + 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (want_arrays) OPTMC_CUDA(cudaMemcpyAsync(hbuf + 64, ctx->d_betas, arr_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return OPTMC_OK;
+  };
+  int rcf = fetch();
+  if (rcf) return rcf;
   if (sw.impl_used == OPTMC_SWEEP_RESIDENT) {
     // The persistent sweep sums Gram moments in fixed point (|moment| < 2^43).  On overflow (or NaN/Inf
     // prices) AUTO repeats the sweep with the split kernels; an explicit RESIDENT request fails loudly.
-    int flags[4] = {0, 0, 0, 0};
-    OPTMC_CUDA(cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
-    OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int* flags = reinterpret_cast<const int*>(hbuf + 4 * sizeof(double));
     if (flags[0]) {
       if (sw.lp.impl != OPTMC_SWEEP_AUTO) {
         set_error("resident sweep: a Gram moment left the fixed-point exchange range (|m| < 2^43) or is not finite; use impl = SPLIT");
@@ -137,14 +157,16 @@ static int fetch_results(optmc_ctx* ctx, optmc_lsm_result* out) {
       sw.lp.impl = OPTMC_SWEEP_AUTO;
       if (rc) return rc;
       sw.n_launches += launches;
+      rcf = fetch();
+      if (rcf) return rcf;
     }
   }
-  OPTMC_CUDA(cudaMemcpyAsync(fin, ctx->d_final, sizeof(fin), cudaMemcpyDeviceToHost, ctx->stream));
-  if (out->betas) { hb.resize((size_t)n1 * kMaxBeta); OPTMC_CUDA(cudaMemcpyAsync(hb.data(), ctx->d_betas, hb.size() * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
-  if (out->boundary) { hbnd.resize(n1); OPTMC_CUDA(cudaMemcpyAsync(hbnd.data(), ctx->d_bnd, (size_t)n1 * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
-  if (out->ex_count) { hexc.resize(n1); OPTMC_CUDA(cudaMemcpyAsync(hexc.data(), ctx->d_exc, (size_t)n1 * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
-  if (out->n_itm) { hn.resize(n1); OPTMC_CUDA(cudaMemcpyAsync(hn.data(), ctx->d_nitm, (size_t)n1 * 8, cudaMemcpyDeviceToHost, ctx->stream)); }
-  OPTMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  double fin[4];
+  memcpy(fin, hbuf, sizeof(fin));
+  const double* hb = reinterpret_cast<const double*>(hbuf + 64);
+  const unsigned long long* hbnd = reinterpret_cast<const unsigned long long*>(hbuf + 64 + cap * kMaxBeta * 8);
+  const unsigned long long* hexc = hbnd + cap;
+  const long long* hn = reinterpret_cast<const long long*>(hexc + cap);
   out->price = fin[0];
   out->stderr_ = fin[1];
   out->n_paths = sw.M;
@@ -219,11 +241,11 @@ int optmc_ctx_create(int device, optmc_ctx** out) {
   OPTMC_CUDA(cudaMalloc((void**)&c->tickets, 1024 * sizeof(unsigned int)));
   OPTMC_CUDA(cudaMemset(c->tickets, 0, 1024 * sizeof(unsigned int)));
   OPTMC_CUDA(cudaMalloc((void**)&c->gram, 16 * sizeof(double)));
-  OPTMC_CUDA(cudaMalloc((void**)&c->d_final, 4 * sizeof(double)));
+  OPTMC_CUDA(cudaMalloc((void**)&c->d_final, 4 * sizeof(double) + 4 * sizeof(int)));  // [price, stderr, sum, sum^2 | flags]
+  c->d_flags = reinterpret_cast<int*>(c->d_final + 4);
   OPTMC_CUDA(cudaMalloc(&c->xchg, xchg_bytes()));
   OPTMC_CUDA(cudaMemset(c->xchg, 0, xchg_bytes()));
   for (int i = 0; i < 3; ++i) OPTMC_CUDA(cudaEventCreate(&c->ev[i]));
-  OPTMC_CUDA(cudaMalloc((void**)&c->d_flags, 4 * sizeof(int)));
   OPTMC_CUDA(cudaMemset(c->d_flags, 0, 4 * sizeof(int)));
   *out = c;
   return OPTMC_OK;
@@ -235,8 +257,10 @@ int optmc_ctx_destroy(optmc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->slab); cudaFree(ctx->cf); cudaFree(ctx->partials); cudaFree(ctx->tickets); cudaFree(ctx->gram);
-  cudaFree(ctx->d_betas); cudaFree(ctx->d_bnd); cudaFree(ctx->d_exc); cudaFree(ctx->d_nitm); cudaFree(ctx->d_valid);
-  cudaFree(ctx->d_final); cudaFree(ctx->xchg); cudaFree(ctx->d_flags); cudaFree(ctx->batch_dev); cudaFree(ctx->spill); cudaFree(ctx->qmc_dev); cudaFree(ctx->gnet_rows); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
+  cudaFree(ctx->d_betas);  // one block with d_bnd / d_exc / d_nitm / d_valid
+  cudaFreeHost(ctx->h_fetch);
+  cudaFree(ctx->d_final);  // one block with d_flags
+  cudaFree(ctx->xchg); cudaFree(ctx->batch_dev); cudaFree(ctx->spill); cudaFree(ctx->qmc_dev); cudaFree(ctx->gnet_rows); cudaFree(ctx->eu_out); cudaFree(ctx->eu_par); cudaFree(ctx->eu_tickets);
   for (int r = 0; r < 8; ++r) if (ctx->comm.opened[r]) cudaIpcCloseMemHandle(ctx->comm.peers[r]);
   cudaFree(ctx->comm.local);
   for (int i = 0; i < 3; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);

@@ -100,7 +100,8 @@ struct optmc_ctx {
   long long* d_nitm = nullptr;          // [(N+1)]
   int* d_valid = nullptr;               // [(N+1)]
   size_t per_date_cap = 0;              // N+1 capacity of the per-date arrays
-  double* d_final = nullptr;            // [4] price, stderr, sum, sumsq
+  double* d_final = nullptr;            // [4] price, stderr, sum, sumsq (d_flags follows in the same allocation)
+  void* h_fetch = nullptr; size_t h_fetch_cap = 0;  // pinned staging of fetch_results
   void* xchg = nullptr;                 // exchange accumulators of the persistent sweep, xchg_bytes()
   int* d_flags = nullptr;               // [4]: [0] = fixed-point exchange overflow
   void* batch_dev = nullptr; size_t batch_dev_cap = 0;  // per-wave descriptors / accumulators / results
