@@ -75,8 +75,10 @@ __device__ __forceinline__ unsigned int pack2_bf16(float lo, float hi) {
 __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
   return make_uint4(pack2_bf16(v[0], v[1]), pack2_bf16(v[2], v[3]), pack2_bf16(v[4], v[5]), pack2_bf16(v[6], v[7]));
 }
+// every thread of the CTA calls this (whole warps): the wait is left on a warp-wide vote, so the warp is converged for
+// the .sync.aligned tensor-memory loads that follow
 __device__ __forceinline__ void tc_bar_wait(unsigned long long* bar, unsigned int parity) {
-  mbar_wait(reinterpret_cast<uint64_t*>(bar), parity);
+  mbar_wait_warp(reinterpret_cast<uint64_t*>(bar), parity);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 // order this thread's shared-memory tile writes (generic proxy) and TMEM reads before the barrier that precedes the
