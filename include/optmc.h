@@ -371,7 +371,9 @@ int optmc_lsm_finish(optmc_ctx* ctx, double* sums_dev);
 
 /* ---- fused host-facing calls (what the compat layer's pricer methods call) ------------------- */
 /* price_american_enhanced_lsm (om3:439-651): paths into a context-owned slab + sweep.  Host scalars in,
- * host results out. */
+ * host results out.  When `out` carries no per-date arrays (the reference's function returns the price alone) the
+ * persistent sweep does not produce them either: a later optmc_lsm_fetch then reads NaN / none / 0 for every date.  Pass
+ * out = NULL (fetch later) or the arrays to have them. */
 int optmc_price_american(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_params* rng, int64_t M,
                          int32_t N, int32_t dtype, const optmc_lsm_params* lp, optmc_lsm_result* out);
 /* Batched American pricing: the S0 x maturity curve drivers (om3:697-713 compute_curve_for_S0, om3gpu:934-956

@@ -652,6 +652,8 @@ int optmc_price_american(optmc_ctx* ctx, const optmc_model_params* mp, const opt
   OPTMC_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   rc = bind_sweep(ctx, ctx->slab, ld, M, N, dtype, lp);
   if (rc) return rc;
+  // the caller wants the price only (the reference's price_american_enhanced_lsm returns a float): no per-date outputs
+  ctx->sw.no_arrays = out && !out->betas && !out->boundary && !out->ex_count && !out->n_itm;
   rc = run_sweep(ctx);
   if (rc) return rc;
   OPTMC_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -133,7 +133,7 @@ int sweep_resident(optmc_ctx* ctx) {
   a.groups = nullptr; a.cpg = p.ncta; a.nstage = p.nstage; a.stage_stride = p.stage_stride;
   a.sticky = (sw.lp.semantics & OPTMC_SEM_STICKY_MASK) ? 1 : 0;
   a.one.xw = reinterpret_cast<unsigned long long*>(ctx->xchg); a.one.flags = ctx->d_flags;
-  a.one.betas = ctx->d_betas; a.one.bnd = ctx->d_bnd; a.one.exc = ctx->d_exc; a.one.nitm = ctx->d_nitm;
+  if (!sw.no_arrays) { a.one.betas = ctx->d_betas; a.one.bnd = ctx->d_bnd; a.one.exc = ctx->d_exc; a.one.nitm = ctx->d_nitm; }
   a.one.final_out = ctx->d_final;
   if (ctx->sharded_M_total > 0) {  // optmc_lsm_poly_sharded: in-kernel exchange with the peer ranks
     a.comm.nranks = ctx->comm.nranks; a.comm.rank = ctx->comm.rank; a.comm.g0 = ctx->comm.g;

@@ -47,6 +47,8 @@ struct SweepDesc {  // the sweep currently bound to the context (begin/gram/upda
   bool have_results = false;
   bool finals_on_device = false;
   bool rerun_done = false;  // AUTO: the split sweep already replaced an overflowed resident sweep
+  bool no_arrays = false;   // one-shot pricing whose caller asked for the price only: the persistent sweep skips the
+                            // per-date outputs (betas, boundary, exercise / ITM counts stay NaN / none / 0)
 };
 
 // Strike constants of a sweep in the storage type (fp32 slabs: K = Kh + Kl with Kh a float; Kcmp = the float
