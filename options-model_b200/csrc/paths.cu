@@ -180,7 +180,9 @@ __device__ __forceinline__ void paths_body(const PathArgs& a) {
 // (tools/paths_bench.cu): 1.02 ms for 4 x 1 M x 252 = 3.96 TB/s written, against 1.33 ms for the scalar step above;
 // the kernel is bound by the FMA pipe (quarter-rate IMAD.WIDE of Philox + the packed FMAs) and the MUFU pipe.
 constexpr int kFastThreads = 128;
-template <int SCHEME>
+// HASV: the variance slab is written too (callers that ask for V); without it the kernel carries no second row pointer
+// and no per-step branch -- two registers less in a kernel that spills at its 64-register budget.
+template <int SCHEME, bool HASV>
 __device__ __forceinline__ void paths_body_x2(const PathArgs& a) {
   constexpr bool ABSORB = SCHEME == OPTMC_SCHEME_HESTON_REF_ABSORB;
   const long long c0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -191,7 +193,7 @@ __device__ __forceinline__ void paths_body_x2(const PathArgs& a) {
   const HestonPairX2 hx = heston_pair_x2_consts(hc, ABSORB);
   f2_t sP[2], sM[2], uP[2], uM[2];
   float* Srow = static_cast<float*>(a.S) + c0;
-  float* Vrow = a.V ? static_cast<float*>(a.V) + c0 : nullptr;
+  float* Vrow = HASV ? static_cast<float*>(a.V) + c0 : nullptr;
   {
     const float s0 = (float)a.S0, v0 = (float)a.v0;
     const float u0 = (ABSORB ? fmaxf(v0, 0.0f) : v0) * hc.dt;  // the step assumes the truncated state (om3:229)
@@ -199,7 +201,7 @@ __device__ __forceinline__ void paths_body_x2(const PathArgs& a) {
     for (int h = 0; h < 2; ++h) { sP[h] = sM[h] = f2_splat(s0); uP[h] = uM[h] = f2_splat(u0); }
     f2_store4(Srow, sP[0], sP[1]);
     f2_store4(Srow + a.Mh, sP[0], sP[1]);
-    if (Vrow) {
+    if (HASV) {
       f2_store4(Vrow, f2_splat(v0), f2_splat(v0));
       f2_store4(Vrow + a.Mh, f2_splat(v0), f2_splat(v0));
     }
@@ -216,7 +218,7 @@ __device__ __forceinline__ void paths_body_x2(const PathArgs& a) {
     }
     f2_store4(Srow, sP[0], sP[1]);
     f2_store4(Srow + a.Mh, sM[0], sM[1]);
-    if (Vrow) {
+    if (HASV) {
       Vrow += a.ld;
       f2_store4(Vrow, f2_mul(uP[0], inv_dt), f2_mul(uP[1], inv_dt));
       f2_store4(Vrow + a.Mh, f2_mul(uM[0], inv_dt), f2_mul(uM[1], inv_dt));
@@ -234,12 +236,12 @@ __device__ __forceinline__ void paths_body_x2(const PathArgs& a) {
     step(std::integral_constant<int, 2>{}, p);
   }
 }
-template <int SCHEME> __global__ void __launch_bounds__(kFastThreads, 8) paths_x2_kernel(const PathArgs a) {
-  paths_body_x2<SCHEME>(a);
+template <int SCHEME, bool HASV> __global__ void __launch_bounds__(kFastThreads, 8) paths_x2_kernel(const PathArgs a) {
+  paths_body_x2<SCHEME, HASV>(a);
 }
 template <int SCHEME> __global__ void __launch_bounds__(kFastThreads, 8) paths_x2_batch_kernel(const PathArgs* __restrict__ args) {
   const PathArgs a = args[blockIdx.y];
-  paths_body_x2<SCHEME>(a);
+  paths_body_x2<SCHEME, false>(a);  // batches never store the variance
 }
 // Threads per CTA (<= 128) for `units` threads per option and G options: the count that minimises the busiest SM's
 // lane count, ceil(CTAs / SMs) * roundup32(threads); ties go to the larger CTA.
@@ -352,8 +354,14 @@ int launch_paths(optmc_ctx* ctx, const optmc_model_params* mp, const optmc_rng_p
     const long long units = a.Mh / 4;
     const unsigned block = fast_block(ctx, units, 1);
     const unsigned grid = (unsigned)((units + block - 1) / block);
-    if (mp->scheme == OPTMC_SCHEME_HESTON_REF_ABSORB) paths_x2_kernel<OPTMC_SCHEME_HESTON_REF_ABSORB><<<grid, block, 0, ctx->stream>>>(a);
-    else paths_x2_kernel<OPTMC_SCHEME_HESTON_FULL_TRUNC><<<grid, block, 0, ctx->stream>>>(a);
+    const bool absorb = mp->scheme == OPTMC_SCHEME_HESTON_REF_ABSORB;
+    if (a.V) {
+      if (absorb) paths_x2_kernel<OPTMC_SCHEME_HESTON_REF_ABSORB, true><<<grid, block, 0, ctx->stream>>>(a);
+      else paths_x2_kernel<OPTMC_SCHEME_HESTON_FULL_TRUNC, true><<<grid, block, 0, ctx->stream>>>(a);
+    } else {
+      if (absorb) paths_x2_kernel<OPTMC_SCHEME_HESTON_REF_ABSORB, false><<<grid, block, 0, ctx->stream>>>(a);
+      else paths_x2_kernel<OPTMC_SCHEME_HESTON_FULL_TRUNC, false><<<grid, block, 0, ctx->stream>>>(a);
+    }
     ctx->launches++;
     OPTMC_CUDA(cudaGetLastError());
     return OPTMC_OK;
