@@ -435,3 +435,24 @@ def test_path_sharded_batch_single_rank_group(eng, mods):
         e.comm_finalize()
     finally:
         e.close()
+
+
+def test_price_only_call_skips_per_date_outputs(eng, mods):
+    """optmc_price_american with a result block that carries no per-date arrays (what the reference's
+    price_american_enhanced_lsm needs: it returns a float) tells the persistent sweep to skip them: same price and
+    standard error bit for bit; a later optmc_lsm_fetch then reads NaN / none / 0 for every date, whereas a call that
+    asks for the arrays (or an asynchronous call, whose caller fetches later) gets them."""
+    L, E, orc = mods
+    model = E.heston(100.0, 0.05, 1.0, **HP)
+    for sem in ("reference", "textbook"):
+        full = eng.price_american(model, 200_000, 40, 100.0, "put", "f32", E.RngSpec(seed=5), semantics=sem, arrays=True)
+        lean = eng.price_american(model, 200_000, 40, 100.0, "put", "f32", E.RngSpec(seed=5), semantics=sem, arrays=False)
+        assert lean.price == full.price and lean.stderr == full.stderr
+        after = eng.lsm_fetch(40)
+        assert np.isnan(after.betas).all() and int(after.ex_count.sum()) == 0 and np.isnan(after.boundary).all()
+        assert full.ex_count[1:40].sum() > 0 and np.isfinite(full.betas[1:39]).any()
+        eng.price_american(model, 200_000, 40, 100.0, "put", "f32", E.RngSpec(seed=5), semantics=sem, asynchronous=True)
+        late = eng.lsm_fetch(40)
+        np.testing.assert_array_equal(late.ex_count, full.ex_count)
+        np.testing.assert_array_equal(late.betas, full.betas)
+        assert late.price == full.price
